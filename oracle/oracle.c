@@ -1,0 +1,639 @@
+/*
+ * TEST INFRASTRUCTURE — CPU restatement ("oracle") of the reference's global-assembly path.
+ *
+ * This file restates, in plain C, the algorithm of labmec/NeoPZ for
+ *   TPZLinearAnalysis::Assemble -> TPZStructMatrixOR::Serial_Assemble -> TPZCompElH1::CalcStiff
+ *   -> TPZMatPoisson / TPZElasticity3D Contribute(BC) -> TPZSYsmpMatrix / TPZFYsmpMatrix AddKel + AddFel
+ * following the reference's arithmetic ORDER (so results agree to the last few ulps), each function
+ * citing the reference file:line it follows.  It is a checker only: nothing under neopz_b200/ may
+ * import, link or call it (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg).
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function below against fixtures
+ * produced by the compiled, unmodified reference (oracle/refdriver.cpp -> tests/golden/ *.npz) and
+ * against the reference's own known-answer vector UnitTest_PZ/TestMaterial/CubeStiffMatrix.txt.
+ *
+ * Scope: H1 elements of uniform order p<=2 on hexahedra / tetrahedra and their quadrilateral /
+ * triangular boundary faces (for p<=2 no side has more than one shape function, hence no
+ * orientation transforms: Shape/TPZShapeH1.cpp:71,77).  Simplex quadrature tables are data of the
+ * reference (Integral/tpzintrulet.cpp, tpzintrulet3d.cpp) and are passed in by the caller.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared oracle/oracle.c -o oracle/liboracle.so -lm
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_HEX 0
+#define ORC_TET 1
+#define ORC_QUAD 2
+#define ORC_TRI 3
+
+#define ORC_POISSON 0
+#define ORC_ELAST3D 1
+#define ORC_POISSON_BC 2
+#define ORC_ELAST3D_BC 3
+
+/* ------------------------------------------------------------------------------------------
+ * Quadrature.  Integral/tpzgaussrule.cpp:171-243 (Gauss-Legendre by Newton iteration in
+ * long double, points stored interleaved -z,+z), :172 npts = (int)(0.51*(order+2)).
+ * ------------------------------------------------------------------------------------------ */
+static long double orc_machine_precision(void) {
+    /* Integral/tpzgaussrule.cpp:552-563 */
+    long double value = 1.0L;
+    while (1.0L < (long double)(1.0L + value)) value = value / 2.0L;
+    value = 2.0L * value;
+    return value;
+}
+
+int orc_gauss1d_ld(int order, long double *loc, long double *w) {
+    int npoints = (int)(0.51 * (order + 2));
+    if (npoints < 1) npoints = 1;
+    const long double tol = orc_machine_precision();
+    const int m = (npoints + 1) / 2;
+    for (int i = 0; i < m; i++) {
+        long double p1 = ((long double)i) + 0.75L;
+        long double p2 = ((long double)npoints) + 0.5L;
+        long double z = cosl((M_PI * p1) / p2);
+        long double z1, pp, p3, dif, den;
+        long iteration = 0;
+        do {
+            iteration++;
+            p1 = 1.0L;
+            p2 = 0.0L;
+            for (int j = 0; j < npoints; j++) {
+                p3 = p2;
+                p2 = p1;
+                p1 = ((2.0L * ((long double)j) + 1.0L) * z * p2 - (((long double)j) * p3)) / (((long double)j) + 1.0L);
+            }
+            den = (z * z) - 1.0L;
+            if (fabsl(den) < 1.e-16L) z = 0.5L;
+            pp = ((long double)npoints) * (z * p1 - p2) / den;
+            z1 = z;
+            if (fabsl(pp) < 1.e-16L) z = 0.5L;
+            else z = z1 - p1 / pp;
+            dif = fabsl(z - z1);
+        } while (fabsl(dif) > tol && iteration < 100000);
+        long double weight = 2.0L / ((1.0L - z * z) * pp * pp);
+        loc[2 * i] = -z;
+        w[2 * i] = weight;
+        if ((2 * i + 1) < npoints) {
+            loc[2 * i + 1] = z;
+            w[2 * i + 1] = weight;
+        }
+    }
+    return npoints;
+}
+
+/* hexahedron: Integral/pzquad.cpp:268-284, ik fastest; weight product formed in long double */
+int orc_rule_hex(int order, double *pts, double *w) {
+    long double l[64], ww[64];
+    const int n = orc_gauss1d_ld(order, l, ww);
+    for (int ip = 0; ip < n * n * n; ip++) {
+        const int ik = ip % n, ie = (ip % (n * n)) / n, iz = ip / (n * n);
+        pts[3 * ip + 0] = (double)l[ik];
+        pts[3 * ip + 1] = (double)l[ie];
+        pts[3 * ip + 2] = (double)l[iz];
+        w[ip] = (double)(ww[ik] * ww[ie] * ww[iz]);
+    }
+    return n * n * n;
+}
+
+/* quadrilateral: Integral/pzquad.cpp:153-169, ik = ip / nEta (ksi slowest) */
+int orc_rule_quad(int order, double *pts, double *w) {
+    long double l[64], ww[64];
+    const int n = orc_gauss1d_ld(order, l, ww);
+    for (int ip = 0; ip < n * n; ip++) {
+        const int ik = ip / n, ie = ip - (ip / n) * n;
+        pts[2 * ip + 0] = (double)l[ik];
+        pts[2 * ip + 1] = (double)l[ie];
+        w[ip] = (double)(ww[ik] * ww[ie]);
+    }
+    return n * n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Topology tables (combinatorial facts of the reference elements; Topology/tpzcube.cpp:30-80,
+ * Topology/tpztetrahedron.h:283, Topology/tpzquadrilateral.cpp, Topology/tpztriangle.cpp).
+ * ------------------------------------------------------------------------------------------ */
+static const int cube_edge_nodes[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {0, 4}, {1, 5}, {2, 6}, {3, 7}, {4, 5}, {5, 6}, {6, 7}, {7, 4}};
+/* first and third corner of each face (ContainedSideLocId(face,0) and (face,2)), tpzcube.cpp:31-33 */
+static const int cube_face_n02[6][2] = {{0, 2}, {0, 5}, {1, 6}, {3, 6}, {0, 7}, {4, 6}};
+static const int cube_highsides[27][7] = {
+    {8, 11, 12, 20, 21, 24, 26}, {8, 9, 13, 20, 21, 22, 26}, {9, 10, 14, 20, 22, 23, 26}, {10, 11, 15, 20, 23, 24, 26},
+    {12, 16, 19, 21, 24, 25, 26}, {13, 16, 17, 21, 22, 25, 26}, {14, 17, 18, 22, 23, 25, 26}, {15, 18, 19, 23, 24, 25, 26},
+    {20, 21, 26}, {20, 22, 26}, {20, 23, 26}, {20, 24, 26}, {21, 24, 26}, {21, 22, 26}, {22, 23, 26}, {23, 24, 26},
+    {21, 25, 26}, {22, 25, 26}, {23, 25, 26}, {24, 25, 26}, {26}, {26}, {26}, {26}, {26}, {26}, {-1}};
+static const int cube_nhigh[27] = {7, 7, 7, 7, 7, 7, 7, 7, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 0};
+static const int tet_edge_nodes[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+
+/* ------------------------------------------------------------------------------------------
+ * H1 shape functions, p <= 2.  Shape/TPZShapeH1.cpp:42-116 with
+ *   hex : Shape/pzshapecube.cpp:36-85 (ShapeCorner), :92-152 (ShapeGenerating)
+ *   quad: Shape/pzshapequad.cpp:36-59, :67-93
+ *   tet : Shape/pzshapetetra.cpp:53-71, :101-164
+ *   tri : Shape/pzshapetriang.cpp:34-45, :53-81
+ * phi[n], dphi[dim][n] (row = direction), n returned.
+ * NConnectShapeF at p=2: edge 1, quad face 1, hex interior 1, tri face 0, tet interior 0.
+ * ------------------------------------------------------------------------------------------ */
+static void hex_corner(const double *pt, double *phi, double (*d)[27]) {
+    double x[2], dx[2], y[2], dy[2], z[2], dz[2];
+    x[0] = (1. - pt[0]) / 2.; x[1] = (1. + pt[0]) / 2.; dx[0] = -0.5; dx[1] = 0.5;
+    y[0] = (1. - pt[1]) / 2.; y[1] = (1. + pt[1]) / 2.; dy[0] = -0.5; dy[1] = 0.5;
+    z[0] = (1. - pt[2]) / 2.; z[1] = (1. + pt[2]) / 2.; dz[0] = -0.5; dz[1] = 0.5;
+    static const int s[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    for (int a = 0; a < 8; a++) {
+        phi[a] = x[s[a][0]] * y[s[a][1]] * z[s[a][2]];
+        d[0][a] = dx[s[a][0]] * y[s[a][1]] * z[s[a][2]];
+        d[1][a] = x[s[a][0]] * dy[s[a][1]] * z[s[a][2]];
+        d[2][a] = x[s[a][0]] * y[s[a][1]] * dz[s[a][2]];
+    }
+}
+
+static int shape_hex(int p, const double *pt, double *phi, double *dphi_out) {
+    double ph[27], d[3][27];
+    hex_corner(pt, ph, d);
+    if (p == 1) {
+        for (int a = 0; a < 8; a++) { phi[a] = ph[a]; for (int k = 0; k < 3; k++) dphi_out[k * 8 + a] = d[k][a]; }
+        return 8;
+    }
+    for (int is = 8; is < 27; is++) {
+        int is1, is2;
+        if (is < 20) { is1 = cube_edge_nodes[is - 8][0]; is2 = cube_edge_nodes[is - 8][1]; }
+        else if (is < 26) { is1 = cube_face_n02[is - 20][0]; is2 = cube_face_n02[is - 20][1]; }
+        else { is1 = 0; is2 = 6; }
+        ph[is] = ph[is1] * ph[is2];
+        for (int k = 0; k < 3; k++) d[k][is] = d[k][is1] * ph[is2] + ph[is1] * d[k][is2];
+    }
+    for (int is = 8; is < 27; is++) {
+        for (int h = 0; h < cube_nhigh[is]; h++) {
+            const int hs = cube_highsides[is][h];
+            ph[is] += ph[hs];
+            for (int k = 0; k < 3; k++) d[k][is] += d[k][hs];
+        }
+        const int mult = is < 20 ? 4 : (is < 26 ? 16 : 64);
+        ph[is] *= mult;
+        for (int k = 0; k < 3; k++) d[k][is] *= mult;
+    }
+    for (int a = 0; a < 27; a++) { phi[a] = ph[a]; for (int k = 0; k < 3; k++) dphi_out[k * 27 + a] = d[k][a]; }
+    return 27;
+}
+
+static int shape_quad(int p, const double *pt, double *phi, double *dphi_out) {
+    double ph[9], d[2][9];
+    double x[2], dx[2], y[2], dy[2];
+    x[0] = (1. - pt[0]) / 2.; x[1] = (1. + pt[0]) / 2.; dx[0] = -0.5; dx[1] = 0.5;
+    y[0] = (1. - pt[1]) / 2.; y[1] = (1. + pt[1]) / 2.; dy[0] = -0.5; dy[1] = 0.5;
+    static const int s[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+    for (int a = 0; a < 4; a++) {
+        ph[a] = x[s[a][0]] * y[s[a][1]];
+        d[0][a] = dx[s[a][0]] * y[s[a][1]];
+        d[1][a] = x[s[a][0]] * dy[s[a][1]];
+    }
+    int n = 4;
+    if (p >= 2) {
+        for (int is = 4; is < 8; is++) {
+            const int a = is % 4, b = (is + 1) % 4;
+            ph[is] = ph[a] * ph[b];
+            for (int k = 0; k < 2; k++) d[k][is] = d[k][a] * ph[b] + ph[a] * d[k][b];
+        }
+        ph[8] = ph[0] * ph[2];
+        for (int k = 0; k < 2; k++) d[k][8] = d[k][0] * ph[2] + ph[0] * d[k][2];
+        for (int is = 4; is < 8; is++) {
+            ph[is] += ph[8];
+            d[0][is] += d[0][8]; d[1][is] += d[1][8];
+            ph[is] *= 4.; d[0][is] *= 4.; d[1][is] *= 4.;
+        }
+        ph[8] *= 16.; d[0][8] *= 16.; d[1][8] *= 16.;
+        n = 9;
+    }
+    for (int a = 0; a < n; a++) { phi[a] = ph[a]; for (int k = 0; k < 2; k++) dphi_out[k * n + a] = d[k][a]; }
+    return n;
+}
+
+static int shape_tet(int p, const double *pt, double *phi, double *dphi_out) {
+    double ph[10], d[3][10];
+    ph[0] = 1 - pt[0] - pt[1] - pt[2]; ph[1] = pt[0]; ph[2] = pt[1]; ph[3] = pt[2];
+    static const double dc[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) d[k][a] = dc[a][k];
+    int n = 4;
+    if (p >= 2) {
+        for (int e = 0; e < 6; e++) {
+            const int a = tet_edge_nodes[e][0], b = tet_edge_nodes[e][1], is = 4 + e;
+            ph[is] = ph[a] * ph[b];
+            for (int k = 0; k < 3; k++) d[k][is] = d[k][a] * ph[b] + ph[a] * d[k][b];
+        }
+        for (int is = 4; is < 10; is++) { ph[is] *= 4.; for (int k = 0; k < 3; k++) d[k][is] *= 4.; }
+        n = 10;
+    }
+    for (int a = 0; a < n; a++) { phi[a] = ph[a]; for (int k = 0; k < 3; k++) dphi_out[k * n + a] = d[k][a]; }
+    return n;
+}
+
+static int shape_tri(int p, const double *pt, double *phi, double *dphi_out) {
+    double ph[6], d[2][6];
+    ph[0] = 1. - pt[0] - pt[1]; ph[1] = pt[0]; ph[2] = pt[1];
+    d[0][0] = -1.; d[1][0] = -1.; d[0][1] = 1.; d[1][1] = 0.; d[0][2] = 0.; d[1][2] = 1.;
+    int n = 3;
+    if (p >= 2) {
+        for (int is = 3; is < 6; is++) {
+            const int a = is % 3, b = (is + 1) % 3;
+            ph[is] = ph[a] * ph[b];
+            for (int k = 0; k < 2; k++) d[k][is] = d[k][a] * ph[b] + ph[a] * d[k][b];
+        }
+        for (int is = 3; is < 6; is++) { ph[is] *= 4.; d[0][is] *= 4.; d[1][is] *= 4.; }
+        n = 6;
+    }
+    for (int a = 0; a < n; a++) { phi[a] = ph[a]; for (int k = 0; k < 2; k++) dphi_out[k * n + a] = d[k][a]; }
+    return n;
+}
+
+int orc_shape(int topo, int p, const double *pt, double *phi, double *dphi) {
+    if (p < 1 || p > 2) return -1;
+    switch (topo) {
+        case ORC_HEX: return shape_hex(p, pt, phi, dphi);
+        case ORC_TET: return shape_tet(p, pt, phi, dphi);
+        case ORC_QUAD: return shape_quad(p, pt, phi, dphi);
+        case ORC_TRI: return shape_tri(p, pt, phi, dphi);
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Geometry: gradient of the (multi)linear map.  coords[node][3].
+ *   hex : Geom/TPZGeoCube.h:123-151 with Topology/tpzcube.cpp:367-417 (TShape)
+ *   quad: Geom/pzgeoquad.h:144-172 with Topology/tpzquadrilateral.cpp:153-173
+ *   tet : Geom/pzgeotetrahedra.h:106-151 ; tri: Geom/pzgeotriangle.h:150-179
+ * gradx[3][dim]
+ * ------------------------------------------------------------------------------------------ */
+static void gradx_of(int topo, const double *coords, const double *pt, double gradx[3][3]) {
+    double ph[8], d[3][27];
+    int nn = 0, dim = 3;
+    memset(d, 0, sizeof(d));
+    if (topo == ORC_HEX) {
+        hex_corner(pt, ph, d);
+        nn = 8;
+    } else if (topo == ORC_QUAD) {
+        const double qsi = pt[0], eta = pt[1];
+        d[0][0] = 0.25 * (eta - 1.); d[1][0] = 0.25 * (qsi - 1.);
+        d[0][1] = 0.25 * (1. - eta); d[1][1] = -0.25 * (1. + qsi);
+        d[0][2] = 0.25 * (1. + eta); d[1][2] = 0.25 * (1. + qsi);
+        d[0][3] = -0.25 * (1. + eta); d[1][3] = 0.25 * (1. - qsi);
+        nn = 4; dim = 2;
+    } else if (topo == ORC_TET) {
+        static const double dc[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) d[k][a] = dc[a][k];
+        nn = 4;
+    } else {
+        d[0][0] = -1.; d[1][0] = -1.; d[0][1] = 1.; d[1][1] = 0.; d[0][2] = 0.; d[1][2] = 1.;
+        nn = 3; dim = 2;
+    }
+    for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) gradx[j][k] = 0.;
+    for (int i = 0; i < nn; i++)
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < dim; k++) gradx[j][k] += coords[3 * i + j] * d[k][i];
+}
+
+/* Mesh/pzgeoel.cpp:1167-1356: 3-D branch :1296-1344, 2-D Gram-Schmidt branch :1228-1295.
+ * Returns detjac (signed), jacinv[dim][dim]. */
+static double jacobian_of(int dim, double gradx[3][3], double jacinv[3][3]) {
+    double detjac = 0.0;
+    if (dim == 3) {
+        double (*jac)[3] = gradx;
+        detjac -= jac[0][2] * jac[1][1] * jac[2][0];
+        detjac += jac[0][1] * jac[1][2] * jac[2][0];
+        detjac += jac[0][2] * jac[1][0] * jac[2][1];
+        detjac -= jac[0][0] * jac[1][2] * jac[2][1];
+        detjac -= jac[0][1] * jac[1][0] * jac[2][2];
+        detjac += jac[0][0] * jac[1][1] * jac[2][2];
+        if (fabs(detjac) < 1.e-12) detjac = 1.e-12; /* IsZero -> ZeroTolerance(), Common/pzreal.h */
+        jacinv[0][0] = (-jac[1][2] * jac[2][1] + jac[1][1] * jac[2][2]) / detjac;
+        jacinv[0][1] = (jac[0][2] * jac[2][1] - jac[0][1] * jac[2][2]) / detjac;
+        jacinv[0][2] = (-jac[0][2] * jac[1][1] + jac[0][1] * jac[1][2]) / detjac;
+        jacinv[1][0] = (jac[1][2] * jac[2][0] - jac[1][0] * jac[2][2]) / detjac;
+        jacinv[1][1] = (-jac[0][2] * jac[2][0] + jac[0][0] * jac[2][2]) / detjac;
+        jacinv[1][2] = (jac[0][2] * jac[1][0] - jac[0][0] * jac[1][2]) / detjac;
+        jacinv[2][0] = (-jac[1][1] * jac[2][0] + jac[1][0] * jac[2][1]) / detjac;
+        jacinv[2][1] = (jac[0][1] * jac[2][0] - jac[0][0] * jac[2][1]) / detjac;
+        jacinv[2][2] = (-jac[0][1] * jac[1][0] + jac[0][0] * jac[1][1]) / detjac;
+        return detjac;
+    }
+    /* dim == 2 */
+    double v1[3], v2[3], v1t[3], v2t[3];
+    for (int i = 0; i < 3; i++) { v1[i] = gradx[i][0]; v2[i] = gradx[i][1]; }
+    double n1 = 0.0, n2 = 0.0, dot = 0.0;
+    for (int i = 0; i < 3; i++) { n1 += v1[i] * v1[i]; dot += v1[i] * v2[i]; }
+    n1 = sqrt(n1);
+    for (int i = 0; i < 3; i++) {
+        v1t[i] = v1[i] / n1;
+        v2t[i] = v2[i] - dot * v1t[i] / n1;
+        n2 += v2t[i] * v2t[i];
+    }
+    n2 = sqrt(n2);
+    const double j00 = n1, j01 = dot / n1, j10 = 0.0, j11 = n2;
+    detjac = j00 * j11 - j10 * j01;
+    jacinv[0][0] = +j11 / detjac;
+    jacinv[1][1] = +j00 / detjac;
+    jacinv[0][1] = -j01 / detjac;
+    jacinv[1][0] = -j10 / detjac;
+    if (fabs(detjac) < 1.e-12) detjac = 1.e-12;
+    return detjac;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Element descriptor + CalcStiff.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t topo, p, kind, bctype;
+    double coords[24]; /* [node][3] */
+    /* Poisson: mat[0]=fScale, mat[1]=constant source f (what the forcing std::function returns)
+     * Elasticity3D: mat[0..2]=C1,C2,C3 ; mat[3..5]=fForce ; mat[6..8]=fPreStress
+     * BC: mat[0]=big number ; mat[1..9]=val1 (row-major ns x ns) ; mat[10..12]=val2 ; mat[13]=fScale */
+    double mat[16];
+    int32_t nq, pad;
+    const double *qpts; /* [nq][dim] */
+    const double *qw;   /* [nq] */
+} orc_elem_t;
+
+static int topo_dim(int topo) { return (topo == ORC_HEX || topo == ORC_TET) ? 3 : 2; }
+
+/* Material/Poisson/TPZMatPoisson.cpp:19-42 */
+static void contribute_poisson(int n, const double *phi, const double *dphix, double weight, const double *mat, double *ek, double *ef) {
+    const double fScale = mat[0], force = mat[1];
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) {
+            double s = 0;
+            for (int x = 0; x < 3; x++) s += dphix[x * n + i] * dphix[x * n + j];
+            ek[j * n + i] += weight * fScale * s;
+        }
+        ef[i] += weight * fScale * phi[i] * force;
+    }
+}
+
+/* Material/Elasticity/TPZElasticity3D.cpp:269-372 (CODE3 branch); ek column-major ndof x ndof */
+static void contribute_elast(int n, const double *phi, const double *dphi, double weight, const double *mat, double *ek, double *ef) {
+    const double C1 = mat[0], C2 = mat[1], C3 = mat[2];
+    const double *locForce = mat + 3, *fPreStress = mat + 6;
+    const int nd = 3 * n;
+#define EK(i, j) ek[(size_t)(j) * nd + (i)]
+    for (int jn = 0; jn < n; jn++) {
+        double dphij[3];
+        for (int kd = 0; kd < 3; kd++) {
+            dphij[kd] = dphi[kd * n + jn];
+            ef[jn * 3 + kd] += weight * (locForce[kd] * phi[jn] - fPreStress[kd] * dphi[kd * n + jn]);
+        }
+        for (int in = 0; in < n; in++) {
+            double D[3][3];
+            for (int ud = 0; ud < 3; ud++)
+                for (int vd = 0; vd < 3; vd++) D[vd][ud] = dphi[vd * n + in] * dphij[ud];
+            EK(in * 3 + 0, jn * 3 + 0) += weight * ((D[1][1] + D[2][2]) * C1 + D[0][0] * C3);
+            EK(in * 3 + 1, jn * 3 + 0) += weight * (D[0][1] * C1 - D[1][0] * C2);
+            EK(in * 3 + 2, jn * 3 + 0) += weight * (D[0][2] * C1 - D[2][0] * C2);
+            EK(in * 3 + 0, jn * 3 + 1) += weight * (D[1][0] * C1 - D[0][1] * C2);
+            EK(in * 3 + 1, jn * 3 + 1) += weight * ((D[0][0] + D[2][2]) * C1 + D[1][1] * C3);
+            EK(in * 3 + 2, jn * 3 + 1) += weight * (D[1][2] * C1 - D[2][1] * C2);
+            EK(in * 3 + 0, jn * 3 + 2) += weight * (D[2][0] * C1 - D[0][2] * C2);
+            EK(in * 3 + 1, jn * 3 + 2) += weight * (D[2][1] * C1 - D[1][2] * C2);
+            EK(in * 3 + 2, jn * 3 + 2) += weight * ((D[0][0] + D[1][1]) * C1 + D[2][2] * C3);
+        }
+    }
+#undef EK
+}
+
+/* Material/Poisson/TPZMatPoisson.cpp:45-121 (types 0,1) */
+static int contribute_poisson_bc(int n, const double *phi, double weight, int type, const double *mat, double *ek, double *ef) {
+    const double big = mat[0], v2 = mat[10], fScale = mat[13];
+    if (type == 0) {
+        for (int in = 0; in < n; in++) {
+            ef[in] += big * v2 * phi[in] * weight;
+            for (int jn = 0; jn < n; jn++) ek[jn * n + in] += big * phi[in] * phi[jn] * weight;
+        }
+        return 0;
+    }
+    if (type == 1) {
+        for (int in = 0; in < n; in++) ef[in] += v2 * fScale * phi[in] * weight;
+        return 0;
+    }
+    return -1;
+}
+
+/* Material/Elasticity/TPZElasticity3D.cpp:616-773 (types 0,1,2), BIGNUMBER=1e12 (:630) */
+static int contribute_elast_bc(int n, const double *phi, double weight, int type, const double *mat, double *ek, double *ef) {
+    const double BIG = 1.e12;
+    const double *val1 = mat + 1, *val2 = mat + 10;
+    const int nd = 3 * n;
+#define EK(i, j) ek[(size_t)(j) * nd + (i)]
+    switch (type) {
+        case 0:
+            for (int in = 0; in < n; in++) {
+                for (int k = 0; k < 3; k++) ef[3 * in + k] += BIG * val2[k] * phi[in] * weight;
+                for (int jn = 0; jn < n; jn++)
+                    for (int k = 0; k < 3; k++) EK(3 * in + k, 3 * jn + k) += BIG * phi[in] * phi[jn] * weight;
+            }
+            return 0;
+        case 1:
+            for (int in = 0; in < n; in++)
+                for (int k = 0; k < 3; k++) ef[3 * in + k] += val2[k] * phi[in] * weight;
+            return 0;
+        case 2:
+            for (int in = 0; in < n; in++) {
+                for (int k = 0; k < 3; k++) ef[3 * in + k] += val2[k] * phi[in] * weight;
+                for (int jn = 0; jn < n; jn++)
+                    for (int idf = 0; idf < 3; idf++)
+                        for (int jdf = 0; jdf < 3; jdf++)
+                            EK(3 * in + idf, 3 * jn + jdf) += val1[3 * idf + jdf] * weight * phi[in] * phi[jn];
+            }
+            return 0;
+    }
+#undef EK
+    return -1;
+}
+
+/* Mesh/pzinterpolationspace.cpp:404-473 (quadrature loop), :266-297 (ComputeRequiredData),
+ * Mesh/TPZCompElH1.cpp:140-149 (dphix = jacinv^T dphi via Matrix/pzfmatrix.cpp:608-622).
+ * ek: column-major ndof x ndof (zeroed here), ef: ndof. returns ndof or <0 */
+int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
+    const int dim = topo_dim(e->topo);
+    const int ns = (e->kind == ORC_ELAST3D || e->kind == ORC_ELAST3D_BC) ? 3 : 1;
+    double phi[27], dphi[3 * 27], dphix[3 * 27];
+    double pt0[3] = {0, 0, 0};
+    const int n = orc_shape(e->topo, e->p, pt0, phi, dphi);
+    if (n < 0) return -1;
+    const int nd = n * ns;
+    memset(ek, 0, sizeof(double) * nd * nd);
+    memset(ef, 0, sizeof(double) * nd);
+    for (int q = 0; q < e->nq; q++) {
+        const double *pt = e->qpts + (size_t)q * dim;
+        double weight = e->qw[q];
+        double gradx[3][3], jacinv[3][3];
+        gradx_of(e->topo, e->coords, pt, gradx);
+        double detjac = jacobian_of(dim, gradx, jacinv);
+        detjac = fabs(detjac);
+        orc_shape(e->topo, e->p, pt, phi, dphi);
+        for (int j = 0; j < n; j++)
+            for (int c = 0; c < dim; c++) {
+                double val = 0.;
+                for (int k = 0; k < dim; k++) val += jacinv[k][c] * dphi[k * n + j];
+                dphix[c * n + j] = 0. + 1. * val;
+            }
+        weight *= fabs(detjac);
+        int rc = 0;
+        switch (e->kind) {
+            case ORC_POISSON: contribute_poisson(n, phi, dphix, weight, e->mat, ek, ef); break;
+            case ORC_ELAST3D: contribute_elast(n, phi, dphix, weight, e->mat, ek, ef); break;
+            case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
+            case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
+            default: rc = -1;
+        }
+        if (rc) return -2;
+    }
+    return nd;
+}
+
+/* single-point Contribute of TPZElasticity3D, for the reference's known-answer test
+ * UnitTest_PZ/TestMaterial/TestMaterial.cpp:18-40 (dphix = I3, weight = 8) */
+void orc_elast_contribute_point(int n, const double *phi, const double *dphix, double weight, const double *mat, double *ek, double *ef) {
+    contribute_elast(n, phi, dphix, weight, mat, ek, ef);
+}
+
+/* TPZElasticity3D::SetC, Material/Elasticity/TPZElasticity3D.h:183-188 */
+void orc_elast_constants(double E, double nu, double *C) {
+    C[0] = E / (2. + 2. * nu);
+    C[1] = E * nu / (-1. + nu + 2. * nu * nu);
+    C[2] = E * (nu - 1.) / (-1. + nu + 2. * nu * nu);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CSR pattern.  Mesh/pzcmesh.cpp:1223-1267 (element graph = seqnums of each element's connects),
+ * External/TPZRenumbering.cpp:30-110 (node->element graph, then node->node graph as an ascending
+ * std::set with self erased), StrMatrix/TPZSSpStructMatrix.cpp:50-193 (symmetric, upper) and
+ * StrMatrix/TPZSpStructMatrix.cpp:53-190 (full, rows sorted).  No equation filter.
+ * Two-call protocol: ja == NULL -> only count; returns nnz.  ia has neq+1 entries.
+ * ------------------------------------------------------------------------------------------ */
+static int cmp_i64(const void *a, const void *b) {
+    const int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+    return (x > y) - (x < y);
+}
+
+int64_t orc_pattern(int symmetric, int64_t nel, const int64_t *elgraphindex, const int64_t *elgraph, int64_t nblock,
+                    const int64_t *blockpos, const int64_t *blocksize, int64_t *ia, int64_t *ja) {
+    /* NodeToElGraph */
+    int64_t *n2e_idx = (int64_t *)calloc(nblock + 1, sizeof(int64_t));
+    const int64_t last = elgraphindex[nel];
+    for (int64_t k = 0; k < last; k++) n2e_idx[elgraph[k] + 1]++;
+    for (int64_t b = 0; b < nblock; b++) n2e_idx[b + 1] += n2e_idx[b];
+    int64_t *n2e = (int64_t *)malloc(sizeof(int64_t) * (last > 0 ? last : 1));
+    int64_t *cursor = (int64_t *)malloc(sizeof(int64_t) * (nblock + 1));
+    memcpy(cursor, n2e_idx, sizeof(int64_t) * (nblock + 1));
+    for (int64_t el = 0; el < nel; el++)
+        for (int64_t k = elgraphindex[el]; k < elgraphindex[el + 1]; k++) n2e[cursor[elgraph[k]]++] = el;
+    /* ConvertGraph + SetupMatrixData, block row by block row */
+    int64_t cap = 4096, *buf = (int64_t *)malloc(sizeof(int64_t) * cap);
+    int64_t pos = 0, ieq = 0;
+    for (int64_t i = 0; i < nblock; i++) {
+        int64_t cnt = 0;
+        for (int64_t e = n2e_idx[i]; e < n2e_idx[i + 1]; e++) {
+            const int64_t gel = n2e[e];
+            for (int64_t k = elgraphindex[gel]; k < elgraphindex[gel + 1]; k++) {
+                if (cnt == cap) { cap *= 2; buf = (int64_t *)realloc(buf, sizeof(int64_t) * cap); }
+                buf[cnt++] = elgraph[k];
+            }
+        }
+        qsort(buf, cnt, sizeof(int64_t), cmp_i64);
+        int64_t m = 0;
+        for (int64_t k = 0; k < cnt; k++)
+            if (buf[k] != i && (m == 0 || buf[m - 1] != buf[k])) buf[m++] = buf[k];
+        const int64_t iblsize = blocksize[i], iblpos = blockpos[i];
+        if (iblsize == 0) continue; /* NumActive == 0 */
+        for (int64_t ibleq = 0; ibleq < iblsize; ibleq++) {
+            ia[ieq] = pos;
+            if (symmetric) {
+                for (int64_t j = 0; j < iblsize; j++) {
+                    const int64_t jeq = iblpos + j;
+                    if (jeq < ieq) continue;
+                    if (ja) ja[pos] = jeq;
+                    pos++;
+                }
+                for (int64_t k = 0; k < m; k++) {
+                    const int64_t col = buf[k];
+                    if (col < i) continue;
+                    for (int64_t j = 0; j < blocksize[col]; j++) {
+                        const int64_t jeq = blockpos[col] + j;
+                        if (jeq < ieq) continue;
+                        if (ja) ja[pos] = jeq;
+                        pos++;
+                    }
+                }
+            } else {
+                const int64_t first = pos;
+                for (int64_t j = 0; j < iblsize; j++) { if (ja) ja[pos] = iblpos + j; pos++; }
+                for (int64_t k = 0; k < m; k++) {
+                    const int64_t col = buf[k];
+                    for (int64_t j = 0; j < blocksize[col]; j++) { if (ja) ja[pos] = blockpos[col] + j; pos++; }
+                }
+                if (ja) qsort(ja + first, pos - first, sizeof(int64_t), cmp_i64); /* std::stable_sort of distinct keys */
+            }
+            ieq++;
+        }
+    }
+    ia[ieq] = pos;
+    free(buf); free(cursor); free(n2e); free(n2e_idx);
+    return pos;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Scatter-add.  Matrix/pzsysmp.cpp:370-411 (sym: only jpos>=ipos, skip |v|<1e-12, sequential
+ * hit k++ else linear search of the row), Matrix/pzysmp.cpp:178-218 (full),
+ * Matrix/pzfmatrix.cpp:285-299 (AddFel).  Returns the number of entries NOT found (must be 0).
+ * ------------------------------------------------------------------------------------------ */
+int64_t orc_addkel(int symmetric, const int64_t *ia, const int64_t *ja, double *a, int nd, const double *ek, const int64_t *dest) {
+    int64_t k = 0, missing = 0;
+    for (int i = 0; i < nd; i++) {
+        for (int j = 0; j < nd; j++) {
+            const int64_t ipos = dest[i], jpos = dest[j];
+            if (symmetric && jpos < ipos) continue;
+            const double value = ek[(size_t)j * nd + i];
+            if (!(fabs(value) < 1.e-12)) {
+                int flag = 0;
+                k++;
+                if (k >= ia[ipos] && k < ia[ipos + 1] && ja[k] == jpos) {
+                    a[k] += value;
+                    flag = 1;
+                } else {
+                    for (k = ia[ipos]; k < ia[ipos + 1]; k++) {
+                        if (ja[k] == jpos) { a[k] += value; flag = 1; break; }
+                    }
+                }
+                if (!flag) missing++;
+            }
+        }
+    }
+    return missing;
+}
+
+void orc_addfel(double *rhs, int nd, const double *ef, const int64_t *dest) {
+    for (int i = 0; i < nd; i++) rhs[dest[i]] += ef[i];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Whole serial assembly (StrMatrix/pzstrmatrixor.cpp:104-365): elements in index order,
+ * CalcStiff -> destination indices -> AddKel -> AddFel.
+ * elems[nel]; dest_ptr[nel+1], dest[] concatenated (Mesh/pzelmat.cpp:37-70 done by the caller,
+ * who owns the connect/block tables).  a and rhs must be zeroed by the caller.
+ * ------------------------------------------------------------------------------------------ */
+int64_t orc_assemble(int symmetric, int64_t nel, const orc_elem_t *elems, const int64_t *dest_ptr, const int64_t *dest,
+                     const int64_t *ia, const int64_t *ja, double *a, double *rhs) {
+    double *ek = (double *)malloc(sizeof(double) * 81 * 81), *ef = (double *)malloc(sizeof(double) * 81);
+    int64_t missing = 0;
+    for (int64_t el = 0; el < nel; el++) {
+        const int nd = orc_calcstiff(&elems[el], ek, ef);
+        if (nd < 0) { missing = -1; break; }
+        if (dest_ptr[el + 1] - dest_ptr[el] != nd) { missing = -2; break; }
+        missing += orc_addkel(symmetric, ia, ja, a, nd, ek, dest + dest_ptr[el]);
+        orc_addfel(rhs, nd, ef, dest + dest_ptr[el]);
+    }
+    free(ek); free(ef);
+    return missing;
+}
+
+int orc_sizeof_elem(void) { return (int)sizeof(orc_elem_t); }

@@ -1,0 +1,52 @@
+"""Regenerates tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref/refdriver, built
+by oracle/Makefile.ref from /root/reference).  Only runs where the reference exists (this container);
+the .npz files it writes are committed so the GPU box needs neither the reference nor this script.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "refdriver")
+
+# name: (n, p, phys, tet, perturb, bctype, with_elmats)
+CASES = {
+    "hex_p1_poisson_n3": (3, 1, 0, 0, 0.0, 0, 1),
+    "hex_p1_poisson_n3_pert": (3, 1, 0, 0, 0.15, 1, 1),
+    "hex_p2_poisson_n2_pert": (2, 2, 0, 0, 0.15, 1, 1),
+    "hex_p2_poisson_n3": (3, 2, 0, 0, 0.0, 0, 0),
+    "hex_p1_elast_n2_pert": (2, 1, 1, 0, 0.15, 1, 1),
+    "hex_p2_elast_n2_pert": (2, 2, 1, 0, 0.15, 1, 1),
+    "tet_p1_poisson_n2_pert": (2, 1, 0, 1, 0.15, 0, 1),
+    "tet_p2_poisson_n2_pert": (2, 2, 0, 1, 0.15, 1, 1),
+    "tet_p2_elast_n2_pert": (2, 2, 1, 1, 0.15, 1, 1),
+}
+
+
+def main():
+    if not os.path.exists(DRIVER):
+        sys.exit("oracle/_ref/refdriver missing: run `make -f oracle/Makefile.ref -j8` first")
+    for name, (n, p, phys, tet, pert, bctype, elm) in CASES.items():
+        with tempfile.TemporaryDirectory() as d:
+            subprocess.check_call([DRIVER, "dump", d, str(n), str(p), str(phys), str(tet), repr(pert),
+                                   str(bctype), str(elm)], stdout=subprocess.DEVNULL)
+            arrays = {}
+            for f in sorted(os.listdir(d)):
+                if f.endswith(".npy"):
+                    arrays[f[:-4]] = np.load(os.path.join(d, f))
+            meta = json.load(open(os.path.join(d, "meta.json")))
+            arrays["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+            out = os.path.join(HERE, name + ".npz")
+            np.savez_compressed(out, **arrays)
+            print(name, "->", os.path.getsize(out) // 1024, "KiB", meta)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Helpers shared by the tests: load the committed reference fixtures (tests/golden/*.npz, written by
+tests/golden/make_golden.py from the unmodified reference) and turn them into oracle inputs."""
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+# material data of oracle/refdriver.cpp's recipe
+E_MOD, NU = 1000.0, 0.3
+ELAST_FORCE = (0.0, 0.0, -1.0)
+NEUMANN_POISSON = 0.75
+NEUMANN_ELAST = (0.25, -0.5, 2.0)
+TAGS = {orc.HEX: "hex", orc.TET: "tet", orc.QUAD: "quad", orc.TRI: "tri"}
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["meta"] = json.loads(bytes(g.pop("meta_json")).decode())
+    return g
+
+
+def material_vector(g, topo, matid):
+    """(kind, bctype, mat[16]) in the oracle's convention for an element of this topology/material id."""
+    phys = g["meta"]["phys"]
+    big = float(g["meta"]["bignumber"])
+    mat = np.zeros(16)
+    if matid == 1:
+        if phys == 0:
+            mat[0], mat[1] = 1.0, 1.0
+            return orc.POISSON, 0, mat
+        mat[0:3] = orc.elast_constants(E_MOD, NU)
+        mat[3:6] = ELAST_FORCE
+        return orc.ELAST3D, 0, mat
+    bctype = 0 if matid == -1 else 1
+    mat[0] = big
+    mat[13] = 1.0
+    if phys == 0:
+        mat[10] = 0.0 if bctype == 0 else NEUMANN_POISSON
+        return orc.POISSON_BC, bctype, mat
+    if bctype == 1:
+        mat[10:13] = NEUMANN_ELAST
+    return orc.ELAST3D_BC, bctype, mat
+
+
+def oracle_elements(g):
+    """One ctypes Elem per computational element, in element order; returns (list_of_arrays, keepalive)."""
+    p = g["meta"]["p"]
+    ncel = len(g["el_type"])
+    arrays, keep = [], []
+    for e in range(ncel):
+        topo = int(g["el_type"][e])
+        nn = orc.TOPO_NNODE[topo]
+        nodes = g["el_nodes"][e, :nn]
+        coords = g["nodes"][nodes][None, :, :]
+        kind, bctype, mat = material_vector(g, topo, int(g["el_matid"][e]))
+        tag = TAGS[topo]
+        arr, k = orc.make_elems(topo, p, kind, bctype, coords, mat, g[f"rule_{tag}_pts"], g[f"rule_{tag}_w"])
+        arrays.append(arr)
+        keep.append(k)
+    return arrays, keep
+
+
+def elgraph(g):
+    """Element graph of Mesh/pzcmesh.cpp:1223-1267: seqnums of every element's connects."""
+    ncel = len(g["el_type"])
+    idx = [0]
+    graph = []
+    for e in range(ncel):
+        nc = int(g["el_ncon"][e])
+        graph.extend(g["el_conseq"][e, :nc].tolist())
+        idx.append(len(graph))
+    return np.array(idx, dtype=np.int64), np.array(graph, dtype=np.int64)
