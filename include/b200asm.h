@@ -1,0 +1,138 @@
+/*
+ * b200asm — C ABI of the B200-native global-assembly engine.
+ *
+ * This is the drop-in boundary underneath NeoPZ's parallel-strategy interface
+ * (StrMatrix/TPZStrMatParInterface.h:44-48, the two Assemble() virtuals that
+ * StrMatrix/pzstrmatrixor.cpp:41-101 implements on the CPU).  The C++ strategy
+ * TPZStructMatrixB200<TVar> (neopz_b200/csrc/neopz/TPZStructMatrixB200.h) flattens a TPZCompMesh
+ * once and drives these entry points; so does the Python host (neopz_b200/strmatrix.py) and the
+ * benchmark.  Plain pointers and sizes only: no NeoPZ, no torch types.
+ *
+ * All functions return 0 on success, a negative B200ASM_E* code on failure; the message is
+ * available from b200asm_last_error().  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with B200ASM_ENODEVICE.
+ */
+#ifndef B200ASM_H
+#define B200ASM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200asm_ctx b200asm_ctx;
+
+/* element topologies (reference: MElementType ECube/ETetraedro/EQuadrilateral/ETriangle) */
+enum { B200ASM_HEX = 0, B200ASM_TET = 1, B200ASM_QUAD = 2, B200ASM_TRI = 3 };
+/* weak forms:
+ *  POISSON       Material/Poisson/TPZMatPoisson.cpp:19-42
+ *  ELASTICITY3D  Material/Elasticity/TPZElasticity3D.cpp:85-107,269-372
+ *  BC            the boundary forms of both (TPZMatPoisson.cpp:45-121, TPZElasticity3D.cpp:616-773)
+ *                reduced to  ek(ns*i+a, ns*j+b) += M[a][b]*phi_i*phi_j*w ,  ef(ns*i+a) += v[a]*phi_i*w */
+enum { B200ASM_POISSON = 0, B200ASM_ELASTICITY3D = 1, B200ASM_BC = 2 };
+
+enum {
+    B200ASM_OK = 0,
+    B200ASM_EINVAL = -1,     /* bad argument / unsupported element configuration */
+    B200ASM_ENODEVICE = -2,  /* no CUDA device: the engine has no CPU path */
+    B200ASM_ECUDA = -3,      /* a CUDA runtime call failed */
+    B200ASM_ESTATE = -4,     /* call order violated (e.g. assemble before set_pattern) */
+    B200ASM_EPATTERN = -5    /* an element entry has no slot in the CSR pattern (cf. pzsysmp.cpp:409) */
+};
+
+/* flags of b200asm_set_pattern */
+#define B200ASM_SYMMETRIC 1 /* TPZSYsmpMatrix: upper triangle, Matrix/pzsysmp.h:108-127 */
+#define B200ASM_FULL 0      /* TPZFYsmpMatrix: all entries, Matrix/pzysmp.h:229-237 */
+
+/* scatter strategies (b200asm_set_option "scatter") */
+#define B200ASM_SCATTER_ATOMIC 0 /* red.global.add.f64 */
+#define B200ASM_SCATTER_COLORED 1 /* conflict-free element colouring, deterministic */
+
+/*
+ * A homogeneous batch of computational elements: same topology, same uniform order p, same
+ * material.  Mirrors what CalcStiff sees per element (Mesh/pzinterpolationspace.cpp:404-473):
+ * corner nodes, the integration rule, the shape tables and the material constants.
+ */
+typedef struct {
+    int32_t topology; /* B200ASM_HEX ... */
+    int32_t porder;   /* uniform order of every connect of the batch (1 or 2) */
+    int32_t kind;     /* B200ASM_POISSON ... */
+    int32_t nstate;   /* TPZMaterial::NStateVariables(): 1 or 3 */
+    int64_t nel;
+    const int32_t *elnodes; /* [nel][ncorner] indices into the node table (TPZGeoEl::NodeIndex) */
+    const int64_t *dest;    /* [nel][nshape*nstate] TPZElementMatrix::fDestinationIndex, Mesh/pzelmat.cpp:37-70 */
+    int32_t nqp;            /* points of the TPZIntPoints rule of order 2p (Mesh/pzelctemp.cpp:35-47) */
+    int32_t nshape;         /* H1 shape functions per element */
+    const double *qpts;     /* [nqp][dim]  TPZIntPoints::Point */
+    const double *qwts;     /* [nqp] */
+    const double *phi;      /* [nqp][nshape]       TPZShapeH1<TSHAPE>::Shape at the points (Shape/TPZShapeH1.cpp:42-116) */
+    const double *dphi;     /* [nqp][dim][nshape]  master-element gradients */
+    /* POISSON:      coef[0]=fScale, coef[1]=value of the (constant) forcing function
+     * ELASTICITY3D: coef[0..2]=C1,C2,C3 (TPZElasticity3D.h:183-188), coef[3..5]=fForce, coef[6..8]=fPreStress
+     * BC:           coef[0..8]=M (3x3 row-major, upper-left ns x ns used), coef[9..11]=v */
+    double coef[16];
+    const double *force; /* optional [nel][nqp][nstate]: forcing function evaluated by the host at the
+                            integration points (std::function callbacks stay on the host); NULL = constant */
+} b200asm_group;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int b200asm_create(b200asm_ctx **out, int device);
+void b200asm_destroy(b200asm_ctx *ctx);
+const char *b200asm_last_error(const b200asm_ctx *ctx); /* ctx may be NULL: last create() error */
+/* run on an existing CUDA stream (cudaStream_t passed as void*); default: a stream the context owns */
+int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
+/* integer options: "scatter" (B200ASM_SCATTER_*) */
+int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);
+
+/* ---- flattened mesh ---------------------------------------------------------------------- */
+/* node coordinates xyz[nnodes][3] (TPZGeoNode::Coord).  May be called again to move the nodes. */
+int b200asm_set_nodes(b200asm_ctx *ctx, int64_t nnodes, const double *xyz);
+/* copies the batch to the device; returns the group index (>=0) or an error code */
+int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *g);
+/* replaces coef[] of a group (material constants may change between assemblies) */
+int b200asm_set_group_coef(b200asm_ctx *ctx, int group, const double coef[16]);
+int b200asm_clear_groups(b200asm_ctx *ctx);
+
+/* ---- CSR pattern --------------------------------------------------------------------------
+ * ia[neq+1], ja[nnz] exactly as TPZSYsmpMatrix::IA()/JA() (or TPZFYsmpMatrix) hold them after
+ * TPZSSpStructMatrix::Create() (StrMatrix/TPZSSpStructMatrix.cpp:31-193).  Uploads the pattern and
+ * builds, on the device, the element-entry -> CSR-position scatter map of every group. */
+int b200asm_set_pattern(b200asm_ctx *ctx, int64_t neq, const int64_t *ia, const int64_t *ja, int symmetric);
+
+/* ---- assembly -----------------------------------------------------------------------------
+ * Zeroes A and rhs on the device, runs every group (CalcStiff + AddKel + AddFel of
+ * StrMatrix/pzstrmatrixor.cpp:157-250 for all elements at once) and, when the host pointers are
+ * non-NULL, copies the result back: a_host[nnz] in CSR order, rhs_host[neq].  Synchronous. */
+int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_host);
+/* asynchronous, device resident (no copies, no synchronisation): enqueue on the context stream */
+int b200asm_assemble_async(b200asm_ctx *ctx);
+int b200asm_synchronize(b200asm_ctx *ctx);
+/* copy the device-resident result to the host (synchronous) */
+int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_host);
+/* device pointers of the resident CSR values / rhs (for a GPU solver downstream) */
+int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev);
+/* number of kernels launched by this context so far, and bytes moved H2D/D2H */
+int b200asm_counters(const b200asm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* ---- host-side helpers (pure CPU, no device needed) ----------------------------------------
+ * Gauss-Legendre rule the reference uses for order `order` (Integral/tpzgaussrule.cpp:171-243):
+ * npts = (int)(0.51*(order+2)) points in the reference's interleaved -z,+z order. Returns npts. */
+int b200asm_gauss_legendre(int order, double *loc, double *w);
+/* tensor rules for hexahedra / quadrilaterals of order 2p in the reference's point order
+ * (Integral/pzquad.cpp:153-169,268-284).  Returns the number of points. */
+int b200asm_tensor_rule(int topology, int order, double *qpts, double *qw);
+/* H1 shape tables (uniform p<=2) at given master-element points.  Returns nshape. */
+int b200asm_shape_tables(int topology, int porder, int nqp, const double *qpts, double *phi, double *dphi);
+/* CSR pattern of the reference from the element->connect graph (Mesh/pzcmesh.cpp:1223-1267,
+ * External/TPZRenumbering.cpp:76-110, TPZSSpStructMatrix.cpp:50-193 / TPZSpStructMatrix.cpp:53-190).
+ * elgraphindex[nel+1], elgraph[]: sequence numbers of each element's connects; blockpos/blocksize
+ * per sequence number (TPZBlock::Position/Size).  Two calls: ja==NULL returns nnz and fills ia. */
+int64_t b200asm_build_pattern(int symmetric, int64_t nel, const int64_t *elgraphindex, const int64_t *elgraph,
+                              int64_t nblock, const int64_t *blockpos, const int64_t *blocksize, int64_t *ia,
+                              int64_t *ja, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ASM_H */

@@ -1,0 +1,230 @@
+"""ctypes binding of libb200asm.so (C ABI declared in include/b200asm.h).
+
+The library is built in-tree by __graft_entry__.build() / neopz_b200/build.py.  There is no Python
+or CPU fallback: if the shared library is missing or no CUDA device is present, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200asm.so")
+
+HEX, TET, QUAD, TRI = 0, 1, 2, 3
+POISSON, ELASTICITY3D, BC = 0, 1, 2
+ENODEVICE = -2
+
+
+class B200AsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200asm error {code}: {msg}")
+        self.code = code
+
+
+class Group(C.Structure):
+    _fields_ = [("topology", C.c_int32), ("porder", C.c_int32), ("kind", C.c_int32), ("nstate", C.c_int32),
+                ("nel", C.c_int64),
+                ("elnodes", C.POINTER(C.c_int32)), ("dest", C.POINTER(C.c_int64)),
+                ("nqp", C.c_int32), ("nshape", C.c_int32),
+                ("qpts", C.POINTER(C.c_double)), ("qwts", C.POINTER(C.c_double)),
+                ("phi", C.POINTER(C.c_double)), ("dphi", C.POINTER(C.c_double)),
+                ("coef", C.c_double * 16),
+                ("force", C.POINTER(C.c_double))]
+
+
+_lib = None
+
+# every symbol include/b200asm.h declares (tests/test_capi_symbols.py checks the header against this)
+SYMBOLS = [
+    "b200asm_create", "b200asm_destroy", "b200asm_last_error", "b200asm_set_stream", "b200asm_set_option",
+    "b200asm_set_nodes", "b200asm_add_group", "b200asm_set_group_coef", "b200asm_clear_groups",
+    "b200asm_set_pattern", "b200asm_assemble", "b200asm_assemble_async", "b200asm_synchronize",
+    "b200asm_download", "b200asm_device_pointers", "b200asm_counters",
+    "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
+]
+
+
+def lib():
+    """Load the native library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). neopz_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip64, ip32 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    L.b200asm_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.b200asm_destroy.argtypes = [vp]
+    L.b200asm_destroy.restype = None
+    L.b200asm_last_error.argtypes = [vp]
+    L.b200asm_last_error.restype = C.c_char_p
+    L.b200asm_set_stream.argtypes = [vp, vp]
+    L.b200asm_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.b200asm_set_nodes.argtypes = [vp, C.c_int64, dp]
+    L.b200asm_add_group.argtypes = [vp, C.POINTER(Group)]
+    L.b200asm_set_group_coef.argtypes = [vp, C.c_int, dp]
+    L.b200asm_clear_groups.argtypes = [vp]
+    L.b200asm_set_pattern.argtypes = [vp, C.c_int64, ip64, ip64, C.c_int]
+    L.b200asm_assemble.argtypes = [vp, dp, dp]
+    L.b200asm_assemble_async.argtypes = [vp]
+    L.b200asm_synchronize.argtypes = [vp]
+    L.b200asm_download.argtypes = [vp, dp, dp]
+    L.b200asm_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.b200asm_counters.argtypes = [vp, ip64, ip64, ip64]
+    L.b200asm_gauss_legendre.argtypes = [C.c_int, dp, dp]
+    L.b200asm_tensor_rule.argtypes = [C.c_int, C.c_int, dp, dp]
+    L.b200asm_shape_tables.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.b200asm_build_pattern.argtypes = [C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64, C.c_int]
+    L.b200asm_build_pattern.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def i64ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64)) if a is not None else None
+
+
+def i32ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+# ---- host-side helpers (no device) -------------------------------------------------------------
+def tensor_rule(topology, order):
+    dim = 3 if topology == HEX else 2
+    pts = np.zeros((64 ** 2 if dim == 2 else 16 ** 3, dim))
+    w = np.zeros(len(pts))
+    n = lib().b200asm_tensor_rule(topology, order, dptr(pts), dptr(w))
+    if n < 0:
+        raise B200AsmError(n, "tensor_rule")
+    return pts[:n].copy(), w[:n].copy()
+
+
+def shape_tables(topology, porder, qpts):
+    qpts = np.ascontiguousarray(qpts, dtype=np.float64)
+    nq, dim = qpts.shape
+    phi = np.zeros((nq, 27))
+    dphi = np.zeros((nq, dim, 27))
+    phi_flat = np.zeros(nq * 27)
+    dphi_flat = np.zeros(nq * dim * 27)
+    n = lib().b200asm_shape_tables(topology, porder, nq, dptr(qpts), dptr(phi_flat), dptr(dphi_flat))
+    if n < 0:
+        raise B200AsmError(n, "shape_tables")
+    phi = phi_flat[: nq * n].reshape(nq, n).copy()
+    dphi = dphi_flat[: nq * dim * n].reshape(nq, dim, n).copy()
+    return phi, dphi
+
+
+def build_pattern(symmetric, elgraphindex, elgraph, blockpos, blocksize, nthreads=0):
+    elgraphindex = np.ascontiguousarray(elgraphindex, dtype=np.int64)
+    elgraph = np.ascontiguousarray(elgraph, dtype=np.int64)
+    blockpos = np.ascontiguousarray(blockpos, dtype=np.int64)
+    blocksize = np.ascontiguousarray(blocksize, dtype=np.int64)
+    neq = int(blocksize.sum())
+    ia = np.zeros(neq + 1, dtype=np.int64)
+    nel = len(elgraphindex) - 1
+    args = (int(bool(symmetric)), nel, i64ptr(elgraphindex), i64ptr(elgraph), len(blockpos), i64ptr(blockpos),
+            i64ptr(blocksize), i64ptr(ia))
+    nnz = lib().b200asm_build_pattern(*args, None, nthreads)
+    if nnz < 0:
+        raise B200AsmError(nnz, "build_pattern")
+    ja = np.empty(nnz, dtype=np.int64)
+    nnz2 = lib().b200asm_build_pattern(*args, i64ptr(ja), nthreads)
+    assert nnz2 == nnz
+    return ia, ja
+
+
+# ---- device context ------------------------------------------------------------------------------
+class Context:
+    """Owns one b200asm_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().b200asm_create(C.byref(self._h), device)
+        if rc != 0:
+            raise B200AsmError(rc, lib().b200asm_last_error(None).decode())
+        self._keep = []
+
+    def _check(self, rc):
+        if rc < 0:
+            raise B200AsmError(rc, lib().b200asm_last_error(self._h).decode())
+        return rc
+
+    def close(self):
+        if self._h:
+            lib().b200asm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(lib().b200asm_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def set_nodes(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._check(lib().b200asm_set_nodes(self._h, xyz.shape[0], dptr(xyz)))
+
+    def add_group(self, topology, porder, kind, nstate, elnodes, dest, qpts, qwts, phi, dphi, coef, force=None):
+        elnodes = np.ascontiguousarray(elnodes, dtype=np.int32)
+        dest = np.ascontiguousarray(dest, dtype=np.int64)
+        qpts = np.ascontiguousarray(qpts, dtype=np.float64)
+        qwts = np.ascontiguousarray(qwts, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        dphi = np.ascontiguousarray(dphi, dtype=np.float64)
+        g = Group()
+        g.topology, g.porder, g.kind, g.nstate = topology, porder, kind, nstate
+        g.nel = elnodes.shape[0]
+        g.elnodes, g.dest = i32ptr(elnodes), i64ptr(dest)
+        g.nqp, g.nshape = len(qwts), phi.shape[1]
+        g.qpts, g.qwts, g.phi, g.dphi = dptr(qpts), dptr(qwts), dptr(phi), dptr(dphi)
+        c = np.zeros(16)
+        c[: len(coef)] = coef
+        g.coef[:] = c.tolist()
+        if force is not None:
+            force = np.ascontiguousarray(force, dtype=np.float64)
+            g.force = dptr(force)
+        return self._check(lib().b200asm_add_group(self._h, C.byref(g)))
+
+    def set_group_coef(self, group, coef):
+        c = np.zeros(16)
+        c[: len(coef)] = coef
+        self._check(lib().b200asm_set_group_coef(self._h, group, dptr(c)))
+
+    def clear_groups(self):
+        self._check(lib().b200asm_clear_groups(self._h))
+
+    def set_pattern(self, ia, ja, symmetric):
+        ia = np.ascontiguousarray(ia, dtype=np.int64)
+        ja = np.ascontiguousarray(ja, dtype=np.int64)
+        self._check(lib().b200asm_set_pattern(self._h, len(ia) - 1, i64ptr(ia), i64ptr(ja), int(bool(symmetric))))
+
+    def assemble(self, a_host=None, rhs_host=None):
+        self._check(lib().b200asm_assemble(self._h, dptr(a_host), dptr(rhs_host)))
+
+    def assemble_async(self):
+        self._check(lib().b200asm_assemble_async(self._h))
+
+    def synchronize(self):
+        self._check(lib().b200asm_synchronize(self._h))
+
+    def download(self, a_host=None, rhs_host=None):
+        self._check(lib().b200asm_download(self._h, dptr(a_host), dptr(rhs_host)))
+
+    def device_pointers(self):
+        a, r = C.c_void_p(), C.c_void_p()
+        self._check(lib().b200asm_device_pointers(self._h, C.byref(a), C.byref(r)))
+        return a.value, r.value
+
+    def counters(self):
+        k, h, d = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(lib().b200asm_counters(self._h, C.byref(k), C.byref(h), C.byref(d)))
+        return k.value, h.value, d.value

@@ -1,0 +1,920 @@
+// b200asm — hand-written sm_100a kernels + the C ABI (include/b200asm.h) of the B200 assembly engine.
+//
+// What one b200asm_assemble() replaces (reference, all on the CPU, one element at a time):
+//   StrMatrix/pzstrmatrixor.cpp:157-250   element loop: CalcStiff -> ComputeDestinationIndices -> AddKel -> AddFel
+//   Mesh/pzinterpolationspace.cpp:404-473 quadrature loop (CalcStiffInternal)
+//   Mesh/pzgeoel.cpp:1145-1356            Jacobian, determinant, inverse
+//   Mesh/TPZCompElH1.cpp:140-149          dphix = jacinv^T dphi
+//   Material/Poisson/TPZMatPoisson.cpp:19-42, Material/Elasticity/TPZElasticity3D.cpp:269-372  Contribute
+//   Matrix/pzsysmp.cpp:370-411, Matrix/pzysmp.cpp:178-218, Matrix/pzfmatrix.cpp:285-299        scatter-add
+//
+// Design (DESIGN.md has the long version):
+//   * elements are processed in batches of EPB per CTA by a persistent grid (multiple of the SM count);
+//   * phase 1: per (element, point) Jacobian -> J^-1 and w|detJ| into shared memory;
+//   * phase 2: per point q, x-gradients sqrt(w|detJ|) * J^-T grad(phi_i) of all shape functions into a
+//     double-buffered shared-memory panel A (K rows x M columns per element);
+//   * phase 3: the element matrix is the Gram matrix A^T A.  Only its local upper triangle is formed,
+//     in TILE x TILE register tiles, one thread per (element, tile): each k-row costs 2*TILE shared
+//     loads for TILE^2 DFMAs.  Poisson: M = nshape, 3 rows per point.  Elasticity3D: M = 3*nshape
+//     (column 3*i+d), 1 row per point; the nine products per node pair are combined with C1,C2,C3
+//     in registers afterwards (exactly the nine formulas of TPZElasticity3D.cpp:318-326);
+//   * scatter: every tile entry has a precomputed CSR position (device-built scatter map, laid out so
+//     that a warp reads consecutive ints) and is added with red.global.add.f64.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200asm.h"
+
+// ------------------------------------------------------------------------------------------------
+// device-side parameter blocks
+// ------------------------------------------------------------------------------------------------
+struct VolParams {
+    int64_t nel;
+    int64_t nbatch;
+    int nq;
+    int kind;  // B200ASM_POISSON / B200ASM_ELASTICITY3D
+    const double *__restrict__ xyz;
+    const int32_t *__restrict__ elnodes;  // [nel][NN]
+    const int32_t *__restrict__ dest;     // [nel][M]
+    const double *__restrict__ qw;        // [nq]
+    const double *__restrict__ phi;       // [nq][N]
+    const double *__restrict__ dphi;      // [nq][3][N]
+    const double *__restrict__ dng;       // [nq][3][NN] gradients of the corner (geometry) functions
+    const double *__restrict__ force;     // optional [nel][nq][NS]
+    const int32_t *__restrict__ smap;     // [nbatch][TILE*TILE][EPB*NT]
+    const int32_t *__restrict__ smapT;    // same, transposed entry (full storage only)
+    double *__restrict__ a;
+    double *__restrict__ rhs;
+    double coef[16];
+};
+
+template <int NN_, int N_, int NS_, int TILE_, int EPB_>
+struct VolCfg {
+    static constexpr int NN = NN_, N = N_, NS = NS_, TILE = TILE_, EPB = EPB_;
+    static constexpr int M = N * NS;
+    static constexpr int NTB = (M + TILE - 1) / TILE;
+    static constexpr int MP = NTB * TILE;
+    static constexpr int NT = NTB * (NTB + 1) / 2;
+    static constexpr int KQ = NS == 1 ? 3 : 1;  // panel rows per integration point
+    static constexpr int SLOTS = EPB * NT;      // (element, tile) work items per batch
+    static constexpr int NTHREADS = ((SLOTS + 31) / 32) * 32;
+    static constexpr int JS = 11;                       // J^-1 (9), w|detJ|, sqrt(w|detJ|)
+    static constexpr int FPT = (EPB * M + NTHREADS - 1) / NTHREADS;  // rhs items per thread
+    static constexpr int AS = KQ * MP;                  // panel doubles per element per buffer
+    static size_t smem_bytes(int nq) { return sizeof(double) * ((size_t)EPB * NN * 3 + (size_t)EPB * nq * JS + 2 * (size_t)EPB * AS); }
+};
+
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+// decode the linear index of an upper-triangular tile into (bi, bj), bi <= bj
+template <int NTB>
+__device__ __forceinline__ void tile_coords(int t, int &bi, int &bj) {
+    bi = 0;
+#pragma unroll
+    for (int row = 0; row < NTB - 1; row++) {
+        const int cnt = NTB - row;
+        if (bi == row && t >= cnt) {
+            t -= cnt;
+            bi = row + 1;
+        }
+    }
+    bj = bi + t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// volume elements (hexahedra / tetrahedra)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS) assemble_volume_kernel(const VolParams p) {
+    constexpr int NN = C::NN, N = C::N, NS = C::NS, TILE = C::TILE, EPB = C::EPB, M = C::M, MP = C::MP;
+    constexpr int NT = C::NT, KQ = C::KQ, NTHREADS = C::NTHREADS, JS = C::JS, FPT = C::FPT, AS = C::AS;
+    extern __shared__ double smem[];
+    double *Xs = smem;                              // [EPB][NN][3]
+    double *JI = Xs + EPB * NN * 3;                 // [EPB][nq][JS]
+    double *As = JI + (size_t)EPB * p.nq * JS;      // [2][EPB][KQ][MP]
+    const int tid = threadIdx.x;
+    const int nq = p.nq;
+
+    for (int i = tid; i < 2 * EPB * AS; i += NTHREADS) As[i] = 0.0;  // padding columns stay zero for ever
+
+    const bool has_tile = tid < C::SLOTS;
+    const int el_t = tid / NT;
+    int bi, bj;
+    tile_coords<C::NTB>(tid % NT, bi, bj);
+    const int I0 = bi * TILE, J0 = bj * TILE;
+
+    for (int64_t batch = blockIdx.x; batch < p.nbatch; batch += gridDim.x) {
+        const int64_t e0 = batch * EPB;
+        const int nloc = (int)min((int64_t)EPB, p.nel - e0);
+        __syncthreads();  // the previous batch no longer reads Xs / JI / As
+
+        for (int i = tid; i < nloc * NN; i += NTHREADS) {
+            const int64_t node = p.elnodes[e0 * NN + i];
+            Xs[i * 3 + 0] = p.xyz[node * 3 + 0];
+            Xs[i * 3 + 1] = p.xyz[node * 3 + 1];
+            Xs[i * 3 + 2] = p.xyz[node * 3 + 2];
+        }
+        __syncthreads();
+
+        // ---- phase 1: geometry per (element, point) ------------------------------------------
+        for (int it = tid; it < nloc * nq; it += NTHREADS) {
+            const int el = it / nq, q = it - el * nq;
+            const double *X = Xs + el * NN * 3;
+            const double *dn = p.dng + (size_t)q * 3 * NN;
+            double j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0, j20 = 0, j21 = 0, j22 = 0;
+#pragma unroll
+            for (int a = 0; a < NN; a++) {  // gradx(j,k) += x_a[j] * dN_a/dxi_k   (Geom/TPZGeoCube.h:141-149)
+                const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a), d2 = __ldg(dn + 2 * NN + a);
+                const double x = X[a * 3], y = X[a * 3 + 1], z = X[a * 3 + 2];
+                j00 += x * d0; j01 += x * d1; j02 += x * d2;
+                j10 += y * d0; j11 += y * d1; j12 += y * d2;
+                j20 += z * d0; j21 += z * d1; j22 += z * d2;
+            }
+            // Mesh/pzgeoel.cpp:1309-1336
+            double det = 0.0;
+            det -= j02 * j11 * j20;
+            det += j01 * j12 * j20;
+            det += j02 * j10 * j21;
+            det -= j00 * j12 * j21;
+            det -= j01 * j10 * j22;
+            det += j00 * j11 * j22;
+            if (fabs(det) < 1.e-12) det = 1.e-12;
+            const double id = 1.0 / det;
+            double *o = JI + ((size_t)el * nq + q) * JS;
+            o[0] = (-j12 * j21 + j11 * j22) * id;
+            o[1] = (j02 * j21 - j01 * j22) * id;
+            o[2] = (-j02 * j11 + j01 * j12) * id;
+            o[3] = (j12 * j20 - j10 * j22) * id;
+            o[4] = (-j02 * j20 + j00 * j22) * id;
+            o[5] = (j02 * j10 - j00 * j12) * id;
+            o[6] = (-j11 * j20 + j10 * j21) * id;
+            o[7] = (j01 * j20 - j00 * j21) * id;
+            o[8] = (-j01 * j10 + j00 * j11) * id;
+            const double w = __ldg(p.qw + q) * fabs(det);  // weight *= fabs(detjac)  (pzinterpolationspace.cpp:468)
+            o[9] = w;
+            o[10] = sqrt(w);
+        }
+
+        double acc[TILE][TILE];
+#pragma unroll
+        for (int r = 0; r < TILE; r++)
+#pragma unroll
+            for (int c = 0; c < TILE; c++) acc[r][c] = 0.0;
+        double facc[FPT];
+#pragma unroll
+        for (int k = 0; k < FPT; k++) facc[k] = 0.0;
+        __syncthreads();
+
+        for (int q = 0; q < nq; q++) {
+            double *Ab = As + (size_t)(q & 1) * EPB * AS;
+            // ---- phase 2: panel rows of point q: sqrt(w) * jacinv^T * dphi  (TPZCompElH1.cpp:147) ----
+            for (int it = tid; it < nloc * N; it += NTHREADS) {
+                const int el = it / N, i = it - el * N;
+                const double *ji = JI + ((size_t)el * nq + q) * JS;
+                const double *dp = p.dphi + (size_t)q * 3 * N + i;
+                const double d0 = __ldg(dp), d1 = __ldg(dp + N), d2 = __ldg(dp + 2 * N);
+                const double sw = ji[10];
+                const double g0 = (ji[0] * d0 + ji[3] * d1 + ji[6] * d2) * sw;
+                const double g1 = (ji[1] * d0 + ji[4] * d1 + ji[7] * d2) * sw;
+                const double g2 = (ji[2] * d0 + ji[5] * d1 + ji[8] * d2) * sw;
+                double *row = Ab + (size_t)el * AS;
+                if (NS == 1) {
+                    row[i] = g0;
+                    row[MP + i] = g1;
+                    row[2 * MP + i] = g2;
+                } else {
+                    row[3 * i] = g0;
+                    row[3 * i + 1] = g1;
+                    row[3 * i + 2] = g2;
+                }
+            }
+            __syncthreads();
+            // ---- phase 3: Gram update of this thread's register tile --------------------------
+            if (has_tile && el_t < nloc) {
+                const double *row = Ab + (size_t)el_t * AS;
+#pragma unroll
+                for (int kr = 0; kr < KQ; kr++) {
+                    double a[TILE], b[TILE];
+#pragma unroll
+                    for (int r = 0; r < TILE; r++) a[r] = row[kr * MP + I0 + r];
+#pragma unroll
+                    for (int c = 0; c < TILE; c++) b[c] = row[kr * MP + J0 + c];
+#pragma unroll
+                    for (int r = 0; r < TILE; r++)
+#pragma unroll
+                        for (int c = 0; c < TILE; c++) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+                }
+            }
+            // ---- load vector of point q ---------------------------------------------------------
+#pragma unroll
+            for (int k = 0; k < FPT; k++) {
+                const int it = tid + k * NTHREADS;
+                if (it < nloc * M) {
+                    const int el = it / M, m = it - el * M;
+                    const double *ji = JI + ((size_t)el * nq + q) * JS;
+                    const double w = ji[9];
+                    if (NS == 1) {
+                        // ef(i) += weight*fScale*phi(i)*force   (TPZMatPoisson.cpp:39-40)
+                        const double f = p.force ? p.force[((e0 + el) * nq + q)] : p.coef[1];
+                        facc[k] += w * p.coef[0] * __ldg(p.phi + (size_t)q * N + m) * f;
+                    } else {
+                        // ef(3j+k) += weight*(force_k*phi_j - prestress_k*dphi(k,j))   (TPZElasticity3D.cpp:278)
+                        const int j = m / 3, kd = m - 3 * j;
+                        const double f = p.force ? p.force[((e0 + el) * nq + q) * 3 + kd] : p.coef[3 + kd];
+                        const double wdphi = ji[10] * Ab[(size_t)el * AS + m];  // w * dphix(kd, j)
+                        facc[k] += w * f * __ldg(p.phi + (size_t)q * N + j) - p.coef[6 + kd] * wdphi;
+                    }
+                }
+            }
+        }
+
+        // ---- epilogue: scatter-add into CSR values and rhs -----------------------------------
+        if (has_tile && el_t < nloc) {
+            if (NS == 3) {
+                // nine sums S[v][u] per node pair -> the 3x3 block of ek  (TPZElasticity3D.cpp:318-326)
+                const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
+#pragma unroll
+                for (int il = 0; il < TILE / 3; il++)
+#pragma unroll
+                    for (int jl = 0; jl < TILE / 3; jl++) {
+                        double S[3][3];
+#pragma unroll
+                        for (int v = 0; v < 3; v++)
+#pragma unroll
+                            for (int u = 0; u < 3; u++) S[v][u] = acc[3 * il + v][3 * jl + u];
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++) {
+                                double e;
+                                if (a == b) e = (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3;
+                                else e = S[b][a] * C1 - S[a][b] * C2;
+                                acc[3 * il + a][3 * jl + b] = e;
+                            }
+                    }
+            } else {
+                const double s = p.coef[0];
+#pragma unroll
+                for (int r = 0; r < TILE; r++)
+#pragma unroll
+                    for (int c = 0; c < TILE; c++) acc[r][c] *= s;
+            }
+            const int32_t *sm = p.smap + (size_t)batch * TILE * TILE * C::SLOTS + tid;
+            const int32_t *smT = p.smapT ? p.smapT + (size_t)batch * TILE * TILE * C::SLOTS + tid : nullptr;
+#pragma unroll
+            for (int r = 0; r < TILE; r++)
+#pragma unroll
+                for (int c = 0; c < TILE; c++) {
+                    const int32_t pos = sm[(r * TILE + c) * C::SLOTS];
+                    if (pos >= 0) red_add(p.a + pos, acc[r][c]);
+                    if (smT) {
+                        const int32_t posT = smT[(r * TILE + c) * C::SLOTS];
+                        if (posT >= 0) red_add(p.a + posT, acc[r][c]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < FPT; k++) {
+            const int it = tid + k * NTHREADS;
+            if (it < nloc * M) red_add(p.rhs + p.dest[e0 * M + it], facc[k]);
+        }
+    }
+}
+
+// scatter-map construction for a volume group: one thread per (batch, tile entry, slot)
+template <class C>
+__global__ void build_volume_smap_kernel(int64_t nel, int64_t nbatch, const int32_t *__restrict__ dest,
+                                         const int64_t *__restrict__ ia, const int64_t *__restrict__ ja, int symmetric,
+                                         int32_t *__restrict__ smap, int32_t *__restrict__ smapT, int *__restrict__ missing) {
+    constexpr int TILE = C::TILE, M = C::M, NT = C::NT, SLOTS = C::SLOTS;
+    const int64_t total = nbatch * TILE * TILE * SLOTS;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(idx % SLOTS);
+        const int rc = (int)((idx / SLOTS) % (TILE * TILE));
+        const int64_t batch = idx / ((int64_t)SLOTS * TILE * TILE);
+        const int el_l = slot / NT;
+        int bi, bj;
+        tile_coords<C::NTB>(slot % NT, bi, bj);
+        const int r = rc / TILE, c = rc % TILE;
+        const int i = bi * TILE + r, j = bj * TILE + c;
+        const int64_t el = batch * C::EPB + el_l;
+        int32_t pos = -1, posT = -1;
+        if (el < nel && i < M && j < M && i <= j) {
+            const int64_t di = dest[el * M + i], dj = dest[el * M + j];
+            auto find = [&](int64_t row, int64_t col) -> int32_t {
+                int64_t lo = ia[row], hi = ia[row + 1] - 1;
+                while (lo <= hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    const int64_t v = ja[mid];
+                    if (v == col) return (int32_t)mid;
+                    if (v < col) lo = mid + 1; else hi = mid - 1;
+                }
+                atomicAdd(missing, 1);
+                return -1;
+            };
+            if (symmetric) {
+                pos = find(min(di, dj), max(di, dj));
+            } else {
+                pos = find(di, dj);
+                if (i != j) posT = find(dj, di);
+            }
+        }
+        smap[idx] = pos;
+        if (smapT) smapT[idx] = posT;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary faces (quadrilaterals / triangles): one thread per element
+//   ek(ns*i+a, ns*j+b) += M[a][b]*phi_i*phi_j*w ,  ef(ns*i+a) += v[a]*phi_i*w
+// with w = weight*|detjac| of the 2-D Gram-Schmidt branch of TPZGeoEl::Jacobian (pzgeoel.cpp:1228-1295)
+// ------------------------------------------------------------------------------------------------
+struct BcParams {
+    int64_t nel;
+    int nq;
+    const double *__restrict__ xyz;
+    const int32_t *__restrict__ elnodes;
+    const int32_t *__restrict__ dest;
+    const double *__restrict__ qw;
+    const double *__restrict__ phi;   // [nq][N]
+    const double *__restrict__ dng;   // [nq][2][NN]
+    const int32_t *__restrict__ smap;   // [N*N*NS*NS][nel]
+    const int32_t *__restrict__ smapT;
+    double *__restrict__ a;
+    double *__restrict__ rhs;
+    double coef[16];
+};
+
+template <int NN, int N, int NS>
+__global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
+    const int64_t el = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (el >= p.nel) return;
+    double X[NN][3];
+#pragma unroll
+    for (int a = 0; a < NN; a++) {
+        const int64_t node = p.elnodes[el * NN + a];
+        X[a][0] = p.xyz[node * 3];
+        X[a][1] = p.xyz[node * 3 + 1];
+        X[a][2] = p.xyz[node * 3 + 2];
+    }
+    double S[N][N];  // sum_q phi_i phi_j w   (upper part used)
+    double T[N];     // sum_q phi_i w
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        T[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) S[i][j] = 0.0;
+    }
+    for (int q = 0; q < p.nq; q++) {
+        const double *dn = p.dng + (size_t)q * 2 * NN;
+        double v1[3] = {0, 0, 0}, v2[3] = {0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < NN; a++) {
+            const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                v1[k] += X[a][k] * d0;
+                v2[k] += X[a][k] * d1;
+            }
+        }
+        double n1 = 0, dot = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            n1 += v1[k] * v1[k];
+            dot += v1[k] * v2[k];
+        }
+        n1 = sqrt(n1);
+        double n2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double v1t = v1[k] / n1;
+            const double v2t = v2[k] - dot * v1t / n1;
+            n2 += v2t * v2t;
+        }
+        n2 = sqrt(n2);
+        double det = n1 * n2;
+        if (fabs(det) < 1.e-12) det = 1.e-12;
+        const double w = __ldg(p.qw + q) * fabs(det);
+        double ph[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) ph[i] = __ldg(p.phi + (size_t)q * N + i);
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            T[i] += ph[i] * w;
+#pragma unroll
+            for (int j = i; j < N; j++) S[i][j] += ph[i] * ph[j] * w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = i; j < N; j++)
+#pragma unroll
+            for (int a = 0; a < NS; a++)
+#pragma unroll
+                for (int b = 0; b < NS; b++) {
+                    if (i == j && b < a) continue;
+                    const double mab = p.coef[a * 3 + b], mba = p.coef[b * 3 + a];
+                    if (mab == 0.0 && mba == 0.0) continue;
+                    const size_t idx = ((size_t)((i * N + j) * NS + a) * NS + b) * p.nel + el;
+                    const int32_t pos = p.smap[idx];
+                    if (pos >= 0 && mab != 0.0) red_add(p.a + pos, mab * S[i][j]);
+                    if (p.smapT) {
+                        const int32_t posT = p.smapT[idx];
+                        if (posT >= 0 && mba != 0.0) red_add(p.a + posT, mba * S[i][j]);
+                    }
+                }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int a = 0; a < NS; a++) {
+            const double v = p.coef[9 + a];
+            if (v != 0.0) red_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T[i]);
+        }
+}
+
+__global__ void build_bc_smap_kernel(int64_t nel, int n, int ns, const int32_t *__restrict__ dest,
+                                     const int64_t *__restrict__ ia, const int64_t *__restrict__ ja, int symmetric,
+                                     int32_t *__restrict__ smap, int32_t *__restrict__ smapT, int *__restrict__ missing) {
+    const int m = n * ns;
+    const int64_t total = (int64_t)n * n * ns * ns * nel;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t el = idx % nel;
+        int e = (int)(idx / nel);
+        const int b = e % ns; e /= ns;
+        const int a = e % ns; e /= ns;
+        const int j = e % n;
+        const int i = e / n;
+        int32_t pos = -1, posT = -1;
+        if (i < j || (i == j && a <= b)) {
+            const int64_t di = dest[el * m + i * ns + a], dj = dest[el * m + j * ns + b];
+            auto find = [&](int64_t row, int64_t col) -> int32_t {
+                int64_t lo = ia[row], hi = ia[row + 1] - 1;
+                while (lo <= hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    const int64_t v = ja[mid];
+                    if (v == col) return (int32_t)mid;
+                    if (v < col) lo = mid + 1; else hi = mid - 1;
+                }
+                atomicAdd(missing, 1);
+                return -1;
+            };
+            if (symmetric) {
+                pos = find(min(di, dj), max(di, dj));
+            } else {
+                pos = find(di, dj);
+                if (di != dj) posT = find(dj, di);
+            }
+        }
+        smap[idx] = pos;
+        if (smapT) smapT[idx] = posT;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: context, groups, dispatch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Group {
+    int topology = 0, porder = 0, kind = 0, ns = 1, nn = 0, n = 0, nq = 0, m = 0, dim = 3;
+    int64_t nel = 0, nbatch = 0;
+    int cfg = -1;  // index into the dispatch table
+    double coef[16];
+    int32_t *d_elnodes = nullptr, *d_dest = nullptr, *d_smap = nullptr, *d_smapT = nullptr;
+    double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
+    size_t smap_len = 0;
+};
+
+}  // namespace
+
+struct b200asm_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    double *d_xyz = nullptr;
+    int64_t nnodes = 0;
+    std::vector<Group> groups;
+    int64_t neq = 0, nnz = 0;
+    int symmetric = 1;
+    bool have_pattern = false;
+    int64_t *d_ia = nullptr;
+    double *d_a = nullptr, *d_rhs = nullptr;
+    int *d_missing = nullptr;
+    int64_t launches = 0, h2d = 0, d2h = 0;
+    int scatter = B200ASM_SCATTER_ATOMIC;
+    std::string err;
+};
+
+namespace {
+
+int fail(b200asm_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, B200ASM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+template <class T>
+int upload(b200asm_ctx *ctx, T **dptr, const T *host, size_t count) {
+    CK(cudaMalloc((void **)dptr, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) {
+        CK(cudaMemcpyAsync(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d += (int64_t)(count * sizeof(T));
+    }
+    return 0;
+}
+
+// ---- dispatch tables ---------------------------------------------------------------------------
+// volume configurations:            NN  N  NS TILE EPB
+using HexP1Poisson = VolCfg<8, 8, 1, 8, 64>;
+using HexP1Elast = VolCfg<8, 8, 3, 6, 12>;
+using HexP2Poisson = VolCfg<8, 27, 1, 9, 16>;
+using HexP2Elast = VolCfg<8, 27, 3, 9, 4>;
+using TetP1Poisson = VolCfg<4, 4, 1, 4, 128>;
+using TetP1Elast = VolCfg<4, 4, 3, 6, 32>;
+using TetP2Poisson = VolCfg<4, 10, 1, 5, 32>;
+using TetP2Elast = VolCfg<4, 10, 3, 6, 8>;
+
+struct VolEntry {
+    int topology, porder, ns;
+    int epb, tile, slots, nthreads;
+    size_t (*smem)(int nq);
+    cudaError_t (*launch)(const VolParams &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*launch_smap)(int64_t nel, int64_t nbatch, const int32_t *dest, const int64_t *ia, const int64_t *ja,
+                               int symmetric, int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t);
+    cudaError_t (*prepare)(size_t smem, int *ctas_per_sm);
+};
+
+template <class C>
+cudaError_t launch_vol(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
+    assemble_volume_kernel<C><<<grid, C::NTHREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t launch_vol_smap(int64_t nel, int64_t nbatch, const int32_t *dest, const int64_t *ia, const int64_t *ja,
+                            int symmetric, int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_volume_smap_kernel<C><<<grid, 256, 0, s>>>(nel, nbatch, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t prepare_vol(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_volume_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_volume_kernel<C>, C::NTHREADS, smem);
+}
+template <class C>
+VolEntry make_entry(int topology, int porder) {
+    return VolEntry{topology, porder, C::NS, C::EPB, C::TILE, C::SLOTS, C::NTHREADS, &C::smem_bytes,
+                    &launch_vol<C>, &launch_vol_smap<C>, &prepare_vol<C>};
+}
+
+const VolEntry kVol[] = {
+    make_entry<HexP1Poisson>(B200ASM_HEX, 1), make_entry<HexP1Elast>(B200ASM_HEX, 1),
+    make_entry<HexP2Poisson>(B200ASM_HEX, 2), make_entry<HexP2Elast>(B200ASM_HEX, 2),
+    make_entry<TetP1Poisson>(B200ASM_TET, 1), make_entry<TetP1Elast>(B200ASM_TET, 1),
+    make_entry<TetP2Poisson>(B200ASM_TET, 2), make_entry<TetP2Elast>(B200ASM_TET, 2),
+};
+constexpr int kNumVol = sizeof(kVol) / sizeof(kVol[0]);
+
+template <int NN, int N, int NS>
+cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
+    const int grid = (int)((p.nel + 127) / 128);
+    assemble_bc_kernel<NN, N, NS><<<grid, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cudaStream_t s) {
+    if (topology == B200ASM_QUAD && porder == 1) return ns == 1 ? launch_bc<4, 4, 1>(p, s) : launch_bc<4, 4, 3>(p, s);
+    if (topology == B200ASM_QUAD && porder == 2) return ns == 1 ? launch_bc<4, 9, 1>(p, s) : launch_bc<4, 9, 3>(p, s);
+    if (topology == B200ASM_TRI && porder == 1) return ns == 1 ? launch_bc<3, 3, 1>(p, s) : launch_bc<3, 3, 3>(p, s);
+    if (topology == B200ASM_TRI && porder == 2) return ns == 1 ? launch_bc<3, 6, 1>(p, s) : launch_bc<3, 6, 3>(p, s);
+    return cudaErrorInvalidValue;
+}
+
+int nshape_of(int topology, int p) {
+    switch (topology) {
+        case B200ASM_HEX: return p == 1 ? 8 : 27;
+        case B200ASM_TET: return p == 1 ? 4 : 10;
+        case B200ASM_QUAD: return p == 1 ? 4 : 9;
+        case B200ASM_TRI: return p == 1 ? 3 : 6;
+    }
+    return -1;
+}
+int ncorner_of(int topology) {
+    switch (topology) {
+        case B200ASM_HEX: return 8;
+        case B200ASM_TET: return 4;
+        case B200ASM_QUAD: return 4;
+        case B200ASM_TRI: return 3;
+    }
+    return -1;
+}
+
+void free_group(Group &g) {
+    cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
+    cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
+    g = Group();
+}
+
+int build_smaps(b200asm_ctx *ctx, const int64_t *d_ja) {
+    CK(cudaMemsetAsync(ctx->d_missing, 0, sizeof(int), ctx->stream));
+    for (Group &g : ctx->groups) {
+        cudaFree(g.d_smap); cudaFree(g.d_smapT);
+        g.d_smap = g.d_smapT = nullptr;
+        if (g.kind == B200ASM_BC) {
+            g.smap_len = (size_t)g.n * g.n * g.ns * g.ns * g.nel;
+        } else {
+            const VolEntry &ve = kVol[g.cfg];
+            g.nbatch = (g.nel + ve.epb - 1) / ve.epb;
+            g.smap_len = (size_t)g.nbatch * ve.tile * ve.tile * ve.slots;
+        }
+        CK(cudaMalloc((void **)&g.d_smap, std::max<size_t>(g.smap_len, 1) * sizeof(int32_t)));
+        if (!ctx->symmetric) CK(cudaMalloc((void **)&g.d_smapT, std::max<size_t>(g.smap_len, 1) * sizeof(int32_t)));
+        if (g.smap_len == 0) continue;
+        const int grid = (int)std::min<size_t>((g.smap_len + 255) / 256, (size_t)ctx->num_sms * 32);
+        if (g.kind == B200ASM_BC) {
+            build_bc_smap_kernel<<<grid, 256, 0, ctx->stream>>>(g.nel, g.n, g.ns, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric,
+                                                                g.d_smap, g.d_smapT, ctx->d_missing);
+            CK(cudaGetLastError());
+        } else {
+            CK(kVol[g.cfg].launch_smap(g.nel, g.nbatch, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT,
+                                        ctx->d_missing, grid, ctx->stream));
+        }
+        ctx->launches++;
+    }
+    int missing = 0;
+    CK(cudaMemcpyAsync(&missing, ctx->d_missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (missing)
+        return fail(ctx, B200ASM_EPATTERN, "scatter map: " + std::to_string(missing) +
+                                               " element entries have no position in the CSR pattern");
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *b200asm_last_error(const b200asm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int b200asm_create(b200asm_ctx **out, int device) {
+    b200asm_ctx *ctx = nullptr;
+    if (!out) return fail(ctx, B200ASM_EINVAL, "b200asm_create: out == NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, B200ASM_ENODEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) +
+                                                "): b200asm has no CPU path");
+    if (device < 0 || device >= ndev) return fail(ctx, B200ASM_EINVAL, "b200asm_create: bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(ctx, B200ASM_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    b200asm_ctx *c = new b200asm_ctx();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_missing, sizeof(int)) != cudaSuccess) {
+        delete c;
+        return fail(ctx, B200ASM_ECUDA, "b200asm_create: stream/alloc failed");
+    }
+    c->own_stream = true;
+    *out = c;
+    return 0;
+}
+
+extern "C" void b200asm_destroy(b200asm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (Group &g : ctx->groups) free_group(g);
+    cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return 0;
+}
+
+extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return B200ASM_EINVAL;
+    if (!strcmp(name, "scatter")) {
+        if (value != B200ASM_SCATTER_ATOMIC) return fail(ctx, B200ASM_EINVAL, "scatter: only B200ASM_SCATTER_ATOMIC is implemented");
+        ctx->scatter = (int)value;
+        return 0;
+    }
+    return fail(ctx, B200ASM_EINVAL, std::string("unknown option ") + name);
+}
+
+extern "C" int b200asm_set_nodes(b200asm_ctx *ctx, int64_t nnodes, const double *xyz) {
+    if (!ctx || nnodes < 0 || (nnodes && !xyz)) return fail(ctx, B200ASM_EINVAL, "b200asm_set_nodes: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (nnodes != ctx->nnodes || !ctx->d_xyz) {
+        cudaFree(ctx->d_xyz);
+        ctx->d_xyz = nullptr;
+        CK(cudaMalloc((void **)&ctx->d_xyz, std::max<int64_t>(nnodes, 1) * 3 * sizeof(double)));
+        ctx->nnodes = nnodes;
+    }
+    CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)nnodes * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += nnodes * 3 * (int64_t)sizeof(double);
+    return 0;
+}
+
+extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
+    if (!ctx || !gi) return B200ASM_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    Group g;
+    g.topology = gi->topology; g.porder = gi->porder; g.kind = gi->kind; g.ns = gi->nstate; g.nel = gi->nel;
+    g.nn = ncorner_of(gi->topology);
+    g.n = nshape_of(gi->topology, gi->porder);
+    g.nq = gi->nqp;
+    g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET) ? 3 : 2;
+    if (g.nn < 0 || g.n < 0 || gi->porder < 1 || gi->porder > 2)
+        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p in {1,2}, hex/tet/quad/tri)");
+    if (gi->nshape != g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not match topology/order");
+    if (g.ns != 1 && g.ns != 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1 or 3");
+    if (g.nel < 0 || g.nq <= 0 || g.nq > 512) return fail(ctx, B200ASM_EINVAL, "add_group: bad nel/nqp");
+    if (!gi->elnodes || !gi->dest || !gi->qpts || !gi->qwts || !gi->phi || !gi->dphi)
+        return fail(ctx, B200ASM_EINVAL, "add_group: NULL table");
+    const bool volume = g.dim == 3;
+    if (volume) {
+        if (gi->kind == B200ASM_POISSON && g.ns != 1) return fail(ctx, B200ASM_EINVAL, "add_group: Poisson has nstate 1");
+        if (gi->kind == B200ASM_ELASTICITY3D && g.ns != 3) return fail(ctx, B200ASM_EINVAL, "add_group: Elasticity3D has nstate 3");
+        if (gi->kind != B200ASM_POISSON && gi->kind != B200ASM_ELASTICITY3D)
+            return fail(ctx, B200ASM_EINVAL, "add_group: volume elements need kind POISSON or ELASTICITY3D");
+        for (int k = 0; k < kNumVol; k++)
+            if (kVol[k].topology == g.topology && kVol[k].porder == g.porder && kVol[k].ns == g.ns) g.cfg = k;
+        if (g.cfg < 0) return fail(ctx, B200ASM_EINVAL, "add_group: no kernel for this configuration");
+    } else if (gi->kind != B200ASM_BC) {
+        return fail(ctx, B200ASM_EINVAL, "add_group: face elements need kind BC");
+    }
+    g.m = g.n * g.ns;
+    memcpy(g.coef, gi->coef, sizeof(g.coef));
+
+    // destination indices as int32 (the reference's own CSR loops are 32-bit: Matrix/pzsysmp.cpp:62,73)
+    std::vector<int32_t> dest32((size_t)g.nel * g.m);
+    for (size_t k = 0; k < dest32.size(); k++) {
+        const int64_t d = gi->dest[k];
+        if (d < 0 || d > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "add_group: destination index out of int32 range");
+        dest32[k] = (int32_t)d;
+    }
+    // gradients of the geometric (corner) functions at the points = the p=1 shape gradients
+    std::vector<double> gphi((size_t)g.nq * g.nn), dng((size_t)g.nq * g.dim * g.nn);
+    if (b200asm_shape_tables(g.topology, 1, g.nq, gi->qpts, gphi.data(), dng.data()) != g.nn)
+        return fail(ctx, B200ASM_EINVAL, "add_group: geometry table failed");
+    int rc;
+    if ((rc = upload(ctx, &g.d_elnodes, gi->elnodes, (size_t)g.nel * g.nn))) return rc;
+    if ((rc = upload(ctx, &g.d_dest, dest32.data(), dest32.size()))) return rc;
+    if ((rc = upload(ctx, &g.d_qw, gi->qwts, (size_t)g.nq))) return rc;
+    if ((rc = upload(ctx, &g.d_phi, gi->phi, (size_t)g.nq * g.n))) return rc;
+    if ((rc = upload(ctx, &g.d_dphi, gi->dphi, (size_t)g.nq * g.dim * g.n))) return rc;
+    if ((rc = upload(ctx, &g.d_dng, dng.data(), dng.size()))) return rc;
+    if (gi->force && volume)
+        if ((rc = upload(ctx, &g.d_force, gi->force, (size_t)g.nel * g.nq * g.ns))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // dest32 / dng are stack-owned
+    ctx->groups.push_back(g);
+    ctx->have_pattern = false;  // scatter maps must be rebuilt
+    return (int)ctx->groups.size() - 1;
+}
+
+extern "C" int b200asm_set_group_coef(b200asm_ctx *ctx, int group, const double coef[16]) {
+    if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !coef) return fail(ctx, B200ASM_EINVAL, "set_group_coef: bad arguments");
+    memcpy(ctx->groups[group].coef, coef, sizeof(double) * 16);
+    return 0;
+}
+
+extern "C" int b200asm_clear_groups(b200asm_ctx *ctx) {
+    if (!ctx) return B200ASM_EINVAL;
+    cudaSetDevice(ctx->device);
+    for (Group &g : ctx->groups) free_group(g);
+    ctx->groups.clear();
+    ctx->have_pattern = false;
+    return 0;
+}
+
+extern "C" int b200asm_set_pattern(b200asm_ctx *ctx, int64_t neq, const int64_t *ia, const int64_t *ja, int symmetric) {
+    if (!ctx || neq < 0 || !ia) return fail(ctx, B200ASM_EINVAL, "set_pattern: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nnz = ia[neq];
+    if (nnz < 0 || nnz > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "set_pattern: nnz must fit int32 per device (shard the rows)");
+    if (nnz && !ja) return fail(ctx, B200ASM_EINVAL, "set_pattern: ja == NULL");
+    cudaFree(ctx->d_ia); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs);
+    ctx->d_ia = nullptr; ctx->d_a = ctx->d_rhs = nullptr;
+    ctx->neq = neq; ctx->nnz = nnz; ctx->symmetric = symmetric ? 1 : 0;
+    int64_t *d_ja = nullptr;
+    int rc;
+    if ((rc = upload(ctx, &ctx->d_ia, ia, (size_t)neq + 1))) return rc;
+    if ((rc = upload(ctx, &d_ja, ja, (size_t)nnz))) return rc;
+    CK(cudaMalloc((void **)&ctx->d_a, std::max<int64_t>(nnz, 1) * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_rhs, std::max<int64_t>(neq, 1) * sizeof(double)));
+    rc = build_smaps(ctx, d_ja);
+    cudaFree(d_ja);  // column indices are only needed to build the maps
+    if (rc) return rc;
+    ctx->have_pattern = true;
+    return 0;
+}
+
+extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (!ctx->have_pattern) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
+    if (!ctx->d_xyz) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_nodes first");
+    CK(cudaSetDevice(ctx->device));
+    // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75
+    CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
+    for (const Group &g : ctx->groups) {
+        if (g.nel == 0) continue;
+        if (g.kind == B200ASM_BC) {
+            BcParams p;
+            p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
+            p.qw = g.d_qw; p.phi = g.d_phi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
+            p.a = ctx->d_a; p.rhs = ctx->d_rhs;
+            memcpy(p.coef, g.coef, sizeof(p.coef));
+            CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+        } else {
+            const VolEntry &ve = kVol[g.cfg];
+            VolParams p;
+            p.nel = g.nel; p.nbatch = g.nbatch; p.nq = g.nq; p.kind = g.kind;
+            p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest; p.qw = g.d_qw; p.phi = g.d_phi;
+            p.dphi = g.d_dphi; p.dng = g.d_dng; p.force = g.d_force; p.smap = g.d_smap; p.smapT = g.d_smapT;
+            p.a = ctx->d_a; p.rhs = ctx->d_rhs;
+            memcpy(p.coef, g.coef, sizeof(p.coef));
+            const size_t smem = ve.smem(g.nq);
+            if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
+            // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)
+            int per_sm = 1;
+            CK(ve.prepare(smem, &per_sm));
+            if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
+            const int grid = (int)std::min<int64_t>(g.nbatch, (int64_t)ctx->num_sms * per_sm);
+            CK(ve.launch(p, grid, smem, ctx->stream));
+        }
+        ctx->launches++;
+    }
+    return 0;
+}
+
+extern "C" int b200asm_synchronize(b200asm_ctx *ctx) {
+    if (!ctx) return B200ASM_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (!ctx->d_a) return fail(ctx, B200ASM_ESTATE, "download: nothing assembled");
+    CK(cudaSetDevice(ctx->device));
+    if (a_host) {
+        CK(cudaMemcpyAsync(a_host, ctx->d_a, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += ctx->nnz * (int64_t)sizeof(double);
+    }
+    if (rhs_host) {
+        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs, (size_t)ctx->neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += ctx->neq * (int64_t)sizeof(double);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
+    int rc = b200asm_assemble_async(ctx);
+    if (rc) return rc;
+    return b200asm_download(ctx, a_host, rhs_host);
+}
+
+extern "C" int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (a_dev) *a_dev = ctx->d_a;
+    if (rhs_dev) *rhs_dev = ctx->d_rhs;
+    return 0;
+}
+
+extern "C" int b200asm_counters(const b200asm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (kernel_launches) *kernel_launches = ctx->launches;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h;
+    return 0;
+}

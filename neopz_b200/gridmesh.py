@@ -1,0 +1,289 @@
+"""Flattened H1 meshes on structured grids, numbered exactly as NeoPZ numbers them.
+
+Host-side mirror (numpy) of what the reference produces for the benchmark meshes:
+  * TPZGeoMeshTools::CreateGeoMeshOnGrid (Mesh/TPZGeoMeshTools.cpp:105-219) with TPZGenGrid3D
+    (Pre/TPZGenGrid3D.cpp:51-180 volume elements, :245-400 boundary faces): node id
+    iz*(nx+1)*(ny+1)+iy*(nx+1)+ix, hexahedra in (iz,iy,ix) order, 5 tetrahedra per cell with the
+    parity rotation, then the z-, y- and x-faces;
+  * TPZCompMesh::AutoBuild with SetAllCreateFunctionsContinuous: computational elements are created
+    in geometric-element order (Mesh/pzcreateapproxspace.cpp:252-325) and every element asks, side
+    by side (side order of Topology/tpzcube.cpp etc.), for the connect of that side, creating it when
+    no neighbour has one yet.  Connect index == sequence number (no renumbering,
+    TPZLinearAnalysis(cmesh,false)), block positions are the running sum of the block sizes
+    (Matrix/pzblock.h) — so first-touch order over (element, side) reproduces the numbering;
+  * TPZElementMatrix::ComputeDestinationIndices (Mesh/pzelmat.cpp:37-70).
+
+tests/test_gridmesh.py compares every array against fixtures dumped from the reference.
+The result is what the NeoPZ-side flattener (csrc/neopz/TPZStructMatrixB200.cpp) extracts from a
+TPZCompMesh, in the layout the C ABI (include/b200asm.h) takes.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+# local node ids of every side, in side order
+HEX_SIDES = ([[i] for i in range(8)] +
+             [[0, 1], [1, 2], [2, 3], [3, 0], [0, 4], [1, 5], [2, 6], [3, 7], [4, 5], [5, 6], [6, 7], [7, 4]] +
+             [[0, 1, 2, 3], [0, 1, 5, 4], [1, 2, 6, 5], [3, 2, 6, 7], [0, 3, 7, 4], [4, 5, 6, 7]] +
+             [[0, 1, 2, 3, 4, 5, 6, 7]])
+TET_SIDES = ([[i] for i in range(4)] + [[0, 1], [1, 2], [2, 0], [0, 3], [1, 3], [2, 3]] +
+             [[0, 1, 2], [0, 1, 3], [1, 2, 3], [0, 2, 3]] + [[0, 1, 2, 3]])
+QUAD_SIDES = [[i] for i in range(4)] + [[0, 1], [1, 2], [2, 3], [3, 0]] + [[0, 1, 2, 3]]
+TRI_SIDES = [[i] for i in range(3)] + [[0, 1], [1, 2], [2, 0]] + [[0, 1, 2]]
+SIDES = {capi.HEX: HEX_SIDES, capi.TET: TET_SIDES, capi.QUAD: QUAD_SIDES, capi.TRI: TRI_SIDES}
+NCORNER = {capi.HEX: 8, capi.TET: 4, capi.QUAD: 4, capi.TRI: 3}
+DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2}
+
+
+def side_nshape(topology, side_nodes, p):
+    """TSHAPE::NConnectShapeF(side, p) for p in {1,2} (Shape/pzshapecube.cpp:573-584, pzshapetetra.cpp:447-466)."""
+    k = len(side_nodes)
+    if k == 1:
+        return 1
+    if p == 1:
+        return 0
+    if k == 2:
+        return 1  # edge: p-1
+    if topology in (capi.HEX, capi.QUAD):
+        return 1  # quad face (p-1)^2, hex interior (p-1)^3
+    return 0      # triangle face / tet interior: none at p=2
+
+
+@dataclass
+class ElementBlock:
+    """Consecutive computational elements of one topology and material id."""
+    topology: int
+    matid: int
+    first: int              # index of the first element in the computational mesh
+    elnodes: np.ndarray     # [nel][ncorner] int32
+    connects: np.ndarray    # [nel][nsides] int64 sequence numbers (TPZCompEl::ConnectIndex -> SequenceNumber)
+    dest: np.ndarray = None  # [nel][ndof] int64
+
+
+@dataclass
+class FlatMesh:
+    """What the flattener hands to the C ABI (one entry of `blocks` becomes one b200asm_group)."""
+    porder: int
+    nstate: int
+    nodes: np.ndarray                   # [nnodes][3]
+    blocks: list = field(default_factory=list)
+    block_pos: np.ndarray = None        # TPZBlock::Position per sequence number
+    block_size: np.ndarray = None       # TPZBlock::Size
+    neq: int = 0
+
+    @property
+    def nelements(self):
+        return sum(len(b.elnodes) for b in self.blocks)
+
+    def element_graph(self):
+        """TPZCompMesh::ComputeElGraph (Mesh/pzcmesh.cpp:1223-1267): seqnums of all connects, element order."""
+        idx = [0]
+        parts = []
+        for b in sorted(self.blocks, key=lambda b: b.first):
+            nel, ns = b.connects.shape
+            parts.append(b.connects.reshape(-1))
+            idx.append(idx[-1] + nel * ns)
+        graph = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+        index = np.concatenate([np.arange(idx[k], idx[k + 1], b.connects.shape[1], dtype=np.int64)
+                                for k, b in enumerate(sorted(self.blocks, key=lambda b: b.first))] +
+                               [np.array([idx[-1]], dtype=np.int64)])
+        return index, graph
+
+
+def _first_touch_ids(keys):
+    """Rank of first occurrence: keys[k] -> index in order of first appearance (greedy connect creation)."""
+    uniq, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[order] = np.arange(len(uniq), dtype=np.int64)
+    return rank[inv], len(uniq)
+
+
+def flatten(nodes, element_blocks, porder, nstate):
+    """Number connects / equations of a conforming H1 mesh the way NeoPZ's AutoBuild does.
+
+    element_blocks: list of (topology, matid, elnodes[nel][ncorner]) in computational-element order.
+    """
+    nnodes = len(nodes)
+    # entity keys per (element, side) as (class, ab, c) triples, in element order
+    triples = []
+    shapes = []
+    for topo, _matid, elnodes in element_blocks:
+        sides = SIDES[topo]
+        en = np.asarray(elnodes, dtype=np.int64)
+        nel = en.shape[0]
+        t = np.empty((nel, len(sides), 3), dtype=np.int64)
+        for s, loc in enumerate(sides):
+            k = len(loc)
+            if k == 1:
+                t[:, s, 0] = 0
+                t[:, s, 1] = en[:, loc[0]]
+                t[:, s, 2] = -1
+            else:
+                srt = np.sort(en[:, loc], axis=1)
+                iscell = (k == NCORNER[topo] and DIM[topo] == 3)
+                t[:, s, 0] = 1 if k == 2 else (3 if iscell else 2)
+                t[:, s, 1] = srt[:, 0] * nnodes + srt[:, 1]
+                t[:, s, 2] = srt[:, 2] if k > 2 else -1
+        triples.append(t.reshape(-1, 3))
+        shapes.append((nel, len(sides)))
+    allt = np.concatenate(triples, axis=0)
+    # two-level packing: (class, ab) -> dense id, then (id, c) -> one int64
+    lvl1 = allt[:, 0] * (np.int64(nnodes) * nnodes) + allt[:, 1]
+    _, inv1 = np.unique(lvl1, return_inverse=True)
+    key = inv1.astype(np.int64) * (nnodes + 1) + (allt[:, 2] + 1)
+    conn_flat, nconnects = _first_touch_ids(key)
+
+    # block sizes: nshape(side) * nstate of the side that created the connect (same for all sharers)
+    size = np.zeros(nconnects, dtype=np.int64)
+    off = 0
+    for (topo, _m, _e), (nel, ns) in zip(element_blocks, shapes):
+        nsh = np.array([side_nshape(topo, loc, porder) for loc in SIDES[topo]], dtype=np.int64) * nstate
+        size[conn_flat[off:off + nel * ns]] = np.tile(nsh, nel)
+        off += nel * ns
+    pos = np.concatenate([[0], np.cumsum(size)[:-1]]).astype(np.int64)
+    neq = int(size.sum())
+
+    mesh = FlatMesh(porder=porder, nstate=nstate, nodes=np.ascontiguousarray(nodes, dtype=np.float64),
+                    block_pos=pos, block_size=size, neq=neq)
+    off = 0
+    first = 0
+    for (topo, matid, elnodes), (nel, ns) in zip(element_blocks, shapes):
+        conn = conn_flat[off:off + nel * ns].reshape(nel, ns)
+        off += nel * ns
+        # destination indices: connects with shape functions, in side order; idf fastest (pzelmat.cpp:45-59)
+        active = [s for s, loc in enumerate(SIDES[topo]) if side_nshape(topo, loc, porder) > 0]
+        d = pos[conn[:, active]]                                  # [nel][nshape]
+        dest = (d[:, :, None] + np.arange(nstate, dtype=np.int64)[None, None, :]).reshape(nel, -1)
+        mesh.blocks.append(ElementBlock(topology=topo, matid=matid, first=first,
+                                        elnodes=np.ascontiguousarray(elnodes, dtype=np.int32),
+                                        connects=conn, dest=np.ascontiguousarray(dest)))
+        first += nel
+    return mesh
+
+
+def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_matid=1,
+                  min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0):
+    """Nodes and element blocks of CreateGeoMeshOnGrid(3, minX, maxX, matids, {n,n,n}, type, createBoundEls=true).
+
+    n: divisions per direction (int or 3-tuple).  bc_matids = (zmin, ymin, xmin... ) in the reference's
+    argument order matids[1..6] = (Zmin, Xmin?, ...): see below.
+    """
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    min_x = np.asarray(min_x, dtype=np.float64)
+    max_x = np.asarray(max_x, dtype=np.float64)
+    ix, iy, iz = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    # node id = iz*(nx+1)*(ny+1) + iy*(nx+1) + ix  -> order arrays as [iz][iy][ix]
+    I = np.transpose(ix, (2, 1, 0)).reshape(-1)
+    J = np.transpose(iy, (2, 1, 0)).reshape(-1)
+    K = np.transpose(iz, (2, 1, 0)).reshape(-1)
+    nodes = np.empty((len(I), 3))
+    # fMinX + ((fMaxX-fMinX) * i)/nel   (Pre/TPZGenGrid3D.cpp:72-74)
+    nodes[:, 0] = min_x[0] + ((max_x[0] - min_x[0]) * I) / nx
+    nodes[:, 1] = min_x[1] + ((max_x[1] - min_x[1]) * J) / ny
+    nodes[:, 2] = min_x[2] + ((max_x[2] - min_x[2]) * K) / nz
+    if perturb != 0.0:
+        # the deterministic perturbation of oracle/refdriver.cpp: non-constant Jacobians
+        h = 1.0 / nx
+        ids = np.arange(len(nodes), dtype=np.float64)
+        for d in range(3):
+            nodes[:, d] += perturb * h * np.sin(2.0 * np.pi * ids / 97.0 + float(d))
+    sx, sy = 1, nx + 1
+    sz = (nx + 1) * (ny + 1)
+
+    ez, ey, ex = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ex, ey, ez = ex.reshape(-1), ey.reshape(-1), ez.reshape(-1)
+    first = ez * sz + ey * sy + ex
+    cube = np.stack([first, first + 1, first + 1 + sy, first + sy,
+                     first + sz, first + 1 + sz, first + 1 + sy + sz, first + sy + sz], axis=1)
+    blocks = []
+    if not tetrahedra:
+        blocks.append((capi.HEX, vol_matid, cube))
+    else:
+        perm = (ex + ey + ez) % 2
+        rows = np.arange(len(cube))
+
+        def cn(k, top=False):  # cubenode[(k+permut)%4 (+4)]
+            return cube[rows, (k + perm) % 4 + (4 if top else 0)]
+        t0 = np.stack([cn(0), cn(1), cn(3), cn(0, True)], axis=1)
+        t1 = np.stack([cn(1, True), cn(0, True), cn(2, True), cn(1)], axis=1)
+        t2 = np.stack([cn(2), cn(3), cn(1), cn(2, True)], axis=1)
+        t3 = np.stack([cn(3, True), cn(2, True), cn(0, True), cn(3)], axis=1)
+        t4 = np.stack([cn(0, True), cn(1), cn(3), cn(2, True)], axis=1)
+        tets = np.stack([t0, t1, t2, t3, t4], axis=1).reshape(-1, 4)
+        blocks.append((capi.TET, vol_matid, tets))
+
+    # boundary faces, BuildBoundaryElements(matIdZmin, matIdXmin, matIdYmin, matIdXmax, matIdYmax, matIdZmax)
+    # called with matids[1..6]; the loops use: z-faces (Zmin,Zmax), y-faces (Ymin,Ymax), x-faces (Xmin,Xmax)
+    m_zmin, m_xmin, m_ymin, m_xmax, m_ymax, m_zmax = bc_matids
+    face_topo = capi.TRI if tetrahedra else capi.QUAD
+
+    def emit(matid, faces):
+        if blocks and blocks[-1][0] == face_topo and blocks[-1][1] == matid:
+            blocks[-1] = (face_topo, matid, np.concatenate([blocks[-1][2], faces], axis=0))
+        else:
+            blocks.append((face_topo, matid, faces))
+
+    # top/bottom: iZ in {0, nz}; loops iY, iX
+    for izf, matid in ((0, m_zmin), (nz, m_zmax)):
+        fy, fx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+        fx, fy = fx.reshape(-1), fy.reshape(-1)
+        f = izf * sz + fy * sy + fx
+        if not tetrahedra:
+            faces = np.stack([f, f + 1, f + sy + 1, f + sy], axis=1)
+        else:
+            odd = ((fx + fy + izf) % 2) == 1
+            ta = np.stack([f, f + 1, f + sy + np.where(odd, 1, 0)], axis=1)
+            tb = np.stack([f + np.where(odd, 0, 1), f + sy, f + sy + 1], axis=1)
+            faces = np.stack([ta, tb], axis=1).reshape(-1, 3)
+        emit(matid, faces)
+    # left/right: for iZ: for iY in {0, ny}: for iX
+    per_z = []
+    for izf in range(nz):
+        for iyf, matid in ((0, m_ymin), (ny, m_ymax)):
+            fx = np.arange(nx)
+            f = izf * sz + iyf * sy + fx
+            cnt = fx + iyf + izf
+            if not tetrahedra:
+                faces = np.stack([f, f + 1, f + sz + 1, f + sz], axis=1)
+            else:
+                odd = (cnt % 2) == 1
+                ta = np.stack([f, f + 1, f + sz + np.where(odd, 1, 0)], axis=1)
+                tb = np.stack([f + np.where(odd, 0, 1), f + sz + 1, f + sz], axis=1)
+                faces = np.stack([ta, tb], axis=1).reshape(-1, 3)
+            per_z.append((matid, faces))
+    for matid, faces in per_z:
+        emit(matid, faces)
+    # front/back: for iZ: for iY: for iX in {0, nx}
+    fz, fy = np.meshgrid(np.arange(nz), np.arange(ny), indexing="ij")
+    fz, fy = fz.reshape(-1), fy.reshape(-1)
+    pieces = []
+    for ixf, matid in ((0, m_xmin), (nx, m_xmax)):
+        f = fz * sz + fy * sy + ixf
+        cnt = ixf + fy + fz
+        if not tetrahedra:
+            faces = np.stack([f, f + sy, f + sz + sy, f + sz], axis=1)
+        else:
+            odd = (cnt % 2) == 1
+            ta = np.stack([f, f + sy, f + sz + np.where(odd, sy, 0)], axis=1)
+            tb = np.stack([f + np.where(odd, 0, sy), f + sz + sy, f + sz], axis=1)
+            faces = np.stack([ta, tb], axis=1)  # [nface][2][3]
+        pieces.append((matid, faces))
+    # interleave: for each (iZ,iY): xmin face(s) then xmax face(s)
+    (m0, f0), (m1, f1) = pieces
+    if m0 == m1:
+        inter = np.stack([f0, f1], axis=1)
+        emit(m0, inter.reshape(-1, f0.shape[-1]))
+    else:
+        k = f0.shape[0]
+        for r in range(k):
+            emit(m0, f0[r].reshape(-1, f0.shape[-1]))
+            emit(m1, f1[r].reshape(-1, f1.shape[-1]))
+    return nodes, blocks
+
+
+def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0):
+    nodes, blocks = grid_elements(n, tetrahedra=tetrahedra, bc_matids=bc_matids, perturb=perturb)
+    return flatten(nodes, blocks, porder, nstate)

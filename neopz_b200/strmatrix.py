@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference's struct-matrix interface for the B200 strategy.
+
+Names and call order follow NeoPZ so that the parity tests read like the reference's own
+(UnitTest_PZ/TestStruct/StructMatrixUnitTest.cpp): build materials, build the struct matrix on a
+mesh, Create() the CSR pattern, Assemble() into it, or CreateAssemble() in one go
+(StrMatrix/TPZStrMatParInterface.cpp:6-26).  The mesh is a gridmesh.FlatMesh (what the C++ strategy
+csrc/neopz/TPZStructMatrixB200.cpp extracts from a TPZCompMesh); all arithmetic happens in the CUDA
+library behind the C ABI (include/b200asm.h).  No CPU fallback.
+"""
+import os
+
+import numpy as np
+
+from . import capi
+from .gridmesh import DIM, FlatMesh
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+# ---------------------------------------------------------------------------------------------
+# materials (constants exactly as the reference derives them)
+# ---------------------------------------------------------------------------------------------
+class TPZMatPoisson:
+    """Material/Poisson/TPZMatPoisson.h: -scale*Laplace(u) = f.  nstate 1."""
+    nstate = 1
+
+    def __init__(self, matid, dim=3):
+        self.id, self.dim = matid, dim
+        self.fScale = 1.0
+        self.force = 0.0                     # no forcing function set -> 0 (TPZMatPoisson.cpp:24-27)
+        # TPZMaterial::fBigNumber, Material/TPZMaterial.h:125: pow(10, max_digits10)*2/3
+        self.fBigNumber = (10.0 ** 17) * 2 / 3
+
+    def SetScaleFactor(self, s):
+        self.fScale = float(s)
+
+    def SetForcingFunction(self, value):
+        """Constant forcing function (the host evaluates callbacks; a constant needs no table)."""
+        self.force = float(value)
+
+    def CreateBC(self, matid, bctype, val1, val2):
+        return TPZBndCond(self, matid, bctype, val1, val2)
+
+    def coef(self):
+        return [self.fScale, self.force]
+
+    kind = capi.POISSON
+
+
+class TPZElasticity3D:
+    """Material/Elasticity/TPZElasticity3D.h: constants of SetC (:183-188).  nstate 3."""
+    nstate = 3
+    kind = capi.ELASTICITY3D
+
+    def __init__(self, matid, E, poisson, force, prestress=(0.0, 0.0, 0.0)):
+        self.id = matid
+        self.fE, self.fPoisson = float(E), float(poisson)
+        self.fForce = [float(x) for x in force]
+        self.fPreStress = [float(x) for x in prestress]
+        nu = self.fPoisson
+        self.C1 = self.fE / (2. + 2. * nu)
+        self.C2 = self.fE * nu / (-1. + nu + 2. * nu * nu)
+        self.C3 = self.fE * (nu - 1.) / (-1. + nu + 2. * nu * nu)
+
+    def CreateBC(self, matid, bctype, val1, val2):
+        return TPZBndCond(self, matid, bctype, val1, val2)
+
+    def coef(self):
+        return [self.C1, self.C2, self.C3] + self.fForce + self.fPreStress
+
+
+class TPZBndCond:
+    """TPZBndCondT: type 0 Dirichlet (penalty), 1 Neumann, 2 mixed (Elasticity3D only)."""
+    kind = capi.BC
+
+    def __init__(self, material, matid, bctype, val1, val2):
+        self.material, self.id, self.type = material, matid, int(bctype)
+        self.nstate = material.nstate
+        self.val1 = np.zeros((3, 3))
+        v1 = np.atleast_2d(np.asarray(val1, dtype=np.float64))
+        self.val1[: v1.shape[0], : v1.shape[1]] = v1
+        self.val2 = np.zeros(3)
+        v2 = np.atleast_1d(np.asarray(val2, dtype=np.float64))
+        self.val2[: len(v2)] = v2
+
+    def coef(self):
+        """(M, v) of  ek += M[a][b] phi_i phi_j w ,  ef += v[a] phi_i w  (include/b200asm.h)."""
+        ns = self.nstate
+        M = np.zeros((3, 3))
+        v = np.zeros(3)
+        if isinstance(self.material, TPZMatPoisson):
+            big = self.material.fBigNumber
+            if self.type == 0:      # TPZMatPoisson.cpp:79-90
+                M[0, 0] = big
+                v[0] = big * self.val2[0]
+            elif self.type == 1:    # :93-100
+                v[0] = self.val2[0] * self.material.fScale
+            else:
+                raise ValueError("TPZMatPoisson: boundary condition type %d not supported" % self.type)
+        else:
+            big = 1.e12             # TPZElasticity3D.cpp:630
+            if self.type == 0:      # :663-675
+                M[:ns, :ns] = np.eye(ns) * big
+                v[:ns] = big * self.val2[:ns]
+            elif self.type == 1:    # :677-683
+                v[:ns] = self.val2[:ns]
+            elif self.type == 2:    # :684-697
+                M[:, :] = self.val1
+                v[:ns] = self.val2[:ns]
+            else:
+                raise ValueError("TPZElasticity3D: boundary condition type %d not supported" % self.type)
+        return M.reshape(-1).tolist() + v.tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+# integration rules + shape tables per topology / order
+# ---------------------------------------------------------------------------------------------
+def element_tables(topology, porder):
+    """(qpts, qw, phi, dphi) of the rule of order 2p the reference attaches to an element
+    (Mesh/pzelctemp.cpp:35-47, Material/TPZMatSingleSpace.cpp:61-72)."""
+    order = 2 * porder
+    if topology in (capi.HEX, capi.QUAD):
+        qpts, qw = capi.tensor_rule(topology, order)
+    else:
+        z = np.load(os.path.join(_DATA, "simplex_rules.npz"))
+        tag = "tet" if topology == capi.TET else "tri"
+        qpts, qw = z[f"{tag}_order{order}_pts"], z[f"{tag}_order{order}_w"]
+    phi, dphi = capi.shape_tables(topology, porder, qpts)
+    return qpts, qw, phi, dphi
+
+
+# ---------------------------------------------------------------------------------------------
+# the struct matrix
+# ---------------------------------------------------------------------------------------------
+class TPZStructMatrixB200:
+    """TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>> (symmetric=True) or
+    TPZSpStructMatrix<...> (symmetric=False) on a flattened mesh."""
+
+    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0):
+        self.mesh = mesh
+        self.materials = {m.id: m for m in (materials.values() if isinstance(materials, dict) else materials)}
+        self.symmetric = bool(symmetric)
+        self.fNumThreads = nthreads
+        self.ctx = capi.Context(device)
+        self.ia = self.ja = None
+        self._flattened = False
+        self.group_of_block = []
+
+    def SetNumThreads(self, n):
+        self.fNumThreads = n
+
+    # -- flatten: one b200asm_group per element block --------------------------------------------
+    def _flatten(self):
+        if self._flattened:
+            return
+        mesh = self.mesh
+        self.ctx.set_nodes(mesh.nodes)
+        for b in mesh.blocks:
+            mat = self.materials.get(b.matid)
+            if mat is None:
+                raise KeyError(f"no material with id {b.matid}")
+            if mat.nstate != mesh.nstate:
+                raise ValueError("material nstate does not match the mesh")
+            if (DIM[b.topology] == 3) == (mat.kind == capi.BC):
+                raise ValueError(f"material {b.matid}: volume/boundary kind does not match element dimension")
+            qpts, qw, phi, dphi = element_tables(b.topology, mesh.porder)
+            gid = self.ctx.add_group(b.topology, mesh.porder, mat.kind, mat.nstate, b.elnodes, b.dest,
+                                     qpts, qw, phi, dphi, mat.coef())
+            self.group_of_block.append(gid)
+        self._flattened = True
+
+    # -- TPZStructMatrix::Create -------------------------------------------------------------------
+    def Create(self):
+        """CSR pattern, bit-exact with the reference's Create() (TPZSSpStructMatrix.cpp:31-193)."""
+        idx, graph = self.mesh.element_graph()
+        self.ia, self.ja = capi.build_pattern(self.symmetric, idx, graph, self.mesh.block_pos,
+                                              self.mesh.block_size, self.fNumThreads)
+        self._flatten()
+        self.ctx.set_pattern(self.ia, self.ja, self.symmetric)
+        return self.ia, self.ja
+
+    def SetPattern(self, ia, ja):
+        """Use a pattern created elsewhere (e.g. by the reference's own Create())."""
+        self.ia = np.ascontiguousarray(ia, dtype=np.int64)
+        self.ja = np.ascontiguousarray(ja, dtype=np.int64)
+        self._flatten()
+        self.ctx.set_pattern(self.ia, self.ja, self.symmetric)
+
+    # -- TPZStrMatParInterface::Assemble(stiffness, rhs) ---------------------------------------------
+    def Assemble(self, a=None, rhs=None):
+        """Zero + assemble into the created pattern; returns (a, rhs) host arrays."""
+        if self.ia is None:
+            raise RuntimeError("Assemble: call Create() first")
+        if a is None:
+            a = np.empty(len(self.ja))
+        if rhs is None:
+            rhs = np.empty(self.mesh.neq)
+        self.ctx.assemble(a, rhs)
+        return a, rhs
+
+    def CreateAssemble(self):
+        ia, ja = self.Create()
+        a, rhs = self.Assemble()
+        return ia, ja, a, rhs
+
+    def UpdateMaterials(self):
+        for b, gid in zip(self.mesh.blocks, self.group_of_block):
+            self.ctx.set_group_coef(gid, self.materials[b.matid].coef())

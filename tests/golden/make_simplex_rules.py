@@ -1,0 +1,24 @@
+"""Extracts the reference's simplex quadrature tables (Integral/tpzintrulet.cpp, tpzintrulet3d.cpp —
+published Dunavant / Zhang-Cui-Liu style tables, pure data) for the orders the hot path uses
+(order 2p, p in {1,2}) from the golden fixtures (which oracle/_ref/refdriver read through
+TPZIntPoints::Point) into neopz_b200/data/simplex_rules.npz, the table the standalone host ships.
+The NeoPZ drop-in strategy does not use this file: it reads the rules from the live TPZIntPoints."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from tests import golden_util as gu  # noqa: E402
+
+out = {}
+for name, p in (("tet_p1_poisson_n2_pert", 1), ("tet_p2_poisson_n2_pert", 2)):
+    g = gu.load(name)
+    for tag in ("tet", "tri"):
+        out[f"{tag}_order{2 * p}_pts"] = g[f"rule_{tag}_pts"]
+        out[f"{tag}_order{2 * p}_w"] = g[f"rule_{tag}_w"]
+path = os.path.join(ROOT, "neopz_b200", "data", "simplex_rules.npz")
+np.savez(path, **out)
+print({k: v.shape for k, v in out.items()})

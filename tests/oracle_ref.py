@@ -1,0 +1,60 @@
+"""Run the oracle (oracle/oracle.c, bit-identical to the reference on the golden fixtures) on a
+neopz_b200.gridmesh.FlatMesh with neopz_b200.strmatrix materials.  Checker only."""
+import os
+
+import numpy as np
+
+from oracle import oracle as orc
+
+_SIMPLEX = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neopz_b200", "data",
+                        "simplex_rules.npz")
+
+
+def _rule(topo, p):
+    if topo in (orc.HEX, orc.QUAD):
+        return orc.rule(topo, 2 * p)
+    z = np.load(_SIMPLEX)  # tables of the reference (tests/golden/make_simplex_rules.py)
+    tag = "tet" if topo == orc.TET else "tri"
+    return z[f"{tag}_order{2 * p}_pts"], z[f"{tag}_order{2 * p}_w"]
+
+
+def _mat_vector(mat):
+    """oracle convention (oracle.c orc_elem_t.mat) from a strmatrix material object."""
+    from neopz_b200 import strmatrix as sm
+    m = np.zeros(16)
+    if isinstance(mat, sm.TPZMatPoisson):
+        m[0], m[1] = mat.fScale, mat.force
+        return orc.POISSON, 0, m
+    if isinstance(mat, sm.TPZElasticity3D):
+        m[0:3] = orc.elast_constants(mat.fE, mat.fPoisson)
+        m[3:6] = mat.fForce
+        m[6:9] = mat.fPreStress
+        return orc.ELAST3D, 0, m
+    base = mat.material
+    m[1:10] = mat.val1.reshape(-1)
+    m[10:13] = mat.val2
+    if isinstance(base, sm.TPZMatPoisson):
+        m[0] = base.fBigNumber
+        m[13] = base.fScale
+        return orc.POISSON_BC, mat.type, m
+    m[0] = 1.e12
+    return orc.ELAST3D_BC, mat.type, m
+
+
+def oracle_assemble(mesh, materials, symmetric, ia, ja):
+    """Serial reference-order assembly of the whole mesh; returns (a, rhs)."""
+    elems, keep, dest_parts = [], [], []
+    for b in sorted(mesh.blocks, key=lambda b: b.first):
+        kind, bctype, mvec = _mat_vector(materials[b.matid])
+        qpts, qw = _rule(b.topology, mesh.porder)
+        coords = mesh.nodes[b.elnodes]
+        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw)
+        elems.append(arr)
+        keep.append(k)
+        dest_parts.append(b.dest)
+    ptr = [0]
+    for d in dest_parts:
+        nel, nd = d.shape
+        ptr.extend((ptr[-1] + nd * np.arange(1, nel + 1)).tolist())
+    dest = np.concatenate([d.reshape(-1) for d in dest_parts])
+    return orc.assemble(symmetric, elems, np.array(ptr, dtype=np.int64), dest, ia, ja, mesh.neq)
