@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 assembly path (BASELINE.json metric).
+
+A "step" = one full assembly (zero A and rhs, element matrices of every element, scatter-add into the
+CSR values and the load vector) of the configured mesh, on a pattern created once — the same quantity
+the reference times as the second TPZLinearAnalysis::Assemble() (Analysis/TPZLinearAnalysis.cpp:73-77).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm   (CUDA, through the C ABI)
+    python bench.py --impl reference --steps 3 --warmup 1     # reference (NeoPZ TPZStructMatrixOR on the host cores)
+
+Default workload = BASELINE.json configs[1]: 3D Poisson, H1 p=2, 128^3 hexahedra (~17M DOF), one B200.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per volume element, SURVEY.md 8(d) (reference arithmetic, full ek, mul/add = 1 flop)
+F_EL = {("hex", 1, "poisson"): 6.4e3, ("hex", 2, "poisson"): 158e3, ("tet", 2, "elasticity"): 85.7e3,
+        ("hex", 2, "elasticity"): 1.149e6, ("hex", 1, "elasticity"): None, ("tet", 2, "poisson"): None}
+B_EL = {("hex", 1, "poisson"): 0.49e3, ("hex", 2, "poisson"): 3.98e3, ("tet", 2, "elasticity"): 3.63e3,
+        ("hex", 2, "elasticity"): 32.8e3}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="grid divisions per direction (per GPU)")
+    ap.add_argument("--p", type=int, default=2)
+    ap.add_argument("--phys", default="poisson", choices=["poisson", "elasticity"])
+    ap.add_argument("--topo", default="hex", choices=["hex", "tet"])
+    ap.add_argument("--cpu-n", type=int, default=0, help="grid size of the bounded CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a, n=None):
+    n = n or a.n
+    return f"3D {a.phys} H1 p={a.p} {a.topo} {n}^3 grid, sym CSR (TPZSSpStructMatrix), Dirichlet on all faces"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the UNMODIFIED reference (oracle/_ref, built from /root/reference by
+# oracle/Makefile.ref) timed on this box's host cores, bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_n(a):
+    if a.cpu_n:
+        return a.cpu_n
+    # ~10-30 s of CPU work including mesh + Create(): sized from the survey's per-element costs
+    if a.phys == "poisson":
+        return {1: 48, 2: 32}.get(a.p, 8) if a.topo == "hex" else 20
+    return {1: 24, 2: 14}.get(a.p, 6) if a.topo == "hex" else 14
+
+
+def run_reference(a, steps, warmup):
+    drv = os.path.join(ROOT, "oracle", "_ref", "refdriver")
+    cores = os.cpu_count() or 1
+    n = cpu_sample_n(a)
+    if os.path.exists(drv):
+        reps = max(1, steps)
+        out = subprocess.run([drv, "time", str(n), str(a.p), "1" if a.phys == "elasticity" else "0",
+                              "1" if a.topo == "tet" else "0", str(cores), str(reps + warmup)],
+                             capture_output=True, text=True, check=True).stdout
+        line = [l for l in out.splitlines() if l.startswith("{")][-1]
+        r = json.loads(line)
+        sec = r["assemble_s_mean"]
+        return {"value": r["vol_elements"] / sec, "dof_per_s": r["neq"] / sec, "unit": "elements/s", "cores": cores,
+                "kind": "reference", "ms_per_step": sec * 1e3,
+                "sample": f"{workload_name(a, n)}: {r['vol_elements']} volume elements, {r['neq']} DOF, "
+                          f"TPZStructMatrixOR SetNumThreads({cores}), mean of {reps + warmup} re-assemblies"}
+    # fallback: the oracle port (scalar, 1 core)
+    import numpy as np
+    from neopz_b200 import gridmesh
+    from tests.oracle_ref import oracle_assemble
+    from tests.test_gpu_parity import materials_for
+    from neopz_b200 import capi
+    n = max(4, n // 2)
+    mesh = gridmesh.grid_mesh(n, a.p, 3 if a.phys == "elasticity" else 1, tetrahedra=a.topo == "tet")
+    mats = materials_for(1 if a.phys == "elasticity" else 0)
+    idx, graph = mesh.element_graph()
+    ia, ja = capi.build_pattern(True, idx, graph, mesh.block_pos, mesh.block_size, 0)
+    t0 = time.time()
+    oracle_assemble(mesh, mats, True, ia, ja)
+    sec = time.time() - t0
+    nvol = len(mesh.blocks[0].elnodes)
+    return {"value": nvol / sec, "dof_per_s": mesh.neq / sec, "unit": "elements/s", "cores": 1, "kind": "port",
+            "ms_per_step": sec * 1e3, "sample": f"{workload_name(a, n)}: oracle/oracle.c serial port, {nvol} elements"}
+
+
+# ------------------------------------------------------------------------------------------------
+def clocks_sampler(stop, samples, device):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(device)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                samples.append([x.strip() for x in out.split(",")])
+        except Exception:
+            pass
+        stop.wait(0.1)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(float(s[0]) for s in samples)
+    reasons = set()
+    for s in samples:
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "power_w_max": max(float(s[2]) for s in samples),
+            "reasons": sorted(reasons), "samples": len(samples)}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference(a, a.steps, a.warmup)
+        line = {"impl": "reference", "metric": "assembled volume elements/s (Assemble on a created pattern)",
+                "value": r["value"], "unit": "elements/s", "dof_per_s": r["dof_per_s"], "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": "elements/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from neopz_b200 import gridmesh, strmatrix as sm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the assembly engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- one-off setup (reported, not timed as assembly): mesh flatten, pattern, scatter maps ------------------
+    t0 = time.time()
+    ns = 3 if a.phys == "elasticity" else 1
+    mesh = gridmesh.grid_mesh(a.n, a.p, ns, tetrahedra=a.topo == "tet", perturb=0.1)
+    t_flat = time.time() - t0
+    if a.phys == "poisson":
+        mat = sm.TPZMatPoisson(1, 3)
+        mat.SetForcingFunction(1.0)
+        mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.0])}
+    else:
+        mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
+        mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank)
+    stream = torch.cuda.current_stream()
+    strmat.ctx.set_stream(stream.cuda_stream)
+    t0 = time.time()
+    ia, ja = strmat.Create()
+    torch.cuda.synchronize()
+    t_create = time.time() - t0
+    nvol = len(mesh.blocks[0].elnodes)
+    neq, nnz = mesh.neq, len(ja)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------
+    for _ in range(max(3, a.warmup)):
+        strmat.ctx.assemble_async()
+    barrier()
+    k0 = strmat.ctx.counters()[0]
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+    if rank == 0:
+        th.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_all0.record(stream)
+    for s0, s1 in evs:
+        s0.record(stream)
+        strmat.ctx.assemble_async()
+        s1.record(stream)
+    e_all1.record(stream)
+    barrier()
+    stop.set()
+    total_ms = e_all0.elapsed_time(e_all1)
+    step_ms = [s0.elapsed_time(s1) for s0, s1 in evs]
+    launches = strmat.ctx.counters()[0] - k0
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / a.steps
+    value = nvol * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (H2D of the nodes, D2H of A and rhs, every step) ----
+    e2e = None
+    if not a.no_e2e:
+        a_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        r_host = torch.empty(neq, dtype=torch.float64).pin_memory()
+        x_host = torch.from_numpy(mesh.nodes.copy()).pin_memory()
+        a_np, r_np, x_np = a_host.numpy(), r_host.numpy(), x_host.numpy()
+        ksteps = max(2, min(a.steps, 5))
+        strmat.ctx.set_nodes(x_np)
+        strmat.ctx.assemble(a_np, r_np)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            strmat.ctx.set_nodes(x_np)          # H2D: node coordinates (the geometry input of the step)
+            strmat.ctx.assemble(a_np, r_np)     # kernels + D2H of the CSR values and the load vector
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / ksteps
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": nvol * world / e2e_s, "unit": "elements/s", "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes + r_np.nbytes),
+               "steps": ksteps, "note": "b200asm_set_nodes + b200asm_assemble(a_host, rhs_host), pinned host buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (assemble_volume_kernel) ------------------------------------
+    key = (a.topo, a.p, a.phys)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp64 = {}
+    try:
+        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    fp64_peak = max(fp64.get("dfma_tflops", 0.0), fp64.get("dmma_tflops", 0.0)) or 37.0
+    kernel_ms = float(np.median(step_ms))  # the volume kernel is >95% of the step (profiles/ launch list)
+    roofline = None
+    if F_EL.get(key):
+        flops = F_EL[key] * nvol
+        byts = B_EL[key] * nvol
+        ach_tf = flops / (kernel_ms * 1e-3) / 1e12
+        ach_gb = byts / (kernel_ms * 1e-3) / 1e9
+        t_fp, t_hbm = flops / (fp64_peak * 1e12), byts / (hbm_peak * 1e9)
+        if t_fp >= t_hbm:
+            roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                        "peak_source": "measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json): "
+                                       "MEASURED_PEAKS.json carries no FP64 figure"}
+        else:
+            roofline = {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+        roofline.update({"traffic": None, "algorithmic_flops_per_element": F_EL[key], "algorithmic_bytes_per_element": B_EL[key],
+                         "hbm_GBps_algorithmic": ach_gb, "hbm_peak_GBps": hbm_peak,
+                         "kernel": "assemble_volume_kernel", "kernel_ms": kernel_ms})
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            r = run_reference(a, 3, 1)
+            cpu = {"value": r["value"], "unit": "elements/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                   "dof_per_s": r["dof_per_s"]}
+        except Exception as ex:  # the baseline is reported, never the product path
+            cpu = {"value": None, "unit": "elements/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(ex)[:200]}
+
+    line = {"metric": "assembled volume elements/s (Assemble on a created pattern)", "value": value, "unit": "elements/s",
+            "dof_per_s": neq * world / (ms_per_step * 1e-3),
+            "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
+                       "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
+                       "perturbed_nodes": True, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": summarize_clocks(samples), "step_ms": step_ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

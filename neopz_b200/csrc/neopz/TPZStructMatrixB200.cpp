@@ -1,0 +1,477 @@
+// TPZStructMatrixB200 — NeoPZ-side host code of the B200 assembly strategy (see the header).
+//
+// Everything here runs once per mesh (flatten) or once per Assemble() (node coordinates, material
+// constants, one C-ABI call); the arithmetic of CalcStiff / Contribute / AddKel / AddFel happens in the
+// CUDA library (neopz_b200/csrc/b200asm.cu).
+#include "TPZStructMatrixB200.h"
+
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "Elasticity/TPZElasticity3D.h"
+#include "Poisson/TPZMatPoisson.h"
+#include "TPZBndCondT.h"
+#include "TPZCompElH1.h"
+#include "TPZFMatrixRef.h"
+#include "TPZMatLoadCases.h"
+#include "TPZMaterial.h"
+#include "TPZShapeData.h"
+#include "TPZShapeH1.h"
+#include "TPZStructMatrix.h"
+#include "pzcmesh.h"
+#include "pzfmatrix.h"
+#include "pzgmesh.h"
+#include "pzgnode.h"
+#include "pzinterpolationspace.h"
+#include "pzshapecube.h"
+#include "pzshapequad.h"
+#include "pzshapetetra.h"
+#include "pzshapetriang.h"
+#include "pzsysmp.h"
+#include "pzysmp.h"
+
+#include "../../../include/b200asm.h"
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
+
+[[noreturn]] void Fatal(const std::string &msg) {
+    PZError << "TPZStructMatrixB200: " << msg << std::endl;
+    DebugStop();
+    std::abort();
+}
+
+// protected constants of TPZElasticity3D (Material/Elasticity/TPZElasticity3D.h:225-248)
+struct ElastAccess : public TPZElasticity3D {
+    using TPZElasticity3D::C1;
+    using TPZElasticity3D::C2;
+    using TPZElasticity3D::C3;
+    using TPZElasticity3D::fForce;
+    using TPZElasticity3D::fPreStress;
+};
+
+struct GroupKey {
+    int topology, matid, porder;
+    bool operator<(const GroupKey &o) const { return std::tie(topology, matid, porder) < std::tie(o.topology, o.matid, o.porder); }
+};
+
+struct HostGroup {
+    b200asm_group meta{};
+    TPZMaterial *material = nullptr;
+    std::vector<int32_t> elnodes;
+    std::vector<int64_t> dest;
+    std::vector<double> qpts, qw, phi, dphi, force;
+    std::vector<TPZCompEl *> elements;
+    bool has_forcing = false;
+};
+
+int TopologyOf(MElementType t) {
+    switch (t) {
+        case ECube: return B200ASM_HEX;
+        case ETetraedro: return B200ASM_TET;
+        case EQuadrilateral: return B200ASM_QUAD;
+        case ETriangle: return B200ASM_TRI;
+        default: return -1;
+    }
+}
+
+template <class TSHAPE>
+void ShapeTables(TPZCompEl *cel, int porder, HostGroup &g) {
+    // integration rule and shape tables through the reference's own objects
+    auto *intel = dynamic_cast<TPZInterpolationSpace *>(cel);
+    TPZGeoEl *gel = cel->Reference();
+    const int nc = TSHAPE::NCornerNodes, ns = TSHAPE::NSides, dim = TSHAPE::Dimension;
+    TPZManVector<int64_t, 8> ids(nc);
+    TPZManVector<int, 27> orders(ns - nc, porder);
+    for (int i = 0; i < nc; i++) ids[i] = gel->NodeIndex(i);
+    TPZShapeData sd;
+    TPZShapeH1<TSHAPE>::Initialize(ids, orders, sd);
+    const TPZIntPoints &rule = intel->GetIntegrationRule();
+    const int nq = rule.NPoints();
+    const int nshape = sd.fPhi.Rows();
+    g.qpts.resize((size_t)nq * dim);
+    g.qw.resize(nq);
+    g.phi.resize((size_t)nq * nshape);
+    g.dphi.resize((size_t)nq * dim * nshape);
+    TPZManVector<REAL, 3> pt(dim);
+    for (int q = 0; q < nq; q++) {
+        REAL w;
+        rule.Point(q, pt, w);
+        g.qw[q] = w;
+        for (int d = 0; d < dim; d++) g.qpts[(size_t)q * dim + d] = pt[d];
+        TPZShapeH1<TSHAPE>::Shape(pt, sd);
+        for (int i = 0; i < nshape; i++) {
+            g.phi[(size_t)q * nshape + i] = sd.fPhi(i, 0);
+            for (int d = 0; d < dim; d++) g.dphi[((size_t)q * dim + d) * nshape + i] = sd.fDPhi(d, i);
+        }
+    }
+    g.meta.nqp = nq;
+    g.meta.nshape = nshape;
+}
+
+}  // namespace
+
+struct TPZB200AssemblyCache {
+    b200asm_ctx *ctx = nullptr;
+    TPZCompMesh *mesh = nullptr;
+    int64_t nelem = -1, neq = -1, nconnects = -1, nnz = -1;
+    int symmetric = -1;
+    bool pattern_set = false;
+    std::vector<HostGroup> groups;
+    double flatten_ms = 0, pattern_ms = 0, assemble_ms = 0;
+    ~TPZB200AssemblyCache() {
+        if (ctx) b200asm_destroy(ctx);
+    }
+};
+
+namespace {
+
+void Check(TPZB200AssemblyCache &c, int rc, const char *what) {
+    if (rc < 0) Fatal(std::string(what) + " failed: " + b200asm_last_error(c.ctx));
+}
+
+// material constants of a group, re-read at every Assemble (they may change between assemblies)
+void FillCoef(HostGroup &g) {
+    double *coef = g.meta.coef;
+    std::memset(coef, 0, sizeof(double) * 16);
+    TPZMaterial *mat = g.material;
+    if (auto *bc = dynamic_cast<TPZBndCondT<STATE> *>(mat)) {
+        if (bc->HasForcingFunctionBC()) Fatal("boundary conditions with a forcing function are not supported yet");
+        TPZMaterial *vol = bc->Material();
+        const int type = bc->Type();
+        const TPZFMatrix<STATE> &v1 = bc->Val1();
+        const TPZVec<STATE> &v2 = bc->Val2();
+        if (auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(vol)) {
+            const double big = pois->BigNumber();
+            if (type == 0) {  // Material/Poisson/TPZMatPoisson.cpp:79-90
+                coef[0] = big;
+                coef[9] = big * v2[0];
+            } else if (type == 1) {  // :93-100
+                coef[9] = v2[0] * pois->ScaleFactor();
+            } else {
+                Fatal("TPZMatPoisson boundary condition type " + std::to_string(type) + " is not supported");
+            }
+        } else if (dynamic_cast<TPZElasticity3D *>(vol)) {
+            const double big = 1.e12;  // Material/Elasticity/TPZElasticity3D.cpp:630
+            if (type == 0) {
+                for (int a = 0; a < 3; a++) {
+                    coef[a * 3 + a] = big;
+                    coef[9 + a] = big * v2[a];
+                }
+            } else if (type == 1) {
+                for (int a = 0; a < 3; a++) coef[9 + a] = v2[a];
+            } else if (type == 2) {
+                for (int a = 0; a < 3; a++) {
+                    for (int b = 0; b < 3; b++) coef[a * 3 + b] = v1.GetVal(a, b);
+                    coef[9 + a] = v2[a];
+                }
+            } else {
+                Fatal("TPZElasticity3D boundary condition type " + std::to_string(type) + " is not supported");
+            }
+        } else {
+            Fatal("boundary condition of an unsupported material");
+        }
+        return;
+    }
+    if (auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(mat)) {
+        coef[0] = pois->ScaleFactor();
+        coef[1] = 0.0;  // the source comes from the forcing-function table (or is absent)
+        return;
+    }
+    if (auto *el = dynamic_cast<TPZElasticity3D *>(mat)) {
+        auto *acc = static_cast<ElastAccess *>(el);
+        coef[0] = acc->C1;
+        coef[1] = acc->C2;
+        coef[2] = acc->C3;
+        for (int k = 0; k < 3; k++) {
+            coef[3 + k] = acc->fForce[k];
+            coef[6 + k] = acc->fPreStress[k];
+        }
+        return;
+    }
+    Fatal("unsupported material (TPZMatPoisson<STATE>, TPZElasticity3D and their TPZBndCondT only)");
+}
+
+// forcing std::function evaluated on the host at every integration point (Material/TPZMatTypes.h:15-19)
+void FillForce(HostGroup &g) {
+    g.has_forcing = false;
+    g.meta.force = nullptr;
+    const int ns = g.meta.nstate;
+    const int dim = (g.meta.topology == B200ASM_HEX || g.meta.topology == B200ASM_TET) ? 3 : 2;
+    if (dim != 3) return;
+    auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(g.material);
+    auto *el = dynamic_cast<TPZElasticity3D *>(g.material);
+    const bool hasf = pois ? pois->HasForcingFunction() : (el ? el->HasForcingFunction() : false);
+    if (!hasf) return;
+    const int nq = g.meta.nqp;
+    g.force.assign((size_t)g.meta.nel * nq * ns, 0.0);
+    TPZManVector<REAL, 3> qsi(3), x(3);
+    for (int64_t e = 0; e < g.meta.nel; e++) {
+        TPZGeoEl *gel = g.elements[e]->Reference();
+        for (int q = 0; q < nq; q++) {
+            for (int d = 0; d < 3; d++) qsi[d] = g.qpts[(size_t)q * 3 + d];
+            gel->X(qsi, x);
+            TPZManVector<STATE, 3> f(ns, 0.);
+            if (pois) {
+                pois->ForcingFunction()(x, f);
+            } else {
+                auto *acc = static_cast<ElastAccess *>(el);
+                for (int k = 0; k < 3; k++) f[k] = acc->fForce[k];  // locForce(fForce) then the callback
+                el->ForcingFunction()(x, f);
+            }
+            for (int k = 0; k < ns; k++) g.force[((size_t)e * nq + q) * ns + k] = f[k];
+        }
+    }
+    g.has_forcing = true;
+    g.meta.force = g.force.data();
+}
+
+void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
+    TPZCompMesh *cmesh = strmat->Mesh();
+    c.groups.clear();
+    std::map<GroupKey, size_t> index;
+    const int64_t nel = cmesh->NElements();
+    for (int64_t iel = 0; iel < nel; iel++) {
+        TPZCompEl *cel = cmesh->Element(iel);
+        if (!cel) continue;
+        TPZMaterial *mat = cel->Material();
+        if (!mat) continue;  // the reference skips elements without material too
+        if (!strmat->ShouldCompute(mat->Id())) continue;  // TPZStructMatrix::SetMaterialIds filter
+        TPZGeoEl *gel = cel->Reference();
+        if (!gel) Fatal("computational element without geometric reference");
+        const int topo = TopologyOf(gel->Type());
+        const bool h1 = dynamic_cast<TPZCompElH1<pzshape::TPZShapeCube> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTetra> *>(cel) ||
+                        dynamic_cast<TPZCompElH1<pzshape::TPZShapeQuad> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTriang> *>(cel);
+        if (topo < 0 || !h1) Fatal("element " + std::to_string(iel) + " is not an H1 hexahedron/tetrahedron/quadrilateral/triangle");
+        if (!gel->IsLinearMapping()) Fatal("element " + std::to_string(iel) + " has a non-(multi)linear geometric map");
+        // uniform order, no constraints
+        const int ncon = cel->NConnects();
+        const int ncorner = gel->NCornerNodes();
+        int porder = -1;
+        for (int i = 0; i < ncon; i++) {
+            TPZConnect &con = cel->Connect(i);
+            if (con.HasDependency() || con.IsCondensed()) Fatal("hanging nodes / condensed connects are not supported");
+            if (i >= ncorner) {
+                if (porder < 0) porder = con.Order();
+                if (con.Order() != porder) Fatal("non-uniform polynomial order inside an element is not supported");
+            }
+        }
+        if (porder < 1 || porder > 2) Fatal("polynomial order " + std::to_string(porder) + " is not supported yet (p in {1,2})");
+        const GroupKey key{topo, mat->Id(), porder};
+        auto it = index.find(key);
+        if (it == index.end()) {
+            it = index.emplace(key, c.groups.size()).first;
+            c.groups.emplace_back();
+            HostGroup &g = c.groups.back();
+            g.material = mat;
+            g.meta.topology = topo;
+            g.meta.porder = porder;
+            g.meta.nstate = mat->NStateVariables();
+            const bool isbc = dynamic_cast<TPZBndCond *>(mat) != nullptr;
+            if (isbc) g.meta.kind = B200ASM_BC;
+            else if (dynamic_cast<TPZMatPoisson<STATE> *>(mat)) g.meta.kind = B200ASM_POISSON;
+            else if (dynamic_cast<TPZElasticity3D *>(mat)) g.meta.kind = B200ASM_ELASTICITY3D;
+            else Fatal("unsupported material id " + std::to_string(mat->Id()));
+            if (auto *lc = dynamic_cast<TPZMatLoadCasesBase *>(mat))
+                if (lc->NumLoadCases() != 1) Fatal("more than one load case is not supported");
+            switch (topo) {
+                case B200ASM_HEX: ShapeTables<pzshape::TPZShapeCube>(cel, porder, g); break;
+                case B200ASM_TET: ShapeTables<pzshape::TPZShapeTetra>(cel, porder, g); break;
+                case B200ASM_QUAD: ShapeTables<pzshape::TPZShapeQuad>(cel, porder, g); break;
+                default: ShapeTables<pzshape::TPZShapeTriang>(cel, porder, g); break;
+            }
+        }
+        HostGroup &g = c.groups[it->second];
+        auto *intel = dynamic_cast<TPZInterpolationSpace *>(cel);
+        if (intel->GetIntegrationRule().NPoints() != g.meta.nqp) Fatal("elements of one material/order use different integration rules");
+        for (int i = 0; i < ncorner; i++) g.elnodes.push_back((int32_t)gel->NodeIndex(i));
+        // TPZElementMatrix::ComputeDestinationIndices, Mesh/pzelmat.cpp:37-70
+        int ndof = 0;
+        for (int i = 0; i < ncon; i++) {
+            TPZConnect &con = cel->Connect(i);
+            const int64_t seq = con.SequenceNumber();
+            const int64_t first = cmesh->Block().Position(seq);
+            const int ndf = cmesh->Block().Size(seq);
+            for (int idf = 0; idf < ndf; idf++) g.dest.push_back(first + idf);
+            ndof += ndf;
+        }
+        if (ndof != g.meta.nshape * g.meta.nstate) Fatal("element " + std::to_string(iel) + ": unexpected number of equations");
+        g.elements.push_back(cel);
+    }
+    // node table
+    TPZGeoMesh *gmesh = cmesh->Reference();
+    const int64_t nnodes = gmesh->NNodes();
+    std::vector<double> xyz((size_t)nnodes * 3);
+    for (int64_t i = 0; i < nnodes; i++)
+        for (int d = 0; d < 3; d++) xyz[(size_t)i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
+    Check(c, b200asm_clear_groups(c.ctx), "b200asm_clear_groups");
+    Check(c, b200asm_set_nodes(c.ctx, nnodes, xyz.data()), "b200asm_set_nodes");
+    for (HostGroup &g : c.groups) {
+        g.meta.nel = (int64_t)g.elements.size();
+        g.meta.elnodes = g.elnodes.data();
+        g.meta.dest = g.dest.data();
+        g.meta.qpts = g.qpts.data();
+        g.meta.qwts = g.qw.data();
+        g.meta.phi = g.phi.data();
+        g.meta.dphi = g.dphi.data();
+        FillCoef(g);
+        FillForce(g);
+        Check(c, b200asm_add_group(c.ctx, &g.meta), "b200asm_add_group");
+    }
+    c.mesh = cmesh;
+    c.nelem = nel;
+    c.neq = cmesh->NEquations();
+    c.nconnects = cmesh->NConnects();
+    c.pattern_set = false;
+}
+
+}  // namespace
+
+template <class TVar>
+TPZStructMatrixB200<TVar>::TPZStructMatrixB200() : fCache(std::make_shared<TPZB200AssemblyCache>()) {}
+
+// copies (TPZStructMatrix::Clone through TPZAnalysis::SetStructuralMatrix) start with an empty cache
+template <class TVar>
+TPZStructMatrixB200<TVar>::TPZStructMatrixB200(const TPZStructMatrixB200 &copy)
+    : TPZStrMatParInterface(copy), fDevice(copy.fDevice), fCache(std::make_shared<TPZB200AssemblyCache>()) {}
+
+template <class TVar>
+TPZStructMatrixB200<TVar> &TPZStructMatrixB200<TVar>::operator=(const TPZStructMatrixB200 &copy) {
+    TPZStrMatParInterface::operator=(copy);
+    fDevice = copy.fDevice;
+    fCache = std::make_shared<TPZB200AssemblyCache>();
+    return *this;
+}
+
+template <class TVar>
+TPZStructMatrixB200<TVar>::~TPZStructMatrixB200() = default;
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::LastTimings(double &flatten_ms, double &pattern_ms, double &assemble_ms) const {
+    flatten_ms = fCache->flatten_ms;
+    pattern_ms = fCache->pattern_ms;
+    assemble_ms = fCache->assemble_ms;
+}
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) {
+    auto *strmat = dynamic_cast<TPZStructMatrix *>(this);
+    if (!strmat) Fatal("the strategy must be combined with a TPZStructMatrix");
+    if (strmat->EquationFilter().IsActive()) Fatal("an active equation filter is not supported yet");
+    auto *rhsmat = dynamic_cast<TPZFMatrix<STATE> *>(&rhs);
+    auto *sym = dynamic_cast<TPZSYsmpMatrix<STATE> *>(&stiffness);
+    auto *full = dynamic_cast<TPZFYsmpMatrix<STATE> *>(&stiffness);
+    if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
+    if (!sym && !full) Fatal("the stiffness matrix must be TPZSYsmpMatrix<STATE> or TPZFYsmpMatrix<STATE>");
+    TPZCompMesh *cmesh = strmat->Mesh();
+    TPZB200AssemblyCache &c = *fCache;
+    if (!c.ctx) {
+        if (b200asm_create(&c.ctx, fDevice) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
+    }
+    // (re)flatten when the mesh changed
+    auto t0 = clk::now();
+    c.flatten_ms = 0;
+    if (c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects()) {
+        Flatten(c, strmat);
+        c.flatten_ms = ms_since(t0);
+    } else {
+        // geometry and material constants may have changed since the last assembly
+        TPZGeoMesh *gmesh = cmesh->Reference();
+        const int64_t nnodes = gmesh->NNodes();
+        std::vector<double> xyz((size_t)nnodes * 3);
+        for (int64_t i = 0; i < nnodes; i++)
+            for (int d = 0; d < 3; d++) xyz[(size_t)i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
+        Check(c, b200asm_set_nodes(c.ctx, nnodes, xyz.data()), "b200asm_set_nodes");
+        int gi = 0;
+        for (HostGroup &g : c.groups) {
+            FillCoef(g);
+            Check(c, b200asm_set_group_coef(c.ctx, gi++, g.meta.coef), "b200asm_set_group_coef");
+        }
+    }
+    if (guiInterface && guiInterface->AmIKilled()) return;
+    // pattern of the matrix Create() produced
+    t0 = clk::now();
+    c.pattern_ms = 0;
+    const int symmetric = sym ? 1 : 0;
+    double *values = nullptr;
+    int64_t nnz = 0;
+    if (sym) {
+        nnz = sym->JA().size();
+        values = &sym->A()[0];
+    } else {
+        // values in place through the public TPZMatrix::Storage() (Matrix/pzmatrix.cpp:61-67)
+        TPZFMatrixRef<STATE> st = full->Storage();
+        nnz = st.Rows();
+        values = &st(0, 0);
+    }
+    if (!c.pattern_set || c.symmetric != symmetric || c.nnz != nnz) {
+        if (sym) {
+            Check(c, b200asm_set_pattern(c.ctx, sym->Rows(), &sym->IA()[0], &sym->JA()[0], 1), "b200asm_set_pattern");
+        } else {
+            TPZVec<int64_t> ia, ja;
+            TPZVec<STATE> a;
+            full->GetData(ia, ja, a);
+            Check(c, b200asm_set_pattern(c.ctx, full->Rows(), &ia[0], &ja[0], 0), "b200asm_set_pattern");
+        }
+        c.pattern_set = true;
+        c.symmetric = symmetric;
+        c.nnz = nnz;
+        c.pattern_ms = ms_since(t0);
+    }
+    if (guiInterface && guiInterface->AmIKilled()) return;
+    // assemble; the reference ADDS into rhs (TPZFMatrix::AddFel), the matrix arrives zeroed
+    t0 = clk::now();
+    const int64_t neq = rhsmat->Rows();
+    if (neq != c.neq || rhsmat->Cols() != 1) Fatal("rhs has the wrong size (one load case, NEquations rows)");
+    std::vector<double> rhsloc;
+    double *rhsptr = nullptr;
+    if (ComputeRhs()) {
+        rhsloc.resize(neq);
+        rhsptr = rhsloc.data();
+    }
+    Check(c, b200asm_assemble(c.ctx, values, rhsptr), "b200asm_assemble");
+    if (rhsptr) {
+        double *dst = &(*rhsmat)(0, 0);
+        for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc[i];
+    }
+    c.assemble_ms = ms_since(t0);
+}
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) {
+    // residual-only assembly (TPZLinearAnalysis::AssembleResidual) is row N3 of the scope table: not yet on the device
+    Fatal("Assemble(rhs) (right-hand side only) is not implemented yet; use Assemble(stiffness, rhs)");
+}
+
+template <class TVar>
+int TPZStructMatrixB200<TVar>::ClassId() const {
+    return Hash("TPZStructMatrixB200") ^ TPZStrMatParInterface::ClassId() << 1 ^ ClassIdOrHash<TVar>() << 2;
+}
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::Read(TPZStream &buf, void *context) {
+    TPZStrMatParInterface::Read(buf, context);
+    buf.Read(&fDevice);
+}
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::Write(TPZStream &buf, int withclassid) const {
+    TPZStrMatParInterface::Write(buf, withclassid);
+    buf.Write(&fDevice);
+}
+
+template class TPZStructMatrixB200<STATE>;
+template class TPZRestoreClass<TPZStructMatrixB200<STATE>>;
+
+// The member functions of the struct matrices are defined in their .cpp and explicitly instantiated only
+// for OR/OT/TBBFlow (StrMatrix/TPZSSpStructMatrix.cpp:217-223, TPZSpStructMatrix.cpp:214-220), so a new
+// parallel layer instantiates them here.
+#include "TPZSSpStructMatrix.cpp"
+#include "TPZSpStructMatrix.cpp"
+template class TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>;
+template class TPZSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>;

@@ -1,0 +1,68 @@
+/**
+ * @file TPZStructMatrixB200.h
+ * @brief Parallel layer for NeoPZ struct matrices that assembles on an NVIDIA B200 (sm_100a).
+ *
+ * A fourth TPZStrMatParInterface strategy next to TPZStructMatrixOR / OT / TBBFlow
+ * (StrMatrix/TPZStrMatParInterface.h:34-92, pattern of StrMatrix/pzstrmatrixor.h:29-119).  Use it as
+ *
+ *     TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>> strmat(cmesh);   // or TPZSpStructMatrix
+ *     an.SetStructuralMatrix(strmat);
+ *     an.Assemble();                                                         // unchanged user code
+ *
+ * Assemble(stiffness, rhs) flattens the TPZCompMesh once (node coordinates, corner nodes, destination
+ * indices exactly as Mesh/pzelmat.cpp:37-70, integration rules read through TPZIntPoints::Point, shape
+ * tables through TPZShapeH1<TSHAPE>::Shape, material constants, forcing functions evaluated on the
+ * host at the integration points) and drives the CUDA engine through the C ABI of include/b200asm.h.
+ * The CSR pattern is the one the struct matrix's own Create() produced; values are written in place
+ * into TPZSYsmpMatrix::A() / TPZFYsmpMatrix storage and the rhs into the TPZFMatrix.
+ *
+ * Supported: H1 TPZCompElH1 elements of uniform order p in {1,2} on hexahedra / tetrahedra with
+ * TPZMatPoisson<STATE> or TPZElasticity3D, boundary faces with TPZBndCondT<STATE> (types 0,1; 2 for
+ * elasticity), no hanging nodes, inactive equation filter, one load case.  Anything else is reported on
+ * PZError followed by DebugStop(), the reference's error convention (pzstrmatrixor.cpp:107-114).
+ * There is no CPU fallback.
+ */
+#ifndef TPZSTRUCTMATRIXB200_H
+#define TPZSTRUCTMATRIXB200_H
+
+#include <memory>
+
+#include "TPZStrMatParInterface.h"
+#include "pzreal.h"
+
+class TPZBaseMatrix;
+class TPZStructMatrix;
+class TPZCompMesh;
+
+struct TPZB200AssemblyCache;  // flattened mesh + device context, shared by copies (Clone())
+
+template <class TVar>
+class TPZStructMatrixB200 : public virtual TPZStrMatParInterface {
+public:
+    TPZStructMatrixB200();
+    TPZStructMatrixB200(const TPZStructMatrixB200 &copy);
+    TPZStructMatrixB200 &operator=(const TPZStructMatrixB200 &copy);
+    virtual ~TPZStructMatrixB200();
+
+    //! Assemble the global system of equations into a matrix that has already been created.
+    void Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) override;
+    //! Assemble the global right hand side vector.
+    void Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) override;
+
+    //! CUDA device used by this strategy (default 0).
+    void SetDevice(int device) { fDevice = device; }
+    int Device() const { return fDevice; }
+    //! Milliseconds the last Assemble() spent in flatten / pattern upload / device assembly + copies.
+    void LastTimings(double &flatten_ms, double &pattern_ms, double &assemble_ms) const;
+
+    int ClassId() const override;
+    void Read(TPZStream &buf, void *context) override;
+    void Write(TPZStream &buf, int withclassid) const override;
+
+protected:
+    int fDevice{0};
+    std::shared_ptr<TPZB200AssemblyCache> fCache;
+};
+
+extern template class TPZStructMatrixB200<STATE>;
+#endif

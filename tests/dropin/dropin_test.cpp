@@ -1,0 +1,201 @@
+// Drop-in test of the B200 strategy inside the UNMODIFIED reference (test code; reads like
+// UnitTest_PZ/TestStruct/StructMatrixUnitTest.cpp "Compare parallel and serial matrices", :215-246).
+//
+// Same mesh, same TPZLinearAnalysis user code, two struct matrices:
+//   TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>    (reference CPU path, serial + threaded)
+//   TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>  (this repo, CUDA)
+// Checks: IA/JA identical (memcmp), ||A_gpu - A_ref||_F / ||A_ref||_F <= 1e-12 (all rows and rows without
+// penalty entries), rhs likewise, and the reference's own CG (TPZStepSolver::SetCG, Jacobi preconditioner)
+// on both systems gives solutions within 1e-10.  Prints one JSON line; exit code 0 iff all checks pass.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <thread>
+
+#include "Elasticity/TPZElasticity3D.h"
+#include "Poisson/TPZMatPoisson.h"
+#include "TPZBndCondT.h"
+#include "TPZGeoMeshTools.h"
+#include "TPZLinearAnalysis.h"
+#include "TPZSSpStructMatrix.h"
+#include "TPZSpStructMatrix.h"
+#include "TPZStructMatrixB200.h"
+#include "pzcmesh.h"
+#include "pzgmesh.h"
+#include "pzgnode.h"
+#include "pzstepsolver.h"
+#include "pzsysmp.h"
+#include "pzysmp.h"
+
+using clk = std::chrono::steady_clock;
+static double secs(clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
+static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb) {
+    TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
+    TPZManVector<int, 7> matids(7, -1);
+    matids[0] = 1;
+    matids[6] = -2;  // zmax: Neumann
+    TPZManVector<int, 3> ndiv(3, n);
+    TPZGeoMesh *gmesh = TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv,
+                                                             tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true);
+    if (perturb != 0.0) {
+        const double h = 1.0 / n;
+        for (int64_t i = 0; i < gmesh->NNodes(); i++)
+            for (int d = 0; d < 3; d++) {
+                TPZGeoNode &nd = gmesh->NodeVec()[i];
+                nd.SetCoord(d, nd.Coord(d) + perturb * h * std::sin(2.0 * M_PI * (double)i / 97.0 + (double)d));
+            }
+    }
+    TPZCompMesh *cmesh = new TPZCompMesh(gmesh);
+    cmesh->SetDimModel(3);
+    cmesh->SetDefaultOrder(p);
+    if (phys == 0) {
+        auto *m = new TPZMatPoisson<STATE>(1, 3);
+        // x-dependent source: exercises the host-evaluated forcing table
+        m->SetForcingFunction([](const TPZVec<REAL> &x, TPZVec<STATE> &f) { f[0] = 1.0 + x[0] * x[1] - 0.5 * x[2]; }, 2);
+        cmesh->InsertMaterialObject(m);
+        TPZFNMatrix<1, STATE> v1(1, 1, 0.);
+        TPZManVector<STATE, 1> v2(1, 0.3), v2n(1, 0.75);
+        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+    } else {
+        TPZManVector<STATE, 3> force(3, 0.);
+        force[2] = -1.;
+        auto *m = new TPZElasticity3D(1, 1000., 0.3, force);
+        cmesh->InsertMaterialObject(m);
+        TPZFNMatrix<9, STATE> v1(3, 3, 0.);
+        TPZManVector<STATE, 3> v2(3, 0.), v2n(3, 0.);
+        v2[0] = 0.01;
+        v2n[0] = 0.25; v2n[1] = -0.5; v2n[2] = 2.0;
+        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+    }
+    cmesh->SetAllCreateFunctionsContinuous();
+    cmesh->AutoBuild();
+    cmesh->AdjustBoundaryElements();
+    cmesh->CleanUpUnconnectedNodes();
+    return cmesh;
+}
+
+struct Csr {
+    std::vector<int64_t> ia, ja;
+    std::vector<double> a, rhs, sol;
+};
+
+template <class TStrMat>
+static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Csr &out, double &t_first, double &t_second) {
+    TPZLinearAnalysis an(cmesh, false);
+    TStrMat strmat(cmesh);
+    strmat.SetNumThreads(nthreads);
+    an.SetStructuralMatrix(strmat);
+    TPZStepSolver<STATE> step;
+    step.SetDirect(symmetric ? ELDLt : ELU);  // never decomposed: the CG below is run on the assembled matrix
+    an.SetSolver(step);
+    auto t0 = clk::now();
+    an.Assemble();
+    auto t1 = clk::now();
+    an.Assemble();
+    auto t2 = clk::now();
+    t_first = secs(t0, t1);
+    t_second = secs(t1, t2);
+    auto mtx = an.MatrixSolver<STATE>().Matrix();
+    const int64_t neq = cmesh->NEquations();
+    if (symmetric) {
+        auto *sp = dynamic_cast<TPZSYsmpMatrix<STATE> *>(mtx.operator->());
+        out.ia.assign(sp->IA().begin(), sp->IA().end());
+        out.ja.assign(sp->JA().begin(), sp->JA().end());
+        out.a.assign(sp->A().begin(), sp->A().end());
+    } else {
+        auto *sp = dynamic_cast<TPZFYsmpMatrix<STATE> *>(mtx.operator->());
+        TPZVec<int64_t> ia, ja;
+        TPZVec<STATE> a;
+        sp->GetData(ia, ja, a);
+        out.ia.assign(ia.begin(), ia.end());
+        out.ja.assign(ja.begin(), ja.end());
+        out.a.assign(a.begin(), a.end());
+    }
+    out.rhs.resize(neq);
+    TPZFMatrix<STATE> &rhsm = an.Rhs();
+    for (int64_t i = 0; i < neq; i++) out.rhs[i] = rhsm(i, 0);
+    if (solve) {
+        // the reference's own CG (Solvers/LinearSolvers/cg.h:44-120 through TPZMatrix::SolveCG) with its Jacobi
+        // preconditioner, on the assembled system
+        TPZStepSolver<STATE> pre(mtx);
+        pre.SetJacobi(1, 0., 0);
+        TPZStepSolver<STATE> cg(mtx);
+        cg.SetCG(50000, pre, 1.e-15, 0);
+        TPZFMatrix<STATE> sol(neq, 1, 0.), f(rhsm);
+        cg.Solve(f, sol);
+        out.sol.resize(neq);
+        for (int64_t i = 0; i < neq; i++) out.sol[i] = sol(i, 0);
+    }
+}
+
+static double RelF(const std::vector<double> &x, const std::vector<double> &ref) {
+    long double num = 0, den = 0;
+    for (size_t i = 0; i < x.size(); i++) {
+        num += (long double)(x[i] - ref[i]) * (x[i] - ref[i]);
+        den += (long double)ref[i] * ref[i];
+    }
+    return den > 0 ? (double)std::sqrt(num / den) : (double)std::sqrt(num);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 6) {
+        std::cerr << "usage: dropin_test n p phys(0|1) tet(0|1) symmetric(0|1) [solve(0|1)] [cpu_threads]\n";
+        return 2;
+    }
+    const int n = atoi(argv[1]), p = atoi(argv[2]), phys = atoi(argv[3]), tet = atoi(argv[4]), symmetric = atoi(argv[5]);
+    const int solve = argc > 6 ? atoi(argv[6]) : 1;
+    const int threads = argc > 7 ? atoi(argv[7]) : (int)std::thread::hardware_concurrency();
+    TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12);
+    Csr ref, refmt, gpu;
+    double t1, t2, tm1, tm2, g1, g2;
+    if (symmetric) {
+        Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, 0, true, solve, ref, t1, t2);
+        Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, true, false, refmt, tm1, tm2);
+        Run<TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, true, solve, gpu, g1, g2);
+    } else {
+        Run<TPZSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, 0, false, false, ref, t1, t2);
+        Run<TPZSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, false, false, refmt, tm1, tm2);
+        Run<TPZSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, false, false, gpu, g1, g2);
+    }
+    const bool same_ia = ref.ia.size() == gpu.ia.size() && !memcmp(ref.ia.data(), gpu.ia.data(), ref.ia.size() * 8);
+    const bool same_ja = ref.ja.size() == gpu.ja.size() && !memcmp(ref.ja.data(), gpu.ja.data(), ref.ja.size() * 8);
+    const double errA = RelF(gpu.a, ref.a), errR = RelF(gpu.rhs, ref.rhs);
+    // rows without penalty entries
+    const int64_t neq = (int64_t)ref.ia.size() - 1;
+    std::vector<char> bigrow(neq, 0);
+    for (int64_t r = 0; r < neq; r++)
+        for (int64_t k = ref.ia[r]; k < ref.ia[r + 1]; k++)
+            if (std::fabs(ref.a[k]) > 1e9) bigrow[r] = 1;
+    long double num = 0, den = 0;
+    double maxrel = 0;
+    for (int64_t r = 0; r < neq; r++) {
+        if (bigrow[r]) continue;
+        double rowmax = 0;
+        for (int64_t k = ref.ia[r]; k < ref.ia[r + 1]; k++) rowmax = std::max(rowmax, std::fabs(ref.a[k]));
+        for (int64_t k = ref.ia[r]; k < ref.ia[r + 1]; k++) {
+            const double d = gpu.a[k] - ref.a[k];
+            num += (long double)d * d;
+            den += (long double)ref.a[k] * ref.a[k];
+            if (rowmax > 0) maxrel = std::max(maxrel, std::fabs(d) / rowmax);
+        }
+    }
+    const double errInt = den > 0 ? (double)std::sqrt(num / den) : 0.0;
+    const double errMT = RelF(refmt.a, ref.a);
+    double errSol = 0;
+    if (solve && symmetric) errSol = RelF(gpu.sol, ref.sol);
+    const int64_t nvol = (int64_t)n * n * n * (tet ? 5 : 1);
+    const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10;
+    std::cout.precision(6);
+    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric
+              << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
+              << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
+              << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel
+              << ", \"relF_rhs\": " << errR << ", \"relF_cg_solution\": " << errSol << ", \"relF_A_ref_threads_vs_serial\": " << errMT
+              << ", \"cpu_serial_assemble_s\": " << t2 << ", \"cpu_threads\": " << threads << ", \"cpu_threaded_assemble_s\": " << tm2
+              << ", \"gpu_first_assemble_s\": " << g1 << ", \"gpu_second_assemble_s\": " << g2 << ", \"ok\": " << ok << "}" << std::endl;
+    return ok ? 0 : 1;
+}

@@ -1,0 +1,32 @@
+"""Drop-in test inside the UNMODIFIED reference: tests/_bin/dropin_test (built by __graft_entry__.build()
+where /root/reference exists; the binary, neopz_b200/libpzb200.so and oracle/_ref/libpz.so travel to the GPU
+box) runs TPZLinearAnalysis::Assemble() with TPZStructMatrixOR (CPU) and TPZStructMatrixB200 (CUDA) on the same
+TPZCompMesh and compares: IA/JA memcmp, ||A-Aref||_F <= 1e-12 (all rows and non-penalty rows), rhs, and the
+reference's own CG on both systems (solution within 1e-10)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "_bin", "dropin_test")
+
+# n, p, phys (0 Poisson / 1 Elasticity3D), tet, symmetric, solve
+CASES = [(6, 1, 0, 0, 1, 1), (5, 2, 0, 0, 1, 1), (4, 2, 1, 0, 1, 1), (4, 2, 0, 1, 1, 1), (3, 2, 1, 1, 1, 1),
+         (4, 2, 0, 0, 0, 0), (3, 2, 1, 0, 0, 0), (5, 1, 1, 0, 1, 1)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_dropin_strategy_matches_reference(case):
+    if not os.path.exists(BIN):
+        pytest.skip("tests/_bin/dropin_test not built (needs /root/reference at build time)")
+    out = subprocess.run([BIN] + [str(x) for x in case] + ["4"], capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(lines[-1])
+    assert r["ia_identical"] == 1 and r["ja_identical"] == 1
+    assert r["relF_A"] <= 1e-12 and r["relF_A_nonpenalty_rows"] <= 1e-12 and r["relF_rhs"] <= 1e-12
+    assert r["relF_cg_solution"] <= 1e-10
+    assert out.returncode == 0
