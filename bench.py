@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--phys", default="poisson", choices=["poisson", "elasticity"])
     ap.add_argument("--topo", default="hex", choices=["hex", "tet"])
     ap.add_argument("--cpu-n", type=int, default=0, help="grid size of the bounded CPU-baseline sample (0 = auto)")
+    ap.add_argument("--engine", type=int, default=1, help="0: register-tile DFMA kernels, 1: DMMA panel kernels where available")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -170,7 +171,7 @@ def main():
     else:
         mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
         mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
-    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
     t0 = time.time()
@@ -293,7 +294,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
-                       "perturbed_nodes": True, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
+                       "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}
     print(json.dumps(line))

@@ -169,6 +169,9 @@ class Context:
     def set_stream(self, cuda_stream_handle):
         self._check(lib().b200asm_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
 
+    def set_option(self, name, value):
+        self._check(lib().b200asm_set_option(self._h, name.encode(), int(value)))
+
     def set_nodes(self, xyz):
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         self._check(lib().b200asm_set_nodes(self._h, xyz.shape[0], dptr(xyz)))

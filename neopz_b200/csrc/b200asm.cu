@@ -73,6 +73,8 @@ struct VolCfg {
 
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 
+#include "gram_mma.cuh"
+
 // decode the linear index of an upper-triangular tile into (bi, bj), bi <= bj
 template <int NTB>
 __device__ __forceinline__ void tile_coords(int t, int &bi, int &bj) {
@@ -488,7 +490,8 @@ thread_local std::string g_create_error;
 struct Group {
     int topology = 0, porder = 0, kind = 0, ns = 1, nn = 0, n = 0, nq = 0, m = 0, dim = 3;
     int64_t nel = 0, nbatch = 0;
-    int cfg = -1;  // index into the dispatch table
+    int cfg = -1;  // index into the dispatch table (register-tile kernels)
+    int mma = -1;  // index into the DMMA dispatch table, -1: none
     double coef[16];
     int32_t *d_elnodes = nullptr, *d_dest = nullptr, *d_smap = nullptr, *d_smapT = nullptr;
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
@@ -513,6 +516,7 @@ struct b200asm_ctx {
     int *d_missing = nullptr;
     int64_t launches = 0, h2d = 0, d2h = 0;
     int scatter = B200ASM_SCATTER_ATOMIC;
+    int engine = 1;  // 1: DMMA panel kernel where one exists, 0: register-tile DFMA kernels only
     std::string err;
 };
 
@@ -592,6 +596,43 @@ const VolEntry kVol[] = {
 };
 constexpr int kNumVol = sizeof(kVol) / sizeof(kVol[0]);
 
+// DMMA panel kernels (gram_mma.cuh):  NN  N  warps/CTA  min CTAs/SM
+using HexP2PoissonMma = MmaCfg<8, 27, 8, 2>;
+using TetP2PoissonMma = MmaCfg<4, 10, 8, 2>;
+
+struct MmaEntry {
+    int topology, porder, ns;
+    int slots, nthreads, wpc;
+    size_t (*smem)(int nq);
+    cudaError_t (*launch)(const VolParams &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*launch_smap)(int64_t nel, const int32_t *dest, const int64_t *ia, const int64_t *ja, int symmetric,
+                               int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t);
+    cudaError_t (*prepare)(size_t smem, int *ctas_per_sm);
+};
+template <class C>
+cudaError_t launch_mma(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
+    assemble_gram_mma_kernel<C><<<grid, C::WPC * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t launch_mma_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int64_t *ja, int symmetric,
+                            int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_mma_smap_kernel<C><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t prepare_mma(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_gram_mma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_gram_mma_kernel<C>, C::WPC * 32, smem);
+}
+template <class C>
+MmaEntry make_mma_entry(int topology, int porder) {
+    return MmaEntry{topology, porder, 1, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_mma<C>, &launch_mma_smap<C>, &prepare_mma<C>};
+}
+const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2)};
+constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
+
 template <int NN, int N, int NS>
 cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
     const int grid = (int)((p.nel + 127) / 128);
@@ -639,6 +680,8 @@ int build_smaps(b200asm_ctx *ctx, const int64_t *d_ja) {
         g.d_smap = g.d_smapT = nullptr;
         if (g.kind == B200ASM_BC) {
             g.smap_len = (size_t)g.n * g.n * g.ns * g.ns * g.nel;
+        } else if (g.mma >= 0 && ctx->engine == 1) {
+            g.smap_len = (size_t)g.nel * kMma[g.mma].slots;
         } else {
             const VolEntry &ve = kVol[g.cfg];
             g.nbatch = (g.nel + ve.epb - 1) / ve.epb;
@@ -652,6 +695,9 @@ int build_smaps(b200asm_ctx *ctx, const int64_t *d_ja) {
             build_bc_smap_kernel<<<grid, 256, 0, ctx->stream>>>(g.nel, g.n, g.ns, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric,
                                                                 g.d_smap, g.d_smapT, ctx->d_missing);
             CK(cudaGetLastError());
+        } else if (g.mma >= 0 && ctx->engine == 1) {
+            CK(kMma[g.mma].launch_smap(g.nel, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT, ctx->d_missing,
+                                        grid, ctx->stream));
         } else {
             CK(kVol[g.cfg].launch_smap(g.nel, g.nbatch, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT,
                                         ctx->d_missing, grid, ctx->stream));
@@ -726,6 +772,12 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
         ctx->scatter = (int)value;
         return 0;
     }
+    if (!strcmp(name, "engine")) {
+        if (value != 0 && value != 1) return fail(ctx, B200ASM_EINVAL, "engine: 0 (register tiles) or 1 (DMMA where available)");
+        ctx->engine = (int)value;
+        ctx->have_pattern = false;  // the scatter-map layout depends on the kernel
+        return 0;
+    }
     return fail(ctx, B200ASM_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -768,6 +820,8 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         for (int k = 0; k < kNumVol; k++)
             if (kVol[k].topology == g.topology && kVol[k].porder == g.porder && kVol[k].ns == g.ns) g.cfg = k;
         if (g.cfg < 0) return fail(ctx, B200ASM_EINVAL, "add_group: no kernel for this configuration");
+        for (int k = 0; k < kNumMma; k++)
+            if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns) g.mma = k;
     } else if (gi->kind != B200ASM_BC) {
         return fail(ctx, B200ASM_EINVAL, "add_group: face elements need kind BC");
     }
@@ -855,13 +909,26 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             memcpy(p.coef, g.coef, sizeof(p.coef));
             CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
         } else {
-            const VolEntry &ve = kVol[g.cfg];
             VolParams p;
             p.nel = g.nel; p.nbatch = g.nbatch; p.nq = g.nq; p.kind = g.kind;
             p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest; p.qw = g.d_qw; p.phi = g.d_phi;
             p.dphi = g.d_dphi; p.dng = g.d_dng; p.force = g.d_force; p.smap = g.d_smap; p.smapT = g.d_smapT;
             p.a = ctx->d_a; p.rhs = ctx->d_rhs;
             memcpy(p.coef, g.coef, sizeof(p.coef));
+            if (g.mma >= 0 && ctx->engine == 1) {
+                const MmaEntry &me = kMma[g.mma];
+                const size_t smem = me.smem(g.nq);
+                if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
+                int per_sm = 1;
+                CK(me.prepare(smem, &per_sm));
+                if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
+                const int64_t want = (g.nel + me.wpc - 1) / me.wpc;
+                const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm);
+                CK(me.launch(p, grid, smem, ctx->stream));
+                ctx->launches++;
+                continue;
+            }
+            const VolEntry &ve = kVol[g.cfg];
             const size_t smem = ve.smem(g.nq);
             if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
             // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)

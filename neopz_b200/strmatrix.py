@@ -136,12 +136,14 @@ class TPZStructMatrixB200:
     """TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>> (symmetric=True) or
     TPZSpStructMatrix<...> (symmetric=False) on a flattened mesh."""
 
-    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0):
+    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0, engine=None):
         self.mesh = mesh
         self.materials = {m.id: m for m in (materials.values() if isinstance(materials, dict) else materials)}
         self.symmetric = bool(symmetric)
         self.fNumThreads = nthreads
         self.ctx = capi.Context(device)
+        if engine is not None:  # 0: register-tile DFMA kernels only, 1 (default): DMMA panel kernels where available
+            self.ctx.set_option("engine", engine)
         self.ia = self.ja = None
         self._flattened = False
         self.group_of_block = []

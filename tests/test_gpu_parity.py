@@ -90,6 +90,22 @@ def test_against_oracle(n, p, phys, tet):
         assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
 
 
+@pytest.mark.parametrize("n,p,phys,tet", [(5, 2, 0, 0), (4, 2, 0, 1)])
+def test_engines_agree(n, p, phys, tet):
+    """Register-tile DFMA kernels (engine 0) and DMMA panel kernels (engine 1) against the oracle and each other."""
+    mesh = gridmesh.grid_mesh(n, p, 1, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    mats = materials_for(phys, neumann=True)
+    res = {}
+    for engine in (0, 1):
+        for symmetric in (True, False):
+            strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, engine=engine)
+            ia, ja, a, rhs = strmat.CreateAssemble()
+            a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+            assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+            res[(engine, symmetric)] = a
+    assert relF(res[(0, True)], res[(1, True)]) <= TOL
+
+
 def _full_from_sym(ia, ja, a, neq):
     import scipy.sparse as sp
     U = sp.csr_matrix((a, ja, ia), shape=(neq, neq))
