@@ -30,7 +30,8 @@ struct MmaCfg {
     static constexpr int JS = 11;
     static constexpr int XSP = NN * 3 + ((NN * 3) & 1);
     static constexpr int SLOTS = NTILES * 2 * 32;  // scatter-map entries per element
-    __host__ __device__ static int warp_doubles(int nq) { int n = XSP + nq * JS + KC * LD; return n + (n & 1); }
+    __host__ __device__ static int qstride(int nq) { return ((nq + 31) / 32) * 32; }  // JI is [JS][qstride]
+    __host__ __device__ static int warp_doubles(int nq) { int n = XSP + qstride(nq) * JS + KC * LD; return n + (n & 1); }
     static size_t smem_bytes(int nq) { return sizeof(double) * (size_t)WPC * warp_doubles(nq); }
 };
 
@@ -48,18 +49,30 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
     const int nq = p.nq;
     double *Xs = smem + (size_t)warp * C::warp_doubles(nq);
     double *JI = Xs + C::XSP;
-    double *Pn = JI + nq * JS;
+    const int QS = C::qstride(nq);
+    double *Pn = JI + QS * JS;
     for (int i = lane; i < KC * LD; i += 32) Pn[i] = 0.0;  // padding columns stay zero
     __syncwarp();
     const int g = lane >> 2, tg = lane & 3;
     const int64_t nwarps = (int64_t)gridDim.x * C::WPC;
 
-    for (int64_t el = (int64_t)blockIdx.x * C::WPC + warp; el < p.nel; el += nwarps) {
+    const int64_t el_first = (int64_t)blockIdx.x * C::WPC + warp;
+    int32_t next_node = (lane < NN && el_first < p.nel) ? p.elnodes[el_first * NN + lane] : 0;
+    for (int64_t el = el_first; el < p.nel; el += nwarps) {
+        // the scatter positions of this element are fetched now (HBM latency hidden behind the arithmetic):
+        // the atomics of the epilogue would otherwise serialise these loads
+        int32_t pos[NTILES * 2];
+        {
+            const int32_t *sm = p.smap + (size_t)el * C::SLOTS + lane;
+#pragma unroll
+            for (int k = 0; k < NTILES * 2; k++) pos[k] = __ldcs(sm + k * 32);
+        }
         if (lane < NN) {
-            const int64_t node = p.elnodes[el * NN + lane];
+            const int64_t node = next_node;
             Xs[lane * 3 + 0] = p.xyz[node * 3 + 0];
             Xs[lane * 3 + 1] = p.xyz[node * 3 + 1];
             Xs[lane * 3 + 2] = p.xyz[node * 3 + 2];
+            if (el + nwarps < p.nel) next_node = p.elnodes[(el + nwarps) * NN + lane];
         }
         __syncwarp();
         // ---- phase 1: geometry at the integration points (Geom/TPZGeoCube.h:141-149, Mesh/pzgeoel.cpp:1309-1336)
@@ -83,19 +96,19 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             det += j00 * j11 * j22;
             if (fabs(det) < 1.e-12) det = 1.e-12;
             const double id = 1.0 / det;
-            double *o = JI + q * JS;
-            o[0] = (-j12 * j21 + j11 * j22) * id;
-            o[1] = (j02 * j21 - j01 * j22) * id;
-            o[2] = (-j02 * j11 + j01 * j12) * id;
-            o[3] = (j12 * j20 - j10 * j22) * id;
-            o[4] = (-j02 * j20 + j00 * j22) * id;
-            o[5] = (j02 * j10 - j00 * j12) * id;
-            o[6] = (-j11 * j20 + j10 * j21) * id;
-            o[7] = (j01 * j20 - j00 * j21) * id;
-            o[8] = (-j01 * j10 + j00 * j11) * id;
+            double *o = JI + q;  // field k of point q at JI[k*QS + q]: conflict-free stores, broadcast reads
+            o[0 * QS] = (-j12 * j21 + j11 * j22) * id;
+            o[1 * QS] = (j02 * j21 - j01 * j22) * id;
+            o[2 * QS] = (-j02 * j11 + j01 * j12) * id;
+            o[3 * QS] = (j12 * j20 - j10 * j22) * id;
+            o[4 * QS] = (-j02 * j20 + j00 * j22) * id;
+            o[5 * QS] = (j02 * j10 - j00 * j12) * id;
+            o[6 * QS] = (-j11 * j20 + j10 * j21) * id;
+            o[7 * QS] = (j01 * j20 - j00 * j21) * id;
+            o[8 * QS] = (-j01 * j10 + j00 * j11) * id;
             const double w = __ldg(p.qw + q) * fabs(det);
-            o[9] = w;
-            o[10] = sqrt(w);
+            o[9 * QS] = w;
+            o[10 * QS] = sqrt(w);
         }
         __syncwarp();
 
@@ -104,24 +117,31 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
         for (int t = 0; t < NTILES; t++) acc[t][0] = acc[t][1] = 0.0;
 
         for (int q0 = 0; q0 < nq; q0 += QC) {
-            // ---- phase 2: panel rows of QC points (Mesh/TPZCompElH1.cpp:147) ----------------------
-            for (int it = lane; it < QC * N; it += 32) {
-                const int ql = it / N, i = it - ql * N;
-                const int q = q0 + ql;
-                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-                if (q < nq) {
-                    const double *ji = JI + q * JS;
+            // ---- phase 2: panel rows of QC points (Mesh/TPZCompElH1.cpp:147): lane <-> shape function,
+            // the table loads of all QC points are issued before the first use
+            for (int i = lane; i < N; i += 32) {
+                double d[QC][3];
+#pragma unroll
+                for (int ql = 0; ql < QC; ql++) {
+                    const int q = q0 + ql;
                     const double *dp = p.dphi + (size_t)q * 3 * N + i;
-                    const double d0 = __ldg(dp), d1 = __ldg(dp + N), d2 = __ldg(dp + 2 * N);
-                    const double sw = ji[10];
-                    g0 = (ji[0] * d0 + ji[3] * d1 + ji[6] * d2) * sw;
-                    g1 = (ji[1] * d0 + ji[4] * d1 + ji[7] * d2) * sw;
-                    g2 = (ji[2] * d0 + ji[5] * d1 + ji[8] * d2) * sw;
+                    d[ql][0] = q < nq ? __ldg(dp) : 0.0;
+                    d[ql][1] = q < nq ? __ldg(dp + N) : 0.0;
+                    d[ql][2] = q < nq ? __ldg(dp + 2 * N) : 0.0;
                 }
-                double *row = Pn + (3 * ql) * LD + i;
-                row[0] = g0;
-                row[LD] = g1;
-                row[2 * LD] = g2;
+#pragma unroll
+                for (int ql = 0; ql < QC; ql++) {
+                    const int q = min(q0 + ql, nq - 1);  // tail rows: d == 0 -> zero rows
+                    const double *ji = JI + q;
+                    const double sw = ji[10 * QS];
+                    const double g0 = (ji[0 * QS] * d[ql][0] + ji[3 * QS] * d[ql][1] + ji[6 * QS] * d[ql][2]) * sw;
+                    const double g1 = (ji[1 * QS] * d[ql][0] + ji[4 * QS] * d[ql][1] + ji[7 * QS] * d[ql][2]) * sw;
+                    const double g2 = (ji[2 * QS] * d[ql][0] + ji[5 * QS] * d[ql][1] + ji[8 * QS] * d[ql][2]) * sw;
+                    double *row = Pn + (3 * ql) * LD + i;
+                    row[0] = g0;
+                    row[LD] = g1;
+                    row[2 * LD] = g2;
+                }
             }
             __syncwarp();
             // ---- phase 3: Gram update, 3 k-steps of 4 panel rows -----------------------------------
@@ -147,25 +167,24 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             double f = 0.0;
             for (int q = 0; q < nq; q++) {
                 const double fq = p.force ? p.force[el * nq + q] : p.coef[1];
-                f += JI[q * JS + 9] * p.coef[0] * __ldg(p.phi + (size_t)q * N + lane) * fq;
+                f += JI[9 * QS + q] * p.coef[0] * __ldg(p.phi + (size_t)q * N + lane) * fq;
             }
             atomicAdd(p.rhs + p.dest[el * N + lane], f);
         }
         // ---- scatter-add of the upper triangle ---------------------------------------------------
         const double s = p.coef[0];
-        const int32_t *sm = p.smap + (size_t)el * C::SLOTS + lane;
         const int32_t *smT = p.smapT ? p.smapT + (size_t)el * C::SLOTS + lane : nullptr;
+        if (smT) {
+            int32_t posT[NTILES * 2];
 #pragma unroll
-        for (int t = 0; t < NTILES; t++)
+            for (int k = 0; k < NTILES * 2; k++) posT[k] = __ldcs(smT + k * 32);
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int32_t pos = sm[(t * 2 + e) * 32];
-                if (pos >= 0) atomicAdd(p.a + pos, s * acc[t][e]);
-                if (smT) {
-                    const int32_t posT = smT[(t * 2 + e) * 32];
-                    if (posT >= 0) atomicAdd(p.a + posT, s * acc[t][e]);
-                }
-            }
+            for (int k = 0; k < NTILES * 2; k++)
+                if (posT[k] >= 0) atomicAdd(p.a + posT[k], s * acc[k >> 1][k & 1]);
+        }
+#pragma unroll
+        for (int k = 0; k < NTILES * 2; k++)
+            if (pos[k] >= 0) atomicAdd(p.a + pos[k], s * acc[k >> 1][k & 1]);
     }
 }
 

@@ -165,20 +165,26 @@ def flatten(nodes, element_blocks, porder, nstate):
 
 
 def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_matid=1,
-                  min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0):
-    """Nodes and element blocks of CreateGeoMeshOnGrid(3, minX, maxX, matids, {n,n,n}, type, createBoundEls=true).
+                  min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0, z_layers=None, with_layers=False):
+    """Nodes and element blocks of CreateGeoMeshOnGrid(3, minX, maxX, matids, {nx,ny,nz}, type, createBoundEls=true).
 
-    n: divisions per direction (int or 3-tuple).  bc_matids = (zmin, ymin, xmin... ) in the reference's
-    argument order matids[1..6] = (Zmin, Xmin?, ...): see below.
+    n: divisions per direction (int or 3-tuple).  bc_matids = matids[1..6] of the reference call, i.e. the
+    arguments of BuildBoundaryElements(Zmin, Xmin, Ymin, Xmax, Ymax, Zmax) (Pre/TPZGenGrid3D.cpp:230-232).
+    z_layers=(iz0, iz1): only the element layers iz0 <= iz < iz1 of the global grid (slab of a sharded mesh);
+    node indices are then local to the slab (global id - iz0*(nx+1)*(ny+1)), coordinates and the element /
+    face parities are those of the global grid.  with_layers: blocks carry a 4th entry, the global layer of
+    every element.
     """
     nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    iz0, iz1 = (0, nz) if z_layers is None else z_layers
+    nzl = iz1 - iz0
     min_x = np.asarray(min_x, dtype=np.float64)
     max_x = np.asarray(max_x, dtype=np.float64)
-    ix, iy, iz = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
-    # node id = iz*(nx+1)*(ny+1) + iy*(nx+1) + ix  -> order arrays as [iz][iy][ix]
-    I = np.transpose(ix, (2, 1, 0)).reshape(-1)
-    J = np.transpose(iy, (2, 1, 0)).reshape(-1)
-    K = np.transpose(iz, (2, 1, 0)).reshape(-1)
+    sx, sy = 1, nx + 1
+    sz = (nx + 1) * (ny + 1)
+    # node id = iz*(nx+1)*(ny+1) + iy*(nx+1) + ix
+    K, J, I = np.meshgrid(np.arange(iz0, iz1 + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
     nodes = np.empty((len(I), 3))
     # fMinX + ((fMaxX-fMinX) * i)/nel   (Pre/TPZGenGrid3D.cpp:72-74)
     nodes[:, 0] = min_x[0] + ((max_x[0] - min_x[0]) * I) / nx
@@ -187,22 +193,20 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
     if perturb != 0.0:
         # the deterministic perturbation of oracle/refdriver.cpp: non-constant Jacobians
         h = 1.0 / nx
-        ids = np.arange(len(nodes), dtype=np.float64)
+        ids = (K * sz + J * sy + I).astype(np.float64)  # global node ids
         for d in range(3):
             nodes[:, d] += perturb * h * np.sin(2.0 * np.pi * ids / 97.0 + float(d))
-    sx, sy = 1, nx + 1
-    sz = (nx + 1) * (ny + 1)
 
-    ez, ey, ex = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ez, ey, ex = np.meshgrid(np.arange(nzl), np.arange(ny), np.arange(nx), indexing="ij")
     ex, ey, ez = ex.reshape(-1), ey.reshape(-1), ez.reshape(-1)
     first = ez * sz + ey * sy + ex
     cube = np.stack([first, first + 1, first + 1 + sy, first + sy,
                      first + sz, first + 1 + sz, first + 1 + sy + sz, first + sy + sz], axis=1)
-    blocks = []
+    blocks = []  # [topology, matid, elnodes, layer]
     if not tetrahedra:
-        blocks.append((capi.HEX, vol_matid, cube))
+        blocks.append([capi.HEX, vol_matid, cube, ez + iz0])
     else:
-        perm = (ex + ey + ez) % 2
+        perm = (ex + ey + ez + iz0) % 2
         rows = np.arange(len(cube))
 
         def cn(k, top=False):  # cubenode[(k+permut)%4 (+4)]
@@ -213,24 +217,27 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
         t3 = np.stack([cn(3, True), cn(2, True), cn(0, True), cn(3)], axis=1)
         t4 = np.stack([cn(0, True), cn(1), cn(3), cn(2, True)], axis=1)
         tets = np.stack([t0, t1, t2, t3, t4], axis=1).reshape(-1, 4)
-        blocks.append((capi.TET, vol_matid, tets))
+        blocks.append([capi.TET, vol_matid, tets, np.repeat(ez + iz0, 5)])
 
-    # boundary faces, BuildBoundaryElements(matIdZmin, matIdXmin, matIdYmin, matIdXmax, matIdYmax, matIdZmax)
-    # called with matids[1..6]; the loops use: z-faces (Zmin,Zmax), y-faces (Ymin,Ymax), x-faces (Xmin,Xmax)
     m_zmin, m_xmin, m_ymin, m_xmax, m_ymax, m_zmax = bc_matids
     face_topo = capi.TRI if tetrahedra else capi.QUAD
+    per_face = 2 if tetrahedra else 1
 
-    def emit(matid, faces):
-        if blocks and blocks[-1][0] == face_topo and blocks[-1][1] == matid:
-            blocks[-1] = (face_topo, matid, np.concatenate([blocks[-1][2], faces], axis=0))
+    def emit(matid, faces, layer):
+        layer = np.repeat(layer, per_face)
+        if blocks[-1][0] == face_topo and blocks[-1][1] == matid:
+            blocks[-1][2] = np.concatenate([blocks[-1][2], faces], axis=0)
+            blocks[-1][3] = np.concatenate([blocks[-1][3], layer], axis=0)
         else:
-            blocks.append((face_topo, matid, faces))
+            blocks.append([face_topo, matid, faces, layer])
 
     # top/bottom: iZ in {0, nz}; loops iY, iX
-    for izf, matid in ((0, m_zmin), (nz, m_zmax)):
+    for izf, matid, present in ((0, m_zmin, iz0 == 0), (nz, m_zmax, iz1 == nz)):
+        if not present:
+            continue
         fy, fx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
         fx, fy = fx.reshape(-1), fy.reshape(-1)
-        f = izf * sz + fy * sy + fx
+        f = (izf - iz0) * sz + fy * sy + fx
         if not tetrahedra:
             faces = np.stack([f, f + 1, f + sy + 1, f + sy], axis=1)
         else:
@@ -238,14 +245,13 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
             ta = np.stack([f, f + 1, f + sy + np.where(odd, 1, 0)], axis=1)
             tb = np.stack([f + np.where(odd, 0, 1), f + sy, f + sy + 1], axis=1)
             faces = np.stack([ta, tb], axis=1).reshape(-1, 3)
-        emit(matid, faces)
+        emit(matid, faces, np.full(len(f), 0 if izf == 0 else nz - 1))
     # left/right: for iZ: for iY in {0, ny}: for iX
-    per_z = []
-    for izf in range(nz):
+    for izl in range(nzl):
         for iyf, matid in ((0, m_ymin), (ny, m_ymax)):
             fx = np.arange(nx)
-            f = izf * sz + iyf * sy + fx
-            cnt = fx + iyf + izf
+            f = izl * sz + iyf * sy + fx
+            cnt = fx + iyf + izl + iz0
             if not tetrahedra:
                 faces = np.stack([f, f + 1, f + sz + 1, f + sz], axis=1)
             else:
@@ -253,35 +259,34 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
                 ta = np.stack([f, f + 1, f + sz + np.where(odd, 1, 0)], axis=1)
                 tb = np.stack([f + np.where(odd, 0, 1), f + sz + 1, f + sz], axis=1)
                 faces = np.stack([ta, tb], axis=1).reshape(-1, 3)
-            per_z.append((matid, faces))
-    for matid, faces in per_z:
-        emit(matid, faces)
+            emit(matid, faces, np.full(len(f), izl + iz0))
     # front/back: for iZ: for iY: for iX in {0, nx}
-    fz, fy = np.meshgrid(np.arange(nz), np.arange(ny), indexing="ij")
+    fz, fy = np.meshgrid(np.arange(nzl), np.arange(ny), indexing="ij")
     fz, fy = fz.reshape(-1), fy.reshape(-1)
     pieces = []
     for ixf, matid in ((0, m_xmin), (nx, m_xmax)):
         f = fz * sz + fy * sy + ixf
-        cnt = ixf + fy + fz
+        cnt = ixf + fy + fz + iz0
         if not tetrahedra:
-            faces = np.stack([f, f + sy, f + sz + sy, f + sz], axis=1)
+            faces = np.stack([f, f + sy, f + sz + sy, f + sz], axis=1)[:, None, :]
         else:
             odd = (cnt % 2) == 1
             ta = np.stack([f, f + sy, f + sz + np.where(odd, sy, 0)], axis=1)
             tb = np.stack([f + np.where(odd, 0, sy), f + sz + sy, f + sz], axis=1)
             faces = np.stack([ta, tb], axis=1)  # [nface][2][3]
         pieces.append((matid, faces))
-    # interleave: for each (iZ,iY): xmin face(s) then xmax face(s)
+    # interleaved: for each (iZ,iY): the xmin face(s) then the xmax face(s)
     (m0, f0), (m1, f1) = pieces
     if m0 == m1:
-        inter = np.stack([f0, f1], axis=1)
-        emit(m0, inter.reshape(-1, f0.shape[-1]))
+        inter = np.stack([f0, f1], axis=1)  # [k][2][per_face][nc]
+        emit(m0, inter.reshape(-1, f0.shape[-1]), np.repeat(fz + iz0, 2))
     else:
-        k = f0.shape[0]
-        for r in range(k):
-            emit(m0, f0[r].reshape(-1, f0.shape[-1]))
-            emit(m1, f1[r].reshape(-1, f1.shape[-1]))
-    return nodes, blocks
+        for r in range(f0.shape[0]):
+            emit(m0, f0[r].reshape(-1, f0.shape[-1]), np.array([fz[r] + iz0]))
+            emit(m1, f1[r].reshape(-1, f1.shape[-1]), np.array([fz[r] + iz0]))
+    if with_layers:
+        return nodes, [tuple(b) for b in blocks]
+    return nodes, [tuple(b[:3]) for b in blocks]
 
 
 def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0):
