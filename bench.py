@@ -160,9 +160,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- one-off setup (reported, not timed as assembly): mesh flatten, pattern, scatter maps ------------------
+    # N > 1: ONE global mesh of n x n x (n*N) elements, z-slab per rank, rows owned by the rank that first touches
+    # them, interface-row contributions exchanged over NCCL every step (neopz_b200/distributed.py) -> weak scaling
+    from neopz_b200 import distributed
     t0 = time.time()
     ns = 3 if a.phys == "elasticity" else 1
-    mesh = gridmesh.grid_mesh(a.n, a.p, ns, tetrahedra=a.topo == "tet", perturb=0.1)
+    slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=0.1)
+    mesh = slab.mesh
     t_flat = time.time() - t0
     if a.phys == "poisson":
         mat = sm.TPZMatPoisson(1, 3)
@@ -171,15 +175,17 @@ def main():
     else:
         mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
         mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
-    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine)
+    sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine) if world > 1 else None
+    strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
     t0 = time.time()
-    ia, ja = strmat.Create()
+    ia, ja = sharded.Create() if sharded else strmat.Create()
     torch.cuda.synchronize()
     t_create = time.time() - t0
     nvol = len(mesh.blocks[0].elnodes)
-    neq, nnz = mesh.neq, len(ja)
+    neq, nnz = slab.nown, len(ja)
+    step_async = sharded.AssembleDevice if sharded else strmat.ctx.assemble_async
 
     def barrier():
         if world > 1:
@@ -188,7 +194,7 @@ def main():
 
     # ---- device-resident timing ---------------------------------------------------------------------
     for _ in range(max(3, a.warmup)):
-        strmat.ctx.assemble_async()
+        step_async()
     barrier()
     k0 = strmat.ctx.counters()[0]
     stop, samples = threading.Event(), []
@@ -201,7 +207,7 @@ def main():
     e_all0.record(stream)
     for s0, s1 in evs:
         s0.record(stream)
-        strmat.ctx.assemble_async()
+        step_async()
         s1.record(stream)
     e_all1.record(stream)
     barrier()
@@ -220,17 +226,22 @@ def main():
     e2e = None
     if not a.no_e2e:
         a_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
-        r_host = torch.empty(neq, dtype=torch.float64).pin_memory()
+        r_host = torch.empty(mesh.neq, dtype=torch.float64).pin_memory()
         x_host = torch.from_numpy(mesh.nodes.copy()).pin_memory()
         a_np, r_np, x_np = a_host.numpy(), r_host.numpy(), x_host.numpy()
         ksteps = max(2, min(a.steps, 5))
-        strmat.ctx.set_nodes(x_np)
-        strmat.ctx.assemble(a_np, r_np)  # warm-up
+        def e2e_step():
+            strmat.ctx.set_nodes(x_np)          # H2D: node coordinates (the geometry input of the step)
+            if sharded:
+                sharded.AssembleDevice()        # kernels + NCCL interface exchange
+                strmat.ctx.download(a_np, r_np)  # D2H of the CSR values and the load vector
+            else:
+                strmat.ctx.assemble(a_np, r_np)  # kernels + D2H
+        e2e_step()  # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
-            strmat.ctx.set_nodes(x_np)          # H2D: node coordinates (the geometry input of the step)
-            strmat.ctx.assemble(a_np, r_np)     # kernels + D2H of the CSR values and the load vector
+            e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / ksteps
         if world > 1:
@@ -292,7 +303,8 @@ def main():
             "dof_per_s": neq * world / (ms_per_step * 1e-3),
             "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
+            "config": {"workload": workload_name(a) if world == 1 else workload_name(a).replace(f"{a.n}^3", f"{a.n}x{a.n}x{a.n * world}") +
+                       f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
                        "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

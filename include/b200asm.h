@@ -112,6 +112,10 @@ int b200asm_synchronize(b200asm_ctx *ctx);
 int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_host);
 /* device pointers of the resident CSR values / rhs (for a GPU solver downstream) */
 int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev);
+/* Multi-GPU interface exchange (row-sharded assembly, neopz_b200/distributed.py): adds n values received from the
+ * neighbouring rank into the resident CSR values (target 0) or rhs (target 1) at precomputed, distinct
+ * positions: dst[positions[k]] += values[k].  positions/values are DEVICE pointers; asynchronous. */
+int b200asm_scatter_add(b200asm_ctx *ctx, int target, const int32_t *positions_dev, const double *values_dev, int64_t n);
 /* number of kernels launched by this context so far, and bytes moved H2D/D2H */
 int b200asm_counters(const b200asm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

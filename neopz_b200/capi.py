@@ -40,7 +40,7 @@ SYMBOLS = [
     "b200asm_create", "b200asm_destroy", "b200asm_last_error", "b200asm_set_stream", "b200asm_set_option",
     "b200asm_set_nodes", "b200asm_add_group", "b200asm_set_group_coef", "b200asm_clear_groups",
     "b200asm_set_pattern", "b200asm_assemble", "b200asm_assemble_async", "b200asm_synchronize",
-    "b200asm_download", "b200asm_device_pointers", "b200asm_counters",
+    "b200asm_download", "b200asm_device_pointers", "b200asm_counters", "b200asm_scatter_add",
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
 ]
 
@@ -73,6 +73,7 @@ def lib():
     L.b200asm_download.argtypes = [vp, dp, dp]
     L.b200asm_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.b200asm_counters.argtypes = [vp, ip64, ip64, ip64]
+    L.b200asm_scatter_add.argtypes = [vp, C.c_int, vp, vp, C.c_int64]
     L.b200asm_gauss_legendre.argtypes = [C.c_int, dp, dp]
     L.b200asm_tensor_rule.argtypes = [C.c_int, C.c_int, dp, dp]
     L.b200asm_shape_tables.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
@@ -221,6 +222,10 @@ class Context:
 
     def download(self, a_host=None, rhs_host=None):
         self._check(lib().b200asm_download(self._h, dptr(a_host), dptr(rhs_host)))
+
+    def scatter_add(self, target, positions_dev_ptr, values_dev_ptr, n):
+        """dst[positions[k]] += values[k] on the device (target 0: CSR values, 1: rhs); raw device pointers."""
+        self._check(lib().b200asm_scatter_add(self._h, target, C.c_void_p(positions_dev_ptr), C.c_void_p(values_dev_ptr), n))
 
     def device_pointers(self):
         a, r = C.c_void_p(), C.c_void_p()

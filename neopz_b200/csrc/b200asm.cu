@@ -47,6 +47,9 @@ struct VolParams {
     const double *__restrict__ phi;       // [nq][N]
     const double *__restrict__ dphi;      // [nq][3][N]
     const double *__restrict__ dng;       // [nq][3][NN] gradients of the corner (geometry) functions
+    const double *__restrict__ dng_t;     // [3][NN][nq]  same, point index fastest (DMMA kernels)
+    const double *__restrict__ dphi_pad;  // [nq][3][NP]  rows padded to NP = 16*ceil(N/16) doubles (DMMA kernels)
+    const double *__restrict__ phi_pad;   // [nq][NP]
     const double *__restrict__ force;     // optional [nel][nq][NS]
     const int32_t *__restrict__ smap;     // [nbatch][TILE*TILE][EPB*NT]
     const int32_t *__restrict__ smapT;    // same, transposed entry (full storage only)
@@ -290,6 +293,11 @@ __global__ void __launch_bounds__(C::NTHREADS) assemble_volume_kernel(const VolP
     }
 }
 
+// interface exchange: dst[pos[k]] += val[k], positions are distinct (one per received CSR entry)
+__global__ void scatter_add_kernel(double *__restrict__ dst, const int32_t *__restrict__ pos, const double *__restrict__ val, int64_t n) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) dst[pos[k]] += val[k];
+}
+
 // scatter-map construction for a volume group: one thread per (batch, tile entry, slot)
 template <class C>
 __global__ void build_volume_smap_kernel(int64_t nel, int64_t nbatch, const int32_t *__restrict__ dest,
@@ -495,6 +503,7 @@ struct Group {
     double coef[16];
     int32_t *d_elnodes = nullptr, *d_dest = nullptr, *d_smap = nullptr, *d_smapT = nullptr;
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
+    double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr;
     size_t smap_len = 0;
 };
 
@@ -670,6 +679,7 @@ int ncorner_of(int topology) {
 void free_group(Group &g) {
     cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
     cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
+    cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad);
     g = Group();
 }
 
@@ -846,6 +856,24 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     if ((rc = upload(ctx, &g.d_phi, gi->phi, (size_t)g.nq * g.n))) return rc;
     if ((rc = upload(ctx, &g.d_dphi, gi->dphi, (size_t)g.nq * g.dim * g.n))) return rc;
     if ((rc = upload(ctx, &g.d_dng, dng.data(), dng.size()))) return rc;
+    std::vector<double> dng_t, dphi_pad, phi_pad;
+    if (volume) {
+        // table layouts of the DMMA kernels (gram_mma.cuh): coalesced / whole-line accesses
+        const int np = ((g.n + 15) / 16) * 16;
+        dng_t.assign((size_t)3 * g.nn * g.nq, 0.0);
+        dphi_pad.assign((size_t)g.nq * 3 * np, 0.0);
+        phi_pad.assign((size_t)g.nq * np, 0.0);
+        for (int q = 0; q < g.nq; q++)
+            for (int d = 0; d < 3; d++) {
+                for (int a = 0; a < g.nn; a++) dng_t[((size_t)d * g.nn + a) * g.nq + q] = dng[((size_t)q * 3 + d) * g.nn + a];
+                for (int i = 0; i < g.n; i++) dphi_pad[((size_t)q * 3 + d) * np + i] = gi->dphi[((size_t)q * 3 + d) * g.n + i];
+            }
+        for (int q = 0; q < g.nq; q++)
+            for (int i = 0; i < g.n; i++) phi_pad[(size_t)q * np + i] = gi->phi[(size_t)q * g.n + i];
+        if ((rc = upload(ctx, &g.d_dng_t, dng_t.data(), dng_t.size()))) return rc;
+        if ((rc = upload(ctx, &g.d_dphi_pad, dphi_pad.data(), dphi_pad.size()))) return rc;
+        if ((rc = upload(ctx, &g.d_phi_pad, phi_pad.data(), phi_pad.size()))) return rc;
+    }
     if (gi->force && volume)
         if ((rc = upload(ctx, &g.d_force, gi->force, (size_t)g.nel * g.nq * g.ns))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));  // dest32 / dng are stack-owned
@@ -913,6 +941,7 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             p.nel = g.nel; p.nbatch = g.nbatch; p.nq = g.nq; p.kind = g.kind;
             p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest; p.qw = g.d_qw; p.phi = g.d_phi;
             p.dphi = g.d_dphi; p.dng = g.d_dng; p.force = g.d_force; p.smap = g.d_smap; p.smapT = g.d_smapT;
+            p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad;
             p.a = ctx->d_a; p.rhs = ctx->d_rhs;
             memcpy(p.coef, g.coef, sizeof(p.coef));
             if (g.mma >= 0 && ctx->engine == 1) {
@@ -969,6 +998,20 @@ extern "C" int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_ho
     int rc = b200asm_assemble_async(ctx);
     if (rc) return rc;
     return b200asm_download(ctx, a_host, rhs_host);
+}
+
+extern "C" int b200asm_scatter_add(b200asm_ctx *ctx, int target, const int32_t *positions_dev, const double *values_dev, int64_t n) {
+    if (!ctx || n < 0 || (n && (!positions_dev || !values_dev)) || (target != 0 && target != 1))
+        return fail(ctx, B200ASM_EINVAL, "scatter_add: bad arguments");
+    double *dst = target == 0 ? ctx->d_a : ctx->d_rhs;
+    if (!dst) return fail(ctx, B200ASM_ESTATE, "scatter_add: nothing assembled");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 8);
+    scatter_add_kernel<<<grid, 256, 0, ctx->stream>>>(dst, positions_dev, values_dev, n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
 }
 
 extern "C" int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev) {

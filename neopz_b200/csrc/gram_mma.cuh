@@ -10,13 +10,13 @@
 //
 // Mapping (one warp per element, no block-level synchronisation at all):
 //   phase 1  lane q: Jacobian, inverse, w|detJ| of integration point q            -> per-warp smem
-//   phase 2  per chunk of QC=4 points: lanes over (point, shape) compute the panel rows
+//   phase 2  per chunk of QC=4 points: lane <-> shape function computes the panel rows
 //            P[(q,d)][i] = sqrt(w|detJ|) * sum_e jacinv(e,d) dphi(e,i)            -> per-warp smem [12][LD]
 //   phase 3  3 k-steps of 4 rows: one fragment load per 8-column block, then one DMMA per upper tile
 //            (fragment of block b: lane l reads P[4s+(l&3)][8b+(l>>2)]; it is the A operand of tile
 //            rows b and the B operand of tile columns b, PTX ISA "mma.m8n8k4" f64 layouts)
 //   epilogue lane l holds C[8bi+(l>>2)][8bj+2(l&3)+{0,1}] of every tile: scatter through the map.
-// LD = 8*NB (+8 when NB is even) doubles keeps the four k-rows of a fragment in disjoint banks.
+// LD = 8*NB + 4 doubles keeps the 16 lanes of a half-warp (4 k-rows x 4 columns) in 16 distinct banks.
 #pragma once
 
 template <int NN_, int N_, int WPC_, int MINB_>
@@ -24,10 +24,11 @@ struct MmaCfg {
     static constexpr int NN = NN_, N = N_, WPC = WPC_, MINB = MINB_;
     static constexpr int NB = (N + 7) / 8;
     static constexpr int MP = 8 * NB;
-    static constexpr int LD = (NB % 2 == 0) ? MP + 8 : MP;
+    static constexpr int LD = MP + 4;   // 4 k-rows x 4 column groups of a half-warp fall into 16 distinct 8-byte banks
+    static constexpr int NP = ((N + 15) / 16) * 16;  // padded row length of the shape tables (whole 128-byte lines)
     static constexpr int NTILES = NB * (NB + 1) / 2;
     static constexpr int QC = 4, KC = 12;
-    static constexpr int JS = 11;
+    static constexpr int JS = 10;       // sqrt(w|detJ|)*jacinv (9) and w|detJ|
     static constexpr int XSP = NN * 3 + ((NN * 3) & 1);
     static constexpr int SLOTS = NTILES * 2 * 32;  // scatter-map entries per element
     __host__ __device__ static int qstride(int nq) { return ((nq + 31) / 32) * 32; }  // JI is [JS][qstride]
@@ -43,7 +44,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 
 template <class C>
 __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel(const VolParams p) {
-    constexpr int NN = C::NN, N = C::N, NB = C::NB, LD = C::LD, NTILES = C::NTILES, QC = C::QC, KC = C::KC, JS = C::JS;
+    constexpr int NN = C::NN, N = C::N, NB = C::NB, LD = C::LD, NTILES = C::NTILES, QC = C::QC, KC = C::KC, JS = C::JS, NP = C::NP;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nq = p.nq;
@@ -77,11 +78,11 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
         __syncwarp();
         // ---- phase 1: geometry at the integration points (Geom/TPZGeoCube.h:141-149, Mesh/pzgeoel.cpp:1309-1336)
         for (int q = lane; q < nq; q += 32) {
-            const double *dn = p.dng + (size_t)q * 3 * NN;
+            const double *dn = p.dng_t + q;  // [3][NN][nq]: consecutive lanes read consecutive doubles
             double j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0, j20 = 0, j21 = 0, j22 = 0;
 #pragma unroll
             for (int a = 0; a < NN; a++) {
-                const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a), d2 = __ldg(dn + 2 * NN + a);
+                const double d0 = __ldg(dn + (size_t)a * nq), d1 = __ldg(dn + (size_t)(NN + a) * nq), d2 = __ldg(dn + (size_t)(2 * NN + a) * nq);
                 const double x = Xs[a * 3], y = Xs[a * 3 + 1], z = Xs[a * 3 + 2];
                 j00 += x * d0; j01 += x * d1; j02 += x * d2;
                 j10 += y * d0; j11 += y * d1; j12 += y * d2;
@@ -96,19 +97,19 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             det += j00 * j11 * j22;
             if (fabs(det) < 1.e-12) det = 1.e-12;
             const double id = 1.0 / det;
+            const double w = __ldg(p.qw + q) * fabs(det);  // weight *= fabs(detjac)
+            const double sid = sqrt(w) * id;
             double *o = JI + q;  // field k of point q at JI[k*QS + q]: conflict-free stores, broadcast reads
-            o[0 * QS] = (-j12 * j21 + j11 * j22) * id;
-            o[1 * QS] = (j02 * j21 - j01 * j22) * id;
-            o[2 * QS] = (-j02 * j11 + j01 * j12) * id;
-            o[3 * QS] = (j12 * j20 - j10 * j22) * id;
-            o[4 * QS] = (-j02 * j20 + j00 * j22) * id;
-            o[5 * QS] = (j02 * j10 - j00 * j12) * id;
-            o[6 * QS] = (-j11 * j20 + j10 * j21) * id;
-            o[7 * QS] = (j01 * j20 - j00 * j21) * id;
-            o[8 * QS] = (-j01 * j10 + j00 * j11) * id;
-            const double w = __ldg(p.qw + q) * fabs(det);
+            o[0 * QS] = (-j12 * j21 + j11 * j22) * sid;
+            o[1 * QS] = (j02 * j21 - j01 * j22) * sid;
+            o[2 * QS] = (-j02 * j11 + j01 * j12) * sid;
+            o[3 * QS] = (j12 * j20 - j10 * j22) * sid;
+            o[4 * QS] = (-j02 * j20 + j00 * j22) * sid;
+            o[5 * QS] = (j02 * j10 - j00 * j12) * sid;
+            o[6 * QS] = (-j11 * j20 + j10 * j21) * sid;
+            o[7 * QS] = (j01 * j20 - j00 * j21) * sid;
+            o[8 * QS] = (-j01 * j10 + j00 * j11) * sid;
             o[9 * QS] = w;
-            o[10 * QS] = sqrt(w);
         }
         __syncwarp();
 
@@ -124,19 +125,18 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
 #pragma unroll
                 for (int ql = 0; ql < QC; ql++) {
                     const int q = q0 + ql;
-                    const double *dp = p.dphi + (size_t)q * 3 * N + i;
+                    const double *dp = p.dphi_pad + (size_t)q * 3 * NP + i;  // rows padded to whole 128-byte lines
                     d[ql][0] = q < nq ? __ldg(dp) : 0.0;
-                    d[ql][1] = q < nq ? __ldg(dp + N) : 0.0;
-                    d[ql][2] = q < nq ? __ldg(dp + 2 * N) : 0.0;
+                    d[ql][1] = q < nq ? __ldg(dp + NP) : 0.0;
+                    d[ql][2] = q < nq ? __ldg(dp + 2 * NP) : 0.0;
                 }
 #pragma unroll
                 for (int ql = 0; ql < QC; ql++) {
                     const int q = min(q0 + ql, nq - 1);  // tail rows: d == 0 -> zero rows
                     const double *ji = JI + q;
-                    const double sw = ji[10 * QS];
-                    const double g0 = (ji[0 * QS] * d[ql][0] + ji[3 * QS] * d[ql][1] + ji[6 * QS] * d[ql][2]) * sw;
-                    const double g1 = (ji[1 * QS] * d[ql][0] + ji[4 * QS] * d[ql][1] + ji[7 * QS] * d[ql][2]) * sw;
-                    const double g2 = (ji[2 * QS] * d[ql][0] + ji[5 * QS] * d[ql][1] + ji[8 * QS] * d[ql][2]) * sw;
+                    const double g0 = ji[0 * QS] * d[ql][0] + ji[3 * QS] * d[ql][1] + ji[6 * QS] * d[ql][2];
+                    const double g1 = ji[1 * QS] * d[ql][0] + ji[4 * QS] * d[ql][1] + ji[7 * QS] * d[ql][2];
+                    const double g2 = ji[2 * QS] * d[ql][0] + ji[5 * QS] * d[ql][1] + ji[8 * QS] * d[ql][2];
                     double *row = Pn + (3 * ql) * LD + i;
                     row[0] = g0;
                     row[LD] = g1;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             double f = 0.0;
             for (int q = 0; q < nq; q++) {
                 const double fq = p.force ? p.force[el * nq + q] : p.coef[1];
-                f += JI[9 * QS + q] * p.coef[0] * __ldg(p.phi + (size_t)q * N + lane) * fq;
+                f += JI[9 * QS + q] * p.coef[0] * __ldg(p.phi_pad + (size_t)q * NP + lane) * fq;
             }
             atomicAdd(p.rhs + p.dest[el * N + lane], f);
         }

@@ -120,8 +120,6 @@ def slab_mesh(nxy, nz_total, rank, world, porder, nstate, tetrahedra=False, bc_m
     nown = int(size[own].sum())
     nupper = int(size[upper].sum())
     ext2glob = np.empty(nghost + nown + nupper, dtype=np.int64)
-    for c_new, c_old in enumerate(order):
-        pass  # (vectorised below)
     starts = new_pos
     reps = new_size
     base = np.repeat(glob[order], reps)
@@ -136,6 +134,8 @@ def slab_mesh(nxy, nz_total, rank, world, porder, nstate, tetrahedra=False, bc_m
     for blk, (_t, _m, _e, layer) in zip(full.blocks, blocks):
         keep = (layer >= z0) & (layer < z1)
         conn = newid[blk.connects[keep]]
+        if len(conn) == 0:
+            continue
         assert conn.min() >= 0
         active = [s for s, loc in enumerate(SIDES[blk.topology]) if side_nshape(blk.topology, loc, porder) > 0]
         d = new_pos[conn[:, active]]
