@@ -35,12 +35,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=128, help="grid divisions per direction (per GPU)")
+    ap.add_argument("--grid", dest="n", type=int, default=128, help="grid divisions per direction (per GPU)")
     ap.add_argument("--p", type=int, default=2)
     ap.add_argument("--phys", default="poisson", choices=["poisson", "elasticity"])
     ap.add_argument("--topo", default="hex", choices=["hex", "tet"])
     ap.add_argument("--cpu-n", type=int, default=0, help="grid size of the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--engine", type=int, default=1, help="0: register-tile DFMA kernels, 1: DMMA panel kernels where available")
+    ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -175,8 +176,8 @@ def main():
     else:
         mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
         mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
-    sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine) if world > 1 else None
-    strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine)
+    sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter) if world > 1 else None
+    strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
     t0 = time.time()
@@ -306,7 +307,7 @@ def main():
             "config": {"workload": workload_name(a) if world == 1 else workload_name(a).replace(f"{a.n}^3", f"{a.n}x{a.n}x{a.n * world}") +
                        f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
-                       "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
+                       "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}
     print(json.dumps(line))

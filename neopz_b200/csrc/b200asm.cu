@@ -55,6 +55,8 @@ struct VolParams {
     const int32_t *__restrict__ smapT;    // same, transposed entry (full storage only)
     double *__restrict__ a;
     double *__restrict__ rhs;
+    int atomic;  // 1: red.global.add.f64; 0: plain read-modify-write (the launch covers one colour: no two
+                 // elements of it share an equation, so no two threads touch the same entry)
     double coef[16];
 };
 
@@ -75,8 +77,14 @@ struct VolCfg {
 };
 
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+// scatter-add of one entry: atomic, or plain when the launch is conflict-free by colouring
+__device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) {
+    if (atomic) atomicAdd(addr, v);
+    else *addr += v;
+}
 
 #include "gram_mma.cuh"
+#include "gram_mma_team.cuh"
 
 // decode the linear index of an upper-triangular tile into (bi, bj), bi <= bj
 template <int NTB>
@@ -278,17 +286,17 @@ __global__ void __launch_bounds__(C::NTHREADS) assemble_volume_kernel(const VolP
 #pragma unroll
                 for (int c = 0; c < TILE; c++) {
                     const int32_t pos = sm[(r * TILE + c) * C::SLOTS];
-                    if (pos >= 0) red_add(p.a + pos, acc[r][c]);
+                    if (pos >= 0) scatter_add(p.a + pos, acc[r][c], p.atomic);
                     if (smT) {
                         const int32_t posT = smT[(r * TILE + c) * C::SLOTS];
-                        if (posT >= 0) red_add(p.a + posT, acc[r][c]);
+                        if (posT >= 0) scatter_add(p.a + posT, acc[r][c], p.atomic);
                     }
                 }
         }
 #pragma unroll
         for (int k = 0; k < FPT; k++) {
             const int it = tid + k * NTHREADS;
-            if (it < nloc * M) red_add(p.rhs + p.dest[e0 * M + it], facc[k]);
+            if (it < nloc * M) scatter_add(p.rhs + p.dest[e0 * M + it], facc[k], p.atomic);
         }
     }
 }
@@ -347,7 +355,9 @@ __global__ void build_volume_smap_kernel(int64_t nel, int64_t nbatch, const int3
 // with w = weight*|detjac| of the 2-D Gram-Schmidt branch of TPZGeoEl::Jacobian (pzgeoel.cpp:1228-1295)
 // ------------------------------------------------------------------------------------------------
 struct BcParams {
-    int64_t nel;
+    int64_t nel;      // elements of the group (stride of the entry-major scatter map)
+    int64_t el0, el1; // this launch covers elements [el0, el1) (one colour, or the whole group)
+    int atomic;
     int nq;
     const double *__restrict__ xyz;
     const int32_t *__restrict__ elnodes;
@@ -364,8 +374,8 @@ struct BcParams {
 
 template <int NN, int N, int NS>
 __global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
-    const int64_t el = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (el >= p.nel) return;
+    const int64_t el = p.el0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (el >= p.el1) return;
     double X[NN][3];
 #pragma unroll
     for (int a = 0; a < NN; a++) {
@@ -435,10 +445,10 @@ __global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
                     if (mab == 0.0 && mba == 0.0) continue;
                     const size_t idx = ((size_t)((i * N + j) * NS + a) * NS + b) * p.nel + el;
                     const int32_t pos = p.smap[idx];
-                    if (pos >= 0 && mab != 0.0) red_add(p.a + pos, mab * S[i][j]);
+                    if (pos >= 0 && mab != 0.0) scatter_add(p.a + pos, mab * S[i][j], p.atomic);
                     if (p.smapT) {
                         const int32_t posT = p.smapT[idx];
-                        if (posT >= 0 && mba != 0.0) red_add(p.a + posT, mba * S[i][j]);
+                        if (posT >= 0 && mba != 0.0) scatter_add(p.a + posT, mba * S[i][j], p.atomic);
                     }
                 }
 #pragma unroll
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
 #pragma unroll
         for (int a = 0; a < NS; a++) {
             const double v = p.coef[9 + a];
-            if (v != 0.0) red_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T[i]);
+            if (v != 0.0) scatter_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T[i], p.atomic);
         }
 }
 
@@ -505,6 +515,10 @@ struct Group {
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
     double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr;
     size_t smap_len = 0;
+    // element colouring (B200ASM_SCATTER_COLORED): elements are stored sorted by colour; seg = colour boundaries
+    // ({0, nel} when not coloured); seg_smap = offset of every segment's scatter map (register-tile kernels)
+    std::vector<int64_t> seg;
+    std::vector<size_t> seg_smap;
 };
 
 }  // namespace
@@ -639,12 +653,42 @@ template <class C>
 MmaEntry make_mma_entry(int topology, int porder) {
     return MmaEntry{topology, porder, 1, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_mma<C>, &launch_mma_smap<C>, &prepare_mma<C>};
 }
-const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2)};
+// team kernels (gram_mma_team.cuh):   NN  N  NS  warps/element  elements/CTA  min CTAs/SM
+using HexP2ElastTeam = TeamCfg<8, 27, 3, 5, 1, 2>;
+using TetP2ElastTeam = TeamCfg<4, 10, 3, 3, 2, 2>;
+using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
+
+template <class C>
+cudaError_t launch_team(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
+    assemble_gram_team_kernel<C><<<grid, C::NTHREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t launch_team_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int64_t *ja, int symmetric,
+                             int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_team_smap_kernel<C><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t prepare_team(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_gram_team_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_gram_team_kernel<C>, C::NTHREADS, smem);
+}
+template <class C>
+MmaEntry make_team_entry(int topology, int porder) {
+    return MmaEntry{topology, porder, C::NS, C::SLOTS, C::NTHREADS, C::EPC, &C::smem_bytes, &launch_team<C>, &launch_team_smap<C>, &prepare_team<C>};
+}
+// wpc = elements processed concurrently by one CTA
+const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2),
+                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1)};
+// (tetrahedra p=2 elasticity stays on the register-tile kernel: 130 M el/s vs 99 M el/s for TetP2ElastTeam on a 40^3x5
+//  mesh — padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
 
 template <int NN, int N, int NS>
 cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
-    const int grid = (int)((p.nel + 127) / 128);
+    const int grid = (int)((p.el1 - p.el0 + 127) / 128);
     assemble_bc_kernel<NN, N, NS><<<grid, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
@@ -676,6 +720,28 @@ int ncorner_of(int topology) {
     return -1;
 }
 
+// Greedy element colouring: two elements that share an equation get different colours (the idea of the
+// reference's TPZStructMatrix::ComputeElementColors, StrMatrix/TPZStructMatrix.cpp:104-161, with a 64-bit colour
+// mask per equation instead of its O(nel * ncolours) sweeps).  Returns the number of colours, -1 if more than 64.
+int colour_elements(int64_t nel, int m, const int64_t *dest, int64_t neq_hint, std::vector<int32_t> &colour) {
+    int64_t neq = neq_hint;
+    for (int64_t k = 0; k < nel * m; k++) neq = std::max<int64_t>(neq, dest[k] + 1);
+    std::vector<uint64_t> used((size_t)neq, 0);
+    colour.assign((size_t)nel, 0);
+    int ncol = 0;
+    for (int64_t el = 0; el < nel; el++) {
+        uint64_t u = 0;
+        for (int k = 0; k < m; k++) u |= used[dest[el * m + k]];
+        if (~u == 0) return -1;
+        const int c = __builtin_ctzll(~u);
+        colour[el] = c;
+        ncol = std::max(ncol, c + 1);
+        const uint64_t bit = 1ull << c;
+        for (int k = 0; k < m; k++) used[dest[el * m + k]] |= bit;
+    }
+    return ncol;
+}
+
 void free_group(Group &g) {
     cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
     cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
@@ -693,9 +759,14 @@ int build_smaps(b200asm_ctx *ctx, const int64_t *d_ja) {
         } else if (g.mma >= 0 && ctx->engine == 1) {
             g.smap_len = (size_t)g.nel * kMma[g.mma].slots;
         } else {
+            // batches never straddle a colour: every segment has its own batches and its own piece of the map
             const VolEntry &ve = kVol[g.cfg];
-            g.nbatch = (g.nel + ve.epb - 1) / ve.epb;
-            g.smap_len = (size_t)g.nbatch * ve.tile * ve.tile * ve.slots;
+            g.seg_smap.assign(g.seg.size(), 0);
+            for (size_t c = 0; c + 1 < g.seg.size(); c++) {
+                const int64_t nb = (g.seg[c + 1] - g.seg[c] + ve.epb - 1) / ve.epb;
+                g.seg_smap[c + 1] = g.seg_smap[c] + (size_t)nb * ve.tile * ve.tile * ve.slots;
+            }
+            g.smap_len = g.seg_smap.back();
         }
         CK(cudaMalloc((void **)&g.d_smap, std::max<size_t>(g.smap_len, 1) * sizeof(int32_t)));
         if (!ctx->symmetric) CK(cudaMalloc((void **)&g.d_smapT, std::max<size_t>(g.smap_len, 1) * sizeof(int32_t)));
@@ -709,8 +780,14 @@ int build_smaps(b200asm_ctx *ctx, const int64_t *d_ja) {
             CK(kMma[g.mma].launch_smap(g.nel, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT, ctx->d_missing,
                                         grid, ctx->stream));
         } else {
-            CK(kVol[g.cfg].launch_smap(g.nel, g.nbatch, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT,
-                                        ctx->d_missing, grid, ctx->stream));
+            const VolEntry &ve = kVol[g.cfg];
+            for (size_t c = 0; c + 1 < g.seg.size(); c++) {
+                const int64_t n = g.seg[c + 1] - g.seg[c];
+                if (n == 0) continue;
+                const int64_t nb = (n + ve.epb - 1) / ve.epb;
+                CK(ve.launch_smap(n, nb, g.d_dest + g.seg[c] * g.m, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap + g.seg_smap[c],
+                                  g.d_smapT ? g.d_smapT + g.seg_smap[c] : nullptr, ctx->d_missing, grid, ctx->stream));
+            }
         }
         ctx->launches++;
     }
@@ -778,7 +855,8 @@ extern "C" int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream) {
 extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return B200ASM_EINVAL;
     if (!strcmp(name, "scatter")) {
-        if (value != B200ASM_SCATTER_ATOMIC) return fail(ctx, B200ASM_EINVAL, "scatter: only B200ASM_SCATTER_ATOMIC is implemented");
+        if (value != B200ASM_SCATTER_ATOMIC && value != B200ASM_SCATTER_COLORED) return fail(ctx, B200ASM_EINVAL, "scatter: unknown mode");
+        if (!ctx->groups.empty()) return fail(ctx, B200ASM_ESTATE, "scatter: set the mode before the first b200asm_add_group");
         ctx->scatter = (int)value;
         return 0;
     }
@@ -838,19 +916,39 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     g.m = g.n * g.ns;
     memcpy(g.coef, gi->coef, sizeof(g.coef));
 
+    // element order on the device: mesh order, or sorted by colour for the conflict-free scatter
+    std::vector<int64_t> order((size_t)g.nel);
+    for (int64_t e = 0; e < g.nel; e++) order[e] = e;
+    g.seg = {0, g.nel};
+    if (ctx->scatter == B200ASM_SCATTER_COLORED && g.nel > 0) {
+        std::vector<int32_t> colour;
+        const int ncol = colour_elements(g.nel, g.m, gi->dest, 0, colour);
+        if (ncol < 0) return fail(ctx, B200ASM_EINVAL, "add_group: the mesh needs more than 64 element colours");
+        std::vector<int64_t> count(ncol + 1, 0);
+        for (int64_t e = 0; e < g.nel; e++) count[colour[e] + 1]++;
+        for (int c = 0; c < ncol; c++) count[c + 1] += count[c];
+        g.seg.assign(count.begin(), count.end());
+        std::vector<int64_t> cursor(count.begin(), count.end() - 1);
+        for (int64_t e = 0; e < g.nel; e++) order[cursor[colour[e]]++] = e;  // stable within a colour
+    }
     // destination indices as int32 (the reference's own CSR loops are 32-bit: Matrix/pzsysmp.cpp:62,73)
     std::vector<int32_t> dest32((size_t)g.nel * g.m);
-    for (size_t k = 0; k < dest32.size(); k++) {
-        const int64_t d = gi->dest[k];
-        if (d < 0 || d > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "add_group: destination index out of int32 range");
-        dest32[k] = (int32_t)d;
+    std::vector<int32_t> elnodes((size_t)g.nel * g.nn);
+    for (int64_t e = 0; e < g.nel; e++) {
+        const int64_t src = order[e];
+        for (int k = 0; k < g.m; k++) {
+            const int64_t d = gi->dest[src * g.m + k];
+            if (d < 0 || d > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "add_group: destination index out of int32 range");
+            dest32[(size_t)e * g.m + k] = (int32_t)d;
+        }
+        for (int k = 0; k < g.nn; k++) elnodes[(size_t)e * g.nn + k] = gi->elnodes[src * g.nn + k];
     }
     // gradients of the geometric (corner) functions at the points = the p=1 shape gradients
     std::vector<double> gphi((size_t)g.nq * g.nn), dng((size_t)g.nq * g.dim * g.nn);
     if (b200asm_shape_tables(g.topology, 1, g.nq, gi->qpts, gphi.data(), dng.data()) != g.nn)
         return fail(ctx, B200ASM_EINVAL, "add_group: geometry table failed");
     int rc;
-    if ((rc = upload(ctx, &g.d_elnodes, gi->elnodes, (size_t)g.nel * g.nn))) return rc;
+    if ((rc = upload(ctx, &g.d_elnodes, elnodes.data(), elnodes.size()))) return rc;
     if ((rc = upload(ctx, &g.d_dest, dest32.data(), dest32.size()))) return rc;
     if ((rc = upload(ctx, &g.d_qw, gi->qwts, (size_t)g.nq))) return rc;
     if ((rc = upload(ctx, &g.d_phi, gi->phi, (size_t)g.nq * g.n))) return rc;
@@ -874,8 +972,13 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if ((rc = upload(ctx, &g.d_dphi_pad, dphi_pad.data(), dphi_pad.size()))) return rc;
         if ((rc = upload(ctx, &g.d_phi_pad, phi_pad.data(), phi_pad.size()))) return rc;
     }
-    if (gi->force && volume)
-        if ((rc = upload(ctx, &g.d_force, gi->force, (size_t)g.nel * g.nq * g.ns))) return rc;
+    std::vector<double> force;
+    if (gi->force && volume) {
+        const size_t per = (size_t)g.nq * g.ns;
+        force.resize((size_t)g.nel * per);
+        for (int64_t e = 0; e < g.nel; e++) memcpy(&force[(size_t)e * per], gi->force + (size_t)order[e] * per, per * sizeof(double));
+        if ((rc = upload(ctx, &g.d_force, force.data(), force.size()))) return rc;
+    }
     CK(cudaStreamSynchronize(ctx->stream));  // dest32 / dng are stack-owned
     ctx->groups.push_back(g);
     ctx->have_pattern = false;  // scatter maps must be rebuilt
@@ -927,47 +1030,63 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
     // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75
     CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
+    const int atomic = ctx->scatter == B200ASM_SCATTER_ATOMIC ? 1 : 0;
     for (const Group &g : ctx->groups) {
         if (g.nel == 0) continue;
+        const size_t nseg = g.seg.size() - 1;  // 1, or the number of colours
         if (g.kind == B200ASM_BC) {
             BcParams p;
             p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
             p.qw = g.d_qw; p.phi = g.d_phi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
-            p.a = ctx->d_a; p.rhs = ctx->d_rhs;
+            p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic;
             memcpy(p.coef, g.coef, sizeof(p.coef));
-            CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+            for (size_t c = 0; c < nseg; c++) {
+                p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];
+                if (p.el1 == p.el0) continue;
+                CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+                ctx->launches++;
+            }
+            continue;
+        }
+        const bool use_mma = g.mma >= 0 && ctx->engine == 1;
+        size_t smem = 0;
+        int per_sm = 1;
+        if (use_mma) {
+            smem = kMma[g.mma].smem(g.nq);
+            if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
+            CK(kMma[g.mma].prepare(smem, &per_sm));
         } else {
+            smem = kVol[g.cfg].smem(g.nq);
+            if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
+            CK(kVol[g.cfg].prepare(smem, &per_sm));
+        }
+        if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
+        for (size_t c = 0; c < nseg; c++) {
+            const int64_t e0 = g.seg[c], n = g.seg[c + 1] - g.seg[c];
+            if (n == 0) continue;
             VolParams p;
-            p.nel = g.nel; p.nbatch = g.nbatch; p.nq = g.nq; p.kind = g.kind;
-            p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest; p.qw = g.d_qw; p.phi = g.d_phi;
-            p.dphi = g.d_dphi; p.dng = g.d_dng; p.force = g.d_force; p.smap = g.d_smap; p.smapT = g.d_smapT;
+            p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = atomic;
+            p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
+            p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
+            p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;
             p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad;
             p.a = ctx->d_a; p.rhs = ctx->d_rhs;
             memcpy(p.coef, g.coef, sizeof(p.coef));
-            if (g.mma >= 0 && ctx->engine == 1) {
-                const MmaEntry &me = kMma[g.mma];
-                const size_t smem = me.smem(g.nq);
-                if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
-                int per_sm = 1;
-                CK(me.prepare(smem, &per_sm));
-                if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
-                const int64_t want = (g.nel + me.wpc - 1) / me.wpc;
-                const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm);
-                CK(me.launch(p, grid, smem, ctx->stream));
-                ctx->launches++;
-                continue;
-            }
-            const VolEntry &ve = kVol[g.cfg];
-            const size_t smem = ve.smem(g.nq);
-            if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
             // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)
-            int per_sm = 1;
-            CK(ve.prepare(smem, &per_sm));
-            if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
-            const int grid = (int)std::min<int64_t>(g.nbatch, (int64_t)ctx->num_sms * per_sm);
-            CK(ve.launch(p, grid, smem, ctx->stream));
+            if (use_mma) {
+                const MmaEntry &me = kMma[g.mma];
+                const size_t off = (size_t)e0 * me.slots;
+                p.nbatch = 0; p.smap = g.d_smap + off; p.smapT = g.d_smapT ? g.d_smapT + off : nullptr;
+                const int64_t want = (n + me.wpc - 1) / me.wpc;
+                CK(me.launch(p, (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
+            } else {
+                const VolEntry &ve = kVol[g.cfg];
+                p.nbatch = (n + ve.epb - 1) / ve.epb;
+                p.smap = g.d_smap + g.seg_smap[c]; p.smapT = g.d_smapT ? g.d_smapT + g.seg_smap[c] : nullptr;
+                CK(ve.launch(p, (int)std::min<int64_t>(p.nbatch, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
+            }
+            ctx->launches++;
         }
-        ctx->launches++;
     }
     return 0;
 }

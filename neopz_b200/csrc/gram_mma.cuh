@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
                 const double fq = p.force ? p.force[el * nq + q] : p.coef[1];
                 f += JI[9 * QS + q] * p.coef[0] * __ldg(p.phi_pad + (size_t)q * NP + lane) * fq;
             }
-            atomicAdd(p.rhs + p.dest[el * N + lane], f);
+            scatter_add(p.rhs + p.dest[el * N + lane], f, p.atomic);
         }
         // ---- scatter-add of the upper triangle ---------------------------------------------------
         const double s = p.coef[0];
@@ -180,11 +180,11 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             for (int k = 0; k < NTILES * 2; k++) posT[k] = __ldcs(smT + k * 32);
 #pragma unroll
             for (int k = 0; k < NTILES * 2; k++)
-                if (posT[k] >= 0) atomicAdd(p.a + posT[k], s * acc[k >> 1][k & 1]);
+                if (posT[k] >= 0) scatter_add(p.a + posT[k], s * acc[k >> 1][k & 1], p.atomic);
         }
 #pragma unroll
         for (int k = 0; k < NTILES * 2; k++)
-            if (pos[k] >= 0) atomicAdd(p.a + pos[k], s * acc[k >> 1][k & 1]);
+            if (pos[k] >= 0) scatter_add(p.a + pos[k], s * acc[k >> 1][k & 1], p.atomic);
     }
 }
 

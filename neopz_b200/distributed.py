@@ -203,7 +203,8 @@ class ShardedStructMatrix:
     A `local_assembler(mesh, materials, symmetric, ia, ja) -> (a, rhs)` may be injected instead (the CPU tests
     inject the oracle and run the exchange over gloo)."""
 
-    def __init__(self, slab: SlabMesh, materials, symmetric=True, device=0, local_assembler=None, nthreads=0, engine=None):
+    def __init__(self, slab: SlabMesh, materials, symmetric=True, device=0, local_assembler=None, nthreads=0, engine=None,
+                 scatter=None):
         import torch.distributed as dist
         self.dist = dist
         self.slab = slab
@@ -214,7 +215,7 @@ class ShardedStructMatrix:
         if local_assembler is None:
             from .strmatrix import TPZStructMatrixB200
             self.strmat = TPZStructMatrixB200(slab.mesh, materials, symmetric=symmetric, device=device, nthreads=nthreads,
-                                              engine=engine)
+                                              engine=engine, scatter=scatter)
         self.nthreads = nthreads
         self.ia = self.ja = None
 

@@ -106,6 +106,25 @@ def test_engines_agree(n, p, phys, tet):
     assert relF(res[(0, True)], res[(1, True)]) <= TOL
 
 
+@pytest.mark.parametrize("n,p,phys,tet,engine", [(5, 2, 0, 0, 1), (4, 2, 1, 0, 1), (4, 2, 1, 1, 0), (6, 1, 0, 0, 0), (4, 2, 0, 1, 1)])
+def test_colored_scatter_is_deterministic(n, p, phys, tet, engine):
+    """Conflict-free scatter by element colouring (no atomics): parity with the oracle and bit-reproducible results
+    (the reference is bit-reproducible too); the atomic mode agrees to rounding."""
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    mats = materials_for(phys, neumann=True)
+    for symmetric in (True, False):
+        runs = []
+        for _rep in range(2):
+            strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, engine=engine, scatter="colored")
+            ia, ja, a, rhs = strmat.CreateAssemble()
+            a2, rhs2 = strmat.Assemble()
+            assert np.array_equal(a, a2) and np.array_equal(rhs, rhs2)
+            runs.append((a, rhs))
+        assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(runs[0][0], a_ref) <= TOL and relF(runs[0][1], rhs_ref) <= TOL
+
+
 def _full_from_sym(ia, ja, a, neq):
     import scipy.sparse as sp
     U = sp.csr_matrix((a, ja, ia), shape=(neq, neq))
