@@ -47,6 +47,17 @@ def parse():
     return ap.parse_args()
 
 
+def kernel_name(a):
+    if a.engine == 1:
+        if a.phys == "poisson" and a.p == 2:
+            return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"
+        if a.phys == "poisson" and a.p >= 3:
+            return "assemble_gram_team_kernel (warp team per element, mma.sync.m8n8k4.f64)"
+        if a.phys == "elasticity" and a.topo == "hex":
+            return "assemble_gram_team_kernel (warp team per element, mma.sync.m8n8k4.f64)"
+    return "assemble_volume_kernel (register-tile DFMA)"
+
+
 def workload_name(a, n=None):
     n = n or a.n
     return f"3D {a.phys} H1 p={a.p} {a.topo} {n}^3 grid, sym CSR (TPZSSpStructMatrix), Dirichlet on all faces"
@@ -102,6 +113,28 @@ def run_reference(a, steps, warmup):
 
 # ------------------------------------------------------------------------------------------------
 def clocks_sampler(stop, samples, device):
+    """SM clock / throttle reasons DURING the timed region: NVML in-process (a few hundred samples per second);
+    nvidia-smi polling as the fallback."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap))
+        while not stop.is_set():
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx),
+                            str(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                           ["Active" if r & b else "Not Active" for _n, b in bits])
+            stop.wait(0.002)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
@@ -112,7 +145,7 @@ def clocks_sampler(stop, samples, device):
                 samples.append([x.strip() for x in out.split(",")])
         except Exception:
             pass
-        stop.wait(0.1)
+        stop.wait(0.05)
 
 
 def summarize_clocks(samples):
@@ -213,6 +246,14 @@ def main():
     e_all1.record(stream)
     barrier()
     stop.set()
+    # duration of the dominant kernel alone (the volume group's launches), CUDA events on the launching stream,
+    # taken right after the timed region so that the step timing above carries no extra event records
+    strmat.ctx.set_option("timing", 1)
+    vol_ms = []
+    for _ in range(min(a.steps, 5)):
+        step_async()
+        vol_ms.append(strmat.ctx.group_time_ms(strmat.group_of_block[0]))
+    strmat.ctx.set_option("timing", 0)
     total_ms = e_all0.elapsed_time(e_all1)
     step_ms = [s0.elapsed_time(s1) for s0, s1 in evs]
     launches = strmat.ctx.counters()[0] - k0
@@ -272,7 +313,7 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     fp64_peak = max(fp64.get("dfma_tflops", 0.0), fp64.get("dmma_tflops", 0.0)) or 37.0
-    kernel_ms = float(np.median(step_ms))  # the volume kernel is >95% of the step (profiles/ launch list)
+    kernel_ms = float(np.mean(vol_ms))  # average launch duration of the volume kernel (its share of the step: see "kernel_share")
     roofline = None
     if F_EL.get(key):
         flops = F_EL[key] * nvol
@@ -281,15 +322,23 @@ def main():
         ach_gb = byts / (kernel_ms * 1e-3) / 1e9
         t_fp, t_hbm = flops / (fp64_peak * 1e12), byts / (hbm_peak * 1e9)
         if t_fp >= t_hbm:
-            roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+            roofline = {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 / DFMA; the larger measured peak)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                         "peak_source": "measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json): "
                                        "MEASURED_PEAKS.json carries no FP64 figure"}
         else:
             roofline = {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
-        roofline.update({"traffic": None, "algorithmic_flops_per_element": F_EL[key], "algorithmic_bytes_per_element": B_EL[key],
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{a.topo},{a.p},{a.phys},{a.n},{a.scatter}")
+            if tr and world == 1 and a.engine == 1:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
+        roofline.update({"traffic": traffic, "algorithmic_flops_per_element": F_EL[key], "algorithmic_bytes_per_element": B_EL[key],
                          "hbm_GBps_algorithmic": ach_gb, "hbm_peak_GBps": hbm_peak,
-                         "kernel": "assemble_volume_kernel", "kernel_ms": kernel_ms})
+                         "kernel": kernel_name(a), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                         "peaks": {"fp64_tflops": fp64_peak, "hbm_gbs": hbm_peak}})
 
     cpu = None
     if not a.no_cpu_baseline:

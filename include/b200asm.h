@@ -82,7 +82,8 @@ void b200asm_destroy(b200asm_ctx *ctx);
 const char *b200asm_last_error(const b200asm_ctx *ctx); /* ctx may be NULL: last create() error */
 /* run on an existing CUDA stream (cudaStream_t passed as void*); default: a stream the context owns */
 int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
-/* integer options: "scatter" (B200ASM_SCATTER_*) */
+/* integer options: "scatter" (B200ASM_SCATTER_*), "engine" (0 register-tile DFMA kernels, 1 DMMA kernels where one
+ * exists), "timing" (1: CUDA events around every group's kernel launches, read by b200asm_group_time_ms) */
 int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);
 
 /* ---- flattened mesh ---------------------------------------------------------------------- */
@@ -116,6 +117,9 @@ int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev);
  * neighbouring rank into the resident CSR values (target 0) or rhs (target 1) at precomputed, distinct
  * positions: dst[positions[k]] += values[k].  positions/values are DEVICE pointers; asynchronous. */
 int b200asm_scatter_add(b200asm_ctx *ctx, int target, const int32_t *positions_dev, const double *values_dev, int64_t n);
+/* duration (ms, CUDA events on the context stream) of the kernel launches of one group in the LAST assembly;
+ * needs option "timing" = 1.  Waits for that group's launches to finish. */
+int b200asm_group_time_ms(b200asm_ctx *ctx, int group, double *ms);
 /* number of kernels launched by this context so far, and bytes moved H2D/D2H */
 int b200asm_counters(const b200asm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

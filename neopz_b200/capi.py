@@ -40,7 +40,7 @@ SYMBOLS = [
     "b200asm_create", "b200asm_destroy", "b200asm_last_error", "b200asm_set_stream", "b200asm_set_option",
     "b200asm_set_nodes", "b200asm_add_group", "b200asm_set_group_coef", "b200asm_clear_groups",
     "b200asm_set_pattern", "b200asm_assemble", "b200asm_assemble_async", "b200asm_synchronize",
-    "b200asm_download", "b200asm_device_pointers", "b200asm_counters", "b200asm_scatter_add",
+    "b200asm_download", "b200asm_device_pointers", "b200asm_counters", "b200asm_scatter_add", "b200asm_group_time_ms",
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
 ]
 
@@ -73,6 +73,7 @@ def lib():
     L.b200asm_download.argtypes = [vp, dp, dp]
     L.b200asm_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.b200asm_counters.argtypes = [vp, ip64, ip64, ip64]
+    L.b200asm_group_time_ms.argtypes = [vp, C.c_int, dp]
     L.b200asm_scatter_add.argtypes = [vp, C.c_int, vp, vp, C.c_int64]
     L.b200asm_gauss_legendre.argtypes = [C.c_int, dp, dp]
     L.b200asm_tensor_rule.argtypes = [C.c_int, C.c_int, dp, dp]
@@ -231,6 +232,12 @@ class Context:
         a, r = C.c_void_p(), C.c_void_p()
         self._check(lib().b200asm_device_pointers(self._h, C.byref(a), C.byref(r)))
         return a.value, r.value
+
+    def group_time_ms(self, group):
+        """CUDA-event duration of the kernel launches of `group` in the last assembly (option "timing" = 1)."""
+        ms = C.c_double()
+        self._check(lib().b200asm_group_time_ms(self._h, group, C.byref(ms)))
+        return ms.value
 
     def counters(self):
         k, h, d = C.c_int64(), C.c_int64(), C.c_int64()

@@ -519,6 +519,7 @@ struct Group {
     // ({0, nel} when not coloured); seg_smap = offset of every segment's scatter map (register-tile kernels)
     std::vector<int64_t> seg;
     std::vector<size_t> seg_smap;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // "timing" option: events around this group's launches
 };
 
 }  // namespace
@@ -540,6 +541,7 @@ struct b200asm_ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     int scatter = B200ASM_SCATTER_ATOMIC;
     int engine = 1;  // 1: DMMA panel kernel where one exists, 0: register-tile DFMA kernels only
+    int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
     std::string err;
 };
 
@@ -746,6 +748,8 @@ void free_group(Group &g) {
     cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
     cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
     cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad);
+    if (g.ev0) cudaEventDestroy(g.ev0);
+    if (g.ev1) cudaEventDestroy(g.ev1);
     g = Group();
 }
 
@@ -864,6 +868,10 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
         if (value != 0 && value != 1) return fail(ctx, B200ASM_EINVAL, "engine: 0 (register tiles) or 1 (DMMA where available)");
         ctx->engine = (int)value;
         ctx->have_pattern = false;  // the scatter-map layout depends on the kernel
+        return 0;
+    }
+    if (!strcmp(name, "timing")) {
+        ctx->timing = value ? 1 : 0;
         return 0;
     }
     return fail(ctx, B200ASM_EINVAL, std::string("unknown option ") + name);
@@ -1031,9 +1039,13 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
     const int atomic = ctx->scatter == B200ASM_SCATTER_ATOMIC ? 1 : 0;
-    for (const Group &g : ctx->groups) {
+    for (Group &g : ctx->groups) {
         if (g.nel == 0) continue;
         const size_t nseg = g.seg.size() - 1;  // 1, or the number of colours
+        if (ctx->timing) {
+            if (!g.ev0) { CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); }
+            CK(cudaEventRecord(g.ev0, ctx->stream));
+        }
         if (g.kind == B200ASM_BC) {
             BcParams p;
             p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
@@ -1046,6 +1058,7 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
                 CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
                 ctx->launches++;
             }
+            if (ctx->timing) CK(cudaEventRecord(g.ev1, ctx->stream));
             continue;
         }
         const bool use_mma = g.mma >= 0 && ctx->engine == 1;
@@ -1087,7 +1100,19 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             }
             ctx->launches++;
         }
+        if (ctx->timing) CK(cudaEventRecord(g.ev1, ctx->stream));
     }
+    return 0;
+}
+
+extern "C" int b200asm_group_time_ms(b200asm_ctx *ctx, int group, double *ms) {
+    if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !ms) return fail(ctx, B200ASM_EINVAL, "group_time_ms: bad arguments");
+    const Group &g = ctx->groups[group];
+    if (!g.ev0) return fail(ctx, B200ASM_ESTATE, "group_time_ms: set option \"timing\" = 1 and assemble first");
+    CK(cudaEventSynchronize(g.ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, g.ev0, g.ev1));
+    *ms = t;
     return 0;
 }
 

@@ -248,15 +248,217 @@ static int shape_tri(int p, const double *pt, double *phi, double *dphi_out) {
     return n;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * H1 shape functions of arbitrary order on hexahedra / quadrilaterals (p >= 3 needs the side
+ * orientations).  Shape/TPZShapeH1.cpp:42-116:
+ *   first function of a side = blend function (ShapeGenerating); the others = blend * phin(i), i >= 1, where
+ *   phin = TSHAPE::ShapeInternal(side, T pt) (Chebyshev products, Shape/pzshapelinear.cpp:15-33,306-312,
+ *   Shape/pzshapequad.cpp:317-337, Shape/pzshapecube.cpp:460-485) and T = ParametricTransform(transform id)
+ *   * TransformElementToSide(side) (Shape/pzgenericshape.cpp:13-55; Topology/tpzcube.cpp:583-655,
+ *   Topology/tpzquadrilateral.cpp:296-332; table gTrans2dQ Shape/pzshapequad.cpp:23-32).  The volume side of a
+ *   3-D element keeps the untransformed point (pzgenericshape.cpp:40-43).
+ *   Transform ids from the global corner-node indices: edges Topology/tpzcube.cpp:1073-1089, quadrilateral
+ *   faces Topology/tpzquadrilateral.cpp:591-618.
+ *   dphi of a side function: dphiblend*phin + phiblend*(T.Mult^T dphin)  (TPZShapeH1.cpp:86-101).
+ * ------------------------------------------------------------------------------------------ */
+#define ORC_MAXP 6
+#define ORC_MAXSHAPE ((ORC_MAXP + 1) * (ORC_MAXP + 1) * (ORC_MAXP + 1))
+
+static const double gTrans2dQ[8][2][2] = {{{1., 0.}, {0., 1.}},  {{0., 1.}, {1., 0.}},   {{0., 1.}, {-1., 0.}}, {{-1., 0.}, {0., 1.}},
+                                          {{-1., 0.}, {0., -1.}}, {{0., -1.}, {-1., 0.}}, {{0., -1.}, {1., 0.}}, {{1., 0.}, {0., -1.}}};
+static const int cube_face_nodes[6][4] = {{0, 1, 2, 3}, {0, 1, 5, 4}, {1, 2, 6, 5}, {3, 2, 6, 7}, {0, 3, 7, 4}, {4, 5, 6, 7}};
+
+/* Topology/tpzquadrilateral.cpp:591-618 */
+static int quad_transform_id(const int64_t *id) {
+    int id0, id1, minid;
+    id0 = (id[0] < id[1]) ? 0 : 1;
+    id1 = (id[2] < id[3]) ? 2 : 3;
+    minid = (id[id0] < id[id1]) ? id0 : id1;
+    id0 = (minid + 1) % 4;
+    id1 = (minid + 3) % 4;
+    const int64_t minglob = id[minid];
+    if (id[id0] < id[id1]) {
+        if (minglob == id[0]) return 0;
+        if (minglob == id[1]) return 2;
+        if (minglob == id[2]) return 4;
+        if (minglob == id[3]) return 6;
+    } else {
+        if (minglob == id[0]) return 1;
+        if (minglob == id[1]) return 3;
+        if (minglob == id[2]) return 5;
+        if (minglob == id[3]) return 7;
+    }
+    return 0;
+}
+
+/* Shape/pzshapelinear.cpp:15-33 */
+static void chebyshev(double x, int num, double *phi, double *dphi) {
+    if (num <= 0) return;
+    phi[0] = 1.0; dphi[0] = 0.0;
+    if (num == 1) return;
+    phi[1] = x; dphi[1] = 1.0;
+    for (int ord = 2; ord < num; ord++) {
+        phi[ord] = 2.0 * x * phi[ord - 1] - phi[ord - 2];
+        dphi[ord] = 2.0 * x * dphi[ord - 1] + 2.0 * phi[ord - 1] - dphi[ord - 2];
+    }
+}
+
+/* TSHAPE::TransformElementToSide(side).Mult(): sidedim x dim, entries 0/+-1 (Sum is zero for cube and quad) */
+static void element_to_side(int topo, int side, int *sidedim, double E[3][3]) {
+    memset(E, 0, sizeof(double) * 9);
+    if (topo == ORC_HEX) {
+        if (side < 20) {
+            *sidedim = 1;
+            switch (side) {
+                case 8: case 16: E[0][0] = 1.; break;
+                case 9: case 17: E[0][1] = 1.; break;
+                case 10: case 18: E[0][0] = -1.; break;
+                case 11: case 19: E[0][1] = -1.; break;
+                default: E[0][2] = 1.; break; /* 12..15 */
+            }
+        } else if (side < 26) {
+            *sidedim = 2;
+            switch (side) {
+                case 20: case 25: E[0][0] = 1.; E[1][1] = 1.; break;
+                case 21: case 23: E[0][0] = 1.; E[1][2] = 1.; break;
+                default: E[0][1] = 1.; E[1][2] = 1.; break; /* 22, 24 */
+            }
+        } else {
+            *sidedim = 3;
+            E[0][0] = E[1][1] = E[2][2] = 1.;
+        }
+    } else { /* ORC_QUAD */
+        if (side < 8) {
+            *sidedim = 1;
+            switch (side) {
+                case 4: E[0][0] = 1.; break;
+                case 5: E[0][1] = 1.; break;
+                case 6: E[0][0] = -1.; break;
+                default: E[0][1] = -1.; break;
+            }
+        } else {
+            *sidedim = 2;
+            E[0][0] = E[1][1] = 1.;
+        }
+    }
+}
+
+/* GetSideTransform (pzgenericshape.cpp:13-55): T = P * E */
+static void side_transform(int topo, int side, const int64_t *ids, int *sidedim, double T[3][3]) {
+    double E[3][3];
+    const int dim = topo == ORC_HEX ? 3 : 2;
+    element_to_side(topo, side, sidedim, E);
+    if (topo == ORC_HEX && side == 26) { memcpy(T, E, sizeof(E)); return; }
+    double P[3][3];
+    memset(P, 0, sizeof(P));
+    if (*sidedim == 1) {
+        int a, b;
+        if (topo == ORC_HEX) { a = cube_edge_nodes[side - 8][0]; b = cube_edge_nodes[side - 8][1]; }
+        else { a = side - 4; b = (side - 3) % 4; }
+        P[0][0] = ids[a] < ids[b] ? 1. : -1.;
+    } else {
+        int64_t loc[4];
+        for (int i = 0; i < 4; i++) loc[i] = topo == ORC_HEX ? ids[cube_face_nodes[side - 20][i]] : ids[i];
+        const int tid = quad_transform_id(loc);
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) P[i][j] = gTrans2dQ[tid][i][j];
+    }
+    for (int i = 0; i < *sidedim; i++)
+        for (int j = 0; j < dim; j++) {
+            double v = 0.;
+            for (int k = 0; k < *sidedim; k++) v += P[i][k] * E[k][j];
+            T[i][j] = v;
+        }
+}
+
+/* blend (generating) functions of all sides: the p = 2 tables of shape_hex / shape_quad */
+static int shape_hq_general(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi_out) {
+    const int dim = topo == ORC_HEX ? 3 : 2;
+    const int nc = topo == ORC_HEX ? 8 : 4, nsides = topo == ORC_HEX ? 27 : 9;
+    double bphi[27], bd[3 * 27];
+    if (topo == ORC_HEX) shape_hex(2, pt, bphi, bd); else shape_quad(2, pt, bphi, bd);
+    int n = nc;
+    for (int side = nc; side < nsides; side++) {
+        int sd;
+        if (topo == ORC_HEX) sd = side < 20 ? 1 : (side < 26 ? 2 : 3); else sd = side < 8 ? 1 : 2;
+        int ns = p - 1;
+        if (sd == 2) ns *= (p - 1);
+        if (sd == 3) ns *= (p - 1) * (p - 1);
+        n += ns;
+    }
+    /* output arrays are [dim][n] */
+    for (int a = 0; a < nc; a++) { phi[a] = bphi[a]; for (int k = 0; k < dim; k++) dphi_out[k * n + a] = bd[k * nsides + a]; }
+    int shape = nc;
+    for (int side = nc; side < nsides; side++) {
+        int sidedim;
+        double T[3][3];
+        side_transform(topo, side, ids, &sidedim, T);
+        const int ord1 = p - 1;
+        int numshape = ord1;
+        if (sidedim == 2) numshape = ord1 * ord1;
+        if (sidedim == 3) numshape = ord1 * ord1 * ord1;
+        if (numshape == 0) continue;
+        phi[shape] = bphi[side];
+        for (int k = 0; k < dim; k++) dphi_out[k * n + shape] = bd[k * nsides + side];
+        shape++;
+        if (numshape == 1) continue;
+        double out[3] = {0, 0, 0};
+        for (int i = 0; i < sidedim; i++) {
+            double v = 0.;
+            for (int j = 0; j < dim; j++) v += T[i][j] * pt[j];
+            out[i] = v;
+        }
+        double c[3][ORC_MAXP], dc[3][ORC_MAXP];
+        for (int i = 0; i < sidedim; i++) chebyshev(out[i], ord1, c[i], dc[i]);
+        for (int idx = 1; idx < numshape; idx++) {
+            double pn, dn[3] = {0, 0, 0};
+            if (sidedim == 1) { pn = c[0][idx]; dn[0] = dc[0][idx]; }
+            else if (sidedim == 2) {
+                const int i = idx / ord1, j = idx % ord1;
+                pn = c[0][i] * c[1][j];
+                dn[0] = dc[0][i] * c[1][j];
+                dn[1] = c[0][i] * dc[1][j];
+            } else {
+                const int i = idx / (ord1 * ord1), j = (idx / ord1) % ord1, k = idx % ord1;
+                pn = c[0][i] * c[1][j] * c[2][k];
+                dn[0] = dc[0][i] * c[1][j] * c[2][k];
+                dn[1] = c[0][i] * dc[1][j] * c[2][k];
+                dn[2] = c[0][i] * c[1][j] * dc[2][k];
+            }
+            phi[shape] = bphi[side] * pn;
+            for (int xj = 0; xj < dim; xj++) {
+                double aux;
+                if (sidedim < 3) {
+                    aux = 0.;
+                    for (int s2 = 0; s2 < sidedim; s2++) aux += T[s2][xj] * dn[s2];
+                } else aux = dn[xj];
+                dphi_out[xj * n + shape] = bd[xj * nsides + side] * pn + bphi[side] * aux;
+            }
+            shape++;
+        }
+    }
+    return n;
+}
+
+/* ids: global corner-node indices (gel->NodeIndex, Mesh/TPZCompElH1.cpp:110); may be NULL for p <= 2 */
+int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi) {
+    if (p < 1) return -1;
+    if (p <= 2) {
+        switch (topo) {
+            case ORC_HEX: return shape_hex(p, pt, phi, dphi);
+            case ORC_TET: return shape_tet(p, pt, phi, dphi);
+            case ORC_QUAD: return shape_quad(p, pt, phi, dphi);
+            case ORC_TRI: return shape_tri(p, pt, phi, dphi);
+        }
+        return -1;
+    }
+    if (p > ORC_MAXP || !ids) return -1;
+    if (topo == ORC_HEX || topo == ORC_QUAD) return shape_hq_general(topo, p, ids, pt, phi, dphi);
+    return -1; /* simplices of order >= 3: not restated */
+}
+
 int orc_shape(int topo, int p, const double *pt, double *phi, double *dphi) {
     if (p < 1 || p > 2) return -1;
-    switch (topo) {
-        case ORC_HEX: return shape_hex(p, pt, phi, dphi);
-        case ORC_TET: return shape_tet(p, pt, phi, dphi);
-        case ORC_QUAD: return shape_quad(p, pt, phi, dphi);
-        case ORC_TRI: return shape_tri(p, pt, phi, dphi);
-    }
-    return -1;
+    return orc_shape_ids(topo, p, 0, pt, phi, dphi);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -353,6 +555,7 @@ typedef struct {
     int32_t nq, pad;
     const double *qpts; /* [nq][dim] */
     const double *qw;   /* [nq] */
+    int64_t ids[8];     /* global corner-node indices (orientation of the sides, p >= 3) */
 } orc_elem_t;
 
 static int topo_dim(int topo) { return (topo == ORC_HEX || topo == ORC_TET) ? 3 : 2; }
@@ -455,9 +658,9 @@ static int contribute_elast_bc(int n, const double *phi, double weight, int type
 int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
     const int dim = topo_dim(e->topo);
     const int ns = (e->kind == ORC_ELAST3D || e->kind == ORC_ELAST3D_BC) ? 3 : 1;
-    double phi[27], dphi[3 * 27], dphix[3 * 27];
+    static __thread double phi[ORC_MAXSHAPE], dphi[3 * ORC_MAXSHAPE], dphix[3 * ORC_MAXSHAPE];
     double pt0[3] = {0, 0, 0};
-    const int n = orc_shape(e->topo, e->p, pt0, phi, dphi);
+    const int n = orc_shape_ids(e->topo, e->p, e->ids, pt0, phi, dphi);
     if (n < 0) return -1;
     const int nd = n * ns;
     memset(ek, 0, sizeof(double) * nd * nd);
@@ -469,7 +672,7 @@ int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
         gradx_of(e->topo, e->coords, pt, gradx);
         double detjac = jacobian_of(dim, gradx, jacinv);
         detjac = fabs(detjac);
-        orc_shape(e->topo, e->p, pt, phi, dphi);
+        orc_shape_ids(e->topo, e->p, e->ids, pt, phi, dphi);
         for (int j = 0; j < n; j++)
             for (int c = 0; c < dim; c++) {
                 double val = 0.;

@@ -86,7 +86,10 @@ struct Case {
     int n = 4, p = 1, phys = 0, tet = 0;
     double perturb = 0.0;
     int bctype = 0;  // type of the BC on matid -1 (0 Dirichlet, 1 Neumann on zmax only -> matid -2)
+    int scramble = 0;  // != 0: node indices permuted by a seeded Fisher-Yates shuffle, so that the side
+                       // orientations (transform ids, Shape/pzgenericshape.cpp:57-68) differ between elements
 };
+static std::vector<int64_t> g_node_perm;  // new index of every grid node (identity without scramble)
 
 static TPZCompMesh *build_mesh(const Case &c) {
     TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
@@ -107,6 +110,31 @@ static TPZCompMesh *build_mesh(const Case &c) {
                 nd.SetCoord(d, x);
             }
         }
+    }
+    g_node_perm.resize(gmesh->NNodes());
+    for (int64_t i = 0; i < gmesh->NNodes(); i++) g_node_perm[i] = i;
+    if (c.scramble) {
+        const int64_t nn = gmesh->NNodes();
+        uint64_t st = 0x9E3779B97F4A7C15ull * (uint64_t)c.scramble + 12345u;
+        for (int64_t i = nn - 1; i > 0; i--) {
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            const int64_t j = (int64_t)((st >> 33) % (uint64_t)(i + 1));
+            std::swap(g_node_perm[i], g_node_perm[j]);
+        }
+        std::vector<TPZGeoNode> old(nn);
+        for (int64_t i = 0; i < nn; i++) old[i] = gmesh->NodeVec()[i];
+        for (int64_t i = 0; i < nn; i++) {
+            TPZGeoNode &nd = gmesh->NodeVec()[g_node_perm[i]];
+            nd = old[i];
+            nd.SetNodeId((int)g_node_perm[i]);
+        }
+        for (int64_t e = 0; e < gmesh->NElements(); e++) {
+            TPZGeoEl *gel = gmesh->Element(e);
+            if (!gel) continue;
+            for (int k = 0; k < gel->NNodes(); k++) gel->SetNodeIndex(k, g_node_perm[gel->NodeIndex(k)]);
+        }
+        gmesh->ResetConnectivities();
+        gmesh->BuildConnectivity();
     }
     TPZCompMesh *cmesh = new TPZCompMesh(gmesh);
     cmesh->SetDimModel(3);
@@ -188,6 +216,52 @@ static void dump_shape(const std::string &dir, const std::string &tag, TPZCompEl
     save_vec(dir, "shape_" + tag + "_ids", idv);
 }
 
+// shape functions of EVERY element of one topology at a few integration points (orientation-dependent for p >= 3)
+template <class TSHAPE>
+static void dump_shape_all(const std::string &dir, const std::string &tag, TPZCompMesh *cmesh, MElementType type) {
+    const int nc = TSHAPE::NCornerNodes, ns = TSHAPE::NSides, dim = TSHAPE::Dimension;
+    std::vector<double> phi, dphi;
+    std::vector<int64_t> ids_all, elidx, qsel;
+    int nshape = 0, nqs = 0;
+    for (int64_t iel = 0; iel < cmesh->NElements(); iel++) {
+        TPZCompEl *cel = cmesh->Element(iel);
+        if (!cel || cel->Reference()->Type() != type) continue;
+        auto *intel = dynamic_cast<TPZInterpolationSpace *>(cel);
+        TPZGeoEl *gel = cel->Reference();
+        TPZManVector<int64_t, 8> ids(nc);
+        TPZManVector<int, 27> orders(ns - nc);
+        for (int i = 0; i < nc; i++) ids[i] = gel->NodeIndex(i);
+        for (int i = nc; i < ns; i++) orders[i - nc] = cel->Connect(i).Order();
+        TPZShapeData sd;
+        TPZShapeH1<TSHAPE>::Initialize(ids, orders, sd);
+        const TPZIntPoints &rule = intel->GetIntegrationRule();
+        const int nq = rule.NPoints();
+        nshape = sd.fPhi.Rows();
+        if (qsel.empty()) {
+            qsel = {0, nq / 3, (2 * nq) / 3, nq - 1};
+            nqs = 4;
+        }
+        TPZManVector<REAL, 3> pt(dim);
+        for (int k = 0; k < nqs; k++) {
+            REAL wq;
+            rule.Point((int)qsel[k], pt, wq);
+            TPZShapeH1<TSHAPE>::Shape(pt, sd);
+            for (int i = 0; i < nshape; i++) phi.push_back(sd.fPhi(i, 0));
+            for (int d = 0; d < dim; d++)
+                for (int i = 0; i < nshape; i++) dphi.push_back(sd.fDPhi(d, i));
+        }
+        for (int i = 0; i < nc; i++) ids_all.push_back(ids[i]);
+        elidx.push_back(iel);
+    }
+    if (elidx.empty()) return;
+    const int64_t ne = (int64_t)elidx.size();
+    save_vec(dir, "shapeall_" + tag + "_phi", phi, {ne, nqs, nshape});
+    save_vec(dir, "shapeall_" + tag + "_dphi", dphi, {ne, nqs, dim, nshape});
+    save_vec(dir, "shapeall_" + tag + "_ids", ids_all, {ne, nc});
+    save_vec(dir, "shapeall_" + tag + "_el", elidx);
+    save_vec(dir, "shapeall_" + tag + "_q", qsel);
+}
+
 static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     TPZCompMesh *cmesh = build_mesh(c);
     TPZGeoMesh *gmesh = cmesh->Reference();
@@ -196,6 +270,13 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     for (int64_t i = 0; i < nn; i++)
         for (int d = 0; d < 3; d++) nodes[i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
     save_vec(dir, "nodes", nodes, {nn, 3});
+    save_vec(dir, "node_perm", g_node_perm);
+    if (c.p >= 3) {
+        dump_shape_all<pzshape::TPZShapeCube>(dir, "hex", cmesh, ECube);
+        dump_shape_all<pzshape::TPZShapeTetra>(dir, "tet", cmesh, ETetraedro);
+        dump_shape_all<pzshape::TPZShapeQuad>(dir, "quad", cmesh, EQuadrilateral);
+        dump_shape_all<pzshape::TPZShapeTriang>(dir, "tri", cmesh, ETriangle);
+    }
 
     TPZLinearAnalysis an(cmesh, false);
     const int64_t ncel = cmesh->NElements();
@@ -324,7 +405,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     std::ofstream meta(dir + "/meta.json");
     meta.precision(17);
     meta << "{\"n\": " << c.n << ", \"p\": " << c.p << ", \"phys\": " << c.phys << ", \"tet\": " << c.tet
-         << ", \"perturb\": " << c.perturb << ", \"bctype\": " << c.bctype << ", \"neq\": " << neq
+         << ", \"perturb\": " << c.perturb << ", \"bctype\": " << c.bctype << ", \"scramble\": " << c.scramble << ", \"neq\": " << neq
          << ", \"ncel\": " << ncel << ", \"nnodes\": " << nn;
     TPZMaterial *mat = cmesh->FindMaterial(1);
     meta << ", \"bignumber\": " << mat->BigNumber();
@@ -383,6 +464,7 @@ int main(int argc, char **argv) {
         std::string dir = argv[2];
         c.n = atoi(argv[3]); c.p = atoi(argv[4]); c.phys = atoi(argv[5]); c.tet = atoi(argv[6]);
         c.perturb = atof(argv[7]); c.bctype = atoi(argv[8]);
+        if (argc >= 11) c.scramble = atoi(argv[10]);
         return cmd_dump(dir, c, atoi(argv[9]));
     }
     if (cmd == "time" && argc >= 8) {
