@@ -22,11 +22,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# algorithmic work per volume element, SURVEY.md 8(d) (reference arithmetic, full ek, mul/add = 1 flop)
-F_EL = {("hex", 1, "poisson"): 6.4e3, ("hex", 2, "poisson"): 158e3, ("tet", 2, "elasticity"): 85.7e3,
-        ("hex", 2, "elasticity"): 1.149e6, ("hex", 1, "elasticity"): None, ("tet", 2, "poisson"): None}
-B_EL = {("hex", 1, "poisson"): 0.49e3, ("hex", 2, "poisson"): 3.98e3, ("tet", 2, "elasticity"): 3.63e3,
-        ("hex", 2, "elasticity"): 32.8e3}
+def algorithmic_work(topo, p, phys, nvol, neq, nnz):
+    """FLOPs per volume element counted on the reference's arithmetic (full ek, mul/add = 1 flop each)
+    and compulsory HBM bytes per element (node coordinates + destination indices + every stored CSR value and rhs
+    entry written once + the scatter-map read of the element's stored entries)."""
+    if topo == "hex":
+        n, q, nodes, G = (p + 1) ** 3, int(0.51 * (2 * p + 2)) ** 3, 8, 194
+    else:
+        n, q, nodes, G = {1: 4, 2: 10}[p], {1: 4, 2: 14}[p], 4, 122   # tetrahedra: rules of order 2p (Zhang-Cui-Liu tables)
+    if phys == "poisson":
+        ndof, flops = n, q * (7 * n * n + 2 * n) + q * (18 * n + G)
+    else:
+        ndof, flops = 3 * n, q * (57 * n * n + 12 * n) + q * (18 * n + G)
+    e_el = ndof * (ndof + 1) // 2
+    byts = 8 * nodes * 3 + 4 * ndof + 8.0 * nnz / nvol + 8.0 * neq / nvol + 4 * e_el
+    return float(flops), float(byts)
 
 
 def parse():
@@ -72,8 +82,8 @@ def cpu_sample_n(a):
         return a.cpu_n
     # ~10-30 s of CPU work including mesh + Create(): sized from the survey's per-element costs
     if a.phys == "poisson":
-        return {1: 48, 2: 32}.get(a.p, 8) if a.topo == "hex" else 20
-    return {1: 24, 2: 14}.get(a.p, 6) if a.topo == "hex" else 14
+        return {1: 48, 2: 32, 3: 14, 4: 8}.get(a.p, 6) if a.topo == "hex" else 20
+    return {1: 24, 2: 14, 3: 8}.get(a.p, 6) if a.topo == "hex" else 14
 
 
 def run_reference(a, steps, warmup):
@@ -300,7 +310,6 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (assemble_volume_kernel) ------------------------------------
-    key = (a.topo, a.p, a.phys)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -315,9 +324,10 @@ def main():
     fp64_peak = max(fp64.get("dfma_tflops", 0.0), fp64.get("dmma_tflops", 0.0)) or 37.0
     kernel_ms = float(np.mean(vol_ms))  # average launch duration of the volume kernel (its share of the step: see "kernel_share")
     roofline = None
-    if F_EL.get(key):
-        flops = F_EL[key] * nvol
-        byts = B_EL[key] * nvol
+    f_el, b_el = algorithmic_work(a.topo, a.p, a.phys, nvol, neq, nnz)
+    if True:
+        flops = f_el * nvol
+        byts = b_el * nvol
         ach_tf = flops / (kernel_ms * 1e-3) / 1e12
         ach_gb = byts / (kernel_ms * 1e-3) / 1e9
         t_fp, t_hbm = flops / (fp64_peak * 1e12), byts / (hbm_peak * 1e9)
@@ -335,7 +345,7 @@ def main():
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except Exception:
             pass
-        roofline.update({"traffic": traffic, "algorithmic_flops_per_element": F_EL[key], "algorithmic_bytes_per_element": B_EL[key],
+        roofline.update({"traffic": traffic, "algorithmic_flops_per_element": f_el, "algorithmic_bytes_per_element": b_el,
                          "hbm_GBps_algorithmic": ach_gb, "hbm_peak_GBps": hbm_peak,
                          "kernel": kernel_name(a), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
                          "peaks": {"fp64_tflops": fp64_peak, "hbm_gbs": hbm_peak}})

@@ -101,6 +101,16 @@ int b200asm_clear_groups(b200asm_ctx *ctx);
  * builds, on the device, the element-entry -> CSR-position scatter map of every group. */
 int b200asm_set_pattern(b200asm_ctx *ctx, int64_t neq, const int64_t *ia, const int64_t *ja, int symmetric);
 
+/* The same pattern built ON THE DEVICE from the element->connect graph (the inputs of b200asm_build_pattern below):
+ * replaces TPZSSpStructMatrix::Create / TPZSpStructMatrix::Create (StrMatrix/TPZSSpStructMatrix.cpp:31-193,
+ * StrMatrix/TPZSpStructMatrix.cpp:53-190; External/TPZRenumbering.cpp:30-110) bit-exactly, without ever holding the
+ * pattern in host memory, makes it the current pattern of the context and builds the scatter maps. */
+int b200asm_build_pattern_device(b200asm_ctx *ctx, int symmetric, int64_t nel, const int64_t *elgraphindex,
+                                 const int64_t *elgraph, int64_t nblock, const int64_t *blockpos, const int64_t *blocksize,
+                                 int64_t *neq_out, int64_t *nnz_out);
+/* copies the current pattern to the host as the reference stores it (int64 IA/JA); either pointer may be NULL */
+int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *ja_host);
+
 /* ---- assembly -----------------------------------------------------------------------------
  * Zeroes A and rhs on the device, runs every group (CalcStiff + AddKel + AddFel of
  * StrMatrix/pzstrmatrixor.cpp:157-250 for all elements at once) and, when the host pointers are
@@ -132,6 +142,19 @@ int b200asm_gauss_legendre(int order, double *loc, double *w);
 int b200asm_tensor_rule(int topology, int order, double *qpts, double *qw);
 /* H1 shape tables (uniform p<=2) at given master-element points.  Returns nshape. */
 int b200asm_shape_tables(int topology, int porder, int nqp, const double *qpts, double *phi, double *dphi);
+/* number of H1 shape functions of an element of uniform order p (TSHAPE::NShapeF): hex (p+1)^3, quad (p+1)^2;
+ * tetrahedra / triangles for p <= 2. */
+int b200asm_nshape(int topology, int porder);
+/* Side-orientation key of every element from the GLOBAL indices of its corner nodes (what
+ * ComputeTransforms / GetTransformId derive per side: Shape/pzgenericshape.cpp:57-68, Topology/tpzcube.cpp:1059-1111,
+ * Topology/tpzquadrilateral.cpp:591-618): 1 bit per edge, 3 bits per quadrilateral face.  For p >= 3 the shape
+ * functions of a side depend on it; elements with equal keys share their tables (one b200asm_group per key).
+ * elnodes[nel][ncorner]. */
+int b200asm_orientation_keys(int topology, int64_t nel, const int32_t *elnodes, int64_t *keys);
+/* H1 shape tables of uniform order p (any p for hex / quad) for the orientation class `key`:
+ * TPZShapeH1<TSHAPE>::Shape (Shape/TPZShapeH1.cpp:42-116) at the given points.  Returns nshape. */
+int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts, double *phi,
+                                  double *dphi);
 /* CSR pattern of the reference from the element->connect graph (Mesh/pzcmesh.cpp:1223-1267,
  * External/TPZRenumbering.cpp:76-110, TPZSSpStructMatrix.cpp:50-193 / TPZSpStructMatrix.cpp:53-190).
  * elgraphindex[nel+1], elgraph[]: sequence numbers of each element's connects; blockpos/blocksize

@@ -42,6 +42,8 @@ SYMBOLS = [
     "b200asm_set_pattern", "b200asm_assemble", "b200asm_assemble_async", "b200asm_synchronize",
     "b200asm_download", "b200asm_device_pointers", "b200asm_counters", "b200asm_scatter_add", "b200asm_group_time_ms",
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
+    "b200asm_nshape", "b200asm_orientation_keys", "b200asm_shape_tables_oriented",
+    "b200asm_build_pattern_device", "b200asm_get_pattern",
 ]
 
 
@@ -78,6 +80,11 @@ def lib():
     L.b200asm_gauss_legendre.argtypes = [C.c_int, dp, dp]
     L.b200asm_tensor_rule.argtypes = [C.c_int, C.c_int, dp, dp]
     L.b200asm_shape_tables.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.b200asm_build_pattern_device.argtypes = [vp, C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64]
+    L.b200asm_get_pattern.argtypes = [vp, ip64, ip64]
+    L.b200asm_nshape.argtypes = [C.c_int, C.c_int]
+    L.b200asm_orientation_keys.argtypes = [C.c_int, C.c_int64, ip32, ip64]
+    L.b200asm_shape_tables_oriented.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, dp, dp, dp]
     L.b200asm_build_pattern.argtypes = [C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64, C.c_int]
     L.b200asm_build_pattern.restype = C.c_int64
     _lib = L
@@ -107,18 +114,33 @@ def tensor_rule(topology, order):
     return pts[:n].copy(), w[:n].copy()
 
 
-def shape_tables(topology, porder, qpts):
+def nshape(topology, porder):
+    n = lib().b200asm_nshape(topology, porder)
+    if n < 0:
+        raise B200AsmError(n, f"nshape: unsupported topology {topology} / order {porder}")
+    return n
+
+
+def orientation_keys(topology, elnodes):
+    """Side-orientation class of every element (from the global corner-node indices); all zero for simplices."""
+    elnodes = np.ascontiguousarray(elnodes, dtype=np.int32)
+    keys = np.zeros(len(elnodes), dtype=np.int64)
+    rc = lib().b200asm_orientation_keys(topology, len(elnodes), i32ptr(elnodes), i64ptr(keys))
+    if rc < 0:
+        raise B200AsmError(rc, "orientation_keys")
+    return keys
+
+
+def shape_tables(topology, porder, qpts, key=0):
+    """phi[nq][n], dphi[nq][dim][n] of the orientation class `key` (irrelevant for p <= 2)."""
     qpts = np.ascontiguousarray(qpts, dtype=np.float64)
     nq, dim = qpts.shape
-    phi = np.zeros((nq, 27))
-    dphi = np.zeros((nq, dim, 27))
-    phi_flat = np.zeros(nq * 27)
-    dphi_flat = np.zeros(nq * dim * 27)
-    n = lib().b200asm_shape_tables(topology, porder, nq, dptr(qpts), dptr(phi_flat), dptr(dphi_flat))
-    if n < 0:
-        raise B200AsmError(n, "shape_tables")
-    phi = phi_flat[: nq * n].reshape(nq, n).copy()
-    dphi = dphi_flat[: nq * dim * n].reshape(nq, dim, n).copy()
+    n = nshape(topology, porder)
+    phi = np.zeros((nq, n))
+    dphi = np.zeros((nq, dim, n))
+    rc = lib().b200asm_shape_tables_oriented(topology, porder, int(key), nq, dptr(qpts), dptr(phi), dptr(dphi))
+    if rc != n:
+        raise B200AsmError(rc, "shape_tables")
     return phi, dphi
 
 
@@ -211,6 +233,25 @@ class Context:
         ia = np.ascontiguousarray(ia, dtype=np.int64)
         ja = np.ascontiguousarray(ja, dtype=np.int64)
         self._check(lib().b200asm_set_pattern(self._h, len(ia) - 1, i64ptr(ia), i64ptr(ja), int(bool(symmetric))))
+
+    def build_pattern_device(self, symmetric, elgraphindex, elgraph, blockpos, blocksize):
+        """CSR pattern of the reference built on the device from the element graph; becomes the current pattern.
+        Returns (neq, nnz)."""
+        elgraphindex = np.ascontiguousarray(elgraphindex, dtype=np.int64)
+        elgraph = np.ascontiguousarray(elgraph, dtype=np.int64)
+        blockpos = np.ascontiguousarray(blockpos, dtype=np.int64)
+        blocksize = np.ascontiguousarray(blocksize, dtype=np.int64)
+        neq, nnz = C.c_int64(), C.c_int64()
+        self._check(lib().b200asm_build_pattern_device(self._h, int(bool(symmetric)), len(elgraphindex) - 1, i64ptr(elgraphindex),
+                                                       i64ptr(elgraph), len(blockpos), i64ptr(blockpos), i64ptr(blocksize),
+                                                       C.byref(neq), C.byref(nnz)))
+        return neq.value, nnz.value
+
+    def get_pattern(self, neq, nnz, want_ja=True):
+        ia = np.empty(neq + 1, dtype=np.int64)
+        ja = np.empty(nnz, dtype=np.int64) if want_ja else None
+        self._check(lib().b200asm_get_pattern(self._h, i64ptr(ia), i64ptr(ja)))
+        return ia, ja
 
     def assemble(self, a_host=None, rhs_host=None):
         self._check(lib().b200asm_assemble(self._h, dptr(a_host), dptr(rhs_host)))

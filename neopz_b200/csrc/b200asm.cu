@@ -85,6 +85,7 @@ __device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) 
 
 #include "gram_mma.cuh"
 #include "gram_mma_team.cuh"
+#include "pattern_device.cuh"
 
 // decode the linear index of an upper-triangular tile into (bi, bj), bi <= bj
 template <int NTB>
@@ -309,7 +310,7 @@ __global__ void scatter_add_kernel(double *__restrict__ dst, const int32_t *__re
 // scatter-map construction for a volume group: one thread per (batch, tile entry, slot)
 template <class C>
 __global__ void build_volume_smap_kernel(int64_t nel, int64_t nbatch, const int32_t *__restrict__ dest,
-                                         const int64_t *__restrict__ ia, const int64_t *__restrict__ ja, int symmetric,
+                                         const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, int symmetric,
                                          int32_t *__restrict__ smap, int32_t *__restrict__ smapT, int *__restrict__ missing) {
     constexpr int TILE = C::TILE, M = C::M, NT = C::NT, SLOTS = C::SLOTS;
     const int64_t total = nbatch * TILE * TILE * SLOTS;
@@ -460,8 +461,80 @@ __global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
         }
 }
 
+// boundary faces of higher order (more than 9 shape functions): one WARP per face, runtime sizes.
+// lanes <-> integration points for the surface Jacobian, then lanes <-> entries (i <= j) of the face mass matrix.
+__global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p, int NN, int N, int NS) {
+    extern __shared__ double bc_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t el = p.el0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (el >= p.el1) return;
+    double *W = bc_smem + (size_t)warp * p.nq;
+    for (int q = lane; q < p.nq; q += 32) {
+        const double *dn = p.dng + (size_t)q * 2 * NN;
+        double v1[3] = {0, 0, 0}, v2[3] = {0, 0, 0};
+        for (int a = 0; a < NN; a++) {
+            const int64_t node = p.elnodes[el * NN + a];
+            const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double x = p.xyz[node * 3 + k];
+                v1[k] += x * d0;
+                v2[k] += x * d1;
+            }
+        }
+        double n1 = 0, dot = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            n1 += v1[k] * v1[k];
+            dot += v1[k] * v2[k];
+        }
+        n1 = sqrt(n1);
+        double n2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double v1t = v1[k] / n1;
+            const double v2t = v2[k] - dot * v1t / n1;
+            n2 += v2t * v2t;
+        }
+        n2 = sqrt(n2);
+        double det = n1 * n2;
+        if (fabs(det) < 1.e-12) det = 1.e-12;
+        W[q] = __ldg(p.qw + q) * fabs(det);
+    }
+    __syncwarp();
+    const int npair = N * (N + 1) / 2;
+    for (int idx = lane; idx < npair; idx += 32) {
+        int i = 0, rem = idx;  // (i, j), i <= j, row-major over the upper triangle
+        while (rem >= N - i) { rem -= N - i; i++; }
+        const int j = i + rem;
+        double S = 0.0;
+        for (int q = 0; q < p.nq; q++) S += __ldg(p.phi + (size_t)q * N + i) * __ldg(p.phi + (size_t)q * N + j) * W[q];
+        for (int a = 0; a < NS; a++)
+            for (int b = 0; b < NS; b++) {
+                if (i == j && b < a) continue;
+                const double mab = p.coef[a * 3 + b], mba = p.coef[b * 3 + a];
+                if (mab == 0.0 && mba == 0.0) continue;
+                const size_t sidx = ((size_t)((i * N + j) * NS + a) * NS + b) * p.nel + el;
+                const int32_t pos = p.smap[sidx];
+                if (pos >= 0 && mab != 0.0) scatter_add(p.a + pos, mab * S, p.atomic);
+                if (p.smapT) {
+                    const int32_t posT = p.smapT[sidx];
+                    if (posT >= 0 && mba != 0.0) scatter_add(p.a + posT, mba * S, p.atomic);
+                }
+            }
+    }
+    for (int i = lane; i < N; i += 32) {
+        double T = 0.0;
+        for (int q = 0; q < p.nq; q++) T += __ldg(p.phi + (size_t)q * N + i) * W[q];
+        for (int a = 0; a < NS; a++) {
+            const double v = p.coef[9 + a];
+            if (v != 0.0) scatter_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T, p.atomic);
+        }
+    }
+}
+
 __global__ void build_bc_smap_kernel(int64_t nel, int n, int ns, const int32_t *__restrict__ dest,
-                                     const int64_t *__restrict__ ia, const int64_t *__restrict__ ja, int symmetric,
+                                     const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, int symmetric,
                                      int32_t *__restrict__ smap, int32_t *__restrict__ smapT, int *__restrict__ missing) {
     const int m = n * ns;
     const int64_t total = (int64_t)n * n * ns * ns * nel;
@@ -536,6 +609,7 @@ struct b200asm_ctx {
     int symmetric = 1;
     bool have_pattern = false;
     int64_t *d_ia = nullptr;
+    int32_t *d_ja = nullptr;  // column indices, resident (scatter maps, SpMV of the CG solver)
     double *d_a = nullptr, *d_rhs = nullptr;
     int *d_missing = nullptr;
     int64_t launches = 0, h2d = 0, d2h = 0;
@@ -575,6 +649,9 @@ using HexP1Poisson = VolCfg<8, 8, 1, 8, 64>;
 using HexP1Elast = VolCfg<8, 8, 3, 6, 12>;
 using HexP2Poisson = VolCfg<8, 27, 1, 9, 16>;
 using HexP2Elast = VolCfg<8, 27, 3, 9, 4>;
+using HexP3Poisson = VolCfg<8, 64, 1, 8, 4>;
+using HexP4Poisson = VolCfg<8, 125, 1, 9, 2>;
+using HexP3Elast = VolCfg<8, 64, 3, 6, 1>;
 using TetP1Poisson = VolCfg<4, 4, 1, 4, 128>;
 using TetP1Elast = VolCfg<4, 4, 3, 6, 32>;
 using TetP2Poisson = VolCfg<4, 10, 1, 5, 32>;
@@ -585,7 +662,7 @@ struct VolEntry {
     int epb, tile, slots, nthreads;
     size_t (*smem)(int nq);
     cudaError_t (*launch)(const VolParams &, int grid, size_t smem, cudaStream_t);
-    cudaError_t (*launch_smap)(int64_t nel, int64_t nbatch, const int32_t *dest, const int64_t *ia, const int64_t *ja,
+    cudaError_t (*launch_smap)(int64_t nel, int64_t nbatch, const int32_t *dest, const int64_t *ia, const int32_t *ja,
                                int symmetric, int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t);
     cudaError_t (*prepare)(size_t smem, int *ctas_per_sm);
 };
@@ -596,7 +673,7 @@ cudaError_t launch_vol(const VolParams &p, int grid, size_t smem, cudaStream_t s
     return cudaGetLastError();
 }
 template <class C>
-cudaError_t launch_vol_smap(int64_t nel, int64_t nbatch, const int32_t *dest, const int64_t *ia, const int64_t *ja,
+cudaError_t launch_vol_smap(int64_t nel, int64_t nbatch, const int32_t *dest, const int64_t *ia, const int32_t *ja,
                             int symmetric, int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
     build_volume_smap_kernel<C><<<grid, 256, 0, s>>>(nel, nbatch, dest, ia, ja, symmetric, smap, smapT, missing);
     return cudaGetLastError();
@@ -616,6 +693,7 @@ VolEntry make_entry(int topology, int porder) {
 const VolEntry kVol[] = {
     make_entry<HexP1Poisson>(B200ASM_HEX, 1), make_entry<HexP1Elast>(B200ASM_HEX, 1),
     make_entry<HexP2Poisson>(B200ASM_HEX, 2), make_entry<HexP2Elast>(B200ASM_HEX, 2),
+    make_entry<HexP3Poisson>(B200ASM_HEX, 3), make_entry<HexP4Poisson>(B200ASM_HEX, 4), make_entry<HexP3Elast>(B200ASM_HEX, 3),
     make_entry<TetP1Poisson>(B200ASM_TET, 1), make_entry<TetP1Elast>(B200ASM_TET, 1),
     make_entry<TetP2Poisson>(B200ASM_TET, 2), make_entry<TetP2Elast>(B200ASM_TET, 2),
 };
@@ -630,7 +708,7 @@ struct MmaEntry {
     int slots, nthreads, wpc;
     size_t (*smem)(int nq);
     cudaError_t (*launch)(const VolParams &, int grid, size_t smem, cudaStream_t);
-    cudaError_t (*launch_smap)(int64_t nel, const int32_t *dest, const int64_t *ia, const int64_t *ja, int symmetric,
+    cudaError_t (*launch_smap)(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
                                int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t);
     cudaError_t (*prepare)(size_t smem, int *ctas_per_sm);
 };
@@ -640,7 +718,7 @@ cudaError_t launch_mma(const VolParams &p, int grid, size_t smem, cudaStream_t s
     return cudaGetLastError();
 }
 template <class C>
-cudaError_t launch_mma_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int64_t *ja, int symmetric,
+cudaError_t launch_mma_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
                             int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
     build_mma_smap_kernel<C><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
     return cudaGetLastError();
@@ -659,6 +737,9 @@ MmaEntry make_mma_entry(int topology, int porder) {
 using HexP2ElastTeam = TeamCfg<8, 27, 3, 5, 1, 2>;
 using TetP2ElastTeam = TeamCfg<4, 10, 3, 3, 2, 2>;
 using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
+// higher-order Poisson: one warp per 4x4 superblock of 8x8 tiles (p=3: 8x8 tiles -> 3 warps; p=4: 16x16 -> 10 warps)
+using HexP3PoissonTeam = TeamCfg<8, 64, 1, 3, 2, 3, 4>;
+using HexP4PoissonTeam = TeamCfg<8, 125, 1, 10, 1, 2, 4>;
 
 template <class C>
 cudaError_t launch_team(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
@@ -666,7 +747,7 @@ cudaError_t launch_team(const VolParams &p, int grid, size_t smem, cudaStream_t 
     return cudaGetLastError();
 }
 template <class C>
-cudaError_t launch_team_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int64_t *ja, int symmetric,
+cudaError_t launch_team_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
                              int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
     build_team_smap_kernel<C><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
     return cudaGetLastError();
@@ -683,7 +764,8 @@ MmaEntry make_team_entry(int topology, int porder) {
 }
 // wpc = elements processed concurrently by one CTA
 const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2),
-                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1)};
+                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
+                         make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4)};
 // (tetrahedra p=2 elasticity stays on the register-tile kernel: 130 M el/s vs 99 M el/s for TetP2ElastTeam on a 40^3x5
 //  mesh — padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
@@ -696,6 +778,13 @@ cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
 }
 
 cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cudaStream_t s) {
+    if (porder >= 3) {
+        if (topology != B200ASM_QUAD) return cudaErrorInvalidValue;
+        const int n = (porder + 1) * (porder + 1);
+        const int grid = (int)((p.el1 - p.el0 + 3) / 4);
+        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, 4, n, ns);
+        return cudaGetLastError();
+    }
     if (topology == B200ASM_QUAD && porder == 1) return ns == 1 ? launch_bc<4, 4, 1>(p, s) : launch_bc<4, 4, 3>(p, s);
     if (topology == B200ASM_QUAD && porder == 2) return ns == 1 ? launch_bc<4, 9, 1>(p, s) : launch_bc<4, 9, 3>(p, s);
     if (topology == B200ASM_TRI && porder == 1) return ns == 1 ? launch_bc<3, 3, 1>(p, s) : launch_bc<3, 3, 3>(p, s);
@@ -703,15 +792,7 @@ cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cud
     return cudaErrorInvalidValue;
 }
 
-int nshape_of(int topology, int p) {
-    switch (topology) {
-        case B200ASM_HEX: return p == 1 ? 8 : 27;
-        case B200ASM_TET: return p == 1 ? 4 : 10;
-        case B200ASM_QUAD: return p == 1 ? 4 : 9;
-        case B200ASM_TRI: return p == 1 ? 3 : 6;
-    }
-    return -1;
-}
+int nshape_of(int topology, int p) { return b200asm_nshape(topology, p); }
 int ncorner_of(int topology) {
     switch (topology) {
         case B200ASM_HEX: return 8;
@@ -753,7 +834,7 @@ void free_group(Group &g) {
     g = Group();
 }
 
-int build_smaps(b200asm_ctx *ctx, const int64_t *d_ja) {
+int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
     CK(cudaMemsetAsync(ctx->d_missing, 0, sizeof(int), ctx->stream));
     for (Group &g : ctx->groups) {
         cudaFree(g.d_smap); cudaFree(g.d_smapT);
@@ -840,7 +921,7 @@ extern "C" void b200asm_destroy(b200asm_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (Group &g : ctx->groups) free_group(g);
-    cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
+    cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -900,8 +981,8 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     g.n = nshape_of(gi->topology, gi->porder);
     g.nq = gi->nqp;
     g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET) ? 3 : 2;
-    if (g.nn < 0 || g.n < 0 || gi->porder < 1 || gi->porder > 2)
-        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p in {1,2}, hex/tet/quad/tri)");
+    if (g.nn < 0 || g.n < 0 || gi->porder < 1)
+        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad 1..4, tet/tri 1..2)");
     if (gi->nshape != g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not match topology/order");
     if (g.ns != 1 && g.ns != 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1 or 3");
     if (g.nel < 0 || g.nq <= 0 || g.nq > 512) return fail(ctx, B200ASM_EINVAL, "add_group: bad nel/nqp");
@@ -1008,25 +1089,167 @@ extern "C" int b200asm_clear_groups(b200asm_ctx *ctx) {
     return 0;
 }
 
+namespace {
+void drop_pattern(b200asm_ctx *ctx) {
+    cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs);
+    ctx->d_ia = nullptr; ctx->d_ja = nullptr; ctx->d_a = ctx->d_rhs = nullptr;
+    ctx->have_pattern = false;
+}
+int grid_for(const b200asm_ctx *ctx, int64_t n, int threads) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)ctx->num_sms * 16));
+}
+}  // namespace
+
 extern "C" int b200asm_set_pattern(b200asm_ctx *ctx, int64_t neq, const int64_t *ia, const int64_t *ja, int symmetric) {
     if (!ctx || neq < 0 || !ia) return fail(ctx, B200ASM_EINVAL, "set_pattern: bad arguments");
     CK(cudaSetDevice(ctx->device));
     const int64_t nnz = ia[neq];
     if (nnz < 0 || nnz > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "set_pattern: nnz must fit int32 per device (shard the rows)");
     if (nnz && !ja) return fail(ctx, B200ASM_EINVAL, "set_pattern: ja == NULL");
-    cudaFree(ctx->d_ia); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs);
-    ctx->d_ia = nullptr; ctx->d_a = ctx->d_rhs = nullptr;
+    drop_pattern(ctx);
     ctx->neq = neq; ctx->nnz = nnz; ctx->symmetric = symmetric ? 1 : 0;
-    int64_t *d_ja = nullptr;
+    int64_t *d_ja64 = nullptr;
     int rc;
     if ((rc = upload(ctx, &ctx->d_ia, ia, (size_t)neq + 1))) return rc;
-    if ((rc = upload(ctx, &d_ja, ja, (size_t)nnz))) return rc;
+    if ((rc = upload(ctx, &d_ja64, ja, (size_t)nnz))) return rc;
+    CK(cudaMalloc((void **)&ctx->d_ja, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    if (nnz) {
+        patdev::narrow_kernel<<<grid_for(ctx, nnz, 256), 256, 0, ctx->stream>>>(nnz, d_ja64, ctx->d_ja);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ja64);
     CK(cudaMalloc((void **)&ctx->d_a, std::max<int64_t>(nnz, 1) * sizeof(double)));
     CK(cudaMalloc((void **)&ctx->d_rhs, std::max<int64_t>(neq, 1) * sizeof(double)));
-    rc = build_smaps(ctx, d_ja);
-    cudaFree(d_ja);  // column indices are only needed to build the maps
+    rc = build_smaps(ctx, ctx->d_ja);
     if (rc) return rc;
     ctx->have_pattern = true;
+    return 0;
+}
+
+extern "C" int b200asm_build_pattern_device(b200asm_ctx *ctx, int symmetric, int64_t nel, const int64_t *elgraphindex,
+                                            const int64_t *elgraph, int64_t nblock, const int64_t *blockpos,
+                                            const int64_t *blocksize, int64_t *neq_out, int64_t *nnz_out) {
+    if (!ctx || nel < 0 || nblock < 0 || !elgraphindex || !blockpos || !blocksize || (nel && !elgraph))
+        return fail(ctx, B200ASM_EINVAL, "build_pattern_device: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t total = elgraphindex[nel];
+    const int64_t neq = nblock ? blockpos[nblock - 1] + blocksize[nblock - 1] : 0;
+    if (nblock > 0x7fffffff || neq > 0x7fffffff || nel > 0x7fffffff)
+        return fail(ctx, B200ASM_EINVAL, "build_pattern_device: blocks / equations / elements must fit int32 per device");
+    std::vector<int32_t> eg32((size_t)std::max<int64_t>(total, 1)), bs32((size_t)std::max<int64_t>(nblock, 1));
+    for (int64_t k = 0; k < total; k++) {
+        if (elgraph[k] < 0 || elgraph[k] >= nblock) return fail(ctx, B200ASM_EINVAL, "build_pattern_device: connect out of range");
+        eg32[k] = (int32_t)elgraph[k];
+    }
+    for (int64_t b = 0; b < nblock; b++) bs32[b] = (int32_t)blocksize[b];
+    drop_pattern(ctx);
+    ctx->neq = neq; ctx->symmetric = symmetric ? 1 : 0;
+
+    int64_t *d_egi = nullptr, *d_bpos = nullptr, *d_n2e_idx = nullptr, *d_rowlen = nullptr;
+    int32_t *d_eg = nullptr, *d_bsize = nullptr, *d_cnt = nullptr, *d_n2e = nullptr;
+    int *d_err = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_egi); cudaFree(d_bpos); cudaFree(d_n2e_idx); cudaFree(d_rowlen); cudaFree(d_eg); cudaFree(d_bsize);
+        cudaFree(d_cnt); cudaFree(d_n2e); cudaFree(d_err); cudaFree(d_tmp);
+    };
+#define CKP(call)                                                                                      \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            cleanup();                                                                                   \
+            return fail(ctx, B200ASM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                                \
+    } while (0)
+    int rc;
+    if ((rc = upload(ctx, &d_egi, elgraphindex, (size_t)nel + 1)) || (rc = upload(ctx, &d_eg, eg32.data(), (size_t)total)) ||
+        (rc = upload(ctx, &d_bpos, blockpos, (size_t)nblock)) || (rc = upload(ctx, &d_bsize, bs32.data(), (size_t)nblock))) {
+        cleanup();
+        return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    // block -> elements: count, scan, fill
+    CKP(cudaMalloc((void **)&d_cnt, (size_t)(nblock + 1) * sizeof(int32_t)));
+    CKP(cudaMalloc((void **)&d_n2e_idx, (size_t)(nblock + 1) * sizeof(int64_t)));
+    CKP(cudaMalloc((void **)&d_n2e, (size_t)std::max<int64_t>(total, 1) * sizeof(int32_t)));
+    CKP(cudaMalloc((void **)&d_err, sizeof(int)));
+    CKP(cudaMemsetAsync(d_cnt, 0, (size_t)(nblock + 1) * sizeof(int32_t), st));
+    CKP(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    if (total) patdev::count_incidence_kernel<<<grid_for(ctx, total, 256), 256, 0, st>>>(total, d_eg, d_cnt);
+    size_t tmp_bytes = 0, tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_n2e_idx, (int)(nblock + 1), st);
+    CKP(cudaMalloc((void **)&d_rowlen, (size_t)(neq + 1) * sizeof(int64_t)));
+    cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_rowlen, d_rowlen, (int)(neq + 1), st);
+    tmp_bytes = std::max(tmp_bytes, tmp2);
+    CKP(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CKP(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, d_n2e_idx, (int)(nblock + 1), st));
+    CKP(cudaMemsetAsync(d_cnt, 0, (size_t)(nblock + 1) * sizeof(int32_t), st));
+    if (nel) patdev::fill_incidence_kernel<<<grid_for(ctx, nel, 256), 256, 0, st>>>(nel, d_egi, d_eg, d_n2e_idx, d_cnt, d_n2e);
+    CKP(cudaGetLastError());
+    // sweep 1: row lengths -> IA
+    patdev::Params pp{};
+    pp.symmetric = ctx->symmetric; pp.nel = nel; pp.nblock = nblock; pp.egi = d_egi; pp.eg = d_eg; pp.bpos = d_bpos;
+    pp.bsize = d_bsize; pp.n2e_idx = d_n2e_idx; pp.n2e = d_n2e; pp.rowlen = d_rowlen; pp.error = d_err;
+    CKP(cudaMemsetAsync(d_rowlen, 0, (size_t)(neq + 1) * sizeof(int64_t), st));
+    const int pgrid = (int)std::max<int64_t>(1, std::min<int64_t>((nblock + patdev::WARPS - 1) / patdev::WARPS, (int64_t)ctx->num_sms * 64));
+    patdev::pattern_kernel<1><<<pgrid, patdev::WARPS * 32, 0, st>>>(pp);
+    CKP(cudaGetLastError());
+    CKP(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_rowlen, d_rowlen, (int)(neq + 1), st));
+    int64_t nnz = 0;
+    int err = 0;
+    CKP(cudaMemcpyAsync(&nnz, d_rowlen + neq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CKP(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    ctx->launches += 5;
+    if (err) {
+        cleanup();
+        return fail(ctx, B200ASM_EINVAL, "build_pattern_device: a connect has more neighbour candidates than the device builder holds (use b200asm_build_pattern)");
+    }
+    if (nnz > 0x7fffffff) {
+        cleanup();
+        return fail(ctx, B200ASM_EINVAL, "build_pattern_device: nnz must fit int32 per device (shard the rows)");
+    }
+    // sweep 2: column indices
+    ctx->nnz = nnz;
+    ctx->d_ia = d_rowlen;
+    d_rowlen = nullptr;
+    CKP(cudaMalloc((void **)&ctx->d_ja, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    pp.ia = ctx->d_ia; pp.ja = ctx->d_ja;
+    patdev::pattern_kernel<2><<<pgrid, patdev::WARPS * 32, 0, st>>>(pp);
+    CKP(cudaGetLastError());
+    ctx->launches++;
+    CKP(cudaStreamSynchronize(st));
+    cleanup();
+#undef CKP
+    CK(cudaMalloc((void **)&ctx->d_a, std::max<int64_t>(nnz, 1) * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_rhs, std::max<int64_t>(neq, 1) * sizeof(double)));
+    if (neq_out) *neq_out = neq;
+    if (nnz_out) *nnz_out = nnz;
+    rc = build_smaps(ctx, ctx->d_ja);
+    if (rc) return rc;
+    ctx->have_pattern = true;
+    return 0;
+}
+
+extern "C" int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *ja_host) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (!ctx->d_ia || !ctx->d_ja) return fail(ctx, B200ASM_ESTATE, "get_pattern: no pattern on the device");
+    CK(cudaSetDevice(ctx->device));
+    if (ia_host) {
+        CK(cudaMemcpyAsync(ia_host, ctx->d_ia, (size_t)(ctx->neq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += (ctx->neq + 1) * (int64_t)sizeof(int64_t);
+    }
+    if (ja_host && ctx->nnz) {
+        // int32 on the device; widened on the host in place (back to front)
+        int32_t *tmp = reinterpret_cast<int32_t *>(ja_host);
+        CK(cudaMemcpyAsync(tmp, ctx->d_ja, (size_t)ctx->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int64_t k = ctx->nnz - 1; k >= 0; k--) ja_host[k] = tmp[k];
+        ctx->d2h += ctx->nnz * (int64_t)sizeof(int32_t);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

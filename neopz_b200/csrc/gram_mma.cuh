@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
 // (row 8bi+(lane>>2), col 8bj+2(lane&3)+e) of the element matrix, -1 for padding / lower triangle
 template <class C>
 __global__ void build_mma_smap_kernel(int64_t nel, const int32_t *__restrict__ dest, const int64_t *__restrict__ ia,
-                                      const int64_t *__restrict__ ja, int symmetric, int32_t *__restrict__ smap,
+                                      const int32_t *__restrict__ ja, int symmetric, int32_t *__restrict__ smap,
                                       int32_t *__restrict__ smapT, int *__restrict__ missing) {
     constexpr int N = C::N, NB = C::NB, SLOTS = C::SLOTS;
     const int64_t total = nel * SLOTS;

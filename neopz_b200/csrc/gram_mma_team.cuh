@@ -13,9 +13,12 @@
 // registers); geometry and panel phases are shared by the team and separated by a named barrier.
 #pragma once
 
-template <int NN_, int N_, int NS_, int WPE_, int EPC_, int MINB_>
+// SB_ > 0 (Poisson, higher p): the upper triangle of tiles is cut into SB x SB "superblocks", ONE per warp of the
+// team (WPE must equal the number of upper superblocks): a k-step then costs 2*SB fragment loads for SB*SB DMMAs
+// (SB loads for the SB(SB+1)/2 DMMAs of a diagonal superblock) instead of 2 loads per DMMA.
+template <int NN_, int N_, int NS_, int WPE_, int EPC_, int MINB_, int SB_ = 0>
 struct TeamCfg {
-    static constexpr int NN = NN_, N = N_, NS = NS_, WPE = WPE_, EPC = EPC_, MINB = MINB_;
+    static constexpr int NN = NN_, N = N_, NS = NS_, WPE = WPE_, EPC = EPC_, MINB = MINB_, SB = SB_;
     static constexpr int NBN = (N + 7) / 8;              // node blocks of 8
     static constexpr int NPAD = 8 * NBN;
     static constexpr int MP = NS * NPAD;                 // panel columns
@@ -24,9 +27,11 @@ struct TeamCfg {
     static constexpr int KQ = NS == 1 ? 3 : 1;           // panel rows per integration point
     static constexpr int QC = NS == 1 ? 4 : 8;           // points per chunk
     static constexpr int KC = QC * KQ;                   // panel rows per chunk (multiple of 4)
-    static constexpr int NGROUPS = NBN * (NBN + 1) / 2;  // node-block pairs ib <= jb
-    static constexpr int TPG = NS == 1 ? 1 : 9;          // tiles per group
+    static constexpr int NSB = SB > 0 ? NBN / SB : NBN;  // superblocks per direction (SB == 0: a group = a tile pair)
+    static constexpr int NGROUPS = NSB * (NSB + 1) / 2;  // node-block pairs ib <= jb (SB > 0: superblock pairs)
+    static constexpr int TPG = SB > 0 ? SB * SB : (NS == 1 ? 1 : 9);  // tiles per group
     static constexpr int GPW = (NGROUPS + WPE - 1) / WPE;  // groups per warp
+    static_assert(SB == 0 || (NS == 1 && NBN % (SB > 0 ? SB : 1) == 0 && NGROUPS == WPE), "superblocks: Poisson, SB | NBN, one per warp");
     static constexpr int JS = 10;
     static constexpr int XSP = NN * 3 + ((NN * 3) & 1);
     static constexpr int TEAM_THREADS = WPE * 32;
@@ -40,16 +45,16 @@ struct TeamCfg {
     // group index -> (ib, jb), row-major over the upper triangle
     __host__ __device__ static constexpr int group_ib(int gidx) {
         int ib = 0, t = gidx;
-        for (int row = 0; row < NBN - 1; row++) {
-            const int cnt = NBN - row;
+        for (int row = 0; row < NSB - 1; row++) {
+            const int cnt = NSB - row;
             if (ib == row && t >= cnt) { t -= cnt; ib = row + 1; }
         }
         return ib;
     }
     __host__ __device__ static constexpr int group_jb(int gidx) {
         int ib = 0, t = gidx;
-        for (int row = 0; row < NBN - 1; row++) {
-            const int cnt = NBN - row;
+        for (int row = 0; row < NSB - 1; row++) {
+            const int cnt = NSB - row;
             if (ib == row && t >= cnt) { t -= cnt; ib = row + 1; }
         }
         return ib + t;
@@ -76,7 +81,19 @@ __device__ __forceinline__ void team_mma_chunk(const double *__restrict__ Pn, do
             const int gidx = W + gl * C::WPE;  // compile-time after unrolling
             if (gidx < C::NGROUPS) {
                 const int ib = C::group_ib(gidx), jb = C::group_jb(gidx);
-                if (C::NS == 1) {
+                if (C::SB > 0) {
+                    constexpr int SB = C::SB > 0 ? C::SB : 1;
+                    double fi[SB], fj[SB];
+#pragma unroll
+                    for (int a = 0; a < SB; a++) fi[a] = row[8 * (ib * SB + a)];
+#pragma unroll
+                    for (int b = 0; b < SB; b++) fj[b] = (ib == jb) ? fi[b] : row[8 * (jb * SB + b)];
+#pragma unroll
+                    for (int a = 0; a < SB; a++)
+#pragma unroll
+                        for (int b = 0; b < SB; b++)
+                            if (ib != jb || a <= b) dmma_m8n8k4(acc[gl * C::TPG + a * SB + b][0], acc[gl * C::TPG + a * SB + b][1], fi[a], fj[b]);
+                } else if (C::NS == 1) {
                     const double fi = row[8 * ib];
                     const double fj = (ib == jb) ? fi : row[8 * jb];
                     dmma_m8n8k4(acc[gl][0], acc[gl][1], fi, fj);
@@ -111,7 +128,10 @@ __device__ __forceinline__ void team_epilogue(const VolParams &p, int64_t el, do
 #pragma unroll
             for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(sm + (gl * TPG * 2 + k) * 32);
             double val[TPG * 2];
-            if (C::NS == 1) {
+            if (C::SB > 0) {
+#pragma unroll
+                for (int k = 0; k < TPG * 2; k++) val[k] = p.coef[0] * acc[gl * TPG + (k >> 1)][k & 1];
+            } else if (C::NS == 1) {
                 val[0] = p.coef[0] * acc[gl][0];
                 val[1] = p.coef[0] * acc[gl][1];
             } else {
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
 // scatter map of the team kernel: slot ((((W*GPW+gl)*TPG + t)*2 + e)*32 + lane) of element el
 template <class C>
 __global__ void build_team_smap_kernel(int64_t nel, const int32_t *__restrict__ dest, const int64_t *__restrict__ ia,
-                                       const int64_t *__restrict__ ja, int symmetric, int32_t *__restrict__ smap,
+                                       const int32_t *__restrict__ ja, int symmetric, int32_t *__restrict__ smap,
                                        int32_t *__restrict__ smapT, int *__restrict__ missing) {
     constexpr int N = C::N, NS = C::NS, SLOTS = C::SLOTS, TPG = C::TPG, M = C::M;
     const int64_t total = nel * SLOTS;
@@ -318,10 +338,18 @@ __global__ void build_team_smap_kernel(int64_t nel, const int32_t *__restrict__ 
         const int gidx = W + gl * C::WPE;
         int32_t pos = -1, posT = -1;
         if (gidx < C::NGROUPS) {
-            const int ib = C::group_ib(gidx), jb = C::group_jb(gidx);
+            int ib = C::group_ib(gidx), jb = C::group_jb(gidx);
+            bool tile_ok = true;
+            if (C::SB > 0) {  // tile t = a*SB + b of superblock (ib, jb)
+                constexpr int SB = C::SB > 0 ? C::SB : 1;
+                const int ta = t / SB, tb = t % SB;
+                tile_ok = ib != jb || ta <= tb;
+                ib = ib * SB + ta;
+                jb = jb * SB + tb;
+            }
             const int in = 8 * ib + (lane >> 2), jn = 8 * jb + 2 * (lane & 3) + e;
-            const int a = NS == 1 ? 0 : t / 3, b = NS == 1 ? 0 : t % 3;
-            if (in < N && jn < N && (in < jn || (in == jn && a <= b))) {
+            const int a = (NS == 1 || C::SB > 0) ? 0 : t / 3, b = (NS == 1 || C::SB > 0) ? 0 : t % 3;
+            if (tile_ok && in < N && jn < N && (in < jn || (in == jn && a <= b))) {
                 const int i = in * NS + a, j = jn * NS + b;
                 const int64_t di = dest[el * M + i], dj = dest[el * M + j];
                 auto find = [&](int64_t row, int64_t col) -> int32_t {

@@ -11,6 +11,16 @@
 //                pzshapetriang.cpp:34-81)
 // Shape order = side order of the reference topology (Topology/tpzcube.cpp:30-80 etc.), which is
 // also the connect order and the local dof order of TPZElementMatrix.
+//
+// Order p >= 3 (hexahedra / quadrilaterals): a side with more than one function multiplies its blend
+// function by Chebyshev polynomials of the side's own parametric coordinates (Shape/TPZShapeH1.cpp:64-113,
+// pzshapelinear.cpp:15-33, pzshapequad.cpp:317-337, pzshapecube.cpp:460-485).  Those coordinates are the
+// element coordinates of the side's free axes, permuted and reflected according to the GLOBAL indices of
+// the side's corner nodes (transform ids: Topology/tpzcube.cpp:1059-1111, tpzquadrilateral.cpp:591-618;
+// matrices: pzshapequad.cpp:23-32, tpzcube.cpp:583-655), so that neighbouring elements agree on the
+// functions of a shared side.  Here the whole orientation of an element is packed into one integer key
+// (b200asm_orientation_keys: 1 bit per edge, 3 bits per face); elements with equal keys share their tables
+// and are assembled as one group.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -30,6 +40,88 @@ const int kHexSide[27][3] = {
 const int kQuadSide[9][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}, {2, 0}, {1, 2}, {2, 1}, {0, 2}, {2, 2}};
 const int kTetEdge[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
 const int kTriEdge[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+
+// corner pairs of the edges and corner cycles of the faces (side order of Topology/tpzcube.cpp:30-80)
+const int kHexEdge[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {0, 4}, {1, 5}, {2, 6}, {3, 7}, {4, 5}, {5, 6}, {6, 7}, {7, 4}};
+const int kHexFace[6][4] = {{0, 1, 2, 3}, {0, 1, 5, 4}, {1, 2, 6, 5}, {3, 2, 6, 7}, {0, 3, 7, 4}, {4, 5, 6, 7}};
+// natural parametrisation of a side inside the element: free axis and its sign per side coordinate
+// (TransformElementToSide: edges 10,11,18,19 run against their axis)
+const int kHexEdgeAxis[12] = {0, 1, 0, 1, 2, 2, 2, 2, 0, 1, 0, 1};
+const int kHexEdgeSign[12] = {1, 1, -1, -1, 1, 1, 1, 1, 1, 1, -1, -1};
+const int kHexFaceAxes[6][2] = {{0, 1}, {0, 2}, {1, 2}, {0, 2}, {1, 2}, {0, 1}};
+const int kQuadEdgeAxis[4] = {0, 1, 0, 1};
+const int kQuadEdgeSign[4] = {1, 1, -1, -1};
+// the eight symmetries of the square as (source coordinate, sign) per output coordinate (gTrans2dQ)
+const int kSquareSrc[8][2] = {{0, 1}, {1, 0}, {1, 0}, {0, 1}, {0, 1}, {1, 0}, {1, 0}, {0, 1}};
+const int kSquareSgn[8][2] = {{1, 1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}, {-1, -1}, {-1, 1}, {1, -1}};
+
+// which of the eight square symmetries maps the face onto its canonical orientation: start at the corner with the
+// smallest global index, walk towards the smaller of its two neighbours
+inline int square_symmetry(int64_t a, int64_t b, int64_t c, int64_t d) {
+    const int64_t v[4] = {a, b, c, d};
+    int m = 0;
+    for (int k = 1; k < 4; k++)
+        if (v[k] < v[m]) m = k;
+    const bool ccw = v[(m + 1) & 3] < v[(m + 3) & 3];
+    return 2 * m + (ccw ? 0 : 1);
+}
+
+struct SideParam {  // side coordinate k = sign[k] * x[axis[k]]
+    int sdim;
+    int axis[3];
+    int sign[3];
+};
+
+// decode the orientation key of an element into the parametrisation of side `side`
+inline SideParam side_param(int topology, int side, int64_t key) {
+    SideParam sp;
+    if (topology == B200ASM_HEX) {
+        if (side < 20) {
+            const int e = side - 8;
+            sp.sdim = 1;
+            sp.axis[0] = kHexEdgeAxis[e];
+            sp.sign[0] = kHexEdgeSign[e] * (((key >> e) & 1) ? -1 : 1);
+        } else if (side < 26) {
+            const int f = side - 20;
+            const int t = (int)((key >> (12 + 3 * f)) & 7);
+            sp.sdim = 2;
+            for (int k = 0; k < 2; k++) {
+                sp.axis[k] = kHexFaceAxes[f][kSquareSrc[t][k]];
+                sp.sign[k] = kSquareSgn[t][k];
+            }
+        } else {
+            sp.sdim = 3;
+            for (int k = 0; k < 3; k++) { sp.axis[k] = k; sp.sign[k] = 1; }
+        }
+    } else {
+        if (side < 8) {
+            const int e = side - 4;
+            sp.sdim = 1;
+            sp.axis[0] = kQuadEdgeAxis[e];
+            sp.sign[0] = kQuadEdgeSign[e] * (((key >> e) & 1) ? -1 : 1);
+        } else {
+            const int t = (int)((key >> 4) & 7);
+            sp.sdim = 2;
+            for (int k = 0; k < 2; k++) {
+                sp.axis[k] = kSquareSrc[t][k];
+                sp.sign[k] = kSquareSgn[t][k];
+            }
+        }
+    }
+    return sp;
+}
+
+// T_0..T_{num-1} and derivatives (three-term recurrence, Shape/pzshapelinear.cpp:15-33)
+inline void chebyshev_T(double x, int num, double *t, double *dt) {
+    if (num <= 0) return;
+    t[0] = 1.0; dt[0] = 0.0;
+    if (num == 1) return;
+    t[1] = x; dt[1] = 1.0;
+    for (int k = 2; k < num; k++) {
+        t[k] = 2.0 * x * t[k - 1] - t[k - 2];
+        dt[k] = 2.0 * x * dt[k - 1] + 2.0 * t[k - 1] - dt[k - 2];
+    }
+}
 
 inline void factors1d(double t, double f[3], double df[3]) {
     f[0] = (1. - t) / 2.;
@@ -177,6 +269,118 @@ extern "C" int b200asm_shape_tables(int topology, int porder, int nqp, const dou
                 }
             }
         }
+    }
+    return n;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// orientation keys and tables of arbitrary order (hexahedra, quadrilaterals)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200asm_nshape(int topology, int porder) {
+    if (porder < 1) return B200ASM_EINVAL;
+    const int p = porder;
+    switch (topology) {
+        case B200ASM_HEX: return (p + 1) * (p + 1) * (p + 1);
+        case B200ASM_QUAD: return (p + 1) * (p + 1);
+        case B200ASM_TET: return p <= 2 ? (p == 1 ? 4 : 10) : B200ASM_EINVAL;
+        case B200ASM_TRI: return p <= 2 ? (p == 1 ? 3 : 6) : B200ASM_EINVAL;
+    }
+    return B200ASM_EINVAL;
+}
+
+extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t *elnodes, int64_t *keys) {
+    if (nel < 0 || (nel && (!elnodes || !keys))) return B200ASM_EINVAL;
+    if (topology == B200ASM_TET || topology == B200ASM_TRI) {  // p <= 2 only: no orientation dependence
+        for (int64_t e = 0; e < nel; e++) keys[e] = 0;
+        return 0;
+    }
+    if (topology != B200ASM_HEX && topology != B200ASM_QUAD) return B200ASM_EINVAL;
+    const int nc = topology == B200ASM_HEX ? 8 : 4;
+    for (int64_t e = 0; e < nel; e++) {
+        const int32_t *id = elnodes + e * nc;
+        int64_t key = 0;
+        if (topology == B200ASM_HEX) {
+            for (int k = 0; k < 12; k++)
+                if (!(id[kHexEdge[k][0]] < id[kHexEdge[k][1]])) key |= (int64_t)1 << k;
+            for (int f = 0; f < 6; f++) {
+                const int *c = kHexFace[f];
+                key |= (int64_t)square_symmetry(id[c[0]], id[c[1]], id[c[2]], id[c[3]]) << (12 + 3 * f);
+            }
+        } else {
+            for (int k = 0; k < 4; k++)
+                if (!(id[k] < id[(k + 1) & 3])) key |= (int64_t)1 << k;
+            key |= (int64_t)square_symmetry(id[0], id[1], id[2], id[3]) << 4;
+        }
+        keys[e] = key;
+    }
+    return 0;
+}
+
+extern "C" int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts,
+                                             double *phi, double *dphi) {
+    if (porder < 1 || porder > 8 || nqp < 0) return B200ASM_EINVAL;
+    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI)
+        return b200asm_shape_tables(topology, porder, nqp, qpts, phi, dphi);
+    if (topology != B200ASM_HEX && topology != B200ASM_QUAD) return B200ASM_EINVAL;
+    const int dim = topology == B200ASM_HEX ? 3 : 2;
+    const int nsides = topology == B200ASM_HEX ? 27 : 9, nc = topology == B200ASM_HEX ? 8 : 4;
+    const int n = b200asm_nshape(topology, porder);
+    const int m = porder - 1;  // Chebyshev functions per side direction
+    for (int q = 0; q < nqp; q++) {
+        const double *pt = qpts + (size_t)q * dim;
+        double *ph = phi + (size_t)q * n;
+        double *dp = dphi + (size_t)q * dim * n;
+        double f[3][3], df[3][3];
+        for (int d = 0; d < dim; d++) factors1d(pt[d], f[d], df[d]);
+        int shape = 0;
+        for (int side = 0; side < nsides; side++) {
+            // blend function of the side and its gradient
+            const int *a = dim == 3 ? kHexSide[side] : kQuadSide[side];
+            double B, dB[3] = {0, 0, 0};
+            if (dim == 3) {
+                B = f[0][a[0]] * f[1][a[1]] * f[2][a[2]];
+                dB[0] = df[0][a[0]] * f[1][a[1]] * f[2][a[2]];
+                dB[1] = f[0][a[0]] * df[1][a[1]] * f[2][a[2]];
+                dB[2] = f[0][a[0]] * f[1][a[1]] * df[2][a[2]];
+            } else {
+                B = f[0][a[0]] * f[1][a[1]];
+                dB[0] = df[0][a[0]] * f[1][a[1]];
+                dB[1] = f[0][a[0]] * df[1][a[1]];
+            }
+            ph[shape] = B;
+            for (int d = 0; d < dim; d++) dp[d * n + shape] = dB[d];
+            shape++;
+            if (side < nc) continue;
+            const SideParam sp = side_param(topology, side, key);
+            int count = m;
+            for (int k = 1; k < sp.sdim; k++) count *= m;
+            double T[3][8], dT[3][8];
+            for (int k = 0; k < sp.sdim; k++) chebyshev_T(sp.sign[k] * pt[sp.axis[k]], m, T[k], dT[k]);
+            for (int idx = 1; idx < count; idx++) {
+                int i[3] = {0, 0, 0};
+                if (sp.sdim == 1) i[0] = idx;
+                else if (sp.sdim == 2) { i[0] = idx / m; i[1] = idx % m; }
+                else { i[0] = idx / (m * m); i[1] = (idx / m) % m; i[2] = idx % m; }
+                double val = T[0][i[0]];
+                for (int k = 1; k < sp.sdim; k++) val *= T[k][i[k]];
+                double g[3] = {0, 0, 0};  // gradient of the Chebyshev product w.r.t. the element coordinates
+                for (int k = 0; k < sp.sdim; k++) {
+                    double t = 1.0;
+                    bool first = true;
+                    for (int l = 0; l < sp.sdim; l++) {
+                        const double fac = l == k ? dT[l][i[l]] : T[l][i[l]];
+                        t = first ? fac : t * fac;
+                        first = false;
+                    }
+                    g[sp.axis[k]] = sp.sign[k] * t;
+                }
+                ph[shape] = B * val;
+                for (int d = 0; d < dim; d++) dp[d * n + shape] = dB[d] * val + B * g[d];
+                shape++;
+            }
+        }
+        if (shape != n) return B200ASM_EINVAL;
     }
     return n;
 }

@@ -55,9 +55,14 @@ struct ElastAccess : public TPZElasticity3D {
     using TPZElasticity3D::fPreStress;
 };
 
+// one device group per (topology, material, order, side-orientation class): for p >= 3 the shape functions of a side
+// depend on the global indices of its corner nodes (Shape/pzgenericshape.cpp:57-68), elements of one class share tables
 struct GroupKey {
     int topology, matid, porder;
-    bool operator<(const GroupKey &o) const { return std::tie(topology, matid, porder) < std::tie(o.topology, o.matid, o.porder); }
+    int64_t orientation;
+    bool operator<(const GroupKey &o) const {
+        return std::tie(topology, matid, porder, orientation) < std::tie(o.topology, o.matid, o.porder, o.orientation);
+    }
 };
 
 struct HostGroup {
@@ -261,8 +266,16 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
                 if (con.Order() != porder) Fatal("non-uniform polynomial order inside an element is not supported");
             }
         }
-        if (porder < 1 || porder > 2) Fatal("polynomial order " + std::to_string(porder) + " is not supported yet (p in {1,2})");
-        const GroupKey key{topo, mat->Id(), porder};
+        const bool tensor = topo == B200ASM_HEX || topo == B200ASM_QUAD;
+        if (porder < 1 || porder > (tensor ? 4 : 2))
+            Fatal("polynomial order " + std::to_string(porder) + " is not supported (hexahedra/quadrilaterals 1..4, simplices 1..2)");
+        int64_t orientation = 0;
+        if (porder >= 3) {
+            int32_t corner[8];
+            for (int i = 0; i < ncorner; i++) corner[i] = (int32_t)gel->NodeIndex(i);
+            if (b200asm_orientation_keys(topo, 1, corner, &orientation) != 0) Fatal("b200asm_orientation_keys failed");
+        }
+        const GroupKey key{topo, mat->Id(), porder, orientation};
         auto it = index.find(key);
         if (it == index.end()) {
             it = index.emplace(key, c.groups.size()).first;

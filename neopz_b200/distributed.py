@@ -137,9 +137,7 @@ def slab_mesh(nxy, nz_total, rank, world, porder, nstate, tetrahedra=False, bc_m
         if len(conn) == 0:
             continue
         assert conn.min() >= 0
-        active = [s for s, loc in enumerate(SIDES[blk.topology]) if side_nshape(blk.topology, loc, porder) > 0]
-        d = new_pos[conn[:, active]]
-        dest = (d[:, :, None] + np.arange(nstate, dtype=np.int64)[None, None, :]).reshape(len(conn), -1)
+        dest = gridmesh.destination_indices(blk.topology, conn, new_pos, porder, nstate)
         if len(conn):
             mesh.blocks.append(ElementBlock(topology=blk.topology, matid=blk.matid, first=first,
                                             elnodes=np.ascontiguousarray(blk.elnodes[keep]), connects=conn,

@@ -38,17 +38,30 @@ DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2}
 
 
 def side_nshape(topology, side_nodes, p):
-    """TSHAPE::NConnectShapeF(side, p) for p in {1,2} (Shape/pzshapecube.cpp:573-584, pzshapetetra.cpp:447-466)."""
+    """TSHAPE::NConnectShapeF(side, p) (Shape/pzshapecube.cpp:573-584, pzshapequad.cpp, pzshapetetra.cpp:447-466):
+    vertex 1, edge p-1, quadrilateral (p-1)^2, hexahedron interior (p-1)^3; simplices are supported for p <= 2
+    (triangle face / tetrahedron interior: none)."""
     k = len(side_nodes)
     if k == 1:
         return 1
-    if p == 1:
-        return 0
     if k == 2:
-        return 1  # edge: p-1
+        return p - 1
     if topology in (capi.HEX, capi.QUAD):
-        return 1  # quad face (p-1)^2, hex interior (p-1)^3
-    return 0      # triangle face / tet interior: none at p=2
+        return (p - 1) ** 2 if k == 4 else (p - 1) ** 3
+    if p > 2:
+        raise ValueError("tetrahedra / triangles: uniform order p <= 2 only")
+    return 0
+
+
+def destination_indices(topology, connects, block_pos, porder, nstate):
+    """TPZElementMatrix::ComputeDestinationIndices (Mesh/pzelmat.cpp:37-70): connects in side order, all
+    equations of a connect consecutively (shape-major, state fastest)."""
+    cols = []
+    for s, loc in enumerate(SIDES[topology]):
+        n = side_nshape(topology, loc, porder) * nstate
+        if n:
+            cols.append(block_pos[connects[:, s]][:, None] + np.arange(n, dtype=np.int64)[None, :])
+    return np.ascontiguousarray(np.concatenate(cols, axis=1))
 
 
 @dataclass
@@ -110,6 +123,7 @@ def flatten(nodes, element_blocks, porder, nstate):
     # entity keys per (element, side) as (class, ab, c) triples, in element order
     triples = []
     shapes = []
+    ncell = 0
     for topo, _matid, elnodes in element_blocks:
         sides = SIDES[topo]
         en = np.asarray(elnodes, dtype=np.int64)
@@ -125,8 +139,14 @@ def flatten(nodes, element_blocks, porder, nstate):
                 srt = np.sort(en[:, loc], axis=1)
                 iscell = (k == NCORNER[topo] and DIM[topo] == 3)
                 t[:, s, 0] = 1 if k == 2 else (3 if iscell else 2)
-                t[:, s, 1] = srt[:, 0] * nnodes + srt[:, 1]
-                t[:, s, 2] = srt[:, 2] if k > 2 else -1
+                if iscell:  # the volume side is never shared: keyed by the element itself
+                    t[:, s, 1] = ncell + np.arange(nel, dtype=np.int64)
+                    t[:, s, 2] = -1
+                else:       # edges: both nodes; faces: the three smallest nodes (distinct faces share at most two)
+                    t[:, s, 1] = srt[:, 0] * nnodes + srt[:, 1]
+                    t[:, s, 2] = srt[:, 2] if k > 2 else -1
+        if DIM[topo] == 3:
+            ncell += nel
         triples.append(t.reshape(-1, 3))
         shapes.append((nel, len(sides)))
     allt = np.concatenate(triples, axis=0)
@@ -153,10 +173,7 @@ def flatten(nodes, element_blocks, porder, nstate):
     for (topo, matid, elnodes), (nel, ns) in zip(element_blocks, shapes):
         conn = conn_flat[off:off + nel * ns].reshape(nel, ns)
         off += nel * ns
-        # destination indices: connects with shape functions, in side order; idf fastest (pzelmat.cpp:45-59)
-        active = [s for s, loc in enumerate(SIDES[topo]) if side_nshape(topo, loc, porder) > 0]
-        d = pos[conn[:, active]]                                  # [nel][nshape]
-        dest = (d[:, :, None] + np.arange(nstate, dtype=np.int64)[None, None, :]).reshape(nel, -1)
+        dest = destination_indices(topo, conn, pos, porder, nstate)
         mesh.blocks.append(ElementBlock(topology=topo, matid=matid, first=first,
                                         elnodes=np.ascontiguousarray(elnodes, dtype=np.int32),
                                         connects=conn, dest=np.ascontiguousarray(dest)))
@@ -289,6 +306,13 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
     return nodes, [tuple(b[:3]) for b in blocks]
 
 
-def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0):
+def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0, node_perm=None):
+    """node_perm[i] = new index of grid node i (a renumbered mesh: same geometry, different side orientations)."""
     nodes, blocks = grid_elements(n, tetrahedra=tetrahedra, bc_matids=bc_matids, perturb=perturb)
+    if node_perm is not None:
+        node_perm = np.asarray(node_perm, dtype=np.int64)
+        renum = np.empty_like(nodes)
+        renum[node_perm] = nodes
+        nodes = renum
+        blocks = [(t, m, node_perm[np.asarray(e, dtype=np.int64)]) for t, m, e in blocks]
     return flatten(nodes, blocks, porder, nstate)

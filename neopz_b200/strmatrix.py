@@ -115,9 +115,10 @@ class TPZBndCond:
 # ---------------------------------------------------------------------------------------------
 # integration rules + shape tables per topology / order
 # ---------------------------------------------------------------------------------------------
-def element_tables(topology, porder):
+def element_tables(topology, porder, key=0):
     """(qpts, qw, phi, dphi) of the rule of order 2p the reference attaches to an element
-    (Mesh/pzelctemp.cpp:35-47, Material/TPZMatSingleSpace.cpp:61-72)."""
+    (Mesh/pzelctemp.cpp:35-47, Material/TPZMatSingleSpace.cpp:61-72); key = side-orientation class of the
+    elements (capi.orientation_keys), relevant for p >= 3."""
     order = 2 * porder
     if topology in (capi.HEX, capi.QUAD):
         qpts, qw = capi.tensor_rule(topology, order)
@@ -125,7 +126,7 @@ def element_tables(topology, porder):
         z = np.load(os.path.join(_DATA, "simplex_rules.npz"))
         tag = "tet" if topology == capi.TET else "tri"
         qpts, qw = z[f"{tag}_order{order}_pts"], z[f"{tag}_order{order}_w"]
-    phi, dphi = capi.shape_tables(topology, porder, qpts)
+    phi, dphi = capi.shape_tables(topology, porder, qpts, key)
     return qpts, qw, phi, dphi
 
 
@@ -148,7 +149,8 @@ class TPZStructMatrixB200:
             self.ctx.set_option("scatter", {"atomic": 0, "colored": 1}[scatter])
         self.ia = self.ja = None
         self._flattened = False
-        self.group_of_block = []
+        self.group_of_block = []    # first (for p <= 2: the only) group of every element block
+        self.groups_of_block = []   # all groups of every element block (one per side-orientation class)
 
     def SetNumThreads(self, n):
         self.fNumThreads = n
@@ -167,18 +169,34 @@ class TPZStructMatrixB200:
                 raise ValueError("material nstate does not match the mesh")
             if (DIM[b.topology] == 3) == (mat.kind == capi.BC):
                 raise ValueError(f"material {b.matid}: volume/boundary kind does not match element dimension")
-            qpts, qw, phi, dphi = element_tables(b.topology, mesh.porder)
-            gid = self.ctx.add_group(b.topology, mesh.porder, mat.kind, mat.nstate, b.elnodes, b.dest,
-                                     qpts, qw, phi, dphi, mat.coef())
-            self.group_of_block.append(gid)
+            # p >= 3: the shape functions of a side depend on the orientation of the side (global corner-node
+            # indices): one group per orientation class of the block; p <= 2: one group per block
+            keys = capi.orientation_keys(b.topology, b.elnodes) if mesh.porder >= 3 else np.zeros(len(b.elnodes), np.int64)
+            gids = []
+            for key in np.unique(keys):
+                sel = slice(None) if mesh.porder < 3 else np.nonzero(keys == key)[0]
+                qpts, qw, phi, dphi = element_tables(b.topology, mesh.porder, key)
+                gids.append(self.ctx.add_group(b.topology, mesh.porder, mat.kind, mat.nstate, b.elnodes[sel], b.dest[sel],
+                                               qpts, qw, phi, dphi, mat.coef()))
+            self.groups_of_block.append(gids)
+            self.group_of_block.append(gids[0])
         self._flattened = True
 
     # -- TPZStructMatrix::Create -------------------------------------------------------------------
-    def Create(self):
-        """CSR pattern, bit-exact with the reference's Create() (TPZSSpStructMatrix.cpp:31-193)."""
+    def Create(self, on_device=False, download=True):
+        """CSR pattern, bit-exact with the reference's Create() (TPZSSpStructMatrix.cpp:31-193).
+        on_device: build it on the GPU (b200asm_build_pattern_device) instead of the threaded host builder;
+        download=False then leaves IA/JA on the device only (self.ja stays None; self.nnz is set)."""
         idx, graph = self.mesh.element_graph()
+        if on_device:
+            self._flatten()
+            neq, self.nnz = self.ctx.build_pattern_device(self.symmetric, idx, graph, self.mesh.block_pos, self.mesh.block_size)
+            assert neq == self.mesh.neq
+            self.ia, self.ja = self.ctx.get_pattern(neq, self.nnz, want_ja=download)
+            return self.ia, self.ja
         self.ia, self.ja = capi.build_pattern(self.symmetric, idx, graph, self.mesh.block_pos,
                                               self.mesh.block_size, self.fNumThreads)
+        self.nnz = len(self.ja)
         self._flatten()
         self.ctx.set_pattern(self.ia, self.ja, self.symmetric)
         return self.ia, self.ja
@@ -187,6 +205,7 @@ class TPZStructMatrixB200:
         """Use a pattern created elsewhere (e.g. by the reference's own Create())."""
         self.ia = np.ascontiguousarray(ia, dtype=np.int64)
         self.ja = np.ascontiguousarray(ja, dtype=np.int64)
+        self.nnz = len(self.ja)
         self._flatten()
         self.ctx.set_pattern(self.ia, self.ja, self.symmetric)
 
@@ -196,7 +215,7 @@ class TPZStructMatrixB200:
         if self.ia is None:
             raise RuntimeError("Assemble: call Create() first")
         if a is None:
-            a = np.empty(len(self.ja))
+            a = np.empty(self.nnz)
         if rhs is None:
             rhs = np.empty(self.mesh.neq)
         self.ctx.assemble(a, rhs)
@@ -208,5 +227,6 @@ class TPZStructMatrixB200:
         return ia, ja, a, rhs
 
     def UpdateMaterials(self):
-        for b, gid in zip(self.mesh.blocks, self.group_of_block):
-            self.ctx.set_group_coef(gid, self.materials[b.matid].coef())
+        for b, gids in zip(self.mesh.blocks, self.groups_of_block):
+            for gid in gids:
+                self.ctx.set_group_coef(gid, self.materials[b.matid].coef())

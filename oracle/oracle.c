@@ -14,7 +14,8 @@
  *
  * Scope: H1 elements of uniform order p<=2 on hexahedra / tetrahedra and their quadrilateral /
  * triangular boundary faces (for p<=2 no side has more than one shape function, hence no
- * orientation transforms: Shape/TPZShapeH1.cpp:71,77).  Simplex quadrature tables are data of the
+ * orientation transforms: Shape/TPZShapeH1.cpp:71,77), and of uniform order 3..6 on hexahedra /
+ * quadrilaterals (side orientation from the global corner-node indices, orc_shape_ids).  Simplex quadrature tables are data of the
  * reference (Integral/tpzintrulet.cpp, tpzintrulet3d.cpp) and are passed in by the caller.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared oracle/oracle.c -o oracle/liboracle.so -lm
@@ -826,7 +827,8 @@ void orc_addfel(double *rhs, int nd, const double *ef, const int64_t *dest) {
  * ------------------------------------------------------------------------------------------ */
 int64_t orc_assemble(int symmetric, int64_t nel, const orc_elem_t *elems, const int64_t *dest_ptr, const int64_t *dest,
                      const int64_t *ia, const int64_t *ja, double *a, double *rhs) {
-    double *ek = (double *)malloc(sizeof(double) * 81 * 81), *ef = (double *)malloc(sizeof(double) * 81);
+    const size_t ndmax = 3 * ORC_MAXSHAPE;
+    double *ek = (double *)malloc(sizeof(double) * ndmax * ndmax), *ef = (double *)malloc(sizeof(double) * ndmax);
     int64_t missing = 0;
     for (int64_t el = 0; el < nel; el++) {
         const int nd = orc_calcstiff(&elems[el], ek, ef);

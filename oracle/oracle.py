@@ -31,7 +31,8 @@ class Elem(C.Structure):
     _fields_ = [("topo", C.c_int32), ("p", C.c_int32), ("kind", C.c_int32), ("bctype", C.c_int32),
                 ("coords", C.c_double * 24), ("mat", C.c_double * 16),
                 ("nq", C.c_int32), ("pad", C.c_int32),
-                ("qpts", C.POINTER(C.c_double)), ("qw", C.POINTER(C.c_double))]
+                ("qpts", C.POINTER(C.c_double)), ("qw", C.POINTER(C.c_double)),
+                ("ids", C.c_int64 * 8)]
 
 
 _lib = None
@@ -47,6 +48,7 @@ def lib():
         _lib.orc_rule_hex.argtypes = [C.c_int, dp, dp]
         _lib.orc_rule_quad.argtypes = [C.c_int, dp, dp]
         _lib.orc_shape.argtypes = [C.c_int, C.c_int, dp, dp, dp]
+        _lib.orc_shape_ids.argtypes = [C.c_int, C.c_int, ip, dp, dp, dp]
         _lib.orc_calcstiff.argtypes = [C.POINTER(Elem), dp, dp]
         _lib.orc_elast_contribute_point.argtypes = [C.c_int, dp, dp, C.c_double, dp, dp, dp]
         _lib.orc_elast_constants.argtypes = [C.c_double, C.c_double, dp]
@@ -78,12 +80,17 @@ def rule(topo, order):
     return pts[:n].copy(), w[:n].copy()
 
 
-def shape(topo, p, pt):
+def shape(topo, p, pt, ids=None):
+    """phi[n], dphi[dim][n] at one master-element point; ids = global corner-node indices (needed for p >= 3)."""
     dim = TOPO_DIM[topo]
-    phi = np.zeros(27)
-    dphi = np.zeros(3 * 27)
+    phi = np.zeros(343)
+    dphi = np.zeros(3 * 343)
     pt = np.ascontiguousarray(pt, dtype=np.float64)
-    n = lib().orc_shape(topo, p, _dp(pt), _dp(phi), _dp(dphi))
+    if ids is None:
+        n = lib().orc_shape(topo, p, _dp(pt), _dp(phi), _dp(dphi))
+    else:
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        n = lib().orc_shape_ids(topo, p, _ip(ids), _dp(pt), _dp(phi), _dp(dphi))
     assert n > 0
     return phi[:n].copy(), dphi[: dim * n].reshape(dim, n).copy()
 
@@ -94,8 +101,9 @@ def elast_constants(E, nu):
     return c
 
 
-def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw):
-    """coords: (nel, nnode, 3).  Returns (ctypes array of Elem, keepalive)."""
+def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None):
+    """coords: (nel, nnode, 3); ids: (nel, nnode) global corner-node indices (orientation, p >= 3).
+    Returns (ctypes array of Elem, keepalive)."""
     nel = coords.shape[0]
     nn = TOPO_NNODE[topo]
     qpts = np.ascontiguousarray(qpts, dtype=np.float64)
@@ -110,6 +118,8 @@ def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw):
         m = np.zeros(16)
         m[: len(mat)] = mat
         el.mat[:] = m.tolist()
+        if ids is not None:
+            el.ids[:nn] = [int(v) for v in ids[e][:nn]]
         el.nq = len(qw)
         el.qpts = _dp(qpts)
         el.qw = _dp(qw)

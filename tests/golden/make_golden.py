@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "refdriver")
 
-# name: (n, p, phys, tet, perturb, bctype, with_elmats)
+# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed])
+# scramble != 0: node indices shuffled so that the side orientations differ from element to element (p >= 3)
 CASES = {
     "hex_p1_poisson_n3": (3, 1, 0, 0, 0.0, 0, 1),
     "hex_p1_poisson_n3_pert": (3, 1, 0, 0, 0.15, 1, 1),
@@ -27,16 +28,26 @@ CASES = {
     "tet_p1_poisson_n2_pert": (2, 1, 0, 1, 0.15, 0, 1),
     "tet_p2_poisson_n2_pert": (2, 2, 0, 1, 0.15, 1, 1),
     "tet_p2_elast_n2_pert": (2, 2, 1, 1, 0.15, 1, 1),
+    "hex_p3_poisson_n2_pert_scr": (2, 3, 0, 0, 0.15, 1, 1, 7),
+    "hex_p4_poisson_n2_pert_scr": (2, 4, 0, 0, 0.15, 1, 1, 11),
+    "hex_p3_elast_n2_pert_scr": (2, 3, 1, 0, 0.15, 1, 1, 5),
+    "hex_p4_poisson_n2": (2, 4, 0, 0, 0.0, 0, 0, 0),
+    "hex_p3_poisson_n3_pert": (3, 3, 0, 0, 0.15, 1, 0, 0),
 }
 
 
 def main():
     if not os.path.exists(DRIVER):
         sys.exit("oracle/_ref/refdriver missing: run `make -f oracle/Makefile.ref -j8` first")
-    for name, (n, p, phys, tet, pert, bctype, elm) in CASES.items():
+    only = set(sys.argv[1:])
+    for name, case in CASES.items():
+        if only and name not in only:
+            continue
+        n, p, phys, tet, pert, bctype, elm = case[:7]
+        scr = case[7] if len(case) > 7 else 0
         with tempfile.TemporaryDirectory() as d:
             subprocess.check_call([DRIVER, "dump", d, str(n), str(p), str(phys), str(tet), repr(pert),
-                                   str(bctype), str(elm)], stdout=subprocess.DEVNULL)
+                                   str(bctype), str(elm), str(scr)], stdout=subprocess.DEVNULL)
             arrays = {}
             for f in sorted(os.listdir(d)):
                 if f.endswith(".npy"):

@@ -60,7 +60,8 @@ def oracle_elements(g):
         coords = g["nodes"][nodes][None, :, :]
         kind, bctype, mat = material_vector(g, topo, int(g["el_matid"][e]))
         tag = TAGS[topo]
-        arr, k = orc.make_elems(topo, p, kind, bctype, coords, mat, g[f"rule_{tag}_pts"], g[f"rule_{tag}_w"])
+        arr, k = orc.make_elems(topo, p, kind, bctype, coords, mat, g[f"rule_{tag}_pts"], g[f"rule_{tag}_w"],
+                                ids=nodes[None, :])
         arrays.append(arr)
         keep.append(k)
     return arrays, keep

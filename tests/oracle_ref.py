@@ -48,7 +48,7 @@ def oracle_assemble(mesh, materials, symmetric, ia, ja):
         kind, bctype, mvec = _mat_vector(materials[b.matid])
         qpts, qw = _rule(b.topology, mesh.porder)
         coords = mesh.nodes[b.elnodes]
-        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw)
+        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw, ids=b.elnodes)
         elems.append(arr)
         keep.append(k)
         dest_parts.append(b.dest)

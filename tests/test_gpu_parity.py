@@ -7,7 +7,7 @@ Tolerance (BASELINE.json north_star): pattern bit-exact; ||A-Aref||_F/||Aref||_F
 import numpy as np
 import pytest
 
-from neopz_b200 import gridmesh, strmatrix as sm
+from neopz_b200 import capi, gridmesh, strmatrix as sm
 from tests import golden_util as gu
 from tests.oracle_ref import oracle_assemble
 
@@ -49,7 +49,7 @@ def test_against_reference_fixtures(name, symmetric):
     neumann = m["bctype"] == 1
     bc = (-1, -1, -1, -1, -1, -2 if neumann else -1)
     mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
-                              bc_matids=bc, perturb=m["perturb"])
+                              bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
     strmat = sm.TPZStructMatrixB200(mesh, materials_for(m["phys"], neumann), symmetric=symmetric)
     ia, ja, a, rhs = strmat.CreateAssemble()
     pre = "sym" if symmetric else "full"
@@ -86,6 +86,62 @@ def test_against_oracle(n, p, phys, tet):
         assert relF(a, a_ref) <= TOL
         assert relF(rhs, rhs_ref) <= TOL
         # ragged last batch + re-assembly must reproduce (Zero()+Assemble path, TPZLinearAnalysis.cpp:73-77)
+        a2, rhs2 = strmat.Assemble()
+        assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
+
+
+@pytest.mark.parametrize("name", gu.ALL_CASES)
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_device_pattern_bit_exact(name, symmetric):
+    """b200asm_build_pattern_device (CSR pattern built on the GPU) == the reference's Create(): memcmp of IA and JA;
+    assembling into it gives the reference's values."""
+    g = gu.load(name)
+    m = g["meta"]
+    neumann = m["bctype"] == 1
+    bc = (-1, -1, -1, -1, -1, -2 if neumann else -1)
+    mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
+                              bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
+    strmat = sm.TPZStructMatrixB200(mesh, materials_for(m["phys"], neumann), symmetric=symmetric)
+    ia, ja = strmat.Create(on_device=True)
+    pre = "sym" if symmetric else "full"
+    assert np.array_equal(ia, g[pre + "_ia"]) and np.array_equal(ja, g[pre + "_ja"])
+    a, rhs = strmat.Assemble()
+    assert relF(a, g[pre + "_a"]) <= TOL and relF(rhs, g["rhs"]) <= TOL
+
+
+@pytest.mark.parametrize("n,p,ns,tet", [(24, 2, 1, 0), (12, 2, 3, 1), (10, 3, 1, 0), (40, 1, 3, 0)])
+def test_device_pattern_matches_host_builder_at_scale(n, p, ns, tet):
+    mesh = gridmesh.grid_mesh(n, p, ns, tetrahedra=bool(tet))
+    idx, graph = mesh.element_graph()
+    for symmetric in (True, False):
+        ia, ja = capi.build_pattern(symmetric, idx, graph, mesh.block_pos, mesh.block_size, 0)
+        ctx = capi.Context(0)
+        neq, nnz = ctx.build_pattern_device(symmetric, idx, graph, mesh.block_pos, mesh.block_size)
+        assert (neq, nnz) == (mesh.neq, len(ja))
+        ia_d, ja_d = ctx.get_pattern(neq, nnz)
+        assert np.array_equal(ia, ia_d) and np.array_equal(ja, ja_d)
+        ctx.close()
+
+
+def _shuffled(n, seed):
+    """Random renumbering of the (n+1)^3 grid nodes: every element gets its own side orientations (p >= 3)."""
+    return np.random.default_rng(seed).permutation((n + 1) ** 3)
+
+
+@pytest.mark.parametrize("n,p,phys,engine,shuffle", [(3, 3, 0, 1, 1), (3, 4, 0, 1, 1), (2, 3, 1, 1, 1), (4, 3, 0, 0, 0),
+                                                     (3, 4, 0, 0, 1), (5, 4, 0, 1, 0), (5, 3, 0, 1, 0)])
+def test_high_order_hex_against_oracle(n, p, phys, engine, shuffle):
+    """p = 3, 4 hexahedra (BASELINE config C4): orientation-dependent shape tables, one group per orientation class;
+    DMMA superblock team kernels (engine 1) and register-tile kernels (engine 0); quadrilateral faces of order p."""
+    perm = _shuffled(n, 1234 + n + p) if shuffle else None
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12, node_perm=perm)
+    mats = materials_for(phys, neumann=True)
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, engine=engine)
+        ia, ja, a, rhs = strmat.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL
+        assert relF(rhs, rhs_ref) <= TOL
         a2, rhs2 = strmat.Assemble()
         assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
 

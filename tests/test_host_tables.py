@@ -16,12 +16,20 @@ def test_rules_and_shape_tables(name):
     for tag, topo in TOPO.items():
         if f"rule_{tag}_w" not in g:
             continue
-        qpts, qw, phi, dphi = strmatrix.element_tables(topo, p)
+        key = capi.orientation_keys(topo, g[f"shape_{tag}_ids"][None, :])[0]
+        qpts, qw, phi, dphi = strmatrix.element_tables(topo, p, key)
         assert np.array_equal(qpts, g[f"rule_{tag}_pts"])  # integration points: bit-exact
         assert np.array_equal(qw, g[f"rule_{tag}_w"])
         assert phi.shape == g[f"shape_{tag}_phi"].shape
         assert np.abs(phi - g[f"shape_{tag}_phi"]).max() < 4e-16
         assert np.abs(dphi - g[f"shape_{tag}_dphi"]).max() < 1e-15
+        if f"shapeall_{tag}_phi" in g:  # p >= 3: every element of the fixture, each with its own orientation class
+            keys = capi.orientation_keys(topo, g[f"shapeall_{tag}_ids"])
+            pts = qpts[g[f"shapeall_{tag}_q"]]
+            for e, k in enumerate(keys):
+                phi, dphi = capi.shape_tables(topo, p, pts, k)
+                assert np.abs(phi - g[f"shapeall_{tag}_phi"][e]).max() < 4e-16
+                assert np.abs(dphi - g[f"shapeall_{tag}_dphi"][e]).max() < 2e-15
 
 
 def test_gauss_legendre_orders():
