@@ -116,6 +116,11 @@ int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *ja_host);
  * StrMatrix/pzstrmatrixor.cpp:157-250 for all elements at once) and, when the host pointers are
  * non-NULL, copies the result back: a_host[nnz] in CSR order, rhs_host[neq].  Synchronous. */
 int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_host);
+/* Load vector only: TPZStrMatParInterface::Assemble(rhs) (StrMatrix/TPZStrMatParInterface.h:47-48; the reference's
+ * CalcResidual path Mesh/pzinterpolationspace.cpp:476-527, which for these linear materials evaluates the same ef as
+ * CalcStiff).  Zeroes rhs on the device, runs every group without the Gram products and without touching the CSR
+ * values, copies rhs back when rhs_host != NULL. */
+int b200asm_assemble_rhs(b200asm_ctx *ctx, double *rhs_host);
 /* asynchronous, device resident (no copies, no synchronisation): enqueue on the context stream */
 int b200asm_assemble_async(b200asm_ctx *ctx);
 int b200asm_synchronize(b200asm_ctx *ctx);
@@ -123,6 +128,17 @@ int b200asm_synchronize(b200asm_ctx *ctx);
 int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_host);
 /* device pointers of the resident CSR values / rhs (for a GPU solver downstream) */
 int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev);
+/* ---- solve (device resident) ------------------------------------------------------------------
+ * Conjugate gradients on the resident CSR values, statement by statement the reference's
+ * CG(A, x, b, M, residual, max_iter, tol, FromCurrent) (Solvers/LinearSolvers/cg.h:44-120) with the product of
+ * TPZSYsmpMatrix::MultAdd (Matrix/pzsysmp.cpp:190-232) / TPZFYsmpMatrix::MultAdd.
+ * precond: 0 identity (TPZCopySolve), 1 one Jacobi sweep (TPZStepSolver::SetJacobi(1, 0., 0)): z = D^-1 r.
+ * f_host: right-hand side (NULL: the assembled load vector on the device).  x_host: initial guess when from_current != 0,
+ * receives the solution (NULL: leave it on the device, b200asm_cg_solution_device).  Stops when ||r||/||b|| <= tol
+ * (the reference's criterion) or after max_iter iterations; reports both. */
+int b200asm_cg_solve(b200asm_ctx *ctx, int precond, int64_t max_iter, double tol, int from_current, const double *f_host,
+                     double *x_host, int64_t *iters_out, double *resid_out);
+int b200asm_cg_solution_device(b200asm_ctx *ctx, double **x_dev);
 /* Multi-GPU interface exchange (row-sharded assembly, neopz_b200/distributed.py): adds n values received from the
  * neighbouring rank into the resident CSR values (target 0) or rhs (target 1) at precomputed, distinct
  * positions: dst[positions[k]] += values[k].  positions/values are DEVICE pointers; asynchronous. */

@@ -43,7 +43,8 @@ SYMBOLS = [
     "b200asm_download", "b200asm_device_pointers", "b200asm_counters", "b200asm_scatter_add", "b200asm_group_time_ms",
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
     "b200asm_nshape", "b200asm_orientation_keys", "b200asm_shape_tables_oriented",
-    "b200asm_build_pattern_device", "b200asm_get_pattern",
+    "b200asm_build_pattern_device", "b200asm_get_pattern", "b200asm_cg_solve", "b200asm_cg_solution_device",
+    "b200asm_assemble_rhs",
 ]
 
 
@@ -71,6 +72,7 @@ def lib():
     L.b200asm_set_pattern.argtypes = [vp, C.c_int64, ip64, ip64, C.c_int]
     L.b200asm_assemble.argtypes = [vp, dp, dp]
     L.b200asm_assemble_async.argtypes = [vp]
+    L.b200asm_assemble_rhs.argtypes = [vp, dp]
     L.b200asm_synchronize.argtypes = [vp]
     L.b200asm_download.argtypes = [vp, dp, dp]
     L.b200asm_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -82,6 +84,8 @@ def lib():
     L.b200asm_shape_tables.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.b200asm_build_pattern_device.argtypes = [vp, C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64]
     L.b200asm_get_pattern.argtypes = [vp, ip64, ip64]
+    L.b200asm_cg_solve.argtypes = [vp, C.c_int, C.c_int64, C.c_double, C.c_int, dp, dp, ip64, dp]
+    L.b200asm_cg_solution_device.argtypes = [vp, C.POINTER(vp)]
     L.b200asm_nshape.argtypes = [C.c_int, C.c_int]
     L.b200asm_orientation_keys.argtypes = [C.c_int, C.c_int64, ip32, ip64]
     L.b200asm_shape_tables_oriented.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, dp, dp, dp]
@@ -173,6 +177,7 @@ class Context:
         if rc != 0:
             raise B200AsmError(rc, lib().b200asm_last_error(None).decode())
         self._keep = []
+        self._neq = 0
 
     def _check(self, rc):
         if rc < 0:
@@ -233,6 +238,7 @@ class Context:
         ia = np.ascontiguousarray(ia, dtype=np.int64)
         ja = np.ascontiguousarray(ja, dtype=np.int64)
         self._check(lib().b200asm_set_pattern(self._h, len(ia) - 1, i64ptr(ia), i64ptr(ja), int(bool(symmetric))))
+        self._neq = len(ia) - 1
 
     def build_pattern_device(self, symmetric, elgraphindex, elgraph, blockpos, blocksize):
         """CSR pattern of the reference built on the device from the element graph; becomes the current pattern.
@@ -245,6 +251,7 @@ class Context:
         self._check(lib().b200asm_build_pattern_device(self._h, int(bool(symmetric)), len(elgraphindex) - 1, i64ptr(elgraphindex),
                                                        i64ptr(elgraph), len(blockpos), i64ptr(blockpos), i64ptr(blocksize),
                                                        C.byref(neq), C.byref(nnz)))
+        self._neq = neq.value
         return neq.value, nnz.value
 
     def get_pattern(self, neq, nnz, want_ja=True):
@@ -253,8 +260,30 @@ class Context:
         self._check(lib().b200asm_get_pattern(self._h, i64ptr(ia), i64ptr(ja)))
         return ia, ja
 
+    def cg_solve(self, precond=1, max_iter=50000, tol=1e-15, x0=None, f=None, download=True):
+        """CG on the device-resident matrix (reference algorithm: Solvers/LinearSolvers/cg.h:44-120).
+        Returns (x or None, iterations, relative residual)."""
+        n = self.neq()
+        x = None
+        if x0 is not None:
+            x = np.ascontiguousarray(x0, dtype=np.float64).copy()
+        elif download:
+            x = np.zeros(n)
+        if f is not None:
+            f = np.ascontiguousarray(f, dtype=np.float64)
+        it, res = C.c_int64(), C.c_double()
+        self._check(lib().b200asm_cg_solve(self._h, int(precond), int(max_iter), float(tol), int(x0 is not None), dptr(f), dptr(x),
+                                           C.byref(it), C.byref(res)))
+        return x, it.value, res.value
+
+    def neq(self):
+        return self._neq
+
     def assemble(self, a_host=None, rhs_host=None):
         self._check(lib().b200asm_assemble(self._h, dptr(a_host), dptr(rhs_host)))
+
+    def assemble_rhs(self, rhs_host=None):
+        self._check(lib().b200asm_assemble_rhs(self._h, dptr(rhs_host)))
 
     def assemble_async(self):
         self._check(lib().b200asm_assemble_async(self._h))

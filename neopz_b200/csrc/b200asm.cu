@@ -57,6 +57,7 @@ struct VolParams {
     double *__restrict__ rhs;
     int atomic;  // 1: red.global.add.f64; 0: plain read-modify-write (the launch covers one colour: no two
                  // elements of it share an equation, so no two threads touch the same entry)
+    int rhs_only;  // 1: load vector only (TPZStrMatParInterface::Assemble(rhs)): no Gram products, no matrix scatter
     double coef[16];
 };
 
@@ -86,6 +87,7 @@ __device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) 
 #include "gram_mma.cuh"
 #include "gram_mma_team.cuh"
 #include "pattern_device.cuh"
+#include "cg_device.cuh"
 
 // decode the linear index of an upper-triangular tile into (bi, bj), bi <= bj
 template <int NTB>
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(C::NTHREADS) assemble_volume_kernel(const VolP
             }
             __syncthreads();
             // ---- phase 3: Gram update of this thread's register tile --------------------------
-            if (has_tile && el_t < nloc) {
+            if (has_tile && el_t < nloc && !p.rhs_only) {
                 const double *row = Ab + (size_t)el_t * AS;
 #pragma unroll
                 for (int kr = 0; kr < KQ; kr++) {
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(C::NTHREADS) assemble_volume_kernel(const VolP
         }
 
         // ---- epilogue: scatter-add into CSR values and rhs -----------------------------------
-        if (has_tile && el_t < nloc) {
+        if (has_tile && el_t < nloc && !p.rhs_only) {
             if (NS == 3) {
                 // nine sums S[v][u] per node pair -> the 3x3 block of ek  (TPZElasticity3D.cpp:318-326)
                 const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
@@ -359,6 +361,7 @@ struct BcParams {
     int64_t nel;      // elements of the group (stride of the entry-major scatter map)
     int64_t el0, el1; // this launch covers elements [el0, el1) (one colour, or the whole group)
     int atomic;
+    int rhs_only;
     int nq;
     const double *__restrict__ xyz;
     const int32_t *__restrict__ elnodes;
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
             for (int a = 0; a < NS; a++)
 #pragma unroll
                 for (int b = 0; b < NS; b++) {
+                    if (p.rhs_only) continue;
                     if (i == j && b < a) continue;
                     const double mab = p.coef[a * 3 + b], mba = p.coef[b * 3 + a];
                     if (mab == 0.0 && mba == 0.0) continue;
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
         W[q] = __ldg(p.qw + q) * fabs(det);
     }
     __syncwarp();
-    const int npair = N * (N + 1) / 2;
+    const int npair = p.rhs_only ? 0 : N * (N + 1) / 2;
     for (int idx = lane; idx < npair; idx += 32) {
         int i = 0, rem = idx;  // (i, j), i <= j, row-major over the upper triangle
         while (rem >= N - i) { rem -= N - i; i++; }
@@ -581,6 +585,7 @@ thread_local std::string g_create_error;
 struct Group {
     int topology = 0, porder = 0, kind = 0, ns = 1, nn = 0, n = 0, nq = 0, m = 0, dim = 3;
     int64_t nel = 0, nbatch = 0;
+    int64_t max_dest = -1;  // largest destination equation of the group
     int cfg = -1;  // index into the dispatch table (register-tile kernels)
     int mma = -1;  // index into the DMMA dispatch table, -1: none
     double coef[16];
@@ -612,9 +617,15 @@ struct b200asm_ctx {
     int32_t *d_ja = nullptr;  // column indices, resident (scatter maps, SpMV of the CG solver)
     double *d_a = nullptr, *d_rhs = nullptr;
     int *d_missing = nullptr;
+    // conjugate-gradient workspace (b200asm_cg_solve), allocated on first use for cg_n equations
+    int64_t cg_n = 0;
+    double *d_cg = nullptr;       // x, r, p, z, q, diag, f: 7 vectors
+    double *d_cg_part = nullptr;  // per-CTA partial sums
+    cgdev::Scalars *d_cg_sc = nullptr;
     int64_t launches = 0, h2d = 0, d2h = 0;
     int scatter = B200ASM_SCATTER_ATOMIC;
     int engine = 1;  // 1: DMMA panel kernel where one exists, 0: register-tile DFMA kernels only
+    int rhs_only = 0;  // set while b200asm_assemble_rhs runs
     int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
     std::string err;
 };
@@ -922,6 +933,7 @@ extern "C" void b200asm_destroy(b200asm_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Group &g : ctx->groups) free_group(g);
     cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
+    cudaFree(ctx->d_cg); cudaFree(ctx->d_cg_part); cudaFree(ctx->d_cg_sc);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1029,6 +1041,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             const int64_t d = gi->dest[src * g.m + k];
             if (d < 0 || d > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "add_group: destination index out of int32 range");
             dest32[(size_t)e * g.m + k] = (int32_t)d;
+            g.max_dest = std::max(g.max_dest, d);
         }
         for (int k = 0; k < g.nn; k++) elnodes[(size_t)e * g.nn + k] = gi->elnodes[src * g.nn + k];
     }
@@ -1255,11 +1268,11 @@ extern "C" int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *
 
 extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
     if (!ctx) return B200ASM_EINVAL;
-    if (!ctx->have_pattern) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
+    if (!ctx->have_pattern && !ctx->rhs_only) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
     if (!ctx->d_xyz) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_nodes first");
     CK(cudaSetDevice(ctx->device));
     // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75
-    CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
+    if (!ctx->rhs_only) CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
     const int atomic = ctx->scatter == B200ASM_SCATTER_ATOMIC ? 1 : 0;
     for (Group &g : ctx->groups) {
@@ -1273,7 +1286,7 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             BcParams p;
             p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
             p.qw = g.d_qw; p.phi = g.d_phi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
-            p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic;
+            p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
             memcpy(p.coef, g.coef, sizeof(p.coef));
             for (size_t c = 0; c < nseg; c++) {
                 p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];
@@ -1301,7 +1314,7 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             const int64_t e0 = g.seg[c], n = g.seg[c + 1] - g.seg[c];
             if (n == 0) continue;
             VolParams p;
-            p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = atomic;
+            p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
             p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
             p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
             p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;
@@ -1312,13 +1325,14 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             if (use_mma) {
                 const MmaEntry &me = kMma[g.mma];
                 const size_t off = (size_t)e0 * me.slots;
-                p.nbatch = 0; p.smap = g.d_smap + off; p.smapT = g.d_smapT ? g.d_smapT + off : nullptr;
+                p.nbatch = 0; p.smap = g.d_smap ? g.d_smap + off : nullptr; p.smapT = g.d_smapT ? g.d_smapT + off : nullptr;
                 const int64_t want = (n + me.wpc - 1) / me.wpc;
                 CK(me.launch(p, (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
             } else {
                 const VolEntry &ve = kVol[g.cfg];
                 p.nbatch = (n + ve.epb - 1) / ve.epb;
-                p.smap = g.d_smap + g.seg_smap[c]; p.smapT = g.d_smapT ? g.d_smapT + g.seg_smap[c] : nullptr;
+                const size_t soff = c < g.seg_smap.size() ? g.seg_smap[c] : 0;  // (no maps yet in a pattern-less rhs-only run)
+                p.smap = g.d_smap ? g.d_smap + soff : nullptr; p.smapT = g.d_smapT ? g.d_smapT + soff : nullptr;
                 CK(ve.launch(p, (int)std::min<int64_t>(p.nbatch, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
             }
             ctx->launches++;
@@ -1367,6 +1381,33 @@ extern "C" int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_ho
     return b200asm_download(ctx, a_host, rhs_host);
 }
 
+extern "C" int b200asm_assemble_rhs(b200asm_ctx *ctx, double *rhs_host) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (!ctx->have_pattern) {
+        // no matrix pattern (TPZLinearAnalysis::AssembleResidual before any Assemble): size the load vector from the
+        // destination indices of the groups
+        int64_t neq = 0;
+        for (const Group &g : ctx->groups) neq = std::max(neq, g.max_dest + 1);
+        if (neq != ctx->neq || !ctx->d_rhs) {
+            CK(cudaSetDevice(ctx->device));
+            cudaFree(ctx->d_rhs);
+            ctx->d_rhs = nullptr;
+            CK(cudaMalloc((void **)&ctx->d_rhs, std::max<int64_t>(neq, 1) * sizeof(double)));
+            ctx->neq = neq;
+        }
+    }
+    ctx->rhs_only = 1;
+    int rc = b200asm_assemble_async(ctx);
+    ctx->rhs_only = 0;
+    if (rc) return rc;
+    if (rhs_host) {
+        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs, (size_t)ctx->neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += ctx->neq * (int64_t)sizeof(double);
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
 extern "C" int b200asm_scatter_add(b200asm_ctx *ctx, int target, const int32_t *positions_dev, const double *values_dev, int64_t n) {
     if (!ctx || n < 0 || (n && (!positions_dev || !values_dev)) || (target != 0 && target != 1))
         return fail(ctx, B200ASM_EINVAL, "scatter_add: bad arguments");
@@ -1379,6 +1420,100 @@ extern "C" int b200asm_scatter_add(b200asm_ctx *ctx, int target, const int32_t *
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
+}
+
+extern "C" int b200asm_cg_solve(b200asm_ctx *ctx, int precond, int64_t max_iter, double tol, int from_current, const double *f_host,
+                                double *x_host, int64_t *iters_out, double *resid_out) {
+    if (!ctx || max_iter < 0 || (precond != 0 && precond != 1)) return fail(ctx, B200ASM_EINVAL, "cg_solve: bad arguments");
+    if (!ctx->have_pattern || !ctx->d_a || !ctx->d_ja) return fail(ctx, B200ASM_ESTATE, "cg_solve: assemble a matrix first");
+    if (from_current && !x_host && ctx->cg_n != ctx->neq) return fail(ctx, B200ASM_EINVAL, "cg_solve: from_current needs an initial guess");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->neq;
+    cudaStream_t st = ctx->stream;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + cgdev::THREADS - 1) / cgdev::THREADS, (int64_t)ctx->num_sms * 8));
+    const int grid_rows = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->num_sms * 32));
+    if (ctx->cg_n != n || !ctx->d_cg) {
+        cudaFree(ctx->d_cg); cudaFree(ctx->d_cg_part); cudaFree(ctx->d_cg_sc);
+        ctx->d_cg = ctx->d_cg_part = nullptr; ctx->d_cg_sc = nullptr; ctx->cg_n = 0;
+        CK(cudaMalloc((void **)&ctx->d_cg, (size_t)std::max<int64_t>(n, 1) * 7 * sizeof(double)));
+        CK(cudaMalloc((void **)&ctx->d_cg_part, (size_t)ctx->num_sms * 8 * sizeof(double)));
+        CK(cudaMalloc((void **)&ctx->d_cg_sc, sizeof(cgdev::Scalars)));
+        CK(cudaMemsetAsync(ctx->d_cg, 0, (size_t)std::max<int64_t>(n, 1) * 7 * sizeof(double), st));
+        ctx->cg_n = n;
+    }
+    double *x = ctx->d_cg, *r = x + n, *p = r + n, *z = p + n, *q = z + n, *diag = q + n, *f = diag + n;
+    cgdev::Scalars *sc = ctx->d_cg_sc;
+    CK(cudaMemsetAsync(sc, 0, sizeof(cgdev::Scalars), st));
+    // right-hand side: the host vector the caller passes (TPZMatrixSolver::Solve(F, ...)) or the assembled load vector
+    if (f_host) {
+        CK(cudaMemcpyAsync(f, f_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        ctx->h2d += n * (int64_t)sizeof(double);
+    } else {
+        CK(cudaMemcpyAsync(f, ctx->d_rhs, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    auto read_scalars = [&](cgdev::Scalars &h) -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(st);
+    };
+    cgdev::Scalars h{};
+    // normb = Norm(b)
+    cgdev::dot_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, f, f, ctx->d_cg_part, sc, 1);
+    CK(read_scalars(h));
+    double normb = std::sqrt(h.rr);
+    if (normb == 0.0) normb = 1.0;
+    // r = b - A x  (FromCurrent)  or  x = 0, r = b
+    CK(cudaMemcpyAsync(r, f, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (from_current) {
+        if (x_host) {
+            CK(cudaMemcpyAsync(x, x_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+            ctx->h2d += n * (int64_t)sizeof(double);
+        }
+        cgdev::spmv_kernel<<<grid_rows, cgdev::THREADS, 0, st>>>(n, ctx->d_ia, ctx->d_ja, ctx->d_a, ctx->symmetric, -1.0, x, r);
+        ctx->launches++;
+    } else {
+        CK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), st));
+    }
+    if (precond == 1) {
+        cgdev::extract_diag_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, ctx->d_ia, ctx->d_ja, ctx->d_a, ctx->symmetric, diag);
+        ctx->launches++;
+    }
+    cgdev::dot_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, r, r, ctx->d_cg_part, sc, 1);
+    ctx->launches += 2;
+    CK(read_scalars(h));
+    double resid = std::sqrt(h.rr) / normb;
+    int64_t it = 0;
+    if (resid > tol) {
+        for (it = 1; it <= max_iter; it++) {
+            cgdev::precond_dot_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, r, precond == 1 ? diag : nullptr, z, ctx->d_cg_part, sc);
+            cgdev::update_p_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, it == 1, z, p, sc);
+            CK(cudaMemsetAsync(q, 0, (size_t)n * sizeof(double), st));
+            cgdev::spmv_kernel<<<grid_rows, cgdev::THREADS, 0, st>>>(n, ctx->d_ia, ctx->d_ja, ctx->d_a, ctx->symmetric, 1.0, p, q);
+            cgdev::dot_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, p, q, ctx->d_cg_part, sc, 0);
+            cgdev::update_xr_kernel<<<grid, cgdev::THREADS, 0, st>>>(n, p, q, x, r, ctx->d_cg_part, sc);
+            ctx->launches += 5;
+            CK(read_scalars(h));
+            resid = std::sqrt(h.rr) / normb;
+            if (!(resid == resid)) return fail(ctx, B200ASM_ECUDA, "cg_solve: the iteration produced NaN (singular or indefinite system)");
+            if (resid <= tol) break;
+        }
+        if (it > max_iter) it = max_iter;
+    }
+    CK(cudaGetLastError());
+    if (x_host) {
+        CK(cudaMemcpyAsync(x_host, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->d2h += n * (int64_t)sizeof(double);
+    }
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = resid;
+    return 0;
+}
+
+extern "C" int b200asm_cg_solution_device(b200asm_ctx *ctx, double **x_dev) {
+    if (!ctx || !x_dev) return B200ASM_EINVAL;
+    *x_dev = ctx->d_cg;
+    return ctx->d_cg ? 0 : fail(ctx, B200ASM_ESTATE, "cg_solution_device: no solve yet");
 }
 
 extern "C" int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev) {

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
         // the scatter positions of this element are fetched now (HBM latency hidden behind the arithmetic):
         // the atomics of the epilogue would otherwise serialise these loads
         int32_t pos[NTILES * 2];
-        {
+        if (!p.rhs_only) {
             const int32_t *sm = p.smap + (size_t)el * C::SLOTS + lane;
 #pragma unroll
             for (int k = 0; k < NTILES * 2; k++) pos[k] = __ldcs(sm + k * 32);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
 #pragma unroll
         for (int t = 0; t < NTILES; t++) acc[t][0] = acc[t][1] = 0.0;
 
-        for (int q0 = 0; q0 < nq; q0 += QC) {
+        for (int q0 = 0; q0 < (p.rhs_only ? 0 : nq); q0 += QC) {
             // ---- phase 2: panel rows of QC points (Mesh/TPZCompElH1.cpp:147): lane <-> shape function,
             // the table loads of all QC points are issued before the first use
             for (int i = lane; i < N; i += 32) {
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             scatter_add(p.rhs + p.dest[el * N + lane], f, p.atomic);
         }
         // ---- scatter-add of the upper triangle ---------------------------------------------------
+        if (p.rhs_only) continue;
         const double s = p.coef[0];
         const int32_t *smT = p.smapT ? p.smapT + (size_t)el * C::SLOTS + lane : nullptr;
         if (smT) {

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
             Xs[tt * 3 + 1] = p.xyz[node * 3 + 1];
             Xs[tt * 3 + 2] = p.xyz[node * 3 + 2];
         }
-        {   // pull this element's scatter positions towards L2 while the arithmetic runs
+        if (!p.rhs_only) {   // pull this element's scatter positions towards L2 while the arithmetic runs
             const char *base = (const char *)(p.smap + (size_t)el * C::SLOTS);
             for (int off = tt * 128; off < C::SLOTS * 4; off += TT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
         }
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
             }
             team_sync<TT>(team);
             // ---- phase 3: Gram update by every warp for its tile groups --------------------------------
-            TeamRole<C, 0>::mma(w, Pn, acc, g, tg);
+            if (!p.rhs_only) TeamRole<C, 0>::mma(w, Pn, acc, g, tg);
             // ---- load vector of the chunk's points ------------------------------------------------------
 #pragma unroll
             for (int k = 0; k < FPT; k++) {
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
             const int m = tt + k * TT;
             if (m < M) scatter_add(p.rhs + p.dest[el * M + m], facc[k], p.atomic);
         }
-        TeamRole<C, 0>::epilogue(w, p, el, acc, lane);
+        if (!p.rhs_only) TeamRole<C, 0>::epilogue(w, p, el, acc, lane);
     }
 }
 

@@ -345,6 +345,34 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
 
 }  // namespace
 
+namespace {
+// (re)flatten when the mesh changed, otherwise refresh node coordinates and material constants
+void PrepareMesh(TPZB200AssemblyCache &c, TPZStructMatrix *strmat, int device) {
+    TPZCompMesh *cmesh = strmat->Mesh();
+    if (!c.ctx) {
+        if (b200asm_create(&c.ctx, device) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
+    }
+    auto t0 = clk::now();
+    c.flatten_ms = 0;
+    if (c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects()) {
+        Flatten(c, strmat);
+        c.flatten_ms = ms_since(t0);
+        return;
+    }
+    TPZGeoMesh *gmesh = cmesh->Reference();
+    const int64_t nnodes = gmesh->NNodes();
+    std::vector<double> xyz((size_t)nnodes * 3);
+    for (int64_t i = 0; i < nnodes; i++)
+        for (int d = 0; d < 3; d++) xyz[(size_t)i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
+    Check(c, b200asm_set_nodes(c.ctx, nnodes, xyz.data()), "b200asm_set_nodes");
+    int gi = 0;
+    for (HostGroup &g : c.groups) {
+        FillCoef(g);
+        Check(c, b200asm_set_group_coef(c.ctx, gi++, g.meta.coef), "b200asm_set_group_coef");
+    }
+}
+}  // namespace
+
 template <class TVar>
 TPZStructMatrixB200<TVar>::TPZStructMatrixB200() : fCache(std::make_shared<TPZB200AssemblyCache>()) {}
 
@@ -383,32 +411,10 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     if (!sym && !full) Fatal("the stiffness matrix must be TPZSYsmpMatrix<STATE> or TPZFYsmpMatrix<STATE>");
     TPZCompMesh *cmesh = strmat->Mesh();
     TPZB200AssemblyCache &c = *fCache;
-    if (!c.ctx) {
-        if (b200asm_create(&c.ctx, fDevice) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
-    }
-    // (re)flatten when the mesh changed
-    auto t0 = clk::now();
-    c.flatten_ms = 0;
-    if (c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects()) {
-        Flatten(c, strmat);
-        c.flatten_ms = ms_since(t0);
-    } else {
-        // geometry and material constants may have changed since the last assembly
-        TPZGeoMesh *gmesh = cmesh->Reference();
-        const int64_t nnodes = gmesh->NNodes();
-        std::vector<double> xyz((size_t)nnodes * 3);
-        for (int64_t i = 0; i < nnodes; i++)
-            for (int d = 0; d < 3; d++) xyz[(size_t)i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
-        Check(c, b200asm_set_nodes(c.ctx, nnodes, xyz.data()), "b200asm_set_nodes");
-        int gi = 0;
-        for (HostGroup &g : c.groups) {
-            FillCoef(g);
-            Check(c, b200asm_set_group_coef(c.ctx, gi++, g.meta.coef), "b200asm_set_group_coef");
-        }
-    }
+    PrepareMesh(c, strmat, fDevice);
     if (guiInterface && guiInterface->AmIKilled()) return;
     // pattern of the matrix Create() produced
-    t0 = clk::now();
+    auto t0 = clk::now();
     c.pattern_ms = 0;
     const int symmetric = sym ? 1 : 0;
     double *values = nullptr;
@@ -455,10 +461,48 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     c.assemble_ms = ms_since(t0);
 }
 
+// Right-hand side only (TPZLinearAnalysis::AssembleResidual, Analysis/TPZLinearAnalysis.cpp:96-120; the OR strategy's
+// CalcResidual loop, StrMatrix/pzstrmatrixor.cpp:253-365).  For the supported (linear) materials CalcResidual evaluates
+// the same ef as CalcStiff, so the device runs the assembly kernels without the Gram products and the matrix scatter.
 template <class TVar>
 void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) {
-    // residual-only assembly (TPZLinearAnalysis::AssembleResidual) is row N3 of the scope table: not yet on the device
-    Fatal("Assemble(rhs) (right-hand side only) is not implemented yet; use Assemble(stiffness, rhs)");
+    auto *strmat = dynamic_cast<TPZStructMatrix *>(this);
+    if (!strmat) Fatal("the strategy must be combined with a TPZStructMatrix");
+    if (strmat->EquationFilter().IsActive()) Fatal("an active equation filter is not supported yet");
+    auto *rhsmat = dynamic_cast<TPZFMatrix<STATE> *>(&rhs);
+    if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
+    TPZB200AssemblyCache &c = *fCache;
+    PrepareMesh(c, strmat, fDevice);
+    if (guiInterface && guiInterface->AmIKilled()) return;
+    auto t0 = clk::now();
+    const int64_t neq = rhsmat->Rows();
+    if (neq != c.neq || rhsmat->Cols() != 1) Fatal("rhs has the wrong size (one load case, NEquations rows)");
+    std::vector<double> rhsloc(neq);
+    Check(c, b200asm_assemble_rhs(c.ctx, rhsloc.data()), "b200asm_assemble_rhs");
+    double *dst = &(*rhsmat)(0, 0);
+    for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc[i];  // the reference ADDS into rhs (TPZFMatrix::AddFel)
+    c.assemble_ms = ms_since(t0);
+}
+
+// CG on the device-resident matrix of the last Assemble(stiffness, rhs): the reference's algorithm
+// (Solvers/LinearSolvers/cg.h:44-120) with TPZStepSolver::SetJacobi(1, 0., 0) or no preconditioner.
+template <class TVar>
+void TPZStructMatrixB200<TVar>::SolveCG(const TPZFMatrix<TVar> &F, TPZFMatrix<TVar> &result, int64_t &numiterations, REAL &tol,
+                                        bool jacobi, int fromcurrent) {
+    TPZB200AssemblyCache &c = *fCache;
+    if (!c.ctx || !c.pattern_set) Fatal("SolveCG: Assemble(stiffness, rhs) must run first (the matrix lives on the device)");
+    if constexpr (std::is_same<TVar, double>::value) {
+        if (F.Rows() != c.neq || F.Cols() != 1) Fatal("SolveCG: F has the wrong size");
+        if (!fromcurrent || result.Rows() != c.neq || result.Cols() != 1) result.Redim(c.neq, 1);
+        int64_t iters = 0;
+        double resid = 0;
+        Check(c, b200asm_cg_solve(c.ctx, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid),
+              "b200asm_cg_solve");
+        numiterations = iters;
+        tol = resid;
+    } else {
+        Fatal("SolveCG: STATE = double only");
+    }
 }
 
 template <class TVar>

@@ -27,7 +27,9 @@
 
 #include <memory>
 
+#include "TPZMatrixSolver.h"
 #include "TPZStrMatParInterface.h"
+#include "pzfmatrix.h"
 #include "pzreal.h"
 
 class TPZBaseMatrix;
@@ -49,6 +51,12 @@ public:
     //! Assemble the global right hand side vector.
     void Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) override;
 
+    //! Conjugate gradients on the device-resident matrix of the last Assemble(stiffness, rhs) — the reference's CG
+    //! (Solvers/LinearSolvers/cg.h:44-120) with TPZStepSolver::SetJacobi(1,0.,0) (jacobi) or no preconditioner.
+    //! numiterations / tol: in = limits, out = iterations done / relative residual reached (like TPZMatrix::SolveCG).
+    void SolveCG(const TPZFMatrix<TVar> &F, TPZFMatrix<TVar> &result, int64_t &numiterations, REAL &tol, bool jacobi = true,
+                 int fromcurrent = 0);
+
     //! CUDA device used by this strategy (default 0).
     void SetDevice(int device) { fDevice = device; }
     int Device() const { return fDevice; }
@@ -65,4 +73,31 @@ protected:
 };
 
 extern template class TPZStructMatrixB200<STATE>;
+
+/**
+ * @brief TPZMatrixSolver that solves with the matrix the B200 strategy left on the device (no factorisation, no copy of
+ * the matrix): `TPZB200CGSolver<STATE> solver(strategy); an.SetSolver(solver); an.Solve();` — the drop-in for
+ * `TPZStepSolver::SetCG(numiter, Jacobi, tol, fromcurrent)`.
+ */
+template <class TVar>
+class TPZB200CGSolver : public TPZMatrixSolver<TVar> {
+public:
+    TPZB200CGSolver(TPZStructMatrixB200<TVar> *strategy, int64_t maxiter = 50000, REAL tol = 1.e-15, bool jacobi = true, int fromcurrent = 0)
+        : fStrategy(strategy), fMaxIter(maxiter), fTol(tol), fJacobi(jacobi), fFromCurrent(fromcurrent) {}
+    void Solve(const TPZFMatrix<TVar> &F, TPZFMatrix<TVar> &result, TPZFMatrix<TVar> *residual = 0) override {
+        fNumIterations = fMaxIter;
+        fResidual = fTol;
+        fStrategy->SolveCG(F, result, fNumIterations, fResidual, fJacobi, fFromCurrent);
+    }
+    TPZSolver *Clone() const override { return new TPZB200CGSolver<TVar>(*this); }
+    int64_t NumIterations() const { return fNumIterations; }
+    REAL Residual() const { return fResidual; }
+
+private:
+    TPZStructMatrixB200<TVar> *fStrategy;
+    int64_t fMaxIter, fNumIterations{0};
+    REAL fTol, fResidual{0};
+    bool fJacobi;
+    int fFromCurrent;
+};
 #endif

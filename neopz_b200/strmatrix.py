@@ -221,6 +221,20 @@ class TPZStructMatrixB200:
         self.ctx.assemble(a, rhs)
         return a, rhs
 
+    def AssembleRhs(self, rhs=None):
+        """TPZStrMatParInterface::Assemble(rhs): the load vector only (the CSR values on the device stay untouched)."""
+        if self.ia is None:
+            raise RuntimeError("AssembleRhs: call Create() first")
+        if rhs is None:
+            rhs = np.empty(self.mesh.neq)
+        self.ctx.assemble_rhs(rhs)
+        return rhs
+
+    def SolveCG(self, max_iter=50000, tol=1e-15, jacobi=True, x0=None, f=None):
+        """TPZStepSolver::SetCG(max_iter, Jacobi(1) | TPZCopySolve, tol, FromCurrent) + Solve on the device-resident system.
+        Returns (solution, iterations, relative residual)."""
+        return self.ctx.cg_solve(1 if jacobi else 0, max_iter, tol, x0=x0, f=f)
+
     def CreateAssemble(self):
         ia, ja = self.Create()
         a, rhs = self.Assemble()

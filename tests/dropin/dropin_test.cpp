@@ -83,6 +83,9 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
 struct Csr {
     std::vector<int64_t> ia, ja;
     std::vector<double> a, rhs, sol;
+    std::vector<double> residual_rhs;  // TPZLinearAnalysis::AssembleResidual() -> Assemble(rhs)
+    std::vector<double> sol_device;    // B200 only: CG on the device-resident matrix (TPZB200CGSolver through an.Solve())
+    int64_t device_cg_iters = 0;
 };
 
 template <class TStrMat>
@@ -131,6 +134,27 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
         cg.Solve(f, sol);
         out.sol.resize(neq);
         for (int64_t i = 0; i < neq; i++) out.sol[i] = sol(i, 0);
+        // the same solve on the GPU, through the unmodified TPZLinearAnalysis::Solve(): the matrix the strategy left on
+        // the device, the reference's CG algorithm with its Jacobi(1) preconditioner
+        auto *b200 = dynamic_cast<TPZStructMatrixB200<STATE> *>(an.StructMatrix().operator->());
+        if (b200) {
+            TPZB200CGSolver<STATE> dev(b200, 50000, 1.e-15, true, 0);
+            dev.SetMatrix(mtx);
+            an.SetSolver(dev);
+            an.Solve();
+            TPZFMatrix<STATE> &u = an.Solution();
+            out.sol_device.resize(neq);
+            for (int64_t i = 0; i < neq; i++) out.sol_device[i] = u(i, 0);
+            auto *used = dynamic_cast<TPZB200CGSolver<STATE> *>(an.Solver());
+            out.device_cg_iters = used ? used->NumIterations() : -1;
+        }
+    }
+    // right-hand side only: TPZLinearAnalysis::AssembleResidual() -> TPZStrMatParInterface::Assemble(rhs)
+    an.AssembleResidual();
+    out.residual_rhs.resize(neq);
+    {
+        TPZFMatrix<STATE> &res = an.Rhs();
+        for (int64_t i = 0; i < neq; i++) out.residual_rhs[i] = res(i, 0);
     }
 }
 
@@ -189,14 +213,19 @@ int main(int argc, char **argv) {
     const double errMT = RelF(refmt.a, ref.a);
     double errSol = 0;
     if (solve && symmetric) errSol = RelF(gpu.sol, ref.sol);
+    double errSolDev = 0;
+    if (solve && symmetric) errSolDev = RelF(gpu.sol_device, ref.sol);
+    const double errRes = RelF(gpu.residual_rhs, ref.residual_rhs), errResVsRhs = RelF(ref.residual_rhs, ref.rhs);
     const int64_t nvol = (int64_t)n * n * n * (tet ? 5 : 1);
-    const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10;
+    const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
     std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric
               << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
               << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
               << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel
-              << ", \"relF_rhs\": " << errR << ", \"relF_cg_solution\": " << errSol << ", \"relF_A_ref_threads_vs_serial\": " << errMT
+              << ", \"relF_rhs\": " << errR << ", \"relF_cg_solution\": " << errSol << ", \"relF_device_cg_solution\": " << errSolDev
+              << ", \"device_cg_iterations\": " << gpu.device_cg_iters << ", \"relF_residual_rhs\": " << errRes
+              << ", \"ref_residual_rhs_vs_rhs\": " << errResVsRhs << ", \"relF_A_ref_threads_vs_serial\": " << errMT
               << ", \"cpu_serial_assemble_s\": " << t2 << ", \"cpu_threads\": " << threads << ", \"cpu_threaded_assemble_s\": " << tm2
               << ", \"gpu_first_assemble_s\": " << g1 << ", \"gpu_second_assemble_s\": " << g2 << ", \"ok\": " << ok << "}" << std::endl;
     return ok ? 0 : 1;

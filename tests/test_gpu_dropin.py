@@ -30,4 +30,10 @@ def test_dropin_strategy_matches_reference(case):
     assert r["ia_identical"] == 1 and r["ja_identical"] == 1
     assert r["relF_A"] <= 1e-12 and r["relF_A_nonpenalty_rows"] <= 1e-12 and r["relF_rhs"] <= 1e-12
     assert r["relF_cg_solution"] <= 1e-10
+    # N2: CG on the device-resident matrix through the unmodified TPZLinearAnalysis::Solve() vs the reference's CG
+    assert r["relF_device_cg_solution"] <= 1e-10
+    if case[4] == 1 and case[5] == 1:
+        assert r["device_cg_iterations"] > 0
+    # N3: TPZLinearAnalysis::AssembleResidual() -> Assemble(rhs) on the device vs TPZStructMatrixOR
+    assert r["relF_residual_rhs"] <= 1e-12
     assert out.returncode == 0

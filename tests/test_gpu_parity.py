@@ -123,6 +123,48 @@ def test_device_pattern_matches_host_builder_at_scale(n, p, ns, tet):
         ctx.close()
 
 
+@pytest.mark.parametrize("name", ["hex_p2_poisson_n3", "hex_p2_elast_n2_pert", "tet_p2_poisson_n2_pert", "hex_p3_poisson_n3_pert",
+                                  "hex_p1_poisson_n3_pert"])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_device_cg_reproduces_reference_solution(name, symmetric):
+    """GPU CG (Jacobi-preconditioned, the reference's algorithm) on the device-resident assembled system against the
+    reference's own direct (skyline LDLt) solution of the same mesh: 1e-10 (north_star)."""
+    g = gu.load(name)
+    m = g["meta"]
+    neumann = m["bctype"] == 1
+    bc = (-1, -1, -1, -1, -1, -2 if neumann else -1)
+    mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]), bc_matids=bc, perturb=m["perturb"])
+    strmat = sm.TPZStructMatrixB200(mesh, materials_for(m["phys"], neumann), symmetric=symmetric)
+    strmat.CreateAssemble()
+    u, iters, resid = strmat.SolveCG(max_iter=20000, tol=1e-15)
+    assert resid <= 1e-14 and 0 < iters < 20000, (iters, resid)
+    assert relF(u, g["sol"]) <= 1e-10
+    # restart from the solution: converged at iteration 0 (FromCurrent path)
+    # (the true residual b - A u of the penalised system is a little above the recurrence residual the iteration stopped on)
+    u2, it2, res2 = strmat.SolveCG(max_iter=10, tol=1e-9, x0=u)
+    assert it2 == 0 and res2 <= 1e-9 and np.array_equal(u2, u)
+
+
+@pytest.mark.parametrize("n,p,phys,tet,engine", [(4, 2, 0, 0, 1), (3, 2, 1, 0, 1), (3, 2, 1, 1, 0), (3, 4, 0, 0, 1), (5, 1, 0, 0, 0)])
+def test_rhs_only_assembly(n, p, phys, tet, engine):
+    """TPZStrMatParInterface::Assemble(rhs): load vector only, equal to the rhs of the full assembly (and the oracle's);
+    the CSR values on the device stay untouched; also works before any pattern exists (AssembleResidual first)."""
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    mats = materials_for(phys, neumann=True)
+    fresh = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, engine=engine)
+    fresh._flatten()
+    rhs0 = np.empty(mesh.neq)
+    fresh.ctx.assemble_rhs(rhs0)                       # no pattern yet
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, engine=engine)
+    ia, ja, a, rhs = strmat.CreateAssemble()
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    rhs1 = strmat.AssembleRhs()
+    assert relF(rhs1, rhs_ref) <= TOL and relF(rhs0, rhs_ref) <= TOL
+    a_after = np.empty_like(a)
+    strmat.ctx.download(a_after, None)
+    assert np.array_equal(a_after, a)                  # matrix untouched by the rhs-only pass
+
+
 def _shuffled(n, seed):
     """Random renumbering of the (n+1)^3 grid nodes: every element gets its own side orientations (p >= 3)."""
     return np.random.default_rng(seed).permutation((n + 1) ** 3)
