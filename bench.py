@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=0, help="grid size of the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--engine", type=int, default=1, help="0: register-tile DFMA kernels, 1: DMMA panel kernels where available")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
+    ap.add_argument("--pattern", default="device", choices=["device", "host"],
+                    help="one-off setup: CSR pattern built on the GPU (b200asm_build_pattern_device) or by the threaded host builder")
+    ap.add_argument("--cg", type=int, default=0, help="also time N iterations of the device-resident CG (reported as extra keys)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -224,11 +227,14 @@ def main():
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
     t0 = time.time()
-    ia, ja = sharded.Create() if sharded else strmat.Create()
+    if sharded:
+        ia, ja = sharded.Create()
+    else:
+        ia, ja = strmat.Create(on_device=a.pattern == "device", download=False)
     torch.cuda.synchronize()
     t_create = time.time() - t0
     nvol = len(mesh.blocks[0].elnodes)
-    neq, nnz = slab.nown, len(ja)
+    neq, nnz = slab.nown, (len(ja) if ja is not None else strmat.nnz)
     step_async = sharded.AssembleDevice if sharded else strmat.ctx.assemble_async
 
     def barrier():
@@ -304,6 +310,17 @@ def main():
                "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes + r_np.nbytes),
                "steps": ksteps, "note": "b200asm_set_nodes + b200asm_assemble(a_host, rhs_host), pinned host buffers"}
 
+    cg = None
+    if a.cg > 0 and world == 1:
+        # the step after assembly on the same resident matrix: a.cg iterations of the reference's CG algorithm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _x, iters, resid = strmat.ctx.cg_solve(1, a.cg, 0.0, download=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        cg = {"iterations": iters, "relative_residual": resid, "ms_per_iteration": dt * 1e3 / max(iters, 1),
+              "spmv_GBps_algorithmic": (12.0 * nnz + 24.0 * neq) * max(iters, 1) / dt / 1e9}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -366,9 +383,12 @@ def main():
             "config": {"workload": workload_name(a) if world == 1 else workload_name(a).replace(f"{a.n}^3", f"{a.n}x{a.n}x{a.n * world}") +
                        f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
-                       "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create}},
+                       "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
+                                   "pattern_builder": "host (sharded)" if world > 1 else a.pattern}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}
+    if cg:
+        line["device_cg"] = cg
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

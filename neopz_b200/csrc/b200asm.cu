@@ -612,7 +612,8 @@ struct b200asm_ctx {
     std::vector<Group> groups;
     int64_t neq = 0, nnz = 0;
     int symmetric = 1;
-    bool have_pattern = false;
+    bool have_pattern = false;  // IA/JA (and A, rhs) are on the device
+    bool maps_valid = false;    // the scatter maps match the current groups and pattern (rebuilt lazily by assemble)
     int64_t *d_ia = nullptr;
     int32_t *d_ja = nullptr;  // column indices, resident (scatter maps, SpMV of the CG solver)
     double *d_a = nullptr, *d_rhs = nullptr;
@@ -893,6 +894,7 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
     if (missing)
         return fail(ctx, B200ASM_EPATTERN, "scatter map: " + std::to_string(missing) +
                                                " element entries have no position in the CSR pattern");
+    ctx->maps_valid = true;
     return 0;
 }
 
@@ -960,7 +962,7 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
     if (!strcmp(name, "engine")) {
         if (value != 0 && value != 1) return fail(ctx, B200ASM_EINVAL, "engine: 0 (register tiles) or 1 (DMMA where available)");
         ctx->engine = (int)value;
-        ctx->have_pattern = false;  // the scatter-map layout depends on the kernel
+        ctx->maps_valid = false;  // the scatter-map layout depends on the kernel
         return 0;
     }
     if (!strcmp(name, "timing")) {
@@ -1083,7 +1085,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     }
     CK(cudaStreamSynchronize(ctx->stream));  // dest32 / dng are stack-owned
     ctx->groups.push_back(g);
-    ctx->have_pattern = false;  // scatter maps must be rebuilt
+    ctx->maps_valid = false;  // scatter maps are rebuilt (on the resident pattern) by the next assembly
     return (int)ctx->groups.size() - 1;
 }
 
@@ -1098,7 +1100,7 @@ extern "C" int b200asm_clear_groups(b200asm_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Group &g : ctx->groups) free_group(g);
     ctx->groups.clear();
-    ctx->have_pattern = false;
+    ctx->maps_valid = false;
     return 0;
 }
 
@@ -1107,6 +1109,7 @@ void drop_pattern(b200asm_ctx *ctx) {
     cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs);
     ctx->d_ia = nullptr; ctx->d_ja = nullptr; ctx->d_a = ctx->d_rhs = nullptr;
     ctx->have_pattern = false;
+    ctx->maps_valid = false;
 }
 int grid_for(const b200asm_ctx *ctx, int64_t n, int threads) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)ctx->num_sms * 16));
@@ -1135,10 +1138,8 @@ extern "C" int b200asm_set_pattern(b200asm_ctx *ctx, int64_t neq, const int64_t 
     cudaFree(d_ja64);
     CK(cudaMalloc((void **)&ctx->d_a, std::max<int64_t>(nnz, 1) * sizeof(double)));
     CK(cudaMalloc((void **)&ctx->d_rhs, std::max<int64_t>(neq, 1) * sizeof(double)));
-    rc = build_smaps(ctx, ctx->d_ja);
-    if (rc) return rc;
     ctx->have_pattern = true;
-    return 0;
+    return build_smaps(ctx, ctx->d_ja);
 }
 
 extern "C" int b200asm_build_pattern_device(b200asm_ctx *ctx, int symmetric, int64_t nel, const int64_t *elgraphindex,
@@ -1240,10 +1241,8 @@ extern "C" int b200asm_build_pattern_device(b200asm_ctx *ctx, int symmetric, int
     CK(cudaMalloc((void **)&ctx->d_rhs, std::max<int64_t>(neq, 1) * sizeof(double)));
     if (neq_out) *neq_out = neq;
     if (nnz_out) *nnz_out = nnz;
-    rc = build_smaps(ctx, ctx->d_ja);
-    if (rc) return rc;
     ctx->have_pattern = true;
-    return 0;
+    return build_smaps(ctx, ctx->d_ja);
 }
 
 extern "C" int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *ja_host) {
@@ -1271,6 +1270,10 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
     if (!ctx->have_pattern && !ctx->rhs_only) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
     if (!ctx->d_xyz) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_nodes first");
     CK(cudaSetDevice(ctx->device));
+    if (!ctx->rhs_only && !ctx->maps_valid) {  // groups were added / the kernel family changed after the pattern was set
+        const int rc = build_smaps(ctx, ctx->d_ja);
+        if (rc) return rc;
+    }
     // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75
     if (!ctx->rhs_only) CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));

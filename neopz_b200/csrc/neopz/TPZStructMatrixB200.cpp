@@ -532,3 +532,65 @@ template class TPZRestoreClass<TPZStructMatrixB200<STATE>>;
 #include "TPZSpStructMatrix.cpp"
 template class TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>;
 template class TPZSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>;
+
+// ---- Create() on the device ------------------------------------------------------------------------------------
+template <class TVar>
+void TPZStructMatrixB200<TVar>::CreatePatternOnDevice(bool symmetric, TPZStack<int64_t> &elgraph, TPZVec<int64_t> &elgraphindex,
+                                                      TPZVec<int64_t> &ia, TPZVec<int64_t> &ja) {
+    auto *strmat = dynamic_cast<TPZStructMatrix *>(this);
+    if (!strmat) Fatal("the strategy must be combined with a TPZStructMatrix");
+    if (strmat->EquationFilter().IsActive()) Fatal("an active equation filter is not supported yet");
+    TPZCompMesh *cmesh = strmat->Mesh();
+    TPZB200AssemblyCache &c = *fCache;
+    if (!c.ctx) {
+        if (b200asm_create(&c.ctx, fDevice) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
+    }
+    auto t0 = clk::now();
+    // block table: TPZBlock::Position / Size per sequence number of the independent connects
+    // (External/TPZRenumbering.cpp:76-110 works on NIndependentConnects() blocks)
+    const int64_t nblock = cmesh->NIndependentConnects();
+    std::vector<int64_t> bpos(nblock), bsize(nblock);
+    for (int64_t b = 0; b < nblock; b++) {
+        bpos[b] = cmesh->Block().Position(b);
+        bsize[b] = cmesh->Block().Size(b);
+    }
+    const int64_t nel = elgraphindex.size() - 1;
+    int64_t neq = 0, nnz = 0;
+    Check(c, b200asm_build_pattern_device(c.ctx, symmetric ? 1 : 0, nel, &elgraphindex[0], nel && elgraph.size() ? &elgraph[0] : nullptr,
+                                          nblock, bpos.data(), bsize.data(), &neq, &nnz),
+          "b200asm_build_pattern_device");
+    if (neq != cmesh->NEquations()) Fatal("device pattern: unexpected number of equations");
+    ia.resize(neq + 1);
+    ja.resize(nnz);
+    Check(c, b200asm_get_pattern(c.ctx, &ia[0], nnz ? &ja[0] : nullptr), "b200asm_get_pattern");
+    c.pattern_set = true;  // the next Assemble() finds its pattern resident (same nnz / storage kind)
+    c.symmetric = symmetric ? 1 : 0;
+    c.nnz = nnz;
+    c.pattern_ms = ms_since(t0);
+}
+
+template <class TVar>
+TPZMatrix<TVar> *TPZSSpStructMatrixB200<TVar>::SetupMatrixData(TPZStack<int64_t> &elgraph, TPZVec<int64_t> &elgraphindex) {
+    const int64_t neq = this->fEquationFilter.NActiveEquations();
+    auto *mat = new TPZSYsmpMatrix<TVar>(neq, neq);
+    // written in place through the public accessors (Matrix/pzsysmp.h:114-127): no second copy of the pattern
+    this->CreatePatternOnDevice(true, elgraph, elgraphindex, mat->IA(), mat->JA());
+    mat->A().Resize(mat->JA().size());
+    mat->A().Fill(0.);
+    mat->ComputeDiagonal();  // what SetData does after storing the arrays (Matrix/pzsysmp.h:233-240)
+    return mat;
+}
+
+template <class TVar>
+TPZMatrix<TVar> *TPZSpStructMatrixB200<TVar>::SetupMatrixData(TPZStack<int64_t> &elgraph, TPZVec<int64_t> &elgraphindex) {
+    const int64_t neq = this->fEquationFilter.NActiveEquations();
+    auto *mat = new TPZFYsmpMatrix<TVar>(neq, neq);
+    TPZVec<int64_t> ia, ja;
+    this->CreatePatternOnDevice(false, elgraph, elgraphindex, ia, ja);
+    TPZVec<TVar> a(ja.size(), 0.);
+    mat->SetData(ia, ja, a);
+    return mat;
+}
+
+template class TPZSSpStructMatrixB200<STATE>;
+template class TPZSpStructMatrixB200<STATE>;

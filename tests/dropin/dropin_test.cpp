@@ -175,17 +175,21 @@ int main(int argc, char **argv) {
     const int n = atoi(argv[1]), p = atoi(argv[2]), phys = atoi(argv[3]), tet = atoi(argv[4]), symmetric = atoi(argv[5]);
     const int solve = argc > 6 ? atoi(argv[6]) : 1;
     const int threads = argc > 7 ? atoi(argv[7]) : (int)std::thread::hardware_concurrency();
+    // 1: TPZSSpStructMatrixB200 / TPZSpStructMatrixB200, whose Create() builds the CSR pattern on the GPU
+    const int device_create = argc > 8 ? atoi(argv[8]) : 0;
     TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3);
     Csr ref, refmt, gpu;
     double t1, t2, tm1, tm2, g1, g2;
     if (symmetric) {
         Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, 0, true, solve, ref, t1, t2);
         Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, true, false, refmt, tm1, tm2);
-        Run<TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, true, solve, gpu, g1, g2);
+        if (device_create) Run<TPZSSpStructMatrixB200<STATE>>(cmesh, 0, true, solve, gpu, g1, g2);
+        else Run<TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, true, solve, gpu, g1, g2);
     } else {
         Run<TPZSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, 0, false, false, ref, t1, t2);
         Run<TPZSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, false, false, refmt, tm1, tm2);
-        Run<TPZSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, false, false, gpu, g1, g2);
+        if (device_create) Run<TPZSpStructMatrixB200<STATE>>(cmesh, 0, false, false, gpu, g1, g2);
+        else Run<TPZSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, false, false, gpu, g1, g2);
     }
     const bool same_ia = ref.ia.size() == gpu.ia.size() && !memcmp(ref.ia.data(), gpu.ia.data(), ref.ia.size() * 8);
     const bool same_ja = ref.ja.size() == gpu.ja.size() && !memcmp(ref.ja.data(), gpu.ja.data(), ref.ja.size() * 8);
@@ -219,7 +223,7 @@ int main(int argc, char **argv) {
     const int64_t nvol = (int64_t)n * n * n * (tet ? 5 : 1);
     const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
-    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric
+    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"cpu_first_assemble_s\": " << t1
               << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
               << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
               << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel

@@ -19,11 +19,15 @@ CASES = [(6, 1, 0, 0, 1, 1), (5, 2, 0, 0, 1, 1), (4, 2, 1, 0, 1, 1), (4, 2, 0, 1
          (4, 3, 0, 0, 1, 1), (3, 4, 0, 0, 1, 1), (3, 3, 1, 0, 1, 0), (3, 4, 0, 0, 0, 0)]
 
 
+@pytest.mark.parametrize("device_create", [0, 1])
 @pytest.mark.parametrize("case", CASES)
-def test_dropin_strategy_matches_reference(case):
+def test_dropin_strategy_matches_reference(case, device_create):
+    """device_create = 1: TPZSSpStructMatrixB200 / TPZSpStructMatrixB200 — Create() builds the pattern on the GPU (N1)."""
     if not os.path.exists(BIN):
         pytest.skip("tests/_bin/dropin_test not built (needs /root/reference at build time)")
-    out = subprocess.run([BIN] + [str(x) for x in case] + ["4"], capture_output=True, text=True, timeout=600)
+    if device_create and case not in CASES[1::2]:
+        pytest.skip("device-side Create() is exercised on every other case")
+    out = subprocess.run([BIN] + [str(x) for x in case] + ["4", str(device_create)], capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert lines, out.stdout[-2000:] + out.stderr[-2000:]
     r = json.loads(lines[-1])
