@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=0, help="grid size of the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--engine", type=int, default=1, help="0: register-tile DFMA kernels, 1: DMMA panel kernels where available")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
+    ap.add_argument("--debug", type=int, default=0, help="profiling aid: 1 = drop the matrix scatter (wrong results, timing only)")
+    ap.add_argument("--variant", type=int, default=0, help="tuning alternative of the DMMA kernels (0 = default)")
     ap.add_argument("--pattern", default="device", choices=["device", "host"],
                     help="one-off setup: CSR pattern built on the GPU (b200asm_build_pattern_device) or by the threaded host builder")
     ap.add_argument("--cg", type=int, default=0, help="also time N iterations of the device-resident CG (reported as extra keys)")
@@ -223,9 +225,11 @@ def main():
         mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
         mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
     sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter) if world > 1 else None
-    strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter)
+    strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter, variant=a.variant)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
+    if a.debug:
+        strmat.ctx.set_option("debug", a.debug)
     t0 = time.time()
     if sharded:
         ia, ja = sharded.Create()

@@ -58,6 +58,7 @@ struct VolParams {
     int atomic;  // 1: red.global.add.f64; 0: plain read-modify-write (the launch covers one colour: no two
                  // elements of it share an equation, so no two threads touch the same entry)
     int rhs_only;  // 1: load vector only (TPZStrMatParInterface::Assemble(rhs)): no Gram products, no matrix scatter
+    int debug;     // profiling aid (option "debug"): bit 0 = skip the matrix scatter (results are then WRONG)
     double coef[16];
 };
 
@@ -80,8 +81,28 @@ struct VolCfg {
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 // scatter-add of one entry: atomic, or plain when the launch is conflict-free by colouring
 __device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) {
-    if (atomic) atomicAdd(addr, v);
-    else *addr += v;
+    if (atomic == 1) atomicAdd(addr, v);
+    else if (atomic == 0) *addr += v;
+    // atomic == 2: profiling aid, the value is dropped (keeps the arithmetic, removes the memory traffic)
+    else if (v == 1.2345e300) *addr = v;
+}
+
+// predicated reduction: no branch around the red (a divergent `if (pos >= 0) atomicAdd` costs BSSY/BRA/BSYNC per entry)
+__device__ __forceinline__ void red_if_valid(double *a, int32_t pos, double v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\t@p red.global.add.f64 [%0], %2;\n\t}" ::"l"(a + pos), "r"(pos), "d"(v) : "memory");
+}
+// scatter-add of N register values through their precomputed CSR positions (-1 = no slot); the (uniform) scatter mode is
+// tested once, not per entry
+template <int N>
+__device__ __forceinline__ void scatter_many(double *a, const int32_t (&pos)[N], const double (&val)[N], int atomic) {
+    if (atomic == 1) {
+#pragma unroll
+        for (int k = 0; k < N; k++) red_if_valid(a, pos[k], val[k]);
+    } else if (atomic == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (pos[k] >= 0) a[pos[k]] += val[k];
+    }
 }
 
 #include "gram_mma.cuh"
@@ -626,6 +647,8 @@ struct b200asm_ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     int scatter = B200ASM_SCATTER_ATOMIC;
     int engine = 1;  // 1: DMMA panel kernel where one exists, 0: register-tile DFMA kernels only
+    int debug = 0;     // profiling aid, see VolParams::debug
+    int variant = 0;   // tuning alternative of the DMMA kernels (option "variant", before add_group)
     int rhs_only = 0;  // set while b200asm_assemble_rhs runs
     int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
     std::string err;
@@ -714,8 +737,12 @@ constexpr int kNumVol = sizeof(kVol) / sizeof(kVol[0]);
 // DMMA panel kernels (gram_mma.cuh):  NN  N  warps/CTA  min CTAs/SM
 using HexP2PoissonMma = MmaCfg<8, 27, 8, 2>;
 using TetP2PoissonMma = MmaCfg<4, 10, 8, 2>;
+using HexP2PoissonMmaV1 = MmaCfg<8, 27, 8, 3>;
+using HexP2PoissonMmaV2 = MmaCfg<8, 27, 4, 5>;
+using HexP2PoissonMmaV3 = MmaCfg<8, 27, 4, 6>;
 
 struct MmaEntry {
+    int variant;  // 0 = default; others are tuning alternatives selected with option "variant"
     int topology, porder, ns;
     int slots, nthreads, wpc;
     size_t (*smem)(int nq);
@@ -742,13 +769,15 @@ cudaError_t prepare_mma(size_t smem, int *ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_gram_mma_kernel<C>, C::WPC * 32, smem);
 }
 template <class C>
-MmaEntry make_mma_entry(int topology, int porder) {
-    return MmaEntry{topology, porder, 1, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_mma<C>, &launch_mma_smap<C>, &prepare_mma<C>};
+MmaEntry make_mma_entry(int topology, int porder, int variant = 0) {
+    return MmaEntry{variant, topology, porder, 1, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_mma<C>, &launch_mma_smap<C>, &prepare_mma<C>};
 }
 // team kernels (gram_mma_team.cuh):   NN  N  NS  warps/element  elements/CTA  min CTAs/SM
-using HexP2ElastTeam = TeamCfg<8, 27, 3, 5, 1, 2>;
+using HexP2ElastTeam = TeamCfg<8, 27, 3, 10, 1, 2>;   // one tile group (9 tiles) per warp: 96 registers, 20 warps/SM
 using TetP2ElastTeam = TeamCfg<4, 10, 3, 3, 2, 2>;
 using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
+using HexP2ElastTeamV1 = TeamCfg<8, 27, 3, 5, 1, 2>;   // two tile groups per warp (154 registers, 10 warps/SM)
+using HexP2ElastTeamV2 = TeamCfg<8, 27, 3, 10, 1, 3>;
 // higher-order Poisson: one warp per 4x4 superblock of 8x8 tiles (p=3: 8x8 tiles -> 3 warps; p=4: 16x16 -> 10 warps)
 using HexP3PoissonTeam = TeamCfg<8, 64, 1, 3, 2, 3, 4>;
 using HexP4PoissonTeam = TeamCfg<8, 125, 1, 10, 1, 2, 4>;
@@ -771,13 +800,16 @@ cudaError_t prepare_team(size_t smem, int *ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_gram_team_kernel<C>, C::NTHREADS, smem);
 }
 template <class C>
-MmaEntry make_team_entry(int topology, int porder) {
-    return MmaEntry{topology, porder, C::NS, C::SLOTS, C::NTHREADS, C::EPC, &C::smem_bytes, &launch_team<C>, &launch_team_smap<C>, &prepare_team<C>};
+MmaEntry make_team_entry(int topology, int porder, int variant = 0) {
+    return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, C::NTHREADS, C::EPC, &C::smem_bytes, &launch_team<C>, &launch_team_smap<C>, &prepare_team<C>};
 }
 // wpc = elements processed concurrently by one CTA
 const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2),
                          make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
-                         make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4)};
+                         make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
+                         make_mma_entry<HexP2PoissonMmaV1>(B200ASM_HEX, 2, 1), make_mma_entry<HexP2PoissonMmaV2>(B200ASM_HEX, 2, 2),
+                         make_mma_entry<HexP2PoissonMmaV3>(B200ASM_HEX, 2, 3),
+                         make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2)};
 // (tetrahedra p=2 elasticity stays on the register-tile kernel: 130 M el/s vs 99 M el/s for TetP2ElastTeam on a 40^3x5
 //  mesh — padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
@@ -965,6 +997,14 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
         ctx->maps_valid = false;  // the scatter-map layout depends on the kernel
         return 0;
     }
+    if (!strcmp(name, "debug")) {
+        ctx->debug = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "variant")) {
+        ctx->variant = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "timing")) {
         ctx->timing = value ? 1 : 0;
         return 0;
@@ -1012,7 +1052,9 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             if (kVol[k].topology == g.topology && kVol[k].porder == g.porder && kVol[k].ns == g.ns) g.cfg = k;
         if (g.cfg < 0) return fail(ctx, B200ASM_EINVAL, "add_group: no kernel for this configuration");
         for (int k = 0; k < kNumMma; k++)
-            if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns) g.mma = k;
+            if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns &&
+                (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
+                g.mma = k;
     } else if (gi->kind != B200ASM_BC) {
         return fail(ctx, B200ASM_EINVAL, "add_group: face elements need kind BC");
     }
@@ -1317,7 +1359,7 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             const int64_t e0 = g.seg[c], n = g.seg[c + 1] - g.seg[c];
             if (n == 0) continue;
             VolParams p;
-            p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
+            p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = (ctx->debug & 1) ? 2 : atomic; p.rhs_only = ctx->rhs_only; p.debug = ctx->debug;
             p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
             p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
             p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;

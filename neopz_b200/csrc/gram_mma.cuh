@@ -174,18 +174,17 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
         // ---- scatter-add of the upper triangle ---------------------------------------------------
         if (p.rhs_only) continue;
         const double s = p.coef[0];
-        const int32_t *smT = p.smapT ? p.smapT + (size_t)el * C::SLOTS + lane : nullptr;
-        if (smT) {
+        double val[NTILES * 2];
+#pragma unroll
+        for (int k = 0; k < NTILES * 2; k++) val[k] = s * acc[k >> 1][k & 1];
+        if (p.smapT) {
+            const int32_t *smT = p.smapT + (size_t)el * C::SLOTS + lane;
             int32_t posT[NTILES * 2];
 #pragma unroll
             for (int k = 0; k < NTILES * 2; k++) posT[k] = __ldcs(smT + k * 32);
-#pragma unroll
-            for (int k = 0; k < NTILES * 2; k++)
-                if (posT[k] >= 0) scatter_add(p.a + posT[k], s * acc[k >> 1][k & 1], p.atomic);
+            scatter_many<NTILES * 2>(p.a, posT, val, p.atomic);
         }
-#pragma unroll
-        for (int k = 0; k < NTILES * 2; k++)
-            if (pos[k] >= 0) scatter_add(p.a + pos[k], s * acc[k >> 1][k & 1], p.atomic);
+        scatter_many<NTILES * 2>(p.a, pos, val, p.atomic);
     }
 }
 

@@ -32,7 +32,7 @@ struct TeamCfg {
     static constexpr int TPG = SB > 0 ? SB * SB : (NS == 1 ? 1 : 9);  // tiles per group
     static constexpr int GPW = (NGROUPS + WPE - 1) / WPE;  // groups per warp
     static_assert(SB == 0 || (NS == 1 && NBN % (SB > 0 ? SB : 1) == 0 && NGROUPS == WPE), "superblocks: Poisson, SB | NBN, one per warp");
-    static constexpr int JS = 10;
+    static constexpr int JS = 11;                        // sqrt(w|detJ|)*jacinv (9), w|detJ|, sqrt(w|detJ|)
     static constexpr int XSP = NN * 3 + ((NN * 3) & 1);
     static constexpr int TEAM_THREADS = WPE * 32;
     static constexpr int NTHREADS = EPC * TEAM_THREADS;
@@ -40,7 +40,7 @@ struct TeamCfg {
     static constexpr int FPT = (M + TEAM_THREADS - 1) / TEAM_THREADS;  // load-vector items per thread
     static constexpr int SLOTS = WPE * GPW * TPG * 2 * 32;             // scatter-map entries per element
     __host__ __device__ static int qstride(int nq) { return ((nq + 31) / 32) * 32; }
-    __host__ __device__ static int team_doubles(int nq) { int n = XSP + qstride(nq) * JS + KC * LD; return n + (n & 1); }
+    __host__ __device__ static int team_doubles(int nq) { int n = XSP + qstride(nq) * JS + 2 * KC * LD; return n + (n & 1); }  // panel double-buffered
     static size_t smem_bytes(int nq) { return sizeof(double) * (size_t)EPC * team_doubles(nq); }
     // group index -> (ib, jb), row-major over the upper triangle
     __host__ __device__ static constexpr int group_ib(int gidx) {
@@ -123,46 +123,59 @@ __device__ __forceinline__ void team_epilogue(const VolParams &p, int64_t el, do
     for (int gl = 0; gl < C::GPW; gl++) {
         const int gidx = W + gl * C::WPE;
         if (gidx < C::NGROUPS) {
-            // positions of the whole group first: the atomics below would serialise the loads
-            int32_t pos[TPG * 2];
-#pragma unroll
-            for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(sm + (gl * TPG * 2 + k) * 32);
-            double val[TPG * 2];
             if (C::SB > 0) {
+                // superblock: 8 entries at a time (positions first: the atomics would serialise the loads)
+                constexpr int B = 8;
 #pragma unroll
-                for (int k = 0; k < TPG * 2; k++) val[k] = p.coef[0] * acc[gl * TPG + (k >> 1)][k & 1];
-            } else if (C::NS == 1) {
-                val[0] = p.coef[0] * acc[gl][0];
-                val[1] = p.coef[0] * acc[gl][1];
-            } else {
-                const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
+                for (int k0 = 0; k0 < TPG * 2; k0 += B) {
+                    int32_t pos[B];
+                    double val[B];
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    double S[3][3];
+                    for (int k = 0; k < B; k++) pos[k] = __ldcs(sm + (gl * TPG * 2 + k0 + k) * 32);
 #pragma unroll
-                    for (int v = 0; v < 3; v++)
+                    for (int k = 0; k < B; k++) val[k] = p.coef[0] * acc[gl * TPG + ((k0 + k) >> 1)][(k0 + k) & 1];
+                    scatter_many<B>(p.a, pos, val, p.atomic);
+                    if (smT) {
 #pragma unroll
-                        for (int u = 0; u < 3; u++) S[v][u] = acc[gl * 9 + v * 3 + u][e];
-#pragma unroll
-                    for (int a = 0; a < 3; a++)
-#pragma unroll
-                        for (int b = 0; b < 3; b++) {
-                            double x;
-                            if (a == b) x = (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3;
-                            else x = S[b][a] * C1 - S[a][b] * C2;
-                            val[(a * 3 + b) * 2 + e] = x;
-                        }
+                        for (int k = 0; k < B; k++) pos[k] = __ldcs(smT + (gl * TPG * 2 + k0 + k) * 32);
+                        scatter_many<B>(p.a, pos, val, p.atomic);
+                    }
                 }
-            }
+            } else {
+                // positions of the whole group first: the atomics below would serialise the loads
+                int32_t pos[TPG * 2];
 #pragma unroll
-            for (int k = 0; k < TPG * 2; k++)
-                if (pos[k] >= 0) scatter_add(p.a + pos[k], val[k], p.atomic);
-            if (smT) {
+                for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(sm + (gl * TPG * 2 + k) * 32);
+                double val[TPG * 2];
+                if (C::NS == 1) {
+                    val[0] = p.coef[0] * acc[gl][0];
+                    val[1] = p.coef[0] * acc[gl][1];
+                } else {
+                    const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
 #pragma unroll
-                for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(smT + (gl * TPG * 2 + k) * 32);
+                    for (int e = 0; e < 2; e++) {
+                        double S[3][3];
 #pragma unroll
-                for (int k = 0; k < TPG * 2; k++)
-                    if (pos[k] >= 0) scatter_add(p.a + pos[k], val[k], p.atomic);
+                        for (int v = 0; v < 3; v++)
+#pragma unroll
+                            for (int u = 0; u < 3; u++) S[v][u] = acc[gl * 9 + v * 3 + u][e];
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++) {
+                                double x;
+                                if (a == b) x = (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3;
+                                else x = S[b][a] * C1 - S[a][b] * C2;
+                                val[(a * 3 + b) * 2 + e] = x;
+                            }
+                    }
+                }
+                scatter_many<TPG * 2>(p.a, pos, val, p.atomic);
+                if (smT) {
+#pragma unroll
+                    for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(smT + (gl * TPG * 2 + k) * 32);
+                    scatter_many<TPG * 2>(p.a, pos, val, p.atomic);
+                }
             }
         }
     }
@@ -198,10 +211,12 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
     double *Xs = smem + (size_t)team * C::team_doubles(nq);
     double *JI = Xs + C::XSP;
     double *Pn = JI + QS * JS;
-    for (int i = tt; i < KC * LD; i += TT) Pn[i] = 0.0;  // padding columns stay zero
+    for (int i = tt; i < 2 * KC * LD; i += TT) Pn[i] = 0.0;  // padding columns stay zero (both panel buffers)
     team_sync<TT>(team);
     const int g = lane >> 2, tg = lane & 3;
     const int64_t nteams = (int64_t)gridDim.x * C::EPC;
+    // the load vector needs the panel point by point only for a forcing-function table or a non-zero prestress
+    const bool pointwise = p.force != nullptr || (NS == 3 && (p.coef[6] != 0.0 || p.coef[7] != 0.0 || p.coef[8] != 0.0));
 
     for (int64_t el = (int64_t)blockIdx.x * C::EPC + team; el < p.nel; el += nteams) {
         if (tt < NN) {
@@ -249,6 +264,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
             o[7 * QS] = (j01 * j20 - j00 * j21) * sid;
             o[8 * QS] = (-j01 * j10 + j00 * j11) * sid;
             o[9 * QS] = wq;
+            o[10 * QS] = sqrt(wq);
         }
         team_sync<TT>(team);
 
@@ -258,9 +274,23 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
         double facc[FPT];
 #pragma unroll
         for (int k = 0; k < FPT; k++) facc[k] = 0.0;
+        // ---- load vector with a constant force: ef(ns*j+k) = f_k * sum_q w_q phi_j(q)  (TPZMatPoisson.cpp:39-40,
+        // TPZElasticity3D.cpp:278) — one pass over the points per dof, outside the panel loop
+        if (!p.force) {
+#pragma unroll
+            for (int k = 0; k < FPT; k++) {
+                const int m = tt + k * TT;
+                if (m < M) {
+                    const int j = NS == 1 ? m : m / 3;
+                    double t = 0.0;
+                    for (int q = 0; q < nq; q++) t += JI[9 * QS + q] * __ldg(p.phi_pad + (size_t)q * NP + j);
+                    facc[k] = NS == 1 ? p.coef[0] * p.coef[1] * t : p.coef[3 + (m - 3 * j)] * t;
+                }
+            }
+        }
 
-        for (int q0 = 0; q0 < nq; q0 += QC) {
-            // ---- phase 2: panel rows of QC points; items (point, shape) over the team ---------------
+        // ---- phase 2: panel rows of QC points into one of the two panel buffers; items (point, shape) over the team
+        auto build_panel = [&](int q0, double *Pb) {
             for (int it = tt; it < QC * N; it += TT) {
                 const int ql = it / N, i = it - ql * N;
                 const int q = q0 + ql;
@@ -274,37 +304,47 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
                     g2 = ji[2 * QS] * d0 + ji[5 * QS] * d1 + ji[8 * QS] * d2;
                 }
                 if (NS == 1) {
-                    double *row = Pn + (3 * ql) * LD + i;
+                    double *row = Pb + (3 * ql) * LD + i;
                     row[0] = g0;
                     row[LD] = g1;
                     row[2 * LD] = g2;
                 } else {
-                    double *row = Pn + ql * LD + i;  // component-major columns
+                    double *row = Pb + ql * LD + i;  // component-major columns
                     row[0] = g0;
                     row[NPAD] = g1;
                     row[2 * NPAD] = g2;
                 }
             }
-            team_sync<TT>(team);
+        };
+        // software pipeline over the chunks: the panel of chunk c+1 is built (other buffer) by the same warps that then
+        // run the DMMAs of chunk c, so the table loads / FMAs of the build overlap the tensor-pipe work and only ONE
+        // team barrier per chunk remains
+        build_panel(0, Pn);
+        team_sync<TT>(team);
+        int buf = 0;
+        for (int q0 = 0; q0 < nq; q0 += QC, buf ^= 1) {
+            const double *Pc = Pn + buf * (KC * LD);
+            if (q0 + QC < nq) build_panel(q0 + QC, Pn + (buf ^ 1) * (KC * LD));
             // ---- phase 3: Gram update by every warp for its tile groups --------------------------------
-            if (!p.rhs_only) TeamRole<C, 0>::mma(w, Pn, acc, g, tg);
-            // ---- load vector of the chunk's points ------------------------------------------------------
+            if (!p.rhs_only) TeamRole<C, 0>::mma(w, Pc, acc, g, tg);
+            // ---- load vector, point-wise part (forcing-function table and/or prestress only) ------------------
+            if (pointwise) {
 #pragma unroll
-            for (int k = 0; k < FPT; k++) {
-                const int m = tt + k * TT;
-                if (m < M) {
-                    for (int ql = 0; ql < QC; ql++) {
-                        const int q = q0 + ql;
-                        if (q >= nq) break;
-                        const double wq = JI[9 * QS + q];
-                        if (NS == 1) {
-                            const double f = p.force ? p.force[el * nq + q] : p.coef[1];
-                            facc[k] += wq * p.coef[0] * __ldg(p.phi_pad + (size_t)q * NP + m) * f;
-                        } else {
-                            const int j = m / 3, kd = m - 3 * j;
-                            const double f = p.force ? p.force[(el * nq + q) * 3 + kd] : p.coef[3 + kd];
-                            // w*dphix(kd,j) = sqrt(w) * panel entry
-                            facc[k] += wq * f * __ldg(p.phi_pad + (size_t)q * NP + j) - p.coef[6 + kd] * sqrt(wq) * Pn[ql * LD + kd * NPAD + j];
+                for (int k = 0; k < FPT; k++) {
+                    const int m = tt + k * TT;
+                    if (m < M) {
+                        for (int ql = 0; ql < QC; ql++) {
+                            const int q = q0 + ql;
+                            if (q >= nq) break;
+                            const double wq = JI[9 * QS + q];
+                            if (NS == 1) {
+                                facc[k] += wq * p.coef[0] * __ldg(p.phi_pad + (size_t)q * NP + m) * p.force[el * nq + q];
+                            } else {
+                                const int j = m / 3, kd = m - 3 * j;
+                                if (p.force) facc[k] += wq * p.force[(el * nq + q) * 3 + kd] * __ldg(p.phi_pad + (size_t)q * NP + j);
+                                // w*dphix(kd,j) = sqrt(w) * panel entry   (TPZElasticity3D.cpp:278)
+                                facc[k] -= p.coef[6 + kd] * JI[10 * QS + q] * Pc[ql * LD + kd * NPAD + j];
+                            }
                         }
                     }
                 }

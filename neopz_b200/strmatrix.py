@@ -137,7 +137,7 @@ class TPZStructMatrixB200:
     """TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>> (symmetric=True) or
     TPZSpStructMatrix<...> (symmetric=False) on a flattened mesh."""
 
-    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0, engine=None, scatter=None):
+    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0, engine=None, scatter=None, variant=None):
         self.mesh = mesh
         self.materials = {m.id: m for m in (materials.values() if isinstance(materials, dict) else materials)}
         self.symmetric = bool(symmetric)
@@ -145,6 +145,8 @@ class TPZStructMatrixB200:
         self.ctx = capi.Context(device)
         if engine is not None:  # 0: register-tile DFMA kernels only, 1 (default): DMMA panel kernels where available
             self.ctx.set_option("engine", engine)
+        if variant:  # tuning alternative of the DMMA kernels (0 = default)
+            self.ctx.set_option("variant", variant)
         if scatter is not None:  # "atomic" (default) or "colored" (conflict-free element colouring, deterministic)
             self.ctx.set_option("scatter", {"atomic": 0, "colored": 1}[scatter])
         self.ia = self.ja = None

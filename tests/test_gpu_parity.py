@@ -165,6 +165,20 @@ def test_rhs_only_assembly(n, p, phys, tet, engine):
     assert np.array_equal(a_after, a)                  # matrix untouched by the rhs-only pass
 
 
+@pytest.mark.parametrize("n,p,tet,engine", [(3, 2, 0, 1), (4, 1, 0, 1), (3, 2, 1, 0), (2, 3, 0, 0)])
+def test_elasticity_prestress_load_vector(n, p, tet, engine):
+    """ef(3j+k) += w (f_k phi_j - prestress_k dphix(k,j))  (TPZElasticity3D.cpp:278) with a non-zero prestress: the
+    point-wise branch of the load vector in every kernel family."""
+    mesh = gridmesh.grid_mesh(n, p, 3, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    m = sm.TPZElasticity3D(1, gu.E_MOD, gu.NU, (0.3, -0.2, -1.0), prestress=(1.5, -0.75, 2.25))
+    mats = {1: m, -1: m.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3)), -2: m.CreateBC(-2, 1, np.zeros((3, 3)), gu.NEUMANN_ELAST)}
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, engine=engine)
+    ia, ja, a, rhs = strmat.CreateAssemble()
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+    assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+
+
 def _shuffled(n, seed):
     """Random renumbering of the (n+1)^3 grid nodes: every element gets its own side orientations (p >= 3)."""
     return np.random.default_rng(seed).permutation((n + 1) ** 3)
