@@ -775,6 +775,7 @@ MmaEntry make_mma_entry(int topology, int porder, int variant = 0) {
 // team kernels (gram_mma_team.cuh):   NN  N  NS  warps/element  elements/CTA  min CTAs/SM
 using HexP2ElastTeam = TeamCfg<8, 27, 3, 10, 1, 2>;   // one tile group (9 tiles) per warp: 96 registers, 20 warps/SM
 using TetP2ElastTeam = TeamCfg<4, 10, 3, 3, 2, 2>;
+using TetP2ElastTeamV2 = TeamCfg<4, 10, 3, 3, 4, 2>;
 using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
 using HexP2ElastTeamV1 = TeamCfg<8, 27, 3, 5, 1, 2>;   // two tile groups per warp (154 registers, 10 warps/SM)
 using HexP2ElastTeamV2 = TeamCfg<8, 27, 3, 10, 1, 3>;
@@ -809,6 +810,7 @@ const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_m
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
                          make_mma_entry<HexP2PoissonMmaV1>(B200ASM_HEX, 2, 1), make_mma_entry<HexP2PoissonMmaV2>(B200ASM_HEX, 2, 2),
                          make_mma_entry<HexP2PoissonMmaV3>(B200ASM_HEX, 2, 3),
+                         make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1), make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 2),
                          make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2)};
 // (tetrahedra p=2 elasticity stays on the register-tile kernel: 130 M el/s vs 99 M el/s for TetP2ElastTeam on a 40^3x5
 //  mesh — padding 10 shape functions to 16 wastes 60 % of every DMMA tile)

@@ -28,11 +28,12 @@ struct MmaCfg {
     static constexpr int NP = ((N + 15) / 16) * 16;  // padded row length of the shape tables (whole 128-byte lines)
     static constexpr int NTILES = NB * (NB + 1) / 2;
     static constexpr int QC = 4, KC = 12;
-    static constexpr int JS = 10;       // sqrt(w|detJ|)*jacinv (9) and w|detJ|
+    static constexpr int JS = 14;       // doubles per point: sqrt(w|detJ|)*jacinv (9), w|detJ|, padding (even stride: 128-bit
+                                        // broadcast loads; 14 -> the stores of a half-warp fall into 2-way conflicts only)
     static constexpr int XSP = NN * 3 + ((NN * 3) & 1);
     static constexpr int SLOTS = NTILES * 2 * 32;  // scatter-map entries per element
     __host__ __device__ static int qstride(int nq) { return ((nq + 31) / 32) * 32; }  // JI is [JS][qstride]
-    __host__ __device__ static int warp_doubles(int nq) { int n = XSP + qstride(nq) * JS + KC * LD; return n + (n & 1); }
+    __host__ __device__ static int warp_doubles(int nq) { int n = XSP + nq * JS + 2 * KC * LD; return n + (n & 1); }  // two panel buffers
     static size_t smem_bytes(int nq) { return sizeof(double) * (size_t)WPC * warp_doubles(nq); }
 };
 
@@ -50,30 +51,37 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
     const int nq = p.nq;
     double *Xs = smem + (size_t)warp * C::warp_doubles(nq);
     double *JI = Xs + C::XSP;
-    const int QS = C::qstride(nq);
-    double *Pn = JI + QS * JS;
-    for (int i = lane; i < KC * LD; i += 32) Pn[i] = 0.0;  // padding columns stay zero
+    double *Pn = JI + nq * JS;
+    for (int i = lane; i < 2 * KC * LD; i += 32) Pn[i] = 0.0;  // padding columns stay zero (both panel buffers)
     __syncwarp();
     const int g = lane >> 2, tg = lane & 3;
     const int64_t nwarps = (int64_t)gridDim.x * C::WPC;
 
     const int64_t el_first = (int64_t)blockIdx.x * C::WPC + warp;
-    int32_t next_node = (lane < NN && el_first < p.nel) ? p.elnodes[el_first * NN + lane] : 0;
+    // software prefetch across elements: corner-node ids two elements ahead, their coordinates one element ahead
+    int32_t next_node = 0;
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    if (lane < NN && el_first < p.nel) {
+        const int64_t node = p.elnodes[el_first * NN + lane];
+        cx = p.xyz[node * 3 + 0]; cy = p.xyz[node * 3 + 1]; cz = p.xyz[node * 3 + 2];
+        if (el_first + nwarps < p.nel) next_node = p.elnodes[(el_first + nwarps) * NN + lane];
+    }
     for (int64_t el = el_first; el < p.nel; el += nwarps) {
-        // the scatter positions of this element are fetched now (HBM latency hidden behind the arithmetic):
-        // the atomics of the epilogue would otherwise serialise these loads
-        int32_t pos[NTILES * 2];
+        // pull this element's scatter positions towards L2 now; they are loaded into registers only after the last
+        // DMMA has been issued (20 registers less during the main loop)
         if (!p.rhs_only) {
-            const int32_t *sm = p.smap + (size_t)el * C::SLOTS + lane;
-#pragma unroll
-            for (int k = 0; k < NTILES * 2; k++) pos[k] = __ldcs(sm + k * 32);
+            const char *base = (const char *)(p.smap + (size_t)el * C::SLOTS);
+            for (int off = lane * 128; off < C::SLOTS * 4; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
         }
         if (lane < NN) {
-            const int64_t node = next_node;
-            Xs[lane * 3 + 0] = p.xyz[node * 3 + 0];
-            Xs[lane * 3 + 1] = p.xyz[node * 3 + 1];
-            Xs[lane * 3 + 2] = p.xyz[node * 3 + 2];
-            if (el + nwarps < p.nel) next_node = p.elnodes[(el + nwarps) * NN + lane];
+            Xs[lane * 3 + 0] = cx;
+            Xs[lane * 3 + 1] = cy;
+            Xs[lane * 3 + 2] = cz;
+            if (el + nwarps < p.nel) {
+                const int64_t node = next_node;
+                cx = p.xyz[node * 3 + 0]; cy = p.xyz[node * 3 + 1]; cz = p.xyz[node * 3 + 2];
+                if (el + 2 * nwarps < p.nel) next_node = p.elnodes[(el + 2 * nwarps) * NN + lane];
+            }
         }
         __syncwarp();
         // ---- phase 1: geometry at the integration points (Geom/TPZGeoCube.h:141-149, Mesh/pzgeoel.cpp:1309-1336)
@@ -99,27 +107,46 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             const double id = 1.0 / det;
             const double w = __ldg(p.qw + q) * fabs(det);  // weight *= fabs(detjac)
             const double sid = sqrt(w) * id;
-            double *o = JI + q;  // field k of point q at JI[k*QS + q]: conflict-free stores, broadcast reads
-            o[0 * QS] = (-j12 * j21 + j11 * j22) * sid;
-            o[1 * QS] = (j02 * j21 - j01 * j22) * sid;
-            o[2 * QS] = (-j02 * j11 + j01 * j12) * sid;
-            o[3 * QS] = (j12 * j20 - j10 * j22) * sid;
-            o[4 * QS] = (-j02 * j20 + j00 * j22) * sid;
-            o[5 * QS] = (j02 * j10 - j00 * j12) * sid;
-            o[6 * QS] = (-j11 * j20 + j10 * j21) * sid;
-            o[7 * QS] = (j01 * j20 - j00 * j21) * sid;
-            o[8 * QS] = (-j01 * j10 + j00 * j11) * sid;
-            o[9 * QS] = w;
+            double *o = JI + q * JS;  // point-major: the nine factors of a point are read back with 128-bit broadcast loads
+            o[0] = (-j12 * j21 + j11 * j22) * sid;
+            o[1] = (j02 * j21 - j01 * j22) * sid;
+            o[2] = (-j02 * j11 + j01 * j12) * sid;
+            o[3] = (j12 * j20 - j10 * j22) * sid;
+            o[4] = (-j02 * j20 + j00 * j22) * sid;
+            o[5] = (j02 * j10 - j00 * j12) * sid;
+            o[6] = (-j11 * j20 + j10 * j21) * sid;
+            o[7] = (j01 * j20 - j00 * j21) * sid;
+            o[8] = (-j01 * j10 + j00 * j11) * sid;
+            o[9] = w;
         }
         __syncwarp();
+
+        // ---- load vector: ef(i) += weight*fScale*phi(i)*force (TPZMatPoisson.cpp:39-40); three independent chains
+        if (lane < N) {
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            for (int q = 0; q < nq; q += 3) {
+                const double a0 = JI[q * JS + 9] * __ldg(p.phi_pad + (size_t)q * NP + lane);
+                const double a1 = q + 1 < nq ? JI[(q + 1) * JS + 9] * __ldg(p.phi_pad + (size_t)(q + 1) * NP + lane) : 0.0;
+                const double a2 = q + 2 < nq ? JI[(q + 2) * JS + 9] * __ldg(p.phi_pad + (size_t)(q + 2) * NP + lane) : 0.0;
+                if (p.force) {
+                    f0 += a0 * p.force[el * nq + q];
+                    if (q + 1 < nq) f1 += a1 * p.force[el * nq + q + 1];
+                    if (q + 2 < nq) f2 += a2 * p.force[el * nq + q + 2];
+                } else {
+                    f0 += a0; f1 += a1; f2 += a2;
+                }
+            }
+            const double f = (f0 + f1 + f2) * p.coef[0] * (p.force ? 1.0 : p.coef[1]);
+            scatter_add(p.rhs + p.dest[el * N + lane], f, p.atomic);
+        }
 
         double acc[NTILES][2];
 #pragma unroll
         for (int t = 0; t < NTILES; t++) acc[t][0] = acc[t][1] = 0.0;
 
-        for (int q0 = 0; q0 < (p.rhs_only ? 0 : nq); q0 += QC) {
-            // ---- phase 2: panel rows of QC points (Mesh/TPZCompElH1.cpp:147): lane <-> shape function,
-            // the table loads of all QC points are issued before the first use
+        // ---- phase 2: panel rows of QC points (Mesh/TPZCompElH1.cpp:147): lane <-> shape function,
+        // the table loads of all QC points are issued before the first use
+        auto build_panel = [&](int q0, double *Pb) {
             for (int i = lane; i < N; i += 32) {
                 double d[QC][3];
 #pragma unroll
@@ -133,23 +160,33 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
 #pragma unroll
                 for (int ql = 0; ql < QC; ql++) {
                     const int q = min(q0 + ql, nq - 1);  // tail rows: d == 0 -> zero rows
-                    const double *ji = JI + q;
-                    const double g0 = ji[0 * QS] * d[ql][0] + ji[3 * QS] * d[ql][1] + ji[6 * QS] * d[ql][2];
-                    const double g1 = ji[1 * QS] * d[ql][0] + ji[4 * QS] * d[ql][1] + ji[7 * QS] * d[ql][2];
-                    const double g2 = ji[2 * QS] * d[ql][0] + ji[5 * QS] * d[ql][1] + ji[8 * QS] * d[ql][2];
-                    double *row = Pn + (3 * ql) * LD + i;
+                    const double2 *ji = reinterpret_cast<const double2 *>(JI + q * JS);  // 5 x LDS.128, same address in all lanes
+                    const double2 j01 = ji[0], j23 = ji[1], j45 = ji[2], j67 = ji[3], j8w = ji[4];
+                    const double g0 = j01.x * d[ql][0] + j23.y * d[ql][1] + j67.x * d[ql][2];
+                    const double g1 = j01.y * d[ql][0] + j45.x * d[ql][1] + j67.y * d[ql][2];
+                    const double g2 = j23.x * d[ql][0] + j45.y * d[ql][1] + j8w.x * d[ql][2];
+                    double *row = Pb + (3 * ql) * LD + i;
                     row[0] = g0;
                     row[LD] = g1;
                     row[2 * LD] = g2;
                 }
             }
-            __syncwarp();
+        };
+        // software pipeline: the panel of chunk c+1 is built into the other buffer before the DMMAs of chunk c are
+        // issued, so its table loads / FMAs run while the tensor pipe drains; one __syncwarp per chunk
+        const int nq_run = p.rhs_only ? 0 : nq;
+        if (nq_run) build_panel(0, Pn);
+        __syncwarp();
+        int buf = 0;
+        for (int q0 = 0; q0 < nq_run; q0 += QC, buf ^= 1) {
+            const double *Pc = Pn + buf * (KC * LD);
+            if (q0 + QC < nq_run) build_panel(q0 + QC, Pn + (buf ^ 1) * (KC * LD));
             // ---- phase 3: Gram update, 3 k-steps of 4 panel rows -----------------------------------
 #pragma unroll
             for (int s = 0; s < KC / 4; s++) {
                 double fr[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) fr[b] = Pn[(4 * s + tg) * LD + 8 * b + g];
+                for (int b = 0; b < NB; b++) fr[b] = Pc[(4 * s + tg) * LD + 8 * b + g];
                 int t = 0;
 #pragma unroll
                 for (int bi = 0; bi < NB; bi++)
@@ -162,29 +199,28 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
             __syncwarp();
         }
 
-        // ---- load vector: ef(i) += weight*fScale*phi(i)*force (TPZMatPoisson.cpp:39-40) -----------
-        if (lane < N) {
-            double f = 0.0;
-            for (int q = 0; q < nq; q++) {
-                const double fq = p.force ? p.force[el * nq + q] : p.coef[1];
-                f += JI[9 * QS + q] * p.coef[0] * __ldg(p.phi_pad + (size_t)q * NP + lane) * fq;
-            }
-            scatter_add(p.rhs + p.dest[el * N + lane], f, p.atomic);
-        }
         // ---- scatter-add of the upper triangle ---------------------------------------------------
         if (p.rhs_only) continue;
+        // positions in batches of HB entries (loads first: the reds would serialise them); values are scaled on the fly
+        constexpr int HB = NTILES;  // two batches
         const double s = p.coef[0];
-        double val[NTILES * 2];
+        const int32_t *sm = p.smap + (size_t)el * C::SLOTS + lane;
+        const int32_t *smT = p.smapT ? p.smapT + (size_t)el * C::SLOTS + lane : nullptr;
 #pragma unroll
-        for (int k = 0; k < NTILES * 2; k++) val[k] = s * acc[k >> 1][k & 1];
-        if (p.smapT) {
-            const int32_t *smT = p.smapT + (size_t)el * C::SLOTS + lane;
-            int32_t posT[NTILES * 2];
+        for (int k0 = 0; k0 < NTILES * 2; k0 += HB) {
+            int32_t pos[HB];
+            double val[HB];
 #pragma unroll
-            for (int k = 0; k < NTILES * 2; k++) posT[k] = __ldcs(smT + k * 32);
-            scatter_many<NTILES * 2>(p.a, posT, val, p.atomic);
+            for (int k = 0; k < HB; k++) pos[k] = __ldcs(sm + (k0 + k) * 32);
+#pragma unroll
+            for (int k = 0; k < HB; k++) val[k] = s * acc[(k0 + k) >> 1][(k0 + k) & 1];
+            scatter_many<HB>(p.a, pos, val, p.atomic);
+            if (smT) {
+#pragma unroll
+                for (int k = 0; k < HB; k++) pos[k] = __ldcs(smT + (k0 + k) * 32);
+                scatter_many<HB>(p.a, pos, val, p.atomic);
+            }
         }
-        scatter_many<NTILES * 2>(p.a, pos, val, p.atomic);
     }
 }
 

@@ -1,5 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -q -x 2>&1 | tail -4
-for v in 0 1 2; do python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --phys elasticity --grid 64 --variant $v | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('elast variant', $v, d['value'], d['ms_per_step'], d['roofline']['frac'])"; done
-for v in 0 2; do python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --variant $v | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('poisson p2 variant', $v, d['value'], d['ms_per_step'], d['roofline']['frac'])"; done
-for p in 3 4; do python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --p $p --grid 32 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('poisson p', $p, d['value'], d['ms_per_step'], d['roofline']['frac'])"; done
-python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --phys elasticity --p 1 --grid 96 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('elast p1', d['value'], d['ms_per_step'], d['roofline']['frac'])"
+python -m pytest tests/test_gpu_parity.py -q -x 2>&1 | tail -3
+for v in 0 1 2 3; do python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --grid 96 --variant $v | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('C2/96 variant', $v, '%.4g'%d['value'], '%.3f'%d['ms_per_step'], '%.3f'%d['roofline']['kernel_ms'])"; done
+python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --topo tet --grid 64 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('tet p2 poisson', d['value'], d['ms_per_step'], d['roofline']['frac'])"
