@@ -178,6 +178,16 @@ def summarize_clocks(samples):
 
 def main():
     a = parse()
+    # stdout carries exactly ONE line (the JSON): anything libraries print there (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -194,7 +204,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": "elements/s", "cores": r["cores"], "kind": r["kind"],
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import numpy as np
@@ -224,7 +234,8 @@ def main():
     else:
         mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
         mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
-    sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter) if world > 1 else None
+    sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter,
+                                              pattern=a.pattern, variant=a.variant) if world > 1 else None
     strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter, variant=a.variant)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
@@ -238,7 +249,7 @@ def main():
     torch.cuda.synchronize()
     t_create = time.time() - t0
     nvol = len(mesh.blocks[0].elnodes)
-    neq, nnz = slab.nown, (len(ja) if ja is not None else strmat.nnz)
+    neq, nnz = slab.nown, (len(ja) if ja is not None else (sharded.nnz if sharded else strmat.nnz))
     step_async = sharded.AssembleDevice if sharded else strmat.ctx.assemble_async
 
     def barrier():
@@ -388,12 +399,12 @@ def main():
                        f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
                        "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
-                                   "pattern_builder": "host (sharded)" if world > 1 else a.pattern}},
+                                   "pattern_builder": a.pattern}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}
     if cg:
         line["device_cg"] = cg
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

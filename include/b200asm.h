@@ -110,6 +110,8 @@ int b200asm_build_pattern_device(b200asm_ctx *ctx, int symmetric, int64_t nel, c
                                  int64_t *neq_out, int64_t *nnz_out);
 /* copies the current pattern to the host as the reference stores it (int64 IA/JA); either pointer may be NULL */
 int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *ja_host);
+/* column indices [first, first+count) of the resident pattern (the row-sharded setup only needs the interface rows) */
+int b200asm_get_ja_range(b200asm_ctx *ctx, int64_t first, int64_t count, int64_t *ja_host);
 
 /* ---- assembly -----------------------------------------------------------------------------
  * Zeroes A and rhs on the device, runs every group (CalcStiff + AddKel + AddFel of

@@ -44,7 +44,7 @@ SYMBOLS = [
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
     "b200asm_nshape", "b200asm_orientation_keys", "b200asm_shape_tables_oriented",
     "b200asm_build_pattern_device", "b200asm_get_pattern", "b200asm_cg_solve", "b200asm_cg_solution_device",
-    "b200asm_assemble_rhs",
+    "b200asm_assemble_rhs", "b200asm_get_ja_range",
 ]
 
 
@@ -84,6 +84,7 @@ def lib():
     L.b200asm_shape_tables.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.b200asm_build_pattern_device.argtypes = [vp, C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64]
     L.b200asm_get_pattern.argtypes = [vp, ip64, ip64]
+    L.b200asm_get_ja_range.argtypes = [vp, C.c_int64, C.c_int64, ip64]
     L.b200asm_cg_solve.argtypes = [vp, C.c_int, C.c_int64, C.c_double, C.c_int, dp, dp, ip64, dp]
     L.b200asm_cg_solution_device.argtypes = [vp, C.POINTER(vp)]
     L.b200asm_nshape.argtypes = [C.c_int, C.c_int]
@@ -281,6 +282,11 @@ class Context:
 
     def assemble(self, a_host=None, rhs_host=None):
         self._check(lib().b200asm_assemble(self._h, dptr(a_host), dptr(rhs_host)))
+
+    def get_ja_range(self, first, count):
+        ja = np.empty(int(count), dtype=np.int64)
+        self._check(lib().b200asm_get_ja_range(self._h, int(first), int(count), i64ptr(ja)))
+        return ja
 
     def assemble_rhs(self, rhs_host=None):
         self._check(lib().b200asm_assemble_rhs(self._h, dptr(rhs_host)))

@@ -737,6 +737,7 @@ constexpr int kNumVol = sizeof(kVol) / sizeof(kVol[0]);
 // DMMA panel kernels (gram_mma.cuh):  NN  N  warps/CTA  min CTAs/SM
 using HexP2PoissonMma = MmaCfg<8, 27, 8, 2>;
 using TetP2PoissonMma = MmaCfg<4, 10, 8, 2>;
+using HexP1PoissonMma = MmaCfg<8, 8, 8, 4>;
 using HexP2PoissonMmaV1 = MmaCfg<8, 27, 8, 3>;
 using HexP2PoissonMmaV2 = MmaCfg<8, 27, 4, 5>;
 using HexP2PoissonMmaV3 = MmaCfg<8, 27, 4, 6>;
@@ -776,6 +777,10 @@ MmaEntry make_mma_entry(int topology, int porder, int variant = 0) {
 using HexP2ElastTeam = TeamCfg<8, 27, 3, 10, 1, 2>;   // one tile group (9 tiles) per warp: 96 registers, 20 warps/SM
 using TetP2ElastTeam = TeamCfg<4, 10, 3, 3, 2, 2>;
 using TetP2ElastTeamV2 = TeamCfg<4, 10, 3, 3, 4, 2>;
+using TetP2ElastTeamV3 = TeamCfg<4, 10, 3, 3, 4, 3>;
+using TetP2ElastTeamV4 = TeamCfg<4, 10, 3, 3, 8, 1>;
+using TetP2ElastTeamV5 = TeamCfg<4, 10, 3, 1, 8, 2>;   // ONE warp per element (27 tiles, 54 accumulators), no barriers
+using TetP2ElastTeamV6 = TeamCfg<4, 10, 3, 3, 5, 2>;
 using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
 using HexP2ElastTeamV1 = TeamCfg<8, 27, 3, 5, 1, 2>;   // two tile groups per warp (154 registers, 10 warps/SM)
 using HexP2ElastTeamV2 = TeamCfg<8, 27, 3, 10, 1, 3>;
@@ -808,12 +813,15 @@ MmaEntry make_team_entry(int topology, int porder, int variant = 0) {
 const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2),
                          make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
+                         make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
                          make_mma_entry<HexP2PoissonMmaV1>(B200ASM_HEX, 2, 1), make_mma_entry<HexP2PoissonMmaV2>(B200ASM_HEX, 2, 2),
                          make_mma_entry<HexP2PoissonMmaV3>(B200ASM_HEX, 2, 3),
-                         make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1), make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 2),
+                         make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 0), make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1),
+                         make_team_entry<TetP2ElastTeamV3>(B200ASM_TET, 2, 3), make_team_entry<TetP2ElastTeamV4>(B200ASM_TET, 2, 4),
+                         make_team_entry<TetP2ElastTeamV5>(B200ASM_TET, 2, 5), make_team_entry<TetP2ElastTeamV6>(B200ASM_TET, 2, 6),
                          make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2)};
-// (tetrahedra p=2 elasticity stays on the register-tile kernel: 130 M el/s vs 99 M el/s for TetP2ElastTeam on a 40^3x5
-//  mesh — padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
+// (tetrahedra p=2 elasticity: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the register-tile
+//  kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
 
 template <int NN, int N, int NS>
@@ -1287,6 +1295,20 @@ extern "C" int b200asm_build_pattern_device(b200asm_ctx *ctx, int symmetric, int
     if (nnz_out) *nnz_out = nnz;
     ctx->have_pattern = true;
     return build_smaps(ctx, ctx->d_ja);
+}
+
+extern "C" int b200asm_get_ja_range(b200asm_ctx *ctx, int64_t first, int64_t count, int64_t *ja_host) {
+    if (!ctx || first < 0 || count < 0 || (count && !ja_host)) return fail(ctx, B200ASM_EINVAL, "get_ja_range: bad arguments");
+    if (!ctx->d_ja) return fail(ctx, B200ASM_ESTATE, "get_ja_range: no pattern on the device");
+    if (first + count > ctx->nnz) return fail(ctx, B200ASM_EINVAL, "get_ja_range: range exceeds nnz");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    int32_t *tmp = reinterpret_cast<int32_t *>(ja_host);
+    CK(cudaMemcpyAsync(tmp, ctx->d_ja + first, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t k = count - 1; k >= 0; k--) ja_host[k] = tmp[k];
+    ctx->d2h += count * (int64_t)sizeof(int32_t);
+    return 0;
 }
 
 extern "C" int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *ja_host) {

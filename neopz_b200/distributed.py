@@ -162,7 +162,9 @@ def build_recv_maps(slab, ia, ja, sender_ext2glob_ghost, sender_ia_ghost, sender
     """Positions, in this rank's local CSR / rhs, of the ghost-row entries the rank above sends.
 
     sender_ext2glob_ghost: global numbers of the sender's ghost equations; sender_ia_ghost[nghost+1];
-    sender_ja_ghost_glob: global column numbers of the sender's ghost-row entries (sender CSR order)."""
+    sender_ja_ghost_glob: global column numbers of the sender's ghost-row entries (sender CSR order).
+    ja: the local column indices, or a callable ja(first, count) that fetches a range of them (the pattern may live
+    on the device only; just the receiving rows are needed)."""
     nghost_s = len(sender_ext2glob_ghost)
     rows_glob = np.repeat(sender_ext2glob_ghost, np.diff(sender_ia_ghost))
     lo, hi = slab.row0, slab.row0 + slab.nown
@@ -183,7 +185,12 @@ def build_recv_maps(slab, ia, ja, sender_ext2glob_ghost, sender_ia_ghost, sender
     seg_len = ia[urows + 1] - ia[urows]
     seg_pos = np.repeat(ia[urows], seg_len) + (np.arange(seg_len.sum()) - np.repeat(np.cumsum(seg_len) - seg_len, seg_len))
     K = np.int64(len(slab.ext2glob) + 1)
-    keys_local = np.repeat(urows, seg_len) * K + ja[seg_pos]
+    if callable(ja):
+        lo_pos, hi_pos = int(ia[urows.min()]), int(ia[urows.max() + 1])
+        ja_seg = ja(lo_pos, hi_pos - lo_pos)[seg_pos - lo_pos]
+    else:
+        ja_seg = ja[seg_pos]
+    keys_local = np.repeat(urows, seg_len) * K + ja_seg
     keys = rows_ext * K + cols_ext
     k = np.searchsorted(keys_local, keys)
     if np.any(k >= len(keys_local)) or np.any(keys_local[np.minimum(k, len(keys_local) - 1)] != keys):
@@ -202,7 +209,9 @@ class ShardedStructMatrix:
     inject the oracle and run the exchange over gloo)."""
 
     def __init__(self, slab: SlabMesh, materials, symmetric=True, device=0, local_assembler=None, nthreads=0, engine=None,
-                 scatter=None):
+                 scatter=None, pattern="host", variant=None):
+        """pattern: "host" (threaded host builder, IA/JA kept on the host) or "device" (b200asm_build_pattern_device: the
+        column indices stay on the GPU, only the interface rows are ever copied back)."""
         import torch.distributed as dist
         self.dist = dist
         self.slab = slab
@@ -213,7 +222,8 @@ class ShardedStructMatrix:
         if local_assembler is None:
             from .strmatrix import TPZStructMatrixB200
             self.strmat = TPZStructMatrixB200(slab.mesh, materials, symmetric=symmetric, device=device, nthreads=nthreads,
-                                              engine=engine, scatter=scatter)
+                                              engine=engine, scatter=scatter, variant=variant)
+        self.pattern = pattern if local_assembler is None else "host"
         self.nthreads = nthreads
         self.ia = self.ja = None
 
@@ -221,10 +231,22 @@ class ShardedStructMatrix:
     def Create(self):
         import torch
         s = self.slab
-        self.ia, self.ja = capi.build_pattern(self.symmetric, s.graph_index, s.graph, s.mesh.block_pos, s.mesh.block_size,
-                                              self.nthreads)
-        if self.strmat is not None:
-            self.strmat.SetPattern(self.ia, self.ja)
+        if self.pattern == "device":
+            st = self.strmat
+            st._flatten()
+            neq, self.nnz = st.ctx.build_pattern_device(self.symmetric, s.graph_index, s.graph, s.mesh.block_pos, s.mesh.block_size)
+            assert neq == s.mesh.neq
+            self.ia, _ = st.ctx.get_pattern(neq, self.nnz, want_ja=False)
+            st.ia, st.ja, st.nnz = self.ia, None, self.nnz
+            self.ja = None
+            ja_fetch = st.ctx.get_ja_range
+        else:
+            self.ia, self.ja = capi.build_pattern(self.symmetric, s.graph_index, s.graph, s.mesh.block_pos, s.mesh.block_size,
+                                                  self.nthreads)
+            self.nnz = len(self.ja)
+            if self.strmat is not None:
+                self.strmat.SetPattern(self.ia, self.ja)
+            ja_fetch = None
         self.nnz_ghost = int(self.ia[s.nghost])
         dist = self.dist
         cuda = self.strmat is not None and dist.get_backend() == "nccl"
@@ -243,7 +265,8 @@ class ShardedStructMatrix:
         reqs = []
         keep = []
         if down >= 0:
-            for arr in (s.ext2glob[:s.nghost], self.ia[:s.nghost + 1], s.ext2glob[self.ja[:self.nnz_ghost]]):
+            ja_ghost = ja_fetch(0, self.nnz_ghost) if ja_fetch else self.ja[:self.nnz_ghost]
+            for arr in (s.ext2glob[:s.nghost], self.ia[:s.nghost + 1], s.ext2glob[ja_ghost]):
                 t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(dev)
                 keep.append(t)
                 reqs.append(dist.isend(t, down))
@@ -257,7 +280,7 @@ class ShardedStructMatrix:
             r.wait()
         if up < s.world:
             g_eq, g_ia, g_ja = [t.cpu().numpy() for t in bufs]
-            self.a_map, self.rhs_map = build_recv_maps(s, self.ia, self.ja, g_eq, g_ia, g_ja)
+            self.a_map, self.rhs_map = build_recv_maps(s, self.ia, ja_fetch if ja_fetch else self.ja, g_eq, g_ia, g_ja)
             self.recv_nnz, self.recv_neq = len(self.a_map), len(self.rhs_map)
             if self.strmat is not None:
                 self.a_map_dev = torch.from_numpy(self.a_map).to(dev)
@@ -266,7 +289,7 @@ class ShardedStructMatrix:
                 self.recv_rhs = torch.empty(self.recv_neq, dtype=torch.float64, device=dev)
         if self.strmat is not None:
             a_ptr, r_ptr = self.strmat.ctx.device_pointers()
-            self.a_view = _device_view(a_ptr, len(self.ja))
+            self.a_view = _device_view(a_ptr, self.nnz)
             self.rhs_view = _device_view(r_ptr, s.mesh.neq)
         return self.ia, self.ja
 
@@ -296,7 +319,7 @@ class ShardedStructMatrix:
         s = self.slab
         if self.strmat is not None:
             self.AssembleDevice()
-            a = np.empty(len(self.ja))
+            a = np.empty(self.nnz)
             rhs = np.empty(s.mesh.neq)
             self.strmat.ctx.download(a, rhs)
             return a, rhs
@@ -323,7 +346,8 @@ class ShardedStructMatrix:
         s = self.slab
         r0, r1 = s.nghost, s.nghost + s.nown
         lo, hi = self.ia[r0], self.ia[r1]
-        return self.ia[r0:r1 + 1] - lo, s.ext2glob[self.ja[lo:hi]], a[lo:hi], rhs[r0:r1]
+        ja = self.ja[lo:hi] if self.ja is not None else self.strmat.ctx.get_ja_range(lo, hi - lo)
+        return self.ia[r0:r1 + 1] - lo, s.ext2glob[ja], a[lo:hi], rhs[r0:r1]
 
 
 class _DevArr:

@@ -12,7 +12,7 @@ from tests.test_distributed_gloo import _free_port
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, nxy, nzl, p, phys, tet, symmetric, q):
+def _worker(rank, world, port, nxy, nzl, p, phys, tet, symmetric, q, pattern="host"):
     try:
         import torch.distributed as dist
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -26,7 +26,7 @@ def _worker(rank, world, port, nxy, nzl, p, phys, tet, symmetric, q):
         bc = (-1, -1, -1, -1, -1, -2)
         mats = materials_for(phys, neumann=True)
         slab = distributed.slab_mesh(nxy, nzl * world, rank, world, p, ns, tetrahedra=bool(tet), bc_matids=bc, perturb=0.1)
-        sh = distributed.ShardedStructMatrix(slab, mats, symmetric=symmetric, device=rank)
+        sh = distributed.ShardedStructMatrix(slab, mats, symmetric=symmetric, device=rank, pattern=pattern)
         sh.strmat.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         sh.Create()
         for _ in range(2):  # re-assembly must reproduce
@@ -50,15 +50,16 @@ def _worker(rank, world, port, nxy, nzl, p, phys, tet, symmetric, q):
         q.put((rank, "fail: " + traceback.format_exc()[-1500:]))
 
 
-@pytest.mark.parametrize("nxy,nzl,p,phys,tet,symmetric", [(6, 3, 2, 0, 0, True), (4, 2, 2, 1, 0, True), (4, 2, 2, 0, 1, False)])
-def test_sharded_cuda_nccl(nxy, nzl, p, phys, tet, symmetric):
+@pytest.mark.parametrize("pattern", ["host", "device"])
+@pytest.mark.parametrize("nxy,nzl,p,phys,tet,symmetric", [(6, 3, 2, 0, 0, True), (4, 2, 2, 1, 0, True), (4, 2, 2, 0, 1, False), (3, 2, 4, 0, 0, True)])
+def test_sharded_cuda_nccl(nxy, nzl, p, phys, tet, symmetric, pattern):
     world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nxy, nzl, p, phys, tet, symmetric, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nxy, nzl, p, phys, tet, symmetric, q, pattern)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=600) for _ in range(world)]
