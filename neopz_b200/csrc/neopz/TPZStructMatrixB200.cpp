@@ -175,8 +175,17 @@ void FillCoef(HostGroup &g) {
                     for (int b = 0; b < 3; b++) coef[a * 3 + b] = v1.GetVal(a, b);
                     coef[9 + a] = v2[a];
                 }
+            } else if (type == 3) {  // directional null Dirichlet, TPZElasticity3D.cpp:715-723
+                for (int a = 0; a < 3; a++) coef[a * 3 + a] = big * v2[a];
+            } else if (type >= 5 && type <= 8) {  // directional Dirichlet on x / y / z / x and z, :739-772
+                const bool on[3] = {type == 5 || type == 8, type == 6, type == 7 || type == 8};
+                for (int a = 0; a < 3; a++)
+                    if (on[a]) {
+                        coef[a * 3 + a] = big;
+                        coef[9 + a] = big * v2[a];
+                    }
             } else {
-                Fatal("TPZElasticity3D boundary condition type " + std::to_string(type) + " is not supported");
+                Fatal("TPZElasticity3D boundary condition type " + std::to_string(type) + " is not supported (type 4 needs the face normal)");
             }
         } else {
             Fatal("boundary condition of an unsupported material");

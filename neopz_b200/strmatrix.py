@@ -70,7 +70,8 @@ class TPZElasticity3D:
 
 
 class TPZBndCond:
-    """TPZBndCondT: type 0 Dirichlet (penalty), 1 Neumann, 2 mixed (Elasticity3D only)."""
+    """TPZBndCondT: type 0 Dirichlet (penalty), 1 Neumann; Elasticity3D also 2 mixed, 3 directional null Dirichlet,
+    5-8 directional Dirichlet (x, y, z, x and z)."""
     kind = capi.BC
 
     def __init__(self, material, matid, bctype, val1, val2):
@@ -107,6 +108,12 @@ class TPZBndCond:
             elif self.type == 2:    # :684-697
                 M[:, :] = self.val1
                 v[:ns] = self.val2[:ns]
+            elif self.type == 3:    # :715-723 directional null Dirichlet: penalty scaled by val2 per direction
+                M[:ns, :ns] = np.diag(big * self.val2[:ns])
+            elif self.type in (5, 6, 7, 8):   # :739-772 directional Dirichlet on x / y / z / x and z
+                for k in {5: (0,), 6: (1,), 7: (2,), 8: (0, 2)}[self.type]:
+                    M[k, k] = big
+                    v[k] = big * self.val2[k]
             else:
                 raise ValueError("TPZElasticity3D: boundary condition type %d not supported" % self.type)
         return M.reshape(-1).tolist() + v.tolist()

@@ -29,11 +29,14 @@
 #define ORC_TET 1
 #define ORC_QUAD 2
 #define ORC_TRI 3
+#define ORC_LINE 4
 
 #define ORC_POISSON 0
 #define ORC_ELAST3D 1
 #define ORC_POISSON_BC 2
 #define ORC_ELAST3D_BC 3
+#define ORC_ELAST2D 4    /* TPZElasticity2D on quadrilaterals / triangles (plane meshes) */
+#define ORC_ELAST2D_BC 5 /* its boundary conditions on line elements */
 
 /* ------------------------------------------------------------------------------------------
  * Quadrature.  Integral/tpzgaussrule.cpp:171-243 (Gauss-Legendre by Newton iteration in
@@ -101,6 +104,14 @@ int orc_rule_hex(int order, double *pts, double *w) {
 }
 
 /* quadrilateral: Integral/pzquad.cpp:153-169, ik = ip / nEta (ksi slowest) */
+/* TPZInt1d: the 1-D Gauss-Legendre rule itself (Integral/pzquad.cpp, TPZGaussRule) */
+int orc_rule_line(int order, double *pts, double *w) {
+    long double l[64], ww[64];
+    const int n = orc_gauss1d_ld(order, l, ww);
+    for (int ip = 0; ip < n; ip++) { pts[ip] = (double)l[ip]; w[ip] = (double)ww[ip]; }
+    return n;
+}
+
 int orc_rule_quad(int order, double *pts, double *w) {
     long double l[64], ww[64];
     const int n = orc_gauss1d_ld(order, l, ww);
@@ -440,6 +451,19 @@ static int shape_hq_general(int topo, int p, const int64_t *ids, const double *p
     return n;
 }
 
+/* TPZShapeLinear, p <= 2: Shape/pzshapelinear.cpp:269-283 (corner), :285-292 (generating: phi0*phi1*4) */
+static int shape_line(int p, const double *pt, double *phi, double *dphi_out) {
+    const int n = p == 1 ? 2 : 3;
+    phi[0] = (1. - pt[0]) / 2.; phi[1] = (1. + pt[0]) / 2.;
+    dphi_out[0] = -0.5; dphi_out[1] = 0.5;
+    if (p >= 2) {
+        phi[2] = phi[0] * phi[1];
+        dphi_out[2] = dphi_out[0] * phi[1] + phi[0] * dphi_out[1];
+        phi[2] *= 4.; dphi_out[2] *= 4.;
+    }
+    return n;
+}
+
 /* ids: global corner-node indices (gel->NodeIndex, Mesh/TPZCompElH1.cpp:110); may be NULL for p <= 2 */
 int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi) {
     if (p < 1) return -1;
@@ -449,6 +473,7 @@ int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double 
             case ORC_TET: return shape_tet(p, pt, phi, dphi);
             case ORC_QUAD: return shape_quad(p, pt, phi, dphi);
             case ORC_TRI: return shape_tri(p, pt, phi, dphi);
+            case ORC_LINE: return shape_line(p, pt, phi, dphi);
         }
         return -1;
     }
@@ -487,6 +512,9 @@ static void gradx_of(int topo, const double *coords, const double *pt, double gr
         static const double dc[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
         for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) d[k][a] = dc[a][k];
         nn = 4;
+    } else if (topo == ORC_LINE) { /* Geom/pzgeolinear.h: x = sum_a x_a phi_a, phi = (1 -+ xi)/2 */
+        d[0][0] = -0.5; d[0][1] = 0.5;
+        nn = 2; dim = 1;
     } else {
         d[0][0] = -1.; d[1][0] = -1.; d[0][1] = 1.; d[1][1] = 0.; d[0][2] = 0.; d[1][2] = 1.;
         nn = 3; dim = 2;
@@ -499,8 +527,18 @@ static void gradx_of(int topo, const double *coords, const double *pt, double gr
 
 /* Mesh/pzgeoel.cpp:1167-1356: 3-D branch :1296-1344, 2-D Gram-Schmidt branch :1228-1295.
  * Returns detjac (signed), jacinv[dim][dim]. */
-static double jacobian_of(int dim, double gradx[3][3], double jacinv[3][3]) {
+static double jacobian_of(int dim, double gradx[3][3], double jacinv[3][3], double axes[3][3]) {
     double detjac = 0.0;
+    if (dim == 1) { /* Mesh/pzgeoel.cpp:1185-1225 */
+        double n1 = 0.0;
+        for (int i = 0; i < 3; i++) n1 += gradx[i][0] * gradx[i][0];
+        n1 = sqrt(n1);
+        detjac = n1;
+        if (fabs(detjac) < 1.e-12) detjac = 1.e-12;
+        jacinv[0][0] = 1.0 / detjac;
+        for (int i = 0; i < 3; i++) axes[0][i] = gradx[i][0] / n1;
+        return detjac;
+    }
     if (dim == 3) {
         double (*jac)[3] = gradx;
         detjac -= jac[0][2] * jac[1][1] * jac[2][0];
@@ -540,6 +578,11 @@ static double jacobian_of(int dim, double gradx[3][3], double jacinv[3][3]) {
     jacinv[0][1] = -j01 / detjac;
     jacinv[1][0] = -j10 / detjac;
     if (fabs(detjac) < 1.e-12) detjac = 1.e-12;
+    for (int i = 0; i < 3; i++) { /* Mesh/pzgeoel.cpp:1287-1291 */
+        v2t[i] /= n2;
+        axes[0][i] = v1t[i];
+        axes[1][i] = v2t[i];
+    }
     return detjac;
 }
 
@@ -559,15 +602,15 @@ typedef struct {
     int64_t ids[8];     /* global corner-node indices (orientation of the sides, p >= 3) */
 } orc_elem_t;
 
-static int topo_dim(int topo) { return (topo == ORC_HEX || topo == ORC_TET) ? 3 : 2; }
+static int topo_dim(int topo) { return (topo == ORC_HEX || topo == ORC_TET) ? 3 : (topo == ORC_LINE ? 1 : 2); }
 
 /* Material/Poisson/TPZMatPoisson.cpp:19-42 */
-static void contribute_poisson(int n, const double *phi, const double *dphix, double weight, const double *mat, double *ek, double *ef) {
+static void contribute_poisson(int fdim, int n, const double *phi, const double *dphix, double weight, const double *mat, double *ek, double *ef) {
     const double fScale = mat[0], force = mat[1];
     for (int i = 0; i < n; i++) {
         for (int j = 0; j < n; j++) {
             double s = 0;
-            for (int x = 0; x < 3; x++) s += dphix[x * n + i] * dphix[x * n + j];
+            for (int x = 0; x < fdim; x++) s += dphix[x * n + i] * dphix[x * n + j];
             ek[j * n + i] += weight * fScale * s;
         }
         ef[i] += weight * fScale * phi[i] * force;
@@ -648,6 +691,109 @@ static int contribute_elast_bc(int n, const double *phi, double weight, int type
                             EK(3 * in + idf, 3 * jn + jdf) += val1[3 * idf + jdf] * weight * phi[in] * phi[jn];
             }
             return 0;
+        case 3: /* directional null Dirichlet, TPZElasticity3D.cpp:715-723 */
+            for (int in = 0; in < n; in++)
+                for (int jn = 0; jn < n; jn++)
+                    for (int k = 0; k < 3; k++) EK(3 * in + k, 3 * jn + k) += BIG * phi[in] * phi[jn] * weight * val2[k];
+            return 0;
+        case 5: case 6: case 7: case 8: { /* directional Dirichlet on x / y / z / x and z, :739-772 */
+            const int on[3] = {type == 5 || type == 8, type == 6, type == 7 || type == 8};
+            for (int in = 0; in < n; in++) {
+                for (int k = 0; k < 3; k++)
+                    if (on[k]) ef[3 * in + k] += BIG * val2[k] * phi[in] * weight;
+                for (int jn = 0; jn < n; jn++)
+                    for (int k = 0; k < 3; k++)
+                        if (on[k]) EK(3 * in + k, 3 * jn + k) += BIG * phi[in] * phi[jn] * weight;
+            }
+            return 0;
+        }
+    }
+#undef EK
+    return -1; /* type 4 (stress field times the face normal) is not restated */
+}
+
+/* Material/Elasticity/TPZElasticity2D.cpp:86-203.  mat[0]=E, mat[1]=nu, mat[2]=fPlaneStress, mat[3..4]=ff,
+ * mat[5..7]=fPreStressXX, XY, YY.  dphi = dphix in the element's axes, axes[2][3]. */
+static void contribute_elast2d(int n, const double *phi, const double *dphi, double axes[3][3], double weight, const double *mat,
+                               double *ek, double *ef) {
+    const double E = mat[0], nu = mat[1];
+    const int planestress = mat[2] != 0.0;
+    const double floc[2] = {mat[3], mat[4]};
+    const double sxx = mat[5], sxy = mat[6], syy = mat[7];
+    const double Eover1MinNu2 = E / (1 - nu * nu);
+    const double Eover21PlusNu = E / (2. * (1 + nu));
+    const double nu1 = 1. - nu;
+    const double nu2 = (1. - 2. * nu) / 2.;
+    const double F = E / ((1. + nu) * (1. - 2. * nu));
+    const int nd = 2 * n;
+#define EK(i, j) ek[(size_t)(j) * nd + (i)]
+    for (int in = 0; in < n; in++) {
+        const double du00 = dphi[0 * n + in] * axes[0][0] + dphi[1 * n + in] * axes[1][0];
+        const double du10 = dphi[0 * n + in] * axes[0][1] + dphi[1 * n + in] * axes[1][1];
+        ef[2 * in] += weight * (floc[0] * phi[in] - du00 * sxx - du10 * sxy);
+        ef[2 * in + 1] += weight * (floc[1] * phi[in] - du00 * sxy - du10 * syy);
+        for (int jn = 0; jn < n; jn++) {
+            const double du01 = dphi[0 * n + jn] * axes[0][0] + dphi[1 * n + jn] * axes[1][0];
+            const double du11 = dphi[0 * n + jn] * axes[0][1] + dphi[1 * n + jn] * axes[1][1];
+            if (!planestress) {
+                EK(2 * in, 2 * jn) += weight * (nu1 * du00 * du01 + nu2 * du10 * du11) * F;
+                EK(2 * in, 2 * jn + 1) += weight * (nu * du00 * du11 + nu2 * du10 * du01) * F;
+                EK(2 * in + 1, 2 * jn) += weight * (nu * du10 * du01 + nu2 * du00 * du11) * F;
+                EK(2 * in + 1, 2 * jn + 1) += weight * (nu1 * du10 * du11 + nu2 * du00 * du01) * F;
+            } else {
+                EK(2 * in, 2 * jn) += weight * (Eover1MinNu2 * du00 * du01 + Eover21PlusNu * du10 * du11);
+                EK(2 * in, 2 * jn + 1) += weight * (Eover1MinNu2 * nu * du00 * du11 + Eover21PlusNu * du10 * du01);
+                EK(2 * in + 1, 2 * jn) += weight * (Eover1MinNu2 * nu * du10 * du01 + Eover21PlusNu * du00 * du11);
+                EK(2 * in + 1, 2 * jn + 1) += weight * (Eover1MinNu2 * du10 * du11 + Eover21PlusNu * du00 * du01);
+            }
+        }
+    }
+#undef EK
+}
+
+/* Material/Elasticity/TPZElasticity2D.cpp:205-330: types 0 (Dirichlet), 1 (Neumann), 2 (mixed), 3 (directional null
+ * Dirichlet).  mat[0] = TPZMaterial::fBigNumber, mat[1..9] = val1 (3x3 row-major, 2x2 used), mat[10..11] = val2 */
+static int contribute_elast2d_bc(int n, const double *phi, double weight, int type, const double *mat, double *ek, double *ef) {
+    const double BIG = mat[0];
+    const double *val1 = mat + 1, *val2 = mat + 10;
+    const int nd = 2 * n;
+#define EK(i, j) ek[(size_t)(j) * nd + (i)]
+    switch (type) {
+        case 0:
+            for (int in = 0; in < n; in++) {
+                ef[2 * in] += BIG * val2[0] * phi[in] * weight;
+                ef[2 * in + 1] += BIG * val2[1] * phi[in] * weight;
+                for (int jn = 0; jn < n; jn++) {
+                    EK(2 * in, 2 * jn) += BIG * phi[in] * phi[jn] * weight;
+                    EK(2 * in + 1, 2 * jn + 1) += BIG * phi[in] * phi[jn] * weight;
+                }
+            }
+            return 0;
+        case 1:
+            for (int in = 0; in < n; in++) {
+                ef[2 * in] += val2[0] * phi[in] * weight;
+                ef[2 * in + 1] += val2[1] * phi[in] * weight;
+            }
+            return 0;
+        case 2:
+            for (int in = 0; in < n; in++) {
+                ef[2 * in] += val2[0] * phi[in] * weight;
+                ef[2 * in + 1] += val2[1] * phi[in] * weight;
+                for (int jn = 0; jn < n; jn++) {
+                    EK(2 * in, 2 * jn) += val1[0] * phi[in] * phi[jn] * weight;
+                    EK(2 * in + 1, 2 * jn) += val1[3] * phi[in] * phi[jn] * weight;
+                    EK(2 * in + 1, 2 * jn + 1) += val1[4] * phi[in] * phi[jn] * weight;
+                    EK(2 * in, 2 * jn + 1) += val1[1] * phi[in] * phi[jn] * weight;
+                }
+            }
+            return 0;
+        case 3:
+            for (int in = 0; in < n; in++)
+                for (int jn = 0; jn < n; jn++) {
+                    EK(2 * in, 2 * jn) += BIG * phi[in] * phi[jn] * weight * val2[0];
+                    EK(2 * in + 1, 2 * jn + 1) += BIG * phi[in] * phi[jn] * weight * val2[1];
+                }
+            return 0;
     }
 #undef EK
     return -1;
@@ -658,7 +804,7 @@ static int contribute_elast_bc(int n, const double *phi, double weight, int type
  * ek: column-major ndof x ndof (zeroed here), ef: ndof. returns ndof or <0 */
 int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
     const int dim = topo_dim(e->topo);
-    const int ns = (e->kind == ORC_ELAST3D || e->kind == ORC_ELAST3D_BC) ? 3 : 1;
+    const int ns = (e->kind == ORC_ELAST3D || e->kind == ORC_ELAST3D_BC) ? 3 : ((e->kind == ORC_ELAST2D || e->kind == ORC_ELAST2D_BC) ? 2 : 1);
     static __thread double phi[ORC_MAXSHAPE], dphi[3 * ORC_MAXSHAPE], dphix[3 * ORC_MAXSHAPE];
     double pt0[3] = {0, 0, 0};
     const int n = orc_shape_ids(e->topo, e->p, e->ids, pt0, phi, dphi);
@@ -669,9 +815,9 @@ int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
     for (int q = 0; q < e->nq; q++) {
         const double *pt = e->qpts + (size_t)q * dim;
         double weight = e->qw[q];
-        double gradx[3][3], jacinv[3][3];
+        double gradx[3][3], jacinv[3][3], axes[3][3];
         gradx_of(e->topo, e->coords, pt, gradx);
-        double detjac = jacobian_of(dim, gradx, jacinv);
+        double detjac = jacobian_of(dim, gradx, jacinv, axes);
         detjac = fabs(detjac);
         orc_shape_ids(e->topo, e->p, e->ids, pt, phi, dphi);
         for (int j = 0; j < n; j++)
@@ -683,7 +829,9 @@ int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
         weight *= fabs(detjac);
         int rc = 0;
         switch (e->kind) {
-            case ORC_POISSON: contribute_poisson(n, phi, dphix, weight, e->mat, ek, ef); break;
+            case ORC_POISSON: contribute_poisson(dim, n, phi, dphix, weight, e->mat, ek, ef); break;
+            case ORC_ELAST2D: contribute_elast2d(n, phi, dphix, axes, weight, e->mat, ek, ef); break;
+            case ORC_ELAST2D_BC: rc = contribute_elast2d_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
             case ORC_ELAST3D: contribute_elast(n, phi, dphix, weight, e->mat, ek, ef); break;
             case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
             case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;

@@ -12,10 +12,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liboracle.so")
 
-HEX, TET, QUAD, TRI = 0, 1, 2, 3
-POISSON, ELAST3D, POISSON_BC, ELAST3D_BC = 0, 1, 2, 3
-TOPO_DIM = {HEX: 3, TET: 3, QUAD: 2, TRI: 2}
-TOPO_NNODE = {HEX: 8, TET: 4, QUAD: 4, TRI: 3}
+HEX, TET, QUAD, TRI, LINE = 0, 1, 2, 3, 4
+POISSON, ELAST3D, POISSON_BC, ELAST3D_BC, ELAST2D, ELAST2D_BC = 0, 1, 2, 3, 4, 5
+TOPO_DIM = {HEX: 3, TET: 3, QUAD: 2, TRI: 2, LINE: 1}
+TOPO_NNODE = {HEX: 8, TET: 4, QUAD: 4, TRI: 3, LINE: 2}
 
 
 def build():
@@ -47,6 +47,7 @@ def lib():
         ip = C.POINTER(C.c_int64)
         _lib.orc_rule_hex.argtypes = [C.c_int, dp, dp]
         _lib.orc_rule_quad.argtypes = [C.c_int, dp, dp]
+        _lib.orc_rule_line.argtypes = [C.c_int, dp, dp]
         _lib.orc_shape.argtypes = [C.c_int, C.c_int, dp, dp, dp]
         _lib.orc_shape_ids.argtypes = [C.c_int, C.c_int, ip, dp, dp, dp]
         _lib.orc_calcstiff.argtypes = [C.POINTER(Elem), dp, dp]
@@ -75,7 +76,7 @@ def rule(topo, order):
     dim = TOPO_DIM[topo]
     pts = np.zeros((4096, dim))
     w = np.zeros(4096)
-    fn = lib().orc_rule_hex if topo == HEX else lib().orc_rule_quad
+    fn = {HEX: lib().orc_rule_hex, QUAD: lib().orc_rule_quad, LINE: lib().orc_rule_line}[topo]
     n = fn(order, _dp(pts), _dp(w))
     return pts[:n].copy(), w[:n].copy()
 

@@ -34,6 +34,8 @@
 #include "pzshapetriang.h"
 #include "Poisson/TPZMatPoisson.h"
 #include "Elasticity/TPZElasticity3D.h"
+#include "Elasticity/TPZElasticity2D.h"
+#include "pzshapelinear.h"
 #include "TPZBndCond.h"
 #include "TPZBndCondT.h"
 #include <chrono>
@@ -86,6 +88,8 @@ struct Case {
     int n = 4, p = 1, phys = 0, tet = 0;
     double perturb = 0.0;
     int bctype = 0;  // type of the BC on matid -1 (0 Dirichlet, 1 Neumann on zmax only -> matid -2)
+    int dim = 3;       // 2: plane mesh (TPZGenGrid2D): phys 0 = TPZMatPoisson(dim 2), phys 2 / 3 = TPZElasticity2D plane
+                       // strain / plane stress; boundary = line elements, matid -2 on the top side when bctype >= 1
     int scramble = 0;  // != 0: node indices permuted by a seeded Fisher-Yates shuffle, so that the side
                        // orientations (transform ids, Shape/pzgenericshape.cpp:57-68) differ between elements
 };
@@ -93,18 +97,19 @@ static std::vector<int64_t> g_node_perm;  // new index of every grid node (ident
 
 static TPZCompMesh *build_mesh(const Case &c) {
     TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
-    TPZManVector<int, 7> matids(7, -1);
+    TPZManVector<int, 7> matids(c.dim == 3 ? 7 : 5, -1);
     matids[0] = 1;
-    if (c.bctype == 1) matids[6] = -2;  // zmax face gets a Neumann condition
-    TPZManVector<int, 3> ndiv(3, c.n);
-    TPZGeoMesh *gmesh = TPZGeoMeshTools::CreateGeoMeshOnGrid(
-        3, minX, maxX, matids, ndiv, c.tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true);
+    if (c.bctype >= 1) matids[c.dim == 3 ? 6 : 3] = -2;  // zmax face (3-D) / top side (2-D): Neumann (1) or BC type c.bctype (>= 2)
+    TPZManVector<int, 3> ndiv(c.dim, c.n);
+    TPZGeoMesh *gmesh = c.dim == 3
+        ? TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv, c.tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true)
+        : TPZGeoMeshTools::CreateGeoMeshOnGrid(2, minX, maxX, matids, ndiv, c.tet ? MMeshType::ETriangular : MMeshType::EQuadrilateral, true);
     if (c.perturb != 0.0) {
         const double h = 1.0 / c.n;
         const int64_t nn = gmesh->NNodes();
         for (int64_t i = 0; i < nn; i++) {
             TPZGeoNode &nd = gmesh->NodeVec()[i];
-            for (int d = 0; d < 3; d++) {
+            for (int d = 0; d < c.dim; d++) {  // plane meshes stay in z = 0
                 double x = nd.Coord(d);
                 x += c.perturb * h * std::sin(2.0 * M_PI * (double)i / 97.0 + (double)d);
                 nd.SetCoord(d, x);
@@ -137,16 +142,38 @@ static TPZCompMesh *build_mesh(const Case &c) {
         gmesh->BuildConnectivity();
     }
     TPZCompMesh *cmesh = new TPZCompMesh(gmesh);
-    cmesh->SetDimModel(3);
+    cmesh->SetDimModel(c.dim);
     cmesh->SetDefaultOrder(c.p);
-    if (c.phys == 0) {
-        auto *m = new TPZMatPoisson<STATE>(1, 3);
+    if (c.phys >= 2) {
+        // TPZElasticity2D: E = 1000, nu = 0.3, body force (0.5, -1), plane strain (phys 2) or plane stress (phys 3)
+        // (the reference's six-argument constructor has an empty body, Material/Elasticity/TPZElasticity2D.cpp:49-53)
+        auto *m = new TPZElasticity2D(1);
+        m->SetElasticity(1000., 0.3);
+        m->SetBodyForce(0.5, -1.0);
+        if (c.phys == 3) m->SetPlaneStress(); else m->SetPlaneStrain();
+        cmesh->InsertMaterialObject(m);
+        TPZFNMatrix<4, STATE> v1(2, 2, 0.);
+        TPZManVector<STATE, 2> v2(2, 0.);
+        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        if (c.bctype == 1) {
+            TPZManVector<STATE, 2> v2n(2, 0.);
+            v2n[0] = 0.25; v2n[1] = -0.5;
+            cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+        } else if (c.bctype >= 2) {
+            TPZFNMatrix<4, STATE> v1m(2, 2, 0.);
+            v1m(0, 0) = 4.0; v1m(0, 1) = 0.5; v1m(1, 0) = 0.5; v1m(1, 1) = 3.0;
+            TPZManVector<STATE, 2> v2m(2, 0.);
+            v2m[0] = 0.3; v2m[1] = -0.2;
+            cmesh->InsertMaterialObject(m->CreateBC(m, -2, c.bctype, v1m, v2m));
+        }
+    } else if (c.phys == 0) {
+        auto *m = new TPZMatPoisson<STATE>(1, c.dim);
         m->SetForcingFunction([](const TPZVec<REAL> &x, TPZVec<STATE> &f) { f[0] = 1.0; }, 0);
         cmesh->InsertMaterialObject(m);
         TPZFNMatrix<1, STATE> v1(1, 1, 0.);
         TPZManVector<STATE, 1> v2(1, 0.);
         cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
-        if (c.bctype == 1) {
+        if (c.bctype >= 1) {
             TPZManVector<STATE, 1> v2n(1, 0.75);
             cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
         }
@@ -162,10 +189,18 @@ static TPZCompMesh *build_mesh(const Case &c) {
             TPZManVector<STATE, 3> v2n(3, 0.);
             v2n[0] = 0.25; v2n[1] = -0.5; v2n[2] = 2.0;
             cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+        } else if (c.bctype >= 2) {
+            // the other types of TPZElasticity3D::ContributeBC (mixed, directional (null) Dirichlet) on the zmax face
+            TPZFNMatrix<9, STATE> v1m(3, 3, 0.);
+            v1m(0, 0) = 4.0; v1m(0, 1) = 0.5; v1m(1, 0) = 0.5; v1m(1, 1) = 3.0; v1m(1, 2) = 0.25; v1m(2, 1) = 0.25; v1m(2, 2) = 5.0;
+            TPZManVector<STATE, 3> v2m(3, 0.);
+            v2m[0] = 0.3; v2m[1] = -0.2; v2m[2] = 0.7;
+            cmesh->InsertMaterialObject(m->CreateBC(m, -2, c.bctype, v1m, v2m));
         }
     }
     cmesh->SetAllCreateFunctionsContinuous();
     cmesh->AutoBuild();
+    if (getenv("REFDRIVER_DEBUG")) std::cerr << "gmesh elements " << gmesh->NElements() << " materials " << cmesh->NMaterials() << " cmesh elements " << cmesh->NElements() << std::endl;
     cmesh->AdjustBoundaryElements();
     cmesh->CleanUpUnconnectedNodes();
     return cmesh;
@@ -177,6 +212,7 @@ static int eltype(TPZCompEl *cel) {
         case ETetraedro: return 1;
         case EQuadrilateral: return 2;
         case ETriangle: return 3;
+        case EOned: return 4;
         default: return -1;
     }
 }
@@ -285,7 +321,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     std::vector<int32_t> econorder(ncel * 27, -1);
     std::vector<int64_t> dest_ptr(ncel + 1, 0), dest, ek_ptr(ncel + 1, 0);
     std::vector<double> ekv, efv;
-    bool done[4] = {false, false, false, false};
+    bool done[5] = {false, false, false, false, false};
     for (int64_t iel = 0; iel < ncel; iel++) {
         TPZCompEl *cel = cmesh->Element(iel);
         if (!cel) { etype[iel] = -1; dest_ptr[iel + 1] = dest.size(); ek_ptr[iel + 1] = ekv.size(); continue; }
@@ -320,6 +356,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
             if (t == 1) dump_shape<pzshape::TPZShapeTetra>(dir, "tet", cel);
             if (t == 2) dump_shape<pzshape::TPZShapeQuad>(dir, "quad", cel);
             if (t == 3) dump_shape<pzshape::TPZShapeTriang>(dir, "tri", cel);
+            if (t == 4) dump_shape<pzshape::TPZShapeLinear>(dir, "line", cel);
         }
     }
     save_vec(dir, "el_type", etype);
@@ -405,7 +442,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     std::ofstream meta(dir + "/meta.json");
     meta.precision(17);
     meta << "{\"n\": " << c.n << ", \"p\": " << c.p << ", \"phys\": " << c.phys << ", \"tet\": " << c.tet
-         << ", \"perturb\": " << c.perturb << ", \"bctype\": " << c.bctype << ", \"scramble\": " << c.scramble << ", \"neq\": " << neq
+         << ", \"perturb\": " << c.perturb << ", \"bctype\": " << c.bctype << ", \"dim\": " << c.dim << ", \"scramble\": " << c.scramble << ", \"neq\": " << neq
          << ", \"ncel\": " << ncel << ", \"nnodes\": " << nn;
     TPZMaterial *mat = cmesh->FindMaterial(1);
     meta << ", \"bignumber\": " << mat->BigNumber();
@@ -465,6 +502,7 @@ int main(int argc, char **argv) {
         c.n = atoi(argv[3]); c.p = atoi(argv[4]); c.phys = atoi(argv[5]); c.tet = atoi(argv[6]);
         c.perturb = atof(argv[7]); c.bctype = atoi(argv[8]);
         if (argc >= 11) c.scramble = atoi(argv[10]);
+        if (argc >= 12) c.dim = atoi(argv[11]);
         return cmd_dump(dir, c, atoi(argv[9]));
     }
     if (cmd == "time" && argc >= 8) {

@@ -33,6 +33,11 @@ CASES = {
     "hex_p3_elast_n2_pert_scr": (2, 3, 1, 0, 0.15, 1, 1, 5),
     "hex_p4_poisson_n2": (2, 4, 0, 0, 0.0, 0, 0, 0),
     "hex_p3_poisson_n3_pert": (3, 3, 0, 0, 0.15, 1, 0, 0),
+    # TPZElasticity3D::ContributeBC types 2 (mixed), 3 (directional null Dirichlet), 8 (Dirichlet on x and z), 6 (on y)
+    "hex_p2_elast_n2_bc2": (2, 2, 1, 0, 0.15, 2, 0, 0),
+    "hex_p2_elast_n2_bc3": (2, 2, 1, 0, 0.15, 3, 0, 0),
+    "tet_p2_elast_n2_bc8": (2, 2, 1, 1, 0.15, 8, 0, 0),
+    "hex_p1_elast_n2_bc6": (2, 1, 1, 0, 0.15, 6, 1, 0),
 }
 
 

@@ -15,6 +15,8 @@ E_MOD, NU = 1000.0, 0.3
 ELAST_FORCE = (0.0, 0.0, -1.0)
 NEUMANN_POISSON = 0.75
 NEUMANN_ELAST = (0.25, -0.5, 2.0)
+BC_VAL1 = np.array([[4.0, 0.5, 0.0], [0.5, 3.0, 0.25], [0.0, 0.25, 5.0]])
+BC_VAL2 = (0.3, -0.2, 0.7)
 TAGS = {orc.HEX: "hex", orc.TET: "tet", orc.QUAD: "quad", orc.TRI: "tri"}
 
 
@@ -37,14 +39,18 @@ def material_vector(g, topo, matid):
         mat[0:3] = orc.elast_constants(E_MOD, NU)
         mat[3:6] = ELAST_FORCE
         return orc.ELAST3D, 0, mat
-    bctype = 0 if matid == -1 else 1
+    bctype = 0 if matid == -1 else max(1, g["meta"]["bctype"])
     mat[0] = big
     mat[13] = 1.0
     if phys == 0:
+        bctype = min(bctype, 1)
         mat[10] = 0.0 if bctype == 0 else NEUMANN_POISSON
         return orc.POISSON_BC, bctype, mat
     if bctype == 1:
         mat[10:13] = NEUMANN_ELAST
+    elif bctype >= 2:  # refdriver's data for the other TPZElasticity3D::ContributeBC types
+        mat[1:10] = BC_VAL1.reshape(-1)
+        mat[10:13] = BC_VAL2
     return orc.ELAST3D_BC, bctype, mat
 
 

@@ -30,6 +30,19 @@ def materials_for(phys, neumann=False):
     return mats
 
 
+def fixture_setup(g):
+    """(mesh, materials) of a committed reference fixture: oracle/refdriver.cpp's recipe."""
+    m = g["meta"]
+    bct = m["bctype"]
+    bc = (-1, -1, -1, -1, -1, -2 if bct >= 1 else -1)
+    mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
+                              bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
+    mats = materials_for(m["phys"], neumann=bct >= 1)
+    if m["phys"] == 1 and bct >= 2:  # the other TPZElasticity3D::ContributeBC types on the zmax face
+        mats[-2] = mats[1].CreateBC(-2, bct, gu.BC_VAL1, gu.BC_VAL2)
+    return mesh, mats
+
+
 def relF(x, ref):
     return np.linalg.norm(x - ref) / np.linalg.norm(ref)
 
@@ -46,11 +59,8 @@ def interior_relF(ia, a, ref, big_rows):
 def test_against_reference_fixtures(name, symmetric):
     g = gu.load(name)
     m = g["meta"]
-    neumann = m["bctype"] == 1
-    bc = (-1, -1, -1, -1, -1, -2 if neumann else -1)
-    mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
-                              bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
-    strmat = sm.TPZStructMatrixB200(mesh, materials_for(m["phys"], neumann), symmetric=symmetric)
+    mesh, mats = fixture_setup(g)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
     ia, ja, a, rhs = strmat.CreateAssemble()
     pre = "sym" if symmetric else "full"
     assert np.array_equal(ia, g[pre + "_ia"]) and np.array_equal(ja, g[pre + "_ja"])  # pattern: bit-exact
@@ -97,11 +107,8 @@ def test_device_pattern_bit_exact(name, symmetric):
     assembling into it gives the reference's values."""
     g = gu.load(name)
     m = g["meta"]
-    neumann = m["bctype"] == 1
-    bc = (-1, -1, -1, -1, -1, -2 if neumann else -1)
-    mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
-                              bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
-    strmat = sm.TPZStructMatrixB200(mesh, materials_for(m["phys"], neumann), symmetric=symmetric)
+    mesh, mats = fixture_setup(g)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
     ia, ja = strmat.Create(on_device=True)
     pre = "sym" if symmetric else "full"
     assert np.array_equal(ia, g[pre + "_ia"]) and np.array_equal(ja, g[pre + "_ja"])
@@ -131,10 +138,8 @@ def test_device_cg_reproduces_reference_solution(name, symmetric):
     reference's own direct (skyline LDLt) solution of the same mesh: 1e-10 (north_star)."""
     g = gu.load(name)
     m = g["meta"]
-    neumann = m["bctype"] == 1
-    bc = (-1, -1, -1, -1, -1, -2 if neumann else -1)
-    mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]), bc_matids=bc, perturb=m["perturb"])
-    strmat = sm.TPZStructMatrixB200(mesh, materials_for(m["phys"], neumann), symmetric=symmetric)
+    mesh, mats = fixture_setup(g)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
     strmat.CreateAssemble()
     u, iters, resid = strmat.SolveCG(max_iter=20000, tol=1e-15)
     assert resid <= 1e-14 and 0 < iters < 20000, (iters, resid)
@@ -177,6 +182,22 @@ def test_elasticity_prestress_load_vector(n, p, tet, engine):
     a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
     assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
     assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+
+
+@pytest.mark.parametrize("bctype", [2, 3, 5, 6, 7, 8])
+@pytest.mark.parametrize("tet,p", [(0, 2), (1, 2), (0, 3)])
+def test_elasticity_bc_types(bctype, tet, p):
+    """TPZElasticity3D::ContributeBC types 2 (mixed), 3 (directional null Dirichlet), 5-8 (directional Dirichlet)
+    (Material/Elasticity/TPZElasticity3D.cpp:684-772) on one face, full Dirichlet elsewhere."""
+    mesh = gridmesh.grid_mesh(3 if p < 3 else 2, p, 3, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    m = sm.TPZElasticity3D(1, gu.E_MOD, gu.NU, gu.ELAST_FORCE)
+    val1 = np.array([[4.0, 0.5, 0.0], [0.5, 3.0, 0.25], [0.0, 0.25, 5.0]])
+    mats = {1: m, -1: m.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3)), -2: m.CreateBC(-2, bctype, val1, [0.3, -0.2, 0.7])}
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+        ia, ja, a, rhs = strmat.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
 
 
 def _shuffled(n, seed):
