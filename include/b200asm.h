@@ -24,13 +24,15 @@ extern "C" {
 typedef struct b200asm_ctx b200asm_ctx;
 
 /* element topologies (reference: MElementType ECube/ETetraedro/EQuadrilateral/ETriangle) */
-enum { B200ASM_HEX = 0, B200ASM_TET = 1, B200ASM_QUAD = 2, B200ASM_TRI = 3 };
+enum { B200ASM_HEX = 0, B200ASM_TET = 1, B200ASM_QUAD = 2, B200ASM_TRI = 3, B200ASM_LINE = 4 /* EOned */ };
 /* weak forms:
  *  POISSON       Material/Poisson/TPZMatPoisson.cpp:19-42
  *  ELASTICITY3D  Material/Elasticity/TPZElasticity3D.cpp:85-107,269-372
  *  BC            the boundary forms of both (TPZMatPoisson.cpp:45-121, TPZElasticity3D.cpp:616-773)
- *                reduced to  ek(ns*i+a, ns*j+b) += M[a][b]*phi_i*phi_j*w ,  ef(ns*i+a) += v[a]*phi_i*w */
-enum { B200ASM_POISSON = 0, B200ASM_ELASTICITY3D = 1, B200ASM_BC = 2 };
+ *                reduced to  ek(ns*i+a, ns*j+b) += M[a][b]*phi_i*phi_j*w ,  ef(ns*i+a) += v[a]*phi_i*w
+ *  ELASTICITY2D  Material/Elasticity/TPZElasticity2D.cpp:86-203 on the quadrilaterals / triangles of a plane mesh
+ *                (nstate 2; boundary = LINE elements of kind BC); POISSON on QUAD / TRI = TPZMatPoisson(dim 2) */
+enum { B200ASM_POISSON = 0, B200ASM_ELASTICITY3D = 1, B200ASM_BC = 2, B200ASM_ELASTICITY2D = 3 };
 
 enum {
     B200ASM_OK = 0,
@@ -70,6 +72,8 @@ typedef struct {
     const double *dphi;     /* [nqp][dim][nshape]  master-element gradients */
     /* POISSON:      coef[0]=fScale, coef[1]=value of the (constant) forcing function
      * ELASTICITY3D: coef[0..2]=C1,C2,C3 (TPZElasticity3D.h:183-188), coef[3..5]=fForce, coef[6..8]=fPreStress
+     * ELASTICITY2D: coef[0..2]=cA,cB,cC (plane strain: F(1-nu), F(1-2nu)/2, F nu with F=E/((1+nu)(1-2nu)); plane stress:
+     *               E/(1-nu^2), E/(2(1+nu)), nu E/(1-nu^2)), coef[3..4]=body force, coef[5..7]=fPreStressXX, XY, YY
      * BC:           coef[0..8]=M (3x3 row-major, upper-left ns x ns used), coef[9..11]=v */
     double coef[16];
     const double *force; /* optional [nel][nqp][nstate]: forcing function evaluated by the host at the

@@ -11,8 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200asm.so")
 
-HEX, TET, QUAD, TRI = 0, 1, 2, 3
-POISSON, ELASTICITY3D, BC = 0, 1, 2
+HEX, TET, QUAD, TRI, LINE = 0, 1, 2, 3, 4
+POISSON, ELASTICITY3D, BC, ELASTICITY2D = 0, 1, 2, 3
 ENODEVICE = -2
 
 
@@ -110,8 +110,8 @@ def i32ptr(a):
 
 # ---- host-side helpers (no device) -------------------------------------------------------------
 def tensor_rule(topology, order):
-    dim = 3 if topology == HEX else 2
-    pts = np.zeros((64 ** 2 if dim == 2 else 16 ** 3, dim))
+    dim = {HEX: 3, QUAD: 2, LINE: 1}[topology]
+    pts = np.zeros((4096, dim))
     w = np.zeros(len(pts))
     n = lib().b200asm_tensor_rule(topology, order, dptr(pts), dptr(w))
     if n < 0:

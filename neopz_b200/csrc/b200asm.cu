@@ -389,7 +389,10 @@ struct BcParams {
     const int32_t *__restrict__ dest;
     const double *__restrict__ qw;
     const double *__restrict__ phi;   // [nq][N]
-    const double *__restrict__ dng;   // [nq][2][NN]
+    const double *__restrict__ dphi;  // [nq][2][N]   (plane domain elements only)
+    const double *__restrict__ dng;   // [nq][fdim][NN]
+    int kind;                         // plane domain elements: B200ASM_POISSON / B200ASM_ELASTICITY2D
+    int fdim;                         // dimension of the element: 2 (faces, plane elements) or 1 (line elements)
     const int32_t *__restrict__ smap;   // [N*N*NS*NS][nel]
     const int32_t *__restrict__ smapT;
     double *__restrict__ a;
@@ -495,11 +498,11 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
     if (el >= p.el1) return;
     double *W = bc_smem + (size_t)warp * p.nq;
     for (int q = lane; q < p.nq; q += 32) {
-        const double *dn = p.dng + (size_t)q * 2 * NN;
+        const double *dn = p.dng + (size_t)q * p.fdim * NN;
         double v1[3] = {0, 0, 0}, v2[3] = {0, 0, 0};
         for (int a = 0; a < NN; a++) {
             const int64_t node = p.elnodes[el * NN + a];
-            const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a);
+            const double d0 = __ldg(dn + a), d1 = p.fdim == 2 ? __ldg(dn + NN + a) : 0.0;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const double x = p.xyz[node * 3 + k];
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
             n2 += v2t * v2t;
         }
         n2 = sqrt(n2);
-        double det = n1 * n2;
+        double det = p.fdim == 2 ? n1 * n2 : n1;  // line elements: |dx/dxi|  (Mesh/pzgeoel.cpp:1185-1225)
         if (fabs(det) < 1.e-12) det = 1.e-12;
         W[q] = __ldg(p.qw + q) * fabs(det);
     }
@@ -554,6 +557,131 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
         for (int a = 0; a < NS; a++) {
             const double v = p.coef[9 + a];
             if (v != 0.0) scatter_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T, p.atomic);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plane (2-D) domain elements: quadrilaterals / triangles of a plane mesh with TPZMatPoisson(dim 2) or TPZElasticity2D
+// (Material/Elasticity/TPZElasticity2D.cpp:86-203).  One WARP per element, runtime sizes.
+//   lanes <-> integration points: Gram-Schmidt Jacobian, axes (Mesh/pzgeoel.cpp:1228-1295), dphix = jacinv^T dphi in the
+//             element's axes (pzinterpolationspace.cpp:1688-1694), for elasticity rotated to x, y with the axes
+//             (TPZElasticity2D.cpp:152-153), scaled by sqrt(w|detJ|)  -> shared memory G[q][i][2]
+//   lanes <-> node pairs (in <= jn): S[v][u] = sum_q G[q][in][v] G[q][jn][u], then
+//             Poisson:      ek(in,jn) = s (S00 + S11)
+//             Elasticity2D: ek(2in+a,2jn+b) = a==b ? cA S_aa + cB S_a'a' : cC S_ab + cB S_ba
+//             (plane strain: cA = F(1-nu), cB = F(1-2nu)/2, cC = F nu, F = E/((1+nu)(1-2nu)); plane stress: cA = E/(1-nu^2),
+//              cB = E/(2(1+nu)), cC = nu E/(1-nu^2): the host passes the three constants)
+// coef: Poisson [fScale, force]; Elasticity2D [cA, cB, cC, fx, fy, sxx, sxy, syy]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) assemble_plane_kernel(const BcParams p, int NN, int N, int NS) {
+    extern __shared__ double pl_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t el = p.el0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (el >= p.el1) return;
+    const int nq = p.nq;
+    double *W = pl_smem + (size_t)warp * nq * (2 + 2 * N);  // [nq] w|detJ|
+    double *SW = W + nq;                                     // [nq] sqrt(w|detJ|)
+    double *G = SW + nq;                                     // [nq][N][2]
+    for (int q = lane; q < nq; q += 32) {
+        const double *dn = p.dng + (size_t)q * 2 * NN;
+        double v1[3] = {0, 0, 0}, v2[3] = {0, 0, 0};
+        for (int a = 0; a < NN; a++) {
+            const int64_t node = p.elnodes[el * NN + a];
+            const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double x = p.xyz[node * 3 + k];
+                v1[k] += x * d0;
+                v2[k] += x * d1;
+            }
+        }
+        double n1 = 0, dot = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            n1 += v1[k] * v1[k];
+            dot += v1[k] * v2[k];
+        }
+        n1 = sqrt(n1);
+        double a0[3], a1[3], n2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            a0[k] = v1[k] / n1;
+            a1[k] = v2[k] - dot * a0[k] / n1;
+            n2 += a1[k] * a1[k];
+        }
+        n2 = sqrt(n2);
+#pragma unroll
+        for (int k = 0; k < 3; k++) a1[k] /= n2;
+        const double j00 = n1, j01 = dot / n1, j11 = n2;
+        double det = j00 * j11;
+        const double i00 = j11 / det, i11 = j00 / det, i01 = -j01 / det;  // jacinv (i10 = 0)
+        if (fabs(det) < 1.e-12) det = 1.e-12;
+        const double w = __ldg(p.qw + q) * fabs(det);
+        const double sw = sqrt(w);
+        W[q] = w;
+        SW[q] = sw;
+        for (int i = 0; i < N; i++) {
+            const double d0 = __ldg(p.dphi + ((size_t)q * 2 + 0) * N + i), d1 = __ldg(p.dphi + ((size_t)q * 2 + 1) * N + i);
+            const double dx0 = i00 * d0;              // dphidx(0) = jacinv(0,0) dphi0 + jacinv(1,0) dphi1
+            const double dx1 = i01 * d0 + i11 * d1;   // dphidx(1) = jacinv(0,1) dphi0 + jacinv(1,1) dphi1
+            double g0 = dx0, g1 = dx1;
+            if (p.kind == B200ASM_ELASTICITY2D) {     // du = dphix rotated to x, y
+                g0 = dx0 * a0[0] + dx1 * a1[0];
+                g1 = dx0 * a0[1] + dx1 * a1[1];
+            }
+            G[((size_t)q * N + i) * 2 + 0] = sw * g0;
+            G[((size_t)q * N + i) * 2 + 1] = sw * g1;
+        }
+    }
+    __syncwarp();
+    const int npair = p.rhs_only ? 0 : N * (N + 1) / 2;
+    for (int idx = lane; idx < npair; idx += 32) {
+        int in = 0, rem = idx;
+        while (rem >= N - in) { rem -= N - in; in++; }
+        const int jn = in + rem;
+        double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
+        for (int q = 0; q < nq; q++) {
+            const double a0 = G[((size_t)q * N + in) * 2], a1 = G[((size_t)q * N + in) * 2 + 1];
+            const double b0 = G[((size_t)q * N + jn) * 2], b1 = G[((size_t)q * N + jn) * 2 + 1];
+            S00 += a0 * b0; S01 += a0 * b1; S10 += a1 * b0; S11 += a1 * b1;
+        }
+        double e[2][2];
+        if (NS == 1) {
+            e[0][0] = p.coef[0] * (S00 + S11);
+        } else {
+            const double cA = p.coef[0], cB = p.coef[1], cC = p.coef[2];
+            e[0][0] = cA * S00 + cB * S11;
+            e[0][1] = cC * S01 + cB * S10;
+            e[1][0] = cC * S10 + cB * S01;
+            e[1][1] = cA * S11 + cB * S00;
+        }
+        for (int a = 0; a < NS; a++)
+            for (int b = 0; b < NS; b++) {
+                if (in == jn && b < a) continue;
+                const size_t sidx = ((size_t)((in * N + jn) * NS + a) * NS + b) * p.nel + el;
+                const int32_t pos = p.smap[sidx];
+                if (pos >= 0) scatter_add(p.a + pos, e[a][b], p.atomic);
+                if (p.smapT) {
+                    const int32_t posT = p.smapT[sidx];
+                    if (posT >= 0) scatter_add(p.a + posT, e[a][b], p.atomic);
+                }
+            }
+    }
+    for (int i = lane; i < N; i += 32) {
+        double t = 0, gx = 0, gy = 0;  // sum_q w phi_i ; sum_q w du_x ; sum_q w du_y
+        for (int q = 0; q < nq; q++) {
+            t += W[q] * __ldg(p.phi + (size_t)q * N + i);
+            gx += SW[q] * G[((size_t)q * N + i) * 2];
+            gy += SW[q] * G[((size_t)q * N + i) * 2 + 1];
+        }
+        if (NS == 1) {
+            scatter_add(p.rhs + p.dest[el * N + i], p.coef[0] * p.coef[1] * t, p.atomic);
+        } else {
+            // ef(2i) += w (fx phi - du_x sxx - du_y sxy) ; ef(2i+1) += w (fy phi - du_x sxy - du_y syy)
+            const double fx = p.coef[3], fy = p.coef[4], sxx = p.coef[5], sxy = p.coef[6], syy = p.coef[7];
+            scatter_add(p.rhs + p.dest[el * (N * 2) + i * 2], fx * t - gx * sxx - gy * sxy, p.atomic);
+            scatter_add(p.rhs + p.dest[el * (N * 2) + i * 2 + 1], fy * t - gx * sxy - gy * syy, p.atomic);
         }
     }
 }
@@ -607,6 +735,7 @@ struct Group {
     int topology = 0, porder = 0, kind = 0, ns = 1, nn = 0, n = 0, nq = 0, m = 0, dim = 3;
     int64_t nel = 0, nbatch = 0;
     int64_t max_dest = -1;  // largest destination equation of the group
+    bool plane = false;     // quadrilaterals / triangles as DOMAIN elements of a plane problem (kind POISSON / ELASTICITY2D)
     int cfg = -1;  // index into the dispatch table (register-tile kernels)
     int mma = -1;  // index into the DMMA dispatch table, -1: none
     double coef[16];
@@ -832,6 +961,12 @@ cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
 }
 
 cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cudaStream_t s) {
+    if (topology == B200ASM_LINE) {  // boundary of a plane problem
+        const int grid = (int)((p.el1 - p.el0 + 3) / 4);
+        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, 2, porder + 1, ns);
+        return cudaGetLastError();
+    }
+    if (ns == 2) return cudaErrorInvalidValue;
     if (porder >= 3) {
         if (topology != B200ASM_QUAD) return cudaErrorInvalidValue;
         const int n = (porder + 1) * (porder + 1);
@@ -848,6 +983,7 @@ cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cud
 
 int nshape_of(int topology, int p) { return b200asm_nshape(topology, p); }
 int ncorner_of(int topology) {
+    if (topology == B200ASM_LINE) return 2;
     switch (topology) {
         case B200ASM_HEX: return 8;
         case B200ASM_TET: return 4;
@@ -893,7 +1029,7 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
     for (Group &g : ctx->groups) {
         cudaFree(g.d_smap); cudaFree(g.d_smapT);
         g.d_smap = g.d_smapT = nullptr;
-        if (g.kind == B200ASM_BC) {
+        if (g.kind == B200ASM_BC || g.plane) {
             g.smap_len = (size_t)g.n * g.n * g.ns * g.ns * g.nel;
         } else if (g.mma >= 0 && ctx->engine == 1) {
             g.smap_len = (size_t)g.nel * kMma[g.mma].slots;
@@ -911,7 +1047,7 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
         if (!ctx->symmetric) CK(cudaMalloc((void **)&g.d_smapT, std::max<size_t>(g.smap_len, 1) * sizeof(int32_t)));
         if (g.smap_len == 0) continue;
         const int grid = (int)std::min<size_t>((g.smap_len + 255) / 256, (size_t)ctx->num_sms * 32);
-        if (g.kind == B200ASM_BC) {
+        if (g.kind == B200ASM_BC || g.plane) {
             build_bc_smap_kernel<<<grid, 256, 0, ctx->stream>>>(g.nel, g.n, g.ns, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric,
                                                                 g.d_smap, g.d_smapT, ctx->d_missing);
             CK(cudaGetLastError());
@@ -1044,11 +1180,12 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     g.nn = ncorner_of(gi->topology);
     g.n = nshape_of(gi->topology, gi->porder);
     g.nq = gi->nqp;
-    g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET) ? 3 : 2;
+    g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET) ? 3 : (gi->topology == B200ASM_LINE ? 1 : 2);
+    g.plane = g.dim == 2 && (gi->kind == B200ASM_POISSON || gi->kind == B200ASM_ELASTICITY2D);
     if (g.nn < 0 || g.n < 0 || gi->porder < 1)
         return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad 1..4, tet/tri 1..2)");
     if (gi->nshape != g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not match topology/order");
-    if (g.ns != 1 && g.ns != 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1 or 3");
+    if (g.ns < 1 || g.ns > 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1, 2 or 3");
     if (g.nel < 0 || g.nq <= 0 || g.nq > 512) return fail(ctx, B200ASM_EINVAL, "add_group: bad nel/nqp");
     if (!gi->elnodes || !gi->dest || !gi->qpts || !gi->qwts || !gi->phi || !gi->dphi)
         return fail(ctx, B200ASM_EINVAL, "add_group: NULL table");
@@ -1065,8 +1202,15 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns &&
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
                 g.mma = k;
+    } else if (g.plane) {
+        if (gi->porder > 2) return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: p <= 2");
+        if (gi->kind == B200ASM_POISSON && g.ns != 1) return fail(ctx, B200ASM_EINVAL, "add_group: Poisson has nstate 1");
+        if (gi->kind == B200ASM_ELASTICITY2D && g.ns != 2) return fail(ctx, B200ASM_EINVAL, "add_group: Elasticity2D has nstate 2");
+        if (gi->force) return fail(ctx, B200ASM_EINVAL, "add_group: forcing-function tables are not supported on plane elements");
     } else if (gi->kind != B200ASM_BC) {
-        return fail(ctx, B200ASM_EINVAL, "add_group: face elements need kind BC");
+        return fail(ctx, B200ASM_EINVAL, "add_group: face / line elements need kind BC (or POISSON / ELASTICITY2D as plane domain elements)");
+    } else if (g.dim == 1 && gi->porder > 2) {
+        return fail(ctx, B200ASM_EINVAL, "add_group: line elements: p <= 2");
     }
     g.m = g.n * g.ns;
     memcpy(g.coef, gi->coef, sizeof(g.coef));
@@ -1351,16 +1495,24 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
             if (!g.ev0) { CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); }
             CK(cudaEventRecord(g.ev0, ctx->stream));
         }
-        if (g.kind == B200ASM_BC) {
+        if (g.kind == B200ASM_BC || g.plane) {
             BcParams p;
             p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
-            p.qw = g.d_qw; p.phi = g.d_phi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
+            p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
+            p.kind = g.kind; p.fdim = g.dim;
             p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
             memcpy(p.coef, g.coef, sizeof(p.coef));
             for (size_t c = 0; c < nseg; c++) {
                 p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];
                 if (p.el1 == p.el0) continue;
-                CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+                if (g.plane) {
+                    const int grid = (int)((p.el1 - p.el0 + 3) / 4);
+                    const size_t smem = 4 * (size_t)g.nq * (2 + 2 * g.n) * sizeof(double);
+                    assemble_plane_kernel<<<grid, 128, smem, ctx->stream>>>(p, g.nn, g.n, g.ns);
+                    CK(cudaGetLastError());
+                } else {
+                    CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+                }
                 ctx->launches++;
             }
             if (ctx->timing) CK(cudaEventRecord(g.ev1, ctx->stream));

@@ -199,6 +199,13 @@ extern "C" int b200asm_tensor_rule(int topology, int order, double *qpts, double
                 }
         return n * n * n;
     }
+    if (topology == B200ASM_LINE) {  // TPZInt1d: the 1-D rule itself
+        for (int ik = 0; ik < n; ik++) {
+            qpts[ik] = (double)l[ik];
+            qw[ik] = (double)w[ik];
+        }
+        return n;
+    }
     if (topology == B200ASM_QUAD) {
         // point index = ie + n*ik: ksi slowest
         for (int ik = 0; ik < n; ik++)
@@ -221,14 +228,22 @@ extern "C" int b200asm_shape_tables(int topology, int porder, int nqp, const dou
         case B200ASM_QUAD: n = porder == 1 ? 4 : 9; break;
         case B200ASM_TET: n = porder == 1 ? 4 : 10; break;
         case B200ASM_TRI: n = porder == 1 ? 3 : 6; break;
+        case B200ASM_LINE: n = porder + 1; break;
         default: return B200ASM_EINVAL;
     }
-    const int dim = (topology == B200ASM_HEX || topology == B200ASM_TET) ? 3 : 2;
+    const int dim = (topology == B200ASM_HEX || topology == B200ASM_TET) ? 3 : (topology == B200ASM_LINE ? 1 : 2);
     for (int q = 0; q < nqp; q++) {
         const double *pt = qpts + (size_t)q * dim;
         double *ph = phi + (size_t)q * n;
         double *dp = dphi + (size_t)q * dim * n;  // [d][i]
-        if (topology == B200ASM_HEX || topology == B200ASM_QUAD) {
+        if (topology == B200ASM_LINE) {  // TPZShapeLinear (Shape/pzshapelinear.cpp:269-292): l0, l1, 4 l0 l1
+            double f[3], df[3];
+            factors1d(pt[0], f, df);
+            for (int s = 0; s < n; s++) {
+                ph[s] = f[s];
+                dp[s] = df[s];
+            }
+        } else if (topology == B200ASM_HEX || topology == B200ASM_QUAD) {
             double f[3][3], df[3][3];
             for (int d = 0; d < dim; d++) factors1d(pt[d], f[d], df[d]);
             for (int s = 0; s < n; s++) {
@@ -285,13 +300,14 @@ extern "C" int b200asm_nshape(int topology, int porder) {
         case B200ASM_QUAD: return (p + 1) * (p + 1);
         case B200ASM_TET: return p <= 2 ? (p == 1 ? 4 : 10) : B200ASM_EINVAL;
         case B200ASM_TRI: return p <= 2 ? (p == 1 ? 3 : 6) : B200ASM_EINVAL;
+        case B200ASM_LINE: return p <= 2 ? p + 1 : B200ASM_EINVAL;
     }
     return B200ASM_EINVAL;
 }
 
 extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t *elnodes, int64_t *keys) {
     if (nel < 0 || (nel && (!elnodes || !keys))) return B200ASM_EINVAL;
-    if (topology == B200ASM_TET || topology == B200ASM_TRI) {  // p <= 2 only: no orientation dependence
+    if (topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_LINE) {  // p <= 2 only: no orientation dependence
         for (int64_t e = 0; e < nel; e++) keys[e] = 0;
         return 0;
     }
@@ -320,7 +336,7 @@ extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t
 extern "C" int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts,
                                              double *phi, double *dphi) {
     if (porder < 1 || porder > 8 || nqp < 0) return B200ASM_EINVAL;
-    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI)
+    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_LINE)
         return b200asm_shape_tables(topology, porder, nqp, qpts, phi, dphi);
     if (topology != B200ASM_HEX && topology != B200ASM_QUAD) return B200ASM_EINVAL;
     const int dim = topology == B200ASM_HEX ? 3 : 2;

@@ -11,7 +11,9 @@
 #include <tuple>
 #include <vector>
 
+#include "Elasticity/TPZElasticity2D.h"
 #include "Elasticity/TPZElasticity3D.h"
+#include "pzshapelinear.h"
 #include "Poisson/TPZMatPoisson.h"
 #include "TPZBndCondT.h"
 #include "TPZCompElH1.h"
@@ -57,6 +59,15 @@ struct ElastAccess : public TPZElasticity3D {
 
 // one device group per (topology, material, order, side-orientation class): for p >= 3 the shape functions of a side
 // depend on the global indices of its corner nodes (Shape/pzgenericshape.cpp:57-68), elements of one class share tables
+// protected members of TPZElasticity2D (Material/Elasticity/TPZElasticity2D.h:196-232)
+struct Elast2DAccess : public TPZElasticity2D {
+    using TPZElasticity2D::ff;
+    using TPZElasticity2D::fPlaneStress;
+    using TPZElasticity2D::fPreStressXX;
+    using TPZElasticity2D::fPreStressXY;
+    using TPZElasticity2D::fPreStressYY;
+};
+
 struct GroupKey {
     int topology, matid, porder;
     int64_t orientation;
@@ -81,6 +92,7 @@ int TopologyOf(MElementType t) {
         case ETetraedro: return B200ASM_TET;
         case EQuadrilateral: return B200ASM_QUAD;
         case ETriangle: return B200ASM_TRI;
+        case EOned: return B200ASM_LINE;
         default: return -1;
     }
 }
@@ -161,6 +173,20 @@ void FillCoef(HostGroup &g) {
             } else {
                 Fatal("TPZMatPoisson boundary condition type " + std::to_string(type) + " is not supported");
             }
+        } else if (auto *e2 = dynamic_cast<TPZElasticity2D *>(vol)) {
+            const double big = e2->BigNumber();  // Material/Elasticity/TPZElasticity2D.cpp:219
+            if (type == 0) {  // :256-270
+                for (int a = 0; a < 2; a++) {
+                    coef[a * 3 + a] = big;
+                    coef[9 + a] = big * v2[a];
+                }
+            } else if (type == 1) {  // :273-283
+                for (int a = 0; a < 2; a++) coef[9 + a] = v2[a];
+            } else if (type == 3) {  // :305-316
+                for (int a = 0; a < 2; a++) coef[a * 3 + a] = big * v2[a];
+            } else {
+                Fatal("TPZElasticity2D boundary condition type " + std::to_string(type) + " is not supported");
+            }
         } else if (dynamic_cast<TPZElasticity3D *>(vol)) {
             const double big = 1.e12;  // Material/Elasticity/TPZElasticity3D.cpp:630
             if (type == 0) {
@@ -197,6 +223,27 @@ void FillCoef(HostGroup &g) {
         coef[1] = 0.0;  // the source comes from the forcing-function table (or is absent)
         return;
     }
+    if (auto *e2 = dynamic_cast<TPZElasticity2D *>(mat)) {
+        // the three constants of Material/Elasticity/TPZElasticity2D.cpp:141-199 (plane strain / plane stress)
+        auto *acc = static_cast<Elast2DAccess *>(e2);
+        const double E = e2->E(), nu = e2->Nu();
+        if (acc->fPlaneStress) {
+            coef[0] = E / (1 - nu * nu);
+            coef[1] = E / (2. * (1 + nu));
+            coef[2] = E / (1 - nu * nu) * nu;
+        } else {
+            const double F = E / ((1. + nu) * (1. - 2. * nu));
+            coef[0] = (1. - nu) * F;
+            coef[1] = (1. - 2. * nu) / 2. * F;
+            coef[2] = nu * F;
+        }
+        coef[3] = acc->ff[0];
+        coef[4] = acc->ff[1];
+        coef[5] = acc->fPreStressXX;
+        coef[6] = acc->fPreStressXY;
+        coef[7] = acc->fPreStressYY;
+        return;
+    }
     if (auto *el = dynamic_cast<TPZElasticity3D *>(mat)) {
         auto *acc = static_cast<ElastAccess *>(el);
         coef[0] = acc->C1;
@@ -217,7 +264,16 @@ void FillForce(HostGroup &g) {
     g.meta.force = nullptr;
     const int ns = g.meta.nstate;
     const int dim = (g.meta.topology == B200ASM_HEX || g.meta.topology == B200ASM_TET) ? 3 : 2;
-    if (dim != 3) return;
+    if (dim != 3) {
+        // plane domain elements: constant source only (TPZMatPoisson without forcing function has none)
+        if (g.meta.kind != B200ASM_BC) {
+            auto *p2 = dynamic_cast<TPZMatPoisson<STATE> *>(g.material);
+            auto *e2 = dynamic_cast<TPZElasticity2D *>(g.material);
+            if ((p2 && p2->HasForcingFunction()) || (e2 && e2->HasForcingFunction()))
+                Fatal("forcing functions on plane (2-D) domain elements are not supported yet");
+        }
+        return;
+    }
     auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(g.material);
     auto *el = dynamic_cast<TPZElasticity3D *>(g.material);
     const bool hasf = pois ? pois->HasForcingFunction() : (el ? el->HasForcingFunction() : false);
@@ -260,7 +316,8 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
         if (!gel) Fatal("computational element without geometric reference");
         const int topo = TopologyOf(gel->Type());
         const bool h1 = dynamic_cast<TPZCompElH1<pzshape::TPZShapeCube> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTetra> *>(cel) ||
-                        dynamic_cast<TPZCompElH1<pzshape::TPZShapeQuad> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTriang> *>(cel);
+                        dynamic_cast<TPZCompElH1<pzshape::TPZShapeQuad> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTriang> *>(cel) ||
+                        dynamic_cast<TPZCompElH1<pzshape::TPZShapeLinear> *>(cel);
         if (topo < 0 || !h1) Fatal("element " + std::to_string(iel) + " is not an H1 hexahedron/tetrahedron/quadrilateral/triangle");
         if (!gel->IsLinearMapping()) Fatal("element " + std::to_string(iel) + " has a non-(multi)linear geometric map");
         // uniform order, no constraints
@@ -298,6 +355,7 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
             if (isbc) g.meta.kind = B200ASM_BC;
             else if (dynamic_cast<TPZMatPoisson<STATE> *>(mat)) g.meta.kind = B200ASM_POISSON;
             else if (dynamic_cast<TPZElasticity3D *>(mat)) g.meta.kind = B200ASM_ELASTICITY3D;
+            else if (dynamic_cast<TPZElasticity2D *>(mat)) g.meta.kind = B200ASM_ELASTICITY2D;
             else Fatal("unsupported material id " + std::to_string(mat->Id()));
             if (auto *lc = dynamic_cast<TPZMatLoadCasesBase *>(mat))
                 if (lc->NumLoadCases() != 1) Fatal("more than one load case is not supported");
@@ -305,6 +363,7 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
                 case B200ASM_HEX: ShapeTables<pzshape::TPZShapeCube>(cel, porder, g); break;
                 case B200ASM_TET: ShapeTables<pzshape::TPZShapeTetra>(cel, porder, g); break;
                 case B200ASM_QUAD: ShapeTables<pzshape::TPZShapeQuad>(cel, porder, g); break;
+                case B200ASM_LINE: ShapeTables<pzshape::TPZShapeLinear>(cel, porder, g); break;
                 default: ShapeTables<pzshape::TPZShapeTriang>(cel, porder, g); break;
             }
         }

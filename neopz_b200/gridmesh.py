@@ -32,9 +32,10 @@ TET_SIDES = ([[i] for i in range(4)] + [[0, 1], [1, 2], [2, 0], [0, 3], [1, 3], 
              [[0, 1, 2], [0, 1, 3], [1, 2, 3], [0, 2, 3]] + [[0, 1, 2, 3]])
 QUAD_SIDES = [[i] for i in range(4)] + [[0, 1], [1, 2], [2, 3], [3, 0]] + [[0, 1, 2, 3]]
 TRI_SIDES = [[i] for i in range(3)] + [[0, 1], [1, 2], [2, 0]] + [[0, 1, 2]]
-SIDES = {capi.HEX: HEX_SIDES, capi.TET: TET_SIDES, capi.QUAD: QUAD_SIDES, capi.TRI: TRI_SIDES}
-NCORNER = {capi.HEX: 8, capi.TET: 4, capi.QUAD: 4, capi.TRI: 3}
-DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2}
+LINE_SIDES = [[0], [1], [0, 1]]
+SIDES = {capi.HEX: HEX_SIDES, capi.TET: TET_SIDES, capi.QUAD: QUAD_SIDES, capi.TRI: TRI_SIDES, capi.LINE: LINE_SIDES}
+NCORNER = {capi.HEX: 8, capi.TET: 4, capi.QUAD: 4, capi.TRI: 3, capi.LINE: 2}
+DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2, capi.LINE: 1}
 
 
 def side_nshape(topology, side_nodes, p):
@@ -304,6 +305,54 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
     if with_layers:
         return nodes, [tuple(b) for b in blocks]
     return nodes, [tuple(b[:3]) for b in blocks]
+
+
+def grid_elements_2d(n, triangles=False, bc_matids=(-1, -1, -1, -1), dom_matid=1, min_x=(0., 0.), max_x=(1., 1.), perturb=0.0):
+    """Nodes and element blocks of CreateGeoMeshOnGrid(2, minX, maxX, matids, {nx,ny}, type, createBoundEls=true)
+    (Mesh/TPZGeoMeshTools.cpp:186-199 with Pre/TPZGenGrid2D.cpp): node id iy*(nx+1)+ix at x0 + ix*((x1-x0)/nx) (:545-606),
+    quadrilaterals row by row (:625-636), two triangles (0,1,2), (0,2,3) per cell (:486-494), then the line elements of
+    the sides 4 (bottom), 5 (right), 6 (top), 7 (left) in that order (SetBC, :706-765).  bc_matids = matids[1..4]."""
+    nx, ny = (n, n) if np.isscalar(n) else n
+    sy = nx + 1
+    J, I = np.meshgrid(np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    I, J = I.reshape(-1), J.reshape(-1)
+    nodes = np.zeros((len(I), 3))
+    dx, dy = (max_x[0] - min_x[0]) / nx, (max_x[1] - min_x[1]) / ny
+    nodes[:, 0] = min_x[0] + I * dx
+    nodes[:, 1] = min_x[1] + J * dy
+    if perturb != 0.0:
+        h = 1.0 / nx
+        ids = (J * sy + I).astype(np.float64)
+        for d in range(2):  # plane meshes stay in z = 0 (oracle/refdriver.cpp)
+            nodes[:, d] += perturb * h * np.sin(2.0 * np.pi * ids / 97.0 + float(d))
+    ey, ex = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    ex, ey = ex.reshape(-1), ey.reshape(-1)
+    f = ey * sy + ex
+    cell = np.stack([f, f + 1, f + 1 + sy, f + sy], axis=1)  # [ncell][4]
+    blocks = []
+    if not triangles:
+        blocks.append([capi.QUAD, dom_matid, cell])
+    else:
+        tri = np.stack([cell[:, [0, 1, 2]], cell[:, [0, 2, 3]]], axis=1).reshape(-1, 3)
+        blocks.append([capi.TRI, dom_matid, tri])
+
+    def emit(matid, lines):
+        if blocks[-1][0] == capi.LINE and blocks[-1][1] == matid:
+            blocks[-1][2] = np.concatenate([blocks[-1][2], lines], axis=0)
+        else:
+            blocks.append([capi.LINE, matid, lines])
+    row0, rowl = cell[:nx], cell[nx * (ny - 1):]
+    col0, coll = cell[0::nx], cell[nx - 1::nx]
+    emit(bc_matids[0], row0[:, [0, 1]])   # side 4 of the bottom row
+    emit(bc_matids[1], coll[:, [1, 2]])   # side 5 of the last column
+    emit(bc_matids[2], rowl[:, [2, 3]])   # side 6 of the top row
+    emit(bc_matids[3], col0[:, [3, 0]])   # side 7 of the first column
+    return nodes, [tuple(b) for b in blocks]
+
+
+def grid_mesh_2d(n, porder, nstate, triangles=False, bc_matids=(-1,) * 4, perturb=0.0):
+    nodes, blocks = grid_elements_2d(n, triangles=triangles, bc_matids=bc_matids, perturb=perturb)
+    return flatten(nodes, blocks, porder, nstate)
 
 
 def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0, node_perm=None):

@@ -69,6 +69,43 @@ class TPZElasticity3D:
         return [self.C1, self.C2, self.C3] + self.fForce + self.fPreStress
 
 
+class TPZElasticity2D:
+    """Material/Elasticity/TPZElasticity2D.h: plane strain (default of the setters used here) or plane stress.  nstate 2.
+    The kernel takes the three constants of TPZElasticity2D.cpp:141-199: ek(2i+a,2j+b) = a==b ? cA D_aa + cB D_a'a'
+    : cC D_ab + cB D_ba."""
+    nstate = 2
+    kind = capi.ELASTICITY2D
+
+    def __init__(self, matid, E, poisson, fx, fy, planestress=False):
+        self.id = matid
+        self.fE, self.fPoisson = float(E), float(poisson)
+        self.ff = [float(fx), float(fy)]
+        self.fPlaneStress = bool(planestress)
+        self.fPreStress = [0.0, 0.0, 0.0]   # XX, XY, YY
+        self.fBigNumber = (10.0 ** 17) * 2 / 3
+
+    def SetPlaneStress(self):
+        self.fPlaneStress = True
+
+    def SetPlaneStrain(self):
+        self.fPlaneStress = False
+
+    def SetPreStress(self, sxx, syy, sxy, szz=0.0):
+        self.fPreStress = [float(sxx), float(sxy), float(syy)]
+
+    def CreateBC(self, matid, bctype, val1, val2):
+        return TPZBndCond(self, matid, bctype, val1, val2)
+
+    def coef(self):
+        E, nu = self.fE, self.fPoisson
+        if self.fPlaneStress:
+            cA, cB, cC = E / (1 - nu * nu), E / (2. * (1 + nu)), E / (1 - nu * nu) * nu
+        else:
+            F = E / ((1. + nu) * (1. - 2. * nu))
+            cA, cB, cC = (1. - nu) * F, (1. - 2. * nu) / 2. * F, nu * F
+        return [cA, cB, cC] + self.ff + self.fPreStress
+
+
 class TPZBndCond:
     """TPZBndCondT: type 0 Dirichlet (penalty), 1 Neumann; Elasticity3D also 2 mixed, 3 directional null Dirichlet,
     5-8 directional Dirichlet (x, y, z, x and z)."""
@@ -89,7 +126,18 @@ class TPZBndCond:
         ns = self.nstate
         M = np.zeros((3, 3))
         v = np.zeros(3)
-        if isinstance(self.material, TPZMatPoisson):
+        if isinstance(self.material, TPZElasticity2D):
+            big = self.material.fBigNumber   # TPZElasticity2D.cpp:219
+            if self.type == 0:      # :256-270
+                M[:ns, :ns] = np.eye(ns) * big
+                v[:ns] = big * self.val2[:ns]
+            elif self.type == 1:    # :273-283
+                v[:ns] = self.val2[:ns]
+            elif self.type == 3:    # :305-316 directional null Dirichlet
+                M[:ns, :ns] = np.diag(big * self.val2[:ns])
+            else:   # (type 2 crashes in the reference itself: sliced TPZMatLoadCasesBC copy, :220)
+                raise ValueError("TPZElasticity2D: boundary condition type %d not supported" % self.type)
+        elif isinstance(self.material, TPZMatPoisson):
             big = self.material.fBigNumber
             if self.type == 0:      # TPZMatPoisson.cpp:79-90
                 M[0, 0] = big
@@ -127,7 +175,7 @@ def element_tables(topology, porder, key=0):
     (Mesh/pzelctemp.cpp:35-47, Material/TPZMatSingleSpace.cpp:61-72); key = side-orientation class of the
     elements (capi.orientation_keys), relevant for p >= 3."""
     order = 2 * porder
-    if topology in (capi.HEX, capi.QUAD):
+    if topology in (capi.HEX, capi.QUAD, capi.LINE):
         qpts, qw = capi.tensor_rule(topology, order)
     else:
         z = np.load(os.path.join(_DATA, "simplex_rules.npz"))
@@ -176,8 +224,9 @@ class TPZStructMatrixB200:
                 raise KeyError(f"no material with id {b.matid}")
             if mat.nstate != mesh.nstate:
                 raise ValueError("material nstate does not match the mesh")
-            if (DIM[b.topology] == 3) == (mat.kind == capi.BC):
-                raise ValueError(f"material {b.matid}: volume/boundary kind does not match element dimension")
+            meshdim = max(DIM[x.topology] for x in mesh.blocks)
+            if (DIM[b.topology] == meshdim) == (mat.kind == capi.BC):
+                raise ValueError(f"material {b.matid}: domain/boundary kind does not match element dimension")
             # p >= 3: the shape functions of a side depend on the orientation of the side (global corner-node
             # indices): one group per orientation class of the block; p <= 2: one group per block
             keys = capi.orientation_keys(b.topology, b.elnodes) if mesh.porder >= 3 else np.zeros(len(b.elnodes), np.int64)

@@ -13,6 +13,7 @@
 #include <iostream>
 #include <thread>
 
+#include "Elasticity/TPZElasticity2D.h"
 #include "Elasticity/TPZElasticity3D.h"
 #include "Poisson/TPZMatPoisson.h"
 #include "TPZBndCondT.h"
@@ -33,26 +34,42 @@ static double secs(clk::time_point a, clk::time_point b) { return std::chrono::d
 
 // dirichlet: value imposed on matid -1.  The CG comparison uses 0: with a non-zero value the right-hand side norm
 // is ~1e16 (penalty), and a relative residual tolerance of 1e-15 no longer constrains the interior equations.
+// phys 2 / 3: TPZElasticity2D (plane strain / plane stress) on a plane mesh of quadrilaterals (tet = 0) or triangles
 static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, double dirichlet) {
+    const int dim = phys >= 2 ? 2 : 3;
     TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
-    TPZManVector<int, 7> matids(7, -1);
+    TPZManVector<int, 7> matids(dim == 3 ? 7 : 5, -1);
     matids[0] = 1;
-    matids[6] = -2;  // zmax: Neumann
-    TPZManVector<int, 3> ndiv(3, n);
-    TPZGeoMesh *gmesh = TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv,
-                                                             tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true);
+    matids[dim == 3 ? 6 : 3] = -2;  // zmax face / top side: Neumann
+    TPZManVector<int, 3> ndiv(dim, n);
+    TPZGeoMesh *gmesh = dim == 3
+        ? TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv, tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true)
+        : TPZGeoMeshTools::CreateGeoMeshOnGrid(2, minX, maxX, matids, ndiv, tet ? MMeshType::ETriangular : MMeshType::EQuadrilateral, true);
     if (perturb != 0.0) {
         const double h = 1.0 / n;
         for (int64_t i = 0; i < gmesh->NNodes(); i++)
-            for (int d = 0; d < 3; d++) {
+            for (int d = 0; d < dim; d++) {
                 TPZGeoNode &nd = gmesh->NodeVec()[i];
                 nd.SetCoord(d, nd.Coord(d) + perturb * h * std::sin(2.0 * M_PI * (double)i / 97.0 + (double)d));
             }
     }
     TPZCompMesh *cmesh = new TPZCompMesh(gmesh);
-    cmesh->SetDimModel(3);
+    cmesh->SetDimModel(dim);
     cmesh->SetDefaultOrder(p);
-    if (phys == 0) {
+    if (phys >= 2) {
+        auto *m = new TPZElasticity2D(1);
+        m->SetElasticity(1000., 0.3);
+        m->SetBodyForce(0.5, -1.0);
+        m->SetPreStress(0.2, -0.1, 0.05, 0.);
+        if (phys == 3) m->SetPlaneStress(); else m->SetPlaneStrain();
+        cmesh->InsertMaterialObject(m);
+        TPZFNMatrix<4, STATE> v1(2, 2, 0.);
+        TPZManVector<STATE, 2> v2(2, 0.), v2n(2, 0.);
+        v2[0] = dirichlet / 30.;
+        v2n[0] = 0.25; v2n[1] = -0.5;
+        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+    } else if (phys == 0) {
         auto *m = new TPZMatPoisson<STATE>(1, 3);
         // x-dependent source: exercises the host-evaluated forcing table
         m->SetForcingFunction([](const TPZVec<REAL> &x, TPZVec<STATE> &f) { f[0] = 1.0 + x[0] * x[1] - 0.5 * x[2]; }, 2);
@@ -220,7 +237,7 @@ int main(int argc, char **argv) {
     double errSolDev = 0;
     if (solve && symmetric) errSolDev = RelF(gpu.sol_device, ref.sol);
     const double errRes = RelF(gpu.residual_rhs, ref.residual_rhs), errResVsRhs = RelF(ref.residual_rhs, ref.rhs);
-    const int64_t nvol = (int64_t)n * n * n * (tet ? 5 : 1);
+    const int64_t nvol = phys >= 2 ? (int64_t)n * n * (tet ? 2 : 1) : (int64_t)n * n * n * (tet ? 5 : 1);
     const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
     std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"cpu_first_assemble_s\": " << t1

@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "refdriver")
 
-# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed])
+# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed[, dim]])
+# dim 2: plane meshes (TPZGenGrid2D); phys 0 = TPZMatPoisson(dim 2), 2 / 3 = TPZElasticity2D plane strain / plane stress
 # scramble != 0: node indices shuffled so that the side orientations differ from element to element (p >= 3)
 CASES = {
     "hex_p1_poisson_n3": (3, 1, 0, 0, 0.0, 0, 1),
@@ -38,6 +39,13 @@ CASES = {
     "hex_p2_elast_n2_bc3": (2, 2, 1, 0, 0.15, 3, 0, 0),
     "tet_p2_elast_n2_bc8": (2, 2, 1, 1, 0.15, 8, 0, 0),
     "hex_p1_elast_n2_bc6": (2, 1, 1, 0, 0.15, 6, 1, 0),
+    "quad_p2_elast2d_n3_pert": (3, 2, 2, 0, 0.15, 1, 1, 0, 2),
+    # (type 2 of TPZElasticity2D::ContributeBC crashes in the reference itself: sliced TPZMatLoadCasesBC copy, :220)
+    "quad_p1_elast2d_stress_n3_bc3": (3, 1, 3, 0, 0.15, 3, 1, 0, 2),
+    "tri_p2_elast2d_n3_pert": (3, 2, 2, 1, 0.15, 1, 1, 0, 2),
+    "tri_p1_elast2d_stress_n2_bc3": (2, 1, 3, 1, 0.15, 3, 1, 0, 2),
+    "quad_p2_poisson2d_n3_pert": (3, 2, 0, 0, 0.15, 1, 1, 0, 2),
+    "tri_p2_poisson2d_n3_pert": (3, 2, 0, 1, 0.15, 1, 1, 0, 2),
 }
 
 
@@ -50,9 +58,10 @@ def main():
             continue
         n, p, phys, tet, pert, bctype, elm = case[:7]
         scr = case[7] if len(case) > 7 else 0
+        dim = case[8] if len(case) > 8 else 3
         with tempfile.TemporaryDirectory() as d:
             subprocess.check_call([DRIVER, "dump", d, str(n), str(p), str(phys), str(tet), repr(pert),
-                                   str(bctype), str(elm), str(scr)], stdout=subprocess.DEVNULL)
+                                   str(bctype), str(elm), str(scr), str(dim)], stdout=subprocess.DEVNULL)
             arrays = {}
             for f in sorted(os.listdir(d)):
                 if f.endswith(".npy"):

@@ -17,7 +17,12 @@ NEUMANN_POISSON = 0.75
 NEUMANN_ELAST = (0.25, -0.5, 2.0)
 BC_VAL1 = np.array([[4.0, 0.5, 0.0], [0.5, 3.0, 0.25], [0.0, 0.25, 5.0]])
 BC_VAL2 = (0.3, -0.2, 0.7)
-TAGS = {orc.HEX: "hex", orc.TET: "tet", orc.QUAD: "quad", orc.TRI: "tri"}
+TAGS = {orc.HEX: "hex", orc.TET: "tet", orc.QUAD: "quad", orc.TRI: "tri", orc.LINE: "line"}
+# TPZElasticity2D of oracle/refdriver.cpp (phys 2 = plane strain, 3 = plane stress)
+E2D_FORCE = (0.5, -1.0)
+NEUMANN_ELAST2D = (0.25, -0.5)
+BC2D_VAL1 = np.array([[4.0, 0.5], [0.5, 3.0]])
+BC2D_VAL2 = (0.3, -0.2)
 
 
 def load(name):
@@ -32,6 +37,21 @@ def material_vector(g, topo, matid):
     phys = g["meta"]["phys"]
     big = float(g["meta"]["bignumber"])
     mat = np.zeros(16)
+    if phys >= 2:  # TPZElasticity2D
+        if matid == 1:
+            mat[0], mat[1], mat[2] = E_MOD, NU, 1.0 if phys == 3 else 0.0
+            mat[3:5] = E2D_FORCE
+            return orc.ELAST2D, 0, mat
+        bctype = 0 if matid == -1 else max(1, g["meta"]["bctype"])
+        mat[0] = big
+        if bctype == 1:
+            mat[10:12] = NEUMANN_ELAST2D
+        elif bctype >= 2:
+            v1 = np.zeros((3, 3))
+            v1[:2, :2] = BC2D_VAL1
+            mat[1:10] = v1.reshape(-1)
+            mat[10:12] = BC2D_VAL2
+        return orc.ELAST2D_BC, bctype, mat
     if matid == 1:
         if phys == 0:
             mat[0], mat[1] = 1.0, 1.0

@@ -11,7 +11,7 @@ _SIMPLEX = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__
 
 
 def _rule(topo, p):
-    if topo in (orc.HEX, orc.QUAD):
+    if topo in (orc.HEX, orc.QUAD, orc.LINE):
         return orc.rule(topo, 2 * p)
     z = np.load(_SIMPLEX)  # tables of the reference (tests/golden/make_simplex_rules.py)
     tag = "tet" if topo == orc.TET else "tri"
@@ -30,9 +30,17 @@ def _mat_vector(mat):
         m[3:6] = mat.fForce
         m[6:9] = mat.fPreStress
         return orc.ELAST3D, 0, m
+    if isinstance(mat, sm.TPZElasticity2D):
+        m[0], m[1], m[2] = mat.fE, mat.fPoisson, 1.0 if mat.fPlaneStress else 0.0
+        m[3:5] = mat.ff
+        m[5:8] = mat.fPreStress
+        return orc.ELAST2D, 0, m
     base = mat.material
     m[1:10] = mat.val1.reshape(-1)
     m[10:13] = mat.val2
+    if isinstance(base, sm.TPZElasticity2D):
+        m[0] = base.fBigNumber
+        return orc.ELAST2D_BC, mat.type, m
     if isinstance(base, sm.TPZMatPoisson):
         m[0] = base.fBigNumber
         m[13] = base.fScale

@@ -16,7 +16,9 @@ BIN = os.path.join(ROOT, "tests", "_bin", "dropin_test")
 # n, p, phys (0 Poisson / 1 Elasticity3D), tet, symmetric, solve
 CASES = [(6, 1, 0, 0, 1, 1), (5, 2, 0, 0, 1, 1), (4, 2, 1, 0, 1, 1), (4, 2, 0, 1, 1, 1), (3, 2, 1, 1, 1, 1),
          (4, 2, 0, 0, 0, 0), (3, 2, 1, 0, 0, 0), (5, 1, 1, 0, 1, 1),
-         (4, 3, 0, 0, 1, 1), (3, 4, 0, 0, 1, 1), (3, 3, 1, 0, 1, 0), (3, 4, 0, 0, 0, 0)]
+         (4, 3, 0, 0, 1, 1), (3, 4, 0, 0, 1, 1), (3, 3, 1, 0, 1, 0), (3, 4, 0, 0, 0, 0),
+         # phys 2 / 3: TPZElasticity2D plane strain / plane stress on plane meshes (quadrilaterals, triangles)
+         (8, 2, 2, 0, 1, 1), (6, 2, 3, 1, 1, 1), (7, 1, 2, 1, 0, 0), (6, 1, 3, 0, 1, 1)]
 
 
 @pytest.mark.parametrize("device_create", [0, 1])

@@ -34,6 +34,23 @@ def fixture_setup(g):
     """(mesh, materials) of a committed reference fixture: oracle/refdriver.cpp's recipe."""
     m = g["meta"]
     bct = m["bctype"]
+    if m.get("dim", 3) == 2:  # plane meshes: TPZMatPoisson(dim 2) / TPZElasticity2D, line elements on the boundary
+        mesh = gridmesh.grid_mesh_2d(m["n"], m["p"], 2 if m["phys"] >= 2 else 1, triangles=bool(m["tet"]),
+                                     bc_matids=(-1, -1, -2 if bct >= 1 else -1, -1), perturb=m["perturb"])
+        if m["phys"] >= 2:
+            mat = sm.TPZElasticity2D(1, gu.E_MOD, gu.NU, *gu.E2D_FORCE, planestress=m["phys"] == 3)
+            mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((2, 2)), np.zeros(2))}
+            if bct == 1:
+                mats[-2] = mat.CreateBC(-2, 1, np.zeros((2, 2)), gu.NEUMANN_ELAST2D)
+            elif bct >= 2:
+                mats[-2] = mat.CreateBC(-2, bct, gu.BC2D_VAL1, gu.BC2D_VAL2)
+        else:
+            mat = sm.TPZMatPoisson(1, 2)
+            mat.SetForcingFunction(1.0)
+            mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.0])}
+            if bct >= 1:
+                mats[-2] = mat.CreateBC(-2, 1, [[0.0]], [gu.NEUMANN_POISSON])
+        return mesh, mats
     bc = (-1, -1, -1, -1, -1, -2 if bct >= 1 else -1)
     mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
                               bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
@@ -197,6 +214,39 @@ def test_elasticity_bc_types(bctype, tet, p):
         strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
         ia, ja, a, rhs = strmat.CreateAssemble()
         a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+
+
+@pytest.mark.parametrize("n,p,tri,planestress,scatter", [(7, 2, 0, 0, "atomic"), (6, 2, 1, 1, "atomic"), (9, 1, 0, 1, "colored"),
+                                                          (8, 1, 1, 0, "atomic"), (5, 2, 0, 1, "colored")])
+def test_plane_elasticity_against_oracle(n, p, tri, planestress, scatter):
+    """TPZElasticity2D (Material/Elasticity/TPZElasticity2D.cpp:86-203) on plane meshes, with prestress, Dirichlet /
+    Neumann / directional-null-Dirichlet sides (line elements), symmetric and full storage."""
+    mesh = gridmesh.grid_mesh_2d(n, p, 2, triangles=bool(tri), bc_matids=(-1, -3, -2, -1), perturb=0.12)
+    mat = sm.TPZElasticity2D(1, gu.E_MOD, gu.NU, 0.5, -1.0, planestress=bool(planestress))
+    mat.SetPreStress(0.2, -0.1, 0.05)
+    mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((2, 2)), [0.01, -0.02]), -2: mat.CreateBC(-2, 1, np.zeros((2, 2)), [0.25, -0.5]),
+            -3: mat.CreateBC(-3, 3, np.zeros((2, 2)), [1.0, 0.0])}
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, scatter=scatter)
+        ia, ja, a, rhs = strmat.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+        a2, rhs2 = strmat.Assemble()
+        assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
+        assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+
+
+@pytest.mark.parametrize("n,p,tri", [(8, 2, 0), (7, 2, 1), (10, 1, 0), (9, 1, 1)])
+def test_plane_poisson_against_oracle(n, p, tri):
+    """TPZMatPoisson(dim 2) on plane meshes."""
+    mesh = gridmesh.grid_mesh_2d(n, p, 1, triangles=bool(tri), bc_matids=(-1, -1, -2, -1), perturb=0.12)
+    mat = sm.TPZMatPoisson(1, 2)
+    mat.SetForcingFunction(1.5)
+    mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.25]), -2: mat.CreateBC(-2, 1, [[0.0]], [0.75])}
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+        ia, ja, a, rhs = strmat.CreateAssemble(); a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
         assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
 
 

@@ -6,7 +6,7 @@ import pytest
 from neopz_b200 import capi, strmatrix
 from tests import golden_util as gu
 
-TOPO = {"hex": capi.HEX, "tet": capi.TET, "quad": capi.QUAD, "tri": capi.TRI}
+TOPO = {"hex": capi.HEX, "tet": capi.TET, "quad": capi.QUAD, "tri": capi.TRI, "line": capi.LINE}
 
 
 @pytest.mark.parametrize("name", gu.ALL_CASES)
