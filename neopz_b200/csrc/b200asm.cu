@@ -914,6 +914,9 @@ using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
 using HexP2ElastTeamV1 = TeamCfg<8, 27, 3, 5, 1, 2>;   // two tile groups per warp (154 registers, 10 warps/SM)
 using HexP2ElastTeamV2 = TeamCfg<8, 27, 3, 10, 1, 3>;
 // higher-order Poisson: one warp per 4x4 superblock of 8x8 tiles (p=3: 8x8 tiles -> 3 warps; p=4: 16x16 -> 10 warps)
+using HexP2PoissonTeamV4 = TeamCfg<8, 27, 1, 3, 4, 2, 2>;   // 3 warps per element (2x2-tile superblocks), 4 elements per CTA
+using HexP2PoissonTeamV5 = TeamCfg<8, 27, 1, 3, 4, 3, 2>;
+using HexP2PoissonTeamV6 = TeamCfg<8, 27, 1, 3, 8, 1, 2>;
 using HexP3PoissonTeam = TeamCfg<8, 64, 1, 3, 2, 3, 4>;
 using HexP4PoissonTeam = TeamCfg<8, 125, 1, 10, 1, 2, 4>;
 
@@ -945,6 +948,8 @@ const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_m
                          make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
                          make_mma_entry<HexP2PoissonMmaV1>(B200ASM_HEX, 2, 1), make_mma_entry<HexP2PoissonMmaV2>(B200ASM_HEX, 2, 2),
                          make_mma_entry<HexP2PoissonMmaV3>(B200ASM_HEX, 2, 3),
+                         make_team_entry<HexP2PoissonTeamV4>(B200ASM_HEX, 2, 4), make_team_entry<HexP2PoissonTeamV5>(B200ASM_HEX, 2, 5),
+                         make_team_entry<HexP2PoissonTeamV6>(B200ASM_HEX, 2, 6),
                          make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 0), make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1),
                          make_team_entry<TetP2ElastTeamV3>(B200ASM_TET, 2, 3), make_team_entry<TetP2ElastTeamV4>(B200ASM_TET, 2, 4),
                          make_team_entry<TetP2ElastTeamV5>(B200ASM_TET, 2, 5), make_team_entry<TetP2ElastTeamV6>(B200ASM_TET, 2, 6),
