@@ -63,7 +63,9 @@ typedef struct {
     int32_t nstate;   /* TPZMaterial::NStateVariables(): 1 or 3 */
     int64_t nel;
     const int32_t *elnodes; /* [nel][ncorner] indices into the node table (TPZGeoEl::NodeIndex) */
-    const int64_t *dest;    /* [nel][nshape*nstate] TPZElementMatrix::fDestinationIndex, Mesh/pzelmat.cpp:37-70 */
+    const int64_t *dest;    /* [nel][nshape*nstate] TPZElementMatrix::fDestinationIndex, Mesh/pzelmat.cpp:37-70; with an active
+                               TPZEquationFilter the filtered (condensed) index, -1 for removed equations
+                               (TPZEquationFilter::Filter, StrMatrix/TPZEquationFilter.h:120-141) */
     int32_t nqp;            /* points of the TPZIntPoints rule of order 2p (Mesh/pzelctemp.cpp:35-47) */
     int32_t nshape;         /* H1 shape functions per element */
     const double *qpts;     /* [nqp][dim]  TPZIntPoints::Point */

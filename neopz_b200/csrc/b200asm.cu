@@ -87,6 +87,10 @@ __device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) 
     else if (v == 1.2345e300) *addr = v;
 }
 
+// load-vector entry: destination -1 = equation removed by the equation filter (StrMatrix/TPZEquationFilter.h:120-141)
+__device__ __forceinline__ void scatter_rhs(double *rhs, int32_t d, double v, int atomic) {
+    if (d >= 0) scatter_add(rhs + d, v, atomic);
+}
 // predicated reduction: no branch around the red (a divergent `if (pos >= 0) atomicAdd` costs BSSY/BRA/BSYNC per entry)
 __device__ __forceinline__ void red_if_valid(double *a, int32_t pos, double v) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\t@p red.global.add.f64 [%0], %2;\n\t}" ::"l"(a + pos), "r"(pos), "d"(v) : "memory");
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(C::NTHREADS) assemble_volume_kernel(const VolP
 #pragma unroll
         for (int k = 0; k < FPT; k++) {
             const int it = tid + k * NTHREADS;
-            if (it < nloc * M) scatter_add(p.rhs + p.dest[e0 * M + it], facc[k], p.atomic);
+            if (it < nloc * M) scatter_rhs(p.rhs, p.dest[e0 * M + it], facc[k], p.atomic);
         }
     }
 }
@@ -351,6 +355,7 @@ __global__ void build_volume_smap_kernel(int64_t nel, int64_t nbatch, const int3
         if (el < nel && i < M && j < M && i <= j) {
             const int64_t di = dest[el * M + i], dj = dest[el * M + j];
             auto find = [&](int64_t row, int64_t col) -> int32_t {
+                if (row < 0 || col < 0) return -1;  // equation removed by the TPZEquationFilter: no slot, not an error
                 int64_t lo = ia[row], hi = ia[row + 1] - 1;
                 while (lo <= hi) {
                     const int64_t mid = (lo + hi) >> 1;
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(128) assemble_bc_kernel(const BcParams p) {
 #pragma unroll
         for (int a = 0; a < NS; a++) {
             const double v = p.coef[9 + a];
-            if (v != 0.0) scatter_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T[i], p.atomic);
+            if (v != 0.0) scatter_rhs(p.rhs, p.dest[el * (N * NS) + i * NS + a], v * T[i], p.atomic);
         }
 }
 
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
         for (int q = 0; q < p.nq; q++) T += __ldg(p.phi + (size_t)q * N + i) * W[q];
         for (int a = 0; a < NS; a++) {
             const double v = p.coef[9 + a];
-            if (v != 0.0) scatter_add(p.rhs + p.dest[el * (N * NS) + i * NS + a], v * T, p.atomic);
+            if (v != 0.0) scatter_rhs(p.rhs, p.dest[el * (N * NS) + i * NS + a], v * T, p.atomic);
         }
     }
 }
@@ -676,12 +681,12 @@ __global__ void __launch_bounds__(128) assemble_plane_kernel(const BcParams p, i
             gy += SW[q] * G[((size_t)q * N + i) * 2 + 1];
         }
         if (NS == 1) {
-            scatter_add(p.rhs + p.dest[el * N + i], p.coef[0] * p.coef[1] * t, p.atomic);
+            scatter_rhs(p.rhs, p.dest[el * N + i], p.coef[0] * p.coef[1] * t, p.atomic);
         } else {
             // ef(2i) += w (fx phi - du_x sxx - du_y sxy) ; ef(2i+1) += w (fy phi - du_x sxy - du_y syy)
             const double fx = p.coef[3], fy = p.coef[4], sxx = p.coef[5], sxy = p.coef[6], syy = p.coef[7];
-            scatter_add(p.rhs + p.dest[el * (N * 2) + i * 2], fx * t - gx * sxx - gy * sxy, p.atomic);
-            scatter_add(p.rhs + p.dest[el * (N * 2) + i * 2 + 1], fy * t - gx * sxy - gy * syy, p.atomic);
+            scatter_rhs(p.rhs, p.dest[el * (N * 2) + i * 2], fx * t - gx * sxx - gy * sxy, p.atomic);
+            scatter_rhs(p.rhs, p.dest[el * (N * 2) + i * 2 + 1], fy * t - gx * sxy - gy * syy, p.atomic);
         }
     }
 }
@@ -702,6 +707,7 @@ __global__ void build_bc_smap_kernel(int64_t nel, int n, int ns, const int32_t *
         if (i < j || (i == j && a <= b)) {
             const int64_t di = dest[el * m + i * ns + a], dj = dest[el * m + j * ns + b];
             auto find = [&](int64_t row, int64_t col) -> int32_t {
+                if (row < 0 || col < 0) return -1;  // equation removed by the TPZEquationFilter: no slot, not an error
                 int64_t lo = ia[row], hi = ia[row + 1] - 1;
                 while (lo <= hi) {
                     const int64_t mid = (lo + hi) >> 1;
@@ -1004,18 +1010,20 @@ int ncorner_of(int topology) {
 int colour_elements(int64_t nel, int m, const int64_t *dest, int64_t neq_hint, std::vector<int32_t> &colour) {
     int64_t neq = neq_hint;
     for (int64_t k = 0; k < nel * m; k++) neq = std::max<int64_t>(neq, dest[k] + 1);
-    std::vector<uint64_t> used((size_t)neq, 0);
+    std::vector<uint64_t> used((size_t)neq + 1, 0);
+    uint64_t *usedp = used.data() + 1;  // index -1 (filtered equations) is a harmless scratch slot
     colour.assign((size_t)nel, 0);
     int ncol = 0;
     for (int64_t el = 0; el < nel; el++) {
         uint64_t u = 0;
-        for (int k = 0; k < m; k++) u |= used[dest[el * m + k]];
+        for (int k = 0; k < m; k++)
+            if (dest[el * m + k] >= 0) u |= usedp[dest[el * m + k]];
         if (~u == 0) return -1;
         const int c = __builtin_ctzll(~u);
         colour[el] = c;
         ncol = std::max(ncol, c + 1);
         const uint64_t bit = 1ull << c;
-        for (int k = 0; k < m; k++) used[dest[el * m + k]] |= bit;
+        for (int k = 0; k < m; k++) usedp[dest[el * m + k]] |= bit;
     }
     return ncol;
 }
@@ -1241,8 +1249,8 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     for (int64_t e = 0; e < g.nel; e++) {
         const int64_t src = order[e];
         for (int k = 0; k < g.m; k++) {
-            const int64_t d = gi->dest[src * g.m + k];
-            if (d < 0 || d > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "add_group: destination index out of int32 range");
+            const int64_t d = gi->dest[src * g.m + k];  // -1: equation removed by the equation filter
+            if (d < -1 || d > 0x7fffffff) return fail(ctx, B200ASM_EINVAL, "add_group: destination index out of int32 range");
             dest32[(size_t)e * g.m + k] = (int32_t)d;
             g.max_dest = std::max(g.max_dest, d);
         }

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_gram_mma_kernel
                 }
             }
             const double f = (f0 + f1 + f2) * p.coef[0] * (p.force ? 1.0 : p.coef[1]);
-            scatter_add(p.rhs + p.dest[el * N + lane], f, p.atomic);
+            scatter_rhs(p.rhs, p.dest[el * N + lane], f, p.atomic);
         }
 
         double acc[NTILES][2];
@@ -251,6 +251,7 @@ __global__ void build_mma_smap_kernel(int64_t nel, const int32_t *__restrict__ d
         if (i < N && j < N && i <= j) {
             const int64_t di = dest[el * N + i], dj = dest[el * N + j];
             auto find = [&](int64_t row, int64_t col) -> int32_t {
+                if (row < 0 || col < 0) return -1;  // equation removed by the TPZEquationFilter: no slot, not an error
                 int64_t lo = ia[row], hi = ia[row + 1] - 1;
                 while (lo <= hi) {
                     const int64_t mid = (lo + hi) >> 1;

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
 #pragma unroll
         for (int k = 0; k < FPT; k++) {
             const int m = tt + k * TT;
-            if (m < M) scatter_add(p.rhs + p.dest[el * M + m], facc[k], p.atomic);
+            if (m < M) scatter_rhs(p.rhs, p.dest[el * M + m], facc[k], p.atomic);
         }
         if (!p.rhs_only) TeamRole<C, 0>::epilogue(w, p, el, acc, lane);
     }
@@ -393,6 +393,7 @@ __global__ void build_team_smap_kernel(int64_t nel, const int32_t *__restrict__ 
                 const int i = in * NS + a, j = jn * NS + b;
                 const int64_t di = dest[el * M + i], dj = dest[el * M + j];
                 auto find = [&](int64_t row, int64_t col) -> int32_t {
+                    if (row < 0 || col < 0) return -1;  // equation removed by the TPZEquationFilter: no slot, not an error
                     int64_t lo = ia[row], hi = ia[row + 1] - 1;
                     while (lo <= hi) {
                         const int64_t mid = (lo + hi) >> 1;

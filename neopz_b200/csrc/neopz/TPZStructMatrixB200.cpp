@@ -137,6 +137,7 @@ struct TPZB200AssemblyCache {
     b200asm_ctx *ctx = nullptr;
     TPZCompMesh *mesh = nullptr;
     int64_t nelem = -1, neq = -1, nconnects = -1, nnz = -1;
+    int64_t nactive = -1;  // equations of the assembled system: NEquations(), or NActiveEquations() of an active filter
     int symmetric = -1;
     bool pattern_set = false;
     std::vector<HostGroup> groups;
@@ -304,6 +305,18 @@ void FillForce(HostGroup &g) {
 void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
     TPZCompMesh *cmesh = strmat->Mesh();
     c.groups.clear();
+    // active equation filter (StrMatrix/TPZEquationFilter.h): destination indices become the condensed numbers, removed
+    // equations get -1 — what TPZEquationFilter::Filter does per element in the reference (pzstrmatrixor.cpp:205-214)
+    std::vector<int64_t> eqmap;
+    const TPZEquationFilter &filter = strmat->EquationFilter();
+    if (filter.IsActive()) {
+        const int64_t neq = cmesh->NEquations();
+        TPZVec<int64_t> orig(neq), dest(neq);
+        for (int64_t i = 0; i < neq; i++) orig[i] = dest[i] = i;
+        filter.Filter(orig, dest);
+        eqmap.assign(neq, -1);
+        for (int64_t k = 0; k < orig.size(); k++) eqmap[orig[k]] = dest[k];
+    }
     std::map<GroupKey, size_t> index;
     const int64_t nel = cmesh->NElements();
     for (int64_t iel = 0; iel < nel; iel++) {
@@ -378,7 +391,7 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
             const int64_t seq = con.SequenceNumber();
             const int64_t first = cmesh->Block().Position(seq);
             const int ndf = cmesh->Block().Size(seq);
-            for (int idf = 0; idf < ndf; idf++) g.dest.push_back(first + idf);
+            for (int idf = 0; idf < ndf; idf++) g.dest.push_back(eqmap.empty() ? first + idf : eqmap[first + idf]);
             ndof += ndf;
         }
         if (ndof != g.meta.nshape * g.meta.nstate) Fatal("element " + std::to_string(iel) + ": unexpected number of equations");
@@ -407,6 +420,7 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
     c.mesh = cmesh;
     c.nelem = nel;
     c.neq = cmesh->NEquations();
+    c.nactive = filter.IsActive() ? filter.NActiveEquations() : c.neq;
     c.nconnects = cmesh->NConnects();
     c.pattern_set = false;
 }
@@ -422,7 +436,10 @@ void PrepareMesh(TPZB200AssemblyCache &c, TPZStructMatrix *strmat, int device) {
     }
     auto t0 = clk::now();
     c.flatten_ms = 0;
-    if (c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects()) {
+    const TPZEquationFilter &filter = strmat->EquationFilter();
+    const int64_t nactive = filter.IsActive() ? filter.NActiveEquations() : cmesh->NEquations();
+    if (c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects() ||
+        c.nactive != nactive) {
         Flatten(c, strmat);
         c.flatten_ms = ms_since(t0);
         return;
@@ -471,7 +488,7 @@ template <class TVar>
 void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) {
     auto *strmat = dynamic_cast<TPZStructMatrix *>(this);
     if (!strmat) Fatal("the strategy must be combined with a TPZStructMatrix");
-    if (strmat->EquationFilter().IsActive()) Fatal("an active equation filter is not supported yet");
+    const TPZEquationFilter &filter = strmat->EquationFilter();
     auto *rhsmat = dynamic_cast<TPZFMatrix<STATE> *>(&rhs);
     auto *sym = dynamic_cast<TPZSYsmpMatrix<STATE> *>(&stiffness);
     auto *full = dynamic_cast<TPZFYsmpMatrix<STATE> *>(&stiffness);
@@ -515,16 +532,21 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     t0 = clk::now();
     const int64_t neq = rhsmat->Rows();
     if (neq != c.neq || rhsmat->Cols() != 1) Fatal("rhs has the wrong size (one load case, NEquations rows)");
-    std::vector<double> rhsloc;
+    if (stiffness.Rows() != c.nactive) Fatal("the matrix does not have NActiveEquations rows");
+    TPZFMatrix<STATE> rhsloc;  // condensed numbering when the filter is active
     double *rhsptr = nullptr;
     if (ComputeRhs()) {
-        rhsloc.resize(neq);
-        rhsptr = rhsloc.data();
+        rhsloc.Redim(c.nactive, 1);
+        rhsptr = &rhsloc(0, 0);
     }
     Check(c, b200asm_assemble(c.ctx, values, rhsptr), "b200asm_assemble");
     if (rhsptr) {
-        double *dst = &(*rhsmat)(0, 0);
-        for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc[i];
+        if (filter.IsActive()) {
+            filter.Scatter(rhsloc, rhs);  // StrMatrix/pzstrmatrixor.cpp:47-62
+        } else {
+            double *dst = &(*rhsmat)(0, 0);
+            for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc(i, 0);  // the reference adds into rhs (TPZFMatrix::AddFel)
+        }
     }
     c.assemble_ms = ms_since(t0);
 }
@@ -536,7 +558,7 @@ template <class TVar>
 void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZGuiInterface> guiInterface) {
     auto *strmat = dynamic_cast<TPZStructMatrix *>(this);
     if (!strmat) Fatal("the strategy must be combined with a TPZStructMatrix");
-    if (strmat->EquationFilter().IsActive()) Fatal("an active equation filter is not supported yet");
+    const TPZEquationFilter &filter = strmat->EquationFilter();
     auto *rhsmat = dynamic_cast<TPZFMatrix<STATE> *>(&rhs);
     if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
     TPZB200AssemblyCache &c = *fCache;
@@ -545,10 +567,14 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZG
     auto t0 = clk::now();
     const int64_t neq = rhsmat->Rows();
     if (neq != c.neq || rhsmat->Cols() != 1) Fatal("rhs has the wrong size (one load case, NEquations rows)");
-    std::vector<double> rhsloc(neq);
-    Check(c, b200asm_assemble_rhs(c.ctx, rhsloc.data()), "b200asm_assemble_rhs");
-    double *dst = &(*rhsmat)(0, 0);
-    for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc[i];  // the reference ADDS into rhs (TPZFMatrix::AddFel)
+    TPZFMatrix<STATE> rhsloc(c.nactive, 1, 0.);
+    Check(c, b200asm_assemble_rhs(c.ctx, &rhsloc(0, 0)), "b200asm_assemble_rhs");
+    if (filter.IsActive()) {
+        filter.Scatter(rhsloc, rhs);  // StrMatrix/pzstrmatrixor.cpp:79-99
+    } else {
+        double *dst = &(*rhsmat)(0, 0);
+        for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc(i, 0);  // the reference ADDS into rhs (TPZFMatrix::AddFel)
+    }
     c.assemble_ms = ms_since(t0);
 }
 
@@ -560,8 +586,8 @@ void TPZStructMatrixB200<TVar>::SolveCG(const TPZFMatrix<TVar> &F, TPZFMatrix<TV
     TPZB200AssemblyCache &c = *fCache;
     if (!c.ctx || !c.pattern_set) Fatal("SolveCG: Assemble(stiffness, rhs) must run first (the matrix lives on the device)");
     if constexpr (std::is_same<TVar, double>::value) {
-        if (F.Rows() != c.neq || F.Cols() != 1) Fatal("SolveCG: F has the wrong size");
-        if (!fromcurrent || result.Rows() != c.neq || result.Cols() != 1) result.Redim(c.neq, 1);
+        if (F.Rows() != c.nactive || F.Cols() != 1) Fatal("SolveCG: F has the wrong size");
+        if (!fromcurrent || result.Rows() != c.nactive || result.Cols() != 1) result.Redim(c.nactive, 1);
         int64_t iters = 0;
         double resid = 0;
         Check(c, b200asm_cg_solve(c.ctx, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid),
@@ -607,7 +633,8 @@ void TPZStructMatrixB200<TVar>::CreatePatternOnDevice(bool symmetric, TPZStack<i
                                                       TPZVec<int64_t> &ia, TPZVec<int64_t> &ja) {
     auto *strmat = dynamic_cast<TPZStructMatrix *>(this);
     if (!strmat) Fatal("the strategy must be combined with a TPZStructMatrix");
-    if (strmat->EquationFilter().IsActive()) Fatal("an active equation filter is not supported yet");
+    if (strmat->EquationFilter().IsActive())
+        Fatal("Create() on the device does not support an active equation filter: use TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>");
     TPZCompMesh *cmesh = strmat->Mesh();
     TPZB200AssemblyCache &c = *fCache;
     if (!c.ctx) {

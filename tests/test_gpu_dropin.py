@@ -43,3 +43,19 @@ def test_dropin_strategy_matches_reference(case, device_create):
     # N3: TPZLinearAnalysis::AssembleResidual() -> Assemble(rhs) on the device vs TPZStructMatrixOR
     assert r["relF_residual_rhs"] <= 1e-12
     assert out.returncode == 0
+
+
+@pytest.mark.parametrize("case", [(5, 2, 0, 0, 1, 0), (4, 2, 1, 0, 1, 0), (4, 2, 1, 1, 0, 0), (3, 3, 0, 0, 1, 0), (8, 2, 2, 0, 1, 0)])
+def test_dropin_with_equation_filter(case):
+    """Active TPZEquationFilter (SetMinMaxEq: the upper three quarters of the equations): condensed matrix and scattered rhs
+    of the B200 strategy vs TPZStructMatrixOR (StrMatrix/pzstrmatrixor.cpp:41-62, TPZEquationFilter.h:120-141)."""
+    if not os.path.exists(BIN):
+        pytest.skip("tests/_bin/dropin_test not built (needs /root/reference at build time)")
+    out = subprocess.run([BIN] + [str(x) for x in case] + ["4", "0", "1"], capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(lines[-1])
+    assert r["equation_filter"] == 1
+    assert r["ia_identical"] == 1 and r["ja_identical"] == 1
+    assert r["relF_A"] <= 1e-12 and r["relF_rhs"] <= 1e-12 and r["relF_residual_rhs"] <= 1e-12
+    assert out.returncode == 0

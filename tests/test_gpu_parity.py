@@ -250,6 +250,36 @@ def test_plane_poisson_against_oracle(n, p, tri):
         assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
 
 
+@pytest.mark.parametrize("n,p,phys,tet,engine", [(4, 2, 0, 0, 1), (3, 2, 1, 0, 1), (3, 2, 1, 1, 1), (4, 1, 0, 1, 0), (3, 3, 0, 0, 1)])
+def test_filtered_equations(n, p, phys, tet, engine):
+    """Destination index -1 = equation removed by a TPZEquationFilter (TPZEquationFilter::Filter,
+    StrMatrix/TPZEquationFilter.h:120-141): the condensed system of the upper three quarters of the equations equals
+    the corresponding rows / columns of the full assembly."""
+    import copy
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    mats = materials_for(phys, neumann=True)
+    idx, graph = mesh.element_graph()
+    ia, ja = capi.build_pattern(True, idx, graph, mesh.block_pos, mesh.block_size, 0)
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    lo = mesh.neq // 4
+    cond = copy.copy(mesh)
+    cond.blocks = []
+    for b in mesh.blocks:
+        b2 = copy.copy(b)
+        b2.dest = np.where(b.dest >= lo, b.dest - lo, -1)
+        cond.blocks.append(b2)
+    cond.neq = mesh.neq - lo
+    # symmetric upper storage: the rows >= lo only hold columns >= lo, so the condensed pattern is a slice
+    ia_c = ia[lo:] - ia[lo]
+    ja_c = ja[ia[lo]:] - lo
+    for scatter in ("atomic", "colored"):
+        strmat = sm.TPZStructMatrixB200(cond, mats, symmetric=True, engine=engine, scatter=scatter)
+        strmat.SetPattern(ia_c, ja_c)
+        a, rhs = strmat.Assemble()
+        assert relF(a, a_ref[ia[lo]:]) <= TOL and relF(rhs, rhs_ref[lo:]) <= TOL
+        assert relF(strmat.AssembleRhs(), rhs_ref[lo:]) <= TOL
+
+
 def _shuffled(n, seed):
     """Random renumbering of the (n+1)^3 grid nodes: every element gets its own side orientations (p >= 3)."""
     return np.random.default_rng(seed).permutation((n + 1) ** 3)
