@@ -89,7 +89,9 @@ const char *b200asm_last_error(const b200asm_ctx *ctx); /* ctx may be NULL: last
 /* run on an existing CUDA stream (cudaStream_t passed as void*); default: a stream the context owns */
 int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
 /* integer options: "scatter" (B200ASM_SCATTER_*), "engine" (0 register-tile DFMA kernels, 1 DMMA kernels where one
- * exists), "timing" (1: CUDA events around every group's kernel launches, read by b200asm_group_time_ms) */
+ * exists), "timing" (1: CUDA events around every group's kernel launches, read by b200asm_group_time_ms),
+ * "overlap" (default 1: b200asm_assemble with a host matrix copies the finished rows of A back while later element
+ * chunks are still being assembled; "overlap_min_elements" (before add_group) and "overlap_min_bytes" tune the chunking) */
 int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);
 
 /* ---- flattened mesh ---------------------------------------------------------------------- */
@@ -122,7 +124,10 @@ int b200asm_get_ja_range(b200asm_ctx *ctx, int64_t first, int64_t count, int64_t
 /* ---- assembly -----------------------------------------------------------------------------
  * Zeroes A and rhs on the device, runs every group (CalcStiff + AddKel + AddFel of
  * StrMatrix/pzstrmatrixor.cpp:157-250 for all elements at once) and, when the host pointers are
- * non-NULL, copies the result back: a_host[nnz] in CSR order, rhs_host[neq].  Synchronous. */
+ * non-NULL, copies the result back: a_host[nnz] in CSR order, rhs_host[neq].  Synchronous.  With atomic scatter the
+ * download of A overlaps the kernels: large groups run in element chunks and every row that no later chunk can touch
+ * (rows below the smallest destination equation of the remaining elements) is copied on a second stream at once
+ * (only when a_host is page-locked: cudaHostAlloc / cudaHostRegister; pageable memory takes the plain path). */
 int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_host);
 /* Load vector only: TPZStrMatParInterface::Assemble(rhs) (StrMatrix/TPZStrMatParInterface.h:47-48; the reference's
  * CalcResidual path Mesh/pzinterpolationspace.cpp:476-527, which for these linear materials evaluates the same ef as

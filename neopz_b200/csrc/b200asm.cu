@@ -753,6 +753,10 @@ struct Group {
     // ({0, nel} when not coloured); seg_smap = offset of every segment's scatter map (register-tile kernels)
     std::vector<int64_t> seg;
     std::vector<size_t> seg_smap;
+    // overlapped download (b200asm_assemble with a host matrix): element chunks of a large uncoloured group and the
+    // smallest destination equation of every chunk (rows below the minimum of all LATER launches are final)
+    std::vector<int64_t> chunk;
+    std::vector<int64_t> chunk_min;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // "timing" option: events around this group's launches
 };
 
@@ -786,6 +790,13 @@ struct b200asm_ctx {
     int variant = 0;   // tuning alternative of the DMMA kernels (option "variant", before add_group)
     int rhs_only = 0;  // set while b200asm_assemble_rhs runs
     int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
+    int overlap = 1;  // 1: b200asm_assemble downloads the finished rows of A while later element chunks are assembled
+    int64_t overlap_min_elements = 8192;      // smallest element chunk (option, before add_group)
+    int64_t overlap_min_bytes = 32 << 20;     // smallest piece of A worth its own copy (option)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
+    std::vector<int64_t> ov_upto;  // IA at the download frontiers of assemble_overlapped (valid while ov_valid)
+    bool ov_valid = false;
     std::string err;
 };
 
@@ -1086,6 +1097,7 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
         return fail(ctx, B200ASM_EPATTERN, "scatter map: " + std::to_string(missing) +
                                                " element entries have no position in the CSR pattern");
     ctx->maps_valid = true;
+    ctx->ov_valid = false;
     return 0;
 }
 
@@ -1128,6 +1140,8 @@ extern "C" void b200asm_destroy(b200asm_ctx *ctx) {
     cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
     cudaFree(ctx->d_cg); cudaFree(ctx->d_cg_part); cudaFree(ctx->d_cg_sc);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -1166,6 +1180,21 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
     }
     if (!strcmp(name, "timing")) {
         ctx->timing = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "overlap")) {
+        ctx->overlap = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "overlap_min_elements")) {
+        if (value < 1) return fail(ctx, B200ASM_EINVAL, "overlap_min_elements: must be positive");
+        if (!ctx->groups.empty()) return fail(ctx, B200ASM_ESTATE, "overlap_min_elements: set it before the first b200asm_add_group");
+        ctx->overlap_min_elements = value;
+        return 0;
+    }
+    if (!strcmp(name, "overlap_min_bytes")) {
+        if (value < 0) return fail(ctx, B200ASM_EINVAL, "overlap_min_bytes: must not be negative");
+        ctx->overlap_min_bytes = value;
         return 0;
     }
     return fail(ctx, B200ASM_EINVAL, std::string("unknown option ") + name);
@@ -1216,14 +1245,15 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
                 g.mma = k;
     } else if (g.plane) {
-        if (gi->porder > 2) return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: p <= 2");
+        if (gi->porder > (g.topology == B200ASM_QUAD ? 4 : 2))
+            return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: quadrilaterals p <= 4, triangles p <= 2");
         if (gi->kind == B200ASM_POISSON && g.ns != 1) return fail(ctx, B200ASM_EINVAL, "add_group: Poisson has nstate 1");
         if (gi->kind == B200ASM_ELASTICITY2D && g.ns != 2) return fail(ctx, B200ASM_EINVAL, "add_group: Elasticity2D has nstate 2");
         if (gi->force) return fail(ctx, B200ASM_EINVAL, "add_group: forcing-function tables are not supported on plane elements");
     } else if (gi->kind != B200ASM_BC) {
         return fail(ctx, B200ASM_EINVAL, "add_group: face / line elements need kind BC (or POISSON / ELASTICITY2D as plane domain elements)");
-    } else if (g.dim == 1 && gi->porder > 2) {
-        return fail(ctx, B200ASM_EINVAL, "add_group: line elements: p <= 2");
+    } else if (g.dim == 1 && gi->porder > 4) {
+        return fail(ctx, B200ASM_EINVAL, "add_group: line elements: p <= 4");
     }
     g.m = g.n * g.ns;
     memcpy(g.coef, gi->coef, sizeof(g.coef));
@@ -1255,6 +1285,26 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             g.max_dest = std::max(g.max_dest, d);
         }
         for (int k = 0; k < g.nn; k++) elnodes[(size_t)e * g.nn + k] = gi->elnodes[src * g.nn + k];
+    }
+    // element chunks for the overlapped download: boundaries are multiples of every kernel's batch size
+    {
+        constexpr int64_t kAlign = 384, kMaxChunks = 16;
+        int64_t nch = 1;
+        if (volume && g.seg.size() == 2) nch = std::max<int64_t>(1, std::min<int64_t>(kMaxChunks, g.nel / ctx->overlap_min_elements));
+        g.chunk.assign(1, 0);
+        for (int64_t c = 1; c < nch; c++) {
+            const int64_t b = (g.nel * c / nch) / kAlign * kAlign;
+            if (b > g.chunk.back()) g.chunk.push_back(b);
+        }
+        g.chunk.push_back(g.nel);
+        g.chunk_min.assign(g.chunk.size() - 1, INT64_MAX);
+        for (size_t c = 0; c + 1 < g.chunk.size(); c++) {
+            int32_t mn = INT32_MAX;
+            const int32_t *d = dest32.data() + (size_t)g.chunk[c] * g.m, *dend = dest32.data() + (size_t)g.chunk[c + 1] * g.m;
+            for (; d < dend; d++)
+                if (*d >= 0 && *d < mn) mn = *d;
+            if (mn != INT32_MAX) g.chunk_min[c] = mn;
+        }
     }
     // gradients of the geometric (corner) functions at the points = the p=1 shape gradients
     std::vector<double> gphi((size_t)g.nq * g.nn), dng((size_t)g.nq * g.dim * g.nn);
@@ -1488,8 +1538,82 @@ extern "C" int b200asm_get_pattern(b200asm_ctx *ctx, int64_t *ia_host, int64_t *
     return 0;
 }
 
-extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
-    if (!ctx) return B200ASM_EINVAL;
+namespace {
+
+// launches of one group; volume groups without colours may be restricted to the element range [r0, r1) (chunk boundaries
+// of Group::chunk).  r0 < 0: the whole group.
+int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
+    const int atomic = ctx->scatter == B200ASM_SCATTER_ATOMIC ? 1 : 0;
+    const size_t nseg = g.seg.size() - 1;  // 1, or the number of colours
+    if (g.kind == B200ASM_BC || g.plane) {
+        BcParams p;
+        p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
+        p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
+        p.kind = g.kind; p.fdim = g.dim;
+        p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
+        memcpy(p.coef, g.coef, sizeof(p.coef));
+        for (size_t c = 0; c < nseg; c++) {
+            p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];
+            if (p.el1 == p.el0) continue;
+            if (g.plane) {
+                const int grid = (int)((p.el1 - p.el0 + 3) / 4);
+                const size_t smem = 4 * (size_t)g.nq * (2 + 2 * g.n) * sizeof(double);
+                assemble_plane_kernel<<<grid, 128, smem, ctx->stream>>>(p, g.nn, g.n, g.ns);
+                CK(cudaGetLastError());
+            } else {
+                CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+            }
+            ctx->launches++;
+        }
+        return 0;
+    }
+    const bool use_mma = g.mma >= 0 && ctx->engine == 1;
+    size_t smem = 0;
+    int per_sm = 1;
+    if (use_mma) {
+        smem = kMma[g.mma].smem(g.nq);
+        if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
+        CK(kMma[g.mma].prepare(smem, &per_sm));
+    } else {
+        smem = kVol[g.cfg].smem(g.nq);
+        if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
+        CK(kVol[g.cfg].prepare(smem, &per_sm));
+    }
+    if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
+    for (size_t c = 0; c < nseg; c++) {
+        int64_t e0 = g.seg[c], n = g.seg[c + 1] - g.seg[c];
+        if (r0 >= 0) { e0 = r0; n = r1 - r0; }  // (nseg == 1)
+        if (n == 0) continue;
+        VolParams p;
+        p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = (ctx->debug & 1) ? 2 : atomic; p.rhs_only = ctx->rhs_only; p.debug = ctx->debug;
+        p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
+        p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
+        p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;
+        p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad;
+        p.a = ctx->d_a; p.rhs = ctx->d_rhs;
+        memcpy(p.coef, g.coef, sizeof(p.coef));
+        // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)
+        if (use_mma) {
+            const MmaEntry &me = kMma[g.mma];
+            const size_t off = (size_t)e0 * me.slots;
+            p.nbatch = 0; p.smap = g.d_smap ? g.d_smap + off : nullptr; p.smapT = g.d_smapT ? g.d_smapT + off : nullptr;
+            const int64_t want = (n + me.wpc - 1) / me.wpc;
+            CK(me.launch(p, (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
+        } else {
+            const VolEntry &ve = kVol[g.cfg];
+            p.nbatch = (n + ve.epb - 1) / ve.epb;
+            // (no maps yet in a pattern-less rhs-only run); chunk starts are multiples of the batch size
+            size_t soff = c < g.seg_smap.size() ? g.seg_smap[c] : 0;
+            if (r0 >= 0) soff += (size_t)(r0 / ve.epb) * ve.tile * ve.tile * ve.slots;
+            p.smap = g.d_smap ? g.d_smap + soff : nullptr; p.smapT = g.d_smapT ? g.d_smapT + soff : nullptr;
+            CK(ve.launch(p, (int)std::min<int64_t>(p.nbatch, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
+        }
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int begin_assembly(b200asm_ctx *ctx) {
     if (!ctx->have_pattern && !ctx->rhs_only) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
     if (!ctx->d_xyz) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_nodes first");
     CK(cudaSetDevice(ctx->device));
@@ -1500,77 +1624,22 @@ extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
     // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75
     if (!ctx->rhs_only) CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
-    const int atomic = ctx->scatter == B200ASM_SCATTER_ATOMIC ? 1 : 0;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
+    if (!ctx) return B200ASM_EINVAL;
+    int rc = begin_assembly(ctx);
+    if (rc) return rc;
     for (Group &g : ctx->groups) {
         if (g.nel == 0) continue;
-        const size_t nseg = g.seg.size() - 1;  // 1, or the number of colours
         if (ctx->timing) {
             if (!g.ev0) { CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); }
             CK(cudaEventRecord(g.ev0, ctx->stream));
         }
-        if (g.kind == B200ASM_BC || g.plane) {
-            BcParams p;
-            p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
-            p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
-            p.kind = g.kind; p.fdim = g.dim;
-            p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
-            memcpy(p.coef, g.coef, sizeof(p.coef));
-            for (size_t c = 0; c < nseg; c++) {
-                p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];
-                if (p.el1 == p.el0) continue;
-                if (g.plane) {
-                    const int grid = (int)((p.el1 - p.el0 + 3) / 4);
-                    const size_t smem = 4 * (size_t)g.nq * (2 + 2 * g.n) * sizeof(double);
-                    assemble_plane_kernel<<<grid, 128, smem, ctx->stream>>>(p, g.nn, g.n, g.ns);
-                    CK(cudaGetLastError());
-                } else {
-                    CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
-                }
-                ctx->launches++;
-            }
-            if (ctx->timing) CK(cudaEventRecord(g.ev1, ctx->stream));
-            continue;
-        }
-        const bool use_mma = g.mma >= 0 && ctx->engine == 1;
-        size_t smem = 0;
-        int per_sm = 1;
-        if (use_mma) {
-            smem = kMma[g.mma].smem(g.nq);
-            if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
-            CK(kMma[g.mma].prepare(smem, &per_sm));
-        } else {
-            smem = kVol[g.cfg].smem(g.nq);
-            if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
-            CK(kVol[g.cfg].prepare(smem, &per_sm));
-        }
-        if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
-        for (size_t c = 0; c < nseg; c++) {
-            const int64_t e0 = g.seg[c], n = g.seg[c + 1] - g.seg[c];
-            if (n == 0) continue;
-            VolParams p;
-            p.nel = n; p.nq = g.nq; p.kind = g.kind; p.atomic = (ctx->debug & 1) ? 2 : atomic; p.rhs_only = ctx->rhs_only; p.debug = ctx->debug;
-            p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
-            p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
-            p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;
-            p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad;
-            p.a = ctx->d_a; p.rhs = ctx->d_rhs;
-            memcpy(p.coef, g.coef, sizeof(p.coef));
-            // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)
-            if (use_mma) {
-                const MmaEntry &me = kMma[g.mma];
-                const size_t off = (size_t)e0 * me.slots;
-                p.nbatch = 0; p.smap = g.d_smap ? g.d_smap + off : nullptr; p.smapT = g.d_smapT ? g.d_smapT + off : nullptr;
-                const int64_t want = (n + me.wpc - 1) / me.wpc;
-                CK(me.launch(p, (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
-            } else {
-                const VolEntry &ve = kVol[g.cfg];
-                p.nbatch = (n + ve.epb - 1) / ve.epb;
-                const size_t soff = c < g.seg_smap.size() ? g.seg_smap[c] : 0;  // (no maps yet in a pattern-less rhs-only run)
-                p.smap = g.d_smap ? g.d_smap + soff : nullptr; p.smapT = g.d_smapT ? g.d_smapT + soff : nullptr;
-                CK(ve.launch(p, (int)std::min<int64_t>(p.nbatch, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
-            }
-            ctx->launches++;
-        }
+        if ((rc = enqueue_group(ctx, g, -1, -1))) return rc;
         if (ctx->timing) CK(cudaEventRecord(g.ev1, ctx->stream));
     }
     return 0;
@@ -1609,7 +1678,105 @@ extern "C" int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_ho
     return 0;
 }
 
+namespace {
+
+// b200asm_assemble with a host matrix: the D2H copy of the CSR values (PCIe, several times longer than the assembly
+// itself) starts while the kernels still run.  Launch units = whole small groups first, then the element chunks of the
+// large volume groups in element order.  An entry of A lives in row min(dest_i, dest_j) (symmetric) or dest_i (full), so
+// every row below the smallest destination equation of all LATER units is final once the current unit has finished:
+// that prefix of A is copied on a second stream behind an event.  Atomic scatter only (the coloured mode keeps its
+// deterministic launch order).
+int assemble_overlapped(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
+    int rc = begin_assembly(ctx);
+    if (rc) return rc;
+    struct Unit { int group; int64_t r0, r1, min_dest; };
+    std::vector<Unit> units;
+    for (int pass = 0; pass < 2; pass++)
+        for (size_t gi = 0; gi < ctx->groups.size(); gi++) {
+            const Group &g = ctx->groups[gi];
+            if (g.nel == 0) continue;
+            const bool chunked = g.chunk.size() > 2;
+            if (chunked != (pass == 1)) continue;
+            if (!chunked) {
+                units.push_back({(int)gi, -1, -1, g.chunk_min.empty() ? 0 : g.chunk_min[0]});
+            } else {
+                for (size_t c = 0; c + 1 < g.chunk.size(); c++) units.push_back({(int)gi, g.chunk[c], g.chunk[c + 1], g.chunk_min[c]});
+            }
+        }
+    // frontier[u] = first row that a unit after u may still touch
+    std::vector<int64_t> frontier(units.size(), ctx->neq);
+    for (int64_t u = (int64_t)units.size() - 2; u >= 0; u--)
+        frontier[u] = std::min(frontier[u + 1], std::min<int64_t>(units[u + 1].min_dest, ctx->neq));
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // IA at the frontiers (the pattern is device-resident): read once per set of scatter maps
+    if (!ctx->ov_valid || ctx->ov_upto.size() != units.size()) {
+        ctx->ov_upto.assign(units.size(), 0);
+        for (size_t u = 0; u + 1 < units.size(); u++)
+            if (frontier[u] > 0)
+                CK(cudaMemcpyAsync(&ctx->ov_upto[u], ctx->d_ia + frontier[u], sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->ov_valid = true;
+    }
+    const int64_t kMinCopy = std::max<int64_t>(1, ctx->overlap_min_bytes / (int64_t)sizeof(double));
+    int64_t done = 0;                               // entries of A already queued for download
+    size_t nev = 0;
+    for (size_t u = 0; u < units.size(); u++) {
+        Group &g = ctx->groups[units[u].group];
+        const bool first_of_group = u == 0 || units[u - 1].group != units[u].group;
+        const bool last_of_group = u + 1 == units.size() || units[u + 1].group != units[u].group;
+        if (ctx->timing && first_of_group) {
+            if (!g.ev0) { CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); }
+            CK(cudaEventRecord(g.ev0, ctx->stream));
+        }
+        if ((rc = enqueue_group(ctx, g, units[u].r0, units[u].r1))) return rc;
+        if (ctx->timing && last_of_group) CK(cudaEventRecord(g.ev1, ctx->stream));
+        if (u + 1 == units.size()) break;
+        const int64_t upto = ctx->ov_upto[u];
+        if (upto - done < kMinCopy) continue;
+        if (nev == ctx->copy_events.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->copy_events.push_back(e);
+        }
+        CK(cudaEventRecord(ctx->copy_events[nev], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[nev], 0));
+        nev++;
+        CK(cudaMemcpyAsync(a_host + done, ctx->d_a + done, (size_t)(upto - done) * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        done = upto;
+    }
+    // the rest of A and the load vector behind the last kernel
+    if (nev == ctx->copy_events.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->copy_events[nev], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[nev], 0));
+    if (ctx->nnz > done)
+        CK(cudaMemcpyAsync(a_host + done, ctx->d_a + done, (size_t)(ctx->nnz - done) * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->d2h += ctx->nnz * (int64_t)sizeof(double);
+    if (rhs_host) {
+        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs, (size_t)ctx->neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->d2h += ctx->neq * (int64_t)sizeof(double);
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
 extern "C" int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
+    if (!ctx) return B200ASM_EINVAL;
+    if (a_host && ctx->overlap && ctx->scatter == B200ASM_SCATTER_ATOMIC && !ctx->rhs_only && ctx->have_pattern) {
+        bool chunked = false;
+        for (const Group &g : ctx->groups) chunked = chunked || g.chunk.size() > 2;
+        // pageable destinations make cudaMemcpyAsync block the launching thread: overlap only into pinned / registered memory
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, a_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (chunked && pinned) return assemble_overlapped(ctx, a_host, rhs_host);
+    }
     int rc = b200asm_assemble_async(ctx);
     if (rc) return rc;
     return b200asm_download(ctx, a_host, rhs_host);

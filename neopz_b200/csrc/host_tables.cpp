@@ -93,6 +93,10 @@ inline SideParam side_param(int topology, int side, int64_t key) {
             sp.sdim = 3;
             for (int k = 0; k < 3; k++) { sp.axis[k] = k; sp.sign[k] = 1; }
         }
+    } else if (topology == B200ASM_LINE) {
+        sp.sdim = 1;
+        sp.axis[0] = 0;
+        sp.sign[0] = (key & 1) ? -1 : 1;
     } else {
         if (side < 8) {
             const int e = side - 4;
@@ -300,14 +304,18 @@ extern "C" int b200asm_nshape(int topology, int porder) {
         case B200ASM_QUAD: return (p + 1) * (p + 1);
         case B200ASM_TET: return p <= 2 ? (p == 1 ? 4 : 10) : B200ASM_EINVAL;
         case B200ASM_TRI: return p <= 2 ? (p == 1 ? 3 : 6) : B200ASM_EINVAL;
-        case B200ASM_LINE: return p <= 2 ? p + 1 : B200ASM_EINVAL;
+        case B200ASM_LINE: return p + 1;
     }
     return B200ASM_EINVAL;
 }
 
 extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t *elnodes, int64_t *keys) {
     if (nel < 0 || (nel && (!elnodes || !keys))) return B200ASM_EINVAL;
-    if (topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_LINE) {  // p <= 2 only: no orientation dependence
+    if (topology == B200ASM_LINE) {
+        for (int64_t e = 0; e < nel; e++) keys[e] = elnodes[2 * e] < elnodes[2 * e + 1] ? 0 : 1;
+        return 0;
+    }
+    if (topology == B200ASM_TET || topology == B200ASM_TRI) {  // p <= 2 only: no orientation dependence
         for (int64_t e = 0; e < nel; e++) keys[e] = 0;
         return 0;
     }
@@ -336,11 +344,13 @@ extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t
 extern "C" int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts,
                                              double *phi, double *dphi) {
     if (porder < 1 || porder > 8 || nqp < 0) return B200ASM_EINVAL;
-    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_LINE)
+    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI)
         return b200asm_shape_tables(topology, porder, nqp, qpts, phi, dphi);
-    if (topology != B200ASM_HEX && topology != B200ASM_QUAD) return B200ASM_EINVAL;
-    const int dim = topology == B200ASM_HEX ? 3 : 2;
-    const int nsides = topology == B200ASM_HEX ? 27 : 9, nc = topology == B200ASM_HEX ? 8 : 4;
+    if (topology != B200ASM_HEX && topology != B200ASM_QUAD && topology != B200ASM_LINE) return B200ASM_EINVAL;
+    const int dim = topology == B200ASM_HEX ? 3 : (topology == B200ASM_LINE ? 1 : 2);
+    const int nsides = topology == B200ASM_HEX ? 27 : (topology == B200ASM_LINE ? 3 : 9);
+    const int nc = topology == B200ASM_HEX ? 8 : (topology == B200ASM_LINE ? 2 : 4);
+    static const int kLineSide[3][2] = {{0, 0}, {1, 0}, {2, 0}};
     const int n = b200asm_nshape(topology, porder);
     const int m = porder - 1;  // Chebyshev functions per side direction
     for (int q = 0; q < nqp; q++) {
@@ -352,9 +362,12 @@ extern "C" int b200asm_shape_tables_oriented(int topology, int porder, int64_t k
         int shape = 0;
         for (int side = 0; side < nsides; side++) {
             // blend function of the side and its gradient
-            const int *a = dim == 3 ? kHexSide[side] : kQuadSide[side];
+            const int *a = dim == 3 ? kHexSide[side] : (dim == 1 ? kLineSide[side] : kQuadSide[side]);
             double B, dB[3] = {0, 0, 0};
-            if (dim == 3) {
+            if (dim == 1) {
+                B = f[0][a[0]];
+                dB[0] = df[0][a[0]];
+            } else if (dim == 3) {
                 B = f[0][a[0]] * f[1][a[1]] * f[2][a[2]];
                 dB[0] = df[0][a[0]] * f[1][a[1]] * f[2][a[2]];
                 dB[1] = f[0][a[0]] * df[1][a[1]] * f[2][a[2]];

@@ -350,18 +350,24 @@ def grid_elements_2d(n, triangles=False, bc_matids=(-1, -1, -1, -1), dom_matid=1
     return nodes, [tuple(b) for b in blocks]
 
 
-def grid_mesh_2d(n, porder, nstate, triangles=False, bc_matids=(-1,) * 4, perturb=0.0):
+def _renumber_nodes(nodes, blocks, node_perm):
+    """node_perm[i] = new index of grid node i (a renumbered mesh: same geometry, different side orientations)."""
+    if node_perm is None:
+        return nodes, blocks
+    node_perm = np.asarray(node_perm, dtype=np.int64)
+    renum = np.empty_like(nodes)
+    renum[node_perm] = nodes
+    return renum, [(t, m, node_perm[np.asarray(e, dtype=np.int64)]) for t, m, e in blocks]
+
+
+def grid_mesh_2d(n, porder, nstate, triangles=False, bc_matids=(-1,) * 4, perturb=0.0, node_perm=None):
     nodes, blocks = grid_elements_2d(n, triangles=triangles, bc_matids=bc_matids, perturb=perturb)
+    nodes, blocks = _renumber_nodes(nodes, blocks, node_perm)
     return flatten(nodes, blocks, porder, nstate)
 
 
 def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0, node_perm=None):
     """node_perm[i] = new index of grid node i (a renumbered mesh: same geometry, different side orientations)."""
     nodes, blocks = grid_elements(n, tetrahedra=tetrahedra, bc_matids=bc_matids, perturb=perturb)
-    if node_perm is not None:
-        node_perm = np.asarray(node_perm, dtype=np.int64)
-        renum = np.empty_like(nodes)
-        renum[node_perm] = nodes
-        nodes = renum
-        blocks = [(t, m, node_perm[np.asarray(e, dtype=np.int64)]) for t, m, e in blocks]
+    nodes, blocks = _renumber_nodes(nodes, blocks, node_perm)
     return flatten(nodes, blocks, porder, nstate)

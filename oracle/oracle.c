@@ -260,6 +260,19 @@ static int shape_tri(int p, const double *pt, double *phi, double *dphi_out) {
     return n;
 }
 
+/* TPZShapeLinear, p <= 2: Shape/pzshapelinear.cpp:269-283 (corner), :285-292 (generating: phi0*phi1*4) */
+static int shape_line(int p, const double *pt, double *phi, double *dphi_out) {
+    const int n = p == 1 ? 2 : 3;
+    phi[0] = (1. - pt[0]) / 2.; phi[1] = (1. + pt[0]) / 2.;
+    dphi_out[0] = -0.5; dphi_out[1] = 0.5;
+    if (p >= 2) {
+        phi[2] = phi[0] * phi[1];
+        dphi_out[2] = dphi_out[0] * phi[1] + phi[0] * dphi_out[1];
+        phi[2] *= 4.; dphi_out[2] *= 4.;
+    }
+    return n;
+}
+
 /* ------------------------------------------------------------------------------------------
  * H1 shape functions of arbitrary order on hexahedra / quadrilaterals (p >= 3 needs the side
  * orientations).  Shape/TPZShapeH1.cpp:42-116:
@@ -339,6 +352,9 @@ static void element_to_side(int topo, int side, int *sidedim, double E[3][3]) {
             *sidedim = 3;
             E[0][0] = E[1][1] = E[2][2] = 1.;
         }
+    } else if (topo == ORC_LINE) { /* Topology/tpzline.cpp:285-300: the line itself */
+        *sidedim = 1;
+        E[0][0] = 1.;
     } else { /* ORC_QUAD */
         if (side < 8) {
             *sidedim = 1;
@@ -358,7 +374,7 @@ static void element_to_side(int topo, int side, int *sidedim, double E[3][3]) {
 /* GetSideTransform (pzgenericshape.cpp:13-55): T = P * E */
 static void side_transform(int topo, int side, const int64_t *ids, int *sidedim, double T[3][3]) {
     double E[3][3];
-    const int dim = topo == ORC_HEX ? 3 : 2;
+    const int dim = topo == ORC_HEX ? 3 : (topo == ORC_LINE ? 1 : 2);
     element_to_side(topo, side, sidedim, E);
     if (topo == ORC_HEX && side == 26) { memcpy(T, E, sizeof(E)); return; }
     double P[3][3];
@@ -366,6 +382,7 @@ static void side_transform(int topo, int side, const int64_t *ids, int *sidedim,
     if (*sidedim == 1) {
         int a, b;
         if (topo == ORC_HEX) { a = cube_edge_nodes[side - 8][0]; b = cube_edge_nodes[side - 8][1]; }
+        else if (topo == ORC_LINE) { a = 0; b = 1; }
         else { a = side - 4; b = (side - 3) % 4; }
         P[0][0] = ids[a] < ids[b] ? 1. : -1.;
     } else {
@@ -384,14 +401,14 @@ static void side_transform(int topo, int side, const int64_t *ids, int *sidedim,
 
 /* blend (generating) functions of all sides: the p = 2 tables of shape_hex / shape_quad */
 static int shape_hq_general(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi_out) {
-    const int dim = topo == ORC_HEX ? 3 : 2;
-    const int nc = topo == ORC_HEX ? 8 : 4, nsides = topo == ORC_HEX ? 27 : 9;
+    const int dim = topo == ORC_HEX ? 3 : (topo == ORC_LINE ? 1 : 2);
+    const int nc = topo == ORC_HEX ? 8 : (topo == ORC_LINE ? 2 : 4), nsides = topo == ORC_HEX ? 27 : (topo == ORC_LINE ? 3 : 9);
     double bphi[27], bd[3 * 27];
-    if (topo == ORC_HEX) shape_hex(2, pt, bphi, bd); else shape_quad(2, pt, bphi, bd);
+    if (topo == ORC_HEX) shape_hex(2, pt, bphi, bd); else if (topo == ORC_LINE) shape_line(2, pt, bphi, bd); else shape_quad(2, pt, bphi, bd);
     int n = nc;
     for (int side = nc; side < nsides; side++) {
         int sd;
-        if (topo == ORC_HEX) sd = side < 20 ? 1 : (side < 26 ? 2 : 3); else sd = side < 8 ? 1 : 2;
+        if (topo == ORC_HEX) sd = side < 20 ? 1 : (side < 26 ? 2 : 3); else if (topo == ORC_LINE) sd = 1; else sd = side < 8 ? 1 : 2;
         int ns = p - 1;
         if (sd == 2) ns *= (p - 1);
         if (sd == 3) ns *= (p - 1) * (p - 1);
@@ -451,19 +468,6 @@ static int shape_hq_general(int topo, int p, const int64_t *ids, const double *p
     return n;
 }
 
-/* TPZShapeLinear, p <= 2: Shape/pzshapelinear.cpp:269-283 (corner), :285-292 (generating: phi0*phi1*4) */
-static int shape_line(int p, const double *pt, double *phi, double *dphi_out) {
-    const int n = p == 1 ? 2 : 3;
-    phi[0] = (1. - pt[0]) / 2.; phi[1] = (1. + pt[0]) / 2.;
-    dphi_out[0] = -0.5; dphi_out[1] = 0.5;
-    if (p >= 2) {
-        phi[2] = phi[0] * phi[1];
-        dphi_out[2] = dphi_out[0] * phi[1] + phi[0] * dphi_out[1];
-        phi[2] *= 4.; dphi_out[2] *= 4.;
-    }
-    return n;
-}
-
 /* ids: global corner-node indices (gel->NodeIndex, Mesh/TPZCompElH1.cpp:110); may be NULL for p <= 2 */
 int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi) {
     if (p < 1) return -1;
@@ -478,7 +482,7 @@ int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double 
         return -1;
     }
     if (p > ORC_MAXP || !ids) return -1;
-    if (topo == ORC_HEX || topo == ORC_QUAD) return shape_hq_general(topo, p, ids, pt, phi, dphi);
+    if (topo == ORC_HEX || topo == ORC_QUAD || topo == ORC_LINE) return shape_hq_general(topo, p, ids, pt, phi, dphi);
     return -1; /* simplices of order >= 3: not restated */
 }
 

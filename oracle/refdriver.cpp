@@ -312,6 +312,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
         dump_shape_all<pzshape::TPZShapeTetra>(dir, "tet", cmesh, ETetraedro);
         dump_shape_all<pzshape::TPZShapeQuad>(dir, "quad", cmesh, EQuadrilateral);
         dump_shape_all<pzshape::TPZShapeTriang>(dir, "tri", cmesh, ETriangle);
+        dump_shape_all<pzshape::TPZShapeLinear>(dir, "line", cmesh, EOned);
     }
 
     TPZLinearAnalysis an(cmesh, false);

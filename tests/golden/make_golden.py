@@ -46,6 +46,10 @@ CASES = {
     "tri_p1_elast2d_stress_n2_bc3": (2, 1, 3, 1, 0.15, 3, 1, 0, 2),
     "quad_p2_poisson2d_n3_pert": (3, 2, 0, 0, 0.15, 1, 1, 0, 2),
     "tri_p2_poisson2d_n3_pert": (3, 2, 0, 1, 0.15, 1, 1, 0, 2),
+    # plane quadrilaterals of order 3, 4 with oriented line boundary elements (scrambled node numbering)
+    "quad_p3_elast2d_n3_pert_scr": (3, 3, 2, 0, 0.15, 1, 1, 9, 2),
+    "quad_p4_poisson2d_n3_pert_scr": (3, 4, 0, 0, 0.15, 1, 1, 13, 2),
+    "quad_p4_elast2d_stress_n2_bc3_scr": (2, 4, 3, 0, 0.15, 3, 1, 3, 2),
 }
 
 

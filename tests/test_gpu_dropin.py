@@ -18,7 +18,8 @@ CASES = [(6, 1, 0, 0, 1, 1), (5, 2, 0, 0, 1, 1), (4, 2, 1, 0, 1, 1), (4, 2, 0, 1
          (4, 2, 0, 0, 0, 0), (3, 2, 1, 0, 0, 0), (5, 1, 1, 0, 1, 1),
          (4, 3, 0, 0, 1, 1), (3, 4, 0, 0, 1, 1), (3, 3, 1, 0, 1, 0), (3, 4, 0, 0, 0, 0),
          # phys 2 / 3: TPZElasticity2D plane strain / plane stress on plane meshes (quadrilaterals, triangles)
-         (8, 2, 2, 0, 1, 1), (6, 2, 3, 1, 1, 1), (7, 1, 2, 1, 0, 0), (6, 1, 3, 0, 1, 1)]
+         (8, 2, 2, 0, 1, 1), (6, 2, 3, 1, 1, 1), (7, 1, 2, 1, 0, 0), (6, 1, 3, 0, 1, 1),
+         (5, 3, 2, 0, 1, 1), (4, 4, 3, 0, 1, 1), (4, 4, 2, 0, 0, 0)]
 
 
 @pytest.mark.parametrize("device_create", [0, 1])

@@ -36,7 +36,8 @@ def fixture_setup(g):
     bct = m["bctype"]
     if m.get("dim", 3) == 2:  # plane meshes: TPZMatPoisson(dim 2) / TPZElasticity2D, line elements on the boundary
         mesh = gridmesh.grid_mesh_2d(m["n"], m["p"], 2 if m["phys"] >= 2 else 1, triangles=bool(m["tet"]),
-                                     bc_matids=(-1, -1, -2 if bct >= 1 else -1, -1), perturb=m["perturb"])
+                                     bc_matids=(-1, -1, -2 if bct >= 1 else -1, -1), perturb=m["perturb"],
+                                     node_perm=g["node_perm"] if m.get("scramble") else None)
         if m["phys"] >= 2:
             mat = sm.TPZElasticity2D(1, gu.E_MOD, gu.NU, *gu.E2D_FORCE, planestress=m["phys"] == 3)
             mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((2, 2)), np.zeros(2))}
@@ -167,6 +168,34 @@ def test_device_cg_reproduces_reference_solution(name, symmetric):
     assert it2 == 0 and res2 <= 1e-9 and np.array_equal(u2, u)
 
 
+@pytest.mark.parametrize("n,p,phys,tet,engine,symmetric", [(12, 2, 0, 0, 1, True), (10, 2, 1, 0, 1, True), (8, 2, 1, 1, 0, False),
+                                                           (16, 1, 0, 0, 0, True), (9, 2, 0, 1, 1, False), (8, 3, 0, 0, 1, True)])
+def test_overlapped_download_matches_plain_download(n, p, phys, tet, engine, symmetric):
+    """b200asm_assemble(a_host, rhs_host) copies finished rows while later element chunks run (option "overlap"): the
+    host result must equal the plain assemble-then-download of the same context, and the oracle."""
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.1)
+    mats = materials_for(phys, neumann=True)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, engine=engine, scatter="colored")
+    strmat.ctx.set_option("overlap", 0)
+    ia, ja, a_plain, rhs_plain = strmat.CreateAssemble()          # deterministic reference run (coloured, no overlap)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, engine=engine)
+    strmat.ctx.set_option("overlap_min_elements", 128)
+    strmat.ctx.set_option("overlap_min_bytes", 0)
+    strmat.SetPattern(ia, ja)
+    import torch
+    a = torch.full((len(ja),), float("nan"), dtype=torch.float64).pin_memory().numpy()  # the overlap needs page-locked memory
+    rhs = torch.full((mesh.neq,), float("nan"), dtype=torch.float64).pin_memory().numpy()
+    launches0 = strmat.ctx.counters()[0]
+    strmat.Assemble(a, rhs)
+    assert strmat.ctx.counters()[0] - launches0 > len(mesh.blocks)  # the volume group really ran in chunks
+    assert relF(a, a_plain) <= TOL and relF(rhs, rhs_plain) <= TOL
+    if mesh.nelements <= 3000:
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+    a2, _ = strmat.Assemble()                                     # again: events / cached frontiers are reused
+    assert relF(a2, a_plain) <= TOL
+
+
 @pytest.mark.parametrize("n,p,phys,tet,engine", [(4, 2, 0, 0, 1), (3, 2, 1, 0, 1), (3, 2, 1, 1, 0), (3, 4, 0, 0, 1), (5, 1, 0, 0, 0)])
 def test_rhs_only_assembly(n, p, phys, tet, engine):
     """TPZStrMatParInterface::Assemble(rhs): load vector only, equal to the rhs of the full assembly (and the oracle's);
@@ -234,6 +263,30 @@ def test_plane_elasticity_against_oracle(n, p, tri, planestress, scatter):
         assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
         a2, rhs2 = strmat.Assemble()
         assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
+        assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+
+
+@pytest.mark.parametrize("n,p,phys,planestress,shuffle", [(5, 3, 2, 0, 1), (4, 4, 2, 1, 1), (6, 4, 0, 0, 1), (5, 3, 0, 0, 0),
+                                                          (12, 4, 2, 0, 0)])
+def test_high_order_plane_against_oracle(n, p, phys, planestress, shuffle):
+    """p = 3, 4 quadrilaterals of plane meshes with oriented line boundary elements (TPZShapeLinear of order p,
+    Shape/pzshapelinear.cpp:306-312,360-363): one group per side-orientation class."""
+    perm = np.random.default_rng(77 + n + p).permutation((n + 1) ** 2) if shuffle else None
+    mesh = gridmesh.grid_mesh_2d(n, p, 2 if phys else 1, bc_matids=(-1, -3 if phys else -1, -2, -1), perturb=0.12, node_perm=perm)
+    if phys:
+        mat = sm.TPZElasticity2D(1, gu.E_MOD, gu.NU, 0.5, -1.0, planestress=bool(planestress))
+        mat.SetPreStress(0.2, -0.1, 0.05)
+        mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((2, 2)), [0.01, -0.02]),
+                -2: mat.CreateBC(-2, 1, np.zeros((2, 2)), [0.25, -0.5]), -3: mat.CreateBC(-3, 3, np.zeros((2, 2)), [1.0, 0.0])}
+    else:
+        mat = sm.TPZMatPoisson(1, 2)
+        mat.SetForcingFunction(1.5)
+        mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.25]), -2: mat.CreateBC(-2, 1, [[0.0]], [0.75])}
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+        ia, ja, a, rhs = strmat.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
         assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
 
 

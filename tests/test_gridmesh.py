@@ -9,12 +9,12 @@ from tests import golden_util as gu
 
 def _mesh_for(g):
     m = g["meta"]
+    perm = g["node_perm"] if m.get("scramble") else None
     if m.get("dim", 3) == 2:
         bc = (-1, -1, -2 if m["bctype"] >= 1 else -1, -1)
         return gridmesh.grid_mesh_2d(m["n"], m["p"], 2 if m["phys"] >= 2 else 1, triangles=bool(m["tet"]), bc_matids=bc,
-                                     perturb=m["perturb"])
+                                     perturb=m["perturb"], node_perm=perm)
     bc = (-1, -1, -1, -1, -1, -2 if m["bctype"] >= 1 else -1)
-    perm = g["node_perm"] if m.get("scramble") else None
     return gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
                               bc_matids=bc, perturb=m["perturb"], node_perm=perm)
 
