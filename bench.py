@@ -64,6 +64,8 @@ def parse():
 
 def kernel_name(a):
     if a.engine == 1:
+        if a.topo == "tet" and a.variant == 0:
+            return "assemble_affine_simplex_kernel (closed-form element matrices of straight-sided tetrahedra, one warp per element)"
         if a.phys == "poisson" and a.p == 2:
             return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"
         if a.phys == "poisson" and a.p >= 3:

@@ -51,6 +51,7 @@ struct VolParams {
     const double *__restrict__ dphi_pad;  // [nq][3][NP]  rows padded to NP = 16*ceil(N/16) doubles (DMMA kernels)
     const double *__restrict__ phi_pad;   // [nq][NP]
     const double *__restrict__ force;     // optional [nel][nq][NS]
+    const double *__restrict__ aux;       // kernel-specific tables of the group (affine_simplex.cuh: Ghat, cphi, cd)
     const int32_t *__restrict__ smap;     // [nbatch][TILE*TILE][EPB*NT]
     const int32_t *__restrict__ smapT;    // same, transposed entry (full storage only)
     double *__restrict__ a;
@@ -111,6 +112,7 @@ __device__ __forceinline__ void scatter_many(double *a, const int32_t (&pos)[N],
 
 #include "gram_mma.cuh"
 #include "gram_mma_team.cuh"
+#include "affine_simplex.cuh"
 #include "pattern_device.cuh"
 #include "cg_device.cuh"
 
@@ -747,7 +749,7 @@ struct Group {
     double coef[16];
     int32_t *d_elnodes = nullptr, *d_dest = nullptr, *d_smap = nullptr, *d_smapT = nullptr;
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
-    double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr;
+    double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr, *d_aux = nullptr;
     size_t smap_len = 0;
     // element colouring (B200ASM_SCATTER_COLORED): elements are stored sorted by colour; seg = colour boundaries
     // ({0, nel} when not coloured); seg_smap = offset of every segment's scatter map (register-tile kernels)
@@ -958,8 +960,60 @@ template <class C>
 MmaEntry make_team_entry(int topology, int porder, int variant = 0) {
     return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, C::NTHREADS, C::EPC, &C::smem_bytes, &launch_team<C>, &launch_team_smap<C>, &prepare_team<C>};
 }
-// wpc = elements processed concurrently by one CTA
-const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2),
+// closed-form kernels for straight-sided tetrahedra (affine_simplex.cuh):  N  NS  warps/CTA  min CTAs/SM
+using TetP1PoissonAff = AffCfg<4, 1, 8, 3>;
+using TetP1ElastAff = AffCfg<4, 3, 8, 3>;
+using TetP2PoissonAff = AffCfg<10, 1, 8, 3>;
+using TetP2ElastAff = AffCfg<10, 3, 8, 2>;
+template <class C>
+cudaError_t launch_aff(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
+    assemble_affine_simplex_kernel<C><<<grid, C::WPC * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t launch_aff_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
+                            int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_aff_smap_kernel<C><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t prepare_aff(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_affine_simplex_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_affine_simplex_kernel<C>, C::WPC * 32, smem);
+}
+template <class C>
+MmaEntry make_aff_entry(int porder) {
+    return MmaEntry{0, B200ASM_TET, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_aff<C>, &launch_aff_smap<C>, &prepare_aff<C>};
+}
+// Ghat[e][f](in,jn) = sum_q w dphi(e,in) dphi(f,jn), cphi[j] = sum_q w phi_j, cd[e][j] = sum_q w dphi(e,j): the aux table
+template <class C>
+void aff_tables(int nq, const double *qw, const double *phi, const double *dphi, std::vector<double> &aux) {
+    aux.assign(C::AUX_LEN, 0.0);
+    for (int in = 0; in < C::N; in++)
+        for (int jn = in; jn < C::N; jn++)
+            for (int e = 0; e < 3; e++)
+                for (int f = 0; f < 3; f++) {
+                    double v = 0.0;
+                    for (int q = 0; q < nq; q++) v += qw[q] * dphi[((size_t)q * 3 + e) * C::N + in] * dphi[((size_t)q * 3 + f) * C::N + jn];
+                    aux[C::AUX_G + (e * 3 + f) * C::NPP + C::pair_index(in, jn)] = v;
+                }
+    for (int j = 0; j < C::N; j++) {
+        double v = 0.0;
+        for (int q = 0; q < nq; q++) v += qw[q] * phi[(size_t)q * C::N + j];
+        aux[C::AUX_CPHI + j] = v;
+        for (int e = 0; e < 3; e++) {
+            double d = 0.0;
+            for (int q = 0; q < nq; q++) d += qw[q] * dphi[((size_t)q * 3 + e) * C::N + j];
+            aux[C::AUX_CD + e * C::N + j] = d;
+        }
+    }
+}
+// wpc = elements processed concurrently by one CTA; variant 0 = default (the first match wins), variant 7 = the DMMA
+// Gram kernels for tetrahedra that the closed-form kernels replaced
+const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP1ElastAff>(1),
+                         make_aff_entry<TetP2PoissonAff>(2), make_aff_entry<TetP2ElastAff>(2),
+                         make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2, 7),
                          make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
                          make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
@@ -967,12 +1021,12 @@ const MmaEntry kMma[] = {make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_m
                          make_mma_entry<HexP2PoissonMmaV3>(B200ASM_HEX, 2, 3),
                          make_team_entry<HexP2PoissonTeamV4>(B200ASM_HEX, 2, 4), make_team_entry<HexP2PoissonTeamV5>(B200ASM_HEX, 2, 5),
                          make_team_entry<HexP2PoissonTeamV6>(B200ASM_HEX, 2, 6),
-                         make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 0), make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1),
+                         make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 7), make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1),
                          make_team_entry<TetP2ElastTeamV3>(B200ASM_TET, 2, 3), make_team_entry<TetP2ElastTeamV4>(B200ASM_TET, 2, 4),
                          make_team_entry<TetP2ElastTeamV5>(B200ASM_TET, 2, 5), make_team_entry<TetP2ElastTeamV6>(B200ASM_TET, 2, 6),
                          make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2)};
-// (tetrahedra p=2 elasticity: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the register-tile
-//  kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
+// (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
+//  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
 
 template <int NN, int N, int NS>
@@ -1042,7 +1096,7 @@ int colour_elements(int64_t nel, int m, const int64_t *dest, int64_t neq_hint, s
 void free_group(Group &g) {
     cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
     cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
-    cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad);
+    cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad); cudaFree(g.d_aux);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
     g = Group();
@@ -1335,6 +1389,14 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if ((rc = upload(ctx, &g.d_dphi_pad, dphi_pad.data(), dphi_pad.size()))) return rc;
         if ((rc = upload(ctx, &g.d_phi_pad, phi_pad.data(), phi_pad.size()))) return rc;
     }
+    std::vector<double> aux;  // (lives until the synchronize below)
+    if (volume && g.topology == B200ASM_TET) {
+        if (g.n == 4 && g.ns == 1) aff_tables<TetP1PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else if (g.n == 4) aff_tables<TetP1ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else if (g.ns == 1) aff_tables<TetP2PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else aff_tables<TetP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
+    }
     std::vector<double> force;
     if (gi->force && volume) {
         const size_t per = (size_t)g.nq * g.ns;
@@ -1589,7 +1651,7 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
         p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
         p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
         p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;
-        p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad;
+        p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad; p.aux = g.d_aux;
         p.a = ctx->d_a; p.rhs = ctx->d_rhs;
         memcpy(p.coef, g.coef, sizeof(p.coef));
         // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)

@@ -356,6 +356,25 @@ def test_high_order_hex_against_oracle(n, p, phys, engine, shuffle):
         assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
 
 
+@pytest.mark.parametrize("p,phys,variant,scatter", [(2, 1, 0, "atomic"), (2, 0, 0, "atomic"), (1, 1, 0, "atomic"), (1, 0, 0, "colored"),
+                                                    (2, 1, 0, "colored"), (2, 1, 7, "atomic"), (2, 0, 7, "atomic")])
+def test_tetrahedra_kernels_against_oracle(p, phys, variant, scatter):
+    """Straight-sided tetrahedra: the closed-form kernel (affine_simplex.cuh, default) and the DMMA Gram kernels it replaced
+    (variant 7), with prestress, Neumann faces, symmetric and full storage, re-assembly and the rhs-only path."""
+    mesh = gridmesh.grid_mesh(4, p, 3 if phys else 1, tetrahedra=True, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.15)
+    mats = materials_for(phys, neumann=True)
+    if phys:
+        mats[1].fPreStress = [0.3, -0.2, 0.1]
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, variant=variant, scatter=scatter)
+        ia, ja, a, rhs = strmat.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+        a2, rhs2 = strmat.Assemble()
+        assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
+        assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+
+
 @pytest.mark.parametrize("n,p,phys,tet", [(5, 2, 0, 0), (4, 2, 0, 1)])
 def test_engines_agree(n, p, phys, tet):
     """Register-tile DFMA kernels (engine 0) and DMMA panel kernels (engine 1) against the oracle and each other."""
