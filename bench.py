@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--pattern", default="device", choices=["device", "host"],
                     help="one-off setup: CSR pattern built on the GPU (b200asm_build_pattern_device) or by the threaded host builder")
     ap.add_argument("--cg", type=int, default=0, help="also time N iterations of the device-resident CG (reported as extra keys)")
+    ap.add_argument("--perturb", type=float, default=0.1, help="smooth node perturbation in units of h (default 0.1: general trilinear "
+                    "hexahedra; 0 = the uniform grid of CreateGeoMeshOnGrid, whose parallelepiped cells take the closed-form kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -66,6 +68,8 @@ def kernel_name(a):
     if a.engine == 1:
         if a.topo == "tet" and a.variant == 0:
             return "assemble_affine_simplex_kernel (closed-form element matrices of straight-sided tetrahedra, one warp per element)"
+        if a.topo == "hex" and a.perturb == 0.0 and a.p <= 2:
+            return "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)"
         if a.phys == "poisson" and a.p == 2:
             return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"
         if a.phys == "poisson" and a.p >= 3:
@@ -226,7 +230,7 @@ def main():
     from neopz_b200 import distributed
     t0 = time.time()
     ns = 3 if a.phys == "elasticity" else 1
-    slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=0.1)
+    slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=a.perturb)
     mesh = slab.mesh
     t_flat = time.time() - t0
     if a.phys == "poisson":
@@ -337,6 +341,31 @@ def main():
         if serial_s is not None:
             e2e["ms_per_step_without_overlap"] = serial_s * 1e3
 
+    # ---- the same mesh WITHOUT the node perturbation (the literal CreateGeoMeshOnGrid grid of BASELINE.json): every cell is
+    # a parallelepiped, the context measures that on the device and switches the group to the closed-form kernel
+    # (affine_hex.cuh).  Reported next to the headline, which stays on general (trilinear) hexahedra.
+    uniform = None
+    if world == 1 and a.topo == "hex" and a.p <= 2 and a.perturb != 0.0 and a.engine == 1 and not a.debug:
+        import numpy as np
+        moved = np.ascontiguousarray(mesh.nodes)
+        strmat.ctx.set_nodes(gridmesh.grid_nodes(a.n, perturb=0.0))
+        for _ in range(3):
+            step_async()            # (the first one rebuilds the scatter maps in the closed-form kernel's layout)
+        torch.cuda.synchronize()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record(stream)
+        for _ in range(a.steps):
+            step_async()
+        u1.record(stream)
+        torch.cuda.synchronize()
+        ums = u0.elapsed_time(u1) / a.steps
+        uniform = {"value": nvol / (ums * 1e-3), "unit": "elements/s", "ms_per_step": ums,
+                   "kernel": "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)",
+                   "note": "same pattern and materials, unperturbed grid nodes; device-resident like `value`"}
+        strmat.ctx.set_nodes(moved)
+        step_async()
+        torch.cuda.synchronize()
+
     cg = None
     if a.cg > 0 and world == 1:
         # the step after assembly on the same resident matrix: a.cg iterations of the reference's CG algorithm
@@ -410,12 +439,14 @@ def main():
             "config": {"workload": workload_name(a) if world == 1 else workload_name(a).replace(f"{a.n}^3", f"{a.n}x{a.n}x{a.n * world}") +
                        f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
-                       "perturbed_nodes": True, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
+                       "perturbed_nodes": a.perturb != 0.0, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
                                    "pattern_builder": a.pattern}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}
     if cg:
         line["device_cg"] = cg
+    if uniform:
+        line["uniform_grid"] = uniform
     emit(line)
     if world > 1:
         dist.destroy_process_group()

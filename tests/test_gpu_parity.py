@@ -375,6 +375,50 @@ def test_tetrahedra_kernels_against_oracle(p, phys, variant, scatter):
         assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
 
 
+def _sheared(mesh):
+    """An affine image of the grid: every hexahedron becomes a general parallelepiped."""
+    A = np.array([[1.3, 0.2, -0.1], [0.15, 0.8, 0.25], [-0.2, 0.1, 1.1]])
+    mesh.nodes[:] = mesh.nodes @ A.T + np.array([0.3, -0.2, 0.5])
+    return mesh
+
+
+@pytest.mark.parametrize("p,phys,scatter,shear", [(2, 0, "atomic", 1), (2, 1, "atomic", 1), (1, 0, "atomic", 1), (1, 1, "colored", 0),
+                                                  (2, 1, "colored", 1), (2, 0, "atomic", 0)])
+def test_parallelepiped_hexahedra_closed_form(p, phys, scatter, shear):
+    """Hexahedral groups whose elements are all parallelepipeds take the closed-form kernel (affine_hex.cuh; decided on the
+    device from the node coordinates): against the oracle, symmetric and full, with prestress, re-assembly, rhs only; and the
+    decision follows the coordinates (b200asm_set_nodes: perturbed -> Gram/DMMA kernel -> back)."""
+    n = 4
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, bc_matids=(-1, -1, -1, -1, -1, -2))
+    if shear:
+        _sheared(mesh)
+    mats = materials_for(phys, neumann=True)
+    if phys:
+        mats[1].fPreStress = [0.3, -0.2, 0.1]
+    for symmetric in (True, False):
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, scatter=scatter)
+        ia, ja, a, rhs = strmat.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+        a2, rhs2 = strmat.Assemble()
+        assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
+        assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+        # the same context with the closed form switched off must agree
+        strmat.ctx.set_option("affine", 0)
+        a3, rhs3 = strmat.Assemble()
+        assert relF(a3, a_ref) <= TOL and relF(rhs3, rhs_ref) <= TOL
+        strmat.ctx.set_option("affine", 1)
+        # move the nodes: no longer parallelepipeds -> the general kernel (and its scatter-map layout) takes over
+        moved = gridmesh.grid_mesh(n, p, 3 if phys else 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.1)
+        strmat.ctx.set_nodes(moved.nodes)
+        a4, rhs4 = strmat.Assemble()
+        a4_ref, rhs4_ref = oracle_assemble(moved, mats, symmetric, ia, ja)
+        assert relF(a4, a4_ref) <= TOL and relF(rhs4, rhs4_ref) <= TOL
+        strmat.ctx.set_nodes(mesh.nodes)
+        a5, rhs5 = strmat.Assemble()
+        assert relF(a5, a_ref) <= TOL and relF(rhs5, rhs_ref) <= TOL
+
+
 @pytest.mark.parametrize("n,p,phys,tet", [(5, 2, 0, 0), (4, 2, 0, 1)])
 def test_engines_agree(n, p, phys, tet):
     """Register-tile DFMA kernels (engine 0) and DMMA panel kernels (engine 1) against the oracle and each other."""
