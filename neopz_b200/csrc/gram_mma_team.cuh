@@ -181,6 +181,68 @@ __device__ __forceinline__ void team_epilogue(const VolParams &p, int64_t el, do
     }
 }
 
+// Elasticity with ONE tile group per warp (GPW == 1): the node-block pair (ib, jb) of a warp is a RUNTIME value, all warps
+// of the team run the same instructions.  (With compile-time roles the kernel carried WPE copies of the DMMA loop and of
+// the epilogue: the hex p=2 kernel stalled 23 % of its issue slots on instruction fetch, profiles/r01_ncu_full_final_team_hexp2elast.csv.)
+template <class C>
+__device__ __forceinline__ void team_mma_chunk_rt(const double *__restrict__ Pn, double (&acc)[C::GPW * C::TPG][2], int g, int tg, int ib, int jb) {
+    constexpr int LD = C::LD, NPAD = C::NPAD;
+    const bool diag = ib == jb;
+#pragma unroll
+    for (int s = 0; s < C::KC / 4; s++) {
+        const double *row = Pn + (4 * s + tg) * LD + g;
+        double fi[3], fj[3];
+#pragma unroll
+        for (int v = 0; v < 3; v++) fi[v] = row[v * NPAD + 8 * ib];
+        if (diag) {
+#pragma unroll
+            for (int u = 0; u < 3; u++) fj[u] = fi[u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < 3; u++) fj[u] = row[u * NPAD + 8 * jb];
+        }
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+#pragma unroll
+            for (int u = 0; u < 3; u++) dmma_m8n8k4(acc[v * 3 + u][0], acc[v * 3 + u][1], fi[v], fj[u]);
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void team_epilogue_rt(const VolParams &p, int64_t el, double (&acc)[C::GPW * C::TPG][2], int lane, int w) {
+    constexpr int TPG = C::TPG;
+    const int32_t *sm = p.smap + (size_t)el * C::SLOTS + (size_t)w * TPG * 64 + lane;
+    const int32_t *smT = p.smapT ? p.smapT + (size_t)el * C::SLOTS + (size_t)w * TPG * 64 + lane : nullptr;
+    int32_t pos[TPG * 2];
+#pragma unroll
+    for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(sm + k * 32);  // positions first: the atomics would serialise the loads
+    double val[TPG * 2];
+    const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        double S[3][3];
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+#pragma unroll
+            for (int u = 0; u < 3; u++) S[v][u] = acc[v * 3 + u][e];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                double x;
+                if (a == b) x = (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3;
+                else x = S[b][a] * C1 - S[a][b] * C2;
+                val[(a * 3 + b) * 2 + e] = x;
+            }
+    }
+    scatter_many<TPG * 2>(p.a, pos, val, p.atomic);
+    if (smT) {
+#pragma unroll
+        for (int k = 0; k < TPG * 2; k++) pos[k] = __ldcs(smT + k * 32);
+        scatter_many<TPG * 2>(p.a, pos, val, p.atomic);
+    }
+}
+
 template <class C, int W>
 struct TeamRole {
     __device__ static __forceinline__ void mma(int w, const double *Pn, double (&acc)[C::GPW * C::TPG][2], int g, int tg) {
@@ -214,6 +276,8 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
     for (int i = tt; i < 2 * KC * LD; i += TT) Pn[i] = 0.0;  // padding columns stay zero (both panel buffers)
     team_sync<TT>(team);
     const int g = lane >> 2, tg = lane & 3;
+    constexpr bool RT = C::NS == 3 && C::SB == 0 && C::GPW == 1;  // runtime warp roles (one tile group per warp)
+    const int rt_ib = C::group_ib(w < C::NGROUPS ? w : 0), rt_jb = C::group_jb(w < C::NGROUPS ? w : 0);
     const int64_t nteams = (int64_t)gridDim.x * C::EPC;
     // the load vector needs the panel point by point only for a forcing-function table or a non-zero prestress
     const bool pointwise = p.force != nullptr || (NS == 3 && (p.coef[6] != 0.0 || p.coef[7] != 0.0 || p.coef[8] != 0.0));
@@ -326,7 +390,13 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
             const double *Pc = Pn + buf * (KC * LD);
             if (q0 + QC < nq) build_panel(q0 + QC, Pn + (buf ^ 1) * (KC * LD));
             // ---- phase 3: Gram update by every warp for its tile groups --------------------------------
-            if (!p.rhs_only) TeamRole<C, 0>::mma(w, Pc, acc, g, tg);
+            if (!p.rhs_only) {
+                if constexpr (RT) {
+                    if (w < C::NGROUPS) team_mma_chunk_rt<C>(Pc, acc, g, tg, rt_ib, rt_jb);
+                } else {
+                    TeamRole<C, 0>::mma(w, Pc, acc, g, tg);
+                }
+            }
             // ---- load vector, point-wise part (forcing-function table and/or prestress only) ------------------
             if (pointwise) {
 #pragma unroll
@@ -356,7 +426,13 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
             const int m = tt + k * TT;
             if (m < M) scatter_rhs(p.rhs, p.dest[el * M + m], facc[k], p.atomic);
         }
-        if (!p.rhs_only) TeamRole<C, 0>::epilogue(w, p, el, acc, lane);
+        if (!p.rhs_only) {
+            if constexpr (RT) {
+                if (w < C::NGROUPS) team_epilogue_rt<C>(p, el, acc, lane, w);
+            } else {
+                TeamRole<C, 0>::epilogue(w, p, el, acc, lane);
+            }
+        }
     }
 }
 
