@@ -15,6 +15,7 @@
 #ifndef B200ASM_H
 #define B200ASM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -142,6 +143,11 @@ int b200asm_assemble_async(b200asm_ctx *ctx);
 int b200asm_synchronize(b200asm_ctx *ctx);
 /* copy the device-resident result to the host (synchronous) */
 int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_host);
+/* Page-lock / release a host buffer the caller owns (cudaHostRegister / cudaHostUnregister), e.g. the storage of a
+ * TPZSYsmpMatrix (Matrix/pzsysmp.h:223-229): b200asm_assemble then downloads into it at PCIe speed and overlapped with the
+ * kernels.  The buffer must be released before its owner frees it. */
+int b200asm_pin_host(b200asm_ctx *ctx, void *ptr, size_t bytes);
+int b200asm_unpin_host(b200asm_ctx *ctx, void *ptr);
 /* device pointers of the resident CSR values / rhs (for a GPU solver downstream) */
 int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double **rhs_dev);
 /* ---- solve (device resident) ------------------------------------------------------------------

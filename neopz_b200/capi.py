@@ -44,7 +44,7 @@ SYMBOLS = [
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
     "b200asm_nshape", "b200asm_orientation_keys", "b200asm_shape_tables_oriented",
     "b200asm_build_pattern_device", "b200asm_get_pattern", "b200asm_cg_solve", "b200asm_cg_solution_device",
-    "b200asm_assemble_rhs", "b200asm_get_ja_range",
+    "b200asm_assemble_rhs", "b200asm_get_ja_range", "b200asm_pin_host", "b200asm_unpin_host",
 ]
 
 
@@ -73,6 +73,8 @@ def lib():
     L.b200asm_assemble.argtypes = [vp, dp, dp]
     L.b200asm_assemble_async.argtypes = [vp]
     L.b200asm_assemble_rhs.argtypes = [vp, dp]
+    L.b200asm_pin_host.argtypes = [vp, C.c_void_p, C.c_size_t]
+    L.b200asm_unpin_host.argtypes = [vp, C.c_void_p]
     L.b200asm_synchronize.argtypes = [vp]
     L.b200asm_download.argtypes = [vp, dp, dp]
     L.b200asm_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]

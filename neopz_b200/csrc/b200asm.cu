@@ -937,12 +937,15 @@ using TetP2ElastTeamV6 = TeamCfg<4, 10, 3, 3, 5, 2>;
 using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
 using HexP2ElastTeamV1 = TeamCfg<8, 27, 3, 5, 1, 2>;   // two tile groups per warp (154 registers, 10 warps/SM)
 using HexP2ElastTeamV2 = TeamCfg<8, 27, 3, 10, 1, 3>;
+using HexP2ElastTeamV3 = TeamCfg<8, 27, 3, 10, 2, 1>;  // DEFAULT: two teams per CTA, 20 warps = 5 per scheduler (a 10-warp CTA leaves
+                                                       // 3,3,2,2): 30.3 vs 29.0 M el/s at 64^3; the same change on p4 Poisson lost 3 %
 // higher-order Poisson: one warp per 4x4 superblock of 8x8 tiles (p=3: 8x8 tiles -> 3 warps; p=4: 16x16 -> 10 warps)
 using HexP2PoissonTeamV4 = TeamCfg<8, 27, 1, 3, 4, 2, 2>;   // 3 warps per element (2x2-tile superblocks), 4 elements per CTA
 using HexP2PoissonTeamV5 = TeamCfg<8, 27, 1, 3, 4, 3, 2>;
 using HexP2PoissonTeamV6 = TeamCfg<8, 27, 1, 3, 8, 1, 2>;
 using HexP3PoissonTeam = TeamCfg<8, 64, 1, 3, 2, 3, 4>;
 using HexP4PoissonTeam = TeamCfg<8, 125, 1, 10, 1, 2, 4>;
+using HexP4PoissonTeamV1 = TeamCfg<8, 125, 1, 10, 2, 1, 4>;  // two teams per CTA (5 warps per scheduler)
 
 template <class C>
 cudaError_t launch_team(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
@@ -1020,7 +1023,7 @@ void aff_tables(int nq, const double *qw, const double *phi, const double *dphi,
 const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP1ElastAff>(1),
                          make_aff_entry<TetP2PoissonAff>(2), make_aff_entry<TetP2ElastAff>(2),
                          make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2, 7),
-                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
+                         make_team_entry<HexP2ElastTeamV3>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
                          make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
                          make_mma_entry<HexP2PoissonMmaV1>(B200ASM_HEX, 2, 1), make_mma_entry<HexP2PoissonMmaV2>(B200ASM_HEX, 2, 2),
@@ -1030,7 +1033,8 @@ const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP
                          make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 7), make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1),
                          make_team_entry<TetP2ElastTeamV3>(B200ASM_TET, 2, 3), make_team_entry<TetP2ElastTeamV4>(B200ASM_TET, 2, 4),
                          make_team_entry<TetP2ElastTeamV5>(B200ASM_TET, 2, 5), make_team_entry<TetP2ElastTeamV6>(B200ASM_TET, 2, 6),
-                         make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2)};
+                         make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2),
+                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2, 3), make_team_entry<HexP4PoissonTeamV1>(B200ASM_HEX, 4, 1)};
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
@@ -1934,6 +1938,20 @@ extern "C" int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_ho
     int rc = b200asm_assemble_async(ctx);
     if (rc) return rc;
     return b200asm_download(ctx, a_host, rhs_host);
+}
+
+extern "C" int b200asm_pin_host(b200asm_ctx *ctx, void *ptr, size_t bytes) {
+    if (!ctx || !ptr || !bytes) return fail(ctx, B200ASM_EINVAL, "pin_host: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+extern "C" int b200asm_unpin_host(b200asm_ctx *ctx, void *ptr) {
+    if (!ctx || !ptr) return fail(ctx, B200ASM_EINVAL, "unpin_host: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(ptr));
+    return 0;
 }
 
 extern "C" int b200asm_assemble_rhs(b200asm_ctx *ctx, double *rhs_host) {

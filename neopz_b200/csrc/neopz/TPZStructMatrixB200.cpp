@@ -142,7 +142,15 @@ struct TPZB200AssemblyCache {
     bool pattern_set = false;
     std::vector<HostGroup> groups;
     double flatten_ms = 0, pattern_ms = 0, assemble_ms = 0;
+    void *pinned = nullptr;  // value array page-locked by SetPinHostMatrix
+    size_t pinned_bytes = 0;
+    void Unpin() {
+        if (pinned && ctx) b200asm_unpin_host(ctx, pinned);
+        pinned = nullptr;
+        pinned_bytes = 0;
+    }
     ~TPZB200AssemblyCache() {
+        Unpin();
         if (ctx) b200asm_destroy(ctx);
     }
 };
@@ -464,18 +472,24 @@ TPZStructMatrixB200<TVar>::TPZStructMatrixB200() : fCache(std::make_shared<TPZB2
 // copies (TPZStructMatrix::Clone through TPZAnalysis::SetStructuralMatrix) start with an empty cache
 template <class TVar>
 TPZStructMatrixB200<TVar>::TPZStructMatrixB200(const TPZStructMatrixB200 &copy)
-    : TPZStrMatParInterface(copy), fDevice(copy.fDevice), fCache(std::make_shared<TPZB200AssemblyCache>()) {}
+    : TPZStrMatParInterface(copy), fDevice(copy.fDevice), fPinHost(copy.fPinHost), fCache(std::make_shared<TPZB200AssemblyCache>()) {}
 
 template <class TVar>
 TPZStructMatrixB200<TVar> &TPZStructMatrixB200<TVar>::operator=(const TPZStructMatrixB200 &copy) {
     TPZStrMatParInterface::operator=(copy);
     fDevice = copy.fDevice;
+    fPinHost = copy.fPinHost;
     fCache = std::make_shared<TPZB200AssemblyCache>();
     return *this;
 }
 
 template <class TVar>
 TPZStructMatrixB200<TVar>::~TPZStructMatrixB200() = default;
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::UnpinHostMatrix() {
+    fCache->Unpin();
+}
 
 template <class TVar>
 void TPZStructMatrixB200<TVar>::LastTimings(double &flatten_ms, double &pattern_ms, double &assemble_ms) const {
@@ -538,6 +552,12 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     if (ComputeRhs()) {
         rhsloc.Redim(c.nactive, 1);
         rhsptr = &rhsloc(0, 0);
+    }
+    if (fPinHost && nnz > 0 && (c.pinned != values || c.pinned_bytes != (size_t)nnz * sizeof(double))) {
+        c.Unpin();
+        Check(c, b200asm_pin_host(c.ctx, values, (size_t)nnz * sizeof(double)), "b200asm_pin_host");
+        c.pinned = values;
+        c.pinned_bytes = (size_t)nnz * sizeof(double);
     }
     Check(c, b200asm_assemble(c.ctx, values, rhsptr), "b200asm_assemble");
     if (rhsptr) {

@@ -62,6 +62,11 @@ public:
     //! CUDA device used by this strategy (default 0).
     void SetDevice(int device) { fDevice = device; }
     int Device() const { return fDevice; }
+    //! Page-lock the value array of the matrix handed to Assemble() (cudaHostRegister, once per array): the download then
+    //! runs at PCIe speed and overlaps the kernels.  Off by default because the array belongs to the caller's matrix:
+    //! call UnpinHostMatrix() (or destroy / reassign this object) BEFORE that matrix is destroyed.
+    void SetPinHostMatrix(bool pin) { fPinHost = pin; }
+    void UnpinHostMatrix();
     //! Milliseconds the last Assemble() spent in flatten / pattern upload / device assembly + copies.
     void LastTimings(double &flatten_ms, double &pattern_ms, double &assemble_ms) const;
 
@@ -79,6 +84,7 @@ protected:
     template <class T>
     friend class TPZSpStructMatrixB200;
     int fDevice{0};
+    bool fPinHost{false};
     std::shared_ptr<TPZB200AssemblyCache> fCache;
 };
 

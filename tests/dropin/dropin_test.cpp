@@ -105,6 +105,7 @@ struct Csr {
     int64_t device_cg_iters = 0;
 };
 
+static int g_pin = 0;     // 1: TPZStructMatrixB200::SetPinHostMatrix(true) — the matrix values are page-locked for the download
 static int g_filter = 0;  // 1: an equation filter keeps the upper three quarters of the equations (TPZEquationFilter::SetMinMaxEq)
 
 template <class TStrMat>
@@ -113,6 +114,8 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
     TStrMat strmat(cmesh);
     strmat.SetNumThreads(nthreads);
     if (g_filter) strmat.EquationFilter().SetMinMaxEq(cmesh->NEquations() / 4, cmesh->NEquations());
+    if (g_pin)
+        if (auto *b = dynamic_cast<TPZStructMatrixB200<STATE> *>(&strmat)) b->SetPinHostMatrix(true);
     an.SetStructuralMatrix(strmat);
     TPZStepSolver<STATE> step;
     step.SetDirect(symmetric ? ELDLt : ELU);  // never decomposed: the CG below is run on the assembled matrix
@@ -176,6 +179,8 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
         TPZFMatrix<STATE> &res = an.Rhs();
         for (int64_t i = 0; i < neq; i++) out.residual_rhs[i] = res(i, 0);
     }
+    // the value array belongs to the analysis' matrix: release the page lock before the analysis goes away
+    if (auto *b = dynamic_cast<TPZStructMatrixB200<STATE> *>(an.StructMatrix().operator->())) b->UnpinHostMatrix();
 }
 
 static double RelF(const std::vector<double> &x, const std::vector<double> &ref) {
@@ -198,6 +203,7 @@ int main(int argc, char **argv) {
     // 1: TPZSSpStructMatrixB200 / TPZSpStructMatrixB200, whose Create() builds the CSR pattern on the GPU
     const int device_create = argc > 8 ? atoi(argv[8]) : 0;
     g_filter = argc > 9 ? atoi(argv[9]) : 0;
+    g_pin = argc > 10 ? atoi(argv[10]) : 0;
     TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3);
     Csr ref, refmt, gpu;
     double t1, t2, tm1, tm2, g1, g2;
@@ -244,7 +250,7 @@ int main(int argc, char **argv) {
     const int64_t nvol = phys >= 2 ? (int64_t)n * n * (tet ? 2 : 1) : (int64_t)n * n * n * (tet ? 5 : 1);
     const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
-    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"cpu_first_assemble_s\": " << t1
+    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"cpu_first_assemble_s\": " << t1
               << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
               << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
               << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel

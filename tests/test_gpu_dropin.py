@@ -60,3 +60,19 @@ def test_dropin_with_equation_filter(case):
     assert r["ia_identical"] == 1 and r["ja_identical"] == 1
     assert r["relF_A"] <= 1e-12 and r["relF_rhs"] <= 1e-12 and r["relF_residual_rhs"] <= 1e-12
     assert out.returncode == 0
+
+
+@pytest.mark.parametrize("case", [(6, 2, 0, 0, 1, 0), (5, 2, 1, 0, 0, 0)])
+def test_dropin_with_pinned_host_matrix(case):
+    """SetPinHostMatrix(true): the strategy page-locks the TPZSYsmpMatrix / TPZFYsmpMatrix value array (b200asm_pin_host) so
+    that the download runs from pinned memory, overlapped with the kernels; same results, lock released before teardown."""
+    if not os.path.exists(BIN):
+        pytest.skip("tests/_bin/dropin_test not built (needs /root/reference at build time)")
+    out = subprocess.run([BIN] + [str(x) for x in case] + ["4", "0", "0", "1"], capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(lines[-1])
+    assert r["pin_host"] == 1
+    assert r["ia_identical"] == 1 and r["ja_identical"] == 1
+    assert r["relF_A"] <= 1e-12 and r["relF_rhs"] <= 1e-12 and r["relF_residual_rhs"] <= 1e-12
+    assert out.returncode == 0
