@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--cg", type=int, default=0, help="also time N iterations of the device-resident CG (reported as extra keys)")
     ap.add_argument("--perturb", type=float, default=0.1, help="smooth node perturbation in units of h (default 0.1: general trilinear "
                     "hexahedra; 0 = the uniform grid of CreateGeoMeshOnGrid, whose parallelepiped cells take the closed-form kernel)")
+    ap.add_argument("--locality", type=int, default=1, help="0: keep the mesh (lexicographic) element order on the device")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -245,6 +246,8 @@ def main():
     strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter, variant=a.variant)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
+    if not a.locality:
+        strmat.ctx.set_option("locality", 0)
     if a.debug:
         strmat.ctx.set_option("debug", a.debug)
     t0 = time.time()
@@ -439,7 +442,7 @@ def main():
             "config": {"workload": workload_name(a) if world == 1 else workload_name(a).replace(f"{a.n}^3", f"{a.n}x{a.n}x{a.n * world}") +
                        f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
-                       "perturbed_nodes": a.perturb != 0.0, "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
+                       "perturbed_nodes": a.perturb != 0.0, "element_order": "Morton curve inside 16 element chunks" if a.locality else "mesh order", "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
                                    "pattern_builder": a.pattern}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}

@@ -94,6 +94,9 @@ int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
  * "affine" (default 1: hexahedral groups of order <= 2 whose elements are ALL parallelepipeds - measured on the device from
  * the node coordinates, to 1e-13 of the shortest edge vector, again after every b200asm_set_nodes - run the closed-form
  * kernel: constant Jacobian, no quadrature loop; 0: always the Gram / DMMA kernels),
+ * "locality" (default 1, before add_group: volume groups are stored along a Morton curve through the element centroids,
+ * inside every overlap chunk, when b200asm_set_nodes was called first: the rows of A an element shares with its neighbours
+ * are then revisited while they are still in L2),
  * "overlap" (default 1: b200asm_assemble with a host matrix copies the finished rows of A back while later element
  * chunks are still being assembled; "overlap_min_elements" (before add_group) and "overlap_min_bytes" tune the chunking) */
 int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);

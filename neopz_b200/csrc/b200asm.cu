@@ -796,6 +796,8 @@ struct b200asm_ctx {
     int variant = 0;   // tuning alternative of the DMMA kernels (option "variant", before add_group)
     int rhs_only = 0;  // set while b200asm_assemble_rhs runs
     int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
+    int locality = 1;  // 1: volume groups are stored along a space-filling curve (within every overlap chunk), see add_group
+    std::vector<double> h_xyz;  // host copy of the node coordinates (element centroids for the locality order)
     int affine = 1;   // 1: hexahedral groups whose elements are all parallelepipeds use the closed-form kernel
     int overlap = 1;  // 1: b200asm_assemble downloads the finished rows of A while later element chunks are assembled
     int64_t overlap_min_elements = 8192;      // smallest element chunk (option, before add_group)
@@ -1316,6 +1318,11 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
         ctx->overlap = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "locality")) {
+        if (!ctx->groups.empty()) return fail(ctx, B200ASM_ESTATE, "locality: set it before the first b200asm_add_group");
+        ctx->locality = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "affine")) {
         ctx->affine = value ? 1 : 0;
         for (Group &g : ctx->groups) g.aff_checked = false;
@@ -1347,6 +1354,7 @@ extern "C" int b200asm_set_nodes(b200asm_ctx *ctx, int64_t nnodes, const double 
     CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)nnodes * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += nnodes * 3 * (int64_t)sizeof(double);
     for (Group &g : ctx->groups) g.aff_checked = false;  // parallelepiped or not is a property of the coordinates
+    if (ctx->groups.empty()) ctx->h_xyz.assign(xyz, xyz + (size_t)nnodes * 3);  // (only add_group reads it)
     return 0;
 }
 
@@ -1409,6 +1417,67 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         std::vector<int64_t> cursor(count.begin(), count.end() - 1);
         for (int64_t e = 0; e < g.nel; e++) order[cursor[colour[e]]++] = e;  // stable within a colour
     }
+    // element chunks for the overlapped download: boundaries are multiples of every kernel's batch size
+    {
+        constexpr int64_t kAlign = 384, kMaxChunks = 16;
+        int64_t nch = 1;
+        if (volume && g.seg.size() == 2) nch = std::max<int64_t>(1, std::min<int64_t>(kMaxChunks, g.nel / ctx->overlap_min_elements));
+        g.chunk.assign(1, 0);
+        for (int64_t c = 1; c < nch; c++) {
+            const int64_t b = (g.nel * c / nch) / kAlign * kAlign;
+            if (b > g.chunk.back()) g.chunk.push_back(b);
+        }
+        g.chunk.push_back(g.nel);
+    }
+    // locality order (atomic scatter, node coordinates already known): inside every chunk the elements follow a Morton
+    // curve through their centroids.  The persistent grid works on a window of a few thousand consecutive elements; in mesh
+    // (lexicographic) order that window is a thin sheet and the CSR rows shared with the next sheet leave L2 before their
+    // last contribution arrives (the read-modify-write of A then costs HBM traffic twice); along the curve it is a compact
+    // block.  Chunks keep their element sets, so the download frontier of assemble_overlapped is unchanged.
+    if (volume && ctx->locality && g.seg.size() == 2 && g.nel >= 4096 && (int64_t)ctx->h_xyz.size() == ctx->nnodes * 3) {
+        std::vector<float> cen((size_t)g.nel * 3);
+        float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        bool ok = true;
+        for (int64_t e = 0; e < g.nel && ok; e++) {
+            double c[3] = {0, 0, 0};
+            for (int k = 0; k < g.nn; k++) {
+                const int64_t node = gi->elnodes[e * g.nn + k];
+                if (node < 0 || node >= ctx->nnodes) { ok = false; break; }
+                for (int r = 0; r < 3; r++) c[r] += ctx->h_xyz[(size_t)node * 3 + r];
+            }
+            for (int r = 0; r < 3; r++) {
+                const float v = (float)(c[r] / g.nn);
+                cen[(size_t)e * 3 + r] = v;
+                lo[r] = std::min(lo[r], v);
+                hi[r] = std::max(hi[r], v);
+            }
+        }
+        if (ok) {
+            auto spread = [](uint64_t x) {  // 21 bits -> every third bit
+                x &= 0x1fffff;
+                x = (x | x << 32) & 0x1f00000000ffffull;
+                x = (x | x << 16) & 0x1f0000ff0000ffull;
+                x = (x | x << 8) & 0x100f00f00f00f00full;
+                x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+                x = (x | x << 2) & 0x1249249249249249ull;
+                return x;
+            };
+            // cells of one size in all directions (the longest extent spans 2^10 cells)
+            const float ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-30f});
+            const float scale = 1023.0f / ext;
+            std::vector<std::pair<uint64_t, int64_t>> keyed;
+            for (size_t c = 0; c + 1 < g.chunk.size(); c++) {
+                keyed.clear();
+                for (int64_t e = g.chunk[c]; e < g.chunk[c + 1]; e++) {
+                    uint64_t key = 0;
+                    for (int r = 0; r < 3; r++) key |= spread((uint64_t)((cen[(size_t)e * 3 + r] - lo[r]) * scale)) << r;
+                    keyed.emplace_back(key, e);
+                }
+                std::sort(keyed.begin(), keyed.end());
+                for (size_t k = 0; k < keyed.size(); k++) order[g.chunk[c] + (int64_t)k] = keyed[k].second;
+            }
+        }
+    }
     // destination indices as int32 (the reference's own CSR loops are 32-bit: Matrix/pzsysmp.cpp:62,73)
     std::vector<int32_t> dest32((size_t)g.nel * g.m);
     std::vector<int32_t> elnodes((size_t)g.nel * g.nn);
@@ -1422,25 +1491,14 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         }
         for (int k = 0; k < g.nn; k++) elnodes[(size_t)e * g.nn + k] = gi->elnodes[src * g.nn + k];
     }
-    // element chunks for the overlapped download: boundaries are multiples of every kernel's batch size
-    {
-        constexpr int64_t kAlign = 384, kMaxChunks = 16;
-        int64_t nch = 1;
-        if (volume && g.seg.size() == 2) nch = std::max<int64_t>(1, std::min<int64_t>(kMaxChunks, g.nel / ctx->overlap_min_elements));
-        g.chunk.assign(1, 0);
-        for (int64_t c = 1; c < nch; c++) {
-            const int64_t b = (g.nel * c / nch) / kAlign * kAlign;
-            if (b > g.chunk.back()) g.chunk.push_back(b);
-        }
-        g.chunk.push_back(g.nel);
-        g.chunk_min.assign(g.chunk.size() - 1, INT64_MAX);
-        for (size_t c = 0; c + 1 < g.chunk.size(); c++) {
-            int32_t mn = INT32_MAX;
-            const int32_t *d = dest32.data() + (size_t)g.chunk[c] * g.m, *dend = dest32.data() + (size_t)g.chunk[c + 1] * g.m;
-            for (; d < dend; d++)
-                if (*d >= 0 && *d < mn) mn = *d;
-            if (mn != INT32_MAX) g.chunk_min[c] = mn;
-        }
+    // smallest destination equation of every chunk (chunks are sets of elements: the order inside does not matter)
+    g.chunk_min.assign(g.chunk.size() - 1, INT64_MAX);
+    for (size_t c = 0; c + 1 < g.chunk.size(); c++) {
+        int32_t mn = INT32_MAX;
+        const int32_t *d = dest32.data() + (size_t)g.chunk[c] * g.m, *dend = dest32.data() + (size_t)g.chunk[c + 1] * g.m;
+        for (; d < dend; d++)
+            if (*d >= 0 && *d < mn) mn = *d;
+        if (mn != INT32_MAX) g.chunk_min[c] = mn;
     }
     // gradients of the geometric (corner) functions at the points = the p=1 shape gradients
     std::vector<double> gphi((size_t)g.nq * g.nn), dng((size_t)g.nq * g.dim * g.nn);

@@ -419,6 +419,31 @@ def test_parallelepiped_hexahedra_closed_form(p, phys, scatter, shear):
         assert relF(a5, a_ref) <= TOL and relF(rhs5, rhs_ref) <= TOL
 
 
+@pytest.mark.parametrize("n,p,phys,tet,perturb", [(17, 1, 0, 0, 0.1), (10, 2, 1, 1, 0.1), (17, 1, 1, 0, 0.0), (16, 2, 0, 0, 0.1)])
+def test_locality_order_matches_oracle(n, p, phys, tet, perturb):
+    """Groups of >= 4096 elements are stored along a Morton curve (option "locality"): same matrix as the oracle's mesh-order
+    assembly and as the context that keeps the mesh order; forcing tables and the overlapped download follow the permutation."""
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=bool(tet), bc_matids=(-1, -1, -1, -1, -1, -2), perturb=perturb)
+    assert len(mesh.blocks[0].elnodes) >= 4096
+    mats = materials_for(phys, neumann=True)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True)
+    strmat.ctx.set_option("overlap_min_elements", 1024)
+    strmat.ctx.set_option("overlap_min_bytes", 0)
+    ia, ja, a, rhs = strmat.CreateAssemble()
+    plain = sm.TPZStructMatrixB200(mesh, mats, symmetric=True)
+    plain.ctx.set_option("locality", 0)
+    plain.SetPattern(ia, ja)
+    a0, rhs0 = plain.Assemble()
+    assert relF(a, a0) <= TOL and relF(rhs, rhs0) <= TOL
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+    import torch
+    ah = torch.full((len(ja),), float("nan"), dtype=torch.float64).pin_memory().numpy()
+    rh = torch.full((mesh.neq,), float("nan"), dtype=torch.float64).pin_memory().numpy()
+    strmat.Assemble(ah, rh)   # overlapped download, chunks of the permuted group
+    assert relF(ah, a_ref) <= TOL and relF(rh, rhs_ref) <= TOL
+
+
 @pytest.mark.parametrize("n,p,phys,tet", [(5, 2, 0, 0), (4, 2, 0, 1)])
 def test_engines_agree(n, p, phys, tet):
     """Register-tile DFMA kernels (engine 0) and DMMA panel kernels (engine 1) against the oracle and each other."""
