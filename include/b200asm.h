@@ -24,8 +24,9 @@ extern "C" {
 
 typedef struct b200asm_ctx b200asm_ctx;
 
-/* element topologies (reference: MElementType ECube/ETetraedro/EQuadrilateral/ETriangle) */
-enum { B200ASM_HEX = 0, B200ASM_TET = 1, B200ASM_QUAD = 2, B200ASM_TRI = 3, B200ASM_LINE = 4 /* EOned */ };
+/* element topologies (reference: MElementType ECube/ETetraedro/EQuadrilateral/ETriangle/EOned/EPrisma/EPiramide, Common/pzeltype.h:52-62) */
+enum { B200ASM_HEX = 0, B200ASM_TET = 1, B200ASM_QUAD = 2, B200ASM_TRI = 3, B200ASM_LINE = 4 /* EOned */,
+       B200ASM_PRISM = 5 /* EPrisma: TPZShapePrism / TPZGeoPrism */, B200ASM_PYRAMID = 6 /* EPiramide: TPZShapePiram / TPZGeoPyramid */ };
 /* weak forms:
  *  POISSON       Material/Poisson/TPZMatPoisson.cpp:19-42
  *  ELASTICITY3D  Material/Elasticity/TPZElasticity3D.cpp:85-107,269-372
@@ -59,7 +60,7 @@ enum {
  */
 typedef struct {
     int32_t topology; /* B200ASM_HEX ... */
-    int32_t porder;   /* uniform order of every connect of the batch (1 or 2) */
+    int32_t porder;   /* uniform order of every connect of the batch (hex / quad / line: 1..4; tet / tri / prism / pyramid: 1, 2) */
     int32_t kind;     /* B200ASM_POISSON ... */
     int32_t nstate;   /* TPZMaterial::NStateVariables(): 1 or 3 */
     int64_t nel;
@@ -181,10 +182,15 @@ int b200asm_gauss_legendre(int order, double *loc, double *w);
 /* tensor rules for hexahedra / quadrilaterals of order 2p in the reference's point order
  * (Integral/pzquad.cpp:153-169,268-284).  Returns the number of points. */
 int b200asm_tensor_rule(int topology, int order, double *qpts, double *qw);
-/* H1 shape tables (uniform p<=2) at given master-element points.  Returns nshape. */
+/* prism rule of the reference (TPZIntPrism3D, Integral/pzquad.cpp:408-436): the Gauss-Legendre line rule of `order` in zeta times
+ * a triangle rule in (xi, eta) supplied by the caller (the reference's triangle tables are data, Integral/tpzintrulet.cpp);
+ * triangle point fastest, weight = line weight * triangle weight.  Returns the number of points. */
+int b200asm_prism_rule(int order, int ntri, const double *tripts, const double *triw, double *qpts, double *qw);
+/* H1 shape tables (uniform p<=2) at given master-element points.  Returns nshape.  Prisms: Shape/pzshapeprism.cpp:42-205;
+ * pyramids: Shape/pzshapepiram.cpp:47-119,331-392 (rational corner functions; points must stay off the apex). */
 int b200asm_shape_tables(int topology, int porder, int nqp, const double *qpts, double *phi, double *dphi);
 /* number of H1 shape functions of an element of uniform order p (TSHAPE::NShapeF): hex (p+1)^3, quad (p+1)^2;
- * tetrahedra / triangles for p <= 2. */
+ * tetrahedra / triangles / prisms (6, 18) / pyramids (5, 14) for p <= 2. */
 int b200asm_nshape(int topology, int porder);
 /* Side-orientation key of every element from the GLOBAL indices of its corner nodes (what
  * ComputeTransforms / GetTransformId derive per side: Shape/pzgenericshape.cpp:57-68, Topology/tpzcube.cpp:1059-1111,

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200asm.so")
 
-HEX, TET, QUAD, TRI, LINE = 0, 1, 2, 3, 4
+HEX, TET, QUAD, TRI, LINE, PRISM, PYRAMID = 0, 1, 2, 3, 4, 5, 6
 POISSON, ELASTICITY3D, BC, ELASTICITY2D = 0, 1, 2, 3
 ENODEVICE = -2
 
@@ -44,7 +44,7 @@ SYMBOLS = [
     "b200asm_gauss_legendre", "b200asm_tensor_rule", "b200asm_shape_tables", "b200asm_build_pattern",
     "b200asm_nshape", "b200asm_orientation_keys", "b200asm_shape_tables_oriented",
     "b200asm_build_pattern_device", "b200asm_get_pattern", "b200asm_cg_solve", "b200asm_cg_solution_device",
-    "b200asm_assemble_rhs", "b200asm_get_ja_range", "b200asm_pin_host", "b200asm_unpin_host",
+    "b200asm_assemble_rhs", "b200asm_get_ja_range", "b200asm_pin_host", "b200asm_unpin_host", "b200asm_prism_rule",
 ]
 
 
@@ -84,6 +84,7 @@ def lib():
     L.b200asm_gauss_legendre.argtypes = [C.c_int, dp, dp]
     L.b200asm_tensor_rule.argtypes = [C.c_int, C.c_int, dp, dp]
     L.b200asm_shape_tables.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.b200asm_prism_rule.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp]
     L.b200asm_build_pattern_device.argtypes = [vp, C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64]
     L.b200asm_get_pattern.argtypes = [vp, ip64, ip64]
     L.b200asm_get_ja_range.argtypes = [vp, C.c_int64, C.c_int64, ip64]
@@ -118,6 +119,18 @@ def tensor_rule(topology, order):
     n = lib().b200asm_tensor_rule(topology, order, dptr(pts), dptr(w))
     if n < 0:
         raise B200AsmError(n, "tensor_rule")
+    return pts[:n].copy(), w[:n].copy()
+
+
+def prism_rule(order, tripts, triw):
+    """TPZIntPrism3D: line rule of `order` x the given triangle rule (triangle point fastest)."""
+    tripts = np.ascontiguousarray(tripts, dtype=np.float64)
+    triw = np.ascontiguousarray(triw, dtype=np.float64)
+    pts = np.zeros((64 * len(triw), 3))
+    w = np.zeros(len(pts))
+    n = lib().b200asm_prism_rule(order, len(triw), dptr(tripts), dptr(triw), dptr(pts), dptr(w))
+    if n < 0:
+        raise B200AsmError(n, "prism_rule")
     return pts[:n].copy(), w[:n].copy()
 
 

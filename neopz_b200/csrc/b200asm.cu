@@ -846,6 +846,16 @@ using TetP1Poisson = VolCfg<4, 4, 1, 4, 128>;
 using TetP1Elast = VolCfg<4, 4, 3, 6, 32>;
 using TetP2Poisson = VolCfg<4, 10, 1, 5, 32>;
 using TetP2Elast = VolCfg<4, 10, 3, 6, 8>;
+// prisms (6 corner nodes; p=2: 6 + 9 edges + 3 quadrilateral faces = 18 functions) and pyramids (5 corner nodes; p=2: 5 + 8 edges +
+// the base = 14 functions): same kernel, their own tables (rational corner functions of the pyramid included)
+using PrismP1Poisson = VolCfg<6, 6, 1, 6, 64>;
+using PrismP1Elast = VolCfg<6, 6, 3, 6, 16>;
+using PrismP2Poisson = VolCfg<6, 18, 1, 6, 16>;
+using PrismP2Elast = VolCfg<6, 18, 3, 9, 6>;
+using PyrP1Poisson = VolCfg<5, 5, 1, 5, 32>;
+using PyrP1Elast = VolCfg<5, 5, 3, 6, 16>;
+using PyrP2Poisson = VolCfg<5, 14, 1, 7, 16>;
+using PyrP2Elast = VolCfg<5, 14, 3, 6, 4>;
 
 struct VolEntry {
     int topology, porder, ns;
@@ -886,6 +896,10 @@ const VolEntry kVol[] = {
     make_entry<HexP3Poisson>(B200ASM_HEX, 3), make_entry<HexP4Poisson>(B200ASM_HEX, 4), make_entry<HexP3Elast>(B200ASM_HEX, 3),
     make_entry<TetP1Poisson>(B200ASM_TET, 1), make_entry<TetP1Elast>(B200ASM_TET, 1),
     make_entry<TetP2Poisson>(B200ASM_TET, 2), make_entry<TetP2Elast>(B200ASM_TET, 2),
+    make_entry<PrismP1Poisson>(B200ASM_PRISM, 1), make_entry<PrismP1Elast>(B200ASM_PRISM, 1),
+    make_entry<PrismP2Poisson>(B200ASM_PRISM, 2), make_entry<PrismP2Elast>(B200ASM_PRISM, 2),
+    make_entry<PyrP1Poisson>(B200ASM_PYRAMID, 1), make_entry<PyrP1Elast>(B200ASM_PYRAMID, 1),
+    make_entry<PyrP2Poisson>(B200ASM_PYRAMID, 2), make_entry<PyrP2Elast>(B200ASM_PYRAMID, 2),
 };
 constexpr int kNumVol = sizeof(kVol) / sizeof(kVol[0]);
 
@@ -1113,6 +1127,8 @@ int ncorner_of(int topology) {
         case B200ASM_TET: return 4;
         case B200ASM_QUAD: return 4;
         case B200ASM_TRI: return 3;
+        case B200ASM_PRISM: return 6;
+        case B200ASM_PYRAMID: return 5;
     }
     return -1;
 }
@@ -1366,10 +1382,11 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     g.nn = ncorner_of(gi->topology);
     g.n = nshape_of(gi->topology, gi->porder);
     g.nq = gi->nqp;
-    g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET) ? 3 : (gi->topology == B200ASM_LINE ? 1 : 2);
+    g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET || gi->topology == B200ASM_PRISM || gi->topology == B200ASM_PYRAMID)
+                ? 3 : (gi->topology == B200ASM_LINE ? 1 : 2);
     g.plane = g.dim == 2 && (gi->kind == B200ASM_POISSON || gi->kind == B200ASM_ELASTICITY2D);
     if (g.nn < 0 || g.n < 0 || gi->porder < 1)
-        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad 1..4, tet/tri 1..2)");
+        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad 1..4, tet/tri/prism/pyramid 1..2)");
     if (gi->nshape != g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not match topology/order");
     if (g.ns < 1 || g.ns > 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1, 2 or 3");
     if (g.nel < 0 || g.nq <= 0 || g.nq > 512) return fail(ctx, B200ASM_EINVAL, "add_group: bad nel/nqp");

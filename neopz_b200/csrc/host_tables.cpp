@@ -9,6 +9,8 @@
 //                 after the higher-side correction :131-143 collapses)
 //   tet / tri  : barycentric l_a and 4*l_a*l_b on the edges (Shape/pzshapetetra.cpp:53-164,
 //                pzshapetriang.cpp:34-81)
+//   prism      : (triangle set) x (line set)  (Shape/pzshapeprism.cpp:42-205)
+//   pyramid    : rational corner functions and their products (Shape/pzshapepiram.cpp:47-119,331-392)
 // Shape order = side order of the reference topology (Topology/tpzcube.cpp:30-80 etc.), which is
 // also the connect order and the local dof order of TPZElementMatrix.
 //
@@ -224,9 +226,113 @@ extern "C" int b200asm_tensor_rule(int topology, int order, double *qpts, double
     return B200ASM_EINVAL;
 }
 
+// TPZIntPrism3D (Integral/pzquad.cpp:408-436): point ip = (triangle point ip % ntri, line point ip / ntri), weight = line weight
+// (rounded to double) times triangle weight.  The triangle rule is a table of the reference and comes from the caller.
+extern "C" int b200asm_prism_rule(int order, int ntri, const double *tripts, const double *triw, double *qpts, double *qw) {
+    long double l[64], w[64];
+    const int n = gauss_legendre_ld(order, l, w);
+    if (n < 0 || ntri <= 0 || !tripts || !triw) return B200ASM_EINVAL;
+    for (int iz = 0; iz < n; iz++)
+        for (int it = 0; it < ntri; it++) {
+            const int ip = iz * ntri + it;
+            qpts[3 * ip + 0] = tripts[2 * it];
+            qpts[3 * ip + 1] = tripts[2 * it + 1];
+            qpts[3 * ip + 2] = (double)l[iz];
+            qw[ip] = (double)w[iz] * triw[it];
+        }
+    return n * ntri;
+}
+
+namespace {
+
+// Prism, p <= 2: tensor product of the triangle set { lam_a, 4 lam_a lam_b } with the line set { l0, l1, b = 4 l0 l1 }.
+// After the higher-side corrections of Shape/pzshapeprism.cpp:178-193 collapse (l0 + l1 = 1, lam0 + lam1 + lam2 = 1) the
+// functions of the sides are: bottom / top edges 4 lam_a lam_b l0 / l1, vertical edges lam_a b, quadrilateral faces
+// 4 lam_a lam_b b; the triangular faces and the interior carry none at p = 2 (NConnectShapeF :761-775).
+// Side order of Topology/tpzprism.h:275-278.
+void prism_shapes(int porder, const double *pt, int n, double *ph, double *dp) {
+    const double lam[3] = {1.0 - pt[0] - pt[1], pt[0], pt[1]};
+    static const double dlam[3][2] = {{-1.0, -1.0}, {1.0, 0.0}, {0.0, 1.0}};
+    double T[6], dT[6][2];  // triangle functions and their (xi, eta) gradients
+    for (int a = 0; a < 3; a++) {
+        T[a] = lam[a];
+        dT[a][0] = dlam[a][0];
+        dT[a][1] = dlam[a][1];
+    }
+    for (int e = 0; e < 3; e++) {
+        const int a = kTriEdge[e][0], b = kTriEdge[e][1];
+        T[3 + e] = 4.0 * (lam[a] * lam[b]);
+        for (int d = 0; d < 2; d++) dT[3 + e][d] = 4.0 * (dlam[a][d] * lam[b] + lam[a] * dlam[b][d]);
+    }
+    double f[3], df[3];
+    factors1d(pt[2], f, df);
+    // (triangle function, line factor) of every shape function, side by side
+    static const int kTri[18] = {0, 1, 2, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 3, 4, 5};
+    static const int kLin[18] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 2, 2, 2, 1, 1, 1, 2, 2, 2};
+    (void)porder;
+    for (int s = 0; s < n; s++) {
+        const int t = kTri[s], l = kLin[s];
+        ph[s] = T[t] * f[l];
+        dp[0 * n + s] = dT[t][0] * f[l];
+        dp[1 * n + s] = dT[t][1] * f[l];
+        dp[2 * n + s] = T[t] * df[l];
+    }
+}
+
+// Pyramid, p <= 2 (Shape/pzshapepiram.cpp:331-392, :47-119): the corner functions are the rational functions
+// phi_a = (1 - z -+ x)(1 - z -+ y) / (4 (1 - z)), phi_4 = z; edge functions 4 phi_a phi_b, to which the base edges add the base
+// function phi_0 phi_2 before the scaling; base 16 phi_0 phi_2.  Not defined at the apex (never an integration point).
+void pyramid_shapes(int porder, const double *pt, int n, double *ph, double *dp) {
+    const double x = pt[0], y = pt[1], z = pt[2];
+    const double h = 1.0 - z;
+    const double sx[4] = {-1.0, 1.0, 1.0, -1.0}, sy[4] = {-1.0, -1.0, 1.0, 1.0};
+    double v[14], g[14][3];
+    for (int a = 0; a < 4; a++) {
+        const double u = h + sx[a] * x, w = h + sy[a] * y;  // (1 - z +- x), (1 - z +- y)
+        v[a] = 0.25 * u * w / h;
+        g[a][0] = 0.25 * sx[a] * w / h;
+        g[a][1] = 0.25 * sy[a] * u / h;
+        g[a][2] = -0.25 * (u + w - u * w / h) / h;
+    }
+    v[4] = z;
+    g[4][0] = 0.0; g[4][1] = 0.0; g[4][2] = 1.0;
+    if (porder >= 2) {
+        auto product = [&](int s, int a, int b) {
+            v[s] = v[a] * v[b];
+            for (int d = 0; d < 3; d++) g[s][d] = g[a][d] * v[b] + v[a] * g[b][d];
+        };
+        product(13, 0, 2);
+        for (int e = 0; e < 4; e++) {
+            product(5 + e, e, (e + 1) & 3);
+            v[5 + e] += v[13];
+            for (int d = 0; d < 3; d++) g[5 + e][d] += g[13][d];
+            product(9 + e, e, 4);
+        }
+        for (int s = 5; s < 14; s++) {
+            const double scale = s < 13 ? 4.0 : 16.0;
+            v[s] *= scale;
+            for (int d = 0; d < 3; d++) g[s][d] *= scale;
+        }
+    }
+    for (int s = 0; s < n; s++) {
+        ph[s] = v[s];
+        for (int d = 0; d < 3; d++) dp[d * n + s] = g[s][d];
+    }
+}
+
+}  // namespace
+
 extern "C" int b200asm_shape_tables(int topology, int porder, int nqp, const double *qpts, double *phi, double *dphi) {
     if (porder < 1 || porder > 2) return B200ASM_EINVAL;
     int n = 0;
+    if (topology == B200ASM_PRISM || topology == B200ASM_PYRAMID) {
+        n = topology == B200ASM_PRISM ? (porder == 1 ? 6 : 18) : (porder == 1 ? 5 : 14);
+        for (int q = 0; q < nqp; q++) {
+            if (topology == B200ASM_PRISM) prism_shapes(porder, qpts + (size_t)q * 3, n, phi + (size_t)q * n, dphi + (size_t)q * 3 * n);
+            else pyramid_shapes(porder, qpts + (size_t)q * 3, n, phi + (size_t)q * n, dphi + (size_t)q * 3 * n);
+        }
+        return n;
+    }
     switch (topology) {
         case B200ASM_HEX: n = porder == 1 ? 8 : 27; break;
         case B200ASM_QUAD: n = porder == 1 ? 4 : 9; break;
@@ -305,6 +411,8 @@ extern "C" int b200asm_nshape(int topology, int porder) {
         case B200ASM_TET: return p <= 2 ? (p == 1 ? 4 : 10) : B200ASM_EINVAL;
         case B200ASM_TRI: return p <= 2 ? (p == 1 ? 3 : 6) : B200ASM_EINVAL;
         case B200ASM_LINE: return p + 1;
+        case B200ASM_PRISM: return p <= 2 ? (p == 1 ? 6 : 18) : B200ASM_EINVAL;
+        case B200ASM_PYRAMID: return p <= 2 ? (p == 1 ? 5 : 14) : B200ASM_EINVAL;
     }
     return B200ASM_EINVAL;
 }
@@ -315,7 +423,7 @@ extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t
         for (int64_t e = 0; e < nel; e++) keys[e] = elnodes[2 * e] < elnodes[2 * e + 1] ? 0 : 1;
         return 0;
     }
-    if (topology == B200ASM_TET || topology == B200ASM_TRI) {  // p <= 2 only: no orientation dependence
+    if (topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_PRISM || topology == B200ASM_PYRAMID) {  // p <= 2 only: no orientation dependence
         for (int64_t e = 0; e < nel; e++) keys[e] = 0;
         return 0;
     }
@@ -344,7 +452,7 @@ extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t
 extern "C" int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts,
                                              double *phi, double *dphi) {
     if (porder < 1 || porder > 8 || nqp < 0) return B200ASM_EINVAL;
-    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI)
+    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_PRISM || topology == B200ASM_PYRAMID)
         return b200asm_shape_tables(topology, porder, nqp, qpts, phi, dphi);
     if (topology != B200ASM_HEX && topology != B200ASM_QUAD && topology != B200ASM_LINE) return B200ASM_EINVAL;
     const int dim = topology == B200ASM_HEX ? 3 : (topology == B200ASM_LINE ? 1 : 2);

@@ -33,9 +33,15 @@ TET_SIDES = ([[i] for i in range(4)] + [[0, 1], [1, 2], [2, 0], [0, 3], [1, 3], 
 QUAD_SIDES = [[i] for i in range(4)] + [[0, 1], [1, 2], [2, 3], [3, 0]] + [[0, 1, 2, 3]]
 TRI_SIDES = [[i] for i in range(3)] + [[0, 1], [1, 2], [2, 0]] + [[0, 1, 2]]
 LINE_SIDES = [[0], [1], [0, 1]]
-SIDES = {capi.HEX: HEX_SIDES, capi.TET: TET_SIDES, capi.QUAD: QUAD_SIDES, capi.TRI: TRI_SIDES, capi.LINE: LINE_SIDES}
-NCORNER = {capi.HEX: 8, capi.TET: 4, capi.QUAD: 4, capi.TRI: 3, capi.LINE: 2}
-DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2, capi.LINE: 1}
+# Topology/tpzprism.h:275-278, Topology/tpzpyramid.cpp:24-25 (FaceConnectLocId) / :898-925
+PRISM_SIDES = ([[i] for i in range(6)] + [[0, 1], [1, 2], [2, 0], [0, 3], [1, 4], [2, 5], [3, 4], [4, 5], [5, 3]] +
+               [[0, 1, 2], [0, 1, 4, 3], [1, 2, 5, 4], [0, 2, 5, 3], [3, 4, 5]] + [[0, 1, 2, 3, 4, 5]])
+PYRAMID_SIDES = ([[i] for i in range(5)] + [[0, 1], [1, 2], [2, 3], [3, 0], [0, 4], [1, 4], [2, 4], [3, 4]] +
+                 [[0, 1, 2, 3], [0, 1, 4], [1, 2, 4], [3, 2, 4], [0, 3, 4]] + [[0, 1, 2, 3, 4]])
+SIDES = {capi.HEX: HEX_SIDES, capi.TET: TET_SIDES, capi.QUAD: QUAD_SIDES, capi.TRI: TRI_SIDES, capi.LINE: LINE_SIDES,
+         capi.PRISM: PRISM_SIDES, capi.PYRAMID: PYRAMID_SIDES}
+NCORNER = {capi.HEX: 8, capi.TET: 4, capi.QUAD: 4, capi.TRI: 3, capi.LINE: 2, capi.PRISM: 6, capi.PYRAMID: 5}
+DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2, capi.LINE: 1, capi.PRISM: 3, capi.PYRAMID: 3}
 
 
 def side_nshape(topology, side_nodes, p):
@@ -50,7 +56,9 @@ def side_nshape(topology, side_nodes, p):
     if topology in (capi.HEX, capi.QUAD):
         return (p - 1) ** 2 if k == 4 else (p - 1) ** 3
     if p > 2:
-        raise ValueError("tetrahedra / triangles: uniform order p <= 2 only")
+        raise ValueError("tetrahedra / triangles / prisms / pyramids: uniform order p <= 2 only")
+    if topology in (capi.PRISM, capi.PYRAMID) and k == 4:
+        return (p - 1) ** 2   # quadrilateral faces (Shape/pzshapeprism.cpp:761-775, pzshapepiram.cpp:679-696)
     return 0
 
 
@@ -74,6 +82,8 @@ class ElementBlock:
     elnodes: np.ndarray     # [nel][ncorner] int32
     connects: np.ndarray    # [nel][nsides] int64 sequence numbers (TPZCompEl::ConnectIndex -> SequenceNumber)
     dest: np.ndarray = None  # [nel][ndof] int64
+    index: np.ndarray = None  # computational-element index of every element when the block is NOT a consecutive run
+                              # (meshes whose element types interleave, e.g. hexahedra + pyramids); None: first + arange
 
 
 @dataclass
@@ -118,14 +128,19 @@ def _first_touch_ids(keys):
 def flatten(nodes, element_blocks, porder, nstate):
     """Number connects / equations of a conforming H1 mesh the way NeoPZ's AutoBuild does.
 
-    element_blocks: list of (topology, matid, elnodes[nel][ncorner]) in computational-element order.
+    element_blocks: list of (topology, matid, elnodes[nel][ncorner]) in computational-element order, or
+    (topology, matid, elnodes, index) with the computational-element index of every element when elements of different
+    blocks interleave (connects are created in element-index order whatever the block layout).
     """
     nnodes = len(nodes)
     # entity keys per (element, side) as (class, ab, c) triples, in element order
     triples = []
     shapes = []
     ncell = 0
-    for topo, _matid, elnodes in element_blocks:
+    indexed = any(len(b) > 3 and b[3] is not None for b in element_blocks)
+    touch = []  # creation position (element index, side) of every (element, side) entry
+    for blk in element_blocks:
+        topo, _matid, elnodes = blk[:3]
         sides = SIDES[topo]
         en = np.asarray(elnodes, dtype=np.int64)
         nel = en.shape[0]
@@ -150,17 +165,29 @@ def flatten(nodes, element_blocks, porder, nstate):
             ncell += nel
         triples.append(t.reshape(-1, 3))
         shapes.append((nel, len(sides)))
+        if indexed:
+            if len(blk) < 4 or blk[3] is None:
+                raise ValueError("flatten: either every block carries element indices or none does")
+            idx = np.asarray(blk[3], dtype=np.int64)
+            touch.append((idx[:, None] * 32 + np.arange(len(sides), dtype=np.int64)[None, :]).reshape(-1))
     allt = np.concatenate(triples, axis=0)
     # two-level packing: (class, ab) -> dense id, then (id, c) -> one int64
     lvl1 = allt[:, 0] * (np.int64(nnodes) * nnodes) + allt[:, 1]
     _, inv1 = np.unique(lvl1, return_inverse=True)
     key = inv1.astype(np.int64) * (nnodes + 1) + (allt[:, 2] + 1)
-    conn_flat, nconnects = _first_touch_ids(key)
+    if indexed:  # first touch in element-index order, not in block order
+        by_creation = np.argsort(np.concatenate(touch), kind="stable")
+        ranked, nconnects = _first_touch_ids(key[by_creation])
+        conn_flat = np.empty_like(ranked)
+        conn_flat[by_creation] = ranked
+    else:
+        conn_flat, nconnects = _first_touch_ids(key)
 
     # block sizes: nshape(side) * nstate of the side that created the connect (same for all sharers)
     size = np.zeros(nconnects, dtype=np.int64)
     off = 0
-    for (topo, _m, _e), (nel, ns) in zip(element_blocks, shapes):
+    for blk, (nel, ns) in zip(element_blocks, shapes):
+        topo = blk[0]
         nsh = np.array([side_nshape(topo, loc, porder) for loc in SIDES[topo]], dtype=np.int64) * nstate
         size[conn_flat[off:off + nel * ns]] = np.tile(nsh, nel)
         off += nel * ns
@@ -171,13 +198,15 @@ def flatten(nodes, element_blocks, porder, nstate):
                     block_pos=pos, block_size=size, neq=neq)
     off = 0
     first = 0
-    for (topo, matid, elnodes), (nel, ns) in zip(element_blocks, shapes):
+    for blk, (nel, ns) in zip(element_blocks, shapes):
+        topo, matid, elnodes = blk[:3]
         conn = conn_flat[off:off + nel * ns].reshape(nel, ns)
         off += nel * ns
         dest = destination_indices(topo, conn, pos, porder, nstate)
-        mesh.blocks.append(ElementBlock(topology=topo, matid=matid, first=first,
+        index = np.asarray(blk[3], dtype=np.int64) if indexed else None
+        mesh.blocks.append(ElementBlock(topology=topo, matid=matid, first=int(index.min()) if indexed and nel else first,
                                         elnodes=np.ascontiguousarray(elnodes, dtype=np.int32),
-                                        connects=conn, dest=np.ascontiguousarray(dest)))
+                                        connects=conn, dest=np.ascontiguousarray(dest), index=index))
         first += nel
     return mesh
 
@@ -208,7 +237,7 @@ def grid_nodes(n, min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0, z_layers=
 
 
 def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_matid=1,
-                  min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0, z_layers=None, with_layers=False):
+                  min_x=(0., 0., 0.), max_x=(1., 1., 1.), perturb=0.0, z_layers=None, with_layers=False, prisms=False):
     """Nodes and element blocks of CreateGeoMeshOnGrid(3, minX, maxX, matids, {nx,ny,nz}, type, createBoundEls=true).
 
     n: divisions per direction (int or 3-tuple).  bc_matids = matids[1..6] of the reference call, i.e. the
@@ -216,11 +245,14 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
     z_layers=(iz0, iz1): only the element layers iz0 <= iz < iz1 of the global grid (slab of a sharded mesh);
     node indices are then local to the slab (global id - iz0*(nx+1)*(ny+1)), coordinates and the element /
     face parities are those of the global grid.  with_layers: blocks carry a 4th entry, the global layer of
-    every element.
+    every element.  prisms: MMeshType::EPrismatic, two prisms (0,1,2,4,5,6), (0,2,3,4,6,7) per cell (Pre/TPZGenGrid3D.cpp:163-179),
+    two triangles (0,1,2), (0,3,2) per z-face and one quadrilateral per x- / y-face (:297-307, :347-354, :385-392).
     """
     nx, ny, nz = (n, n, n) if np.isscalar(n) else n
     iz0, iz1 = (0, nz) if z_layers is None else z_layers
     nzl = iz1 - iz0
+    if prisms and tetrahedra:
+        raise ValueError("grid_elements: tetrahedra and prisms are exclusive")
     sx, sy = 1, nx + 1
     sz = (nx + 1) * (ny + 1)
     nodes = grid_nodes(n, min_x=min_x, max_x=max_x, perturb=perturb, z_layers=z_layers)
@@ -231,7 +263,10 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
     cube = np.stack([first, first + 1, first + 1 + sy, first + sy,
                      first + sz, first + 1 + sz, first + 1 + sy + sz, first + sy + sz], axis=1)
     blocks = []  # [topology, matid, elnodes, layer]
-    if not tetrahedra:
+    if prisms:
+        pr = np.stack([cube[:, [0, 1, 2, 4, 5, 6]], cube[:, [0, 2, 3, 4, 6, 7]]], axis=1).reshape(-1, 6)
+        blocks.append([capi.PRISM, vol_matid, pr, np.repeat(ez + iz0, 2)])
+    elif not tetrahedra:
         blocks.append([capi.HEX, vol_matid, cube, ez + iz0])
     else:
         perm = (ex + ey + ez + iz0) % 2
@@ -248,11 +283,11 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
         blocks.append([capi.TET, vol_matid, tets, np.repeat(ez + iz0, 5)])
 
     m_zmin, m_xmin, m_ymin, m_xmax, m_ymax, m_zmax = bc_matids
-    face_topo = capi.TRI if tetrahedra else capi.QUAD
     per_face = 2 if tetrahedra else 1
 
     def emit(matid, faces, layer):
-        layer = np.repeat(layer, per_face)
+        face_topo = capi.TRI if faces.shape[1] == 3 else capi.QUAD
+        layer = np.repeat(layer, len(faces) // len(layer))
         if blocks[-1][0] == face_topo and blocks[-1][1] == matid:
             blocks[-1][2] = np.concatenate([blocks[-1][2], faces], axis=0)
             blocks[-1][3] = np.concatenate([blocks[-1][3], layer], axis=0)
@@ -266,7 +301,10 @@ def grid_elements(n, tetrahedra=False, bc_matids=(-1, -1, -1, -1, -1, -1), vol_m
         fy, fx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
         fx, fy = fx.reshape(-1), fy.reshape(-1)
         f = (izf - iz0) * sz + fy * sy + fx
-        if not tetrahedra:
+        if prisms:
+            faces = np.stack([np.stack([f, f + 1, f + sy + 1], axis=1), np.stack([f, f + sy, f + sy + 1], axis=1)],
+                             axis=1).reshape(-1, 3)
+        elif not tetrahedra:
             faces = np.stack([f, f + 1, f + sy + 1, f + sy], axis=1)
         else:
             odd = ((fx + fy + izf) % 2) == 1
@@ -376,8 +414,29 @@ def grid_mesh_2d(n, porder, nstate, triangles=False, bc_matids=(-1,) * 4, pertur
     return flatten(nodes, blocks, porder, nstate)
 
 
-def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0, node_perm=None):
+def mesh_from_elements(nodes, el_type, el_matid, el_nodes, porder, nstate):
+    """FlatMesh of an arbitrary conforming mesh given element by element in computational-element order (topology code,
+    material id, corner nodes padded with -1): elements are gathered into one block per (topology, material id) in order of
+    first appearance, the connects are numbered in element order (AutoBuild)."""
+    el_type = np.asarray(el_type)
+    el_matid = np.asarray(el_matid)
+    el_nodes = np.asarray(el_nodes, dtype=np.int64)
+    blocks, seen = [], {}
+    for e in range(len(el_type)):
+        k = (int(el_type[e]), int(el_matid[e]))
+        if k not in seen:
+            seen[k] = len(blocks)
+            blocks.append([k[0], k[1], []])
+        blocks[seen[k]][2].append(e)
+    out = []
+    for topo, matid, idx in blocks:
+        idx = np.array(idx, dtype=np.int64)
+        out.append((topo, matid, el_nodes[idx, :NCORNER[topo]], idx))
+    return flatten(np.asarray(nodes, dtype=np.float64), out, porder, nstate)
+
+
+def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0, node_perm=None, prisms=False):
     """node_perm[i] = new index of grid node i (a renumbered mesh: same geometry, different side orientations)."""
-    nodes, blocks = grid_elements(n, tetrahedra=tetrahedra, bc_matids=bc_matids, perturb=perturb)
+    nodes, blocks = grid_elements(n, tetrahedra=tetrahedra, bc_matids=bc_matids, perturb=perturb, prisms=prisms)
     nodes, blocks = _renumber_nodes(nodes, blocks, node_perm)
     return flatten(nodes, blocks, porder, nstate)

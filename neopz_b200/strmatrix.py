@@ -179,8 +179,11 @@ def element_tables(topology, porder, key=0):
         qpts, qw = capi.tensor_rule(topology, order)
     else:
         z = np.load(os.path.join(_DATA, "simplex_rules.npz"))
-        tag = "tet" if topology == capi.TET else "tri"
-        qpts, qw = z[f"{tag}_order{order}_pts"], z[f"{tag}_order{order}_w"]
+        if topology == capi.PRISM:  # TPZIntPrism3D: line rule x triangle rule (Integral/pzquad.cpp:408-436)
+            qpts, qw = capi.prism_rule(order, z[f"tri_order{order}_pts"], z[f"tri_order{order}_w"])
+        else:
+            tag = {capi.TET: "tet", capi.TRI: "tri", capi.PYRAMID: "pyr"}[topology]
+            qpts, qw = z[f"{tag}_order{order}_pts"], z[f"{tag}_order{order}_w"]
     phi, dphi = capi.shape_tables(topology, porder, qpts, key)
     return qpts, qw, phi, dphi
 

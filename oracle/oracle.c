@@ -15,7 +15,8 @@
  * Scope: H1 elements of uniform order p<=2 on hexahedra / tetrahedra and their quadrilateral /
  * triangular boundary faces (for p<=2 no side has more than one shape function, hence no
  * orientation transforms: Shape/TPZShapeH1.cpp:71,77), and of uniform order 3..6 on hexahedra /
- * quadrilaterals (side orientation from the global corner-node indices, orc_shape_ids).  Simplex quadrature tables are data of the
+ * quadrilaterals (side orientation from the global corner-node indices, orc_shape_ids), and of uniform order p<=2 on prisms
+ * and pyramids (mixed quadrilateral / triangular faces).  Simplex and pyramid quadrature tables are data of the
  * reference (Integral/tpzintrulet.cpp, tpzintrulet3d.cpp) and are passed in by the caller.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared oracle/oracle.c -o oracle/liboracle.so -lm
@@ -30,6 +31,8 @@
 #define ORC_QUAD 2
 #define ORC_TRI 3
 #define ORC_LINE 4
+#define ORC_PRISM 5 /* EPrisma   (TPZShapePrism, TPZGeoPrism) */
+#define ORC_PYR 6   /* EPiramide (TPZShapePiram, TPZGeoPyramid) */
 
 #define ORC_POISSON 0
 #define ORC_ELAST3D 1
@@ -260,6 +263,138 @@ static int shape_tri(int p, const double *pt, double *phi, double *dphi_out) {
     return n;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Prism, p <= 2.  Shape/pzshapeprism.cpp:42-74 (ShapeCorner), :115-205 (ShapeGenerating), :761-775 (NConnectShapeF:
+ * edges p-1, triangular faces (p-2)(p-1)/2, quadrilateral faces (p-1)^2, interior (p-2)(p-1)^2/2); side tables
+ * Topology/tpzprism.h:275-278, higher-dimension sides Topology/tpzprism.cpp:38-60.  At p = 2: 6 + 9 + 3 = 18 functions
+ * (sides 6..14 and 16, 17, 18).
+ * ------------------------------------------------------------------------------------------ */
+static const int prism_edge_nodes[9][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 4}, {2, 5}, {3, 4}, {4, 5}, {5, 3}};
+static const int prism_face_n02[5][2] = {{0, 2}, {0, 4}, {1, 5}, {0, 5}, {3, 5}}; /* FaceNodes[f][0], [f][2] */
+/* quadrilateral faces among the higher-dimension sides of every edge, in the order of highsides[] */
+static const int prism_edge_quads[9][2] = {{16, -1}, {17, -1}, {18, -1}, {16, 18}, {16, 17}, {17, 18}, {16, -1}, {17, -1}, {18, -1}};
+
+static void prism_corner(const double *pt, double *phi, double (*d)[27]) {
+    phi[0] = .5 * (1. - pt[0] - pt[1]) * (1. - pt[2]);
+    phi[1] = .5 * pt[0] * (1. - pt[2]);
+    phi[2] = .5 * pt[1] * (1. - pt[2]);
+    phi[3] = .5 * (1. - pt[0] - pt[1]) * (1. + pt[2]);
+    phi[4] = .5 * pt[0] * (1. + pt[2]);
+    phi[5] = .5 * pt[1] * (1. + pt[2]);
+    d[0][0] = -.5 * (1. - pt[2]); d[1][0] = -.5 * (1. - pt[2]); d[2][0] = -.5 * (1. - pt[0] - pt[1]);
+    d[0][1] = .5 * (1. - pt[2]);  d[1][1] = .0;                 d[2][1] = -.5 * pt[0];
+    d[0][2] = .0;                 d[1][2] = .5 * (1. - pt[2]);  d[2][2] = -.5 * pt[1];
+    d[0][3] = -.5 * (1. + pt[2]); d[1][3] = -.5 * (1. + pt[2]); d[2][3] = .5 * (1. - pt[0] - pt[1]);
+    d[0][4] = .5 * (1. + pt[2]);  d[1][4] = .0;                 d[2][4] = .5 * pt[0];
+    d[0][5] = .0;                 d[1][5] = .5 * (1. + pt[2]);  d[2][5] = .5 * pt[1];
+}
+
+static int shape_prism(int p, const double *pt, double *phi, double *dphi_out) {
+    double ph[27], d[3][27];
+    prism_corner(pt, ph, d);
+    if (p == 1) {
+        for (int a = 0; a < 6; a++) { phi[a] = ph[a]; for (int k = 0; k < 3; k++) dphi_out[k * 6 + a] = d[k][a]; }
+        return 6;
+    }
+    for (int is = 6; is < 19; is++) {
+        if (is == 15) continue; /* triangular faces and the interior carry no function at p = 2 */
+        int is1, is2;
+        if (is < 15) { is1 = prism_edge_nodes[is - 6][0]; is2 = prism_edge_nodes[is - 6][1]; }
+        else { is1 = prism_face_n02[is - 15][0]; is2 = prism_face_n02[is - 15][1]; }
+        ph[is] = ph[is1] * ph[is2];
+        for (int k = 0; k < 3; k++) d[k][is] = d[k][is1] * ph[is2] + ph[is1] * d[k][is2];
+    }
+    for (int is = 6; is < 15; is++)
+        for (int h = 0; h < 2; h++) {
+            const int hs = prism_edge_quads[is - 6][h];
+            if (hs < 0) continue;
+            ph[is] += ph[hs];
+            for (int k = 0; k < 3; k++) d[k][is] += d[k][hs];
+        }
+    int n = 6;
+    for (int is = 6; is < 19; is++) {
+        if (is == 15) continue;
+        const double mult = is < 15 ? 4. : 16.;
+        phi[n] = ph[is] * mult;
+        for (int k = 0; k < 3; k++) d[k][is] *= mult;
+        n++;
+    }
+    for (int a = 0; a < 6; a++) phi[a] = ph[a];
+    n = 0;
+    for (int is = 0; is < 19; is++) {
+        if (is == 15) continue;
+        for (int k = 0; k < 3; k++) dphi_out[k * 18 + n] = d[k][is];
+        n++;
+    }
+    return 18;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Pyramid, p <= 2.  Shape/pzshapepiram.cpp:331-392 (ShapeCorner: rational corner functions; the apex branch is never
+ * taken at an integration point), :47-119 (ShapeGenerating), :679-696 (NConnectShapeF: edges p-1, base (p-1)^2,
+ * triangular faces (p-2)(p-1)/2, interior sum i(i+1)/2); ContainedSideLocId Topology/tpzpyramid.cpp:898-925.
+ * At p = 2: 5 + 8 + 1 = 14 functions (sides 5..12 and 13).
+ * ------------------------------------------------------------------------------------------ */
+static void pyr_corner(const double *pt, double *phi, double (*d)[27]) {
+    const double T0xz = .5 * (1. - pt[2] - pt[0]) / (1. - pt[2]);
+    const double T0yz = .5 * (1. - pt[2] - pt[1]) / (1. - pt[2]);
+    const double T1xz = .5 * (1. - pt[2] + pt[0]) / (1. - pt[2]);
+    const double T1yz = .5 * (1. - pt[2] + pt[1]) / (1. - pt[2]);
+    const double lmez = (1. - pt[2]);
+    phi[0] = T0xz * T0yz * lmez;
+    phi[1] = T1xz * T0yz * lmez;
+    phi[2] = T1xz * T1yz * lmez;
+    phi[3] = T0xz * T1yz * lmez;
+    phi[4] = pt[2];
+    const double lmexmez = 1. - pt[0] - pt[2];
+    const double lmeymez = 1. - pt[1] - pt[2];
+    const double lmaxmez = 1. + pt[0] - pt[2];
+    const double lmaymez = 1. + pt[1] - pt[2];
+    d[0][0] = -.25 * lmeymez / lmez;
+    d[1][0] = -.25 * lmexmez / lmez;
+    d[2][0] = -.25 * (lmeymez + lmexmez - lmexmez * lmeymez / lmez) / lmez;
+    d[0][1] = .25 * lmeymez / lmez;
+    d[1][1] = -.25 * lmaxmez / lmez;
+    d[2][1] = -.25 * (lmeymez + lmaxmez - lmaxmez * lmeymez / lmez) / lmez;
+    d[0][2] = .25 * lmaymez / lmez;
+    d[1][2] = .25 * lmaxmez / lmez;
+    d[2][2] = -.25 * (lmaymez + lmaxmez - lmaxmez * lmaymez / lmez) / lmez;
+    d[0][3] = -.25 * lmaymez / lmez;
+    d[1][3] = .25 * lmexmez / lmez;
+    d[2][3] = -.25 * (lmaymez + lmexmez - lmexmez * lmaymez / lmez) / lmez;
+    d[0][4] = 0.0;
+    d[1][4] = 0.0;
+    d[2][4] = 1.0;
+}
+
+static int shape_pyr(int p, const double *pt, double *phi, double *dphi_out) {
+    double ph[27], d[3][27];
+    pyr_corner(pt, ph, d);
+    if (p == 1) {
+        for (int a = 0; a < 5; a++) { phi[a] = ph[a]; for (int k = 0; k < 3; k++) dphi_out[k * 5 + a] = d[k][a]; }
+        return 5;
+    }
+    for (int is = 5; is < 14; is++) {
+        int is1, is2;
+        if (is < 9) { is1 = is - 5; is2 = (is - 5 + 1) % 4; }
+        else if (is < 13) { is1 = is - 9; is2 = 4; }
+        else { is1 = 0; is2 = 2; } /* ShapeFaceId[0][0], [0][2] */
+        ph[is] = ph[is1] * ph[is2];
+        for (int k = 0; k < 3; k++) d[k][is] = d[k][is1] * ph[is2] + ph[is1] * d[k][is2];
+    }
+    for (int is = 5; is < 9; is++) { /* the base edges take the base-face function */
+        ph[is] += ph[13];
+        for (int k = 0; k < 3; k++) d[k][is] += d[k][13];
+    }
+    for (int is = 5; is < 14; is++) {
+        const double scale = is < 13 ? 4. : 16.;
+        ph[is] *= scale;
+        for (int k = 0; k < 3; k++) d[k][is] *= scale;
+    }
+    for (int a = 0; a < 14; a++) { phi[a] = ph[a]; for (int k = 0; k < 3; k++) dphi_out[k * 14 + a] = d[k][a]; }
+    return 14;
+}
+
 /* TPZShapeLinear, p <= 2: Shape/pzshapelinear.cpp:269-283 (corner), :285-292 (generating: phi0*phi1*4) */
 static int shape_line(int p, const double *pt, double *phi, double *dphi_out) {
     const int n = p == 1 ? 2 : 3;
@@ -478,6 +613,8 @@ int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double 
             case ORC_QUAD: return shape_quad(p, pt, phi, dphi);
             case ORC_TRI: return shape_tri(p, pt, phi, dphi);
             case ORC_LINE: return shape_line(p, pt, phi, dphi);
+            case ORC_PRISM: return shape_prism(p, pt, phi, dphi);
+            case ORC_PYR: return shape_pyr(p, pt, phi, dphi);
         }
         return -1;
     }
@@ -516,6 +653,13 @@ static void gradx_of(int topo, const double *coords, const double *pt, double gr
         static const double dc[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
         for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) d[k][a] = dc[a][k];
         nn = 4;
+    } else if (topo == ORC_PRISM) { /* Geom/pzgeoprism.h:132-158 with Topology/tpzprism.cpp:323-351 (TShape) */
+        prism_corner(pt, ph, d);
+        nn = 6;
+    } else if (topo == ORC_PYR) { /* Geom/pzgeopyramid.h:127-156 with Topology/tpzpyramid.cpp:282-340 (TShape: the same
+                                     gradients as ShapeCorner away from the apex) */
+        pyr_corner(pt, ph, d);
+        nn = 5;
     } else if (topo == ORC_LINE) { /* Geom/pzgeolinear.h: x = sum_a x_a phi_a, phi = (1 -+ xi)/2 */
         d[0][0] = -0.5; d[0][1] = 0.5;
         nn = 2; dim = 1;
@@ -606,7 +750,9 @@ typedef struct {
     int64_t ids[8];     /* global corner-node indices (orientation of the sides, p >= 3) */
 } orc_elem_t;
 
-static int topo_dim(int topo) { return (topo == ORC_HEX || topo == ORC_TET) ? 3 : (topo == ORC_LINE ? 1 : 2); }
+static int topo_dim(int topo) {
+    return (topo == ORC_HEX || topo == ORC_TET || topo == ORC_PRISM || topo == ORC_PYR) ? 3 : (topo == ORC_LINE ? 1 : 2);
+}
 
 /* Material/Poisson/TPZMatPoisson.cpp:19-42 */
 static void contribute_poisson(int fdim, int n, const double *phi, const double *dphix, double weight, const double *mat, double *ek, double *ef) {

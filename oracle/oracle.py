@@ -12,10 +12,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liboracle.so")
 
-HEX, TET, QUAD, TRI, LINE = 0, 1, 2, 3, 4
+HEX, TET, QUAD, TRI, LINE, PRISM, PYR = 0, 1, 2, 3, 4, 5, 6
 POISSON, ELAST3D, POISSON_BC, ELAST3D_BC, ELAST2D, ELAST2D_BC = 0, 1, 2, 3, 4, 5
-TOPO_DIM = {HEX: 3, TET: 3, QUAD: 2, TRI: 2, LINE: 1}
-TOPO_NNODE = {HEX: 8, TET: 4, QUAD: 4, TRI: 3, LINE: 2}
+TOPO_DIM = {HEX: 3, TET: 3, QUAD: 2, TRI: 2, LINE: 1, PRISM: 3, PYR: 3}
+TOPO_NNODE = {HEX: 8, TET: 4, QUAD: 4, TRI: 3, LINE: 2, PRISM: 6, PYR: 5}
 
 
 def build():

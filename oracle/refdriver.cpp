@@ -32,6 +32,8 @@
 #include "pzshapetetra.h"
 #include "pzshapequad.h"
 #include "pzshapetriang.h"
+#include "pzshapeprism.h"
+#include "pzshapepiram.h"
 #include "Poisson/TPZMatPoisson.h"
 #include "Elasticity/TPZElasticity3D.h"
 #include "Elasticity/TPZElasticity2D.h"
@@ -85,7 +87,8 @@ static void save_vec(const std::string &dir, const std::string &name, const std:
 
 // ---------------------------------------------------------------- mesh recipe
 struct Case {
-    int n = 4, p = 1, phys = 0, tet = 0;
+    int n = 4, p = 1, phys = 0, tet = 0;  // tet: 0 hexahedra / quadrilaterals, 1 tetrahedra / triangles, 2 prisms (MMeshType::EPrismatic),
+                                          // 3 hexahedra + pyramids (MMeshType::EHexaPyrMixed: every other cell split into six pyramids)
     double perturb = 0.0;
     int bctype = 0;  // type of the BC on matid -1 (0 Dirichlet, 1 Neumann on zmax only -> matid -2)
     int dim = 3;       // 2: plane mesh (TPZGenGrid2D): phys 0 = TPZMatPoisson(dim 2), phys 2 / 3 = TPZElasticity2D plane
@@ -102,7 +105,8 @@ static TPZCompMesh *build_mesh(const Case &c) {
     if (c.bctype >= 1) matids[c.dim == 3 ? 6 : 3] = -2;  // zmax face (3-D) / top side (2-D): Neumann (1) or BC type c.bctype (>= 2)
     TPZManVector<int, 3> ndiv(c.dim, c.n);
     TPZGeoMesh *gmesh = c.dim == 3
-        ? TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv, c.tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true)
+        ? TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv,
+                                               c.tet == 1 ? MMeshType::ETetrahedral : (c.tet == 2 ? MMeshType::EPrismatic : (c.tet == 3 ? MMeshType::EHexaPyrMixed : MMeshType::EHexahedral)), true)
         : TPZGeoMeshTools::CreateGeoMeshOnGrid(2, minX, maxX, matids, ndiv, c.tet ? MMeshType::ETriangular : MMeshType::EQuadrilateral, true);
     if (c.perturb != 0.0) {
         const double h = 1.0 / c.n;
@@ -213,6 +217,8 @@ static int eltype(TPZCompEl *cel) {
         case EQuadrilateral: return 2;
         case ETriangle: return 3;
         case EOned: return 4;
+        case EPrisma: return 5;
+        case EPiramide: return 6;
         default: return -1;
     }
 }
@@ -313,6 +319,8 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
         dump_shape_all<pzshape::TPZShapeQuad>(dir, "quad", cmesh, EQuadrilateral);
         dump_shape_all<pzshape::TPZShapeTriang>(dir, "tri", cmesh, ETriangle);
         dump_shape_all<pzshape::TPZShapeLinear>(dir, "line", cmesh, EOned);
+        dump_shape_all<pzshape::TPZShapePrism>(dir, "prism", cmesh, EPrisma);
+        dump_shape_all<pzshape::TPZShapePiram>(dir, "pyr", cmesh, EPiramide);
     }
 
     TPZLinearAnalysis an(cmesh, false);
@@ -322,7 +330,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     std::vector<int32_t> econorder(ncel * 27, -1);
     std::vector<int64_t> dest_ptr(ncel + 1, 0), dest, ek_ptr(ncel + 1, 0);
     std::vector<double> ekv, efv;
-    bool done[5] = {false, false, false, false, false};
+    bool done[7] = {false, false, false, false, false, false, false};
     for (int64_t iel = 0; iel < ncel; iel++) {
         TPZCompEl *cel = cmesh->Element(iel);
         if (!cel) { etype[iel] = -1; dest_ptr[iel + 1] = dest.size(); ek_ptr[iel + 1] = ekv.size(); continue; }
@@ -358,6 +366,8 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
             if (t == 2) dump_shape<pzshape::TPZShapeQuad>(dir, "quad", cel);
             if (t == 3) dump_shape<pzshape::TPZShapeTriang>(dir, "tri", cel);
             if (t == 4) dump_shape<pzshape::TPZShapeLinear>(dir, "line", cel);
+            if (t == 5) dump_shape<pzshape::TPZShapePrism>(dir, "prism", cel);
+            if (t == 6) dump_shape<pzshape::TPZShapePiram>(dir, "pyr", cel);
         }
     }
     save_vec(dir, "el_type", etype);
@@ -479,7 +489,11 @@ static int cmd_time(const Case &c, int nthreads, int reps) {
     auto *sp = dynamic_cast<TPZSYsmpMatrix<STATE> *>(mtx.operator->());
     long double fro = 0;
     for (int64_t k = 0; k < sp->A().size(); k++) fro += (long double)sp->A()[k] * sp->A()[k];
-    const int64_t nvol = (int64_t)c.n * c.n * c.n * (c.tet ? 5 : 1);
+    int64_t nvol = 0;  // volume elements = computational elements of the mesh dimension
+    for (int64_t iel = 0; iel < cmesh->NElements(); iel++) {
+        TPZCompEl *cel = cmesh->Element(iel);
+        if (cel && cel->Reference() && cel->Reference()->Dimension() == c.dim) nvol++;
+    }
     std::cout.precision(17);
     std::cout << "{\"n\": " << c.n << ", \"p\": " << c.p << ", \"phys\": " << c.phys << ", \"tet\": " << c.tet
               << ", \"threads\": " << nthreads << ", \"reps\": " << reps << ", \"vol_elements\": " << nvol

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "refdriver")
 
-# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed[, dim]])
+# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed[, dim]])   tet: 0 hex / quad, 1 tet / tri, 2 prism, 3 hex + pyramid
 # dim 2: plane meshes (TPZGenGrid2D); phys 0 = TPZMatPoisson(dim 2), 2 / 3 = TPZElasticity2D plane strain / plane stress
 # scramble != 0: node indices shuffled so that the side orientations differ from element to element (p >= 3)
 CASES = {
@@ -50,6 +50,16 @@ CASES = {
     "quad_p3_elast2d_n3_pert_scr": (3, 3, 2, 0, 0.15, 1, 1, 9, 2),
     "quad_p4_poisson2d_n3_pert_scr": (3, 4, 0, 0, 0.15, 1, 1, 13, 2),
     "quad_p4_elast2d_stress_n2_bc3_scr": (2, 4, 3, 0, 0.15, 3, 1, 3, 2),
+    # tet = 2: prisms (MMeshType::EPrismatic, triangular + quadrilateral boundary faces);
+    # tet = 3: hexahedra + pyramids (MMeshType::EHexaPyrMixed: every other cell split into six pyramids around a centre node)
+    "prism_p1_poisson_n2_pert": (2, 1, 0, 2, 0.15, 0, 1),
+    "prism_p2_poisson_n2_pert": (2, 2, 0, 2, 0.15, 1, 1),
+    "prism_p2_elast_n2_pert": (2, 2, 1, 2, 0.15, 1, 1),
+    "prism_p1_elast_n3_bc2": (3, 1, 1, 2, 0.15, 2, 0),
+    "hexpyr_p1_poisson_n2_pert": (2, 1, 0, 3, 0.15, 0, 1),
+    "hexpyr_p2_poisson_n2_pert": (2, 2, 0, 3, 0.15, 1, 1),
+    "hexpyr_p2_elast_n2_pert": (2, 2, 1, 3, 0.15, 1, 1),
+    "hexpyr_p1_elast_n3": (3, 1, 1, 3, 0.0, 0, 0),
 }
 
 

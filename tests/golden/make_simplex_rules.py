@@ -1,4 +1,4 @@
-"""Extracts the reference's simplex quadrature tables (Integral/tpzintrulet.cpp, tpzintrulet3d.cpp —
+"""Extracts the reference's simplex / pyramid quadrature tables (Integral/tpzintrulet.cpp, tpzintrulet3d.cpp, tpzintrulep3d.cpp —
 published Dunavant / Zhang-Cui-Liu style tables, pure data) for the orders the hot path uses
 (order 2p, p in {1,2}) from the golden fixtures (which oracle/_ref/refdriver read through
 TPZIntPoints::Point) into neopz_b200/data/simplex_rules.npz, the table the standalone host ships.
@@ -19,6 +19,11 @@ for name, p in (("tet_p1_poisson_n2_pert", 1), ("tet_p2_poisson_n2_pert", 2)):
     for tag in ("tet", "tri"):
         out[f"{tag}_order{2 * p}_pts"] = g[f"rule_{tag}_pts"]
         out[f"{tag}_order{2 * p}_w"] = g[f"rule_{tag}_w"]
+# pyramids: TPZIntRuleP3D tables (Integral/tpzintrulep3d.cpp) of order 2p, read the same way
+for name, p in (("hexpyr_p1_poisson_n2_pert", 1), ("hexpyr_p2_poisson_n2_pert", 2)):
+    g = gu.load(name)
+    out[f"pyr_order{2 * p}_pts"] = g["rule_pyr_pts"]
+    out[f"pyr_order{2 * p}_w"] = g["rule_pyr_w"]
 path = os.path.join(ROOT, "neopz_b200", "data", "simplex_rules.npz")
 np.savez(path, **out)
 print({k: v.shape for k, v in out.items()})

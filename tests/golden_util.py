@@ -17,7 +17,7 @@ NEUMANN_POISSON = 0.75
 NEUMANN_ELAST = (0.25, -0.5, 2.0)
 BC_VAL1 = np.array([[4.0, 0.5, 0.0], [0.5, 3.0, 0.25], [0.0, 0.25, 5.0]])
 BC_VAL2 = (0.3, -0.2, 0.7)
-TAGS = {orc.HEX: "hex", orc.TET: "tet", orc.QUAD: "quad", orc.TRI: "tri", orc.LINE: "line"}
+TAGS = {orc.HEX: "hex", orc.TET: "tet", orc.QUAD: "quad", orc.TRI: "tri", orc.LINE: "line", orc.PRISM: "prism", orc.PYR: "pyr"}
 # TPZElasticity2D of oracle/refdriver.cpp (phys 2 = plane strain, 3 = plane stress)
 E2D_FORCE = (0.5, -1.0)
 NEUMANN_ELAST2D = (0.25, -0.5)

@@ -15,7 +15,13 @@ def _mesh_for(g):
         return gridmesh.grid_mesh_2d(m["n"], m["p"], 2 if m["phys"] >= 2 else 1, triangles=bool(m["tet"]), bc_matids=bc,
                                      perturb=m["perturb"], node_perm=perm)
     bc = (-1, -1, -1, -1, -1, -2 if m["bctype"] >= 1 else -1)
-    return gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=bool(m["tet"]),
+    if m["tet"] == 3:
+        # hexahedra + pyramids (MMeshType::EHexaPyrMixed): the reference creates the pyramids by refinement and reuses the
+        # slots of the deleted hexahedra, so element types interleave; the mesh (nodes, elements in computational-element
+        # order) comes from the fixture, the connect numbering / block table / destination indices are ours
+        return gridmesh.mesh_from_elements(g["nodes"], g["el_type"], g["el_matid"], g["el_nodes"], m["p"],
+                                           3 if m["phys"] == 1 else 1)
+    return gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=m["tet"] == 1, prisms=m["tet"] == 2,
                               bc_matids=bc, perturb=m["perturb"], node_perm=perm)
 
 
@@ -30,14 +36,19 @@ def test_grid_mesh_matches_reference(name):
     e = 0
     for b in mesh.blocks:
         nel, nc = b.elnodes.shape
-        assert b.first == e
-        assert np.all(g["el_type"][e:e + nel] == b.topology)
-        assert np.all(g["el_matid"][e:e + nel] == b.matid)
-        assert np.array_equal(g["el_nodes"][e:e + nel, :nc], b.elnodes)
+        if b.index is None:
+            assert b.first == e
+            idx = np.arange(e, e + nel)
+        else:
+            idx = b.index
+        assert np.all(g["el_type"][idx] == b.topology)
+        assert np.all(g["el_matid"][idx] == b.matid)
+        assert np.array_equal(g["el_nodes"][idx, :nc], b.elnodes)
         ns = b.connects.shape[1]
-        assert np.array_equal(g["el_conseq"][e:e + nel, :ns], b.connects)
-        lo, hi = g["el_dest_ptr"][e], g["el_dest_ptr"][e + nel]
-        assert np.array_equal(g["el_dest"][lo:hi].reshape(nel, -1), b.dest)
+        assert np.array_equal(g["el_conseq"][idx, :ns], b.connects)
+        for k, el in enumerate(idx):
+            lo, hi = g["el_dest_ptr"][el], g["el_dest_ptr"][el + 1]
+            assert np.array_equal(g["el_dest"][lo:hi], b.dest[k])
         e += nel
     assert e == g["meta"]["ncel"]
 

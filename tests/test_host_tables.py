@@ -6,7 +6,8 @@ import pytest
 from neopz_b200 import capi, strmatrix
 from tests import golden_util as gu
 
-TOPO = {"hex": capi.HEX, "tet": capi.TET, "quad": capi.QUAD, "tri": capi.TRI, "line": capi.LINE}
+TOPO = {"hex": capi.HEX, "tet": capi.TET, "quad": capi.QUAD, "tri": capi.TRI, "line": capi.LINE, "prism": capi.PRISM,
+        "pyr": capi.PYRAMID}
 
 
 @pytest.mark.parametrize("name", gu.ALL_CASES)
