@@ -29,6 +29,8 @@
 #include "pzgnode.h"
 #include "pzinterpolationspace.h"
 #include "pzshapecube.h"
+#include "pzshapepiram.h"
+#include "pzshapeprism.h"
 #include "pzshapequad.h"
 #include "pzshapetetra.h"
 #include "pzshapetriang.h"
@@ -93,6 +95,8 @@ int TopologyOf(MElementType t) {
         case EQuadrilateral: return B200ASM_QUAD;
         case ETriangle: return B200ASM_TRI;
         case EOned: return B200ASM_LINE;
+        case EPrisma: return B200ASM_PRISM;
+        case EPiramide: return B200ASM_PYRAMID;
         default: return -1;
     }
 }
@@ -272,7 +276,8 @@ void FillForce(HostGroup &g) {
     g.has_forcing = false;
     g.meta.force = nullptr;
     const int ns = g.meta.nstate;
-    const int dim = (g.meta.topology == B200ASM_HEX || g.meta.topology == B200ASM_TET) ? 3 : 2;
+    const int dim = (g.meta.topology == B200ASM_HEX || g.meta.topology == B200ASM_TET || g.meta.topology == B200ASM_PRISM ||
+                     g.meta.topology == B200ASM_PYRAMID) ? 3 : 2;
     if (dim != 3) {
         // plane domain elements: constant source only (TPZMatPoisson without forcing function has none)
         if (g.meta.kind != B200ASM_BC) {
@@ -338,8 +343,9 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
         const int topo = TopologyOf(gel->Type());
         const bool h1 = dynamic_cast<TPZCompElH1<pzshape::TPZShapeCube> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTetra> *>(cel) ||
                         dynamic_cast<TPZCompElH1<pzshape::TPZShapeQuad> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapeTriang> *>(cel) ||
-                        dynamic_cast<TPZCompElH1<pzshape::TPZShapeLinear> *>(cel);
-        if (topo < 0 || !h1) Fatal("element " + std::to_string(iel) + " is not an H1 hexahedron/tetrahedron/quadrilateral/triangle");
+                        dynamic_cast<TPZCompElH1<pzshape::TPZShapeLinear> *>(cel) || dynamic_cast<TPZCompElH1<pzshape::TPZShapePrism> *>(cel) ||
+                        dynamic_cast<TPZCompElH1<pzshape::TPZShapePiram> *>(cel);
+        if (topo < 0 || !h1) Fatal("element " + std::to_string(iel) + " is not an H1 hexahedron/tetrahedron/prism/pyramid/quadrilateral/triangle/line");
         if (!gel->IsLinearMapping()) Fatal("element " + std::to_string(iel) + " has a non-(multi)linear geometric map");
         // uniform order, no constraints
         const int ncon = cel->NConnects();
@@ -355,7 +361,7 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
         }
         const bool tensor = topo == B200ASM_HEX || topo == B200ASM_QUAD || topo == B200ASM_LINE;
         if (porder < 1 || porder > (tensor ? 4 : 2))
-            Fatal("polynomial order " + std::to_string(porder) + " is not supported (hexahedra/quadrilaterals/lines 1..4, simplices 1..2)");
+            Fatal("polynomial order " + std::to_string(porder) + " is not supported (hexahedra/quadrilaterals/lines 1..4, simplices/prisms/pyramids 1..2)");
         int64_t orientation = 0;
         if (porder >= 3) {
             int32_t corner[8];
@@ -385,6 +391,8 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
                 case B200ASM_TET: ShapeTables<pzshape::TPZShapeTetra>(cel, porder, g); break;
                 case B200ASM_QUAD: ShapeTables<pzshape::TPZShapeQuad>(cel, porder, g); break;
                 case B200ASM_LINE: ShapeTables<pzshape::TPZShapeLinear>(cel, porder, g); break;
+                case B200ASM_PRISM: ShapeTables<pzshape::TPZShapePrism>(cel, porder, g); break;
+                case B200ASM_PYRAMID: ShapeTables<pzshape::TPZShapePiram>(cel, porder, g); break;
                 default: ShapeTables<pzshape::TPZShapeTriang>(cel, porder, g); break;
             }
         }

@@ -35,6 +35,7 @@ static double secs(clk::time_point a, clk::time_point b) { return std::chrono::d
 // dirichlet: value imposed on matid -1.  The CG comparison uses 0: with a non-zero value the right-hand side norm
 // is ~1e16 (penalty), and a relative residual tolerance of 1e-15 no longer constrains the interior equations.
 // phys 2 / 3: TPZElasticity2D (plane strain / plane stress) on a plane mesh of quadrilaterals (tet = 0) or triangles
+// tet (3-D): 0 hexahedra, 1 tetrahedra, 2 prisms (EPrismatic), 3 hexahedra + pyramids (EHexaPyrMixed)
 static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, double dirichlet) {
     const int dim = phys >= 2 ? 2 : 3;
     TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
@@ -43,7 +44,8 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
     matids[dim == 3 ? 6 : 3] = -2;  // zmax face / top side: Neumann
     TPZManVector<int, 3> ndiv(dim, n);
     TPZGeoMesh *gmesh = dim == 3
-        ? TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv, tet ? MMeshType::ETetrahedral : MMeshType::EHexahedral, true)
+        ? TPZGeoMeshTools::CreateGeoMeshOnGrid(3, minX, maxX, matids, ndiv,
+                                               tet == 1 ? MMeshType::ETetrahedral : (tet == 2 ? MMeshType::EPrismatic : (tet == 3 ? MMeshType::EHexaPyrMixed : MMeshType::EHexahedral)), true)
         : TPZGeoMeshTools::CreateGeoMeshOnGrid(2, minX, maxX, matids, ndiv, tet ? MMeshType::ETriangular : MMeshType::EQuadrilateral, true);
     if (perturb != 0.0) {
         const double h = 1.0 / n;
@@ -194,7 +196,7 @@ static double RelF(const std::vector<double> &x, const std::vector<double> &ref)
 
 int main(int argc, char **argv) {
     if (argc < 6) {
-        std::cerr << "usage: dropin_test n p phys(0|1) tet(0|1) symmetric(0|1) [solve(0|1)] [cpu_threads]\n";
+        std::cerr << "usage: dropin_test n p phys(0|1|2|3) tet(0|1|2|3) symmetric(0|1) [solve(0|1)] [cpu_threads]\n";
         return 2;
     }
     const int n = atoi(argv[1]), p = atoi(argv[2]), phys = atoi(argv[3]), tet = atoi(argv[4]), symmetric = atoi(argv[5]);
@@ -247,7 +249,11 @@ int main(int argc, char **argv) {
     double errSolDev = 0;
     if (solve && symmetric) errSolDev = RelF(gpu.sol_device, ref.sol);
     const double errRes = RelF(gpu.residual_rhs, ref.residual_rhs), errResVsRhs = RelF(ref.residual_rhs, ref.rhs);
-    const int64_t nvol = phys >= 2 ? (int64_t)n * n * (tet ? 2 : 1) : (int64_t)n * n * n * (tet ? 5 : 1);
+    int64_t nvol = 0;  // elements of the mesh dimension
+    for (int64_t iel = 0; iel < cmesh->NElements(); iel++) {
+        TPZCompEl *cel = cmesh->Element(iel);
+        if (cel && cel->Reference() && cel->Reference()->Dimension() == cmesh->Dimension()) nvol++;
+    }
     const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
     std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"cpu_first_assemble_s\": " << t1

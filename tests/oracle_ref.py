@@ -14,7 +14,12 @@ def _rule(topo, p):
     if topo in (orc.HEX, orc.QUAD, orc.LINE):
         return orc.rule(topo, 2 * p)
     z = np.load(_SIMPLEX)  # tables of the reference (tests/golden/make_simplex_rules.py)
-    tag = "tet" if topo == orc.TET else "tri"
+    if topo == orc.PRISM:  # TPZIntPrism3D::Point (Integral/pzquad.cpp:423-436): triangle point fastest, w = w_line * w_tri
+        lpts, lw = orc.rule(orc.LINE, 2 * p)
+        tpts, tw = z[f"tri_order{2 * p}_pts"], z[f"tri_order{2 * p}_w"]
+        pts = np.array([[t[0], t[1], zl[0]] for zl in lpts for t in tpts])
+        return pts, np.array([wl * wt for wl in lw for wt in tw])
+    tag = {orc.TET: "tet", orc.TRI: "tri", orc.PYR: "pyr"}[topo]
     return z[f"{tag}_order{2 * p}_pts"], z[f"{tag}_order{2 * p}_w"]
 
 
