@@ -846,6 +846,10 @@ using TetP1Poisson = VolCfg<4, 4, 1, 4, 128>;
 using TetP1Elast = VolCfg<4, 4, 3, 6, 32>;
 using TetP2Poisson = VolCfg<4, 10, 1, 5, 32>;
 using TetP2Elast = VolCfg<4, 10, 3, 6, 8>;
+using TetP3Poisson = VolCfg<4, 20, 1, 5, 8>;    // 20 functions: 4 + 6 x 2 (edges) + 4 (faces)
+using TetP3Elast = VolCfg<4, 20, 3, 6, 2>;
+using TetP4Poisson = VolCfg<4, 35, 1, 7, 4>;    // 35 functions: 4 + 6 x 3 + 4 x 3 + 1 (interior)
+using TetP4Elast = VolCfg<4, 35, 3, 9, 1>;
 // prisms (6 corner nodes; p=2: 6 + 9 edges + 3 quadrilateral faces = 18 functions) and pyramids (5 corner nodes; p=2: 5 + 8 edges +
 // the base = 14 functions): same kernel, their own tables (rational corner functions of the pyramid included)
 using PrismP1Poisson = VolCfg<6, 6, 1, 6, 64>;
@@ -896,6 +900,8 @@ const VolEntry kVol[] = {
     make_entry<HexP3Poisson>(B200ASM_HEX, 3), make_entry<HexP4Poisson>(B200ASM_HEX, 4), make_entry<HexP3Elast>(B200ASM_HEX, 3),
     make_entry<TetP1Poisson>(B200ASM_TET, 1), make_entry<TetP1Elast>(B200ASM_TET, 1),
     make_entry<TetP2Poisson>(B200ASM_TET, 2), make_entry<TetP2Elast>(B200ASM_TET, 2),
+    make_entry<TetP3Poisson>(B200ASM_TET, 3), make_entry<TetP3Elast>(B200ASM_TET, 3),
+    make_entry<TetP4Poisson>(B200ASM_TET, 4), make_entry<TetP4Elast>(B200ASM_TET, 4),
     make_entry<PrismP1Poisson>(B200ASM_PRISM, 1), make_entry<PrismP1Elast>(B200ASM_PRISM, 1),
     make_entry<PrismP2Poisson>(B200ASM_PRISM, 2), make_entry<PrismP2Elast>(B200ASM_PRISM, 2),
     make_entry<PyrP1Poisson>(B200ASM_PYRAMID, 1), make_entry<PyrP1Elast>(B200ASM_PYRAMID, 1),
@@ -1106,10 +1112,10 @@ cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cud
     }
     if (ns == 2) return cudaErrorInvalidValue;
     if (porder >= 3) {
-        if (topology != B200ASM_QUAD) return cudaErrorInvalidValue;
-        const int n = (porder + 1) * (porder + 1);
+        if (topology != B200ASM_QUAD && topology != B200ASM_TRI) return cudaErrorInvalidValue;
+        const int n = topology == B200ASM_QUAD ? (porder + 1) * (porder + 1) : (porder + 1) * (porder + 2) / 2;
         const int grid = (int)((p.el1 - p.el0 + 3) / 4);
-        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, 4, n, ns);
+        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, topology == B200ASM_QUAD ? 4 : 3, n, ns);
         return cudaGetLastError();
     }
     if (topology == B200ASM_QUAD && porder == 1) return ns == 1 ? launch_bc<4, 4, 1>(p, s) : launch_bc<4, 4, 3>(p, s);
@@ -1386,7 +1392,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
                 ? 3 : (gi->topology == B200ASM_LINE ? 1 : 2);
     g.plane = g.dim == 2 && (gi->kind == B200ASM_POISSON || gi->kind == B200ASM_ELASTICITY2D);
     if (g.nn < 0 || g.n < 0 || gi->porder < 1)
-        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad 1..4, tet/tri/prism/pyramid 1..2)");
+        return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad/tet/tri 1..4, prism/pyramid 1..2)");
     if (gi->nshape != g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not match topology/order");
     if (g.ns < 1 || g.ns > 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1, 2 or 3");
     if (g.nel < 0 || g.nq <= 0 || g.nq > 512) return fail(ctx, B200ASM_EINVAL, "add_group: bad nel/nqp");
@@ -1406,8 +1412,8 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
                 g.mma = k;
     } else if (g.plane) {
-        if (gi->porder > (g.topology == B200ASM_QUAD ? 4 : 2))
-            return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: quadrilaterals p <= 4, triangles p <= 2");
+        if (gi->porder > 4)
+            return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: p <= 4");
         if (gi->kind == B200ASM_POISSON && g.ns != 1) return fail(ctx, B200ASM_EINVAL, "add_group: Poisson has nstate 1");
         if (gi->kind == B200ASM_ELASTICITY2D && g.ns != 2) return fail(ctx, B200ASM_EINVAL, "add_group: Elasticity2D has nstate 2");
         if (gi->force) return fail(ctx, B200ASM_EINVAL, "add_group: forcing-function tables are not supported on plane elements");
@@ -1556,7 +1562,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         else aff_tables<HexP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
     }
-    if (volume && g.topology == B200ASM_TET) {
+    if (volume && g.topology == B200ASM_TET && g.porder <= 2) {  // (orders 3, 4 run the register-tile kernel)
         if (g.n == 4 && g.ns == 1) aff_tables<TetP1PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else if (g.n == 4) aff_tables<TetP1ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else if (g.ns == 1) aff_tables<TetP2PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);

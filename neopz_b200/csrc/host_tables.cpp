@@ -68,6 +68,26 @@ inline int square_symmetry(int64_t a, int64_t b, int64_t c, int64_t d) {
     return 2 * m + (ccw ? 0 : 1);
 }
 
+// triangular sides: corner triples of the tetrahedron faces (Topology/tpztetrahedron.h:280) and the symmetry class
+const int kTetFace[4][3] = {{0, 1, 2}, {0, 1, 3}, {1, 2, 3}, {0, 2, 3}};
+inline int triangle_symmetry(int64_t a, int64_t b, int64_t c) {
+    const int64_t v[3] = {a, b, c};
+    int m = 0;
+    for (int k = 1; k < 3; k++)
+        if (v[k] < v[m]) m = k;
+    const bool ccw = v[(m + 1) % 3] < v[(m + 2) % 3];
+    return 2 * m + (ccw ? 0 : 1);
+}
+// With mu = (1 - u - v, u, v) the barycentric coordinates of a triangular side, symmetry class t maps the side coordinates to
+// (u', v') = (mu[kTriPerm[t][0]], mu[kTriPerm[t][1]])  (the six affine maps gTrans2dT / gVet2dT of Shape/pzshapetriang.cpp:18-29)
+const int kTriPerm[6][2] = {{1, 2}, {2, 1}, {2, 0}, {0, 2}, {0, 1}, {1, 0}};
+// side coordinates (u, v) of the tetrahedron faces as affine functions c0 + cx x + cy y + cz z of the element coordinates
+// (Topology/tpztetrahedron.cpp:513-538: faces 10, 11, 13 drop one coordinate, face 12 projects along (1,1,1)/3)
+const double kTetFaceUV[4][2][4] = {{{0, 1, 0, 0}, {0, 0, 1, 0}},
+                                    {{0, 1, 0, 0}, {0, 0, 0, 1}},
+                                    {{1.0 / 3.0, -1.0 / 3.0, 2.0 / 3.0, -1.0 / 3.0}, {1.0 / 3.0, -1.0 / 3.0, -1.0 / 3.0, 2.0 / 3.0}},
+                                    {{0, 0, 1, 0}, {0, 0, 0, 1}}};
+
 struct SideParam {  // side coordinate k = sign[k] * x[axis[k]]
     int sdim;
     int axis[3];
@@ -408,8 +428,8 @@ extern "C" int b200asm_nshape(int topology, int porder) {
     switch (topology) {
         case B200ASM_HEX: return (p + 1) * (p + 1) * (p + 1);
         case B200ASM_QUAD: return (p + 1) * (p + 1);
-        case B200ASM_TET: return p <= 2 ? (p == 1 ? 4 : 10) : B200ASM_EINVAL;
-        case B200ASM_TRI: return p <= 2 ? (p == 1 ? 3 : 6) : B200ASM_EINVAL;
+        case B200ASM_TET: return (p + 1) * (p + 2) * (p + 3) / 6;
+        case B200ASM_TRI: return (p + 1) * (p + 2) / 2;
         case B200ASM_LINE: return p + 1;
         case B200ASM_PRISM: return p <= 2 ? (p == 1 ? 6 : 18) : B200ASM_EINVAL;
         case B200ASM_PYRAMID: return p <= 2 ? (p == 1 ? 5 : 14) : B200ASM_EINVAL;
@@ -423,8 +443,32 @@ extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t
         for (int64_t e = 0; e < nel; e++) keys[e] = elnodes[2 * e] < elnodes[2 * e + 1] ? 0 : 1;
         return 0;
     }
-    if (topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_PRISM || topology == B200ASM_PYRAMID) {  // p <= 2 only: no orientation dependence
+    if (topology == B200ASM_PRISM || topology == B200ASM_PYRAMID) {  // p <= 2 only: no orientation dependence
         for (int64_t e = 0; e < nel; e++) keys[e] = 0;
+        return 0;
+    }
+    if (topology == B200ASM_TET || topology == B200ASM_TRI) {
+        // 1 bit per edge (runs from the larger to the smaller global index), 3 bits per triangular side (which of the six
+        // symmetries of the triangle makes it start at its smallest corner and turn towards the smaller neighbour:
+        // Topology/tpztriangle.cpp:599-622); triangles: edges in bits 0-2, the element itself in bits 3-5;
+        // tetrahedra: edges in bits 0-5, faces in bits 6-17
+        const bool tet = topology == B200ASM_TET;
+        const int nc = tet ? 4 : 3, ne = tet ? 6 : 3;
+        for (int64_t e = 0; e < nel; e++) {
+            const int32_t *id = elnodes + e * nc;
+            int64_t key = 0;
+            for (int k = 0; k < ne; k++) {
+                const int a = tet ? kTetEdge[k][0] : kTriEdge[k][0], b = tet ? kTetEdge[k][1] : kTriEdge[k][1];
+                if (!(id[a] < id[b])) key |= (int64_t)1 << k;
+            }
+            if (tet) {
+                for (int f = 0; f < 4; f++)
+                    key |= (int64_t)triangle_symmetry(id[kTetFace[f][0]], id[kTetFace[f][1]], id[kTetFace[f][2]]) << (6 + 3 * f);
+            } else {
+                key |= (int64_t)triangle_symmetry(id[0], id[1], id[2]) << 3;
+            }
+            keys[e] = key;
+        }
         return 0;
     }
     if (topology != B200ASM_HEX && topology != B200ASM_QUAD) return B200ASM_EINVAL;
@@ -449,11 +493,132 @@ extern "C" int b200asm_orientation_keys(int topology, int64_t nel, const int32_t
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// simplices of order >= 3 (Shape/TPZShapeH1.cpp:42-116 with pzshapetetra.cpp / pzshapetriang.cpp): every side carries its blend
+// function B (edges 4 l_a l_b, triangular sides 27 l_a l_b l_c, tetrahedron interior 54 l_0 l_1 l_2 l_3) and the products of B
+// with Chebyshev polynomials of the side's own coordinates:
+//   edge (a,b):        T_i(s), s = +-(l_b - l_a), i = 1..p-2                 (sign: orientation bit of the edge)
+//   triangular side:   T_i(2u'-1) T_j(2v'-1), i + j <= p-3, by (i+j, j)      ((u',v') = two barycentric coordinates of the side,
+//                                                                              chosen by its symmetry class)
+//   tetrahedron:       T_i(2x-1) T_j(2y-1) T_k(2z-1), i + j + k <= p-4, lexicographic in (i,j,k)
+// ------------------------------------------------------------------------------------------------
+static int simplex_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts, double *phi, double *dphi) {
+    const bool tet = topology == B200ASM_TET;
+    const int dim = tet ? 3 : 2, nc = dim + 1, ne = tet ? 6 : 3, nf = tet ? 4 : 1;
+    const int n = b200asm_nshape(topology, porder);
+    const int p = porder;
+    if (p > 9) return B200ASM_EINVAL;
+    for (int q = 0; q < nqp; q++) {
+        const double *pt = qpts + (size_t)q * dim;
+        double *ph = phi + (size_t)q * n;
+        double *dp = dphi + (size_t)q * dim * n;
+        double lam[4], dlam[4][3];
+        lam[0] = 1.0;
+        for (int d = 0; d < dim; d++) {
+            lam[0] -= pt[d];
+            lam[d + 1] = pt[d];
+        }
+        for (int a = 0; a < nc; a++)
+            for (int d = 0; d < dim; d++) dlam[a][d] = (a == 0) ? -1.0 : (a == d + 1 ? 1.0 : 0.0);
+        int shape = 0;
+        auto emit = [&](double v, const double *g) {
+            ph[shape] = v;
+            for (int d = 0; d < dim; d++) dp[d * n + shape] = g[d];
+            shape++;
+        };
+        for (int a = 0; a < nc; a++) emit(lam[a], dlam[a]);
+        double T[3][16], dT[3][16];
+        // edges
+        for (int e = 0; e < ne; e++) {
+            const int a = tet ? kTetEdge[e][0] : kTriEdge[e][0], b = tet ? kTetEdge[e][1] : kTriEdge[e][1];
+            const double B = 4.0 * (lam[a] * lam[b]);
+            double dB[3], ds[3];
+            const double sgn = ((key >> e) & 1) ? -1.0 : 1.0;
+            for (int d = 0; d < dim; d++) {
+                dB[d] = 4.0 * (dlam[a][d] * lam[b] + lam[a] * dlam[b][d]);
+                ds[d] = sgn * (dlam[b][d] - dlam[a][d]);
+            }
+            emit(B, dB);
+            chebyshev_T(sgn * (lam[b] - lam[a]), p - 1, T[0], dT[0]);
+            for (int i = 1; i < p - 1; i++) {
+                double g[3];
+                for (int d = 0; d < dim; d++) g[d] = dB[d] * T[0][i] + B * (dT[0][i] * ds[d]);
+                emit(B * T[0][i], g);
+            }
+        }
+        // triangular sides
+        for (int f = 0; f < nf; f++) {
+            const int *c = tet ? kTetFace[f] : kTetFace[0];
+            const double B = 27.0 * (lam[c[0]] * lam[c[1]] * lam[c[2]]);
+            double dB[3];
+            for (int d = 0; d < dim; d++)
+                dB[d] = 27.0 * (dlam[c[0]][d] * lam[c[1]] * lam[c[2]] + lam[c[0]] * dlam[c[1]][d] * lam[c[2]] + lam[c[0]] * lam[c[1]] * dlam[c[2]][d]);
+            if (p >= 3) emit(B, dB);
+            const int nin = (p - 2) * (p - 1) / 2;
+            if (nin <= 1) continue;
+            const int t = (int)((key >> (tet ? 6 + 3 * f : 3)) & 7);
+            // side coordinates and their gradients, then mu = (1-u-v, u, v)
+            double mu[3], dmu[3][3];
+            for (int k = 0; k < 2; k++) {
+                double v, g[3] = {0, 0, 0};
+                if (tet) {
+                    const double *cf = kTetFaceUV[f][k];
+                    v = cf[0] + cf[1] * pt[0] + cf[2] * pt[1] + cf[3] * pt[2];
+                    for (int d = 0; d < 3; d++) g[d] = cf[1 + d];
+                } else {
+                    v = pt[k];
+                    g[k] = 1.0;
+                }
+                mu[k + 1] = v;
+                for (int d = 0; d < 3; d++) dmu[k + 1][d] = g[d];
+            }
+            mu[0] = 1.0 - mu[1] - mu[2];
+            for (int d = 0; d < 3; d++) dmu[0][d] = -dmu[1][d] - dmu[2][d];
+            const int k0 = kTriPerm[t][0], k1 = kTriPerm[t][1];
+            chebyshev_T(2.0 * mu[k0] - 1.0, p - 2, T[0], dT[0]);
+            chebyshev_T(2.0 * mu[k1] - 1.0, p - 2, T[1], dT[1]);
+            for (int s = 1; s <= p - 3; s++)       // i + j = s  (s = 0 is the blend function itself)
+                for (int j = 0; j <= s; j++) {
+                    const int i = s - j;
+                    const double val = T[0][i] * T[1][j];
+                    double g[3];
+                    for (int d = 0; d < dim; d++)
+                        g[d] = dB[d] * val + B * (2.0 * dT[0][i] * T[1][j] * dmu[k0][d] + 2.0 * T[0][i] * dT[1][j] * dmu[k1][d]);
+                    emit(B * val, g);
+                }
+        }
+        // interior of the tetrahedron
+        if (tet && p >= 4) {
+            const double B = 54.0 * (lam[0] * lam[1] * lam[2] * lam[3]);
+            double dB[3];
+            for (int d = 0; d < 3; d++)
+                dB[d] = 54.0 * (dlam[0][d] * lam[1] * lam[2] * lam[3] + lam[0] * dlam[1][d] * lam[2] * lam[3] +
+                                lam[0] * lam[1] * dlam[2][d] * lam[3] + lam[0] * lam[1] * lam[2] * dlam[3][d]);
+            const int ord = p - 3;
+            for (int k = 0; k < 3; k++) chebyshev_T(2.0 * pt[k] - 1.0, ord, T[k], dT[k]);
+            for (int i = 0; i < ord; i++)
+                for (int j = 0; j < ord; j++)
+                    for (int k = 0; k < ord; k++) {
+                        if (i + j + k >= ord) continue;
+                        const double val = T[0][i] * T[1][j] * T[2][k];
+                        double g[3];
+                        g[0] = dB[0] * val + B * (2.0 * dT[0][i] * T[1][j] * T[2][k]);
+                        g[1] = dB[1] * val + B * (2.0 * T[0][i] * dT[1][j] * T[2][k]);
+                        g[2] = dB[2] * val + B * (2.0 * T[0][i] * T[1][j] * dT[2][k]);
+                        emit(B * val, g);
+                    }
+        }
+        if (shape != n) return B200ASM_EINVAL;
+    }
+    return n;
+}
+
 extern "C" int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts,
                                              double *phi, double *dphi) {
     if (porder < 1 || porder > 8 || nqp < 0) return B200ASM_EINVAL;
-    if (porder <= 2 || topology == B200ASM_TET || topology == B200ASM_TRI || topology == B200ASM_PRISM || topology == B200ASM_PYRAMID)
+    if (porder <= 2 || topology == B200ASM_PRISM || topology == B200ASM_PYRAMID)
         return b200asm_shape_tables(topology, porder, nqp, qpts, phi, dphi);
+    if (topology == B200ASM_TET || topology == B200ASM_TRI) return simplex_tables_oriented(topology, porder, key, nqp, qpts, phi, dphi);
     if (topology != B200ASM_HEX && topology != B200ASM_QUAD && topology != B200ASM_LINE) return B200ASM_EINVAL;
     const int dim = topology == B200ASM_HEX ? 3 : (topology == B200ASM_LINE ? 1 : 2);
     const int nsides = topology == B200ASM_HEX ? 27 : (topology == B200ASM_LINE ? 3 : 9);

@@ -359,9 +359,9 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
                 if (con.Order() != porder) Fatal("non-uniform polynomial order inside an element is not supported");
             }
         }
-        const bool tensor = topo == B200ASM_HEX || topo == B200ASM_QUAD || topo == B200ASM_LINE;
-        if (porder < 1 || porder > (tensor ? 4 : 2))
-            Fatal("polynomial order " + std::to_string(porder) + " is not supported (hexahedra/quadrilaterals/lines 1..4, simplices/prisms/pyramids 1..2)");
+        const bool upto4 = topo != B200ASM_PRISM && topo != B200ASM_PYRAMID;
+        if (porder < 1 || porder > (upto4 ? 4 : 2))
+            Fatal("polynomial order " + std::to_string(porder) + " is not supported (hexahedra/tetrahedra/quadrilaterals/triangles/lines 1..4, prisms/pyramids 1..2)");
         int64_t orientation = 0;
         if (porder >= 3) {
             int32_t corner[8];

@@ -46,8 +46,8 @@ DIM = {capi.HEX: 3, capi.TET: 3, capi.QUAD: 2, capi.TRI: 2, capi.LINE: 1, capi.P
 
 def side_nshape(topology, side_nodes, p):
     """TSHAPE::NConnectShapeF(side, p) (Shape/pzshapecube.cpp:573-584, pzshapequad.cpp, pzshapetetra.cpp:447-466):
-    vertex 1, edge p-1, quadrilateral (p-1)^2, hexahedron interior (p-1)^3; simplices are supported for p <= 2
-    (triangle face / tetrahedron interior: none)."""
+    vertex 1, edge p-1, quadrilateral (p-1)^2, hexahedron interior (p-1)^3, triangle (p-2)(p-1)/2, tetrahedron interior
+    sum_{i<p-2} i(i+1)/2; prisms / pyramids are supported for p <= 2."""
     k = len(side_nodes)
     if k == 1:
         return 1
@@ -55,9 +55,12 @@ def side_nshape(topology, side_nodes, p):
         return p - 1
     if topology in (capi.HEX, capi.QUAD):
         return (p - 1) ** 2 if k == 4 else (p - 1) ** 3
+    if topology in (capi.TET, capi.TRI):
+        # Shape/pzshapetetra.cpp:451-468, pzshapetriang.cpp:452-468: triangular side (p-2)(p-1)/2, tetrahedron interior sum i(i+1)/2
+        return (p - 2) * (p - 1) // 2 if k == 3 else sum(i * (i + 1) // 2 for i in range(1, p - 2))
     if p > 2:
-        raise ValueError("tetrahedra / triangles / prisms / pyramids: uniform order p <= 2 only")
-    if topology in (capi.PRISM, capi.PYRAMID) and k == 4:
+        raise ValueError("prisms / pyramids: uniform order p <= 2 only")
+    if k == 4:
         return (p - 1) ** 2   # quadrilateral faces (Shape/pzshapeprism.cpp:761-775, pzshapepiram.cpp:679-696)
     return 0
 

@@ -463,10 +463,39 @@ static void chebyshev(double x, int num, double *phi, double *dphi) {
     }
 }
 
-/* TSHAPE::TransformElementToSide(side).Mult(): sidedim x dim, entries 0/+-1 (Sum is zero for cube and quad) */
-static void element_to_side(int topo, int side, int *sidedim, double E[3][3]) {
+/* TSHAPE::TransformElementToSide(side): Mult (sidedim x dim) and Sum (zero for cube and quad; the simplices project
+ * affinely: Topology/tpztetrahedron.cpp:460-545, Topology/tpztriangle.cpp:443-480) */
+static void element_to_side(int topo, int side, int *sidedim, double E[3][3], double Esum[3]) {
     memset(E, 0, sizeof(double) * 9);
-    if (topo == ORC_HEX) {
+    Esum[0] = Esum[1] = Esum[2] = 0.;
+    if (topo == ORC_TET) {
+        *sidedim = side < 10 ? 1 : (side < 14 ? 2 : 3);
+        switch (side) {
+            case 4: E[0][0] = 2.0; E[0][1] = 1.0; E[0][2] = 1.0; Esum[0] = -1.0; break;
+            case 5: E[0][0] = -1.0; E[0][1] = 1.0; break;
+            case 6: E[0][0] = -1.0; E[0][1] = -2.0; E[0][2] = -1.0; Esum[0] = 1.0; break;
+            case 7: E[0][0] = 1.0; E[0][1] = 1.0; E[0][2] = 2.0; Esum[0] = -1.0; break;
+            case 8: E[0][0] = -1.0; E[0][2] = 1.0; break;
+            case 9: E[0][1] = -1.0; E[0][2] = 1.0; break;
+            case 10: E[0][0] = 1.0; E[1][1] = 1.0; break;
+            case 11: E[0][0] = 1.0; E[1][2] = 1.0; break;
+            case 12:
+                E[0][0] = -1.0 / 3.0; E[0][1] = 2.0 / 3.0; E[0][2] = -1.0 / 3.0;
+                E[1][0] = -1.0 / 3.0; E[1][1] = -1.0 / 3.0; E[1][2] = 2.0 / 3.0;
+                Esum[0] = 1.0 / 3.0; Esum[1] = 1.0 / 3.0;
+                break;
+            case 13: E[0][1] = 1.0; E[1][2] = 1.0; break;
+            default: E[0][0] = E[1][1] = E[2][2] = 1.0; break; /* 14 */
+        }
+    } else if (topo == ORC_TRI) {
+        *sidedim = side < 6 ? 1 : 2;
+        switch (side) {
+            case 3: E[0][0] = 2.0; E[0][1] = 1.0; Esum[0] = -1.0; break;
+            case 4: E[0][0] = -1.0; E[0][1] = 1.0; break;
+            case 5: E[0][0] = -1.0; E[0][1] = -2.0; Esum[0] = 1.0; break;
+            default: E[0][0] = 1.0; E[1][1] = 1.0; break; /* 6 */
+        }
+    } else if (topo == ORC_HEX) {
         if (side < 20) {
             *sidedim = 1;
             switch (side) {
@@ -506,32 +535,69 @@ static void element_to_side(int topo, int side, int *sidedim, double E[3][3]) {
     }
 }
 
-/* GetSideTransform (pzgenericshape.cpp:13-55): T = P * E */
-static void side_transform(int topo, int side, const int64_t *ids, int *sidedim, double T[3][3]) {
-    double E[3][3];
-    const int dim = topo == ORC_HEX ? 3 : (topo == ORC_LINE ? 1 : 2);
-    element_to_side(topo, side, sidedim, E);
-    if (topo == ORC_HEX && side == 26) { memcpy(T, E, sizeof(E)); return; }
-    double P[3][3];
+/* Shape/pzshapetriang.cpp:18-27 */
+static const double gTrans2dT[6][2][2] = {{{1., 0.}, {0., 1.}},   {{0., 1.}, {1., 0.}},   {{0., 1.}, {-1., -1.}},
+                                          {{-1., -1.}, {0., 1.}}, {{-1., -1.}, {1., 0.}}, {{1., 0.}, {-1., -1.}}};
+static const double gVet2dT[6][2] = {{0., 0.}, {0., 0.}, {0., 1.}, {1., 0.}, {1., 0.}, {0., 1.}};
+static const int tet_face_nodes[4][3] = {{0, 1, 2}, {0, 1, 3}, {1, 2, 3}, {0, 2, 3}};
+
+/* Topology/tpztriangle.cpp:599-622 */
+static int tri_transform_id(const int64_t *id) {
+    int id0, id1, minid;
+    id0 = (id[0] < id[1]) ? 0 : 1;
+    minid = (id[2] < id[id0]) ? 2 : id0;
+    id0 = (minid + 1) % 3;
+    id1 = (minid + 2) % 3;
+    if (id[id0] < id[id1]) return 2 * minid;
+    return 2 * minid + 1;
+}
+
+/* GetSideTransform (pzgenericshape.cpp:13-55): Mult = P.Mult * E.Mult, Sum = P.Mult * E.Sum + P.Sum, each product formed as
+ * TPZFMatrix::MultAdd does (Matrix/pzfmatrix.cpp:596-606: z = 0, then z += 1 * a(i,k) * x(k,j) for k ascending); the volume
+ * side of a 3-D element keeps TransformElementToSide. */
+static void side_transform(int topo, int side, const int64_t *ids, int *sidedim, double T[3][3], double Tsum[3]) {
+    double E[3][3], Esum[3];
+    const int dim = (topo == ORC_HEX || topo == ORC_TET) ? 3 : (topo == ORC_LINE ? 1 : 2);
+    element_to_side(topo, side, sidedim, E, Esum);
+    if ((topo == ORC_HEX && side == 26) || (topo == ORC_TET && side == 14)) {
+        memcpy(T, E, sizeof(E));
+        memcpy(Tsum, Esum, sizeof(Esum));
+        return;
+    }
+    double P[3][3], Psum[3] = {0., 0., 0.};
     memset(P, 0, sizeof(P));
     if (*sidedim == 1) {
         int a, b;
         if (topo == ORC_HEX) { a = cube_edge_nodes[side - 8][0]; b = cube_edge_nodes[side - 8][1]; }
+        else if (topo == ORC_TET) { a = tet_edge_nodes[side - 4][0]; b = tet_edge_nodes[side - 4][1]; }
+        else if (topo == ORC_TRI) { a = side - 3; b = (side - 2) % 3; }
         else if (topo == ORC_LINE) { a = 0; b = 1; }
         else { a = side - 4; b = (side - 3) % 4; }
         P[0][0] = ids[a] < ids[b] ? 1. : -1.;
+    } else if (topo == ORC_TET || topo == ORC_TRI) {
+        int64_t loc[3];
+        for (int i = 0; i < 3; i++) loc[i] = topo == ORC_TET ? ids[tet_face_nodes[side - 10][i]] : ids[i];
+        const int tid = tri_transform_id(loc);
+        for (int i = 0; i < 2; i++) {
+            for (int j = 0; j < 2; j++) P[i][j] = gTrans2dT[tid][i][j];
+            Psum[i] = gVet2dT[tid][i];
+        }
     } else {
         int64_t loc[4];
         for (int i = 0; i < 4; i++) loc[i] = topo == ORC_HEX ? ids[cube_face_nodes[side - 20][i]] : ids[i];
         const int tid = quad_transform_id(loc);
         for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) P[i][j] = gTrans2dQ[tid][i][j];
     }
-    for (int i = 0; i < *sidedim; i++)
+    for (int i = 0; i < *sidedim; i++) {
         for (int j = 0; j < dim; j++) {
             double v = 0.;
-            for (int k = 0; k < *sidedim; k++) v += P[i][k] * E[k][j];
+            for (int k = 0; k < *sidedim; k++) v += 1. * P[i][k] * E[k][j];
             T[i][j] = v;
         }
+        double v = 0.;
+        for (int k = 0; k < *sidedim; k++) v += 1. * P[i][k] * Esum[k];
+        Tsum[i] = v + Psum[i];
+    }
 }
 
 /* blend (generating) functions of all sides: the p = 2 tables of shape_hex / shape_quad */
@@ -554,8 +620,8 @@ static int shape_hq_general(int topo, int p, const int64_t *ids, const double *p
     int shape = nc;
     for (int side = nc; side < nsides; side++) {
         int sidedim;
-        double T[3][3];
-        side_transform(topo, side, ids, &sidedim, T);
+        double T[3][3], Tsum[3];
+        side_transform(topo, side, ids, &sidedim, T, Tsum);
         const int ord1 = p - 1;
         int numshape = ord1;
         if (sidedim == 2) numshape = ord1 * ord1;
@@ -566,8 +632,8 @@ static int shape_hq_general(int topo, int p, const int64_t *ids, const double *p
         shape++;
         if (numshape == 1) continue;
         double out[3] = {0, 0, 0};
-        for (int i = 0; i < sidedim; i++) {
-            double v = 0.;
+        for (int i = 0; i < sidedim; i++) { /* TPZTransform::Apply, Matrix/pztrnsform.cpp:119-135 */
+            double v = Tsum[i];
             for (int j = 0; j < dim; j++) v += T[i][j] * pt[j];
             out[i] = v;
         }
@@ -603,6 +669,142 @@ static int shape_hq_general(int topo, int p, const int64_t *ids, const double *p
     return n;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Tetrahedra / triangles of order >= 3 (TPZShapeH1<TSHAPE>::Shape, Shape/TPZShapeH1.cpp:42-116):
+ *   blends: ShapeGenerating of ALL sides, Shape/pzshapetetra.cpp:101-164 (edges x4, faces phi_a phi_b phi_c x27, interior
+ *   phi_0 phi_1 phi_2 phi_3 x54), Shape/pzshapetriang.cpp:53-81 (edges x4, interior x27);
+ *   NConnectShapeF: Shape/pzshapetetra.cpp:451-468, pzshapetriang.cpp:452-468;
+ *   internal functions at the transformed point: edges Chebyshev T_i(x) (pzshapelinear.cpp:306-312), triangular sides
+ *   T_i(2 x0 - 1) T_j(2 x1 - 1), i + j < p - 2 ordered by (i + j, j) (pzshapetriang.cpp:279-311), tetrahedron interior
+ *   T_i T_j T_k at 2 x - 1, i + j + k < p - 3 (pzshapetetra.cpp:345-370).
+ * ------------------------------------------------------------------------------------------ */
+static int simplex_nconnect(int topo, int side, int p) {
+    if (topo == ORC_TET) {
+        if (side < 4) return 1;
+        if (side < 10) return p - 1;
+        if (side < 14) return (p - 2) * (p - 1) / 2;
+        int tot = 0;
+        for (int i = 1; i < p - 2; i++) tot += i * (i + 1) / 2;
+        return tot;
+    }
+    if (side < 3) return 1;
+    if (side < 6) return p - 1;
+    return (p - 2) < 0 ? 0 : ((p - 2) * (p - 1)) / 2;
+}
+
+static int shape_simplex_general(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi_out) {
+    const int dim = topo == ORC_TET ? 3 : 2, nc = dim + 1, nsides = topo == ORC_TET ? 15 : 7;
+    double bphi[15], bd[3][15];
+    memset(bd, 0, sizeof(bd));
+    bphi[0] = 1.;
+    for (int k = 0; k < dim; k++) bphi[0] -= pt[k]; /* 1 - pt[0] - pt[1] (- pt[2]) */
+    for (int k = 0; k < dim; k++) { bphi[k + 1] = pt[k]; bd[k][0] = -1.; bd[k][k + 1] = 1.; }
+    if (topo == ORC_TET) {
+        for (int is = 4; is < 10; is++) {
+            const int a = tet_edge_nodes[is - 4][0], b = tet_edge_nodes[is - 4][1];
+            bphi[is] = bphi[a] * bphi[b];
+            for (int k = 0; k < 3; k++) bd[k][is] = bd[k][a] * bphi[b] + bphi[a] * bd[k][b];
+        }
+        for (int is = 10; is < 14; is++) {
+            const int a = tet_face_nodes[is - 10][0], b = tet_face_nodes[is - 10][1], c = tet_face_nodes[is - 10][2];
+            bphi[is] = bphi[a] * bphi[b] * bphi[c];
+            for (int k = 0; k < 3; k++)
+                bd[k][is] = bd[k][a] * bphi[b] * bphi[c] + bphi[a] * bd[k][b] * bphi[c] + bphi[a] * bphi[b] * bd[k][c];
+        }
+        bphi[14] = bphi[0] * bphi[1] * bphi[2] * bphi[3];
+        for (int k = 0; k < 3; k++)
+            bd[k][14] = bd[k][0] * bphi[1] * bphi[2] * bphi[3] + bphi[0] * bd[k][1] * bphi[2] * bphi[3] +
+                        bphi[0] * bphi[1] * bd[k][2] * bphi[3] + bphi[0] * bphi[1] * bphi[2] * bd[k][3];
+        for (int is = 4; is < 15; is++) {
+            const double mult = is < 10 ? 4. : (is < 14 ? 27. : 54.);
+            bphi[is] *= mult;
+            for (int k = 0; k < 3; k++) bd[k][is] *= mult;
+        }
+    } else {
+        for (int is = 3; is < 6; is++) {
+            const int a = is % 3, b = (is + 1) % 3;
+            bphi[is] = bphi[a] * bphi[b];
+            for (int k = 0; k < 2; k++) bd[k][is] = bd[k][a] * bphi[b] + bphi[a] * bd[k][b];
+        }
+        bphi[6] = bphi[0] * bphi[1] * bphi[2];
+        for (int k = 0; k < 2; k++)
+            bd[k][6] = bd[k][0] * bphi[1] * bphi[2] + bphi[0] * bd[k][1] * bphi[2] + bphi[0] * bphi[1] * bd[k][2];
+        for (int is = 3; is < 7; is++) {
+            const double mult = is < 6 ? 4. : 27.;
+            bphi[is] *= mult;
+            for (int k = 0; k < 2; k++) bd[k][is] *= mult;
+        }
+    }
+    int n = nc;
+    for (int side = nc; side < nsides; side++) n += simplex_nconnect(topo, side, p);
+    for (int a = 0; a < nc; a++) { phi[a] = bphi[a]; for (int k = 0; k < dim; k++) dphi_out[k * n + a] = bd[k][a]; }
+    int shape = nc;
+    for (int side = nc; side < nsides; side++) {
+        const int numshape = simplex_nconnect(topo, side, p);
+        if (numshape == 0) continue;
+        phi[shape] = bphi[side];
+        for (int k = 0; k < dim; k++) dphi_out[k * n + shape] = bd[k][side];
+        shape++;
+        if (numshape == 1) continue;
+        int sidedim;
+        double T[3][3], Tsum[3];
+        side_transform(topo, side, ids, &sidedim, T, Tsum);
+        double out[3] = {0, 0, 0};
+        for (int i = 0; i < sidedim; i++) {
+            double v = Tsum[i];
+            for (int j = 0; j < dim; j++) v += T[i][j] * pt[j];
+            out[i] = v;
+        }
+        static __thread double pn[ORC_MAXSHAPE], dn[3][ORC_MAXSHAPE];
+        double c[3][64], dc[3][64];
+        if (sidedim == 1) {
+            chebyshev(out[0], p - 1, c[0], dc[0]);
+            for (int i = 0; i < p - 1; i++) { pn[i] = c[0][i]; dn[0][i] = dc[0][i]; }
+        } else if (sidedim == 2) {
+            const int ns2 = ((p - 2) * (p - 1)) / 2;
+            if (ns2 > 64) return -1;
+            chebyshev(2. * out[0] - 1., ns2, c[0], dc[0]);
+            chebyshev(2. * out[1] - 1., ns2, c[1], dc[1]);
+            int index = 0;
+            for (int iplusj = 0; iplusj < p - 2; iplusj++)
+                for (int j = 0; j <= iplusj; j++) {
+                    const int i = iplusj - j;
+                    pn[index] = c[0][i] * c[1][j];
+                    dn[0][index] = 2.0 * dc[0][i] * c[1][j];
+                    dn[1][index] = 2.0 * c[0][i] * dc[1][j];
+                    index++;
+                }
+        } else {
+            const int ord = p - 3;
+            for (int k = 0; k < 3; k++) chebyshev(2. * out[k] - 1., ord, c[k], dc[k]);
+            int index = 0;
+            for (int i = 0; i < ord; i++)
+                for (int j = 0; j < ord; j++)
+                    for (int k = 0; k < ord; k++)
+                        if (i + j + k < ord) {
+                            pn[index] = c[0][i] * c[1][j] * c[2][k];
+                            dn[0][index] = 2. * dc[0][i] * c[1][j] * c[2][k];
+                            dn[1][index] = 2. * c[0][i] * dc[1][j] * c[2][k];
+                            dn[2][index] = 2. * c[0][i] * c[1][j] * dc[2][k];
+                            index++;
+                        }
+        }
+        for (int idx = 1; idx < numshape; idx++) {
+            phi[shape] = bphi[side] * pn[idx];
+            for (int xj = 0; xj < dim; xj++) {
+                double aux;
+                if (sidedim < 3) {
+                    aux = 0.;
+                    for (int s2 = 0; s2 < sidedim; s2++) aux += T[s2][xj] * dn[s2][idx];
+                } else aux = dn[xj][idx];
+                dphi_out[xj * n + shape] = bd[xj][side] * pn[idx] + bphi[side] * aux;
+            }
+            shape++;
+        }
+    }
+    return n;
+}
+
 /* ids: global corner-node indices (gel->NodeIndex, Mesh/TPZCompElH1.cpp:110); may be NULL for p <= 2 */
 int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double *phi, double *dphi) {
     if (p < 1) return -1;
@@ -620,7 +822,8 @@ int orc_shape_ids(int topo, int p, const int64_t *ids, const double *pt, double 
     }
     if (p > ORC_MAXP || !ids) return -1;
     if (topo == ORC_HEX || topo == ORC_QUAD || topo == ORC_LINE) return shape_hq_general(topo, p, ids, pt, phi, dphi);
-    return -1; /* simplices of order >= 3: not restated */
+    if (topo == ORC_TET || topo == ORC_TRI) return shape_simplex_general(topo, p, ids, pt, phi, dphi);
+    return -1; /* prisms / pyramids of order >= 3: not restated */
 }
 
 int orc_shape(int topo, int p, const double *pt, double *phi, double *dphi) {

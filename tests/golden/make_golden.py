@@ -60,6 +60,15 @@ CASES = {
     "hexpyr_p2_poisson_n2_pert": (2, 2, 0, 3, 0.15, 1, 1),
     "hexpyr_p2_elast_n2_pert": (2, 2, 1, 3, 0.15, 1, 1),
     "hexpyr_p1_elast_n3": (3, 1, 1, 3, 0.0, 0, 0),
+    # simplices of order 3, 4: oriented edges and triangular faces (scrambled node numbering), tetrahedron interior function
+    "tet_p3_poisson_n2_pert_scr": (2, 3, 0, 1, 0.15, 1, 1, 7),
+    "tet_p4_poisson_n2_pert_scr": (2, 4, 0, 1, 0.15, 1, 1, 11),
+    "tet_p3_elast_n2_pert_scr": (2, 3, 1, 1, 0.15, 1, 1, 5),
+    "tet_p4_elast_n1_pert": (1, 4, 1, 1, 0.15, 2, 1, 0),
+    "tet_p3_poisson_n3": (3, 3, 0, 1, 0.0, 0, 0, 0),
+    "tri_p3_elast2d_n3_pert_scr": (3, 3, 2, 1, 0.15, 1, 1, 9, 2),
+    "tri_p4_poisson2d_n3_pert_scr": (3, 4, 0, 1, 0.15, 1, 1, 13, 2),
+    "tri_p4_elast2d_stress_n2_bc3": (2, 4, 3, 1, 0.15, 3, 1, 0, 2),
 }
 
 

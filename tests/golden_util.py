@@ -11,7 +11,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
 # prisms / hexahedra + pyramids: their GPU tests live in tests/test_gpu_prism_pyramid.py
 WEDGE_CASES = [c for c in ALL_CASES if c.startswith("prism") or c.startswith("hexpyr")]
-CORE_CASES = [c for c in ALL_CASES if c not in WEDGE_CASES]
+# tetrahedra / triangles of order 3, 4: tests/test_gpu_simplex_p34.py
+SIMPLEX34_CASES = [c for c in ALL_CASES if c.startswith(("tet_p3", "tet_p4", "tri_p3", "tri_p4"))]
+CORE_CASES = [c for c in ALL_CASES if c not in WEDGE_CASES and c not in SIMPLEX34_CASES]
 
 # material data of oracle/refdriver.cpp's recipe
 E_MOD, NU = 1000.0, 0.3

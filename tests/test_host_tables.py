@@ -23,7 +23,8 @@ def test_rules_and_shape_tables(name):
         assert np.array_equal(qw, g[f"rule_{tag}_w"])
         assert phi.shape == g[f"shape_{tag}_phi"].shape
         assert np.abs(phi - g[f"shape_{tag}_phi"]).max() < 4e-16
-        assert np.abs(dphi - g[f"shape_{tag}_dphi"]).max() < 1e-15
+        # (a few ulp of the largest gradient entry: 5.1 for tetrahedra of order 4)
+        assert np.abs(dphi - g[f"shape_{tag}_dphi"]).max() < 1e-15 * max(1.0, np.abs(g[f"shape_{tag}_dphi"]).max())
         if f"shapeall_{tag}_phi" in g:  # p >= 3: every element of the fixture, each with its own orientation class
             keys = capi.orientation_keys(topo, g[f"shapeall_{tag}_ids"])
             pts = qpts[g[f"shapeall_{tag}_q"]]
