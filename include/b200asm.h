@@ -69,7 +69,10 @@ typedef struct {
                                TPZEquationFilter the filtered (condensed) index, -1 for removed equations
                                (TPZEquationFilter::Filter, StrMatrix/TPZEquationFilter.h:120-141) */
     int32_t nqp;            /* points of the TPZIntPoints rule of order 2p (Mesh/pzelctemp.cpp:35-47) */
-    int32_t nshape;         /* H1 shape functions per element */
+    int32_t nshape;         /* H1 shape functions per element.  Normally b200asm_nshape(topology, porder); a SMALLER count declares an
+                               element whose sides carry different orders (TPZShapeH1<TSHAPE>::Initialize with per-side connect
+                               orders, Shape/TPZShapeH1.cpp:14-37): porder is then the largest order, phi / dphi define the functions,
+                               dest their equations, and the runtime-size kernels run the group */
     const double *qpts;     /* [nqp][dim]  TPZIntPoints::Point */
     const double *qwts;     /* [nqp] */
     const double *phi;      /* [nqp][nshape]       TPZShapeH1<TSHAPE>::Shape at the points (Shape/TPZShapeH1.cpp:42-116) */
@@ -90,8 +93,9 @@ void b200asm_destroy(b200asm_ctx *ctx);
 const char *b200asm_last_error(const b200asm_ctx *ctx); /* ctx may be NULL: last create() error */
 /* run on an existing CUDA stream (cudaStream_t passed as void*); default: a stream the context owns */
 int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
-/* integer options: "scatter" (B200ASM_SCATTER_*), "engine" (0 register-tile DFMA kernels, 1 DMMA kernels where one
- * exists), "timing" (1: CUDA events around every group's kernel launches, read by b200asm_group_time_ms),
+/* integer options: "scatter" (B200ASM_SCATTER_*), "engine" (0 register-tile DFMA kernels, 1 DMMA / closed-form kernels where one
+ * exists, 2 the generic runtime-size kernel for every volume group - the kernel that otherwise only runs the groups without a
+ * specialised one: other orders, sides of different order), "timing" (1: CUDA events around every group's kernel launches, read by b200asm_group_time_ms),
  * "affine" (default 1: hexahedral groups of order <= 2 whose elements are ALL parallelepipeds - measured on the device from
  * the node coordinates, to 1e-13 of the shortest edge vector, again after every b200asm_set_nodes - run the closed-form
  * kernel: constant Jacobian, no quadrature loop; 0: always the Gram / DMMA kernels),

@@ -401,6 +401,7 @@ struct BcParams {
     const double *__restrict__ dng;   // [nq][fdim][NN]
     int kind;                         // plane domain elements: B200ASM_POISSON / B200ASM_ELASTICITY2D
     int fdim;                         // dimension of the element: 2 (faces, plane elements) or 1 (line elements)
+    const double *__restrict__ force;   // generic volume kernel only: optional [nel][nq][NS] forcing-function table
     const int32_t *__restrict__ smap;   // [N*N*NS*NS][nel]
     const int32_t *__restrict__ smapT;
     double *__restrict__ a;
@@ -694,6 +695,133 @@ __global__ void __launch_bounds__(128) assemble_plane_kernel(const BcParams p, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// generic volume kernel: ANY topology and ANY shape-function count (orders beyond the specialised kernels, elements whose
+// sides carry different orders).  Runtime sizes, one CTA per element, thread <-> node pair (in <= jn):
+//   phase 1  thread <-> point: Jacobian, inverse, w|detJ| into shared memory (Mesh/pzgeoel.cpp:1296-1344)
+//   phase 2  per pair: for every point dphix = jacinv^T dphi of both functions (TPZCompElH1.cpp:140-149), the sums
+//            S[v][u] = sum_q w dphix(v,in) dphix(u,jn), then the entries of TPZMatPoisson.cpp:31-38 / TPZElasticity3D.cpp:318-326
+//   phase 3  thread <-> equation: load vector (TPZMatPoisson.cpp:39-40, TPZElasticity3D.cpp:278)
+// Nothing is staged per element beyond 11 doubles per point, so the rule and the function count are only bounded by the
+// entry-major scatter map (N^2 NS^2 int32 per element, the layout of the boundary / plane kernels).  It re-evaluates dphix per
+// pair: ~3x the arithmetic of the tiled kernels, which is the price of having no compile-time size.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) assemble_volume_generic_kernel(const BcParams p, int NN, int N, int NS) {
+    extern __shared__ double gv_smem[];
+    const int nq = p.nq, tid = threadIdx.x;
+    double *JI = gv_smem;                  // [nq][11]: jacinv (9), w|detJ|, unused
+    double *X = JI + (size_t)nq * 11;      // [NN][3]
+    const int M = N * NS;
+    for (int64_t el = p.el0 + blockIdx.x; el < p.el1; el += gridDim.x) {
+        __syncthreads();  // the previous element no longer reads JI / X
+        for (int i = tid; i < NN * 3; i += blockDim.x) X[i] = p.xyz[(int64_t)p.elnodes[el * NN + i / 3] * 3 + i % 3];
+        __syncthreads();
+        for (int q = tid; q < nq; q += blockDim.x) {
+            const double *dn = p.dng + (size_t)q * 3 * NN;
+            double j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0, j20 = 0, j21 = 0, j22 = 0;
+            for (int a = 0; a < NN; a++) {
+                const double d0 = __ldg(dn + a), d1 = __ldg(dn + NN + a), d2 = __ldg(dn + 2 * NN + a);
+                const double x = X[a * 3], y = X[a * 3 + 1], z = X[a * 3 + 2];
+                j00 += x * d0; j01 += x * d1; j02 += x * d2;
+                j10 += y * d0; j11 += y * d1; j12 += y * d2;
+                j20 += z * d0; j21 += z * d1; j22 += z * d2;
+            }
+            double det = 0.0;
+            det -= j02 * j11 * j20;
+            det += j01 * j12 * j20;
+            det += j02 * j10 * j21;
+            det -= j00 * j12 * j21;
+            det -= j01 * j10 * j22;
+            det += j00 * j11 * j22;
+            if (fabs(det) < 1.e-12) det = 1.e-12;
+            const double id = 1.0 / det;
+            double *o = JI + (size_t)q * 11;
+            o[0] = (-j12 * j21 + j11 * j22) * id;
+            o[1] = (j02 * j21 - j01 * j22) * id;
+            o[2] = (-j02 * j11 + j01 * j12) * id;
+            o[3] = (j12 * j20 - j10 * j22) * id;
+            o[4] = (-j02 * j20 + j00 * j22) * id;
+            o[5] = (j02 * j10 - j00 * j12) * id;
+            o[6] = (-j11 * j20 + j10 * j21) * id;
+            o[7] = (j01 * j20 - j00 * j21) * id;
+            o[8] = (-j01 * j10 + j00 * j11) * id;
+            o[9] = __ldg(p.qw + q) * fabs(det);
+        }
+        __syncthreads();
+        const int npair = p.rhs_only ? 0 : N * (N + 1) / 2;
+        for (int idx = tid; idx < npair; idx += blockDim.x) {
+            int in = 0, rem = idx;
+            while (rem >= N - in) { rem -= N - in; in++; }
+            const int jn = in + rem;
+            double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int q = 0; q < nq; q++) {
+                const double *ji = JI + (size_t)q * 11;
+                const double *dp = p.dphi + (size_t)q * 3 * N;
+                const double a0 = __ldg(dp + in), a1 = __ldg(dp + N + in), a2 = __ldg(dp + 2 * N + in);
+                const double b0 = __ldg(dp + jn), b1 = __ldg(dp + N + jn), b2 = __ldg(dp + 2 * N + jn);
+                double gi[3], gj[3];
+#pragma unroll
+                for (int v = 0; v < 3; v++) {
+                    gi[v] = ji[v] * a0 + ji[3 + v] * a1 + ji[6 + v] * a2;
+                    gj[v] = ji[v] * b0 + ji[3 + v] * b1 + ji[6 + v] * b2;
+                }
+                const double w = ji[9];
+                if (NS == 1) {
+                    S[0][0] += w * (gi[0] * gj[0] + gi[1] * gj[1] + gi[2] * gj[2]);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 3; v++)
+#pragma unroll
+                        for (int u = 0; u < 3; u++) S[v][u] += w * gi[v] * gj[u];
+                }
+            }
+            if (NS == 1) {
+                const size_t sidx = (size_t)(in * N + jn) * p.nel + el;
+                const double e = p.coef[0] * S[0][0];
+                const int32_t pos = p.smap[sidx];
+                if (pos >= 0) scatter_add(p.a + pos, e, p.atomic);
+                if (p.smapT) {
+                    const int32_t posT = p.smapT[sidx];
+                    if (posT >= 0) scatter_add(p.a + posT, e, p.atomic);
+                }
+            } else {
+                const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) {
+                        if (in == jn && b < a) continue;
+                        const double e = a == b ? (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3
+                                                : S[b][a] * C1 - S[a][b] * C2;
+                        const size_t sidx = ((size_t)((in * N + jn) * 3 + a) * 3 + b) * p.nel + el;
+                        const int32_t pos = p.smap[sidx];
+                        if (pos >= 0) scatter_add(p.a + pos, e, p.atomic);
+                        if (p.smapT) {
+                            const int32_t posT = p.smapT[sidx];
+                            if (posT >= 0) scatter_add(p.a + posT, e, p.atomic);
+                        }
+                    }
+            }
+        }
+        for (int m = tid; m < M; m += blockDim.x) {
+            const int i = m / NS, a = m - i * NS;
+            double t = 0.0;
+            for (int q = 0; q < nq; q++) {
+                const double *ji = JI + (size_t)q * 11;
+                const double w = ji[9], ph = __ldg(p.phi + (size_t)q * N + i);
+                if (NS == 1) {
+                    const double f = p.force ? p.force[(size_t)el * nq + q] : p.coef[1];
+                    t += w * p.coef[0] * ph * f;
+                } else {
+                    const double *dp = p.dphi + (size_t)q * 3 * N;
+                    const double dx = ji[a] * __ldg(dp + i) + ji[3 + a] * __ldg(dp + N + i) + ji[6 + a] * __ldg(dp + 2 * N + i);
+                    const double f = p.force ? p.force[((size_t)el * nq + q) * 3 + a] : p.coef[3 + a];
+                    t += w * f * ph - p.coef[6 + a] * (w * dx);
+                }
+            }
+            scatter_rhs(p.rhs, p.dest[el * M + m], t, p.atomic);
+        }
+    }
+}
+
 __global__ void build_bc_smap_kernel(int64_t nel, int n, int ns, const int32_t *__restrict__ dest,
                                      const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, int symmetric,
                                      int32_t *__restrict__ smap, int32_t *__restrict__ smapT, int *__restrict__ missing) {
@@ -745,6 +873,8 @@ struct Group {
     int64_t nel = 0, nbatch = 0;
     int64_t max_dest = -1;  // largest destination equation of the group
     bool plane = false;     // quadrilaterals / triangles as DOMAIN elements of a plane problem (kind POISSON / ELASTICITY2D)
+    bool generic = false;   // volume group without a specialised kernel (other orders, non-uniform side orders): generic kernel
+    bool uniform = true;    // nshape is the count of uniform order `porder` (false: the sides carry different orders)
     int cfg = -1;  // index into the dispatch table (register-tile kernels)
     int mma = -1;  // index into the DMMA dispatch table, -1: none
     int aff = -1;  // index into the closed-form table for parallelepiped hexahedra (affine_hex.cuh), -1: none
@@ -1090,6 +1220,10 @@ MmaEntry make_affhex_entry(int porder) {
 const MmaEntry kAffHex[] = {make_affhex_entry<HexP1PoissonAff>(1), make_affhex_entry<HexP1ElastAff>(1),
                             make_affhex_entry<HexP2PoissonAff>(2), make_affhex_entry<HexP2ElastAff>(2)};
 constexpr int kNumAffHex = sizeof(kAffHex) / sizeof(kAffHex[0]);
+// volume group run by assemble_volume_generic_kernel (no specialised kernel, or engine 2 = the generic kernel everywhere)
+bool runs_generic(const b200asm_ctx *ctx, const Group &g) { return g.dim == 3 && (g.generic || ctx->engine == 2); }
+// groups whose scatter map is entry-major ([entry][element]): boundary elements, plane elements, generic volume groups
+bool entry_major(const b200asm_ctx *ctx, const Group &g) { return g.kind == B200ASM_BC || g.plane || runs_generic(ctx, g); }
 // the kernel that runs a volume group on the DMMA / closed-form engine (nullptr: register-tile kernel)
 const MmaEntry *fast_entry(const b200asm_ctx *ctx, const Group &g) {
     if (ctx->engine != 1) return nullptr;
@@ -1104,18 +1238,18 @@ cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t dispatch_bc(int topology, int porder, int ns, const BcParams &p, cudaStream_t s) {
+// porder 0: the sides of the elements carry different orders (n functions): runtime-size warp kernel
+cudaError_t dispatch_bc(int topology, int porder, int nn, int n, int ns, const BcParams &p, cudaStream_t s) {
     if (topology == B200ASM_LINE) {  // boundary of a plane problem
         const int grid = (int)((p.el1 - p.el0 + 3) / 4);
-        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, 2, porder + 1, ns);
+        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, 2, n, ns);
         return cudaGetLastError();
     }
     if (ns == 2) return cudaErrorInvalidValue;
-    if (porder >= 3) {
+    if (porder >= 3 || porder == 0) {
         if (topology != B200ASM_QUAD && topology != B200ASM_TRI) return cudaErrorInvalidValue;
-        const int n = topology == B200ASM_QUAD ? (porder + 1) * (porder + 1) : (porder + 1) * (porder + 2) / 2;
         const int grid = (int)((p.el1 - p.el0 + 3) / 4);
-        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, topology == B200ASM_QUAD ? 4 : 3, n, ns);
+        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, nn, n, ns);
         return cudaGetLastError();
     }
     if (topology == B200ASM_QUAD && porder == 1) return ns == 1 ? launch_bc<4, 4, 1>(p, s) : launch_bc<4, 4, 3>(p, s);
@@ -1178,7 +1312,7 @@ int choose_kernels(b200asm_ctx *ctx) {
     for (Group &g : ctx->groups) {
         if (g.aff < 0 || g.aff_checked) continue;
         bool aff = false;
-        if (ctx->affine && ctx->engine == 1 && g.nel > 0) {
+        if (ctx->affine && ctx->engine == 1 && !g.generic && g.nel > 0) {
             CK(cudaMemsetAsync(ctx->d_missing, 0, sizeof(int), ctx->stream));
             const int grid = (int)std::min<int64_t>((g.nel + 127) / 128, (int64_t)ctx->num_sms * 16);
             hex_affinity_kernel<<<grid, 128, 0, ctx->stream>>>(g.nel, g.d_elnodes, ctx->d_xyz, ctx->d_missing);
@@ -1207,7 +1341,7 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
     for (Group &g : ctx->groups) {
         cudaFree(g.d_smap); cudaFree(g.d_smapT);
         g.d_smap = g.d_smapT = nullptr;
-        if (g.kind == B200ASM_BC || g.plane) {
+        if (entry_major(ctx, g)) {
             g.smap_len = (size_t)g.n * g.n * g.ns * g.ns * g.nel;
         } else if (const MmaEntry *me = fast_entry(ctx, g)) {
             g.smap_len = (size_t)g.nel * me->slots;
@@ -1225,7 +1359,7 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
         if (!ctx->symmetric) CK(cudaMalloc((void **)&g.d_smapT, std::max<size_t>(g.smap_len, 1) * sizeof(int32_t)));
         if (g.smap_len == 0) continue;
         const int grid = (int)std::min<size_t>((g.smap_len + 255) / 256, (size_t)ctx->num_sms * 32);
-        if (g.kind == B200ASM_BC || g.plane) {
+        if (entry_major(ctx, g)) {
             build_bc_smap_kernel<<<grid, 256, 0, ctx->stream>>>(g.nel, g.n, g.ns, g.d_dest, ctx->d_ia, d_ja, ctx->symmetric,
                                                                 g.d_smap, g.d_smapT, ctx->d_missing);
             CK(cudaGetLastError());
@@ -1318,7 +1452,7 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
         return 0;
     }
     if (!strcmp(name, "engine")) {
-        if (value != 0 && value != 1) return fail(ctx, B200ASM_EINVAL, "engine: 0 (register tiles) or 1 (DMMA where available)");
+        if (value < 0 || value > 2) return fail(ctx, B200ASM_EINVAL, "engine: 0 (register tiles), 1 (DMMA / closed form where available) or 2 (generic runtime-size kernel)");
         ctx->engine = (int)value;
         ctx->maps_valid = false;  // the scatter-map layout depends on the kernel
         for (Group &g : ctx->groups) g.aff_checked = false;
@@ -1391,9 +1525,18 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     g.dim = (gi->topology == B200ASM_HEX || gi->topology == B200ASM_TET || gi->topology == B200ASM_PRISM || gi->topology == B200ASM_PYRAMID)
                 ? 3 : (gi->topology == B200ASM_LINE ? 1 : 2);
     g.plane = g.dim == 2 && (gi->kind == B200ASM_POISSON || gi->kind == B200ASM_ELASTICITY2D);
+    if (g.nn > 0 && g.n < 0 && gi->porder >= 1 && gi->nshape >= g.nn &&
+        (gi->topology == B200ASM_PRISM || gi->topology == B200ASM_PYRAMID))
+        g.n = gi->nshape;  // prisms / pyramids of order >= 3: no host formula for the count, the caller's tables define it
     if (g.nn < 0 || g.n < 0 || gi->porder < 1)
         return fail(ctx, B200ASM_EINVAL, "add_group: unsupported topology/order (H1, uniform p: hex/quad/tet/tri 1..4, prism/pyramid 1..2)");
-    if (gi->nshape != g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not match topology/order");
+    if (gi->nshape != g.n) {
+        // the sides carry different orders (p-refined neighbours): the caller's tables define the functions, porder is the
+        // largest order; runtime-size kernels run the group
+        if (gi->nshape < g.nn || gi->nshape > g.n) return fail(ctx, B200ASM_EINVAL, "add_group: nshape does not fit topology/order");
+        g.n = gi->nshape;
+        g.uniform = false;
+    }
     if (g.ns < 1 || g.ns > 3) return fail(ctx, B200ASM_EINVAL, "add_group: nstate must be 1, 2 or 3");
     if (g.nel < 0 || g.nq <= 0 || g.nq > 512) return fail(ctx, B200ASM_EINVAL, "add_group: bad nel/nqp");
     if (!gi->elnodes || !gi->dest || !gi->qpts || !gi->qwts || !gi->phi || !gi->dphi)
@@ -1404,10 +1547,10 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if (gi->kind == B200ASM_ELASTICITY3D && g.ns != 3) return fail(ctx, B200ASM_EINVAL, "add_group: Elasticity3D has nstate 3");
         if (gi->kind != B200ASM_POISSON && gi->kind != B200ASM_ELASTICITY3D)
             return fail(ctx, B200ASM_EINVAL, "add_group: volume elements need kind POISSON or ELASTICITY3D");
-        for (int k = 0; k < kNumVol; k++)
+        for (int k = 0; k < kNumVol && g.uniform; k++)
             if (kVol[k].topology == g.topology && kVol[k].porder == g.porder && kVol[k].ns == g.ns) g.cfg = k;
-        if (g.cfg < 0) return fail(ctx, B200ASM_EINVAL, "add_group: no kernel for this configuration");
-        for (int k = 0; k < kNumMma; k++)
+        if (g.cfg < 0) g.generic = true;  // no specialised kernel: assemble_volume_generic_kernel (runtime sizes)
+        for (int k = 0; k < kNumMma && !g.generic; k++)
             if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns &&
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
                 g.mma = k;
@@ -1553,7 +1696,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if ((rc = upload(ctx, &g.d_phi_pad, phi_pad.data(), phi_pad.size()))) return rc;
     }
     std::vector<double> aux;  // (lives until the synchronize below)
-    if (volume && g.topology == B200ASM_HEX && g.porder <= 2) {
+    if (volume && g.topology == B200ASM_HEX && g.porder <= 2 && !g.generic) {
         for (int k = 0; k < kNumAffHex; k++)
             if (kAffHex[k].porder == g.porder && kAffHex[k].ns == g.ns) g.aff = k;
         if (g.n == 8 && g.ns == 1) aff_tables<HexP1PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
@@ -1562,7 +1705,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         else aff_tables<HexP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
     }
-    if (volume && g.topology == B200ASM_TET && g.porder <= 2) {  // (orders 3, 4 run the register-tile kernel)
+    if (volume && g.topology == B200ASM_TET && g.porder <= 2 && !g.generic) {  // (orders 3, 4 run the register-tile kernel)
         if (g.n == 4 && g.ns == 1) aff_tables<TetP1PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else if (g.n == 4) aff_tables<TetP1ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else if (g.ns == 1) aff_tables<TetP2PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
@@ -1779,23 +1922,29 @@ namespace {
 int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
     const int atomic = ctx->scatter == B200ASM_SCATTER_ATOMIC ? 1 : 0;
     const size_t nseg = g.seg.size() - 1;  // 1, or the number of colours
-    if (g.kind == B200ASM_BC || g.plane) {
+    if (entry_major(ctx, g)) {
         BcParams p;
         p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
         p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
-        p.kind = g.kind; p.fdim = g.dim;
+        p.kind = g.kind; p.fdim = g.dim; p.force = g.d_force;
         p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
         memcpy(p.coef, g.coef, sizeof(p.coef));
         for (size_t c = 0; c < nseg; c++) {
             p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];
+            if (r0 >= 0) { p.el0 = r0; p.el1 = r1; }  // (element chunk of an uncoloured volume group: nseg == 1)
             if (p.el1 == p.el0) continue;
-            if (g.plane) {
+            if (g.dim == 3) {
+                const size_t smem = ((size_t)g.nq * 11 + (size_t)g.nn * 3) * sizeof(double);
+                const int grid = (int)std::min<int64_t>(p.el1 - p.el0, (int64_t)ctx->num_sms * 8);
+                assemble_volume_generic_kernel<<<grid, 128, smem, ctx->stream>>>(p, g.nn, g.n, g.ns);
+                CK(cudaGetLastError());
+            } else if (g.plane) {
                 const int grid = (int)((p.el1 - p.el0 + 3) / 4);
                 const size_t smem = 4 * (size_t)g.nq * (2 + 2 * g.n) * sizeof(double);
                 assemble_plane_kernel<<<grid, 128, smem, ctx->stream>>>(p, g.nn, g.n, g.ns);
                 CK(cudaGetLastError());
             } else {
-                CK(dispatch_bc(g.topology, g.porder, g.ns, p, ctx->stream));
+                CK(dispatch_bc(g.topology, g.uniform ? g.porder : 0, g.nn, g.n, g.ns, p, ctx->stream));
             }
             ctx->launches++;
         }

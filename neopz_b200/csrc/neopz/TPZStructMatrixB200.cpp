@@ -59,8 +59,8 @@ struct ElastAccess : public TPZElasticity3D {
     using TPZElasticity3D::fPreStress;
 };
 
-// one device group per (topology, material, order, side-orientation class): for p >= 3 the shape functions of a side
-// depend on the global indices of its corner nodes (Shape/pzgenericshape.cpp:57-68), elements of one class share tables
+// one device group per (topology, material, side orders, side orientations): the shape functions of a side with more than one
+// function depend on the global indices of its corner nodes (Shape/pzgenericshape.cpp:57-68); elements of one class share tables
 // protected members of TPZElasticity2D (Material/Elasticity/TPZElasticity2D.h:196-232)
 struct Elast2DAccess : public TPZElasticity2D {
     using TPZElasticity2D::ff;
@@ -70,11 +70,13 @@ struct Elast2DAccess : public TPZElasticity2D {
     using TPZElasticity2D::fPreStressYY;
 };
 
+// signature: the order of every side connect and, where a side carries more than one function, its transform id
+// (TSHAPE::GetTransformId, the input of ComputeTransforms): equal signatures <=> equal TPZShapeH1 tables
 struct GroupKey {
-    int topology, matid, porder;
-    int64_t orientation;
+    int topology, matid;
+    std::vector<int> signature;
     bool operator<(const GroupKey &o) const {
-        return std::tie(topology, matid, porder, orientation) < std::tie(o.topology, o.matid, o.porder, o.orientation);
+        return std::tie(topology, matid, signature) < std::tie(o.topology, o.matid, o.signature);
     }
 };
 
@@ -101,15 +103,30 @@ int TopologyOf(MElementType t) {
     }
 }
 
+// orders of the side connects (the element may be p-refined: sides of different order) followed by the transform ids of the
+// sides with more than one function (Shape/pzgenericshape.cpp:57-68)
 template <class TSHAPE>
-void ShapeTables(TPZCompEl *cel, int porder, HostGroup &g) {
+void SideSignature(TPZCompEl *cel, std::vector<int> &sig) {
+    TPZGeoEl *gel = cel->Reference();
+    const int nc = TSHAPE::NCornerNodes, ns = TSHAPE::NSides;
+    TPZManVector<int64_t, 8> ids(nc);
+    for (int i = 0; i < nc; i++) ids[i] = gel->NodeIndex(i);
+    sig.clear();
+    for (int side = nc; side < ns; side++) sig.push_back(cel->Connect(side).Order());
+    for (int side = nc; side < ns; side++)
+        sig.push_back(TSHAPE::NConnectShapeF(side, cel->Connect(side).Order()) > 1 ? TSHAPE::GetTransformId(side, ids) : 0);
+}
+
+template <class TSHAPE>
+void ShapeTables(TPZCompEl *cel, HostGroup &g) {
     // integration rule and shape tables through the reference's own objects
     auto *intel = dynamic_cast<TPZInterpolationSpace *>(cel);
     TPZGeoEl *gel = cel->Reference();
     const int nc = TSHAPE::NCornerNodes, ns = TSHAPE::NSides, dim = TSHAPE::Dimension;
     TPZManVector<int64_t, 8> ids(nc);
-    TPZManVector<int, 27> orders(ns - nc, porder);
+    TPZManVector<int, 27> orders(ns - nc, 1);
     for (int i = 0; i < nc; i++) ids[i] = gel->NodeIndex(i);
+    for (int side = nc; side < ns; side++) orders[side - nc] = cel->Connect(side).Order();
     TPZShapeData sd;
     TPZShapeH1<TSHAPE>::Initialize(ids, orders, sd);
     const TPZIntPoints &rule = intel->GetIntegrationRule();
@@ -347,28 +364,27 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
                         dynamic_cast<TPZCompElH1<pzshape::TPZShapePiram> *>(cel);
         if (topo < 0 || !h1) Fatal("element " + std::to_string(iel) + " is not an H1 hexahedron/tetrahedron/prism/pyramid/quadrilateral/triangle/line");
         if (!gel->IsLinearMapping()) Fatal("element " + std::to_string(iel) + " has a non-(multi)linear geometric map");
-        // uniform order, no constraints
+        // no constraints; the sides may carry different orders (p-refined neighbours)
         const int ncon = cel->NConnects();
         const int ncorner = gel->NCornerNodes();
-        int porder = -1;
+        int porder = 1;
         for (int i = 0; i < ncon; i++) {
             TPZConnect &con = cel->Connect(i);
             if (con.HasDependency() || con.IsCondensed()) Fatal("hanging nodes / condensed connects are not supported");
-            if (i >= ncorner) {
-                if (porder < 0) porder = con.Order();
-                if (con.Order() != porder) Fatal("non-uniform polynomial order inside an element is not supported");
-            }
+            if (i >= ncorner) porder = std::max<int>(porder, con.Order());
         }
-        const bool upto4 = topo != B200ASM_PRISM && topo != B200ASM_PYRAMID;
-        if (porder < 1 || porder > (upto4 ? 4 : 2))
-            Fatal("polynomial order " + std::to_string(porder) + " is not supported (hexahedra/tetrahedra/quadrilaterals/triangles/lines 1..4, prisms/pyramids 1..2)");
-        int64_t orientation = 0;
-        if (porder >= 3) {
-            int32_t corner[8];
-            for (int i = 0; i < ncorner; i++) corner[i] = (int32_t)gel->NodeIndex(i);
-            if (b200asm_orientation_keys(topo, 1, corner, &orientation) != 0) Fatal("b200asm_orientation_keys failed");
+        if (porder > 9) Fatal("polynomial order " + std::to_string(porder) + " is not supported (<= 9)");
+        std::vector<int> signature;
+        switch (topo) {
+            case B200ASM_HEX: SideSignature<pzshape::TPZShapeCube>(cel, signature); break;
+            case B200ASM_TET: SideSignature<pzshape::TPZShapeTetra>(cel, signature); break;
+            case B200ASM_QUAD: SideSignature<pzshape::TPZShapeQuad>(cel, signature); break;
+            case B200ASM_LINE: SideSignature<pzshape::TPZShapeLinear>(cel, signature); break;
+            case B200ASM_PRISM: SideSignature<pzshape::TPZShapePrism>(cel, signature); break;
+            case B200ASM_PYRAMID: SideSignature<pzshape::TPZShapePiram>(cel, signature); break;
+            default: SideSignature<pzshape::TPZShapeTriang>(cel, signature); break;
         }
-        const GroupKey key{topo, mat->Id(), porder, orientation};
+        const GroupKey key{topo, mat->Id(), signature};
         auto it = index.find(key);
         if (it == index.end()) {
             it = index.emplace(key, c.groups.size()).first;
@@ -387,13 +403,13 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
             if (auto *lc = dynamic_cast<TPZMatLoadCasesBase *>(mat))
                 if (lc->NumLoadCases() != 1) Fatal("more than one load case is not supported");
             switch (topo) {
-                case B200ASM_HEX: ShapeTables<pzshape::TPZShapeCube>(cel, porder, g); break;
-                case B200ASM_TET: ShapeTables<pzshape::TPZShapeTetra>(cel, porder, g); break;
-                case B200ASM_QUAD: ShapeTables<pzshape::TPZShapeQuad>(cel, porder, g); break;
-                case B200ASM_LINE: ShapeTables<pzshape::TPZShapeLinear>(cel, porder, g); break;
-                case B200ASM_PRISM: ShapeTables<pzshape::TPZShapePrism>(cel, porder, g); break;
-                case B200ASM_PYRAMID: ShapeTables<pzshape::TPZShapePiram>(cel, porder, g); break;
-                default: ShapeTables<pzshape::TPZShapeTriang>(cel, porder, g); break;
+                case B200ASM_HEX: ShapeTables<pzshape::TPZShapeCube>(cel, g); break;
+                case B200ASM_TET: ShapeTables<pzshape::TPZShapeTetra>(cel, g); break;
+                case B200ASM_QUAD: ShapeTables<pzshape::TPZShapeQuad>(cel, g); break;
+                case B200ASM_LINE: ShapeTables<pzshape::TPZShapeLinear>(cel, g); break;
+                case B200ASM_PRISM: ShapeTables<pzshape::TPZShapePrism>(cel, g); break;
+                case B200ASM_PYRAMID: ShapeTables<pzshape::TPZShapePiram>(cel, g); break;
+                default: ShapeTables<pzshape::TPZShapeTriang>(cel, g); break;
             }
         }
         HostGroup &g = c.groups[it->second];

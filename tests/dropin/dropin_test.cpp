@@ -25,6 +25,7 @@
 #include "pzcmesh.h"
 #include "pzgmesh.h"
 #include "pzgnode.h"
+#include "pzintel.h"
 #include "pzstepsolver.h"
 #include "pzsysmp.h"
 #include "pzysmp.h"
@@ -36,7 +37,9 @@ static double secs(clk::time_point a, clk::time_point b) { return std::chrono::d
 // is ~1e16 (penalty), and a relative residual tolerance of 1e-15 no longer constrains the interior equations.
 // phys 2 / 3: TPZElasticity2D (plane strain / plane stress) on a plane mesh of quadrilaterals (tet = 0) or triangles
 // tet (3-D): 0 hexahedra, 1 tetrahedra, 2 prisms (EPrismatic), 3 hexahedra + pyramids (EHexaPyrMixed)
-static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, double dirichlet) {
+// prefine: every third domain element is p-refined by one order (TPZInterpolatedElement::PRefine): elements, faces and edges
+// of different order meet, the boundary elements follow in AdjustBoundaryElements
+static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, double dirichlet, int prefine = 0) {
     const int dim = phys >= 2 ? 2 : 3;
     TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
     TPZManVector<int, 7> matids(dim == 3 ? 7 : 5, -1);
@@ -94,6 +97,17 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
     }
     cmesh->SetAllCreateFunctionsContinuous();
     cmesh->AutoBuild();
+    if (prefine) {
+        int64_t count = 0;
+        const int64_t nel0 = cmesh->NElements();
+        for (int64_t iel = 0; iel < nel0; iel++) {
+            TPZCompEl *cel = cmesh->Element(iel);
+            if (!cel || !cel->Reference() || cel->Reference()->Dimension() != dim) continue;
+            if (count++ % 3) continue;
+            if (auto *intel = dynamic_cast<TPZInterpolatedElement *>(cel)) intel->PRefine(p + 1);
+        }
+        cmesh->ExpandSolution();
+    }
     cmesh->AdjustBoundaryElements();
     cmesh->CleanUpUnconnectedNodes();
     return cmesh;
@@ -196,7 +210,7 @@ static double RelF(const std::vector<double> &x, const std::vector<double> &ref)
 
 int main(int argc, char **argv) {
     if (argc < 6) {
-        std::cerr << "usage: dropin_test n p phys(0|1|2|3) tet(0|1|2|3) symmetric(0|1) [solve(0|1)] [cpu_threads]\n";
+        std::cerr << "usage: dropin_test n p phys(0|1|2|3) tet(0|1|2|3) symmetric(0|1) [solve(0|1)] [cpu_threads] [device_create] [equation_filter] [pin_host] [prefine]\n";
         return 2;
     }
     const int n = atoi(argv[1]), p = atoi(argv[2]), phys = atoi(argv[3]), tet = atoi(argv[4]), symmetric = atoi(argv[5]);
@@ -206,7 +220,8 @@ int main(int argc, char **argv) {
     const int device_create = argc > 8 ? atoi(argv[8]) : 0;
     g_filter = argc > 9 ? atoi(argv[9]) : 0;
     g_pin = argc > 10 ? atoi(argv[10]) : 0;
-    TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3);
+    const int prefine = argc > 11 ? atoi(argv[11]) : 0;
+    TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3, prefine);
     Csr ref, refmt, gpu;
     double t1, t2, tm1, tm2, g1, g2;
     if (symmetric) {
@@ -256,7 +271,7 @@ int main(int argc, char **argv) {
     }
     const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
-    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"cpu_first_assemble_s\": " << t1
+    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"prefine\": " << prefine << ", \"cpu_first_assemble_s\": " << t1
               << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
               << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
               << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel
