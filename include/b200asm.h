@@ -84,7 +84,10 @@ typedef struct {
      * BC:           coef[0..8]=M (3x3 row-major, upper-left ns x ns used), coef[9..11]=v */
     double coef[16];
     const double *force; /* optional [nel][nqp][nstate]: forcing function evaluated by the host at the
-                            integration points (std::function callbacks stay on the host); NULL = constant */
+                            integration points (std::function callbacks stay on the host); NULL = constant.
+                            kind BC: boundary data given by a function (TPZBndCondT::ForcingFunctionBC): the coefficient of
+                            phi_i * weight in ef at every point (e.g. BigNumber * g(x) for a Dirichlet condition,
+                            TPZMatPoisson.cpp:62-90), replacing the constant coef[9..11] */
 } b200asm_group;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

@@ -560,6 +560,17 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
                 }
             }
     }
+    if (p.force) {
+        // boundary data given by a function (TPZBndCondT::ForcingFunctionBC, e.g. TPZMatPoisson.cpp:62-64, TPZElasticity3D.cpp:637-662):
+        // the host evaluated the coefficient of phi_i * weight in ef at every integration point: force[el][q][a]
+        for (int i = lane; i < N; i += 32)
+            for (int a = 0; a < NS; a++) {
+                double t = 0.0;
+                for (int q = 0; q < p.nq; q++) t += __ldg(p.phi + (size_t)q * N + i) * W[q] * p.force[((size_t)el * p.nq + q) * NS + a];
+                scatter_rhs(p.rhs, p.dest[el * (N * NS) + i * NS + a], t, p.atomic);
+            }
+        return;
+    }
     for (int i = lane; i < N; i += 32) {
         double T = 0.0;
         for (int q = 0; q < p.nq; q++) T += __ldg(p.phi + (size_t)q * N + i) * W[q];
@@ -1246,7 +1257,7 @@ cudaError_t dispatch_bc(int topology, int porder, int nn, int n, int ns, const B
         return cudaGetLastError();
     }
     if (ns == 2) return cudaErrorInvalidValue;
-    if (porder >= 3 || porder == 0) {
+    if (porder >= 3 || porder == 0 || p.force) {  // (a table of boundary data: the runtime-size kernel reads it)
         if (topology != B200ASM_QUAD && topology != B200ASM_TRI) return cudaErrorInvalidValue;
         const int grid = (int)((p.el1 - p.el0 + 3) / 4);
         assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, nn, n, ns);
@@ -1713,7 +1724,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
     }
     std::vector<double> force;
-    if (gi->force && volume) {
+    if (gi->force && (volume || gi->kind == B200ASM_BC)) {
         const size_t per = (size_t)g.nq * g.ns;
         force.resize((size_t)g.nel * per);
         for (int64_t e = 0; e < g.nel; e++) memcpy(&force[(size_t)e * per], gi->force + (size_t)order[e] * per, per * sizeof(double));

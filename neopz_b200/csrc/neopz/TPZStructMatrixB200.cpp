@@ -188,7 +188,8 @@ void FillCoef(HostGroup &g) {
     std::memset(coef, 0, sizeof(double) * 16);
     TPZMaterial *mat = g.material;
     if (auto *bc = dynamic_cast<TPZBndCondT<STATE> *>(mat)) {
-        if (bc->HasForcingFunctionBC()) Fatal("boundary conditions with a forcing function are not supported yet");
+        // (a forcing function replaces val2: FillForce tabulates the load-vector coefficient per integration point and the
+        //  kernel ignores coef[9..11]; the matrix part below stays constant)
         TPZMaterial *vol = bc->Material();
         const int type = bc->Type();
         const TPZFMatrix<STATE> &v1 = bc->Val1();
@@ -293,6 +294,57 @@ void FillForce(HostGroup &g) {
     g.has_forcing = false;
     g.meta.force = nullptr;
     const int ns = g.meta.nstate;
+    if (g.meta.kind == B200ASM_BC) {
+        // boundary data given by a function (TPZBndCondT::ForcingFunctionBC): evaluated on the host at data.x of every
+        // integration point, stored as the coefficient of phi_i * weight in ef (what the constant case keeps in coef[9..11])
+        auto *bc = dynamic_cast<TPZBndCondT<STATE> *>(g.material);
+        if (!bc || !bc->HasForcingFunctionBC()) return;
+        TPZMaterial *vol = bc->Material();
+        auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(vol);
+        auto *e2 = dynamic_cast<TPZElasticity2D *>(vol);
+        auto *e3 = dynamic_cast<TPZElasticity3D *>(vol);
+        const int type = bc->Type();
+        const bool ok = pois ? (type == 0 || type == 1) : (e2 ? (type == 0 || type == 1) : (e3 ? (type == 0 || type == 2 || (type >= 5 && type <= 8)) : false));
+        if (!ok) Fatal("boundary condition type " + std::to_string(type) + " with a forcing function is not supported");
+        const int fdim = g.meta.topology == B200ASM_LINE ? 1 : 2;
+        const int nq = g.meta.nqp;
+        g.force.assign((size_t)g.meta.nel * nq * ns, 0.0);
+        TPZManVector<REAL, 3> qsi(fdim), x(3);
+        for (int64_t e = 0; e < g.meta.nel; e++) {
+            TPZGeoEl *gel = g.elements[e]->Reference();
+            for (int q = 0; q < nq; q++) {
+                for (int d = 0; d < fdim; d++) qsi[d] = g.qpts[(size_t)q * fdim + d];
+                gel->X(qsi, x);
+                TPZManVector<STATE, 3> v2(e3 ? 3 : ns, 0.);
+                TPZFNMatrix<9, STATE> v1(bc->Val1());
+                bc->ForcingFunctionBC()(x, v2, v1);
+                double *out = &g.force[((size_t)e * nq + q) * ns];
+                if (pois) {  // Material/Poisson/TPZMatPoisson.cpp:79-100
+                    out[0] = type == 0 ? pois->BigNumber() * v2[0] : v2[0] * pois->ScaleFactor();
+                } else if (e2) {  // Material/Elasticity/TPZElasticity2D.cpp:256-283
+                    for (int a = 0; a < 2; a++) out[a] = type == 0 ? e2->BigNumber() * v2[a] : v2[a];
+                } else {  // Material/Elasticity/TPZElasticity3D.cpp:637-697,739-772
+                    const double big = 1.e12;
+                    if (type == 0) {
+                        for (int a = 0; a < 3; a++) out[a] = big * v2[a];
+                    } else if (type == 2) {  // val2loc = Val1 * function value
+                        const TPZFMatrix<STATE> &m = bc->Val1();
+                        for (int a = 0; a < 3; a++) {
+                            double t = 0.;
+                            for (int b = 0; b < 3; b++) t += m.GetVal(a, b) * v2[b];
+                            out[a] = t;
+                        }
+                    } else {
+                        const bool on[3] = {type == 5 || type == 8, type == 6, type == 7 || type == 8};
+                        for (int a = 0; a < 3; a++) out[a] = on[a] ? big * v2[a] : 0.;
+                    }
+                }
+            }
+        }
+        g.has_forcing = true;
+        g.meta.force = g.force.data();
+        return;
+    }
     const int dim = (g.meta.topology == B200ASM_HEX || g.meta.topology == B200ASM_TET || g.meta.topology == B200ASM_PRISM ||
                      g.meta.topology == B200ASM_PYRAMID) ? 3 : 2;
     if (dim != 3) {

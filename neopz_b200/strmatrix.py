@@ -120,6 +120,47 @@ class TPZBndCond:
         self.val2 = np.zeros(3)
         v2 = np.atleast_1d(np.asarray(val2, dtype=np.float64))
         self.val2[: len(v2)] = v2
+        self.forcing = None
+
+    def SetForcingFunctionBC(self, fn):
+        """TPZBndCondT::SetForcingFunctionBC: boundary data given by a function.  fn(x[npts][3]) -> val2[npts][nstate]; the host
+        evaluates it at every integration point of every boundary element (the device gets a table, like the domain forcing
+        functions).  Types with val2 in the load vector only: 0, 1 (not Elasticity3D, whose Neumann data then comes from the
+        face normal), 2 (Elasticity3D: val1 * fn), 5-8."""
+        self.forcing = fn
+
+    def HasForcingFunctionBC(self):
+        return self.forcing is not None
+
+    def rhs_coefficient(self, v2):
+        """v2[..., nstate] (values of the forcing function) -> coefficient of phi_i * weight in ef, per state variable:
+        TPZMatPoisson.cpp:79-100, TPZElasticity3D.cpp:637-697,739-772, TPZElasticity2D.cpp:256-283."""
+        ns = self.nstate
+        v2 = np.asarray(v2, dtype=np.float64)[..., :ns]
+        if isinstance(self.material, TPZMatPoisson):
+            if self.type == 0:
+                return self.material.fBigNumber * v2
+            if self.type == 1:
+                return v2 * self.material.fScale
+        elif isinstance(self.material, TPZElasticity2D):
+            if self.type == 0:
+                return self.material.fBigNumber * v2
+            if self.type == 1:
+                return v2
+        else:
+            big = 1.e12
+            if self.type == 0:
+                return big * v2
+            if self.type == 2:   # val2loc[i] = sum_j val1(i,j) * fn_j
+                out = np.zeros_like(v2)
+                for i in range(3):
+                    for j in range(3):
+                        out[..., i] += self.val1[i, j] * v2[..., j]
+                return out
+            if self.type in (5, 6, 7, 8):
+                on = {5: (1, 0, 0), 6: (0, 1, 0), 7: (0, 0, 1), 8: (1, 0, 1)}[self.type]
+                return big * v2 * np.array(on, dtype=np.float64)
+        raise ValueError("boundary condition type %d with a forcing function is not supported" % self.type)
 
     def coef(self):
         """(M, v) of  ek += M[a][b] phi_i phi_j w ,  ef += v[a] phi_i w  (include/b200asm.h)."""
@@ -188,6 +229,16 @@ def element_tables(topology, porder, key=0):
     return qpts, qw, phi, dphi
 
 
+def points_x(topology, qpts, coords):
+    """Physical coordinates of the integration points: x = sum_a N_a(qsi) x_a with the (multi)linear corner functions
+    (TPZGeoEl::X, what ComputeRequiredData stores in data.x).  coords: [nel][ncorner][3] -> [nel][nq][3]."""
+    geo, _ = capi.shape_tables(topology, 1, qpts)           # [nq][ncorner]
+    x = np.zeros((coords.shape[0], geo.shape[0], 3))
+    for a in range(geo.shape[1]):
+        x += geo[None, :, a, None] * coords[:, None, a, :]
+    return x
+
+
 # ---------------------------------------------------------------------------------------------
 # the struct matrix
 # ---------------------------------------------------------------------------------------------
@@ -237,8 +288,12 @@ class TPZStructMatrixB200:
             for key in np.unique(keys):
                 sel = slice(None) if mesh.porder < 3 else np.nonzero(keys == key)[0]
                 qpts, qw, phi, dphi = element_tables(b.topology, mesh.porder, key)
+                force = None
+                if mat.kind == capi.BC and mat.HasForcingFunctionBC():
+                    force = mat.rhs_coefficient(mat.forcing(points_x(b.topology, qpts, mesh.nodes[b.elnodes[sel]]).reshape(-1, 3)))
+                    force = force.reshape(len(b.elnodes[sel]), len(qw), mat.nstate)
                 gids.append(self.ctx.add_group(b.topology, mesh.porder, mat.kind, mat.nstate, b.elnodes[sel], b.dest[sel],
-                                               qpts, qw, phi, dphi, mat.coef()))
+                                               qpts, qw, phi, dphi, mat.coef(), force=force))
             self.groups_of_block.append(gids)
             self.group_of_block.append(gids[0])
         self._flattened = True

@@ -951,6 +951,10 @@ typedef struct {
     const double *qpts; /* [nq][dim] */
     const double *qw;   /* [nq] */
     int64_t ids[8];     /* global corner-node indices (orientation of the sides, p >= 3) */
+    const double *bcval2; /* boundary elements: optional [nq][3], val2 at every integration point when the boundary condition
+                             carries a forcing function (TPZBndCondT::ForcingFunctionBC evaluated at data.x by the caller; what
+                             TPZMatPoisson.cpp:62-64 / TPZElasticity3D.cpp:637-662 / TPZElasticity2D.cpp:244-246 put into v2);
+                             NULL: the constant mat[10..12] */
 } orc_elem_t;
 
 static int topo_dim(int topo) {
@@ -1181,13 +1185,20 @@ int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
             }
         weight *= fabs(detjac);
         int rc = 0;
+        double bmat[16];
+        const double *bm = e->mat;
+        if (e->bcval2) { /* boundary data from a function: val2 of this point */
+            memcpy(bmat, e->mat, sizeof(bmat));
+            for (int k = 0; k < 3; k++) bmat[10 + k] = e->bcval2[(size_t)q * 3 + k];
+            bm = bmat;
+        }
         switch (e->kind) {
             case ORC_POISSON: contribute_poisson(dim, n, phi, dphix, weight, e->mat, ek, ef); break;
             case ORC_ELAST2D: contribute_elast2d(n, phi, dphix, axes, weight, e->mat, ek, ef); break;
-            case ORC_ELAST2D_BC: rc = contribute_elast2d_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
+            case ORC_ELAST2D_BC: rc = contribute_elast2d_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
             case ORC_ELAST3D: contribute_elast(n, phi, dphix, weight, e->mat, ek, ef); break;
-            case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
-            case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, e->mat, ek, ef); break;
+            case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
+            case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
             default: rc = -1;
         }
         if (rc) return -2;

@@ -32,7 +32,8 @@ class Elem(C.Structure):
                 ("coords", C.c_double * 24), ("mat", C.c_double * 16),
                 ("nq", C.c_int32), ("pad", C.c_int32),
                 ("qpts", C.POINTER(C.c_double)), ("qw", C.POINTER(C.c_double)),
-                ("ids", C.c_int64 * 8)]
+                ("ids", C.c_int64 * 8),
+                ("bcval2", C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -102,17 +103,22 @@ def elast_constants(E, nu):
     return c
 
 
-def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None):
-    """coords: (nel, nnode, 3); ids: (nel, nnode) global corner-node indices (orientation, p >= 3).
-    Returns (ctypes array of Elem, keepalive)."""
+def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None, bcval2=None):
+    """coords: (nel, nnode, 3); ids: (nel, nnode) global corner-node indices (orientation, p >= 3); bcval2: (nel, nq, 3) val2 of
+    a boundary condition with a forcing function at every integration point.  Returns (ctypes array of Elem, keepalive)."""
     nel = coords.shape[0]
     nn = TOPO_NNODE[topo]
     qpts = np.ascontiguousarray(qpts, dtype=np.float64)
     qw = np.ascontiguousarray(qw, dtype=np.float64)
     arr = (Elem * nel)()
+    if bcval2 is not None:
+        bcval2 = np.ascontiguousarray(bcval2, dtype=np.float64)
+        assert bcval2.shape == (nel, len(qw), 3)
     for e in range(nel):
         el = arr[e]
         el.topo, el.p, el.kind, el.bctype = topo, p, kind, bctype
+        if bcval2 is not None:
+            el.bcval2 = _dp(bcval2[e])
         flat = np.zeros(24)
         flat[: nn * 3] = coords[e].reshape(-1)
         el.coords[:] = flat.tolist()
@@ -124,7 +130,7 @@ def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None):
         el.nq = len(qw)
         el.qpts = _dp(qpts)
         el.qw = _dp(qw)
-    return arr, (qpts, qw)
+    return arr, (qpts, qw, bcval2)
 
 
 def calcstiff(elem, ndof):

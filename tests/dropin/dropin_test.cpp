@@ -39,7 +39,8 @@ static double secs(clk::time_point a, clk::time_point b) { return std::chrono::d
 // tet (3-D): 0 hexahedra, 1 tetrahedra, 2 prisms (EPrismatic), 3 hexahedra + pyramids (EHexaPyrMixed)
 // prefine: every third domain element is p-refined by one order (TPZInterpolatedElement::PRefine): elements, faces and edges
 // of different order meet, the boundary elements follow in AdjustBoundaryElements
-static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, double dirichlet, int prefine = 0) {
+// bcfunc: the Dirichlet data on matid -1 come from a function of x (TPZBndCondT::SetForcingFunctionBC)
+static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, double dirichlet, int prefine = 0, int bcfunc = 0) {
     const int dim = phys >= 2 ? 2 : 3;
     TPZManVector<REAL, 3> minX(3, 0.), maxX(3, 1.);
     TPZManVector<int, 7> matids(dim == 3 ? 7 : 5, -1);
@@ -72,7 +73,13 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
         TPZManVector<STATE, 2> v2(2, 0.), v2n(2, 0.);
         v2[0] = dirichlet / 30.;
         v2n[0] = 0.25; v2n[1] = -0.5;
-        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        auto *bcd = m->CreateBC(m, -1, 0, v1, v2);
+        if (bcfunc)
+            bcd->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) {
+                u[0] = 0.01 * x[1] + 0.02 * x[0] * x[1];
+                u[1] = -0.03 * x[0];
+            });
+        cmesh->InsertMaterialObject(bcd);
         cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
     } else if (phys == 0) {
         auto *m = new TPZMatPoisson<STATE>(1, 3);
@@ -81,7 +88,12 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
         cmesh->InsertMaterialObject(m);
         TPZFNMatrix<1, STATE> v1(1, 1, 0.);
         TPZManVector<STATE, 1> v2(1, dirichlet), v2n(1, 0.75);
-        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        auto *bcd = m->CreateBC(m, -1, 0, v1, v2);
+        if (bcfunc)
+            bcd->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) {
+                u[0] = 0.3 + x[0] * x[1] - 0.5 * x[2] * x[2];
+            });
+        cmesh->InsertMaterialObject(bcd);
         cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
     } else {
         TPZManVector<STATE, 3> force(3, 0.);
@@ -92,7 +104,14 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
         TPZManVector<STATE, 3> v2(3, 0.), v2n(3, 0.);
         v2[0] = dirichlet / 30.;
         v2n[0] = 0.25; v2n[1] = -0.5; v2n[2] = 2.0;
-        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        auto *bcd = m->CreateBC(m, -1, 0, v1, v2);
+        if (bcfunc)
+            bcd->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) {
+                u[0] = 0.01 * x[1];
+                u[1] = -0.02 * x[0] * x[2];
+                u[2] = 0.005 + 0.01 * x[2];
+            });
+        cmesh->InsertMaterialObject(bcd);
         cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
     }
     cmesh->SetAllCreateFunctionsContinuous();
@@ -210,7 +229,7 @@ static double RelF(const std::vector<double> &x, const std::vector<double> &ref)
 
 int main(int argc, char **argv) {
     if (argc < 6) {
-        std::cerr << "usage: dropin_test n p phys(0|1|2|3) tet(0|1|2|3) symmetric(0|1) [solve(0|1)] [cpu_threads] [device_create] [equation_filter] [pin_host] [prefine]\n";
+        std::cerr << "usage: dropin_test n p phys(0|1|2|3) tet(0|1|2|3) symmetric(0|1) [solve(0|1)] [cpu_threads] [device_create] [equation_filter] [pin_host] [prefine] [bcfunc]\n";
         return 2;
     }
     const int n = atoi(argv[1]), p = atoi(argv[2]), phys = atoi(argv[3]), tet = atoi(argv[4]), symmetric = atoi(argv[5]);
@@ -221,7 +240,8 @@ int main(int argc, char **argv) {
     g_filter = argc > 9 ? atoi(argv[9]) : 0;
     g_pin = argc > 10 ? atoi(argv[10]) : 0;
     const int prefine = argc > 11 ? atoi(argv[11]) : 0;
-    TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3, prefine);
+    const int bcfunc = argc > 12 ? atoi(argv[12]) : 0;
+    TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3, prefine, bcfunc);
     Csr ref, refmt, gpu;
     double t1, t2, tm1, tm2, g1, g2;
     if (symmetric) {
@@ -271,7 +291,7 @@ int main(int argc, char **argv) {
     }
     const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
     std::cout.precision(6);
-    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"prefine\": " << prefine << ", \"cpu_first_assemble_s\": " << t1
+    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"prefine\": " << prefine << ", \"bcfunc\": " << bcfunc << ", \"cpu_first_assemble_s\": " << t1
               << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
               << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
               << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel

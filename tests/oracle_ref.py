@@ -61,7 +61,23 @@ def oracle_assemble(mesh, materials, symmetric, ia, ja):
         kind, bctype, mvec = _mat_vector(materials[b.matid])
         qpts, qw = _rule(b.topology, mesh.porder)
         coords = mesh.nodes[b.elnodes]
-        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw, ids=b.elnodes)
+        bcval2 = None
+        mat = materials[b.matid]
+        if getattr(mat, "forcing", None) is not None:
+            # boundary data from a function: val2 at every integration point (data.x from the product's geometry functions:
+            # the checker and the device share the points, tests/dropin checks them against the reference)
+            from neopz_b200 import strmatrix as sm
+            x = sm.points_x(b.topology, qpts, coords)
+            v2 = np.asarray(mat.forcing(x.reshape(-1, 3)), dtype=np.float64).reshape(len(coords), len(qw), -1)
+            if bctype == 2 and kind == orc.ELAST3D_BC:  # TPZElasticity3D.cpp:646-654: val2loc = val1 * fn
+                w = np.zeros((len(coords), len(qw), 3))
+                for i in range(3):
+                    for j in range(3):
+                        w[..., i] += mat.val1[i, j] * v2[..., j]
+                v2 = w
+            bcval2 = np.zeros((len(coords), len(qw), 3))
+            bcval2[..., : v2.shape[-1]] = v2
+        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw, ids=b.elnodes, bcval2=bcval2)
         elems.append(arr)
         keep.append(k)
         dest_parts.append(b.dest)
