@@ -689,19 +689,28 @@ __global__ void __launch_bounds__(128) assemble_plane_kernel(const BcParams p, i
             }
     }
     for (int i = lane; i < N; i += 32) {
-        double t = 0, gx = 0, gy = 0;  // sum_q w phi_i ; sum_q w du_x ; sum_q w du_y
+        // tx, ty = sum_q w phi_i f(x_q) (the source: a constant, or the host-evaluated forcing function); sum_q w du_x ; sum_q w du_y
+        double tx = 0, ty = 0, gx = 0, gy = 0;
         for (int q = 0; q < nq; q++) {
-            t += W[q] * __ldg(p.phi + (size_t)q * N + i);
+            const double wp = W[q] * __ldg(p.phi + (size_t)q * N + i);
+            if (p.force) {
+                const double *f = p.force + ((size_t)el * nq + q) * NS;
+                tx += wp * f[0];
+                if (NS == 2) ty += wp * f[1];
+            } else {
+                tx += wp * (NS == 1 ? p.coef[1] : p.coef[3]);
+                ty += wp * p.coef[4];
+            }
             gx += SW[q] * G[((size_t)q * N + i) * 2];
             gy += SW[q] * G[((size_t)q * N + i) * 2 + 1];
         }
         if (NS == 1) {
-            scatter_rhs(p.rhs, p.dest[el * N + i], p.coef[0] * p.coef[1] * t, p.atomic);
+            scatter_rhs(p.rhs, p.dest[el * N + i], p.coef[0] * tx, p.atomic);
         } else {
             // ef(2i) += w (fx phi - du_x sxx - du_y sxy) ; ef(2i+1) += w (fy phi - du_x sxy - du_y syy)
-            const double fx = p.coef[3], fy = p.coef[4], sxx = p.coef[5], sxy = p.coef[6], syy = p.coef[7];
-            scatter_rhs(p.rhs, p.dest[el * (N * 2) + i * 2], fx * t - gx * sxx - gy * sxy, p.atomic);
-            scatter_rhs(p.rhs, p.dest[el * (N * 2) + i * 2 + 1], fy * t - gx * sxy - gy * syy, p.atomic);
+            const double sxx = p.coef[5], sxy = p.coef[6], syy = p.coef[7];
+            scatter_rhs(p.rhs, p.dest[el * (N * 2) + i * 2], tx - gx * sxx - gy * sxy, p.atomic);
+            scatter_rhs(p.rhs, p.dest[el * (N * 2) + i * 2 + 1], ty - gx * sxy - gy * syy, p.atomic);
         }
     }
 }
@@ -1570,7 +1579,6 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: p <= 4");
         if (gi->kind == B200ASM_POISSON && g.ns != 1) return fail(ctx, B200ASM_EINVAL, "add_group: Poisson has nstate 1");
         if (gi->kind == B200ASM_ELASTICITY2D && g.ns != 2) return fail(ctx, B200ASM_EINVAL, "add_group: Elasticity2D has nstate 2");
-        if (gi->force) return fail(ctx, B200ASM_EINVAL, "add_group: forcing-function tables are not supported on plane elements");
     } else if (gi->kind != B200ASM_BC) {
         return fail(ctx, B200ASM_EINVAL, "add_group: face / line elements need kind BC (or POISSON / ELASTICITY2D as plane domain elements)");
     } else if (g.dim == 1 && gi->porder > 4) {
@@ -1724,7 +1732,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
     }
     std::vector<double> force;
-    if (gi->force && (volume || gi->kind == B200ASM_BC)) {
+    if (gi->force) {
         const size_t per = (size_t)g.nq * g.ns;
         force.resize((size_t)g.nel * per);
         for (int64_t e = 0; e < g.nel; e++) memcpy(&force[(size_t)e * per], gi->force + (size_t)order[e] * per, per * sizeof(double));

@@ -348,13 +348,25 @@ void FillForce(HostGroup &g) {
     const int dim = (g.meta.topology == B200ASM_HEX || g.meta.topology == B200ASM_TET || g.meta.topology == B200ASM_PRISM ||
                      g.meta.topology == B200ASM_PYRAMID) ? 3 : 2;
     if (dim != 3) {
-        // plane domain elements: constant source only (TPZMatPoisson without forcing function has none)
-        if (g.meta.kind != B200ASM_BC) {
-            auto *p2 = dynamic_cast<TPZMatPoisson<STATE> *>(g.material);
-            auto *e2 = dynamic_cast<TPZElasticity2D *>(g.material);
-            if ((p2 && p2->HasForcingFunction()) || (e2 && e2->HasForcingFunction()))
-                Fatal("forcing functions on plane (2-D) domain elements are not supported yet");
+        // plane domain elements: TPZMatPoisson(dim 2) source, TPZElasticity2D body force (TPZElasticity2D.cpp:120-127)
+        auto *p2 = dynamic_cast<TPZMatPoisson<STATE> *>(g.material);
+        auto *e2 = dynamic_cast<TPZElasticity2D *>(g.material);
+        if (!((p2 && p2->HasForcingFunction()) || (e2 && e2->HasForcingFunction()))) return;
+        const int nq = g.meta.nqp;
+        g.force.assign((size_t)g.meta.nel * nq * ns, 0.0);
+        TPZManVector<REAL, 3> qsi(2), x(3);
+        for (int64_t e = 0; e < g.meta.nel; e++) {
+            TPZGeoEl *gel = g.elements[e]->Reference();
+            for (int q = 0; q < nq; q++) {
+                for (int d = 0; d < 2; d++) qsi[d] = g.qpts[(size_t)q * 2 + d];
+                gel->X(qsi, x);
+                TPZManVector<STATE, 3> f(3, 0.);
+                if (p2) p2->ForcingFunction()(x, f); else e2->ForcingFunction()(x, f);
+                for (int k = 0; k < ns; k++) g.force[((size_t)e * nq + q) * ns + k] = f[k];
+            }
         }
+        g.has_forcing = true;
+        g.meta.force = g.force.data();
         return;
     }
     auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(g.material);

@@ -68,6 +68,8 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
         m->SetBodyForce(0.5, -1.0);
         m->SetPreStress(0.2, -0.1, 0.05, 0.);
         if (phys == 3) m->SetPlaneStress(); else m->SetPlaneStrain();
+        if (bcfunc >= 2)  // x-dependent body force: the host-evaluated forcing table of the plane kernel
+            m->SetForcingFunction([](const TPZVec<REAL> &x, TPZVec<STATE> &f) { f[0] = 0.5 + x[0] * x[1]; f[1] = -1.0 + 0.3 * x[1]; f[2] = 0.; }, 2);
         cmesh->InsertMaterialObject(m);
         TPZFNMatrix<4, STATE> v1(2, 2, 0.);
         TPZManVector<STATE, 2> v2(2, 0.), v2n(2, 0.);
