@@ -35,8 +35,14 @@ class TPZMatPoisson:
         self.fScale = float(s)
 
     def SetForcingFunction(self, value):
-        """Constant forcing function (the host evaluates callbacks; a constant needs no table)."""
-        self.force = float(value)
+        """Forcing function: a constant (needs no table) or a callable f(x[npts][3]) -> [npts] that the host evaluates at the
+        integration points of every element (TPZMatPoisson.cpp:24-27)."""
+        if callable(value):
+            self.forcing, self.force = value, 0.0
+        else:
+            self.forcing, self.force = None, float(value)
+
+    forcing = None
 
     def CreateBC(self, matid, bctype, val1, val2):
         return TPZBndCond(self, matid, bctype, val1, val2)
@@ -61,6 +67,11 @@ class TPZElasticity3D:
         self.C1 = self.fE / (2. + 2. * nu)
         self.C2 = self.fE * nu / (-1. + nu + 2. * nu * nu)
         self.C3 = self.fE * (nu - 1.) / (-1. + nu + 2. * nu * nu)
+        self.forcing = None
+
+    def SetForcingFunction(self, fn):
+        """Body force as a function of x: fn(x[npts][3]) -> [npts][3] (TPZElasticity3D.cpp:271-274), host-evaluated."""
+        self.forcing = fn
 
     def CreateBC(self, matid, bctype, val1, val2):
         return TPZBndCond(self, matid, bctype, val1, val2)
@@ -83,6 +94,11 @@ class TPZElasticity2D:
         self.fPlaneStress = bool(planestress)
         self.fPreStress = [0.0, 0.0, 0.0]   # XX, XY, YY
         self.fBigNumber = (10.0 ** 17) * 2 / 3
+        self.forcing = None
+
+    def SetForcingFunction(self, fn):
+        """Body force as a function of x: fn(x[npts][3]) -> [npts][2] (TPZElasticity2D.cpp:120-127), host-evaluated."""
+        self.forcing = fn
 
     def SetPlaneStress(self):
         self.fPlaneStress = True
@@ -292,6 +308,9 @@ class TPZStructMatrixB200:
                 if mat.kind == capi.BC and mat.HasForcingFunctionBC():
                     force = mat.rhs_coefficient(mat.forcing(points_x(b.topology, qpts, mesh.nodes[b.elnodes[sel]]).reshape(-1, 3)))
                     force = force.reshape(len(b.elnodes[sel]), len(qw), mat.nstate)
+                elif mat.kind != capi.BC and getattr(mat, "forcing", None) is not None:
+                    force = np.asarray(mat.forcing(points_x(b.topology, qpts, mesh.nodes[b.elnodes[sel]]).reshape(-1, 3)), dtype=np.float64)
+                    force = force.reshape(len(b.elnodes[sel]), len(qw), -1)[..., : mat.nstate]
                 gids.append(self.ctx.add_group(b.topology, mesh.porder, mat.kind, mat.nstate, b.elnodes[sel], b.dest[sel],
                                                qpts, qw, phi, dphi, mat.coef(), force=force))
             self.groups_of_block.append(gids)

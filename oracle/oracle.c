@@ -951,10 +951,12 @@ typedef struct {
     const double *qpts; /* [nq][dim] */
     const double *qw;   /* [nq] */
     int64_t ids[8];     /* global corner-node indices (orientation of the sides, p >= 3) */
-    const double *bcval2; /* boundary elements: optional [nq][3], val2 at every integration point when the boundary condition
-                             carries a forcing function (TPZBndCondT::ForcingFunctionBC evaluated at data.x by the caller; what
-                             TPZMatPoisson.cpp:62-64 / TPZElasticity3D.cpp:637-662 / TPZElasticity2D.cpp:244-246 put into v2);
-                             NULL: the constant mat[10..12] */
+    const double *bcval2; /* optional [nq][3]: values of the material's std::function at every integration point (evaluated at data.x
+                             by the caller).  Boundary kinds: val2 when the boundary condition carries a forcing function
+                             (TPZMatPoisson.cpp:62-64 / TPZElasticity3D.cpp:637-662 / TPZElasticity2D.cpp:244-246), replacing
+                             mat[10..12].  Domain kinds: the forcing function of the material - the source of TPZMatPoisson
+                             (TPZMatPoisson.cpp:24-27, replaces mat[1]), the body force of TPZElasticity3D (:271-274, mat[3..5]) and of
+                             TPZElasticity2D (:120-127, mat[3..4]).  NULL: the constants */
 } orc_elem_t;
 
 static int topo_dim(int topo) {
@@ -1187,16 +1189,20 @@ int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
         int rc = 0;
         double bmat[16];
         const double *bm = e->mat;
-        if (e->bcval2) { /* boundary data from a function: val2 of this point */
+        if (e->bcval2) { /* data from a function: the values of this point */
+            const double *v = e->bcval2 + (size_t)q * 3;
             memcpy(bmat, e->mat, sizeof(bmat));
-            for (int k = 0; k < 3; k++) bmat[10 + k] = e->bcval2[(size_t)q * 3 + k];
+            if (e->kind == ORC_POISSON) bmat[1] = v[0];
+            else if (e->kind == ORC_ELAST3D) { bmat[3] = v[0]; bmat[4] = v[1]; bmat[5] = v[2]; }
+            else if (e->kind == ORC_ELAST2D) { bmat[3] = v[0]; bmat[4] = v[1]; }
+            else for (int k = 0; k < 3; k++) bmat[10 + k] = v[k];
             bm = bmat;
         }
         switch (e->kind) {
-            case ORC_POISSON: contribute_poisson(dim, n, phi, dphix, weight, e->mat, ek, ef); break;
-            case ORC_ELAST2D: contribute_elast2d(n, phi, dphix, axes, weight, e->mat, ek, ef); break;
+            case ORC_POISSON: contribute_poisson(dim, n, phi, dphix, weight, bm, ek, ef); break;
+            case ORC_ELAST2D: contribute_elast2d(n, phi, dphix, axes, weight, bm, ek, ef); break;
             case ORC_ELAST2D_BC: rc = contribute_elast2d_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
-            case ORC_ELAST3D: contribute_elast(n, phi, dphix, weight, e->mat, ek, ef); break;
+            case ORC_ELAST3D: contribute_elast(n, phi, dphix, weight, bm, ek, ef); break;
             case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
             case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
             default: rc = -1;

@@ -69,7 +69,9 @@ def oracle_assemble(mesh, materials, symmetric, ia, ja):
             from neopz_b200 import strmatrix as sm
             x = sm.points_x(b.topology, qpts, coords)
             v2 = np.asarray(mat.forcing(x.reshape(-1, 3)), dtype=np.float64).reshape(len(coords), len(qw), -1)
-            if bctype == 2 and kind == orc.ELAST3D_BC:  # TPZElasticity3D.cpp:646-654: val2loc = val1 * fn
+            if kind in (orc.POISSON, orc.ELAST3D, orc.ELAST2D):
+                pass  # domain material: the values are the source / body force themselves
+            elif bctype == 2 and kind == orc.ELAST3D_BC:  # TPZElasticity3D.cpp:646-654: val2loc = val1 * fn
                 w = np.zeros((len(coords), len(qw), 3))
                 for i in range(3):
                     for j in range(3):

@@ -78,3 +78,53 @@ def test_dropin_strategy_matches_reference(case):
     assert r["relF_A"] <= 1e-12 and r["relF_A_nonpenalty_rows"] <= 1e-12 and r["relF_rhs"] <= 1e-12
     assert r["relF_residual_rhs"] <= 1e-12
     assert out.returncode == 0
+
+
+def f1(x):
+    return 1.0 + x[:, 0] * x[:, 1] - 0.5 * x[:, 2]
+
+
+def f3(x):
+    return np.stack([0.2 * x[:, 1], -0.1 * x[:, 0] * x[:, 2], -1.0 + 0.3 * x[:, 2] ** 2], axis=1)
+
+
+# every kernel family reads the host-evaluated forcing table its own way: (n, p, phys, tet, prisms, perturb, engine)
+FORCING_CASES = [(5, 2, 0, 0, False, 0.12, 1),   # DMMA one-warp kernel
+                 (3, 4, 0, 0, False, 0.12, 1),   # DMMA team kernel, Poisson
+                 (4, 2, 1, 0, False, 0.12, 1),   # DMMA team kernel, elasticity
+                 (4, 1, 1, 0, False, 0.12, 1),
+                 (4, 2, 1, 0, False, 0.0, 1),    # closed-form kernel for parallelepipeds
+                 (4, 2, 0, 0, False, 0.0, 1),
+                 (3, 2, 1, 1, False, 0.12, 1),   # closed-form kernel for tetrahedra
+                 (3, 1, 0, 1, False, 0.12, 1),
+                 (2, 3, 1, 1, False, 0.12, 1),   # register-tile kernel (tetrahedra of order 3)
+                 (3, 2, 1, 0, True, 0.12, 1),    # register-tile kernel (prisms)
+                 (4, 2, 1, 0, False, 0.12, 0),   # register-tile kernel (engine 0)
+                 (3, 2, 1, 0, False, 0.12, 2),   # generic runtime-size kernel
+                 (3, 3, 0, 0, False, 0.12, 2)]
+
+
+@pytest.mark.parametrize("n,p,phys,tet,prisms,perturb,engine", FORCING_CASES)
+def test_domain_forcing_functions_against_oracle(n, p, phys, tet, prisms, perturb, engine):
+    """Source of TPZMatPoisson / body force of TPZElasticity3D as functions of x (std::function in the reference, evaluated by
+    the host at the integration points): every kernel family against the oracle fed with the same point values."""
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=bool(tet), prisms=prisms, bc_matids=(-1, -1, -1, -1, -1, -2),
+                              perturb=perturb)
+    mats = materials_for(phys, neumann=True)
+    mats[1].SetForcingFunction(f3 if phys else f1)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, engine=engine)
+    ia, ja, a, rhs = strmat.CreateAssemble()
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+    assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
+
+
+def test_plane_body_force_function_against_oracle():
+    mesh = gridmesh.grid_mesh_2d(5, 3, 2, bc_matids=(-1, -1, -2, -1), perturb=0.1)
+    mat = sm.TPZElasticity2D(1, gu.E_MOD, gu.NU, *gu.E2D_FORCE)
+    mat.SetForcingFunction(lambda x: np.stack([0.5 + x[:, 0] * x[:, 1], -1.0 + 0.3 * x[:, 1]], axis=1))
+    mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((2, 2)), np.zeros(2)), -2: mat.CreateBC(-2, 1, np.zeros((2, 2)), gu.NEUMANN_ELAST2D)}
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True)
+    ia, ja, a, rhs = strmat.CreateAssemble()
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
