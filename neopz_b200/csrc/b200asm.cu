@@ -52,6 +52,7 @@ struct VolParams {
     const double *__restrict__ phi_pad;   // [nq][NP]
     const double *__restrict__ force;     // optional [nel][nq][NS]
     const double *__restrict__ aux;       // kernel-specific tables of the group (affine_simplex.cuh: Ghat, cphi, cd)
+    const double *__restrict__ aux2;      // sumfact_hex.cuh: the factor tables F1, F2 of the group's rule
     const int32_t *__restrict__ smap;     // [nbatch][TILE*TILE][EPB*NT]
     const int32_t *__restrict__ smapT;    // same, transposed entry (full storage only)
     double *__restrict__ a;
@@ -114,6 +115,7 @@ __device__ __forceinline__ void scatter_many(double *a, const int32_t (&pos)[N],
 #include "gram_mma_team.cuh"
 #include "affine_simplex.cuh"
 #include "affine_hex.cuh"
+#include "sumfact_hex.cuh"
 #include "pattern_device.cuh"
 #include "cg_device.cuh"
 
@@ -903,7 +905,8 @@ struct Group {
     double coef[16];
     int32_t *d_elnodes = nullptr, *d_dest = nullptr, *d_smap = nullptr, *d_smapT = nullptr;
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
-    double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr, *d_aux = nullptr;
+    double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr, *d_aux = nullptr, *d_aux2 = nullptr;
+    bool sumfact_ok = false;  // hexahedra p = 2, Poisson, the 27-point tensor rule: the sum-factorisation kernel applies
     size_t smap_len = 0;
     // element colouring (B200ASM_SCATTER_COLORED): elements are stored sorted by colour; seg = colour boundaries
     // ({0, nel} when not coloured); seg_smap = offset of every segment's scatter map (register-tile kernels)
@@ -1190,6 +1193,28 @@ void aff_tables(int nq, const double *qw, const double *phi, const double *dphi,
         }
     }
 }
+// sum-factorisation kernel for hexahedra p = 2, Poisson (sumfact_hex.cuh): one CTA of 64 threads per element
+constexpr int kSumfactVariant = 8;
+template <int MINB, int PRIVATE>
+cudaError_t launch_sumfact(const VolParams &p, int grid, size_t, cudaStream_t s) {
+    assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE><<<grid, sf::NTHREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+inline cudaError_t launch_sumfact_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
+                                       int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_sumfact_smap_kernel<<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <int MINB, int PRIVATE>
+cudaError_t prepare_sumfact(size_t, int *ctas_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE>, sf::NTHREADS, 0);
+}
+inline size_t sumfact_smem(int) { return 0; }
+template <int MINB, int PRIVATE = 0>
+MmaEntry make_sumfact_entry(int variant) {
+    return MmaEntry{variant, B200ASM_HEX, 2, 1, sf::SLOTS, sf::NTHREADS, 1, &sumfact_smem, &launch_sumfact<MINB, PRIVATE>, &launch_sumfact_smap,
+                    &prepare_sumfact<MINB, PRIVATE>};
+}
 // wpc = elements processed concurrently by one CTA; variant 0 = default (the first match wins), variant 7 = the DMMA
 // Gram kernels for tetrahedra that the closed-form kernels replaced
 const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP1ElastAff>(1),
@@ -1206,7 +1231,10 @@ const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP
                          make_team_entry<TetP2ElastTeamV3>(B200ASM_TET, 2, 3), make_team_entry<TetP2ElastTeamV4>(B200ASM_TET, 2, 4),
                          make_team_entry<TetP2ElastTeamV5>(B200ASM_TET, 2, 5), make_team_entry<TetP2ElastTeamV6>(B200ASM_TET, 2, 6),
                          make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2),
-                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2, 3), make_team_entry<HexP4PoissonTeamV1>(B200ASM_HEX, 4, 1)};
+                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2, 3), make_team_entry<HexP4PoissonTeamV1>(B200ASM_HEX, 4, 1),
+                         make_sumfact_entry<12>(kSumfactVariant), make_sumfact_entry<8>(kSumfactVariant + 1),
+                         make_sumfact_entry<12, 1>(kSumfactVariant + 2), make_sumfact_entry<8, 1>(kSumfactVariant + 3),
+                         make_sumfact_entry<16, 1>(kSumfactVariant + 4)};
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
@@ -1320,7 +1348,7 @@ int colour_elements(int64_t nel, int m, const int64_t *dest, int64_t neq_hint, s
 void free_group(Group &g) {
     cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
     cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
-    cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad); cudaFree(g.d_aux);
+    cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad); cudaFree(g.d_aux); cudaFree(g.d_aux2);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
     g = Group();
@@ -1570,10 +1598,20 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         for (int k = 0; k < kNumVol && g.uniform; k++)
             if (kVol[k].topology == g.topology && kVol[k].porder == g.porder && kVol[k].ns == g.ns) g.cfg = k;
         if (g.cfg < 0) g.generic = true;  // no specialised kernel: assemble_volume_generic_kernel (runtime sizes)
-        for (int k = 0; k < kNumMma && !g.generic; k++)
+        if (g.topology == B200ASM_HEX && g.porder == 2 && g.ns == 1 && g.uniform && g.nq == 27) {
+            // the rule is the 3 x 3 x 3 tensor rule with the point order q = q1 + 3 (q2 + 3 q3) (Integral/pzquad.cpp:268-284)
+            g.sumfact_ok = true;
+            for (int q = 0; q < 27 && g.sumfact_ok; q++)
+                g.sumfact_ok = gi->qpts[3 * q] == gi->qpts[3 * (q % 3)] && gi->qpts[3 * q + 1] == gi->qpts[3 * ((q / 3) % 3)] &&
+                               gi->qpts[3 * q + 2] == gi->qpts[3 * (q / 9)];
+        }
+        for (int k = 0; k < kNumMma && !g.generic; k++) {
+            const bool is_sumfact = kMma[k].variant >= kSumfactVariant && kMma[k].variant <= kSumfactVariant + 4;
+            if (is_sumfact && !g.sumfact_ok) continue;
             if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns &&
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
                 g.mma = k;
+        }
     } else if (g.plane) {
         if (gi->porder > 4)
             return fail(ctx, B200ASM_EINVAL, "add_group: plane domain elements: p <= 4");
@@ -1730,6 +1768,14 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         else if (g.ns == 1) aff_tables<TetP2PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else aff_tables<TetP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
+    }
+    std::vector<double> sf_aux(sf::AUX_LEN), sf_f3(4 * 9 * 3);
+    if (volume && g.sumfact_ok) {
+        const double x1d[3] = {gi->qpts[0], gi->qpts[3], gi->qpts[6]};
+        sf::build_tables(x1d, sf_aux.data(), sf_f3.data());
+        if ((rc = upload(ctx, &g.d_aux2, sf_aux.data(), sf_aux.size()))) return rc;
+        // (one table for every context: the values only depend on the reference's 3-point line rule)
+        CK(cudaMemcpyToSymbolAsync(c_sfF3, sf_f3.data(), sf_f3.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
     std::vector<double> force;
     if (gi->force) {
@@ -1992,7 +2038,7 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
         p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes + e0 * g.nn; p.dest = g.d_dest + e0 * g.m;
         p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng;
         p.force = g.d_force ? g.d_force + (size_t)e0 * g.nq * g.ns : nullptr;
-        p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad; p.aux = g.d_aux;
+        p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad; p.aux = g.d_aux; p.aux2 = g.d_aux2;
         p.a = ctx->d_a; p.rhs = ctx->d_rhs;
         memcpy(p.coef, g.coef, sizeof(p.coef));
         // persistent grid: SM count x resident CTAs per SM (registers / shared memory decide)

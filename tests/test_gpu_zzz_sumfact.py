@@ -1,0 +1,33 @@
+"""The sum-factorisation kernels for hexahedra of order 2 (neopz_b200/csrc/sumfact_hex.cuh; non-default tuning variants 8 = one
+barrier per (e,f), 11 = barrier-free) against the oracle: both storages, coloured scatter, load vector only, forcing table.
+(The same checks as tools/sumfact_check.py, whose B200 output is profiles/r01_sumfact_check.jsonl.)"""
+import numpy as np
+import pytest
+
+from neopz_b200 import gridmesh, strmatrix as sm
+from tests.oracle_ref import oracle_assemble
+from tests.test_gpu_parity import TOL, relF
+
+pytestmark = pytest.mark.gpu
+
+
+def _mats(forcing=None):
+    m = sm.TPZMatPoisson(1, 3)
+    m.SetScaleFactor(1.7)
+    m.SetForcingFunction(forcing if forcing else 1.0)
+    return {1: m, -1: m.CreateBC(-1, 0, [[0.0]], [0.0]), -2: m.CreateBC(-2, 1, [[0.0]], [0.75])}
+
+
+@pytest.mark.parametrize("variant", [8, 11])
+@pytest.mark.parametrize("n,symmetric,scatter,forcing", [(5, True, "atomic", False), (4, False, "atomic", False), (5, True, "colored", False),
+                                                         (7, True, "atomic", True)])
+def test_sumfact_variants_against_oracle(variant, n, symmetric, scatter, forcing):
+    mesh = gridmesh.grid_mesh(n, 2, 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
+    mats = _mats((lambda x: 1.0 + x[:, 0] * x[:, 1] - 0.5 * x[:, 2]) if forcing else None)
+    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, variant=variant, scatter=scatter)
+    ia, ja, a, rhs = strmat.CreateAssemble()
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+    assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+    a2, rhs2 = strmat.Assemble()
+    assert relF(a2, a_ref) <= TOL and relF(rhs2, rhs_ref) <= TOL
+    assert relF(strmat.AssembleRhs(), rhs_ref) <= TOL
