@@ -1195,9 +1195,9 @@ void aff_tables(int nq, const double *qw, const double *phi, const double *dphi,
 }
 // sum-factorisation kernel for hexahedra p = 2, Poisson (sumfact_hex.cuh): one CTA of 64 threads per element
 constexpr int kSumfactVariant = 8;
-template <int MINB, int PRIVATE>
+template <int MINB, int PRIVATE, int PREFETCH>
 cudaError_t launch_sumfact(const VolParams &p, int grid, size_t, cudaStream_t s) {
-    assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE><<<grid, sf::NTHREADS, 0, s>>>(p);
+    assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE, PREFETCH><<<grid, sf::NTHREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 inline cudaError_t launch_sumfact_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
@@ -1205,15 +1205,16 @@ inline cudaError_t launch_sumfact_smap(int64_t nel, const int32_t *dest, const i
     build_sumfact_smap_kernel<<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
     return cudaGetLastError();
 }
-template <int MINB, int PRIVATE>
+template <int MINB, int PRIVATE, int PREFETCH>
 cudaError_t prepare_sumfact(size_t, int *ctas_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE>, sf::NTHREADS, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE, PREFETCH>,
+                                                         sf::NTHREADS, 0);
 }
 inline size_t sumfact_smem(int) { return 0; }
-template <int MINB, int PRIVATE = 0>
+template <int MINB, int PRIVATE = 0, int PREFETCH = 0>
 MmaEntry make_sumfact_entry(int variant) {
-    return MmaEntry{variant, B200ASM_HEX, 2, 1, sf::SLOTS, sf::NTHREADS, 1, &sumfact_smem, &launch_sumfact<MINB, PRIVATE>, &launch_sumfact_smap,
-                    &prepare_sumfact<MINB, PRIVATE>};
+    return MmaEntry{variant, B200ASM_HEX, 2, 1, sf::SLOTS, sf::NTHREADS, 1, &sumfact_smem, &launch_sumfact<MINB, PRIVATE, PREFETCH>,
+                    &launch_sumfact_smap, &prepare_sumfact<MINB, PRIVATE, PREFETCH>};
 }
 // wpc = elements processed concurrently by one CTA; variant 0 = default (the first match wins), variant 7 = the DMMA
 // Gram kernels for tetrahedra that the closed-form kernels replaced
@@ -1234,7 +1235,11 @@ const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP
                          make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2, 3), make_team_entry<HexP4PoissonTeamV1>(B200ASM_HEX, 4, 1),
                          make_sumfact_entry<12>(kSumfactVariant), make_sumfact_entry<8>(kSumfactVariant + 1),
                          make_sumfact_entry<12, 1>(kSumfactVariant + 2), make_sumfact_entry<8, 1>(kSumfactVariant + 3),
-                         make_sumfact_entry<16, 1>(kSumfactVariant + 4)};
+                         make_sumfact_entry<16, 1>(kSumfactVariant + 4),
+                         // (13-15: with the coordinate / position prefetch; written after the GPU budget of round 1 was spent:
+                         //  same arithmetic, CPU-emulated, NOT yet run on a GPU - to be measured first thing in round 2)
+                         make_sumfact_entry<8, 0, 1>(kSumfactVariant + 5), make_sumfact_entry<12, 0, 1>(kSumfactVariant + 6),
+                         make_sumfact_entry<8, 1, 1>(kSumfactVariant + 7)};
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
@@ -1606,7 +1611,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
                                gi->qpts[3 * q + 2] == gi->qpts[3 * (q / 9)];
         }
         for (int k = 0; k < kNumMma && !g.generic; k++) {
-            const bool is_sumfact = kMma[k].variant >= kSumfactVariant && kMma[k].variant <= kSumfactVariant + 4;
+            const bool is_sumfact = kMma[k].variant >= kSumfactVariant && kMma[k].variant <= kSumfactVariant + 7;
             if (is_sumfact && !g.sumfact_ok) continue;
             if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns &&
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))

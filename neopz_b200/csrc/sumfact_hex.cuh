@@ -185,7 +185,10 @@ SF_HD bool entry_of(int t, int k, int &i, int &j) {
 #ifdef __CUDACC__
 
 // PRIVATE = 0: stage 1 shared through smem, one barrier per (e,f); PRIVATE = 1: barrier-free (stages_private)
-template <int MINB, int PRIVATE = 0>
+// PREFETCH = 1: the corner coordinates of the CTA's next element are loaded (and the node ids of the one after) while the current
+// element is computed, and the scatter positions are loaded before the factor stages instead of after them: the dependent global
+// loads (ids -> coordinates, ~2 DRAM latencies) and the position loads leave the critical path of every element
+template <int MINB, int PRIVATE = 0, int PREFETCH = 0>
 __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_poisson_kernel(const VolParams p) {
     __shared__ double Xs[24];
     __shared__ double Msm[6 * 27];
@@ -202,13 +205,30 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
             F1[v][k] = __ldg(p.aux2 + sf::AUX_F1 + (v * 6 + p1) * 3 + k);
             F2[v][k] = __ldg(p.aux2 + sf::AUX_F2 + (v * 9 + p2) * 3 + k);
         }
-    for (int64_t el = blockIdx.x; el < p.nel; el += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    double cnext = 0.0;
+    int32_t node_next = 0;
+    if (PREFETCH && t < 24 && (int64_t)blockIdx.x < p.nel) {
+        cnext = p.xyz[(int64_t)p.elnodes[(int64_t)blockIdx.x * 8 + t / 3] * 3 + t % 3];
+        if (blockIdx.x + stride < p.nel) node_next = p.elnodes[(blockIdx.x + stride) * 8 + t / 3];
+    }
+    for (int64_t el = blockIdx.x; el < p.nel; el += stride) {
         __syncthreads();  // the previous element no longer reads Xs / Msm / Wd / S1
         if (!p.rhs_only) {
             const char *base = (const char *)(p.smap + (size_t)el * sf::SLOTS);
             if (t < (sf::SLOTS * 4 + 127) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + t * 128));
         }
-        if (t < 24) Xs[t] = p.xyz[(int64_t)p.elnodes[el * 8 + t / 3] * 3 + t % 3];
+        if (t < 24) {
+            if (PREFETCH) {
+                Xs[t] = cnext;
+                if (el + stride < p.nel) {
+                    cnext = p.xyz[(int64_t)node_next * 3 + t % 3];
+                    if (el + 2 * stride < p.nel) node_next = p.elnodes[(el + 2 * stride) * 8 + t / 3];
+                }
+            } else {
+                Xs[t] = p.xyz[(int64_t)p.elnodes[el * 8 + t / 3] * 3 + t % 3];
+            }
+        }
         __syncthreads();
         if (t < 27) sf::geometry(t, Xs, p.dng, p.qw, p.coef[0], Msm, Wd);
         __syncthreads();
@@ -224,6 +244,12 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
             scatter_rhs(p.rhs, p.dest[el * 27 + i], f, p.atomic);
         }
         if (p.rhs_only) continue;
+        const int32_t *sm = p.smap + (size_t)el * sf::SLOTS + t;
+        int32_t pos[9];
+        if (PREFETCH) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) pos[k] = __ldcs(sm + k * sf::NTHREADS);
+        }
         double acc[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) acc[k] = 0.0;
@@ -239,10 +265,10 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
             }
         }
         // ---- scatter-add: entry k = (i3, j3) of work item t
-        const int32_t *sm = p.smap + (size_t)el * sf::SLOTS + t;
-        int32_t pos[9];
+        if (!PREFETCH) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) pos[k] = __ldcs(sm + k * sf::NTHREADS);
+            for (int k = 0; k < 9; k++) pos[k] = __ldcs(sm + k * sf::NTHREADS);
+        }
         scatter_many<9>(p.a, pos, acc, p.atomic);
         if (p.smapT) {
             const int32_t *smT = p.smapT + (size_t)el * sf::SLOTS + t;
