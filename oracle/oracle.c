@@ -876,6 +876,34 @@ static void gradx_of(int topo, const double *coords, const double *pt, double gr
             for (int k = 0; k < dim; k++) gradx[j][k] += coords[3 * i + j] * d[k][i];
 }
 
+/* data.x of a boundary face: TPZGeoEl::X (Mesh/pzinterpolationspace.cpp:278) = sum_j phi_j(qsi) x_j with the corner functions
+ * TShape of the face, accumulated from 0 in node order (Geom/pzgeoquad.h:127-141 with Topology/tpzquadrilateral.cpp:153-160;
+ * Geom/pzgeotriangle.h with Topology/tpztriangle.cpp:25-29).  coords[node][3] -> x[3].  Quadrilaterals / triangles only. */
+int orc_point_x(int topo, const double *coords, const double *pt, double *x) {
+    double phi[4];
+    int nn;
+    if (topo == ORC_QUAD) {
+        const double qsi = pt[0], eta = pt[1];
+        phi[0] = 0.25 * (1. - qsi) * (1. - eta);
+        phi[1] = 0.25 * (1. + qsi) * (1. - eta);
+        phi[2] = 0.25 * (1. + qsi) * (1. + eta);
+        phi[3] = 0.25 * (1. - qsi) * (1. + eta);
+        nn = 4;
+    } else if (topo == ORC_TRI) {
+        phi[0] = 1.0 - pt[0] - pt[1];
+        phi[1] = pt[0];
+        phi[2] = pt[1];
+        nn = 3;
+    } else {
+        return -1;
+    }
+    for (int i = 0; i < 3; i++) {
+        x[i] = 0.0;
+        for (int j = 0; j < nn; j++) x[i] += phi[j] * coords[3 * j + i];
+    }
+    return 0;
+}
+
 /* Mesh/pzgeoel.cpp:1167-1356: 3-D branch :1296-1344, 2-D Gram-Schmidt branch :1228-1295.
  * Returns detjac (signed), jacinv[dim][dim]. */
 static double jacobian_of(int dim, double gradx[3][3], double jacinv[3][3], double axes[3][3]) {

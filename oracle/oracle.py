@@ -52,6 +52,7 @@ def lib():
         _lib.orc_shape.argtypes = [C.c_int, C.c_int, dp, dp, dp]
         _lib.orc_shape_ids.argtypes = [C.c_int, C.c_int, ip, dp, dp, dp]
         _lib.orc_calcstiff.argtypes = [C.POINTER(Elem), dp, dp]
+        _lib.orc_point_x.argtypes = [C.c_int, dp, dp, dp]
         _lib.orc_elast_contribute_point.argtypes = [C.c_int, dp, dp, C.c_double, dp, dp, dp]
         _lib.orc_elast_constants.argtypes = [C.c_double, C.c_double, dp]
         _lib.orc_pattern.argtypes = [C.c_int, C.c_int64, ip, ip, C.c_int64, ip, ip, ip, ip]
@@ -95,6 +96,15 @@ def shape(topo, p, pt, ids=None):
         n = lib().orc_shape_ids(topo, p, _ip(ids), _dp(pt), _dp(phi), _dp(dphi))
     assert n > 0
     return phi[:n].copy(), dphi[: dim * n].reshape(dim, n).copy()
+
+
+def point_x(topo, coords, pt):
+    """data.x of a boundary face (quadrilateral / triangle) at a master-element point, in the reference's arithmetic."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    pt = np.ascontiguousarray(pt, dtype=np.float64)
+    x = np.zeros(3)
+    assert lib().orc_point_x(topo, _dp(coords), _dp(pt), _dp(x)) == 0
+    return x
 
 
 def elast_constants(E, nu):

@@ -93,6 +93,8 @@ struct Case {
     int bctype = 0;  // type of the BC on matid -1 (0 Dirichlet, 1 Neumann on zmax only -> matid -2)
     int dim = 3;       // 2: plane mesh (TPZGenGrid2D): phys 0 = TPZMatPoisson(dim 2), phys 2 / 3 = TPZElasticity2D plane
                        // strain / plane stress; boundary = line elements, matid -2 on the top side when bctype >= 1
+    int bcfunc = 0;    // 1: the Dirichlet data on matid -1 (and the data of matid -2 when bctype == 2) come from a function of x
+                       // (TPZBndCondT::SetForcingFunctionBC); the functions are those of tests/golden_util.py
     int scramble = 0;  // != 0: node indices permuted by a seeded Fisher-Yates shuffle, so that the side
                        // orientations (transform ids, Shape/pzgenericshape.cpp:57-68) differ between elements
 };
@@ -176,10 +178,16 @@ static TPZCompMesh *build_mesh(const Case &c) {
         cmesh->InsertMaterialObject(m);
         TPZFNMatrix<1, STATE> v1(1, 1, 0.);
         TPZManVector<STATE, 1> v2(1, 0.);
-        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        auto *bcd = m->CreateBC(m, -1, 0, v1, v2);
+        if (c.bcfunc)
+            bcd->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) { u[0] = 0.3 + x[0] * x[1] - 0.5 * x[2] * x[2]; });
+        cmesh->InsertMaterialObject(bcd);
         if (c.bctype >= 1) {
             TPZManVector<STATE, 1> v2n(1, 0.75);
-            cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+            auto *bcn = m->CreateBC(m, -2, 1, v1, v2n);
+            if (c.bcfunc)
+                bcn->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) { u[0] = 0.75 + 2.0 * x[0] - x[1] * x[1]; });
+            cmesh->InsertMaterialObject(bcn);
         }
     } else {
         TPZManVector<STATE, 3> force(3, 0.);
@@ -188,7 +196,14 @@ static TPZCompMesh *build_mesh(const Case &c) {
         cmesh->InsertMaterialObject(m);
         TPZFNMatrix<9, STATE> v1(3, 3, 0.);
         TPZManVector<STATE, 3> v2(3, 0.);
-        cmesh->InsertMaterialObject(m->CreateBC(m, -1, 0, v1, v2));
+        auto elastfunc = [](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) {
+            u[0] = 0.01 * x[1];
+            u[1] = -0.02 * x[0] * x[2];
+            u[2] = 0.005 + 0.01 * x[2];
+        };
+        auto *bcd = m->CreateBC(m, -1, 0, v1, v2);
+        if (c.bcfunc) bcd->SetForcingFunctionBC(elastfunc);
+        cmesh->InsertMaterialObject(bcd);
         if (c.bctype == 1) {
             TPZManVector<STATE, 3> v2n(3, 0.);
             v2n[0] = 0.25; v2n[1] = -0.5; v2n[2] = 2.0;
@@ -199,7 +214,9 @@ static TPZCompMesh *build_mesh(const Case &c) {
             v1m(0, 0) = 4.0; v1m(0, 1) = 0.5; v1m(1, 0) = 0.5; v1m(1, 1) = 3.0; v1m(1, 2) = 0.25; v1m(2, 1) = 0.25; v1m(2, 2) = 5.0;
             TPZManVector<STATE, 3> v2m(3, 0.);
             v2m[0] = 0.3; v2m[1] = -0.2; v2m[2] = 0.7;
-            cmesh->InsertMaterialObject(m->CreateBC(m, -2, c.bctype, v1m, v2m));
+            auto *bcm = m->CreateBC(m, -2, c.bctype, v1m, v2m);
+            if (c.bcfunc && c.bctype == 2) bcm->SetForcingFunctionBC(elastfunc);  // val2loc = val1 * function (TPZElasticity3D.cpp:646-654)
+            cmesh->InsertMaterialObject(bcm);
         }
     }
     cmesh->SetAllCreateFunctionsContinuous();
@@ -453,7 +470,7 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     std::ofstream meta(dir + "/meta.json");
     meta.precision(17);
     meta << "{\"n\": " << c.n << ", \"p\": " << c.p << ", \"phys\": " << c.phys << ", \"tet\": " << c.tet
-         << ", \"perturb\": " << c.perturb << ", \"bctype\": " << c.bctype << ", \"dim\": " << c.dim << ", \"scramble\": " << c.scramble << ", \"neq\": " << neq
+         << ", \"perturb\": " << c.perturb << ", \"bctype\": " << c.bctype << ", \"dim\": " << c.dim << ", \"scramble\": " << c.scramble << ", \"bcfunc\": " << c.bcfunc << ", \"neq\": " << neq
          << ", \"ncel\": " << ncel << ", \"nnodes\": " << nn;
     TPZMaterial *mat = cmesh->FindMaterial(1);
     meta << ", \"bignumber\": " << mat->BigNumber();
@@ -518,6 +535,7 @@ int main(int argc, char **argv) {
         c.perturb = atof(argv[7]); c.bctype = atoi(argv[8]);
         if (argc >= 11) c.scramble = atoi(argv[10]);
         if (argc >= 12) c.dim = atoi(argv[11]);
+        if (argc >= 13) c.bcfunc = atoi(argv[12]);
         return cmd_dump(dir, c, atoi(argv[9]));
     }
     if (cmd == "time" && argc >= 8) {

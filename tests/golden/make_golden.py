@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "refdriver")
 
-# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed[, dim]])   tet: 0 hex / quad, 1 tet / tri, 2 prism, 3 hex + pyramid
+# name: (n, p, phys, tet, perturb, bctype, with_elmats[, scramble seed[, dim[, bcfunc]]])   bcfunc 1: boundary data from functions of x
+#   tet: 0 hex / quad, 1 tet / tri, 2 prism, 3 hex + pyramid
 # dim 2: plane meshes (TPZGenGrid2D); phys 0 = TPZMatPoisson(dim 2), 2 / 3 = TPZElasticity2D plane strain / plane stress
 # scramble != 0: node indices shuffled so that the side orientations differ from element to element (p >= 3)
 CASES = {
@@ -69,6 +70,10 @@ CASES = {
     "tri_p3_elast2d_n3_pert_scr": (3, 3, 2, 1, 0.15, 1, 1, 9, 2),
     "tri_p4_poisson2d_n3_pert_scr": (3, 4, 0, 1, 0.15, 1, 1, 13, 2),
     "tri_p4_elast2d_stress_n2_bc3": (2, 4, 3, 1, 0.15, 3, 1, 0, 2),
+    # boundary data from functions (TPZBndCondT::SetForcingFunctionBC): Dirichlet + Neumann (Poisson), Dirichlet + mixed (Elasticity3D)
+    "hex_p2_poisson_n2_bcfunc": (2, 2, 0, 0, 0.15, 1, 1, 0, 3, 1),
+    "tet_p2_elast_n2_bcfunc": (2, 2, 1, 1, 0.15, 2, 1, 0, 3, 1),
+    "prism_p2_poisson_n2_bcfunc": (2, 2, 0, 2, 0.15, 1, 1, 0, 3, 1),
 }
 
 
@@ -82,9 +87,10 @@ def main():
         n, p, phys, tet, pert, bctype, elm = case[:7]
         scr = case[7] if len(case) > 7 else 0
         dim = case[8] if len(case) > 8 else 3
+        bcfunc = case[9] if len(case) > 9 else 0
         with tempfile.TemporaryDirectory() as d:
             subprocess.check_call([DRIVER, "dump", d, str(n), str(p), str(phys), str(tet), repr(pert),
-                                   str(bctype), str(elm), str(scr), str(dim)], stdout=subprocess.DEVNULL)
+                                   str(bctype), str(elm), str(scr), str(dim), str(bcfunc)], stdout=subprocess.DEVNULL)
             arrays = {}
             for f in sorted(os.listdir(d)):
                 if f.endswith(".npy"):

@@ -13,7 +13,10 @@ ALL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
 WEDGE_CASES = [c for c in ALL_CASES if c.startswith("prism") or c.startswith("hexpyr")]
 # tetrahedra / triangles of order 3, 4: tests/test_gpu_simplex_p34.py
 SIMPLEX34_CASES = [c for c in ALL_CASES if c.startswith(("tet_p3", "tet_p4", "tri_p3", "tri_p4"))]
-CORE_CASES = [c for c in ALL_CASES if c not in WEDGE_CASES and c not in SIMPLEX34_CASES]
+# boundary data from functions: tests/test_gpu_zz_bcfunction.py
+BCFUNC_CASES = [c for c in ALL_CASES if c.endswith("_bcfunc")]
+WEDGE_CASES = [c for c in WEDGE_CASES if c not in BCFUNC_CASES]
+CORE_CASES = [c for c in ALL_CASES if c not in WEDGE_CASES and c not in SIMPLEX34_CASES and c not in BCFUNC_CASES]
 
 # material data of oracle/refdriver.cpp's recipe
 E_MOD, NU = 1000.0, 0.3
@@ -79,6 +82,44 @@ def material_vector(g, topo, matid):
     return orc.ELAST3D_BC, bctype, mat
 
 
+# the boundary functions of oracle/refdriver.cpp (bcfunc = 1), in the same arithmetic order
+def bc_function_poisson_dirichlet(x):
+    return 0.3 + x[0] * x[1] - 0.5 * x[2] * x[2]
+
+
+def bc_function_poisson_neumann(x):
+    return 0.75 + 2.0 * x[0] - x[1] * x[1]
+
+
+def bc_function_elast(x):
+    return (0.01 * x[1], -0.02 * x[0] * x[2], 0.005 + 0.01 * x[2])
+
+
+def bc_point_values(g, topo, matid, bctype, coords, qpts):
+    """[1][nq][3] val2 at the integration points of one boundary element of a bcfunc fixture (None: constant data)."""
+    m = g["meta"]
+    if not m.get("bcfunc") or matid == 1:
+        return None
+    if m["phys"] == 1 and matid == -2 and bctype != 2:
+        return None
+    out = np.zeros((1, len(qpts), 3))
+    for q, pt in enumerate(qpts):
+        x = orc.point_x(topo, coords, pt)   # data.x as the reference computes it
+        if m["phys"] == 0:
+            out[0, q, 0] = bc_function_poisson_dirichlet(x) if matid == -1 else bc_function_poisson_neumann(x)
+        else:
+            u = bc_function_elast(x)
+            if matid == -2:  # mixed condition: val2loc[i] = 0 + sum_j val1(i,j) * u[j]   (TPZElasticity3D.cpp:646-654)
+                for i in range(3):
+                    acc = 0.0
+                    for j in range(3):
+                        acc += BC_VAL1[i, j] * u[j]
+                    out[0, q, i] = acc
+            else:
+                out[0, q, :] = u
+    return out
+
+
 def oracle_elements(g):
     """One ctypes Elem per computational element, in element order; returns (list_of_arrays, keepalive)."""
     p = g["meta"]["p"]
@@ -91,8 +132,9 @@ def oracle_elements(g):
         coords = g["nodes"][nodes][None, :, :]
         kind, bctype, mat = material_vector(g, topo, int(g["el_matid"][e]))
         tag = TAGS[topo]
+        bcv = bc_point_values(g, topo, int(g["el_matid"][e]), bctype, coords[0], g[f"rule_{tag}_pts"])
         arr, k = orc.make_elems(topo, p, kind, bctype, coords, mat, g[f"rule_{tag}_pts"], g[f"rule_{tag}_w"],
-                                ids=nodes[None, :])
+                                ids=nodes[None, :], bcval2=bcv)
         arrays.append(arr)
         keep.append(k)
     return arrays, keep

@@ -61,6 +61,16 @@ def fixture_setup(g):
     mats = materials_for(m["phys"], neumann=bct >= 1)
     if m["phys"] == 1 and bct >= 2:  # the other TPZElasticity3D::ContributeBC types on the zmax face
         mats[-2] = mats[1].CreateBC(-2, bct, gu.BC_VAL1, gu.BC_VAL2)
+    if m.get("bcfunc"):  # boundary data from the functions of oracle/refdriver.cpp (vectorised over the points)
+        if m["phys"] == 0:
+            mats[-1].SetForcingFunctionBC(lambda x: (0.3 + x[:, 0] * x[:, 1] - 0.5 * x[:, 2] * x[:, 2])[:, None])
+            if -2 in mats:
+                mats[-2].SetForcingFunctionBC(lambda x: (0.75 + 2.0 * x[:, 0] - x[:, 1] * x[:, 1])[:, None])
+        else:
+            f = lambda x: np.stack([0.01 * x[:, 1], -0.02 * x[:, 0] * x[:, 2], 0.005 + 0.01 * x[:, 2]], axis=1)  # noqa: E731
+            mats[-1].SetForcingFunctionBC(f)
+            if bct == 2:
+                mats[-2].SetForcingFunctionBC(f)
     return mesh, mats
 
 
