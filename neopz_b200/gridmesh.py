@@ -438,6 +438,83 @@ def mesh_from_elements(nodes, el_type, el_matid, el_nodes, porder, nstate):
     return flatten(np.asarray(nodes, dtype=np.float64), out, porder, nstate)
 
 
+def hexpyr_elements(n, bc_matids=(-1, -1, -1, -1, -1, -1), vol_matid=1, perturb=0.0):
+    """Nodes and elements (in computational-element order) of CreateGeoMeshOnGrid(..., MMeshType::EHexaPyrMixed, createBoundEls=true):
+    every other cell ((iel + iel/nx + iel/(nx ny)) even) is split into six pyramids around a new centre node by the refinement
+    pattern of Pre/TPZGenGrid3D.cpp:181-228; the sons and, later, the boundary quadrilaterals take the element slots the deleted
+    hexahedra freed (TPZAdmChunkVector::AllocateNewElement pops the free stack first), so the element types interleave.
+    Returns (nodes, el_type, el_matid, el_nodes[nel][8] padded with -1) ready for mesh_from_elements."""
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    sy, sz = nx + 1, (nx + 1) * (ny + 1)
+    grid = grid_nodes(n, perturb=0.0)
+    ncell = nx * ny * nz
+    cells = []
+    for iz in range(nz):
+        for iy in range(ny):
+            for ix in range(nx):
+                f = iz * sz + iy * sy + ix
+                cells.append([f, f + 1, f + 1 + sy, f + sy, f + sz, f + 1 + sz, f + 1 + sy + sz, f + sy + sz])
+    slots = {i: (capi.HEX, vol_matid, c) for i, c in enumerate(cells)}
+    free, nxt = [], ncell
+    centres = []
+    sons = ((0, 1, 2, 3), (0, 4, 5, 1), (1, 5, 6, 2), (2, 6, 7, 3), (3, 7, 4, 0), (7, 6, 5, 4))
+
+    def allocate():
+        nonlocal nxt
+        if free:
+            return free.pop()
+        nxt += 1
+        return nxt - 1
+    for iel in range(ncell):
+        if (iel + iel // nx + iel // (nx * ny)) % 2 == 1:
+            continue
+        c = cells[iel]
+        centre = len(grid) + len(centres)
+        x = np.zeros(3)
+        for a in range(8):   # X(0,0,0) of the trilinear map: corner functions 1/8, accumulated in node order
+            x = x + 0.125 * grid[c[a]]
+        centres.append(x)
+        for s in sons:
+            slots[allocate()] = (capi.PYRAMID, vol_matid, [c[s[0]], c[s[1]], c[s[2]], c[s[3]], centre])
+        del slots[iel]
+        free.append(iel)
+    m_zmin, m_xmin, m_ymin, m_xmax, m_ymax, m_zmax = bc_matids
+    for izf, matid in ((0, m_zmin), (nz, m_zmax)):
+        for iy in range(ny):
+            for ix in range(nx):
+                f = izf * sz + iy * sy + ix
+                slots[allocate()] = (capi.QUAD, matid, [f, f + 1, f + sy + 1, f + sy])
+    for iz in range(nz):
+        for iyf, matid in ((0, m_ymin), (ny, m_ymax)):
+            for ix in range(nx):
+                f = iz * sz + iyf * sy + ix
+                slots[allocate()] = (capi.QUAD, matid, [f, f + 1, f + sz + 1, f + sz])
+    for iz in range(nz):
+        for iy in range(ny):
+            for ixf, matid in ((0, m_xmin), (nx, m_xmax)):
+                f = iz * sz + iy * sy + ixf
+                slots[allocate()] = (capi.QUAD, matid, [f, f + sy, f + sz + sy, f + sz])
+    nodes = np.concatenate([grid, np.array(centres).reshape(-1, 3)], axis=0)
+    if perturb != 0.0:  # the deterministic perturbation of oracle/refdriver.cpp, by node index (centre nodes included)
+        h = 1.0 / nx
+        ids = np.arange(len(nodes), dtype=np.float64)
+        for d in range(3):
+            nodes[:, d] += perturb * h * np.sin(2.0 * np.pi * ids / 97.0 + float(d))
+    order = sorted(slots)
+    el_type = np.array([slots[i][0] for i in order], dtype=np.int32)
+    el_matid = np.array([slots[i][1] for i in order], dtype=np.int32)
+    el_nodes = np.full((len(order), 8), -1, dtype=np.int64)
+    for k, i in enumerate(order):
+        el_nodes[k, : len(slots[i][2])] = slots[i][2]
+    return nodes, el_type, el_matid, el_nodes
+
+
+def hexpyr_mesh(n, porder, nstate, bc_matids=(-1,) * 6, perturb=0.0):
+    """Flattened mesh of hexahedra and pyramids side by side (MMeshType::EHexaPyrMixed), numbered as the reference numbers it."""
+    nodes, el_type, el_matid, el_nodes = hexpyr_elements(n, bc_matids=bc_matids, perturb=perturb)
+    return mesh_from_elements(nodes, el_type, el_matid, el_nodes, porder, nstate)
+
+
 def grid_mesh(n, porder, nstate, tetrahedra=False, bc_matids=(-1,) * 6, perturb=0.0, node_perm=None, prisms=False):
     """node_perm[i] = new index of grid node i (a renumbered mesh: same geometry, different side orientations)."""
     nodes, blocks = grid_elements(n, tetrahedra=tetrahedra, bc_matids=bc_matids, perturb=perturb, prisms=prisms)

@@ -53,8 +53,8 @@ def fixture_setup(g):
                 mats[-2] = mat.CreateBC(-2, 1, [[0.0]], [gu.NEUMANN_POISSON])
         return mesh, mats
     bc = (-1, -1, -1, -1, -1, -2 if bct >= 1 else -1)
-    if m["tet"] == 3:  # hexahedra + pyramids: elements (in computational-element order) from the fixture, numbering ours
-        mesh = gridmesh.mesh_from_elements(g["nodes"], g["el_type"], g["el_matid"], g["el_nodes"], m["p"], 3 if m["phys"] == 1 else 1)
+    if m["tet"] == 3:  # hexahedra + pyramids (MMeshType::EHexaPyrMixed)
+        mesh = gridmesh.hexpyr_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, bc_matids=bc, perturb=m["perturb"])
     else:
         mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=m["tet"] == 1, prisms=m["tet"] == 2,
                                   bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)

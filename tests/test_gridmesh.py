@@ -17,10 +17,8 @@ def _mesh_for(g):
     bc = (-1, -1, -1, -1, -1, -2 if m["bctype"] >= 1 else -1)
     if m["tet"] == 3:
         # hexahedra + pyramids (MMeshType::EHexaPyrMixed): the reference creates the pyramids by refinement and reuses the
-        # slots of the deleted hexahedra, so element types interleave; the mesh (nodes, elements in computational-element
-        # order) comes from the fixture, the connect numbering / block table / destination indices are ours
-        return gridmesh.mesh_from_elements(g["nodes"], g["el_type"], g["el_matid"], g["el_nodes"], m["p"],
-                                           3 if m["phys"] == 1 else 1)
+        # slots of the deleted hexahedra, so element types interleave (gridmesh.hexpyr_elements replays that allocation)
+        return gridmesh.hexpyr_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, bc_matids=bc, perturb=m["perturb"])
     return gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=m["tet"] == 1, prisms=m["tet"] == 2,
                               bc_matids=bc, perturb=m["perturb"], node_perm=perm)
 
