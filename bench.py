@@ -28,8 +28,10 @@ def algorithmic_work(topo, p, phys, nvol, neq, nnz):
     entry written once + the scatter-map read of the element's stored entries)."""
     if topo == "hex":
         n, q, nodes, G = (p + 1) ** 3, int(0.51 * (2 * p + 2)) ** 3, 8, 194
+    elif topo == "prism":   # TPZShapePrism, TPZIntPrism3D (line rule x triangle rule); grad x: 6 nodes x 9 x 2 + det / inverse
+        n, q, nodes, G = {1: 6, 2: 18}[p], {1: 6, 2: 18}[p], 6, 158
     else:
-        n, q, nodes, G = {1: 4, 2: 10}[p], {1: 4, 2: 14}[p], 4, 122   # tetrahedra: rules of order 2p (Zhang-Cui-Liu tables)
+        n, q, nodes, G = {1: 4, 2: 10, 3: 20, 4: 35}[p], {1: 4, 2: 14, 3: 24, 4: 46}[p], 4, 122   # tetrahedra: rules of order 2p (Zhang-Cui-Liu tables)
     if phys == "poisson":
         ndof, flops = n, q * (7 * n * n + 2 * n) + q * (18 * n + G)
     else:
@@ -48,7 +50,7 @@ def parse():
     ap.add_argument("--grid", dest="n", type=int, default=128, help="grid divisions per direction (per GPU)")
     ap.add_argument("--p", type=int, default=2)
     ap.add_argument("--phys", default="poisson", choices=["poisson", "elasticity"])
-    ap.add_argument("--topo", default="hex", choices=["hex", "tet"])
+    ap.add_argument("--topo", default="hex", choices=["hex", "tet", "prism"], help="prism: one GPU only (two prisms per grid cell)")
     ap.add_argument("--cpu-n", type=int, default=0, help="grid size of the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--engine", type=int, default=1, help="0: register-tile DFMA kernels, 1: DMMA panel kernels where available")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
@@ -67,13 +69,15 @@ def parse():
 
 def kernel_name(a):
     if a.engine == 1:
-        if a.topo == "tet" and a.variant == 0:
+        if a.topo == "tet" and a.variant == 0 and a.p <= 2:
             return "assemble_affine_simplex_kernel (closed-form element matrices of straight-sided tetrahedra, one warp per element)"
         if a.topo == "hex" and a.perturb == 0.0 and a.p <= 2:
             return "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)"
-        if a.phys == "poisson" and a.p == 2:
+        if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and 8 <= a.variant <= 15:
+            return "assemble_sumfact_hex_p2_poisson_kernel (sum factorisation, one CTA of 64 threads per element)"
+        if a.topo == "hex" and a.phys == "poisson" and a.p == 2:
             return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"
-        if a.phys == "poisson" and a.p >= 3:
+        if a.topo == "hex" and a.phys == "poisson" and a.p >= 3:
             return "assemble_gram_team_kernel (warp team per element, mma.sync.m8n8k4.f64)"
         if a.phys == "elasticity" and a.topo == "hex":
             return "assemble_gram_team_kernel (warp team per element, mma.sync.m8n8k4.f64)"
@@ -105,7 +109,7 @@ def run_reference(a, steps, warmup):
     if os.path.exists(drv):
         reps = max(1, steps)
         out = subprocess.run([drv, "time", str(n), str(a.p), "1" if a.phys == "elasticity" else "0",
-                              "1" if a.topo == "tet" else "0", str(cores), str(reps + warmup)],
+                              {"hex": "0", "tet": "1", "prism": "2"}[a.topo], str(cores), str(reps + warmup)],
                              capture_output=True, text=True, check=True).stdout
         line = [l for l in out.splitlines() if l.startswith("{")][-1]
         r = json.loads(line)
@@ -121,7 +125,7 @@ def run_reference(a, steps, warmup):
     from tests.test_gpu_parity import materials_for
     from neopz_b200 import capi
     n = max(4, n // 2)
-    mesh = gridmesh.grid_mesh(n, a.p, 3 if a.phys == "elasticity" else 1, tetrahedra=a.topo == "tet")
+    mesh = gridmesh.grid_mesh(n, a.p, 3 if a.phys == "elasticity" else 1, tetrahedra=a.topo == "tet", prisms=a.topo == "prism")
     mats = materials_for(1 if a.phys == "elasticity" else 0)
     idx, graph = mesh.element_graph()
     ia, ja = capi.build_pattern(True, idx, graph, mesh.block_pos, mesh.block_size, 0)
@@ -231,7 +235,14 @@ def main():
     from neopz_b200 import distributed
     t0 = time.time()
     ns = 3 if a.phys == "elasticity" else 1
-    slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=a.perturb)
+    if a.topo == "prism":
+        if world > 1:
+            raise SystemExit("bench.py: --topo prism runs on one GPU (the z-slab partition covers hexahedra and tetrahedra)")
+        import types
+        pm = gridmesh.grid_mesh(a.n, a.p, ns, prisms=True, perturb=a.perturb)
+        slab = types.SimpleNamespace(mesh=pm, nown=pm.neq)
+    else:
+        slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=a.perturb)
     mesh = slab.mesh
     t_flat = time.time() - t0
     if a.phys == "poisson":
