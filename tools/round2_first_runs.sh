@@ -40,10 +40,8 @@ for variant in (0, 8, 9, 11, 13, 14, 15):
     s.ctx.close()
 PY
 # 3. ncu: where do the 1500 cycles per element of the sum-factorisation kernel go (variant 8), next to the DMMA kernel
-ncu --set full --clock-control none --import-source on -k regex:assemble_sumfact -c 1 -o gpurun_out/r02_ncu_sumfact_v8 \
-    python bench.py --grid 64 --variant 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:assemble_gram_mma -c 1 -o gpurun_out/r02_ncu_mma \
-    python bench.py --grid 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+bash tools/ncu_capture.sh r02_ncu_sumfact_v8 assemble_sumfact --grid 64 --variant 8
+bash tools/ncu_capture.sh r02_ncu_mma assemble_gram_mma --grid 64
 # 4. the new configurations at sizes that fill the GPU
 python tools/time_configs.py 48 2>&1 | tee gpurun_out/r02_time_configs_n48.jsonl
 python bench.py --topo prism --p 2 --grid 64 --no-e2e 2> /dev/null | tee gpurun_out/r02_bench_prism_p2.json
