@@ -66,18 +66,6 @@ def test_prisms_against_oracle(n, p, phys):
         assert relF(r3, rhs_ref) <= TOL
 
 
-@pytest.mark.parametrize("n,p,phys", [(4, 2, 0), (5, 1, 1), (3, 2, 1)])
-def test_hexpyr_generated_meshes_against_oracle(n, p, phys):
-    """Hexahedra + pyramids of other sizes (gridmesh.hexpyr_mesh replays the reference's generator, slot reuse included)."""
-    mesh = gridmesh.hexpyr_mesh(n, p, 3 if phys else 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12)
-    mats = materials_for(phys, neumann=True)
-    for symmetric in (True, False):
-        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
-        ia, ja, a, rhs = strmat.CreateAssemble()
-        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
-        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
-
-
 @pytest.mark.parametrize("name", ["hexpyr_p2_poisson_n2_pert", "hexpyr_p1_elast_n3", "hexpyr_p2_elast_n2_pert"])
 def test_pyramids_moved_nodes_against_oracle(name):
     """The fixture's hexahedra + pyramids with differently perturbed nodes (b200asm_set_nodes): new geometry, same pattern."""

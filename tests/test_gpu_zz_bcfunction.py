@@ -17,21 +17,6 @@ from tests.test_gpu_parity import TOL, materials_for, relF
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", gu.BCFUNC_CASES)
-@pytest.mark.parametrize("symmetric", [True, False])
-def test_against_reference_fixtures(name, symmetric):
-    """Fixtures of the unmodified reference with boundary data from functions (Dirichlet + Neumann for Poisson, Dirichlet + mixed
-    for Elasticity3D): pattern bit-exact, values and load vector within 1e-12."""
-    from tests.test_gpu_parity import fixture_setup
-    g = gu.load(name)
-    mesh, mats = fixture_setup(g)
-    strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
-    ia, ja, a, rhs = strmat.CreateAssemble()
-    pre = "sym" if symmetric else "full"
-    assert np.array_equal(ia, g[pre + "_ia"]) and np.array_equal(ja, g[pre + "_ja"])
-    assert relF(a, g[pre + "_a"]) <= TOL and relF(rhs, g["rhs"]) <= TOL
-
-
 def g1(x):
     return (0.3 + x[:, 0] * x[:, 1] - 0.5 * x[:, 2] ** 2)[:, None]
 

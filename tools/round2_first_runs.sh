@@ -5,7 +5,7 @@
 set -x
 mkdir -p gpurun_out
 # 1. the 17 GPU tests that only had their CPU halves verified, then the whole suite
-python -m pytest tests/test_gpu_zzz_sumfact.py tests/test_gpu_zz_bcfunction.py tests/test_gpu_prism_pyramid.py -q -p no:cacheprovider 2>&1 | tail -5 | tee gpurun_out/r02_late_tests.log
+python -m pytest tests/test_gpu_zzz_sumfact.py tests/test_gpu_zzzz_added_late.py -q -p no:cacheprovider 2>&1 | tail -5 | tee gpurun_out/r02_late_tests.log
 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -5 | tee gpurun_out/r02_gpu_suite.log
 # 2. sum-factorisation variants: 8/9 barrier form, 11 barrier-free, 13/14 barrier form + prefetch, 15 barrier-free + prefetch
 python - <<'PY' 2>&1 | tee gpurun_out/r02_sumfact_variants.jsonl
