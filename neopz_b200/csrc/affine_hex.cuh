@@ -19,9 +19,11 @@
 // Scatter map: [el][round][a*NS+b][32] int32, read as whole 128-byte lines.
 #pragma once
 
-template <int N_, int NS_, int WPC_, int MINB_>
+// NN_ = 8: parallelepiped hexahedra; NN_ = 4: straight-sided tetrahedra of the orders whose table no longer fits the registers of
+// affine_simplex.cuh (p = 3, 4: 210 / 630 node pairs) - same kernel, the (single) Jacobian from the four corners
+template <int N_, int NS_, int WPC_, int MINB_, int NN_ = 8>
 struct AffHexCfg {
-    static constexpr int NN = 8, N = N_, NS = NS_, WPC = WPC_, MINB = MINB_;
+    static constexpr int NN = NN_, N = N_, NS = NS_, WPC = WPC_, MINB = MINB_;
     static constexpr int M = N * NS;
     static constexpr int NPAIR = N * (N + 1) / 2;
     static constexpr int ROUNDS = (NPAIR + 31) / 32;
@@ -98,11 +100,23 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_affine_hex_kern
     const int64_t nwarps = (int64_t)gridDim.x * C::WPC;
 
     for (int64_t el = (int64_t)blockIdx.x * C::WPC + warp; el < p.nel; el += nwarps) {
+        double j[3][3];
+        if (C::NN == 4) {
+            // straight-sided tetrahedron (Geom/pzgeotetrahedra.h:106-151): gradx(r,d) = x_{d+1}(r) - x_0(r)
+            const int4 n0 = *reinterpret_cast<const int4 *>(p.elnodes + el * 4);
+            const int32_t id[4] = {n0.x, n0.y, n0.z, n0.w};
+            double x0[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) x0[r] = p.xyz[(int64_t)id[0] * 3 + r];
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) j[r][d] = p.xyz[(int64_t)id[d + 1] * 3 + r] - x0[r];
+        } else {
         // corner coordinates: broadcast loads (every lane needs the whole Jacobian)
         const int4 n0 = *reinterpret_cast<const int4 *>(p.elnodes + el * 8), n1 = *reinterpret_cast<const int4 *>(p.elnodes + el * 8 + 4);
         const int32_t id[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
         // gradx at the centre: sum_a x_a dN_a(0), dN_a(0) = sign_a / 8  (constant over a parallelepiped)
-        double j[3][3];
 #pragma unroll
         for (int r = 0; r < 3; r++) j[r][0] = j[r][1] = j[r][2] = 0.0;
 #pragma unroll
@@ -117,11 +131,12 @@ __global__ void __launch_bounds__(C::WPC * 32, C::MINB) assemble_affine_hex_kern
         for (int r = 0; r < 3; r++)
 #pragma unroll
             for (int d = 0; d < 3; d++) j[r][d] *= 0.125;
+        }
         // next element: node coordinates and scatter positions towards L2
         const int64_t nxt = el + nwarps;
         if (nxt < p.nel) {
-            if (lane < 8) {
-                const int64_t node = p.elnodes[nxt * 8 + lane];
+            if (lane < C::NN) {
+                const int64_t node = p.elnodes[nxt * C::NN + lane];
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xyz + node * 3));
             }
             if (!p.rhs_only) {

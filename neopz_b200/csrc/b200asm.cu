@@ -900,6 +900,7 @@ struct Group {
     int cfg = -1;  // index into the dispatch table (register-tile kernels)
     int mma = -1;  // index into the DMMA dispatch table, -1: none
     int aff = -1;  // index into the closed-form table for parallelepiped hexahedra (affine_hex.cuh), -1: none
+    int taff = -1;  // index into kTetAffS (tetrahedra p = 3, 4, option variant = 20), -1: none
     bool use_aff = false;      // every element of the group is a parallelepiped (measured): the closed-form kernel runs
     bool aff_checked = false;  // ... for the current node coordinates
     double coef[16];
@@ -1267,9 +1268,19 @@ cudaError_t prepare_affhex(size_t smem, int *ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_affine_hex_kernel<C>, C::WPC * 32, smem);
 }
 template <class C>
-MmaEntry make_affhex_entry(int porder) {
-    return MmaEntry{0, B200ASM_HEX, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_affhex<C>, &launch_affhex_smap<C>, &prepare_affhex<C>};
+MmaEntry make_affhex_entry(int porder, int topology = B200ASM_HEX, int variant = 0) {
+    return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_affhex<C>, &launch_affhex_smap<C>, &prepare_affhex<C>};
 }
+// the same closed-form kernel on straight-sided tetrahedra of order 3, 4 (table in shared memory).  Tuning variant 20: written
+// after round 1's GPU budget was spent, NOT yet run on a GPU; the default of these orders stays the register-tile kernel.
+constexpr int kTetAffSmemVariant = 20;
+using TetP3PoissonAffS = AffHexCfg<20, 1, 8, 3, 4>;
+using TetP3ElastAffS = AffHexCfg<20, 3, 8, 2, 4>;
+using TetP4PoissonAffS = AffHexCfg<35, 1, 8, 2, 4>;
+using TetP4ElastAffS = AffHexCfg<35, 3, 8, 1, 4>;
+const MmaEntry kTetAffS[] = {make_affhex_entry<TetP3PoissonAffS>(3, B200ASM_TET, kTetAffSmemVariant), make_affhex_entry<TetP3ElastAffS>(3, B200ASM_TET, kTetAffSmemVariant),
+                             make_affhex_entry<TetP4PoissonAffS>(4, B200ASM_TET, kTetAffSmemVariant), make_affhex_entry<TetP4ElastAffS>(4, B200ASM_TET, kTetAffSmemVariant)};
+constexpr int kNumTetAffS = sizeof(kTetAffS) / sizeof(kTetAffS[0]);
 const MmaEntry kAffHex[] = {make_affhex_entry<HexP1PoissonAff>(1), make_affhex_entry<HexP1ElastAff>(1),
                             make_affhex_entry<HexP2PoissonAff>(2), make_affhex_entry<HexP2ElastAff>(2)};
 constexpr int kNumAffHex = sizeof(kAffHex) / sizeof(kAffHex[0]);
@@ -1280,6 +1291,7 @@ bool entry_major(const b200asm_ctx *ctx, const Group &g) { return g.kind == B200
 // the kernel that runs a volume group on the DMMA / closed-form engine (nullptr: register-tile kernel)
 const MmaEntry *fast_entry(const b200asm_ctx *ctx, const Group &g) {
     if (ctx->engine != 1) return nullptr;
+    if (g.taff >= 0) return &kTetAffS[g.taff];
     if (g.use_aff && g.aff >= 0) return &kAffHex[g.aff];
     return g.mma >= 0 ? &kMma[g.mma] : nullptr;
 }
@@ -1765,6 +1777,15 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         else if (g.n == 8) aff_tables<HexP1ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else if (g.ns == 1) aff_tables<HexP2PoissonAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         else aff_tables<HexP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
+    }
+    if (volume && g.topology == B200ASM_TET && (g.porder == 3 || g.porder == 4) && g.uniform && ctx->variant == kTetAffSmemVariant) {
+        for (int k = 0; k < kNumTetAffS; k++)
+            if (kTetAffS[k].porder == g.porder && kTetAffS[k].ns == g.ns) g.taff = k;
+        if (g.porder == 3 && g.ns == 1) aff_tables<TetP3PoissonAffS>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else if (g.porder == 3) aff_tables<TetP3ElastAffS>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else if (g.ns == 1) aff_tables<TetP4PoissonAffS>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
+        else aff_tables<TetP4ElastAffS>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
     }
     if (volume && g.topology == B200ASM_TET && g.porder <= 2 && !g.generic) {  // (orders 3, 4 run the register-tile kernel)

@@ -42,6 +42,26 @@ PY
 # 3. ncu: where do the 1500 cycles per element of the sum-factorisation kernel go (variant 8), next to the DMMA kernel
 bash tools/ncu_capture.sh r02_ncu_sumfact_v8 assemble_sumfact --grid 64 --variant 8
 bash tools/ncu_capture.sh r02_ncu_mma assemble_gram_mma --grid 64
+# 3b. closed-form kernel for tetrahedra of order 3, 4 (variant 20): parity against the oracle, then timing
+python - <<'PY' 2>&1 | tee gpurun_out/r02_tet_closed_form_parity.jsonl
+import json, sys
+sys.path.insert(0, ".")
+import numpy as np
+from neopz_b200 import gridmesh, strmatrix as sm
+from tests.oracle_ref import oracle_assemble
+from tests.test_gpu_parity import materials_for, relF
+for n, p, phys in ((3, 3, 0), (2, 4, 0), (2, 3, 1), (2, 4, 1)):
+    perm = np.random.default_rng(3).permutation((n + 1) ** 3)
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=True, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12, node_perm=perm)
+    mats = materials_for(phys, neumann=True)
+    for sym in (True, False):
+        s = sm.TPZStructMatrixB200(mesh, mats, symmetric=sym, variant=20)
+        ia, ja, a, rhs = s.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, sym, ia, ja)
+        print(json.dumps({"n": n, "p": p, "phys": phys, "symmetric": sym, "relF_A": relF(a, a_ref), "relF_rhs": relF(rhs, rhs_ref)}), flush=True)
+        s.ctx.close()
+PY
+python tools/time_configs.py 24 variant20 2>&1 | tee gpurun_out/r02_time_tet_closed_form.jsonl
 # 4. the new configurations at sizes that fill the GPU
 python tools/time_configs.py 48 2>&1 | tee gpurun_out/r02_time_configs_n48.jsonl
 python bench.py --topo prism --p 2 --grid 64 --no-e2e 2> /dev/null | tee gpurun_out/r02_bench_prism_p2.json

@@ -14,18 +14,28 @@ import numpy as np  # noqa: E402
 
 from neopz_b200 import gridmesh, strmatrix as sm  # noqa: E402
 
-CONFIGS = [  # name, p, phys, tetrahedra, prisms, engine
+CONFIGS = [  # name, p, phys, tetrahedra, prisms, engine[, variant]
     ("prism p1 poisson", 1, 0, False, True, 1), ("prism p2 poisson", 2, 0, False, True, 1), ("prism p2 elasticity", 2, 1, False, True, 1),
     ("tet p3 poisson", 3, 0, True, False, 1), ("tet p3 elasticity", 3, 1, True, False, 1),
     ("tet p4 poisson", 4, 0, True, False, 1), ("tet p4 elasticity", 4, 1, True, False, 1),
     ("hex p2 poisson, generic kernel", 2, 0, False, False, 2), ("hex p2 elasticity, generic kernel", 2, 1, False, False, 2),
     ("hex p2 poisson, register tiles", 2, 0, False, False, 0),
+    # closed-form kernel with the table in shared memory (tuning variant 20; not run on a GPU in round 1)
+    ("tet p3 poisson, closed form", 3, 0, True, False, 1, 20), ("tet p3 elasticity, closed form", 3, 1, True, False, 1, 20),
+    ("tet p4 poisson, closed form", 4, 0, True, False, 1, 20), ("tet p4 elasticity, closed form", 4, 1, True, False, 1, 20),
 ]
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-    for name, p, phys, tet, prisms, engine in CONFIGS:
+    only20 = len(sys.argv) > 2 and sys.argv[2] == "variant20"
+    for cfg in CONFIGS:
+        name, p, phys, tet, prisms, engine = cfg[:6]
+        variant = cfg[6] if len(cfg) > 6 else 0
+        if variant == 20 and not only20 and os.environ.get("B200ASM_TIME_UNVERIFIED") != "1":
+            continue   # (python tools/time_configs.py 24 variant20 measures them, after tests/ has checked their parity)
+        if only20 and variant != 20:
+            continue
         nn = max(6, n // 2) if (p >= 4 or (p >= 3 and phys)) else n
         mesh = gridmesh.grid_mesh(nn, p, 3 if phys else 1, tetrahedra=tet, prisms=prisms, perturb=0.1)
         if phys == 0:
@@ -35,7 +45,7 @@ def main():
         else:
             mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
             mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
-        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, engine=engine)
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, engine=engine, variant=variant)
         strmat.Create(on_device=True, download=False)
         ctx = strmat.ctx
         for _ in range(3):
