@@ -45,3 +45,17 @@ def test_product_never_imports_oracle():
                 if re.search(r"(^|\s)(from|import)\s+oracle\b|liboracle|oracle/oracle|oracle\.c\b|orc_[a-z]+\(", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_enumerations_match_the_python_binding():
+    """Topology / kind codes of include/b200asm.h == the constants of neopz_b200/capi.py (and of the oracle's, which shares the
+    numbering of the element types)."""
+    text = open(os.path.join(ROOT, "include", "b200asm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(B200ASM_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    for name in ("HEX", "TET", "QUAD", "TRI", "LINE", "PRISM", "PYRAMID", "POISSON", "ELASTICITY3D", "BC", "ELASTICITY2D"):
+        assert enums["B200ASM_" + name] == getattr(capi, name), name
+    assert enums["B200ASM_ENODEVICE"] == capi.ENODEVICE
+    from oracle import oracle as orc
+    assert (orc.HEX, orc.TET, orc.QUAD, orc.TRI, orc.LINE, orc.PRISM, orc.PYR) == (capi.HEX, capi.TET, capi.QUAD, capi.TRI, capi.LINE,
+                                                                                  capi.PRISM, capi.PYRAMID)
