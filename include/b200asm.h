@@ -196,16 +196,18 @@ int b200asm_prism_rule(int order, int ntri, const double *tripts, const double *
 /* H1 shape tables (uniform p<=2) at given master-element points.  Returns nshape.  Prisms: Shape/pzshapeprism.cpp:42-205;
  * pyramids: Shape/pzshapepiram.cpp:47-119,331-392 (rational corner functions; points must stay off the apex). */
 int b200asm_shape_tables(int topology, int porder, int nqp, const double *qpts, double *phi, double *dphi);
-/* number of H1 shape functions of an element of uniform order p (TSHAPE::NShapeF): hex (p+1)^3, quad (p+1)^2;
- * tetrahedra / triangles / prisms (6, 18) / pyramids (5, 14) for p <= 2. */
+/* number of H1 shape functions of an element of uniform order p (TSHAPE::NShapeF): hex (p+1)^3, quad (p+1)^2, tetrahedra
+ * (p+1)(p+2)(p+3)/6, triangles (p+1)(p+2)/2, lines p+1; prisms (6, 18) / pyramids (5, 14) for p <= 2. */
 int b200asm_nshape(int topology, int porder);
 /* Side-orientation key of every element from the GLOBAL indices of its corner nodes (what
  * ComputeTransforms / GetTransformId derive per side: Shape/pzgenericshape.cpp:57-68, Topology/tpzcube.cpp:1059-1111,
- * Topology/tpzquadrilateral.cpp:591-618): 1 bit per edge, 3 bits per quadrilateral face.  For p >= 3 the shape
+ * Topology/tpzquadrilateral.cpp:591-618, Topology/tpztetrahedron.cpp:1128-1170, Topology/tpztriangle.cpp:599-658): 1 bit per edge,
+ * 3 bits per quadrilateral or triangular side (hexahedra: edges in bits 0-11, faces from bit 12; tetrahedra: edges 0-5, faces from
+ * bit 6; quadrilaterals: edges 0-3, interior from bit 4; triangles: edges 0-2, interior from bit 3; lines: bit 0).  For p >= 3 the shape
  * functions of a side depend on it; elements with equal keys share their tables (one b200asm_group per key).
  * elnodes[nel][ncorner]. */
 int b200asm_orientation_keys(int topology, int64_t nel, const int32_t *elnodes, int64_t *keys);
-/* H1 shape tables of uniform order p (any p for hex / quad) for the orientation class `key`:
+/* H1 shape tables of uniform order p (any p for hex / quad / line / tet / tri; p <= 2 for prisms / pyramids) for the orientation class `key`:
  * TPZShapeH1<TSHAPE>::Shape (Shape/TPZShapeH1.cpp:42-116) at the given points.  Returns nshape. */
 int b200asm_shape_tables_oriented(int topology, int porder, int64_t key, int nqp, const double *qpts, double *phi,
                                   double *dphi);
