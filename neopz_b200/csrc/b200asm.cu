@@ -1067,9 +1067,6 @@ constexpr int kNumVol = sizeof(kVol) / sizeof(kVol[0]);
 using HexP2PoissonMma = MmaCfg<8, 27, 8, 2>;
 using TetP2PoissonMma = MmaCfg<4, 10, 8, 2>;
 using HexP1PoissonMma = MmaCfg<8, 8, 8, 4>;
-using HexP2PoissonMmaV1 = MmaCfg<8, 27, 8, 3>;
-using HexP2PoissonMmaV2 = MmaCfg<8, 27, 4, 5>;
-using HexP2PoissonMmaV3 = MmaCfg<8, 27, 4, 6>;
 
 struct MmaEntry {
     int variant;  // 0 = default; others are tuning alternatives selected with option "variant"
@@ -1080,6 +1077,7 @@ struct MmaEntry {
     cudaError_t (*launch_smap)(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
                                int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t);
     cudaError_t (*prepare)(size_t smem, int *ctas_per_sm);
+    bool sumfact = false;  // sum-factorisation kernel: needs Group::sumfact_ok (the 3 x 3 x 3 tensor rule in the reference's point order)
 };
 template <class C>
 cudaError_t launch_mma(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
@@ -1103,25 +1101,13 @@ MmaEntry make_mma_entry(int topology, int porder, int variant = 0) {
     return MmaEntry{variant, topology, porder, 1, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_mma<C>, &launch_mma_smap<C>, &prepare_mma<C>};
 }
 // team kernels (gram_mma_team.cuh):   NN  N  NS  warps/element  elements/CTA  min CTAs/SM
-using HexP2ElastTeam = TeamCfg<8, 27, 3, 10, 1, 2>;   // one tile group (9 tiles) per warp: 96 registers, 20 warps/SM
-using TetP2ElastTeam = TeamCfg<4, 10, 3, 3, 2, 2>;
 using TetP2ElastTeamV2 = TeamCfg<4, 10, 3, 3, 4, 2>;
-using TetP2ElastTeamV3 = TeamCfg<4, 10, 3, 3, 4, 3>;
-using TetP2ElastTeamV4 = TeamCfg<4, 10, 3, 3, 8, 1>;
-using TetP2ElastTeamV5 = TeamCfg<4, 10, 3, 1, 8, 2>;   // ONE warp per element (27 tiles, 54 accumulators), no barriers
-using TetP2ElastTeamV6 = TeamCfg<4, 10, 3, 3, 5, 2>;
 using HexP1ElastTeam = TeamCfg<8, 8, 3, 1, 8, 2>;
-using HexP2ElastTeamV1 = TeamCfg<8, 27, 3, 5, 1, 2>;   // two tile groups per warp (154 registers, 10 warps/SM)
-using HexP2ElastTeamV2 = TeamCfg<8, 27, 3, 10, 1, 3>;
 using HexP2ElastTeamV3 = TeamCfg<8, 27, 3, 10, 2, 1>;  // DEFAULT: two teams per CTA, 20 warps = 5 per scheduler (a 10-warp CTA leaves
                                                        // 3,3,2,2): 30.3 vs 29.0 M el/s at 64^3; the same change on p4 Poisson lost 3 %
 // higher-order Poisson: one warp per 4x4 superblock of 8x8 tiles (p=3: 8x8 tiles -> 3 warps; p=4: 16x16 -> 10 warps)
-using HexP2PoissonTeamV4 = TeamCfg<8, 27, 1, 3, 4, 2, 2>;   // 3 warps per element (2x2-tile superblocks), 4 elements per CTA
-using HexP2PoissonTeamV5 = TeamCfg<8, 27, 1, 3, 4, 3, 2>;
-using HexP2PoissonTeamV6 = TeamCfg<8, 27, 1, 3, 8, 1, 2>;
 using HexP3PoissonTeam = TeamCfg<8, 64, 1, 3, 2, 3, 4>;
 using HexP4PoissonTeam = TeamCfg<8, 125, 1, 10, 1, 2, 4>;
-using HexP4PoissonTeamV1 = TeamCfg<8, 125, 1, 10, 2, 1, 4>;  // two teams per CTA (5 warps per scheduler)
 
 template <class C>
 cudaError_t launch_team(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
@@ -1215,32 +1201,25 @@ inline size_t sumfact_smem(int) { return 0; }
 template <int MINB, int PRIVATE = 0, int PREFETCH = 0>
 MmaEntry make_sumfact_entry(int variant) {
     return MmaEntry{variant, B200ASM_HEX, 2, 1, sf::SLOTS, sf::NTHREADS, 1, &sumfact_smem, &launch_sumfact<MINB, PRIVATE, PREFETCH>,
-                    &launch_sumfact_smap, &prepare_sumfact<MINB, PRIVATE, PREFETCH>};
+                    &launch_sumfact_smap, &prepare_sumfact<MINB, PRIVATE, PREFETCH>, true};
 }
-// wpc = elements processed concurrently by one CTA; variant 0 = default (the first match wins), variant 7 = the DMMA
-// Gram kernels for tetrahedra that the closed-form kernels replaced
+// wpc = elements processed concurrently by one CTA; variant 0 = default (the first match wins).  Alternatives kept because a
+// test or a profile refers to them: 7 = the DMMA Gram kernels for tetrahedra that the closed-form kernels replaced, 8 = sum
+// factorisation without the prefetch (12 CTAs/SM), 11 = its barrier-free form, 13 = the default again, 16 = the one-warp DMMA Gram
+// kernel that was the default of hexahedra p = 2 Poisson in round 1 (it still runs every such group whose rule is not the 3 x 3 x 3
+// tensor rule).  Measured on a 96^3 perturbed grid (profiles/r02_sumfact_variants.jsonl): 13: 193.9 M elements/s, 16: 169.1,
+// 8: 163.7, 11: 148.3; the other alternatives of round 1 (9, 10, 12, 14, 15 and the DMMA occupancy variants 1-6) lost and were removed.
 const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP1ElastAff>(1),
                          make_aff_entry<TetP2PoissonAff>(2), make_aff_entry<TetP2ElastAff>(2),
+                         make_sumfact_entry<8, 0, 1>(0),
                          make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2, 7),
                          make_team_entry<HexP2ElastTeamV3>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
                          make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
-                         make_mma_entry<HexP2PoissonMmaV1>(B200ASM_HEX, 2, 1), make_mma_entry<HexP2PoissonMmaV2>(B200ASM_HEX, 2, 2),
-                         make_mma_entry<HexP2PoissonMmaV3>(B200ASM_HEX, 2, 3),
-                         make_team_entry<HexP2PoissonTeamV4>(B200ASM_HEX, 2, 4), make_team_entry<HexP2PoissonTeamV5>(B200ASM_HEX, 2, 5),
-                         make_team_entry<HexP2PoissonTeamV6>(B200ASM_HEX, 2, 6),
-                         make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 7), make_team_entry<TetP2ElastTeam>(B200ASM_TET, 2, 1),
-                         make_team_entry<TetP2ElastTeamV3>(B200ASM_TET, 2, 3), make_team_entry<TetP2ElastTeamV4>(B200ASM_TET, 2, 4),
-                         make_team_entry<TetP2ElastTeamV5>(B200ASM_TET, 2, 5), make_team_entry<TetP2ElastTeamV6>(B200ASM_TET, 2, 6),
-                         make_team_entry<HexP2ElastTeamV1>(B200ASM_HEX, 2, 1), make_team_entry<HexP2ElastTeamV2>(B200ASM_HEX, 2, 2),
-                         make_team_entry<HexP2ElastTeam>(B200ASM_HEX, 2, 3), make_team_entry<HexP4PoissonTeamV1>(B200ASM_HEX, 4, 1),
-                         make_sumfact_entry<12>(kSumfactVariant), make_sumfact_entry<8>(kSumfactVariant + 1),
-                         make_sumfact_entry<12, 1>(kSumfactVariant + 2), make_sumfact_entry<8, 1>(kSumfactVariant + 3),
-                         make_sumfact_entry<16, 1>(kSumfactVariant + 4),
-                         // (13-15: with the coordinate / position prefetch; written after the GPU budget of round 1 was spent:
-                         //  same arithmetic, CPU-emulated, NOT yet run on a GPU - to be measured first thing in round 2)
-                         make_sumfact_entry<8, 0, 1>(kSumfactVariant + 5), make_sumfact_entry<12, 0, 1>(kSumfactVariant + 6),
-                         make_sumfact_entry<8, 1, 1>(kSumfactVariant + 7)};
+                         make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2, 16),
+                         make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 7),
+                         make_sumfact_entry<12>(kSumfactVariant), make_sumfact_entry<8, 1>(kSumfactVariant + 3),
+                         make_sumfact_entry<8, 0, 1>(kSumfactVariant + 5)};
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);
@@ -1271,15 +1250,17 @@ template <class C>
 MmaEntry make_affhex_entry(int porder, int topology = B200ASM_HEX, int variant = 0) {
     return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_affhex<C>, &launch_affhex_smap<C>, &prepare_affhex<C>};
 }
-// the same closed-form kernel on straight-sided tetrahedra of order 3, 4 (table in shared memory).  Tuning variant 20: written
-// after round 1's GPU budget was spent, NOT yet run on a GPU; the default of these orders stays the register-tile kernel.
-constexpr int kTetAffSmemVariant = 20;
+// the same closed-form kernel on straight-sided tetrahedra of order 3, 4 (table in shared memory): the default of these orders
+// since round 2 (profiles/r02_time_tet_closed_form.jsonl: p3 Poisson 489 M elements/s against 108 M of the register-tile
+// kernel, p3 elasticity 55 against 16, p4 20-74 against 3-14; parity profiles/r02_tet_closed_form_parity.jsonl).  Option
+// variant = 21 keeps the register-tile kernel.
+constexpr int kTetRegTileVariant = 21;
 using TetP3PoissonAffS = AffHexCfg<20, 1, 8, 3, 4>;
 using TetP3ElastAffS = AffHexCfg<20, 3, 8, 2, 4>;
 using TetP4PoissonAffS = AffHexCfg<35, 1, 8, 2, 4>;
 using TetP4ElastAffS = AffHexCfg<35, 3, 8, 1, 4>;
-const MmaEntry kTetAffS[] = {make_affhex_entry<TetP3PoissonAffS>(3, B200ASM_TET, kTetAffSmemVariant), make_affhex_entry<TetP3ElastAffS>(3, B200ASM_TET, kTetAffSmemVariant),
-                             make_affhex_entry<TetP4PoissonAffS>(4, B200ASM_TET, kTetAffSmemVariant), make_affhex_entry<TetP4ElastAffS>(4, B200ASM_TET, kTetAffSmemVariant)};
+const MmaEntry kTetAffS[] = {make_affhex_entry<TetP3PoissonAffS>(3, B200ASM_TET), make_affhex_entry<TetP3ElastAffS>(3, B200ASM_TET),
+                             make_affhex_entry<TetP4PoissonAffS>(4, B200ASM_TET), make_affhex_entry<TetP4ElastAffS>(4, B200ASM_TET)};
 constexpr int kNumTetAffS = sizeof(kTetAffS) / sizeof(kTetAffS[0]);
 const MmaEntry kAffHex[] = {make_affhex_entry<HexP1PoissonAff>(1), make_affhex_entry<HexP1ElastAff>(1),
                             make_affhex_entry<HexP2PoissonAff>(2), make_affhex_entry<HexP2ElastAff>(2)};
@@ -1623,8 +1604,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
                                gi->qpts[3 * q + 2] == gi->qpts[3 * (q / 9)];
         }
         for (int k = 0; k < kNumMma && !g.generic; k++) {
-            const bool is_sumfact = kMma[k].variant >= kSumfactVariant && kMma[k].variant <= kSumfactVariant + 7;
-            if (is_sumfact && !g.sumfact_ok) continue;
+            if (kMma[k].sumfact && !g.sumfact_ok) continue;
             if (kMma[k].topology == g.topology && kMma[k].porder == g.porder && kMma[k].ns == g.ns &&
                 (kMma[k].variant == 0 ? g.mma < 0 : kMma[k].variant == ctx->variant))
                 g.mma = k;
@@ -1779,7 +1759,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         else aff_tables<HexP2ElastAff>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);
         if ((rc = upload(ctx, &g.d_aux, aux.data(), aux.size()))) return rc;
     }
-    if (volume && g.topology == B200ASM_TET && (g.porder == 3 || g.porder == 4) && g.uniform && ctx->variant == kTetAffSmemVariant) {
+    if (volume && g.topology == B200ASM_TET && (g.porder == 3 || g.porder == 4) && g.uniform && ctx->variant != kTetRegTileVariant) {
         for (int k = 0; k < kNumTetAffS; k++)
             if (kTetAffS[k].porder == g.porder && kTetAffS[k].ns == g.ns) g.taff = k;
         if (g.porder == 3 && g.ns == 1) aff_tables<TetP3PoissonAffS>(g.nq, gi->qwts, gi->phi, gi->dphi, aux);

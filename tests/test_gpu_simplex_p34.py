@@ -52,16 +52,18 @@ def test_device_pattern_and_colored_scatter(name):
     assert np.array_equal(a, a2) and np.array_equal(rhs, rhs2)  # bit-reproducible
 
 
-@pytest.mark.parametrize("n,p,phys,seed", [(3, 3, 0, 0), (2, 4, 0, 3), (2, 3, 1, 4), (2, 4, 1, 0), (4, 3, 0, 9)])
-def test_tetrahedra_against_oracle(n, p, phys, seed):
-    """Fresh meshes: perturbed nodes, node numbering shuffled with `seed` (0: the grid numbering), Neumann face."""
+@pytest.mark.parametrize("n,p,phys,seed,variant", [(3, 3, 0, 0, 0), (2, 4, 0, 3, 0), (2, 3, 1, 4, 0), (2, 4, 1, 0, 0), (4, 3, 0, 9, 0),
+                                                    (2, 3, 1, 4, 21), (2, 4, 0, 3, 21)])
+def test_tetrahedra_against_oracle(n, p, phys, seed, variant):
+    """Fresh meshes: perturbed nodes, node numbering shuffled with `seed` (0: the grid numbering), Neumann face.  variant 0: the
+    closed-form kernel (default of tetrahedra p = 3, 4 since round 2), 21: the register-tile kernel it replaced."""
     nn = (n + 1) ** 3
     perm = np.random.default_rng(seed).permutation(nn) if seed else None
     mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=True, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12,
                               node_perm=perm)
     mats = materials_for(phys, neumann=True)
     for symmetric in (True, False):
-        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+        strmat = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, variant=variant)
         ia, ja, a, rhs = strmat.CreateAssemble()
         a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
         assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL

@@ -63,5 +63,5 @@ for n, p, phys in ((3, 3, 0), (2, 4, 0), (2, 3, 1), (2, 4, 1)):
 PY
 python tools/time_configs.py 24 variant20 2>&1 | tee gpurun_out/r02_time_tet_closed_form.jsonl
 # 4. the new configurations at sizes that fill the GPU
-python tools/time_configs.py 48 2>&1 | tee gpurun_out/r02_time_configs_n48.jsonl
-python bench.py --topo prism --p 2 --grid 64 --no-e2e 2> /dev/null | tee gpurun_out/r02_bench_prism_p2.json
+# (time_configs 48 dropped: GPU budget)
+
