@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--perturb", type=float, default=0.1, help="smooth node perturbation in units of h (default 0.1: general trilinear "
                     "hexahedra; 0 = the uniform grid of CreateGeoMeshOnGrid, whose parallelepiped cells take the closed-form kernel)")
     ap.add_argument("--locality", type=int, default=1, help="0: keep the mesh (lexicographic) element order on the device")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: interface rows pushed into the owner's memory over "
+                    "NVLink while the interior is assembled (C ABI, b200asm_exchange_*), or NCCL send/recv after the kernels")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -253,7 +255,7 @@ def main():
         mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
         mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
     sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter,
-                                              pattern=a.pattern, variant=a.variant) if world > 1 else None
+                                              pattern=a.pattern, variant=a.variant, exchange=a.exchange) if world > 1 else None
     strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter, variant=a.variant)
     stream = torch.cuda.current_stream()
     strmat.ctx.set_stream(stream.cuda_stream)
@@ -325,11 +327,11 @@ def main():
         ksteps = max(2, min(a.steps, 5))
         def e2e_step():
             strmat.ctx.set_nodes(x_np)          # H2D: node coordinates (the geometry input of the step)
-            if sharded:
+            if sharded and a.exchange == "nccl":
                 sharded.AssembleDevice()        # kernels + NCCL interface exchange
                 strmat.ctx.download(a_np, r_np)  # D2H of the CSR values and the load vector
             else:
-                strmat.ctx.assemble(a_np, r_np)  # kernels + D2H
+                strmat.ctx.assemble(a_np, r_np)  # kernels (+ interface push) + D2H, overlapped
         def e2e_time():
             e2e_step()  # warm-up
             barrier()

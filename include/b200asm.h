@@ -106,7 +106,10 @@ int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
  * inside every overlap chunk, when b200asm_set_nodes was called first: the rows of A an element shares with its neighbours
  * are then revisited while they are still in L2),
  * "overlap" (default 1: b200asm_assemble with a host matrix copies the finished rows of A back while later element
- * chunks are still being assembled; "overlap_min_elements" (before add_group) and "overlap_min_bytes" tune the chunking) */
+ * chunks are still being assembled; "overlap_min_elements" (before add_group) and "overlap_min_bytes" tune the chunking),
+ * "variant" (before add_group: 0 default kernels; 7 DMMA kernels on tetrahedra p <= 2, 8 / 11 / 13 sum-factorisation forms and
+ * 16 the one-warp DMMA kernel on hexahedra p = 2 Poisson, 21 register-tile kernel on tetrahedra p = 3, 4),
+ * "staging_lo" / "staging_hi" (before add_group, row-sharded assembly: see b200asm_exchange_*), "exchange_timeout_ms" */
 int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);
 
 /* ---- flattened mesh ---------------------------------------------------------------------- */
@@ -116,6 +119,10 @@ int b200asm_set_nodes(b200asm_ctx *ctx, int64_t nnodes, const double *xyz);
 int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *g);
 /* replaces coef[] of a group (material constants may change between assemblies) */
 int b200asm_set_group_coef(b200asm_ctx *ctx, int group, const double coef[16]);
+/* replaces the force table of a group ([nel][nqp][nstate] in the element order of add_group): forcing functions and boundary
+ * data that change between assemblies (time-dependent sources; the reference calls the std::function again at every
+ * CalcStiff, Material/Poisson/TPZMatPoisson.cpp:24-27).  The group must have been added with a table. */
+int b200asm_set_group_force(b200asm_ctx *ctx, int group, const double *force);
 int b200asm_clear_groups(b200asm_ctx *ctx);
 
 /* ---- CSR pattern --------------------------------------------------------------------------
@@ -176,6 +183,57 @@ int b200asm_cg_solution_device(b200asm_ctx *ctx, double **x_dev);
  * neighbouring rank into the resident CSR values (target 0) or rhs (target 1) at precomputed, distinct
  * positions: dst[positions[k]] += values[k].  positions/values are DEVICE pointers; asynchronous. */
 int b200asm_scatter_add(b200asm_ctx *ctx, int target, const int32_t *positions_dev, const double *values_dev, int64_t n);
+/* ---- multi-GPU, row-sharded assembly: interface exchange over peer memory -------------------------------
+ * One context per GPU.  Every context holds a LOCAL system: the rows it owns plus "staging" rows that another GPU owns but its
+ * elements contribute to (options "staging_lo" / "staging_hi", local row range, before add_group: the elements that touch
+ * them are stored and launched first).  At every assembly the staged values are added straight into the owner's CSR values and
+ * load vector over NVLink (P2P stores into the peer's memory, mapped with cudaDeviceEnablePeerAccess inside one process or
+ * cudaIpcOpenMemHandle between the processes of a one-process-per-GPU job) on a side stream, while the interior elements are
+ * assembled; GPUs order themselves with step counters in device memory, the host never synchronises.  The reference's only
+ * parallel knob is the thread count of the strategy (StrMatrix/TPZStrMatParInterface.h:62-69); this is the GPU counterpart.
+ * Every context of the job must run the same sequence of assemble calls.  A new pattern drops the links. */
+#define B200ASM_MAX_PEERS 16
+typedef struct { unsigned char handle[64]; int64_t offset; } b200asm_ipc_mem; /* cudaIpcMemHandle_t + offset in the allocation */
+/* handles of this context's CSR values, load vector and flag block, for b200asm_exchange_add_peer in ANOTHER process */
+int b200asm_exchange_export(b200asm_ctx *ctx, b200asm_ipc_mem out[3]);
+/* Declares a peer.  push != 0: this context pushes staged contributions into it (then b200asm_exchange_set_map); push == 0: the
+ * peer pushes into this context, incoming_min_row = smallest local row it touches (-1: unknown).  slot_there = index of the link
+ * to THIS context in the peer's own table (the value its b200asm_exchange_add_peer returns / returned).  Give either the
+ * exported handles of a context in another process (mem) or a context of this process (peer).  Returns the link index. */
+int b200asm_exchange_add_peer(b200asm_ctx *ctx, int push, int slot_there, const b200asm_ipc_mem mem[3], b200asm_ctx *peer,
+                              int64_t incoming_min_row);
+/* what a push link sends: the CSR values [a_src0, a_src0 + n_a) of this context are added at a_dst[k] of the peer's values,
+ * rhs[rhs_src[k]] at rhs_dst[k] of the peer's load vector (host arrays, copied) */
+int b200asm_exchange_set_map(b200asm_ctx *ctx, int link, int64_t n_a, int64_t a_src0, const int32_t *a_dst, int64_t n_rhs,
+                             const int32_t *rhs_src, const int32_t *rhs_dst);
+int b200asm_exchange_clear(b200asm_ctx *ctx);
+/* ---- multi-GPU in ONE process: the same calls as above on a set of devices ------------------------------------------------
+ * The counterpart of TPZStrMatParInterface::SetNumThreads (StrMatrix/TPZStrMatParInterface.h:62-69) for GPUs.  The caller gives
+ * the flattened mesh and the GLOBAL pattern exactly as to one context; b200asm_multi_set_pattern partitions the elements by
+ * their smallest destination equation into chunks of equal work, GPU g owns the row block [row_begin[g],
+ * row_begin[g+1]) of the global CSR, holds its slice of IA / JA / A only, and the contributions of its elements to rows of
+ * other GPUs travel over NVLink through b200asm_exchange_* while the interior elements are assembled.  b200asm_multi_assemble
+ * writes the caller's GLOBAL a_host[nnz] / rhs_host[neq]: every GPU its own slice, concurrently. */
+typedef struct b200asm_multi b200asm_multi;
+int b200asm_multi_create(b200asm_multi **out, int ndev, const int *devices /* NULL: 0 .. ndev-1 */);
+void b200asm_multi_destroy(b200asm_multi *m);
+const char *b200asm_multi_last_error(const b200asm_multi *m);
+int b200asm_multi_num_devices(const b200asm_multi *m);
+int b200asm_multi_context(b200asm_multi *m, int k, b200asm_ctx **ctx); /* the context of the k-th device (timing, counters, pointers) */
+int b200asm_multi_set_option(b200asm_multi *m, const char *name, int64_t value);
+int b200asm_multi_set_nodes(b200asm_multi *m, int64_t nnodes, const double *xyz);
+int b200asm_multi_add_group(b200asm_multi *m, const b200asm_group *g); /* global destination indices; copied */
+int b200asm_multi_set_group_coef(b200asm_multi *m, int group, const double coef[16]);
+int b200asm_multi_set_group_force(b200asm_multi *m, int group, const double *force);
+int b200asm_multi_clear_groups(b200asm_multi *m);
+int b200asm_multi_set_pattern(b200asm_multi *m, int64_t neq, const int64_t *ia, const int64_t *ja, int symmetric);
+/* the partition: row_begin[ndev + 1], elements[ndev], staged_entries[ndev] (CSR entries that travel per assembly); NULL = skip */
+int b200asm_multi_partition(const b200asm_multi *m, int64_t *row_begin, int64_t *elements, int64_t *staged_entries);
+int b200asm_multi_assemble(b200asm_multi *m, double *a_host, double *rhs_host);
+int b200asm_multi_assemble_rhs(b200asm_multi *m, double *rhs_host);
+int b200asm_multi_assemble_async(b200asm_multi *m);
+int b200asm_multi_synchronize(b200asm_multi *m);
+int b200asm_multi_counters(const b200asm_multi *m, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* duration (ms, CUDA events on the context stream) of the kernel launches of one group in the LAST assembly;
  * needs option "timing" = 1.  Waits for that group's launches to finish. */
 int b200asm_group_time_ms(b200asm_ctx *ctx, int group, double *ms);

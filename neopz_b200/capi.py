@@ -33,6 +33,11 @@ class Group(C.Structure):
                 ("force", C.POINTER(C.c_double))]
 
 
+class IpcMem(C.Structure):
+    """b200asm_ipc_mem: a cudaIpcMemHandle_t and the offset of the array inside the allocation it names."""
+    _fields_ = [("handle", C.c_ubyte * 64), ("offset", C.c_int64)]
+
+
 _lib = None
 
 # every symbol include/b200asm.h declares (tests/test_capi_symbols.py checks the header against this)
@@ -45,6 +50,13 @@ SYMBOLS = [
     "b200asm_nshape", "b200asm_orientation_keys", "b200asm_shape_tables_oriented",
     "b200asm_build_pattern_device", "b200asm_get_pattern", "b200asm_cg_solve", "b200asm_cg_solution_device",
     "b200asm_assemble_rhs", "b200asm_get_ja_range", "b200asm_pin_host", "b200asm_unpin_host", "b200asm_prism_rule",
+    "b200asm_exchange_export", "b200asm_exchange_add_peer", "b200asm_exchange_set_map", "b200asm_exchange_clear",
+    "b200asm_set_group_force",
+    "b200asm_multi_create", "b200asm_multi_destroy", "b200asm_multi_last_error", "b200asm_multi_num_devices", "b200asm_multi_context",
+    "b200asm_multi_set_option", "b200asm_multi_set_nodes", "b200asm_multi_add_group", "b200asm_multi_set_group_coef",
+    "b200asm_multi_set_group_force", "b200asm_multi_clear_groups", "b200asm_multi_set_pattern", "b200asm_multi_partition",
+    "b200asm_multi_assemble", "b200asm_multi_assemble_rhs", "b200asm_multi_assemble_async", "b200asm_multi_synchronize",
+    "b200asm_multi_counters",
 ]
 
 
@@ -95,6 +107,31 @@ def lib():
     L.b200asm_shape_tables_oriented.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, dp, dp, dp]
     L.b200asm_build_pattern.argtypes = [C.c_int, C.c_int64, ip64, ip64, C.c_int64, ip64, ip64, ip64, ip64, C.c_int]
     L.b200asm_build_pattern.restype = C.c_int64
+    L.b200asm_exchange_export.argtypes = [vp, C.POINTER(IpcMem)]
+    L.b200asm_exchange_add_peer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(IpcMem), vp, C.c_int64]
+    L.b200asm_exchange_set_map.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, ip32, C.c_int64, ip32, ip32]
+    L.b200asm_exchange_clear.argtypes = [vp]
+    L.b200asm_set_group_force.argtypes = [vp, C.c_int, dp]
+    L.b200asm_multi_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]
+    L.b200asm_multi_destroy.argtypes = [vp]
+    L.b200asm_multi_destroy.restype = None
+    L.b200asm_multi_last_error.argtypes = [vp]
+    L.b200asm_multi_last_error.restype = C.c_char_p
+    L.b200asm_multi_num_devices.argtypes = [vp]
+    L.b200asm_multi_context.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.b200asm_multi_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.b200asm_multi_set_nodes.argtypes = [vp, C.c_int64, dp]
+    L.b200asm_multi_add_group.argtypes = [vp, C.POINTER(Group)]
+    L.b200asm_multi_set_group_coef.argtypes = [vp, C.c_int, dp]
+    L.b200asm_multi_set_group_force.argtypes = [vp, C.c_int, dp]
+    L.b200asm_multi_clear_groups.argtypes = [vp]
+    L.b200asm_multi_set_pattern.argtypes = [vp, C.c_int64, ip64, ip64, C.c_int]
+    L.b200asm_multi_partition.argtypes = [vp, ip64, ip64, ip64]
+    L.b200asm_multi_assemble.argtypes = [vp, dp, dp]
+    L.b200asm_multi_assemble_rhs.argtypes = [vp, dp]
+    L.b200asm_multi_assemble_async.argtypes = [vp]
+    L.b200asm_multi_synchronize.argtypes = [vp]
+    L.b200asm_multi_counters.argtypes = [vp, ip64, ip64, ip64]
     _lib = L
     return L
 
@@ -183,6 +220,31 @@ def build_pattern(symmetric, elgraphindex, elgraph, blockpos, blocksize, nthread
     return ia, ja
 
 
+def make_group(topology, porder, kind, nstate, elnodes, dest, qpts, qwts, phi, dphi, coef, force=None):
+    """b200asm_group over numpy arrays; returns (struct, arrays to keep alive during the call)."""
+    elnodes = np.ascontiguousarray(elnodes, dtype=np.int32)
+    dest = np.ascontiguousarray(dest, dtype=np.int64)
+    qpts = np.ascontiguousarray(qpts, dtype=np.float64)
+    qwts = np.ascontiguousarray(qwts, dtype=np.float64)
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    dphi = np.ascontiguousarray(dphi, dtype=np.float64)
+    g = Group()
+    g.topology, g.porder, g.kind, g.nstate = topology, porder, kind, nstate
+    g.nel = elnodes.shape[0]
+    g.elnodes, g.dest = i32ptr(elnodes), i64ptr(dest)
+    g.nqp, g.nshape = len(qwts), phi.shape[1]
+    g.qpts, g.qwts, g.phi, g.dphi = dptr(qpts), dptr(qwts), dptr(phi), dptr(dphi)
+    c = np.zeros(16)
+    c[: len(coef)] = coef
+    g.coef[:] = c.tolist()
+    keep = [elnodes, dest, qpts, qwts, phi, dphi]
+    if force is not None:
+        force = np.ascontiguousarray(force, dtype=np.float64)
+        g.force = dptr(force)
+        keep.append(force)
+    return g, keep
+
+
 # ---- device context ------------------------------------------------------------------------------
 class Context:
     """Owns one b200asm_ctx (one GPU)."""
@@ -222,25 +284,12 @@ class Context:
         self._check(lib().b200asm_set_nodes(self._h, xyz.shape[0], dptr(xyz)))
 
     def add_group(self, topology, porder, kind, nstate, elnodes, dest, qpts, qwts, phi, dphi, coef, force=None):
-        elnodes = np.ascontiguousarray(elnodes, dtype=np.int32)
-        dest = np.ascontiguousarray(dest, dtype=np.int64)
-        qpts = np.ascontiguousarray(qpts, dtype=np.float64)
-        qwts = np.ascontiguousarray(qwts, dtype=np.float64)
-        phi = np.ascontiguousarray(phi, dtype=np.float64)
-        dphi = np.ascontiguousarray(dphi, dtype=np.float64)
-        g = Group()
-        g.topology, g.porder, g.kind, g.nstate = topology, porder, kind, nstate
-        g.nel = elnodes.shape[0]
-        g.elnodes, g.dest = i32ptr(elnodes), i64ptr(dest)
-        g.nqp, g.nshape = len(qwts), phi.shape[1]
-        g.qpts, g.qwts, g.phi, g.dphi = dptr(qpts), dptr(qwts), dptr(phi), dptr(dphi)
-        c = np.zeros(16)
-        c[: len(coef)] = coef
-        g.coef[:] = c.tolist()
-        if force is not None:
-            force = np.ascontiguousarray(force, dtype=np.float64)
-            g.force = dptr(force)
+        g, keep = make_group(topology, porder, kind, nstate, elnodes, dest, qpts, qwts, phi, dphi, coef, force)
         return self._check(lib().b200asm_add_group(self._h, C.byref(g)))
+
+    def set_group_force(self, group, force):
+        force = np.ascontiguousarray(force, dtype=np.float64)
+        self._check(lib().b200asm_set_group_force(self._h, group, dptr(force)))
 
     def set_group_coef(self, group, coef):
         c = np.zeros(16)
@@ -319,6 +368,30 @@ class Context:
         """dst[positions[k]] += values[k] on the device (target 0: CSR values, 1: rhs); raw device pointers."""
         self._check(lib().b200asm_scatter_add(self._h, target, C.c_void_p(positions_dev_ptr), C.c_void_p(values_dev_ptr), n))
 
+    # ---- interface exchange of the row-sharded assembly (include/b200asm.h: b200asm_exchange_*) ----
+    def exchange_export(self):
+        """bytes (3 x 72) naming this context's CSR values, load vector and flag block for a peer in another process."""
+        mem = (IpcMem * 3)()
+        self._check(lib().b200asm_exchange_export(self._h, mem))
+        return bytes(mem)
+
+    def exchange_add_peer(self, push, slot_there, mem_bytes=None, peer=None, incoming_min_row=-1):
+        mem = None
+        if mem_bytes is not None:
+            mem = (IpcMem * 3).from_buffer_copy(mem_bytes)
+        return self._check(lib().b200asm_exchange_add_peer(self._h, int(bool(push)), int(slot_there), mem,
+                                                           peer._h if peer is not None else None, int(incoming_min_row)))
+
+    def exchange_set_map(self, link, a_src0, a_dst, rhs_src, rhs_dst):
+        a_dst = np.ascontiguousarray(a_dst, dtype=np.int32)
+        rhs_src = np.ascontiguousarray(rhs_src, dtype=np.int32)
+        rhs_dst = np.ascontiguousarray(rhs_dst, dtype=np.int32)
+        self._check(lib().b200asm_exchange_set_map(self._h, int(link), len(a_dst), int(a_src0), i32ptr(a_dst), len(rhs_src),
+                                                   i32ptr(rhs_src), i32ptr(rhs_dst)))
+
+    def exchange_clear(self):
+        self._check(lib().b200asm_exchange_clear(self._h))
+
     def device_pointers(self):
         a, r = C.c_void_p(), C.c_void_p()
         self._check(lib().b200asm_device_pointers(self._h, C.byref(a), C.byref(r)))
@@ -333,4 +406,107 @@ class Context:
     def counters(self):
         k, h, d = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(lib().b200asm_counters(self._h, C.byref(k), C.byref(h), C.byref(d)))
+        return k.value, h.value, d.value
+
+
+class _Borrowed(Context):
+    """A context owned by a MultiContext (never destroyed from here)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._keep = []
+        self._neq = 0
+
+    def close(self):
+        self._h = C.c_void_p()
+
+
+class MultiContext:
+    """Owns one b200asm_multi: the same calls as Context on several GPUs of this process (include/b200asm.h)."""
+
+    def __init__(self, devices):
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = lib().b200asm_multi_create(C.byref(self._h), len(devices), devs)
+        if rc != 0:
+            raise B200AsmError(rc, lib().b200asm_multi_last_error(None).decode())
+        self.ndev = len(devices)
+        self._neq = 0
+
+    def _check(self, rc):
+        if rc < 0:
+            raise B200AsmError(rc, lib().b200asm_multi_last_error(self._h).decode())
+        return rc
+
+    def close(self):
+        if self._h:
+            lib().b200asm_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def context(self, k):
+        h = C.c_void_p()
+        self._check(lib().b200asm_multi_context(self._h, k, C.byref(h)))
+        return _Borrowed(h)
+
+    def set_option(self, name, value):
+        self._check(lib().b200asm_multi_set_option(self._h, name.encode(), int(value)))
+
+    def set_nodes(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._check(lib().b200asm_multi_set_nodes(self._h, xyz.shape[0], dptr(xyz)))
+
+    def add_group(self, topology, porder, kind, nstate, elnodes, dest, qpts, qwts, phi, dphi, coef, force=None):
+        g, keep = make_group(topology, porder, kind, nstate, elnodes, dest, qpts, qwts, phi, dphi, coef, force)
+        return self._check(lib().b200asm_multi_add_group(self._h, C.byref(g)))
+
+    def set_group_coef(self, group, coef):
+        c = np.zeros(16)
+        c[: len(coef)] = coef
+        self._check(lib().b200asm_multi_set_group_coef(self._h, group, dptr(c)))
+
+    def set_group_force(self, group, force):
+        force = np.ascontiguousarray(force, dtype=np.float64)
+        self._check(lib().b200asm_multi_set_group_force(self._h, group, dptr(force)))
+
+    def clear_groups(self):
+        self._check(lib().b200asm_multi_clear_groups(self._h))
+
+    def set_pattern(self, ia, ja, symmetric):
+        ia = np.ascontiguousarray(ia, dtype=np.int64)
+        ja = np.ascontiguousarray(ja, dtype=np.int64)
+        self._check(lib().b200asm_multi_set_pattern(self._h, len(ia) - 1, i64ptr(ia), i64ptr(ja), int(bool(symmetric))))
+        self._neq = len(ia) - 1
+
+    def partition(self):
+        """(row_begin[ndev + 1], elements[ndev], staged CSR entries[ndev]) of the current partition."""
+        rb = np.zeros(self.ndev + 1, dtype=np.int64)
+        el = np.zeros(self.ndev, dtype=np.int64)
+        st = np.zeros(self.ndev, dtype=np.int64)
+        self._check(lib().b200asm_multi_partition(self._h, i64ptr(rb), i64ptr(el), i64ptr(st)))
+        return rb, el, st
+
+    def neq(self):
+        return self._neq
+
+    def assemble(self, a_host=None, rhs_host=None):
+        self._check(lib().b200asm_multi_assemble(self._h, dptr(a_host), dptr(rhs_host)))
+
+    def assemble_rhs(self, rhs_host=None):
+        self._check(lib().b200asm_multi_assemble_rhs(self._h, dptr(rhs_host)))
+
+    def assemble_async(self):
+        self._check(lib().b200asm_multi_assemble_async(self._h))
+
+    def synchronize(self):
+        self._check(lib().b200asm_multi_synchronize(self._h))
+
+    def counters(self):
+        k, h, d = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(lib().b200asm_multi_counters(self._h, C.byref(k), C.byref(h), C.byref(d)))
         return k.value, h.value, d.value

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/b200asm.h"
+#include "exchange.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // device-side parameter blocks
@@ -917,7 +918,13 @@ struct Group {
     // smallest destination equation of every chunk (rows below the minimum of all LATER launches are final)
     std::vector<int64_t> chunk;
     std::vector<int64_t> chunk_min;
+    // row-sharded assembly: the elements [0, n_if) touch staging rows (options "staging_lo" / "staging_hi"); they are chunk 0,
+    // launched before everything else so that their contributions travel while the rest is assembled
+    int64_t n_if = 0;
+    std::vector<int64_t> stored_order;  // groups with a force table: mesh index of every stored element (b200asm_set_group_force)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // "timing" option: events around this group's launches
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // ... around the interface prefix, when it is launched apart
+    bool timed_prefix = false;
 };
 
 }  // namespace
@@ -960,6 +967,29 @@ struct b200asm_ctx {
     std::vector<cudaEvent_t> copy_events;
     std::vector<int64_t> ov_upto;  // IA at the download frontiers of assemble_overlapped (valid while ov_valid)
     bool ov_valid = false;
+    // ---- interface exchange with other GPUs (exchange.cuh) ----
+    struct PeerLink {
+        bool push = false;   // this context pushes its staged contributions into the peer (false: the peer pushes into this one)
+        bool ipc = false;    // the pointers come from cudaIpcOpenMemHandle
+        void *ipc_base[3] = {nullptr, nullptr, nullptr};
+        double *a = nullptr, *rhs = nullptr;   // the peer's CSR values / load vector (push links)
+        unsigned long long *flags = nullptr;   // the peer's flag block
+        int slot_there = 0;                    // index of the link to this context in the PEER's table
+        int64_t n_a = 0, a_src0 = 0, n_rhs = 0;
+        int32_t *d_a_dst = nullptr, *d_rhs_src = nullptr, *d_rhs_dst = nullptr;
+    };
+    std::vector<PeerLink> links;
+    unsigned long long *d_flags = nullptr;  // [2][xch::MAX_LINKS]: ZEROED(step) / PUSHED(step) written by the peer of link i
+    int *d_xerr = nullptr;                  // raised by a wait that timed out
+    unsigned long long xstep = 0;           // assemblies so far (every participating context counts the same)
+    int64_t staging_lo = 0, staging_hi = 0; // local rows [lo, hi) are staging rows (owned by a peer)
+    int64_t incoming_min_row = INT64_MAX;   // smallest local row a peer pushes into (caps the early download)
+    int64_t xtimeout_ms = 30000;
+    // window of the local arrays that goes to the host (options "download_a_count", "download_rhs_first",
+    // "download_rhs_count"; -1 = everything): a context of a row-sharded system only returns the rows it owns
+    int64_t dl_a = -1, dl_r0 = 0, dl_rn = -1;
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_if = nullptr, ev_push = nullptr;
     std::string err;
 };
 
@@ -1349,6 +1379,8 @@ void free_group(Group &g) {
     cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad); cudaFree(g.d_aux); cudaFree(g.d_aux2);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
+    if (g.ev2) cudaEventDestroy(g.ev2);
+    if (g.ev3) cudaEventDestroy(g.ev3);
     g = Group();
 }
 
@@ -1470,6 +1502,11 @@ extern "C" void b200asm_destroy(b200asm_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (Group &g : ctx->groups) free_group(g);
+    b200asm_exchange_clear(ctx);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_xerr);
+    if (ctx->xstream) cudaStreamDestroy(ctx->xstream);
+    if (ctx->ev_if) cudaEventDestroy(ctx->ev_if);
+    if (ctx->ev_push) cudaEventDestroy(ctx->ev_push);
     cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
     cudaFree(ctx->d_cg); cudaFree(ctx->d_cg_part); cudaFree(ctx->d_cg_sc);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1528,6 +1565,23 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
     if (!strcmp(name, "affine")) {
         ctx->affine = value ? 1 : 0;
         for (Group &g : ctx->groups) g.aff_checked = false;
+        return 0;
+    }
+    if (!strcmp(name, "staging_lo") || !strcmp(name, "staging_hi")) {
+        if (value < 0) return fail(ctx, B200ASM_EINVAL, "staging rows: must not be negative");
+        if (!ctx->groups.empty()) return fail(ctx, B200ASM_ESTATE, "staging rows: set them before the first b200asm_add_group");
+        (name[8] == 'l' ? ctx->staging_lo : ctx->staging_hi) = value;
+        return 0;
+    }
+    if (!strcmp(name, "download_a_count") || !strcmp(name, "download_rhs_first") || !strcmp(name, "download_rhs_count")) {
+        if (value < -1) return fail(ctx, B200ASM_EINVAL, "download window: bad value");
+        (name[9] == 'a' ? ctx->dl_a : (name[13] == 'f' ? ctx->dl_r0 : ctx->dl_rn)) = value;
+        ctx->ov_valid = false;
+        return 0;
+    }
+    if (!strcmp(name, "exchange_timeout_ms")) {
+        if (value < 1) return fail(ctx, B200ASM_EINVAL, "exchange_timeout_ms: must be positive");
+        ctx->xtimeout_ms = value;
         return 0;
     }
     if (!strcmp(name, "overlap_min_elements")) {
@@ -1637,15 +1691,37 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         std::vector<int64_t> cursor(count.begin(), count.end() - 1);
         for (int64_t e = 0; e < g.nel; e++) order[cursor[colour[e]]++] = e;  // stable within a colour
     }
+    // row-sharded assembly: elements with an equation among the staging rows come first (stable otherwise) and form chunk 0,
+    // rounded up to the chunk alignment; coloured groups keep their colour order (their contributions are pushed after the
+    // last launch instead of early)
+    constexpr int64_t kAlign = 384;
+    if (ctx->staging_hi > ctx->staging_lo && g.seg.size() == 2 && g.nel > 0) {
+        std::vector<int64_t> first, rest;
+        for (int64_t e = 0; e < g.nel; e++) {
+            bool hit = false;
+            for (int k = 0; k < g.m && !hit; k++) {
+                const int64_t d = gi->dest[e * g.m + k];
+                hit = d >= ctx->staging_lo && d < ctx->staging_hi;
+            }
+            (hit ? first : rest).push_back(e);
+        }
+        if (!first.empty()) {
+            g.n_if = std::min<int64_t>(g.nel, ((int64_t)first.size() + kAlign - 1) / kAlign * kAlign);
+            std::copy(first.begin(), first.end(), order.begin());
+            std::copy(rest.begin(), rest.end(), order.begin() + (int64_t)first.size());
+        }
+    }
     // element chunks for the overlapped download: boundaries are multiples of every kernel's batch size
     {
-        constexpr int64_t kAlign = 384, kMaxChunks = 16;
+        constexpr int64_t kMaxChunks = 16;
+        const int64_t nrest = g.nel - g.n_if;
         int64_t nch = 1;
-        if (volume && g.seg.size() == 2) nch = std::max<int64_t>(1, std::min<int64_t>(kMaxChunks, g.nel / ctx->overlap_min_elements));
+        if (volume && g.seg.size() == 2) nch = std::max<int64_t>(1, std::min<int64_t>(kMaxChunks, nrest / ctx->overlap_min_elements));
         g.chunk.assign(1, 0);
+        if (g.n_if > 0 && g.n_if < g.nel) g.chunk.push_back(g.n_if);
         for (int64_t c = 1; c < nch; c++) {
-            const int64_t b = (g.nel * c / nch) / kAlign * kAlign;
-            if (b > g.chunk.back()) g.chunk.push_back(b);
+            const int64_t b = g.n_if + (nrest * c / nch) / kAlign * kAlign;
+            if (b > g.chunk.back() && b < g.nel) g.chunk.push_back(b);
         }
         g.chunk.push_back(g.nel);
     }
@@ -1688,7 +1764,8 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             std::vector<std::pair<uint64_t, int64_t>> keyed;
             for (size_t c = 0; c + 1 < g.chunk.size(); c++) {
                 keyed.clear();
-                for (int64_t e = g.chunk[c]; e < g.chunk[c + 1]; e++) {
+                for (int64_t k = g.chunk[c]; k < g.chunk[c + 1]; k++) {
+                    const int64_t e = order[k];  // (the interface prefix has already permuted the elements)
                     uint64_t key = 0;
                     for (int r = 0; r < 3; r++) key |= spread((uint64_t)((cen[(size_t)e * 3 + r] - lo[r]) * scale)) << r;
                     keyed.emplace_back(key, e);
@@ -1789,6 +1866,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         force.resize((size_t)g.nel * per);
         for (int64_t e = 0; e < g.nel; e++) memcpy(&force[(size_t)e * per], gi->force + (size_t)order[e] * per, per * sizeof(double));
         if ((rc = upload(ctx, &g.d_force, force.data(), force.size()))) return rc;
+        g.stored_order = order;
     }
     CK(cudaStreamSynchronize(ctx->stream));  // dest32 / dng are stack-owned
     ctx->groups.push_back(g);
@@ -1799,6 +1877,22 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
 extern "C" int b200asm_set_group_coef(b200asm_ctx *ctx, int group, const double coef[16]) {
     if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !coef) return fail(ctx, B200ASM_EINVAL, "set_group_coef: bad arguments");
     memcpy(ctx->groups[group].coef, coef, sizeof(double) * 16);
+    return 0;
+}
+
+extern "C" int b200asm_set_group_force(b200asm_ctx *ctx, int group, const double *force) {
+    if (!ctx || group < 0 || group >= (int)ctx->groups.size()) return fail(ctx, B200ASM_EINVAL, "set_group_force: bad arguments");
+    Group &g = ctx->groups[group];
+    if ((force != nullptr) != (g.d_force != nullptr))
+        return fail(ctx, B200ASM_EINVAL, "set_group_force: the group was added with / without a table (clear the groups to change that)");
+    if (!force) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t per = (size_t)g.nq * g.ns;
+    std::vector<double> tmp((size_t)g.nel * per);
+    for (int64_t e = 0; e < g.nel; e++) memcpy(&tmp[(size_t)e * per], force + (size_t)g.stored_order[e] * per, per * sizeof(double));
+    CK(cudaMemcpyAsync(g.d_force, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += (int64_t)(tmp.size() * sizeof(double));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1813,6 +1907,7 @@ extern "C" int b200asm_clear_groups(b200asm_ctx *ctx) {
 
 namespace {
 void drop_pattern(b200asm_ctx *ctx) {
+    b200asm_exchange_clear(ctx);  // (peers map the arrays of the pattern that goes away)
     cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs);
     ctx->d_ia = nullptr; ctx->d_ja = nullptr; ctx->d_a = ctx->d_rhs = nullptr;
     ctx->have_pattern = false;
@@ -2088,18 +2183,150 @@ int begin_assembly(b200asm_ctx *ctx) {
 
 }  // namespace
 
+namespace {
+
+// One launch unit of an assembly: a whole group (r0 < 0) or the element range [r0, r1) of it.  Order: the interface prefixes of
+// all groups (their contributions are pushed to the owning GPUs behind them), the small groups, then the element chunks of the
+// large volume groups in element order (the order the overlapped download relies on).
+struct Unit { int group; int64_t r0, r1, min_dest; bool prefix; };
+
+void build_units(const b200asm_ctx *ctx, std::vector<Unit> &units, size_t &nprefix) {
+    units.clear();
+    for (size_t gi = 0; gi < ctx->groups.size(); gi++) {
+        const Group &g = ctx->groups[gi];
+        if (g.nel == 0 || g.n_if == 0) continue;
+        units.push_back({(int)gi, 0, g.chunk[1], g.chunk_min[0], true});
+    }
+    nprefix = units.size();
+    for (int pass = 0; pass < 2; pass++)
+        for (size_t gi = 0; gi < ctx->groups.size(); gi++) {
+            const Group &g = ctx->groups[gi];
+            if (g.nel == 0) continue;
+            const bool chunked = g.chunk.size() > 2;
+            if (chunked != (pass == 1)) continue;
+            if (!chunked) {
+                if (g.n_if == 0) units.push_back({(int)gi, -1, -1, g.chunk_min.empty() ? 0 : g.chunk_min[0], false});
+            } else {
+                for (size_t c = g.n_if > 0 ? 1 : 0; c + 1 < g.chunk.size(); c++)
+                    units.push_back({(int)gi, g.chunk[c], g.chunk[c + 1], g.chunk_min[c], false});
+            }
+        }
+}
+
+// after the memsets of begin_assembly: tell every GPU that pushes into this one that the arrays are zeroed
+int exchange_signal_zeroed(b200asm_ctx *ctx) {
+    for (const b200asm_ctx::PeerLink &l : ctx->links) {
+        if (l.push) continue;
+        xch::signal_kernel<<<1, 1, 0, ctx->stream>>>(l.flags + l.slot_there, ctx->xstep);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    return 0;
+}
+
+// behind the interface elements: push the staged contributions on the side stream (waits for the owner's ZEROED signal first)
+int exchange_push(b200asm_ctx *ctx) {
+    bool any = false;
+    for (const b200asm_ctx::PeerLink &l : ctx->links) any = any || l.push;
+    if (!any) return 0;
+    if (!ctx->xstream) {
+        CK(cudaStreamCreateWithFlags(&ctx->xstream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_if, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_push, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ctx->ev_if, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->xstream, ctx->ev_if, 0));
+    const unsigned long long timeout_ns = (unsigned long long)ctx->xtimeout_ms * 1000000ull;
+    for (size_t i = 0; i < ctx->links.size(); i++) {
+        const b200asm_ctx::PeerLink &l = ctx->links[i];
+        if (!l.push) continue;
+        xch::wait_kernel<<<1, 1, 0, ctx->xstream>>>(ctx->d_flags + i, ctx->xstep, timeout_ns, ctx->d_xerr);
+        if (l.n_a && !ctx->rhs_only)
+            xch::push_values_kernel<<<grid_for(ctx, l.n_a, 256), 256, 0, ctx->xstream>>>(l.a, l.d_a_dst, ctx->d_a + l.a_src0, l.n_a);
+        if (l.n_rhs)
+            xch::push_gather_kernel<<<grid_for(ctx, l.n_rhs, 256), 256, 0, ctx->xstream>>>(l.rhs, l.d_rhs_dst, ctx->d_rhs, l.d_rhs_src, l.n_rhs);
+        xch::signal_kernel<<<1, 1, 0, ctx->xstream>>>(l.flags + xch::MAX_LINKS + l.slot_there, ctx->xstep);
+        CK(cudaGetLastError());
+        ctx->launches += 4;
+    }
+    CK(cudaEventRecord(ctx->ev_push, ctx->xstream));
+    return 0;
+}
+
+// end of the step on the main stream: the own pushes are done (the staging rows may be zeroed again) and every peer that pushes
+// into this context has delivered: the owned rows are complete
+int exchange_finish(b200asm_ctx *ctx) {
+    bool any = false;
+    for (const b200asm_ctx::PeerLink &l : ctx->links) any = any || l.push;
+    if (any) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_push, 0));
+    const unsigned long long timeout_ns = (unsigned long long)ctx->xtimeout_ms * 1000000ull;
+    for (size_t i = 0; i < ctx->links.size(); i++) {
+        if (ctx->links[i].push) continue;
+        xch::wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_flags + xch::MAX_LINKS + i, ctx->xstep, timeout_ns, ctx->d_xerr);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int64_t dl_nnz(const b200asm_ctx *ctx) { return ctx->dl_a < 0 ? ctx->nnz : std::min(ctx->dl_a, ctx->nnz); }
+int64_t dl_rhs_first(const b200asm_ctx *ctx) { return std::min(std::max<int64_t>(ctx->dl_r0, 0), ctx->neq); }
+int64_t dl_rhs_count(const b200asm_ctx *ctx) {
+    const int64_t f = dl_rhs_first(ctx);
+    return ctx->dl_rn < 0 ? ctx->neq - f : std::min(ctx->dl_rn, ctx->neq - f);
+}
+
+int check_exchange_error(b200asm_ctx *ctx) {
+    if (ctx->links.empty()) return 0;
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, ctx->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        CK(cudaMemsetAsync(ctx->d_xerr, 0, sizeof(int), ctx->stream));
+        return fail(ctx, B200ASM_ECUDA, "interface exchange: a peer GPU did not signal within the timeout (do all contexts assemble the same number of times?)");
+    }
+    return 0;
+}
+
+// events of the "timing" option around the launches of a group (prefix and remainder apart: other groups run in between)
+int time_mark(b200asm_ctx *ctx, Group &g, bool prefix, bool begin) {
+    if (!g.ev0) {
+        CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); CK(cudaEventCreate(&g.ev2)); CK(cudaEventCreate(&g.ev3));
+    }
+    CK(cudaEventRecord(prefix ? (begin ? g.ev2 : g.ev3) : (begin ? g.ev0 : g.ev1), ctx->stream));
+    if (prefix) g.timed_prefix = true;
+    return 0;
+}
+
+}  // namespace
+
 extern "C" int b200asm_assemble_async(b200asm_ctx *ctx) {
     if (!ctx) return B200ASM_EINVAL;
     int rc = begin_assembly(ctx);
     if (rc) return rc;
-    for (Group &g : ctx->groups) {
-        if (g.nel == 0) continue;
-        if (ctx->timing) {
-            if (!g.ev0) { CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); }
-            CK(cudaEventRecord(g.ev0, ctx->stream));
+    ctx->xstep++;
+    if ((rc = exchange_signal_zeroed(ctx))) return rc;
+    std::vector<Unit> units;
+    size_t nprefix = 0;
+    build_units(ctx, units, nprefix);
+    for (Group &g : ctx->groups) g.timed_prefix = false;
+    bool pushed = false;
+    for (size_t u = 0; u <= units.size(); u++) {
+        if (u == nprefix && !ctx->links.empty() && nprefix > 0) {  // every interface element has been launched
+            if ((rc = exchange_push(ctx))) return rc;
+            pushed = true;
         }
-        if ((rc = enqueue_group(ctx, g, -1, -1))) return rc;
-        if (ctx->timing) CK(cudaEventRecord(g.ev1, ctx->stream));
+        if (u == units.size()) break;
+        Group &g = ctx->groups[units[u].group];
+        const bool first_of_group = u == 0 || units[u - 1].group != units[u].group || units[u - 1].prefix != units[u].prefix;
+        const bool last_of_group = u + 1 == units.size() || units[u + 1].group != units[u].group || units[u + 1].prefix != units[u].prefix;
+        if (ctx->timing && first_of_group && (rc = time_mark(ctx, g, units[u].prefix, true))) return rc;
+        if ((rc = enqueue_group(ctx, g, units[u].r0, units[u].r1))) return rc;
+        if (ctx->timing && last_of_group && (rc = time_mark(ctx, g, units[u].prefix, false))) return rc;
+    }
+    if (!ctx->links.empty()) {
+        if (!pushed && (rc = exchange_push(ctx))) return rc;  // (coloured groups / no prefix: push behind the last launch)
+        if ((rc = exchange_finish(ctx))) return rc;
     }
     return 0;
 }
@@ -2109,32 +2336,37 @@ extern "C" int b200asm_group_time_ms(b200asm_ctx *ctx, int group, double *ms) {
     const Group &g = ctx->groups[group];
     if (!g.ev0) return fail(ctx, B200ASM_ESTATE, "group_time_ms: set option \"timing\" = 1 and assemble first");
     CK(cudaEventSynchronize(g.ev1));
-    float t = 0.f;
+    float t = 0.f, tp = 0.f;
     CK(cudaEventElapsedTime(&t, g.ev0, g.ev1));
-    *ms = t;
+    if (g.timed_prefix) {
+        CK(cudaEventSynchronize(g.ev3));
+        CK(cudaEventElapsedTime(&tp, g.ev2, g.ev3));
+    }
+    *ms = (double)t + (double)tp;
     return 0;
 }
 
 extern "C" int b200asm_synchronize(b200asm_ctx *ctx) {
     if (!ctx) return B200ASM_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return check_exchange_error(ctx);
 }
 
 extern "C" int b200asm_download(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
     if (!ctx) return B200ASM_EINVAL;
     if (!ctx->d_a) return fail(ctx, B200ASM_ESTATE, "download: nothing assembled");
     CK(cudaSetDevice(ctx->device));
-    if (a_host) {
-        CK(cudaMemcpyAsync(a_host, ctx->d_a, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h += ctx->nnz * (int64_t)sizeof(double);
+    if (a_host && dl_nnz(ctx)) {
+        CK(cudaMemcpyAsync(a_host, ctx->d_a, (size_t)dl_nnz(ctx) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += dl_nnz(ctx) * (int64_t)sizeof(double);
     }
-    if (rhs_host) {
-        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs, (size_t)ctx->neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h += ctx->neq * (int64_t)sizeof(double);
+    if (rhs_host && dl_rhs_count(ctx)) {
+        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs + dl_rhs_first(ctx), (size_t)dl_rhs_count(ctx) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += dl_rhs_count(ctx) * (int64_t)sizeof(double);
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return check_exchange_error(ctx);
 }
 
 namespace {
@@ -2148,22 +2380,14 @@ namespace {
 int assemble_overlapped(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
     int rc = begin_assembly(ctx);
     if (rc) return rc;
-    struct Unit { int group; int64_t r0, r1, min_dest; };
+    ctx->xstep++;
+    if ((rc = exchange_signal_zeroed(ctx))) return rc;
     std::vector<Unit> units;
-    for (int pass = 0; pass < 2; pass++)
-        for (size_t gi = 0; gi < ctx->groups.size(); gi++) {
-            const Group &g = ctx->groups[gi];
-            if (g.nel == 0) continue;
-            const bool chunked = g.chunk.size() > 2;
-            if (chunked != (pass == 1)) continue;
-            if (!chunked) {
-                units.push_back({(int)gi, -1, -1, g.chunk_min.empty() ? 0 : g.chunk_min[0]});
-            } else {
-                for (size_t c = 0; c + 1 < g.chunk.size(); c++) units.push_back({(int)gi, g.chunk[c], g.chunk[c + 1], g.chunk_min[c]});
-            }
-        }
-    // frontier[u] = first row that a unit after u may still touch
-    std::vector<int64_t> frontier(units.size(), ctx->neq);
+    size_t nprefix = 0;
+    build_units(ctx, units, nprefix);
+    for (Group &g : ctx->groups) g.timed_prefix = false;
+    // frontier[u] = first row that a unit after u (or a peer GPU pushing into this one) may still touch
+    std::vector<int64_t> frontier(units.size(), std::min(ctx->neq, ctx->incoming_min_row));
     for (int64_t u = (int64_t)units.size() - 2; u >= 0; u--)
         frontier[u] = std::min(frontier[u + 1], std::min<int64_t>(units[u + 1].min_dest, ctx->neq));
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -2177,20 +2401,23 @@ int assemble_overlapped(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
         ctx->ov_valid = true;
     }
     const int64_t kMinCopy = std::max<int64_t>(1, ctx->overlap_min_bytes / (int64_t)sizeof(double));
+    // staging rows never go to the host early: their values are partial sums that belong to another GPU
     int64_t done = 0;                               // entries of A already queued for download
     size_t nev = 0;
+    bool pushed = false;
     for (size_t u = 0; u < units.size(); u++) {
-        Group &g = ctx->groups[units[u].group];
-        const bool first_of_group = u == 0 || units[u - 1].group != units[u].group;
-        const bool last_of_group = u + 1 == units.size() || units[u + 1].group != units[u].group;
-        if (ctx->timing && first_of_group) {
-            if (!g.ev0) { CK(cudaEventCreate(&g.ev0)); CK(cudaEventCreate(&g.ev1)); }
-            CK(cudaEventRecord(g.ev0, ctx->stream));
+        if (u == nprefix && !ctx->links.empty() && nprefix > 0) {
+            if ((rc = exchange_push(ctx))) return rc;
+            pushed = true;
         }
+        Group &g = ctx->groups[units[u].group];
+        const bool first_of_group = u == 0 || units[u - 1].group != units[u].group || units[u - 1].prefix != units[u].prefix;
+        const bool last_of_group = u + 1 == units.size() || units[u + 1].group != units[u].group || units[u + 1].prefix != units[u].prefix;
+        if (ctx->timing && first_of_group && (rc = time_mark(ctx, g, units[u].prefix, true))) return rc;
         if ((rc = enqueue_group(ctx, g, units[u].r0, units[u].r1))) return rc;
-        if (ctx->timing && last_of_group) CK(cudaEventRecord(g.ev1, ctx->stream));
+        if (ctx->timing && last_of_group && (rc = time_mark(ctx, g, units[u].prefix, false))) return rc;
         if (u + 1 == units.size()) break;
-        const int64_t upto = ctx->ov_upto[u];
+        const int64_t upto = std::min(ctx->ov_upto[u], dl_nnz(ctx));
         if (upto - done < kMinCopy) continue;
         if (nev == ctx->copy_events.size()) {
             cudaEvent_t e;
@@ -2203,7 +2430,11 @@ int assemble_overlapped(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
         CK(cudaMemcpyAsync(a_host + done, ctx->d_a + done, (size_t)(upto - done) * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
         done = upto;
     }
-    // the rest of A and the load vector behind the last kernel
+    if (!ctx->links.empty()) {
+        if (!pushed && (rc = exchange_push(ctx))) return rc;
+        if ((rc = exchange_finish(ctx))) return rc;
+    }
+    // the rest of A and the load vector behind the last kernel (and the last incoming push)
     if (nev == ctx->copy_events.size()) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2211,16 +2442,16 @@ int assemble_overlapped(b200asm_ctx *ctx, double *a_host, double *rhs_host) {
     }
     CK(cudaEventRecord(ctx->copy_events[nev], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[nev], 0));
-    if (ctx->nnz > done)
-        CK(cudaMemcpyAsync(a_host + done, ctx->d_a + done, (size_t)(ctx->nnz - done) * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
-    ctx->d2h += ctx->nnz * (int64_t)sizeof(double);
-    if (rhs_host) {
-        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs, (size_t)ctx->neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
-        ctx->d2h += ctx->neq * (int64_t)sizeof(double);
+    if (dl_nnz(ctx) > done)
+        CK(cudaMemcpyAsync(a_host + done, ctx->d_a + done, (size_t)(dl_nnz(ctx) - done) * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->d2h += dl_nnz(ctx) * (int64_t)sizeof(double);
+    if (rhs_host && dl_rhs_count(ctx)) {
+        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs + dl_rhs_first(ctx), (size_t)dl_rhs_count(ctx) * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->d2h += dl_rhs_count(ctx) * (int64_t)sizeof(double);
     }
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return check_exchange_error(ctx);
 }
 
 }  // namespace
@@ -2274,11 +2505,153 @@ extern "C" int b200asm_assemble_rhs(b200asm_ctx *ctx, double *rhs_host) {
     int rc = b200asm_assemble_async(ctx);
     ctx->rhs_only = 0;
     if (rc) return rc;
-    if (rhs_host) {
-        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs, (size_t)ctx->neq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h += ctx->neq * (int64_t)sizeof(double);
+    if (rhs_host && dl_rhs_count(ctx)) {
+        CK(cudaMemcpyAsync(rhs_host, ctx->d_rhs + dl_rhs_first(ctx), (size_t)dl_rhs_count(ctx) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += dl_rhs_count(ctx) * (int64_t)sizeof(double);
         CK(cudaStreamSynchronize(ctx->stream));
+        return check_exchange_error(ctx);
     }
+    return 0;
+}
+
+
+// ---- multi-GPU: interface exchange over peer memory --------------------------------------------------------------
+namespace {
+void free_links(b200asm_ctx *ctx) {
+    for (b200asm_ctx::PeerLink &l : ctx->links) {
+        cudaFree(l.d_a_dst); cudaFree(l.d_rhs_src); cudaFree(l.d_rhs_dst);
+        if (l.ipc)
+            for (void *b : l.ipc_base)
+                if (b) cudaIpcCloseMemHandle(b);
+    }
+    ctx->links.clear();
+    ctx->incoming_min_row = INT64_MAX;
+}
+int ensure_flags(b200asm_ctx *ctx) {
+    if (ctx->d_flags) return 0;
+    CK(cudaMalloc((void **)&ctx->d_flags, 2 * xch::MAX_LINKS * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&ctx->d_xerr, sizeof(int)));
+    CK(cudaMemset(ctx->d_flags, 0, 2 * xch::MAX_LINKS * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->d_xerr, 0, sizeof(int)));
+    return 0;
+}
+// cuMemGetAddressRange through the runtime's driver entry-point query (the library does not link libcuda: it must load on
+// hosts without a driver for the host-side helpers)
+int cuMemGetAddressRange_shim(void **base, size_t *size, void *ptr) {
+    typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
+    static fn_t fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return -1;
+        fn = (fn_t)f;
+    }
+    unsigned long long b = 0;
+    size_t sz = 0;
+    if (fn(&b, &sz, (unsigned long long)(uintptr_t)ptr) != 0) return -1;
+    *base = (void *)(uintptr_t)b;
+    *size = sz;
+    return 0;
+}
+int export_one(b200asm_ctx *ctx, void *ptr, b200asm_ipc_mem *out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(out->handle), "b200asm_ipc_mem::handle holds a cudaIpcMemHandle_t");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(out->handle, &h, sizeof(h));
+    // the handle names the whole allocation the pointer lies in: the importer adds the offset
+    void *base = nullptr;
+    size_t size = 0;
+    if (cuMemGetAddressRange_shim(&base, &size, ptr) != 0) return fail(ctx, B200ASM_ECUDA, "exchange_export: address range query failed");
+    out->offset = (int64_t)((char *)ptr - (char *)base);
+    return 0;
+}
+}  // namespace
+
+extern "C" int b200asm_exchange_export(b200asm_ctx *ctx, b200asm_ipc_mem out[3]) {
+    if (!ctx || !out) return B200ASM_EINVAL;
+    if (!ctx->have_pattern || !ctx->d_a || !ctx->d_rhs) return fail(ctx, B200ASM_ESTATE, "exchange_export: create the pattern first (it allocates the arrays the peers map)");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_flags(ctx))) return rc;
+    if ((rc = export_one(ctx, ctx->d_a, &out[0])) || (rc = export_one(ctx, ctx->d_rhs, &out[1])) || (rc = export_one(ctx, ctx->d_flags, &out[2]))) return rc;
+    return 0;
+}
+
+extern "C" int b200asm_exchange_add_peer(b200asm_ctx *ctx, int push, int slot_there, const b200asm_ipc_mem mem[3], b200asm_ctx *peer,
+                                         int64_t incoming_min_row) {
+    if (!ctx || slot_there < 0 || slot_there >= xch::MAX_LINKS || (!mem == !peer)) return fail(ctx, B200ASM_EINVAL, "exchange_add_peer: bad arguments (give IPC handles or a context of this process)");
+    if ((int)ctx->links.size() >= xch::MAX_LINKS) return fail(ctx, B200ASM_EINVAL, "exchange_add_peer: too many peers");
+    if (!ctx->have_pattern) return fail(ctx, B200ASM_ESTATE, "exchange_add_peer: create the pattern first");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_flags(ctx))) return rc;
+    b200asm_ctx::PeerLink l;
+    l.push = push != 0;
+    l.slot_there = slot_there;
+    if (peer) {
+        if (peer == ctx) return fail(ctx, B200ASM_EINVAL, "exchange_add_peer: a context cannot be its own peer");
+        if (!peer->have_pattern) return fail(ctx, B200ASM_ESTATE, "exchange_add_peer: the peer has no pattern yet");
+        if (peer->device != ctx->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+            if (!can) return fail(ctx, B200ASM_ECUDA, "exchange_add_peer: no peer access between the two devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, B200ASM_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        CK(cudaSetDevice(peer->device));
+        if ((rc = ensure_flags(peer))) { cudaSetDevice(ctx->device); return fail(ctx, rc, peer->err); }
+        CK(cudaSetDevice(ctx->device));
+        l.a = peer->d_a; l.rhs = peer->d_rhs; l.flags = peer->d_flags;
+    } else {
+        l.ipc = true;
+        void **dst[3] = {(void **)&l.a, (void **)&l.rhs, (void **)&l.flags};
+        for (int k = 0; k < 3; k++) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, mem[k].handle, sizeof(h));
+            cudaError_t e = cudaIpcOpenMemHandle(&l.ipc_base[k], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int j = 0; j < k; j++) cudaIpcCloseMemHandle(l.ipc_base[j]);
+                return fail(ctx, B200ASM_ECUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+            *dst[k] = (char *)l.ipc_base[k] + mem[k].offset;
+        }
+    }
+    if (!l.push && incoming_min_row >= 0) ctx->incoming_min_row = std::min(ctx->incoming_min_row, incoming_min_row);
+    ctx->links.push_back(l);
+    ctx->ov_valid = false;
+    return (int)ctx->links.size() - 1;
+}
+
+extern "C" int b200asm_exchange_set_map(b200asm_ctx *ctx, int link, int64_t n_a, int64_t a_src0, const int32_t *a_dst, int64_t n_rhs,
+                                        const int32_t *rhs_src, const int32_t *rhs_dst) {
+    if (!ctx || link < 0 || link >= (int)ctx->links.size() || n_a < 0 || n_rhs < 0 || (n_a && !a_dst) || (n_rhs && (!rhs_src || !rhs_dst)))
+        return fail(ctx, B200ASM_EINVAL, "exchange_set_map: bad arguments");
+    b200asm_ctx::PeerLink &l = ctx->links[link];
+    if (!l.push) return fail(ctx, B200ASM_EINVAL, "exchange_set_map: the link does not push");
+    if (a_src0 < 0 || a_src0 + n_a > ctx->nnz) return fail(ctx, B200ASM_EINVAL, "exchange_set_map: staging segment exceeds the CSR values");
+    for (int64_t k = 0; k < n_rhs; k++)
+        if (rhs_src[k] < 0 || rhs_src[k] >= ctx->neq) return fail(ctx, B200ASM_EINVAL, "exchange_set_map: rhs source out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaFree(l.d_a_dst); cudaFree(l.d_rhs_src); cudaFree(l.d_rhs_dst);
+    l.d_a_dst = l.d_rhs_src = l.d_rhs_dst = nullptr;
+    int rc;
+    if ((rc = upload(ctx, &l.d_a_dst, a_dst, (size_t)n_a)) || (rc = upload(ctx, &l.d_rhs_src, rhs_src, (size_t)n_rhs)) ||
+        (rc = upload(ctx, &l.d_rhs_dst, rhs_dst, (size_t)n_rhs)))
+        return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    l.n_a = n_a; l.a_src0 = a_src0; l.n_rhs = n_rhs;
+    return 0;
+}
+
+extern "C" int b200asm_exchange_clear(b200asm_ctx *ctx) {
+    if (!ctx) return B200ASM_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->xstream) cudaStreamSynchronize(ctx->xstream);
+    free_links(ctx);
+    ctx->xstep = 0;
+    if (ctx->d_flags) cudaMemset(ctx->d_flags, 0, 2 * xch::MAX_LINKS * sizeof(unsigned long long));
     return 0;
 }
 

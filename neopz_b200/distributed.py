@@ -14,10 +14,16 @@ The complete pattern of the own rows needs the first element layer of slab r+1 (
 columns"); no rank ever builds the global mesh: a rank flattens its slab plus one halo layer on each side
 and derives the global equation numbers from the (affine in the layer count) size of the mesh below it.
 
-Exchange.  Ghost rows come first in the local CSR, so the send buffer IS the prefix A[0:nnz_ghost] (and
-rhs[0:nghost]) — nothing is packed.  The receiver adds the buffer into its own rows through a position map
-agreed at setup (only doubles travel at assembly time): torch.distributed send/recv (NCCL over NVLink) +
-b200asm_scatter_add on the device.
+Exchange.  Ghost rows come first in the local CSR, so the staged contributions ARE the prefix A[0:nnz_ghost] (and
+rhs[0:nghost]) — nothing is packed; their positions in the owner's CSR are agreed at setup, only doubles travel at
+assembly time.  Two transports:
+  * exchange="p2p" (default on GPUs): the C ABI's own exchange (include/b200asm.h, b200asm_exchange_*; csrc/exchange.cuh).
+    Every rank maps the arrays of the rank below with CUDA IPC; the elements that touch ghost rows are launched first
+    and a push kernel on a side stream adds the staged values straight into the owner's memory over NVLink while the
+    interior elements are still being assembled; ranks order themselves with step counters in device memory.
+    torch.distributed only carries the setup (sizes, index arrays, IPC handles).
+  * exchange="nccl": torch.distributed send/recv of the prefix after the kernels + b200asm_scatter_add on the receiver
+    (round 1's path; also what the CPU tests run over gloo with an injected local assembler).
 """
 from dataclasses import dataclass
 
@@ -209,9 +215,11 @@ class ShardedStructMatrix:
     inject the oracle and run the exchange over gloo)."""
 
     def __init__(self, slab: SlabMesh, materials, symmetric=True, device=0, local_assembler=None, nthreads=0, engine=None,
-                 scatter=None, pattern="host", variant=None):
+                 scatter=None, pattern="host", variant=None, exchange=None):
         """pattern: "host" (threaded host builder, IA/JA kept on the host) or "device" (b200asm_build_pattern_device: the
-        column indices stay on the GPU, only the interface rows are ever copied back)."""
+        column indices stay on the GPU, only the interface rows are ever copied back).
+        exchange: "p2p" (default with the CUDA backend) or "nccl", see the module docstring.  With "nccl" the context runs on
+        torch's current stream (the collectives order themselves against that stream only)."""
         import torch.distributed as dist
         self.dist = dist
         self.slab = slab
@@ -219,10 +227,18 @@ class ShardedStructMatrix:
         self.symmetric = symmetric
         self.local_assembler = local_assembler
         self.strmat = None
+        self.exchange = exchange or ("p2p" if local_assembler is None else "nccl")
         if local_assembler is None:
+            import torch
             from .strmatrix import TPZStructMatrixB200
             self.strmat = TPZStructMatrixB200(slab.mesh, materials, symmetric=symmetric, device=device, nthreads=nthreads,
                                               engine=engine, scatter=scatter, variant=variant)
+            if self.exchange == "p2p":
+                # the elements that touch ghost rows (local rows [0, nghost)) are stored and launched first
+                self.strmat.ctx.set_option("staging_lo", 0)
+                self.strmat.ctx.set_option("staging_hi", slab.nghost)
+            else:
+                self.strmat.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         self.pattern = pattern if local_assembler is None else "host"
         self.nthreads = nthreads
         self.ia = self.ja = None
@@ -282,23 +298,66 @@ class ShardedStructMatrix:
             g_eq, g_ia, g_ja = [t.cpu().numpy() for t in bufs]
             self.a_map, self.rhs_map = build_recv_maps(s, self.ia, ja_fetch if ja_fetch else self.ja, g_eq, g_ia, g_ja)
             self.recv_nnz, self.recv_neq = len(self.a_map), len(self.rhs_map)
-            if self.strmat is not None:
+            if self.strmat is not None and self.exchange == "nccl":
                 self.a_map_dev = torch.from_numpy(self.a_map).to(dev)
                 self.rhs_map_dev = torch.from_numpy(self.rhs_map).to(dev)
                 self.recv_a = torch.empty(self.recv_nnz, dtype=torch.float64, device=dev)
                 self.recv_rhs = torch.empty(self.recv_neq, dtype=torch.float64, device=dev)
-        if self.strmat is not None:
+        if self.strmat is not None and self.exchange == "p2p":
+            self._attach_peers(dev)
+        elif self.strmat is not None:
             a_ptr, r_ptr = self.strmat.ctx.device_pointers()
             self.a_view = _device_view(a_ptr, self.nnz)
             self.rhs_view = _device_view(r_ptr, s.mesh.neq)
         return self.ia, self.ja
+
+    def _attach_peers(self, dev):
+        """p2p exchange: the owner of the ghost rows (rank - 1) tells this rank where its staged entries go, every rank maps
+        the arrays of its neighbours (CUDA IPC handles travel through torch.distributed) and declares the links.
+        Link order of a rank: [push link to rank - 1], [incoming link from rank + 1]."""
+        import torch
+        dist = self.dist
+        s = self.slab
+        ctx = self.strmat.ctx
+        up, down = s.rank + 1, s.rank - 1
+        handles = [None] * s.world
+        dist.all_gather_object(handles, ctx.exchange_export())
+        # position maps travel back to the sender
+        reqs, keep = [], []
+        if up < s.world:
+            for arr in (self.a_map, self.rhs_map):
+                t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)).to(dev)
+                keep.append(t)
+                reqs.append(dist.isend(t, up))
+        if down >= 0:
+            a_dst = torch.empty(self.nnz_ghost, dtype=torch.int32, device=dev)
+            rhs_dst = torch.empty(s.nghost, dtype=torch.int32, device=dev)
+            reqs += [dist.irecv(a_dst, down), dist.irecv(rhs_dst, down)]
+        for r in reqs:
+            r.wait()
+        if down >= 0:
+            link = ctx.exchange_add_peer(True, slot_there=(1 if down > 0 else 0), mem_bytes=handles[down])
+            ctx.exchange_set_map(link, 0, a_dst.cpu().numpy(), np.arange(s.nghost, dtype=np.int32), rhs_dst.cpu().numpy())
+        if up < s.world:
+            ctx.exchange_add_peer(False, slot_there=0, mem_bytes=handles[up],
+                                  incoming_min_row=int(self.rhs_map.min()) if len(self.rhs_map) else -1)
+        dist.barrier()
+
+    def close(self):
+        """Collective: no rank frees the arrays its neighbours still push into."""
+        if self.strmat is not None:
+            self.strmat.ctx.synchronize()
+            self.dist.barrier()
+            self.strmat.ctx.close()
 
     # ---- assembly --------------------------------------------------------------------------------
     def AssembleDevice(self):
         """Device-resident: local kernels, then the interface exchange (async on the current stream)."""
         dist = self.dist
         s = self.slab
-        self.strmat.ctx.assemble_async()
+        self.strmat.ctx.assemble_async()   # (p2p: the exchange is part of the call)
+        if self.exchange == "p2p":
+            return
         ops = []
         if s.rank > 0 and s.nghost:
             ops.append(dist.P2POp(dist.isend, self.a_view[:self.nnz_ghost], s.rank - 1))

@@ -262,12 +262,17 @@ class TPZStructMatrixB200:
     """TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>> (symmetric=True) or
     TPZSpStructMatrix<...> (symmetric=False) on a flattened mesh."""
 
-    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0, engine=None, scatter=None, variant=None):
+    def __init__(self, mesh: FlatMesh, materials, symmetric=True, device=0, nthreads=0, engine=None, scatter=None, variant=None,
+                 devices=None):
+        """devices: list of CUDA devices of THIS process that share the assembly (b200asm_multi: element partition by the
+        smallest destination equation, row-sharded CSR, interface rows over NVLink) - what SetNumThreads(n) means for the C++
+        strategy; None / one entry: a single context on `device`."""
         self.mesh = mesh
         self.materials = {m.id: m for m in (materials.values() if isinstance(materials, dict) else materials)}
         self.symmetric = bool(symmetric)
         self.fNumThreads = nthreads
-        self.ctx = capi.Context(device)
+        self.multi = devices is not None and len(devices) > 1
+        self.ctx = capi.MultiContext(devices) if self.multi else capi.Context(devices[0] if devices else device)
         if engine is not None:  # 0: register-tile DFMA kernels only, 1 (default): DMMA panel kernels where available
             self.ctx.set_option("engine", engine)
         if variant:  # tuning alternative of the DMMA kernels (0 = default)
@@ -323,6 +328,8 @@ class TPZStructMatrixB200:
         on_device: build it on the GPU (b200asm_build_pattern_device) instead of the threaded host builder;
         download=False then leaves IA/JA on the device only (self.ja stays None; self.nnz is set)."""
         idx, graph = self.mesh.element_graph()
+        if on_device and self.multi:
+            raise ValueError("Create(on_device=True) builds the pattern on ONE GPU; a multi-device struct matrix takes the host builder")
         if on_device:
             self._flatten()
             neq, self.nnz = self.ctx.build_pattern_device(self.symmetric, idx, graph, self.mesh.block_pos, self.mesh.block_size)
