@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--locality", type=int, default=1, help="0: keep the mesh (lexicographic) element order on the device")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: interface rows pushed into the owner's memory over "
                     "NVLink while the interior is assembled (C ABI, b200asm_exchange_*), or NCCL send/recv after the kernels")
+    ap.add_argument("--extra", default="c5,c4,c3", help="other BASELINE.json configurations measured after the headline and reported under "
+                    "\"configs\" (c3 tetrahedra p2 elasticity, c4 hexahedra p4 Poisson, c5 hexahedra p2 elasticity; per-GPU slabs, weak scaling)")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -75,8 +78,8 @@ def kernel_name(a):
             return "assemble_affine_simplex_kernel (closed-form element matrices of straight-sided tetrahedra, one warp per element)"
         if a.topo == "hex" and a.perturb == 0.0 and a.p <= 2:
             return "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)"
-        if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and 8 <= a.variant <= 15:
-            return "assemble_sumfact_hex_p2_poisson_kernel (sum factorisation, one CTA of 64 threads per element)"
+        if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and (a.variant == 0 or 8 <= a.variant <= 15):
+            return "assemble_sumfact_hex_p2_poisson_kernel (sum factorisation with prefetch, one CTA of 64 threads per element)"
         if a.topo == "hex" and a.phys == "poisson" and a.p == 2:
             return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"
         if a.topo == "hex" and a.phys == "poisson" and a.p >= 3:
@@ -100,24 +103,24 @@ def cpu_sample_n(a):
         return a.cpu_n
     # ~10-30 s of CPU work including mesh + Create(): sized from the survey's per-element costs
     if a.phys == "poisson":
-        return {1: 48, 2: 32, 3: 14, 4: 8}.get(a.p, 6) if a.topo == "hex" else 20
+        return {1: 64, 2: 48, 3: 14, 4: 8}.get(a.p, 6) if a.topo == "hex" else 20
     return {1: 24, 2: 14, 3: 8}.get(a.p, 6) if a.topo == "hex" else 14
 
 
-def run_reference(a, steps, warmup):
+def run_reference(a, steps, warmup, dumpdir=None):
     drv = os.path.join(ROOT, "oracle", "_ref", "refdriver")
     cores = os.cpu_count() or 1
     n = cpu_sample_n(a)
     if os.path.exists(drv):
         reps = max(1, steps)
         out = subprocess.run([drv, "time", str(n), str(a.p), "1" if a.phys == "elasticity" else "0",
-                              {"hex": "0", "tet": "1", "prism": "2"}[a.topo], str(cores), str(reps + warmup)],
-                             capture_output=True, text=True, check=True).stdout
+                              {"hex": "0", "tet": "1", "prism": "2"}[a.topo], str(cores), str(reps + warmup), repr(float(a.perturb))] +
+                             ([dumpdir] if dumpdir else []), capture_output=True, text=True, check=True).stdout
         line = [l for l in out.splitlines() if l.startswith("{")][-1]
         r = json.loads(line)
         sec = r["assemble_s_mean"]
         return {"value": r["vol_elements"] / sec, "dof_per_s": r["neq"] / sec, "unit": "elements/s", "cores": cores,
-                "kind": "reference", "ms_per_step": sec * 1e3,
+                "kind": "reference", "ms_per_step": sec * 1e3, "n": n,
                 "sample": f"{workload_name(a, n)}: {r['vol_elements']} volume elements, {r['neq']} DOF, "
                           f"TPZStructMatrixOR SetNumThreads({cores}), mean of {reps + warmup} re-assemblies"}
     # fallback: the oracle port (scalar, 1 core)
@@ -136,7 +139,7 @@ def run_reference(a, steps, warmup):
     sec = time.time() - t0
     nvol = len(mesh.blocks[0].elnodes)
     return {"value": nvol / sec, "dof_per_s": mesh.neq / sec, "unit": "elements/s", "cores": 1, "kind": "port",
-            "ms_per_step": sec * 1e3, "sample": f"{workload_name(a, n)}: oracle/oracle.c serial port, {nvol} elements"}
+            "ms_per_step": sec * 1e3, "n": n, "sample": f"{workload_name(a, n)}: oracle/oracle.c serial port, {nvol} elements"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,6 +192,252 @@ def summarize_clocks(samples):
             "reasons": sorted(reasons), "samples": len(samples)}
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configurations measured next to the headline (reported under "configs" of the same JSON line):
+# per-GPU grids; N > 1 stacks N slabs in z (weak scaling), e.g. C5 at N = 8: 81 x 81 x 648 hexahedra = 103.9 M DOF
+EXTRA_CONFIGS = {
+    "c3": {"topo": "tet", "p": 2, "phys": "elasticity", "n": 113, "n_multi": 96, "perturb": 0.1,
+           "baseline": "configs[2]: 3D elasticity H1 p=2 on tetrahedra, ~30 M DOF on one B200"},
+    "c4": {"topo": "hex", "p": 4, "phys": "poisson", "n": 64, "n_multi": 48, "perturb": 0.1,
+           "baseline": "configs[3]: 3D Poisson H1 p=4 hexahedra (FP64 DMMA path), 1/2/4/8 B200"},
+    "c5": {"topo": "hex", "p": 2, "phys": "elasticity", "n": 81, "n_multi": 81, "perturb": 0.1,
+           "baseline": "configs[4]: 3D elasticity H1 p=2 hexahedra, >= 100 M DOF on 8 B200 (81 x 81 x 81 N)"},
+}
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs NVML reports as closest to the GPU, so that
+    eight ranks do not download 36 GB through one memory controller."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+class Case:
+    """One workload on this rank's GPU: mesh slab, struct matrix, pattern; device-resident timing and roofline."""
+
+    def __init__(self, a, rank, world, local_rank):
+        import numpy as np
+        import torch
+        from neopz_b200 import distributed, gridmesh, strmatrix as sm
+        self.a, self.rank, self.world = a, rank, world
+        self.torch = torch
+        t0 = time.time()
+        ns = 3 if a.phys == "elasticity" else 1
+        if a.topo == "prism":
+            if world > 1:
+                raise SystemExit("bench.py: --topo prism runs on one GPU (the z-slab partition covers hexahedra and tetrahedra)")
+            import types
+            pm = gridmesh.grid_mesh(a.n, a.p, ns, prisms=True, perturb=a.perturb)
+            slab = types.SimpleNamespace(mesh=pm, nown=pm.neq)
+        else:
+            slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=a.perturb)
+        self.slab, self.mesh = slab, slab.mesh
+        self.t_flat = time.time() - t0
+        if a.phys == "poisson":
+            mat = sm.TPZMatPoisson(1, 3)
+            mat.SetForcingFunction(1.0)
+            mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.0])}
+        else:
+            mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
+            mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
+        self.mats = mats
+        self.sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter,
+                                                       pattern=a.pattern, variant=a.variant, exchange=a.exchange) if world > 1 else None
+        self.strmat = self.sharded.strmat if self.sharded else sm.TPZStructMatrixB200(self.mesh, mats, symmetric=True, device=local_rank,
+                                                                                      engine=a.engine, scatter=a.scatter, variant=a.variant)
+        self.stream = torch.cuda.current_stream()
+        self.strmat.ctx.set_stream(self.stream.cuda_stream)
+        if not a.locality:
+            self.strmat.ctx.set_option("locality", 0)
+        if a.debug:
+            self.strmat.ctx.set_option("debug", a.debug)
+        t0 = time.time()
+        if self.sharded:
+            ia, ja = self.sharded.Create()
+        else:
+            ia, ja = self.strmat.Create(on_device=a.pattern == "device", download=False)
+        torch.cuda.synchronize()
+        self.t_create = time.time() - t0
+        self.nvol = len(self.mesh.blocks[0].elnodes)
+        self.neq = slab.nown
+        self.nnz = len(ja) if ja is not None else (self.sharded.nnz if self.sharded else self.strmat.nnz)
+        self.step_async = self.sharded.AssembleDevice if self.sharded else self.strmat.ctx.assemble_async
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def time_device(self, steps, warmup, sampler=None):
+        """W warm-up steps, then exactly K steps between CUDA events on the launching stream; max over ranks."""
+        torch = self.torch
+        for _ in range(max(3, warmup)):
+            self.step_async()
+        self.barrier()
+        k0 = self.strmat.ctx.counters()[0]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if sampler:
+            sampler[0].start()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for s0, s1 in evs:
+            s0.record(self.stream)
+            self.step_async()
+            s1.record(self.stream)
+        e1.record(self.stream)
+        self.barrier()
+        if sampler:
+            sampler[1].set()
+        # duration of the dominant kernel alone (the volume group's launches), CUDA events on the launching stream, taken
+        # right after the timed region so that the step timing above carries no extra event records
+        ctx = self.strmat.ctx
+        ctx.set_option("timing", 1)
+        vol_ms = []
+        for _ in range(min(steps, 5)):
+            self.step_async()
+            vol_ms.append(sum(ctx.group_time_ms(g) for g in self.strmat.groups_of_block[0]))
+        ctx.set_option("timing", 0)
+        total_ms = e0.elapsed_time(e1)
+        self.step_ms = [s0.elapsed_time(s1) for s0, s1 in evs]
+        self.launches = ctx.counters()[0] - k0
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([total_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        self.ms_per_step = total_ms / steps
+        self.kernel_ms = float(sum(vol_ms) / len(vol_ms))
+        self.value = self.nvol * self.world / (self.ms_per_step * 1e-3)
+        return self.value
+
+    def roofline(self, peaks, fp64):
+        a = self.a
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        fp64_peak = max(fp64.get("dfma_tflops", 0.0), fp64.get("dmma_tflops", 0.0)) or 37.0
+        f_el, b_el = algorithmic_work(a.topo, a.p, a.phys, self.nvol, self.neq, self.nnz)
+        flops, byts = f_el * self.nvol, b_el * self.nvol
+        ach_tf = flops / (self.kernel_ms * 1e-3) / 1e12
+        ach_gb = byts / (self.kernel_ms * 1e-3) / 1e9
+        t_fp, t_hbm = flops / (fp64_peak * 1e12), byts / (hbm_peak * 1e9)
+        if t_fp >= t_hbm:
+            r = {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 / DFMA; the larger measured peak)", "achieved": ach_tf,
+                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                 "peak_source": "measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json): "
+                                "MEASURED_PEAKS.json carries no FP64 figure"}
+        else:
+            r = {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{a.topo},{a.p},{a.phys},{a.n},{a.scatter}")
+            if tr and self.world == 1 and a.engine == 1:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
+        # executed arithmetic of the kernels (upper triangle of ek only, fused multiply-adds counted as 2): what the FP64
+        # pipe actually does per element, next to the reference-arithmetic count `achieved` is quoted on
+        x_el = executed_flops(a.topo, a.p, a.phys, kernel_name(a))
+        r.update({"traffic": traffic, "algorithmic_flops_per_element": f_el, "algorithmic_bytes_per_element": b_el,
+                  "hbm_GBps_algorithmic": ach_gb, "hbm_frac_algorithmic": ach_gb / hbm_peak, "hbm_peak_GBps": hbm_peak,
+                  "executed_flops_per_element": x_el,
+                  "fp64_pipe_utilisation_executed": (x_el * self.nvol / (self.kernel_ms * 1e-3) / 1e12 / fp64_peak) if x_el else None,
+                  "kernel": kernel_name(a), "kernel_ms": self.kernel_ms, "kernel_share_of_step": self.kernel_ms / self.ms_per_step,
+                  "peaks": {"fp64_tflops": fp64_peak, "hbm_gbs": hbm_peak}})
+        return r
+
+    def close(self):
+        if self.sharded:
+            self.sharded.close()
+        else:
+            self.strmat.ctx.close()
+        self.strmat = self.sharded = self.slab = self.mesh = None
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
+def executed_flops(topo, p, phys, kernel):
+    """FP64 operations the kernel families execute per element (FMA = 2), from their loop structure:
+    quadrature kernels form the upper triangle of the Gram products of the (3 nq) x n panel (Poisson) or the nine sums
+    per node pair (Elasticity3D) plus the panel build; the closed-form kernels contract a 3 x 3 Jacobian factor with the
+    reference-element table.  None where no model is stated."""
+    if topo == "hex":
+        n, q = (p + 1) ** 3, int(0.51 * (2 * p + 2)) ** 3
+    elif topo == "tet":
+        n, q = {1: 4, 2: 10, 3: 20, 4: 35}[p], {1: 4, 2: 14, 3: 24, 4: 46}[p]
+    else:
+        return None
+    pairs = n * (n + 1) // 2
+    geom = q * (194 if topo == "hex" else 122) + q * 18 * n
+    if "affine" in kernel:      # 54 FMA per node pair (9 Jinv products x 6 table rows) + block combination
+        return 2.0 * 54 * pairs + (9 * 3 * pairs if phys == "elasticity" else 0) + 200
+    if "sumfact" in kernel:
+        return 2.0 * 21000
+    if phys == "poisson":
+        return 2.0 * 3 * q * pairs + geom
+    return 2.0 * 9 * q * pairs + 9 * 3 * pairs + geom
+
+
+def parity_against_reference(a, dumpdir, n, local_rank):
+    """The GPU assembles the SAME mesh the CPU arm just timed (refdriver dumped its IA / JA / A / rhs): pattern equality and
+    relative Frobenius differences.  The reference's arrays are only compared, never used by the GPU path."""
+    import numpy as np
+    from neopz_b200 import gridmesh, strmatrix as sm
+    ns = 3 if a.phys == "elasticity" else 1
+    mesh = gridmesh.grid_mesh(n, a.p, ns, tetrahedra=a.topo == "tet", prisms=a.topo == "prism", perturb=a.perturb)
+    if a.phys == "poisson":
+        mat = sm.TPZMatPoisson(1, 3)
+        mat.SetForcingFunction(1.0)
+        mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.0])}
+    else:
+        mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
+        mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
+    st = sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter, variant=a.variant)
+    ia, ja = st.Create(on_device=True, download=True)
+    av, rhs = st.Assemble()
+    st.ctx.close()
+    ia_r = np.fromfile(os.path.join(dumpdir, "ia.bin"), dtype=np.int64)
+    ja_r = np.fromfile(os.path.join(dumpdir, "ja.bin"), dtype=np.int64)
+    a_r = np.fromfile(os.path.join(dumpdir, "a.bin"), dtype=np.float64)
+    rhs_r = np.fromfile(os.path.join(dumpdir, "rhs.bin"), dtype=np.float64)
+    same = bool(len(ia) == len(ia_r) and len(ja) == len(ja_r) and np.array_equal(ia, ia_r) and np.array_equal(ja, ja_r))
+    out = {"mesh": workload_name(a, n), "neq": int(mesh.neq), "nnz": int(len(ja)), "ia_ja_equal": same,
+           "against": "the unmodified reference (oracle/_ref/refdriver: TPZSSpStructMatrix + TPZStructMatrixOR) on the same mesh in this run"}
+    if same:
+        out["relF_A"] = float(np.linalg.norm(av - a_r) / np.linalg.norm(a_r))
+        out["relF_rhs"] = float(np.linalg.norm(rhs - rhs_r) / max(np.linalg.norm(rhs_r), 1e-300))
+        # rows without penalty entries (SURVEY H3: the Frobenius norm is dominated by the Dirichlet big number)
+        big = 1e10
+        rows = np.repeat(np.arange(len(ia) - 1), np.diff(ia))
+        dirty = np.zeros(len(ia) - 1, dtype=bool)
+        dirty[rows[np.abs(a_r) > big]] = True
+        dirty[ja_r[np.abs(a_r) > big]] = True
+        keep = ~(dirty[rows] | dirty[ja_r])
+        if keep.any():
+            out["relF_A_rows_without_penalty"] = float(np.linalg.norm((av - a_r)[keep]) / np.linalg.norm(a_r[keep]))
+        out["tolerance"] = 1e-12
+        out["ok"] = bool(out["relF_A"] <= 1e-12 and out["relF_rhs"] <= 1e-12)
+    else:
+        out["ok"] = False
+    return out
+
+
 def main():
     a = parse()
     # stdout carries exactly ONE line (the JSON): anything libraries print there (e.g. "NCCL version ...") goes to stderr
@@ -208,6 +457,8 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
+        if not a.cpu_n and a.topo == "hex" and a.p == 2 and a.phys == "poisson":
+            a.cpu_n = 64   # the reference arm runs alone: a larger bounded sample of the headline workload (~2 min in all)
         r = run_reference(a, a.steps, a.warmup)
         line = {"impl": "reference", "metric": "assembled volume elements/s (Assemble on a created pattern)",
                 "value": r["value"], "unit": "elements/s", "dof_per_s": r["dof_per_s"], "n_gpus": a.gpus, "steps": a.steps,
@@ -220,102 +471,43 @@ def main():
         emit(line)
         return
 
+    import copy
     import numpy as np
     import torch
     import torch.distributed as dist
-    from neopz_b200 import gridmesh, strmatrix as sm
+    from neopz_b200 import gridmesh
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the assembly engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    peaks, fp64 = {}, {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    try:
+        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))
+    except Exception:
+        pass
+
     # ---- one-off setup (reported, not timed as assembly): mesh flatten, pattern, scatter maps ------------------
     # N > 1: ONE global mesh of n x n x (n*N) elements, z-slab per rank, rows owned by the rank that first touches
-    # them, interface-row contributions exchanged over NCCL every step (neopz_b200/distributed.py) -> weak scaling
-    from neopz_b200 import distributed
-    t0 = time.time()
-    ns = 3 if a.phys == "elasticity" else 1
-    if a.topo == "prism":
-        if world > 1:
-            raise SystemExit("bench.py: --topo prism runs on one GPU (the z-slab partition covers hexahedra and tetrahedra)")
-        import types
-        pm = gridmesh.grid_mesh(a.n, a.p, ns, prisms=True, perturb=a.perturb)
-        slab = types.SimpleNamespace(mesh=pm, nown=pm.neq)
-    else:
-        slab = distributed.slab_mesh(a.n, a.n * world, rank, world, a.p, ns, tetrahedra=a.topo == "tet", perturb=a.perturb)
-    mesh = slab.mesh
-    t_flat = time.time() - t0
-    if a.phys == "poisson":
-        mat = sm.TPZMatPoisson(1, 3)
-        mat.SetForcingFunction(1.0)
-        mats = {1: mat, -1: mat.CreateBC(-1, 0, [[0.0]], [0.0])}
-    else:
-        mat = sm.TPZElasticity3D(1, 1000.0, 0.3, (0.0, 0.0, -1.0))
-        mats = {1: mat, -1: mat.CreateBC(-1, 0, np.zeros((3, 3)), np.zeros(3))}
-    sharded = distributed.ShardedStructMatrix(slab, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter,
-                                              pattern=a.pattern, variant=a.variant, exchange=a.exchange) if world > 1 else None
-    strmat = sharded.strmat if sharded else sm.TPZStructMatrixB200(mesh, mats, symmetric=True, device=local_rank, engine=a.engine, scatter=a.scatter, variant=a.variant)
-    stream = torch.cuda.current_stream()
-    strmat.ctx.set_stream(stream.cuda_stream)
-    if not a.locality:
-        strmat.ctx.set_option("locality", 0)
-    if a.debug:
-        strmat.ctx.set_option("debug", a.debug)
-    t0 = time.time()
-    if sharded:
-        ia, ja = sharded.Create()
-    else:
-        ia, ja = strmat.Create(on_device=a.pattern == "device", download=False)
-    torch.cuda.synchronize()
-    t_create = time.time() - t0
-    nvol = len(mesh.blocks[0].elnodes)
-    neq, nnz = slab.nown, (len(ja) if ja is not None else (sharded.nnz if sharded else strmat.nnz))
-    step_async = sharded.AssembleDevice if sharded else strmat.ctx.assemble_async
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # them, interface-row contributions pushed over NVLink every step (neopz_b200/distributed.py) -> weak scaling
+    case = Case(a, rank, world, local_rank)
+    strmat, sharded, mesh, stream = case.strmat, case.sharded, case.mesh, case.stream
+    nvol, neq, nnz = case.nvol, case.neq, case.nnz
+    step_async, barrier = case.step_async, case.barrier
 
     # ---- device-resident timing ---------------------------------------------------------------------
-    for _ in range(max(3, a.warmup)):
-        step_async()
-    barrier()
-    k0 = strmat.ctx.counters()[0]
     stop, samples = threading.Event(), []
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
-    if rank == 0:
-        th.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    barrier()
-    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_all0.record(stream)
-    for s0, s1 in evs:
-        s0.record(stream)
-        step_async()
-        s1.record(stream)
-    e_all1.record(stream)
-    barrier()
+    value = case.time_device(a.steps, a.warmup, sampler=(th, stop) if rank == 0 else None)
     stop.set()
-    # duration of the dominant kernel alone (the volume group's launches), CUDA events on the launching stream,
-    # taken right after the timed region so that the step timing above carries no extra event records
-    strmat.ctx.set_option("timing", 1)
-    vol_ms = []
-    for _ in range(min(a.steps, 5)):
-        step_async()
-        vol_ms.append(strmat.ctx.group_time_ms(strmat.group_of_block[0]))
-    strmat.ctx.set_option("timing", 0)
-    total_ms = e_all0.elapsed_time(e_all1)
-    step_ms = [s0.elapsed_time(s1) for s0, s1 in evs]
-    launches = strmat.ctx.counters()[0] - k0
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / a.steps
-    value = nvol * world / (ms_per_step * 1e-3)
+    ms_per_step, step_ms, launches, kernel_ms = case.ms_per_step, case.step_ms, case.launches, case.kernel_ms
 
     # ---- end to end through the C ABI with HOST buffers (H2D of the nodes, D2H of A and rhs, every step) ----
     e2e = None
@@ -324,6 +516,7 @@ def main():
         r_host = torch.empty(mesh.neq, dtype=torch.float64).pin_memory()
         x_host = torch.from_numpy(mesh.nodes.copy()).pin_memory()
         a_np, r_np, x_np = a_host.numpy(), r_host.numpy(), x_host.numpy()
+        a_np[:] = 0.0   # first touch on this rank's NUMA node
         ksteps = max(2, min(a.steps, 5))
         def e2e_step():
             strmat.ctx.set_nodes(x_np)          # H2D: node coordinates (the geometry input of the step)
@@ -352,17 +545,20 @@ def main():
             e2e_s = float(t.item())
         e2e = {"value": nvol * world / e2e_s, "unit": "elements/s", "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes + r_np.nbytes),
+               "d2h_GBps_per_gpu": (a_np.nbytes + r_np.nbytes) / e2e_s / 1e9,
                "steps": ksteps, "note": "b200asm_set_nodes + b200asm_assemble(a_host, rhs_host), pinned host buffers; the D2H of "
                "finished CSR rows overlaps the assembly of later element chunks (option overlap)"}
+        if numa_cpus:
+            e2e["rank_cpu_affinity"] = f"{numa_cpus} CPUs closest to the GPU (NVML), pinned buffers first-touched there"
         if serial_s is not None:
             e2e["ms_per_step_without_overlap"] = serial_s * 1e3
+        del a_host, r_host, x_host, a_np, r_np
 
     # ---- the same mesh WITHOUT the node perturbation (the literal CreateGeoMeshOnGrid grid of BASELINE.json): every cell is
     # a parallelepiped, the context measures that on the device and switches the group to the closed-form kernel
     # (affine_hex.cuh).  Reported next to the headline, which stays on general (trilinear) hexahedra.
     uniform = None
     if world == 1 and a.topo == "hex" and a.p <= 2 and a.perturb != 0.0 and a.engine == 1 and not a.debug:
-        import numpy as np
         moved = np.ascontiguousarray(mesh.nodes)
         strmat.ctx.set_nodes(gridmesh.grid_nodes(a.n, perturb=0.0))
         for _ in range(3):
@@ -375,8 +571,11 @@ def main():
         u1.record(stream)
         torch.cuda.synchronize()
         ums = u0.elapsed_time(u1) / a.steps
+        f_el, b_el = algorithmic_work(a.topo, a.p, a.phys, nvol, neq, nnz)
         uniform = {"value": nvol / (ums * 1e-3), "unit": "elements/s", "ms_per_step": ums,
                    "kernel": "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)",
+                   "hbm_GBps_algorithmic": b_el * nvol / (ums * 1e-3) / 1e9,
+                   "hbm_frac_algorithmic": b_el * nvol / (ums * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
                    "note": "same pattern and materials, unperturbed grid nodes; device-resident like `value`"}
         strmat.ctx.set_nodes(moved)
         step_async()
@@ -393,72 +592,88 @@ def main():
         cg = {"iterations": iters, "relative_residual": resid, "ms_per_iteration": dt * 1e3 / max(iters, 1),
               "spmv_GBps_algorithmic": (12.0 * nnz + 24.0 * neq) * max(iters, 1) / dt / 1e9}
 
+    roofline = case.roofline(peaks, fp64) if rank == 0 else None
+    setup_s = {"flatten_mesh": case.t_flat, "pattern+upload+scatter_map": case.t_create, "pattern_builder": a.pattern}
+    case.close()
+
+    # ---- the other BASELINE.json configurations, device-resident, same timing rules (W >= 3, K steps, CUDA events, max over ranks)
+    extras = {}
+    for name in ([] if a.no_extra else [c for c in a.extra.split(",") if c]):
+        spec = EXTRA_CONFIGS[name]
+        b = copy.copy(a)
+        b.topo, b.p, b.phys, b.perturb, b.variant = spec["topo"], spec["p"], spec["phys"], spec["perturb"], 0
+        b.n = spec["n"] if world == 1 else spec["n_multi"]
+        b.cpu_n = 0
+        try:
+            c = Case(b, rank, world, local_rank)
+            st2, smp2 = threading.Event(), []
+            th2 = threading.Thread(target=clocks_sampler, args=(st2, smp2, local_rank), daemon=True)
+            ksteps = max(3, min(a.steps, 10))
+            c.time_device(ksteps, a.warmup, sampler=(th2, st2) if rank == 0 else None)
+            st2.set()
+            if rank == 0:
+                extras[name] = {"baseline_config": spec["baseline"],
+                                "workload": workload_name(b) if world == 1 else workload_name(b).replace(f"{b.n}^3", f"{b.n}x{b.n}x{b.n * world}") + f", {world} z-slabs",
+                                "value": c.value, "unit": "elements/s", "ms_per_step": c.ms_per_step, "steps": ksteps,
+                                "dof": int(c.neq) * world if world == 1 else None, "dof_per_gpu": int(c.neq), "dof_per_s": None,
+                                "volume_elements_per_gpu": int(c.nvol), "nnz_upper_per_gpu": int(c.nnz),
+                                "roofline": c.roofline(peaks, fp64), "gpu_launches": c.launches, "clocks": summarize_clocks(smp2),
+                                "setup_s": {"flatten_mesh": c.t_flat, "pattern+upload+scatter_map": c.t_create}}
+            # total DOF of the global mesh = sum of the owned rows of all ranks
+            if world > 1:
+                t = torch.tensor([float(c.neq)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t)
+                tot = int(t.item())
+            else:
+                tot = int(c.neq)
+            if rank == 0:
+                extras[name]["dof"] = tot
+                extras[name]["dof_per_s"] = tot / (c.ms_per_step * 1e-3)
+            c.close()
+        except Exception as ex:  # an extra configuration never takes the headline down with it
+            if rank == 0:
+                extras[name] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+            torch.cuda.empty_cache()
+        if rank == 0 and not a.no_cpu_baseline and world == 1 and name in extras and "error" not in extras[name]:
+            try:
+                r = run_reference(b, 2, 1)
+                extras[name]["cpu_baseline"] = {"value": r["value"], "unit": "elements/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            except Exception as ex:
+                extras[name]["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": str(ex)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (assemble_volume_kernel) ------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    fp64 = {}
-    try:
-        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    fp64_peak = max(fp64.get("dfma_tflops", 0.0), fp64.get("dmma_tflops", 0.0)) or 37.0
-    kernel_ms = float(np.mean(vol_ms))  # average launch duration of the volume kernel (its share of the step: see "kernel_share")
-    roofline = None
-    f_el, b_el = algorithmic_work(a.topo, a.p, a.phys, nvol, neq, nnz)
-    if True:
-        flops = f_el * nvol
-        byts = b_el * nvol
-        ach_tf = flops / (kernel_ms * 1e-3) / 1e12
-        ach_gb = byts / (kernel_ms * 1e-3) / 1e9
-        t_fp, t_hbm = flops / (fp64_peak * 1e12), byts / (hbm_peak * 1e9)
-        if t_fp >= t_hbm:
-            roofline = {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 / DFMA; the larger measured peak)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                        "peak_source": "measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json): "
-                                       "MEASURED_PEAKS.json carries no FP64 figure"}
-        else:
-            roofline = {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
-        traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{a.topo},{a.p},{a.phys},{a.n},{a.scatter}")
-            if tr and world == 1 and a.engine == 1:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        except Exception:
-            pass
-        roofline.update({"traffic": traffic, "algorithmic_flops_per_element": f_el, "algorithmic_bytes_per_element": b_el,
-                         "hbm_GBps_algorithmic": ach_gb, "hbm_peak_GBps": hbm_peak,
-                         "kernel": kernel_name(a), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
-                         "peaks": {"fp64_tflops": fp64_peak, "hbm_gbs": hbm_peak}})
-
-    cpu = None
-    if not a.no_cpu_baseline:
+    cpu, parity = None, None
+    if not a.no_cpu_baseline and world == 1:   # (the CPU arm is timed on rank 0 at N = 1 only)
+        import shutil
+        import tempfile
+        dump = tempfile.mkdtemp(prefix="b200asm_parity_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
-            r = run_reference(a, 3, 1)
+            r = run_reference(a, 3, 1, dumpdir=dump)
             cpu = {"value": r["value"], "unit": "elements/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                    "dof_per_s": r["dof_per_s"]}
+            if r["kind"] == "reference":
+                parity = parity_against_reference(a, dump, r["n"], local_rank)
         except Exception as ex:  # the baseline is reported, never the product path
             cpu = {"value": None, "unit": "elements/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(ex)[:200]}
+        finally:
+            shutil.rmtree(dump, ignore_errors=True)
 
     line = {"metric": "assembled volume elements/s (Assemble on a created pattern)", "value": value, "unit": "elements/s",
             "dof_per_s": neq * world / (ms_per_step * 1e-3),
             "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a) if world == 1 else workload_name(a).replace(f"{a.n}^3", f"{a.n}x{a.n}x{a.n * world}") +
-                       f", {world} z-slabs, row-sharded CSR, NCCL interface-row exchange", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
+                       f", {world} z-slabs, row-sharded CSR, interface rows pushed over NVLink ({a.exchange})", "volume_elements_per_gpu": nvol, "dof_per_gpu": neq, "nnz_upper_per_gpu": nnz,
                        "l2": "inputs larger than L2 (CSR values %.1f GB + scatter map rewritten every step)" % (nnz * 8 / 1e9),
-                       "perturbed_nodes": a.perturb != 0.0, "element_order": "Morton curve inside 16 element chunks" if a.locality else "mesh order", "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": {"flatten_mesh": t_flat, "pattern+upload+scatter_map": t_create,
-                                   "pattern_builder": a.pattern}},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                       "perturbed_nodes": a.perturb != 0.0, "element_order": "Morton curve inside 16 element chunks" if a.locality else "mesh order", "engine": "dmma" if a.engine == 1 else "dfma register tiles", "scatter": a.scatter, "setup_s": setup_s},
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches,
             "clocks": summarize_clocks(samples), "step_ms": step_ms}
+    if extras:
+        line["configs"] = extras
     if cg:
         line["device_cg"] = cg
     if uniform:

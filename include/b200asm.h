@@ -91,6 +91,7 @@ typedef struct {
 } b200asm_group;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
+int b200asm_device_count(void); /* CUDA devices visible to this process (0: none - every compute entry point then fails) */
 int b200asm_create(b200asm_ctx **out, int device);
 void b200asm_destroy(b200asm_ctx *ctx);
 const char *b200asm_last_error(const b200asm_ctx *ctx); /* ctx may be NULL: last create() error */

@@ -56,7 +56,7 @@ SYMBOLS = [
     "b200asm_multi_set_option", "b200asm_multi_set_nodes", "b200asm_multi_add_group", "b200asm_multi_set_group_coef",
     "b200asm_multi_set_group_force", "b200asm_multi_clear_groups", "b200asm_multi_set_pattern", "b200asm_multi_partition",
     "b200asm_multi_assemble", "b200asm_multi_assemble_rhs", "b200asm_multi_assemble_async", "b200asm_multi_synchronize",
-    "b200asm_multi_counters",
+    "b200asm_multi_counters", "b200asm_device_count",
 ]
 
 
@@ -70,6 +70,7 @@ def lib():
                           "(nvcc, sm_100a). neopz_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
     vp, dp, ip64, ip32 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    L.b200asm_device_count.argtypes = []
     L.b200asm_create.argtypes = [C.POINTER(vp), C.c_int]
     L.b200asm_destroy.argtypes = [vp]
     L.b200asm_destroy.restype = None

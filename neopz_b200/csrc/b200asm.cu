@@ -84,6 +84,10 @@ struct VolCfg {
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 // scatter-add of one entry: atomic, or plain when the launch is conflict-free by colouring
 __device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) {
+    if (atomic & 4) {  // option "drop_tiny": TPZSYsmpMatrix / TPZFYsmpMatrix::AddKel skip IsZero(value) entries (Matrix/pzsysmp.cpp:381)
+        if (fabs(v) < 1e-12) return;
+        atomic &= 3;
+    }
     if (atomic == 1) atomicAdd(addr, v);
     else if (atomic == 0) *addr += v;
     // atomic == 2: profiling aid, the value is dropped (keeps the arithmetic, removes the memory traffic)
@@ -92,7 +96,7 @@ __device__ __forceinline__ void scatter_add(double *addr, double v, int atomic) 
 
 // load-vector entry: destination -1 = equation removed by the equation filter (StrMatrix/TPZEquationFilter.h:120-141)
 __device__ __forceinline__ void scatter_rhs(double *rhs, int32_t d, double v, int atomic) {
-    if (d >= 0) scatter_add(rhs + d, v, atomic);
+    if (d >= 0) scatter_add(rhs + d, v, atomic & 3);  // (TPZFMatrix::AddFel keeps every entry: no drop_tiny here)
 }
 // predicated reduction: no branch around the red (a divergent `if (pos >= 0) atomicAdd` costs BSSY/BRA/BSYNC per entry)
 __device__ __forceinline__ void red_if_valid(double *a, int32_t pos, double v) {
@@ -508,7 +512,8 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t el = p.el0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (el >= p.el1) return;
-    double *W = bc_smem + (size_t)warp * p.nq;
+    double *W = bc_smem + (size_t)warp * 2 * p.nq;
+    double *W2 = W + p.nq;  // w / jac(0,0)^2: weight of the first-axis derivatives (coef[12] != 0 only)
     for (int q = lane; q < p.nq; q += 32) {
         const double *dn = p.dng + (size_t)q * p.fdim * NN;
         double v1[3] = {0, 0, 0}, v2[3] = {0, 0, 0};
@@ -540,8 +545,12 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
         double det = p.fdim == 2 ? n1 * n2 : n1;  // line elements: |dx/dxi|  (Mesh/pzgeoel.cpp:1185-1225)
         if (fabs(det) < 1.e-12) det = 1.e-12;
         W[q] = __ldg(p.qw + q) * fabs(det);
+        // dphix(0,i) = jacinv(0,0) dphi(0,i) + jacinv(1,0) dphi(1,i) with jacinv(0,0) = 1 / |dx/dxi|, jacinv(1,0) = 0
+        // (Gram-Schmidt Jacobian, Mesh/pzgeoel.cpp:1228-1295 / :1185-1225; dphix = jacinv^T dphi, Mesh/TPZCompElH1.cpp:140-149)
+        W2[q] = W[q] / (n1 * n1);
     }
     __syncwarp();
+    const double cgrad = p.coef[12];
     const int npair = p.rhs_only ? 0 : N * (N + 1) / 2;
     for (int idx = lane; idx < npair; idx += 32) {
         int i = 0, rem = idx;  // (i, j), i <= j, row-major over the upper triangle
@@ -549,6 +558,20 @@ __global__ void __launch_bounds__(128) assemble_bc_warp_kernel(const BcParams p,
         const int j = i + rem;
         double S = 0.0;
         for (int q = 0; q < p.nq; q++) S += __ldg(p.phi + (size_t)q * N + i) * __ldg(p.phi + (size_t)q * N + j) * W[q];
+        if (cgrad != 0.0) {
+            // TPZMatPoisson boundary type 2 (Material/Poisson/TPZMatPoisson.cpp:104-118, one state variable):
+            // ek(i,j) += BigNumber * Val1(0,0) * dphix(0,i) * dphix(0,j) * weight
+            double S2 = 0.0;
+            for (int q = 0; q < p.nq; q++)
+                S2 += __ldg(p.dphi + ((size_t)q * p.fdim) * N + i) * __ldg(p.dphi + ((size_t)q * p.fdim) * N + j) * W2[q];
+            const size_t sidx = ((size_t)((i * N + j) * NS) * NS) * p.nel + el;
+            const int32_t pos = p.smap[sidx];
+            if (pos >= 0) scatter_add(p.a + pos, cgrad * S2, p.atomic);
+            if (p.smapT && i != j) {
+                const int32_t posT = p.smapT[sidx];
+                if (posT >= 0) scatter_add(p.a + posT, cgrad * S2, p.atomic);
+            }
+        }
         for (int a = 0; a < NS; a++)
             for (int b = 0; b < NS; b++) {
                 if (i == j && b < a) continue;
@@ -954,6 +977,7 @@ struct b200asm_ctx {
     int scatter = B200ASM_SCATTER_ATOMIC;
     int engine = 1;  // 1: DMMA panel kernel where one exists, 0: register-tile DFMA kernels only
     int debug = 0;     // profiling aid, see VolParams::debug
+    int drop_tiny = 0;  // option "drop_tiny": the matrix scatter skips |value| < 1e-12 like the reference's AddKel (entry-major kernels only)
     int variant = 0;   // tuning alternative of the DMMA kernels (option "variant", before add_group)
     int rhs_only = 0;  // set while b200asm_assemble_rhs runs
     int timing = 0;  // 1: record CUDA events around every group's launches (b200asm_group_time_ms)
@@ -1296,7 +1320,7 @@ const MmaEntry kAffHex[] = {make_affhex_entry<HexP1PoissonAff>(1), make_affhex_e
                             make_affhex_entry<HexP2PoissonAff>(2), make_affhex_entry<HexP2ElastAff>(2)};
 constexpr int kNumAffHex = sizeof(kAffHex) / sizeof(kAffHex[0]);
 // volume group run by assemble_volume_generic_kernel (no specialised kernel, or engine 2 = the generic kernel everywhere)
-bool runs_generic(const b200asm_ctx *ctx, const Group &g) { return g.dim == 3 && (g.generic || ctx->engine == 2); }
+bool runs_generic(const b200asm_ctx *ctx, const Group &g) { return g.dim == 3 && (g.generic || ctx->engine == 2 || ctx->drop_tiny); }
 // groups whose scatter map is entry-major ([entry][element]): boundary elements, plane elements, generic volume groups
 bool entry_major(const b200asm_ctx *ctx, const Group &g) { return g.kind == B200ASM_BC || g.plane || runs_generic(ctx, g); }
 // the kernel that runs a volume group on the DMMA / closed-form engine (nullptr: register-tile kernel)
@@ -1318,14 +1342,14 @@ cudaError_t launch_bc(const BcParams &p, cudaStream_t s) {
 cudaError_t dispatch_bc(int topology, int porder, int nn, int n, int ns, const BcParams &p, cudaStream_t s) {
     if (topology == B200ASM_LINE) {  // boundary of a plane problem
         const int grid = (int)((p.el1 - p.el0 + 3) / 4);
-        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, 2, n, ns);
+        assemble_bc_warp_kernel<<<grid, 128, 8 * (size_t)p.nq * sizeof(double), s>>>(p, 2, n, ns);
         return cudaGetLastError();
     }
     if (ns == 2) return cudaErrorInvalidValue;
-    if (porder >= 3 || porder == 0 || p.force) {  // (a table of boundary data: the runtime-size kernel reads it)
+    if (porder >= 3 || porder == 0 || p.force || p.coef[12] != 0.0) {  // (a table of boundary data, or the gradient term: the runtime-size kernel)
         if (topology != B200ASM_QUAD && topology != B200ASM_TRI) return cudaErrorInvalidValue;
         const int grid = (int)((p.el1 - p.el0 + 3) / 4);
-        assemble_bc_warp_kernel<<<grid, 128, 4 * (size_t)p.nq * sizeof(double), s>>>(p, nn, n, ns);
+        assemble_bc_warp_kernel<<<grid, 128, 8 * (size_t)p.nq * sizeof(double), s>>>(p, nn, n, ns);
         return cudaGetLastError();
     }
     if (topology == B200ASM_QUAD && porder == 1) return ns == 1 ? launch_bc<4, 4, 1>(p, s) : launch_bc<4, 4, 3>(p, s);
@@ -1473,6 +1497,15 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
 // ------------------------------------------------------------------------------------------------
 extern "C" const char *b200asm_last_error(const b200asm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+extern "C" int b200asm_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return ndev;
+}
+
 extern "C" int b200asm_create(b200asm_ctx **out, int device) {
     b200asm_ctx *ctx = nullptr;
     if (!out) return fail(ctx, B200ASM_EINVAL, "b200asm_create: out == NULL");
@@ -1543,6 +1576,12 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
     }
     if (!strcmp(name, "debug")) {
         ctx->debug = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "drop_tiny")) {
+        ctx->drop_tiny = value ? 1 : 0;
+        ctx->maps_valid = false;  // every volume group moves to the generic (entry-major) kernel
+        for (Group &g : ctx->groups) g.aff_checked = false;
         return 0;
     }
     if (!strcmp(name, "variant")) {
@@ -2093,7 +2132,7 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
         p.nel = g.nel; p.nq = g.nq; p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
         p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng; p.smap = g.d_smap; p.smapT = g.d_smapT;
         p.kind = g.kind; p.fdim = g.dim; p.force = g.d_force;
-        p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic; p.rhs_only = ctx->rhs_only;
+        p.a = ctx->d_a; p.rhs = ctx->d_rhs; p.atomic = atomic | (ctx->drop_tiny ? 4 : 0); p.rhs_only = ctx->rhs_only;
         memcpy(p.coef, g.coef, sizeof(p.coef));
         for (size_t c = 0; c < nseg; c++) {
             p.el0 = g.seg[c]; p.el1 = g.seg[c + 1];

@@ -155,35 +155,128 @@ void ShapeTables(TPZCompEl *cel, HostGroup &g) {
 }  // namespace
 
 struct TPZB200AssemblyCache {
+    // the engine: ONE context (one GPU) or a b200asm_multi (several GPUs of this process); same calls either way
     b200asm_ctx *ctx = nullptr;
+    b200asm_multi *multi = nullptr;
+    std::vector<int> devices;  // the devices the engine was created on
     TPZCompMesh *mesh = nullptr;
     int64_t nelem = -1, neq = -1, nconnects = -1, nnz = -1;
     int64_t nactive = -1;  // equations of the assembled system: NEquations(), or NActiveEquations() of an active filter
+    uint64_t signature = 0;     // hash of what the flattened arrays were derived from (MeshSignature)
+    uint64_t pattern_hash = 0;  // hash of the IA / JA the engine holds
     int symmetric = -1;
     bool pattern_set = false;
+    bool drop_tiny = false;
+    int nloadcases = 1;
     std::vector<HostGroup> groups;
     double flatten_ms = 0, pattern_ms = 0, assemble_ms = 0;
     void *pinned = nullptr;  // value array page-locked by SetPinHostMatrix
     size_t pinned_bytes = 0;
+    std::vector<double> accum;  // previous values of the matrix (SetAccumulate)
+
+    b200asm_ctx *AnyContext() {
+        if (ctx) return ctx;
+        b200asm_ctx *c0 = nullptr;
+        if (multi) b200asm_multi_context(multi, 0, &c0);
+        return c0;
+    }
+    const char *LastError() const { return multi ? b200asm_multi_last_error(multi) : b200asm_last_error(ctx); }
+    int SetOption(const char *name, int64_t v) { return multi ? b200asm_multi_set_option(multi, name, v) : b200asm_set_option(ctx, name, v); }
+    int SetNodes(int64_t n, const double *xyz) { return multi ? b200asm_multi_set_nodes(multi, n, xyz) : b200asm_set_nodes(ctx, n, xyz); }
+    int AddGroup(const b200asm_group *g) { return multi ? b200asm_multi_add_group(multi, g) : b200asm_add_group(ctx, g); }
+    int SetGroupCoef(int gi, const double *coef) { return multi ? b200asm_multi_set_group_coef(multi, gi, coef) : b200asm_set_group_coef(ctx, gi, coef); }
+    int SetGroupForce(int gi, const double *f) { return multi ? b200asm_multi_set_group_force(multi, gi, f) : b200asm_set_group_force(ctx, gi, f); }
+    int ClearGroups() { return multi ? b200asm_multi_clear_groups(multi) : b200asm_clear_groups(ctx); }
+    int SetPattern(int64_t n, const int64_t *ia, const int64_t *ja, int sym) {
+        return multi ? b200asm_multi_set_pattern(multi, n, ia, ja, sym) : b200asm_set_pattern(ctx, n, ia, ja, sym);
+    }
+    int Assemble(double *a, double *rhs) { return multi ? b200asm_multi_assemble(multi, a, rhs) : b200asm_assemble(ctx, a, rhs); }
+    int AssembleRhs(double *rhs) { return multi ? b200asm_multi_assemble_rhs(multi, rhs) : b200asm_assemble_rhs(ctx, rhs); }
+
     void Unpin() {
-        if (pinned && ctx) b200asm_unpin_host(ctx, pinned);
+        if (pinned && AnyContext()) b200asm_unpin_host(AnyContext(), pinned);
         pinned = nullptr;
         pinned_bytes = 0;
     }
-    ~TPZB200AssemblyCache() {
+    void DestroyEngine() {
         Unpin();
         if (ctx) b200asm_destroy(ctx);
+        if (multi) b200asm_multi_destroy(multi);
+        ctx = nullptr;
+        multi = nullptr;
+        devices.clear();
+        mesh = nullptr;
+        nelem = neq = nconnects = nnz = nactive = -1;
+        signature = pattern_hash = 0;
+        pattern_set = false;
+        groups.clear();
     }
+    ~TPZB200AssemblyCache() { DestroyEngine(); }
 };
 
 namespace {
 
 void Check(TPZB200AssemblyCache &c, int rc, const char *what) {
-    if (rc < 0) Fatal(std::string(what) + " failed: " + b200asm_last_error(c.ctx));
+    if (rc < 0) Fatal(std::string(what) + " failed: " + c.LastError());
+}
+
+// 64-bit mix (splitmix64 finaliser) folded over a stream of words
+inline void HashWord(uint64_t &h, uint64_t v) {
+    v += 0x9E3779B97F4A7C15ull + h;
+    v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull;
+    v = (v ^ (v >> 27)) * 0x94D049BB133111EBull;
+    h = (h * 0x100000001B3ull) ^ (v ^ (v >> 31));
+}
+
+// What the flattened arrays depend on besides node coordinates and material constants (those are refreshed at every
+// Assemble): the element list, the material object and id of every element, the ShouldCompute outcome, per connect its block
+// position, block size and order, the geometric corner nodes, and the equation filter.  Connect renumbering (Permute), p
+// changes, SetMaterialIds and replaced material objects all change it.
+uint64_t MeshSignature(TPZStructMatrix *strmat) {
+    TPZCompMesh *cmesh = strmat->Mesh();
+    uint64_t h = 0x243F6A8885A308D3ull;
+    const int64_t nel = cmesh->NElements();
+    HashWord(h, (uint64_t)nel);
+    HashWord(h, (uint64_t)cmesh->NEquations());
+    const TPZEquationFilter &filter = strmat->EquationFilter();
+    HashWord(h, filter.IsActive() ? (uint64_t)filter.NActiveEquations() + 1 : 0);
+    for (int64_t iel = 0; iel < nel; iel++) {
+        TPZCompEl *cel = cmesh->Element(iel);
+        if (!cel) { HashWord(h, 1); continue; }
+        TPZMaterial *mat = cel->Material();
+        if (!mat) { HashWord(h, 2); continue; }
+        if (!strmat->ShouldCompute(mat->Id())) { HashWord(h, 3); continue; }
+        HashWord(h, (uint64_t)(uintptr_t)mat);
+        HashWord(h, (uint64_t)(int64_t)mat->Id());
+        const int ncon = cel->NConnects();
+        for (int i = 0; i < ncon; i++) {
+            TPZConnect &con = cel->Connect(i);
+            const int64_t seq = con.SequenceNumber();
+            HashWord(h, (uint64_t)cmesh->Block().Position(seq) * 64u + (uint64_t)con.Order());
+            HashWord(h, (uint64_t)cmesh->Block().Size(seq));
+        }
+        TPZGeoEl *gel = cel->Reference();
+        if (gel) {
+            const int nc = gel->NCornerNodes();
+            for (int i = 0; i < nc; i++) HashWord(h, (uint64_t)gel->NodeIndex(i));
+        }
+    }
+    return h;
+}
+
+uint64_t PatternHash(int64_t neq, const int64_t *ia, const int64_t *ja) {
+    uint64_t h = 0x13198A2E03707344ull;
+    HashWord(h, (uint64_t)neq);
+    for (int64_t i = 0; i <= neq; i++) HashWord(h, (uint64_t)ia[i]);
+    const int64_t nnz = ia[neq];
+    const int64_t stride = std::max<int64_t>(1, nnz / (1 << 20));  // the row pointers pin the shape; the columns are sampled
+    for (int64_t k = 0; k < nnz; k += stride) HashWord(h, (uint64_t)ja[k]);
+    return h;
 }
 
 // material constants of a group, re-read at every Assemble (they may change between assemblies)
-void FillCoef(HostGroup &g) {
+// load case lc (TPZMatLoadCases: only TPZMatPoisson evaluates more than one, Material/Poisson/TPZMatPoisson.cpp:23,56-70)
+void FillCoef(HostGroup &g, int lc = 0) {
     double *coef = g.meta.coef;
     std::memset(coef, 0, sizeof(double) * 16);
     TPZMaterial *mat = g.material;
@@ -196,11 +289,18 @@ void FillCoef(HostGroup &g) {
         const TPZVec<STATE> &v2 = bc->Val2();
         if (auto *pois = dynamic_cast<TPZMatPoisson<STATE> *>(vol)) {
             const double big = pois->BigNumber();
+            // the value of load case lc: TPZMatLoadCasesBC::GetBCRhsVal (TPZMatPoisson.cpp:64-68; Val2() without a value vector)
+            double v2l = v2[0];
+            if (auto *lcbc = dynamic_cast<TPZMatLoadCasesBC<STATE> *>(bc)) v2l = lcbc->GetBCRhsVal(lc)[0];
             if (type == 0) {  // Material/Poisson/TPZMatPoisson.cpp:79-90
                 coef[0] = big;
-                coef[9] = big * v2[0];
+                coef[9] = big * v2l;
             } else if (type == 1) {  // :93-100
-                coef[9] = v2[0] * pois->ScaleFactor();
+                coef[9] = v2l * pois->ScaleFactor();
+            } else if (type == 2) {  // :104-118 as the reference computes it (then "not implemented" is printed): penalty load
+                                     // vector and BigNumber * Val1(0,0) * dphix(0,i) * dphix(0,j) in the matrix
+                coef[9] = big * v2l;
+                coef[12] = big * v1.GetVal(0, 0);
             } else {
                 Fatal("TPZMatPoisson boundary condition type " + std::to_string(type) + " is not supported");
             }
@@ -234,6 +334,9 @@ void FillCoef(HostGroup &g) {
                 }
             } else if (type == 3) {  // directional null Dirichlet, TPZElasticity3D.cpp:715-723
                 for (int a = 0; a < 3; a++) coef[a * 3 + a] = big * v2[a];
+            } else if (type == 4) {
+                // stress-field Neumann, :724-737: ef += -(Val1 . normal) phi w; the normal of every integration point is
+                // tabulated by FillForce (the kernel reads the load-vector coefficients from the table), no matrix part
             } else if (type >= 5 && type <= 8) {  // directional Dirichlet on x / y / z / x and z, :739-772
                 const bool on[3] = {type == 5 || type == 8, type == 6, type == 7 || type == 8};
                 for (int a = 0; a < 3; a++)
@@ -242,7 +345,7 @@ void FillCoef(HostGroup &g) {
                         coef[9 + a] = big * v2[a];
                     }
             } else {
-                Fatal("TPZElasticity3D boundary condition type " + std::to_string(type) + " is not supported (type 4 needs the face normal)");
+                Fatal("TPZElasticity3D boundary condition type " + std::to_string(type) + " is not supported");
             }
         } else {
             Fatal("boundary condition of an unsupported material");
@@ -290,11 +393,81 @@ void FillCoef(HostGroup &g) {
 }
 
 // forcing std::function evaluated on the host at every integration point (Material/TPZMatTypes.h:15-19)
-void FillForce(HostGroup &g) {
+// the outward unit normal of a boundary face at a point, as TPZInterpolationSpace::ComputeNormal builds it
+// (Mesh/pzinterpolationspace.cpp:300-383): axes(0) x axes(1) of TPZGeoEl::Jacobian, normalised, turned so that it points away
+// from the centre of the neighbouring volume element
+void FaceNormal(TPZCompMesh *cmesh, TPZGeoEl *gel, TPZVec<REAL> &qsi, const TPZVec<REAL> &towards, TPZVec<REAL> &normal) {
+    TPZFNMatrix<9, REAL> jac, axes, jacinv;
+    REAL detjac;
+    gel->Jacobian(qsi, jac, axes, detjac, jacinv);
+    normal.Resize(3);
+    normal[0] = axes(0, 1) * axes(1, 2) - axes(0, 2) * axes(1, 1);
+    normal[1] = -axes(0, 0) * axes(1, 2) + axes(0, 2) * axes(1, 0);
+    normal[2] = axes(0, 0) * axes(1, 1) - axes(0, 1) * axes(1, 0);
+    REAL size = 0.;
+    for (int i = 0; i < 3; i++) size += normal[i] * normal[i];
+    size = sqrt(size);
+    for (int i = 0; i < 3; i++) normal[i] /= size;
+    REAL dot = 0.;
+    for (int i = 0; i < 3; i++) dot += normal[i] * towards[i];
+    if (dot < 0.)
+        for (int i = 0; i < 3; i++) normal[i] *= -1.;
+}
+
+// vector from the centre of the neighbouring volume element to the centre of the face (ComputeNormal's `vec`, :316-345)
+bool OutwardVector(TPZCompMesh *cmesh, TPZGeoEl *gel, TPZVec<REAL> &vec) {
+    const int face = gel->NSides() - 1;
+    TPZGeoElSide thisside(gel, face);
+    TPZGeoElSide neigh = gel->Neighbour(face);
+    while (neigh != thisside) {
+        const int matid = neigh.Element()->MaterialId();
+        if (cmesh->FindMaterial(matid) && neigh.Element()->Dimension() > gel->Dimension()) break;
+        neigh = neigh.Neighbour();
+    }
+    TPZGeoEl *vol = neigh.Element();
+    if (vol == gel) return false;
+    TPZManVector<REAL, 3> c0(gel->Dimension(), 0.), c1(vol->Dimension(), 0.), x0(3, 0.), x1(3, 0.);
+    gel->CenterPoint(face, c0);
+    vol->CenterPoint(vol->NSides() - 1, c1);
+    gel->X(c0, x0);
+    vol->X(c1, x1);
+    vec.Resize(3);
+    for (int i = 0; i < 3; i++) vec[i] = -x1[i] + x0[i];
+    return true;
+}
+
+void FillForce(HostGroup &g, int lc = 0) {
     g.has_forcing = false;
     g.meta.force = nullptr;
     const int ns = g.meta.nstate;
     if (g.meta.kind == B200ASM_BC) {
+        if (auto *bc4 = dynamic_cast<TPZBndCondT<STATE> *>(g.material))
+            if (bc4->Type() == 4 && dynamic_cast<TPZElasticity3D *>(bc4->Material())) {
+                // TPZElasticity3D stress-field Neumann (TPZElasticity3D.cpp:724-737): val2loc = -(Val1 . normal) per point
+                if (g.meta.topology != B200ASM_QUAD && g.meta.topology != B200ASM_TRI) Fatal("boundary condition type 4 on an element that is not a face");
+                const int nq = g.meta.nqp;
+                g.force.assign((size_t)g.meta.nel * nq * 3, 0.0);
+                TPZManVector<REAL, 3> qsi(2), x(3), vec(3, 0.), normal(3, 0.);
+                for (int64_t e = 0; e < g.meta.nel; e++) {
+                    TPZGeoEl *gel = g.elements[e]->Reference();
+                    const bool has_neighbour = OutwardVector(g.elements[e]->Mesh(), gel, vec);
+                    for (int q = 0; q < nq; q++) {
+                        for (int d = 0; d < 2; d++) qsi[d] = g.qpts[(size_t)q * 2 + d];
+                        TPZFNMatrix<9, STATE> v1(bc4->Val1());
+                        if (bc4->HasForcingFunctionBC()) {  // :637-645: the function may replace Val1 (and val2loc[0], unused here)
+                            gel->X(qsi, x);
+                            TPZManVector<STATE, 3> v2(3, 0.);
+                            bc4->ForcingFunctionBC()(x, v2, v1);
+                        }
+                        if (has_neighbour) FaceNormal(g.elements[e]->Mesh(), gel, qsi, vec, normal); else normal.Fill(0.);
+                        double *out = &g.force[((size_t)e * nq + q) * 3];
+                        for (int a = 0; a < 3; a++) out[a] = -(v1(a, 0) * normal[0] + v1(a, 1) * normal[1] + v1(a, 2) * normal[2]);
+                    }
+                }
+                g.has_forcing = true;
+                g.meta.force = g.force.data();
+                return;
+            }
         // boundary data given by a function (TPZBndCondT::ForcingFunctionBC): evaluated on the host at data.x of every
         // integration point, stored as the coefficient of phi_i * weight in ef (what the constant case keeps in coef[9..11])
         auto *bc = dynamic_cast<TPZBndCondT<STATE> *>(g.material);
@@ -304,7 +477,7 @@ void FillForce(HostGroup &g) {
         auto *e2 = dynamic_cast<TPZElasticity2D *>(vol);
         auto *e3 = dynamic_cast<TPZElasticity3D *>(vol);
         const int type = bc->Type();
-        const bool ok = pois ? (type == 0 || type == 1) : (e2 ? (type == 0 || type == 1) : (e3 ? (type == 0 || type == 2 || (type >= 5 && type <= 8)) : false));
+        const bool ok = pois ? (type == 0 || type == 1 || type == 2) : (e2 ? (type == 0 || type == 1) : (e3 ? (type == 0 || type == 2 || (type >= 5 && type <= 8)) : false));
         if (!ok) Fatal("boundary condition type " + std::to_string(type) + " with a forcing function is not supported");
         const int fdim = g.meta.topology == B200ASM_LINE ? 1 : 2;
         const int nq = g.meta.nqp;
@@ -315,12 +488,12 @@ void FillForce(HostGroup &g) {
             for (int q = 0; q < nq; q++) {
                 for (int d = 0; d < fdim; d++) qsi[d] = g.qpts[(size_t)q * fdim + d];
                 gel->X(qsi, x);
-                TPZManVector<STATE, 3> v2(e3 ? 3 : ns, 0.);
+                TPZManVector<STATE, 10> v2(e3 ? 3 : (pois ? std::max(1, pois->NumLoadCases()) : ns), 0.);
                 TPZFNMatrix<9, STATE> v1(bc->Val1());
                 bc->ForcingFunctionBC()(x, v2, v1);
                 double *out = &g.force[((size_t)e * nq + q) * ns];
-                if (pois) {  // Material/Poisson/TPZMatPoisson.cpp:79-100
-                    out[0] = type == 0 ? pois->BigNumber() * v2[0] : v2[0] * pois->ScaleFactor();
+                if (pois) {  // Material/Poisson/TPZMatPoisson.cpp:79-118: v2[nvars * l + iv] of load case l
+                    out[0] = type == 1 ? v2[lc] * pois->ScaleFactor() : pois->BigNumber() * v2[lc];
                 } else if (e2) {  // Material/Elasticity/TPZElasticity2D.cpp:256-283
                     for (int a = 0; a < 2; a++) out[a] = type == 0 ? e2->BigNumber() * v2[a] : v2[a];
                 } else {  // Material/Elasticity/TPZElasticity3D.cpp:637-697,739-772
@@ -360,9 +533,10 @@ void FillForce(HostGroup &g) {
             for (int q = 0; q < nq; q++) {
                 for (int d = 0; d < 2; d++) qsi[d] = g.qpts[(size_t)q * 2 + d];
                 gel->X(qsi, x);
-                TPZManVector<STATE, 3> f(3, 0.);
+                TPZManVector<STATE, 10> f(p2 ? std::max(3, p2->NumLoadCases()) : 3, 0.);
                 if (p2) p2->ForcingFunction()(x, f); else e2->ForcingFunction()(x, f);
-                for (int k = 0; k < ns; k++) g.force[((size_t)e * nq + q) * ns + k] = f[k];
+                if (p2) g.force[((size_t)e * nq + q)] = f[lc];
+                else for (int k = 0; k < ns; k++) g.force[((size_t)e * nq + q) * ns + k] = f[k];
             }
         }
         g.has_forcing = true;
@@ -381,9 +555,10 @@ void FillForce(HostGroup &g) {
         for (int q = 0; q < nq; q++) {
             for (int d = 0; d < 3; d++) qsi[d] = g.qpts[(size_t)q * 3 + d];
             gel->X(qsi, x);
-            TPZManVector<STATE, 3> f(ns, 0.);
+            TPZManVector<STATE, 10> f(pois ? std::max(1, pois->NumLoadCases()) : ns, 0.);
             if (pois) {
                 pois->ForcingFunction()(x, f);
+                f[0] = f[lc];
             } else {
                 auto *acc = static_cast<ElastAccess *>(el);
                 for (int k = 0; k < 3; k++) f[k] = acc->fForce[k];  // locForce(fForce) then the callback
@@ -399,6 +574,7 @@ void FillForce(HostGroup &g) {
 void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
     TPZCompMesh *cmesh = strmat->Mesh();
     c.groups.clear();
+    c.nloadcases = 1;
     // active equation filter (StrMatrix/TPZEquationFilter.h): destination indices become the condensed numbers, removed
     // equations get -1 — what TPZEquationFilter::Filter does per element in the reference (pzstrmatrixor.cpp:205-214)
     std::vector<int64_t> eqmap;
@@ -464,8 +640,12 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
             else if (dynamic_cast<TPZElasticity3D *>(mat)) g.meta.kind = B200ASM_ELASTICITY3D;
             else if (dynamic_cast<TPZElasticity2D *>(mat)) g.meta.kind = B200ASM_ELASTICITY2D;
             else Fatal("unsupported material id " + std::to_string(mat->Id()));
-            if (auto *lc = dynamic_cast<TPZMatLoadCasesBase *>(mat))
-                if (lc->NumLoadCases() != 1) Fatal("more than one load case is not supported");
+            if (auto *lc = dynamic_cast<TPZMatLoadCasesBase *>(mat)) {
+                // several load cases: only TPZMatPoisson evaluates them (TPZElasticity3D / 2D write column 0 only)
+                if (lc->NumLoadCases() > 1 && !isbc && !dynamic_cast<TPZMatPoisson<STATE> *>(mat))
+                    Fatal("more than one load case is supported for TPZMatPoisson only");
+                c.nloadcases = std::max(c.nloadcases, lc->NumLoadCases());
+            }
             switch (topo) {
                 case B200ASM_HEX: ShapeTables<pzshape::TPZShapeCube>(cel, g); break;
                 case B200ASM_TET: ShapeTables<pzshape::TPZShapeTetra>(cel, g); break;
@@ -499,8 +679,8 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
     std::vector<double> xyz((size_t)nnodes * 3);
     for (int64_t i = 0; i < nnodes; i++)
         for (int d = 0; d < 3; d++) xyz[(size_t)i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
-    Check(c, b200asm_clear_groups(c.ctx), "b200asm_clear_groups");
-    Check(c, b200asm_set_nodes(c.ctx, nnodes, xyz.data()), "b200asm_set_nodes");
+    Check(c, c.ClearGroups(), "b200asm_clear_groups");
+    Check(c, c.SetNodes(nnodes, xyz.data()), "b200asm_set_nodes");
     for (HostGroup &g : c.groups) {
         g.meta.nel = (int64_t)g.elements.size();
         g.meta.elnodes = g.elnodes.data();
@@ -511,32 +691,69 @@ void Flatten(TPZB200AssemblyCache &c, TPZStructMatrix *strmat) {
         g.meta.dphi = g.dphi.data();
         FillCoef(g);
         FillForce(g);
-        Check(c, b200asm_add_group(c.ctx, &g.meta), "b200asm_add_group");
+        Check(c, c.AddGroup(&g.meta), "b200asm_add_group");
     }
     c.mesh = cmesh;
     c.nelem = nel;
     c.neq = cmesh->NEquations();
     c.nactive = filter.IsActive() ? filter.NActiveEquations() : c.neq;
     c.nconnects = cmesh->NConnects();
-    c.pattern_set = false;
+    // One context keeps a resident pattern across b200asm_clear_groups (only the scatter maps are rebuilt), e.g. the pattern
+    // Create() built on the device; Assemble() compares its hash with the matrix it is handed.  Several GPUs: the row
+    // partition follows the elements, so the pattern is set again.
+    if (c.multi) c.pattern_set = false;
 }
 
 }  // namespace
 
 namespace {
-// (re)flatten when the mesh changed, otherwise refresh node coordinates and material constants
-void PrepareMesh(TPZB200AssemblyCache &c, TPZStructMatrix *strmat, int device) {
-    TPZCompMesh *cmesh = strmat->Mesh();
-    if (!c.ctx) {
-        if (b200asm_create(&c.ctx, device) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
+// the devices of the engine: an explicit list, else the first min(n, present) devices for SetNumThreads(n >= 2), else one
+std::vector<int> WantedDevices(int device, const std::vector<int> &devices, int numthreads) {
+    if (!devices.empty()) return devices;
+    if (numthreads >= 2) {
+        const int present = b200asm_device_count();
+        const int n = std::min(numthreads, std::min(present, B200ASM_MAX_PEERS / 2));
+        if (n >= 2) {
+            std::vector<int> d(n);
+            for (int k = 0; k < n; k++) d[k] = k;
+            return d;
+        }
     }
+    return {device};
+}
+
+void EnsureEngine(TPZB200AssemblyCache &c, const std::vector<int> &want, bool drop_tiny) {
+    if ((c.ctx || c.multi) && c.devices == want && c.drop_tiny == drop_tiny) return;
+    c.DestroyEngine();
+    if (want.size() == 1) {
+        if (b200asm_create(&c.ctx, want[0]) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
+    } else {
+        if (b200asm_multi_create(&c.multi, (int)want.size(), want.data()) != 0)
+            Fatal(std::string("b200asm_multi_create: ") + b200asm_multi_last_error(nullptr));
+    }
+    c.devices = want;
+    c.drop_tiny = drop_tiny;
+    if (drop_tiny) Check(c, c.SetOption("drop_tiny", 1), "option drop_tiny");
+}
+
+// (re)flatten when the mesh changed, otherwise refresh node coordinates, material constants and forcing tables
+void PrepareMesh(TPZB200AssemblyCache &c, TPZStructMatrix *strmat, bool check_mesh, bool static_forcing) {
+    TPZCompMesh *cmesh = strmat->Mesh();
     auto t0 = clk::now();
     c.flatten_ms = 0;
     const TPZEquationFilter &filter = strmat->EquationFilter();
     const int64_t nactive = filter.IsActive() ? filter.NActiveEquations() : cmesh->NEquations();
-    if (c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects() ||
-        c.nactive != nactive) {
+    bool stale = c.mesh != cmesh || c.nelem != cmesh->NElements() || c.neq != cmesh->NEquations() || c.nconnects != cmesh->NConnects() ||
+                 c.nactive != nactive;
+    uint64_t sig = c.signature;
+    if (!stale && check_mesh) {
+        sig = MeshSignature(strmat);
+        stale = sig != c.signature;
+    }
+    if (stale) {
         Flatten(c, strmat);
+        c.signature = check_mesh ? (sig != c.signature ? sig : MeshSignature(strmat)) : 0;
+        if (check_mesh && c.signature == 0) c.signature = 1;
         c.flatten_ms = ms_since(t0);
         return;
     }
@@ -545,11 +762,33 @@ void PrepareMesh(TPZB200AssemblyCache &c, TPZStructMatrix *strmat, int device) {
     std::vector<double> xyz((size_t)nnodes * 3);
     for (int64_t i = 0; i < nnodes; i++)
         for (int d = 0; d < 3; d++) xyz[(size_t)i * 3 + d] = gmesh->NodeVec()[i].Coord(d);
-    Check(c, b200asm_set_nodes(c.ctx, nnodes, xyz.data()), "b200asm_set_nodes");
+    Check(c, c.SetNodes(nnodes, xyz.data()), "b200asm_set_nodes");
     int gi = 0;
     for (HostGroup &g : c.groups) {
         FillCoef(g);
-        Check(c, b200asm_set_group_coef(c.ctx, gi++, g.meta.coef), "b200asm_set_group_coef");
+        Check(c, c.SetGroupCoef(gi, g.meta.coef), "b200asm_set_group_coef");
+        // forcing functions and boundary functions are called again at every assembly, like the reference's Contribute does
+        // (they may depend on time, and the nodes may have moved)
+        if (g.has_forcing && !static_forcing) {
+            FillForce(g);
+            if (!g.has_forcing) Fatal("a forcing function was removed from a material: call Invalidate()");
+            Check(c, c.SetGroupForce(gi, g.force.data()), "b200asm_set_group_force");
+        }
+        gi++;
+    }
+}
+
+// load case lc >= 1: the groups whose data depend on the load case get the coefficients / tables of that case
+void SelectLoadCase(TPZB200AssemblyCache &c, int lc) {
+    int gi = 0;
+    for (HostGroup &g : c.groups) {
+        FillCoef(g, lc);
+        Check(c, c.SetGroupCoef(gi, g.meta.coef), "b200asm_set_group_coef");
+        if (g.has_forcing) {
+            FillForce(g, lc);
+            Check(c, c.SetGroupForce(gi, g.force.data()), "b200asm_set_group_force");
+        }
+        gi++;
     }
 }
 }  // namespace
@@ -560,13 +799,19 @@ TPZStructMatrixB200<TVar>::TPZStructMatrixB200() : fCache(std::make_shared<TPZB2
 // copies (TPZStructMatrix::Clone through TPZAnalysis::SetStructuralMatrix) start with an empty cache
 template <class TVar>
 TPZStructMatrixB200<TVar>::TPZStructMatrixB200(const TPZStructMatrixB200 &copy)
-    : TPZStrMatParInterface(copy), fDevice(copy.fDevice), fPinHost(copy.fPinHost), fCache(std::make_shared<TPZB200AssemblyCache>()) {}
+    : TPZStrMatParInterface(copy), fDevice(copy.fDevice), fDevices(copy.fDevices), fPinHost(copy.fPinHost), fAccumulate(copy.fAccumulate),
+      fDropTiny(copy.fDropTiny), fStaticForcing(copy.fStaticForcing), fCheckMesh(copy.fCheckMesh), fCache(std::make_shared<TPZB200AssemblyCache>()) {}
 
 template <class TVar>
 TPZStructMatrixB200<TVar> &TPZStructMatrixB200<TVar>::operator=(const TPZStructMatrixB200 &copy) {
     TPZStrMatParInterface::operator=(copy);
     fDevice = copy.fDevice;
+    fDevices = copy.fDevices;
     fPinHost = copy.fPinHost;
+    fAccumulate = copy.fAccumulate;
+    fDropTiny = copy.fDropTiny;
+    fStaticForcing = copy.fStaticForcing;
+    fCheckMesh = copy.fCheckMesh;
     fCache = std::make_shared<TPZB200AssemblyCache>();
     return *this;
 }
@@ -577,6 +822,18 @@ TPZStructMatrixB200<TVar>::~TPZStructMatrixB200() = default;
 template <class TVar>
 void TPZStructMatrixB200<TVar>::UnpinHostMatrix() {
     fCache->Unpin();
+}
+
+template <class TVar>
+void TPZStructMatrixB200<TVar>::Invalidate() {
+    fCache->mesh = nullptr;
+    fCache->signature = 0;
+    fCache->pattern_set = false;
+}
+
+template <class TVar>
+int TPZStructMatrixB200<TVar>::NumDevicesUsed() const {
+    return (int)fCache->devices.size();
 }
 
 template <class TVar>
@@ -596,9 +853,9 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     auto *full = dynamic_cast<TPZFYsmpMatrix<STATE> *>(&stiffness);
     if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
     if (!sym && !full) Fatal("the stiffness matrix must be TPZSYsmpMatrix<STATE> or TPZFYsmpMatrix<STATE>");
-    TPZCompMesh *cmesh = strmat->Mesh();
     TPZB200AssemblyCache &c = *fCache;
-    PrepareMesh(c, strmat, fDevice);
+    EnsureEngine(c, WantedDevices(fDevice, fDevices, this->fNumThreads), fDropTiny);
+    PrepareMesh(c, strmat, fCheckMesh, fStaticForcing);
     if (guiInterface && guiInterface->AmIKilled()) return;
     // pattern of the matrix Create() produced
     auto t0 = clk::now();
@@ -606,54 +863,86 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     const int symmetric = sym ? 1 : 0;
     double *values = nullptr;
     int64_t nnz = 0;
+    TPZVec<int64_t> ia_full, ja_full;
+    const int64_t *ia = nullptr, *ja = nullptr;
     if (sym) {
         nnz = sym->JA().size();
         values = &sym->A()[0];
+        ia = &sym->IA()[0];
+        ja = nnz ? &sym->JA()[0] : nullptr;
     } else {
         // values in place through the public TPZMatrix::Storage() (Matrix/pzmatrix.cpp:61-67)
         TPZFMatrixRef<STATE> st = full->Storage();
         nnz = st.Rows();
         values = &st(0, 0);
     }
-    if (!c.pattern_set || c.symmetric != symmetric || c.nnz != nnz) {
-        if (sym) {
-            Check(c, b200asm_set_pattern(c.ctx, sym->Rows(), &sym->IA()[0], &sym->JA()[0], 1), "b200asm_set_pattern");
-        } else {
-            TPZVec<int64_t> ia, ja;
-            TPZVec<STATE> a;
-            full->GetData(ia, ja, a);
-            Check(c, b200asm_set_pattern(c.ctx, full->Rows(), &ia[0], &ja[0], 0), "b200asm_set_pattern");
-        }
+    // Is the pattern the engine holds the pattern of this matrix?  Symmetric storage exposes IA / JA: their hash decides.
+    // TPZFYsmpMatrix only hands out copies (GetData, Matrix/pzysmp.h:284-288): fetched when the sizes disagree.
+    bool upload = !c.pattern_set || c.symmetric != symmetric || c.nnz != nnz;
+    uint64_t phash = c.pattern_hash;
+    if (sym) {
+        phash = PatternHash(stiffness.Rows(), ia, ja);
+        upload = upload || phash != c.pattern_hash;
+    } else if (upload) {
+        TPZVec<STATE> a;
+        full->GetData(ia_full, ja_full, a);
+        ia = &ia_full[0];
+        ja = nnz ? &ja_full[0] : nullptr;
+        phash = PatternHash(stiffness.Rows(), ia, ja);
+    }
+    if (upload) {
+        Check(c, c.SetPattern(stiffness.Rows(), ia, ja, symmetric), "b200asm_set_pattern");
         c.pattern_set = true;
         c.symmetric = symmetric;
         c.nnz = nnz;
+        c.pattern_hash = phash;
         c.pattern_ms = ms_since(t0);
     }
     if (guiInterface && guiInterface->AmIKilled()) return;
     // assemble; the reference ADDS into rhs (TPZFMatrix::AddFel), the matrix arrives zeroed
     t0 = clk::now();
     const int64_t neq = rhsmat->Rows();
-    if (neq != c.neq || rhsmat->Cols() != 1) Fatal("rhs has the wrong size (one load case, NEquations rows)");
+    const int ncols = (int)rhsmat->Cols();
+    if (neq != c.neq) Fatal("rhs has the wrong size (NEquations rows)");
+    if (ComputeRhs() && ncols < c.nloadcases)
+        Fatal("rhs has " + std::to_string(ncols) + " columns but the materials define " + std::to_string(c.nloadcases) + " load cases");
     if (stiffness.Rows() != c.nactive) Fatal("the matrix does not have NActiveEquations rows");
-    TPZFMatrix<STATE> rhsloc;  // condensed numbering when the filter is active
+    TPZFMatrix<STATE> rhsloc;  // condensed numbering when the filter is active; one column per load case
     double *rhsptr = nullptr;
     if (ComputeRhs()) {
-        rhsloc.Redim(c.nactive, 1);
+        rhsloc.Redim(c.nactive, c.nloadcases);
         rhsptr = &rhsloc(0, 0);
     }
     if (fPinHost && nnz > 0 && (c.pinned != values || c.pinned_bytes != (size_t)nnz * sizeof(double))) {
         c.Unpin();
-        Check(c, b200asm_pin_host(c.ctx, values, (size_t)nnz * sizeof(double)), "b200asm_pin_host");
+        Check(c, b200asm_pin_host(c.AnyContext(), values, (size_t)nnz * sizeof(double)), "b200asm_pin_host");
         c.pinned = values;
         c.pinned_bytes = (size_t)nnz * sizeof(double);
     }
-    Check(c, b200asm_assemble(c.ctx, values, rhsptr), "b200asm_assemble");
+    if (fAccumulate) c.accum.assign(values, values + nnz);  // TPZSYsmpMatrix::AddKel adds to what the matrix holds
+    Check(c, c.Assemble(values, rhsptr), "b200asm_assemble");
+    if (fAccumulate) {
+        for (int64_t k = 0; k < nnz; k++) values[k] += c.accum[k];
+        c.accum.clear();
+        c.accum.shrink_to_fit();
+    }
     if (rhsptr) {
+        // the other load cases (TPZMatPoisson.cpp:23-41,56-100): ek does not depend on the load case, so columns 1.. are
+        // load-vector-only assemblies with the data of that case
+        for (int lc = 1; lc < c.nloadcases; lc++) {
+            if (guiInterface && guiInterface->AmIKilled()) return;
+            SelectLoadCase(c, lc);
+            Check(c, c.AssembleRhs(&rhsloc(0, lc)), "b200asm_assemble_rhs");
+        }
+        if (c.nloadcases > 1) SelectLoadCase(c, 0);
         if (filter.IsActive()) {
             filter.Scatter(rhsloc, rhs);  // StrMatrix/pzstrmatrixor.cpp:47-62
         } else {
-            double *dst = &(*rhsmat)(0, 0);
-            for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc(i, 0);  // the reference adds into rhs (TPZFMatrix::AddFel)
+            for (int lc = 0; lc < c.nloadcases; lc++) {
+                double *dst = &(*rhsmat)(0, lc);
+                const double *src = &rhsloc(0, lc);
+                for (int64_t i = 0; i < neq; i++) dst[i] += src[i];  // the reference adds into rhs (TPZFMatrix::AddFel)
+            }
         }
     }
     c.assemble_ms = ms_since(t0);
@@ -670,18 +959,28 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZG
     auto *rhsmat = dynamic_cast<TPZFMatrix<STATE> *>(&rhs);
     if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
     TPZB200AssemblyCache &c = *fCache;
-    PrepareMesh(c, strmat, fDevice);
+    EnsureEngine(c, WantedDevices(fDevice, fDevices, this->fNumThreads), fDropTiny);
+    PrepareMesh(c, strmat, fCheckMesh, fStaticForcing);
     if (guiInterface && guiInterface->AmIKilled()) return;
     auto t0 = clk::now();
     const int64_t neq = rhsmat->Rows();
-    if (neq != c.neq || rhsmat->Cols() != 1) Fatal("rhs has the wrong size (one load case, NEquations rows)");
-    TPZFMatrix<STATE> rhsloc(c.nactive, 1, 0.);
-    Check(c, b200asm_assemble_rhs(c.ctx, &rhsloc(0, 0)), "b200asm_assemble_rhs");
+    if (neq != c.neq) Fatal("rhs has the wrong size (NEquations rows)");
+    if (rhsmat->Cols() < c.nloadcases) Fatal("rhs has fewer columns than the materials define load cases");
+    if (c.multi && !c.pattern_set) Fatal("Assemble(rhs) on several GPUs needs the row partition of a previous Assemble(stiffness, rhs)");
+    TPZFMatrix<STATE> rhsloc(c.nactive, c.nloadcases, 0.);
+    for (int lc = 0; lc < c.nloadcases; lc++) {
+        if (lc > 0) SelectLoadCase(c, lc);
+        Check(c, c.AssembleRhs(&rhsloc(0, lc)), "b200asm_assemble_rhs");
+    }
+    if (c.nloadcases > 1) SelectLoadCase(c, 0);
     if (filter.IsActive()) {
         filter.Scatter(rhsloc, rhs);  // StrMatrix/pzstrmatrixor.cpp:79-99
     } else {
-        double *dst = &(*rhsmat)(0, 0);
-        for (int64_t i = 0; i < neq; i++) dst[i] += rhsloc(i, 0);  // the reference ADDS into rhs (TPZFMatrix::AddFel)
+        for (int lc = 0; lc < c.nloadcases; lc++) {
+            double *dst = &(*rhsmat)(0, lc);
+            const double *src = &rhsloc(0, lc);
+            for (int64_t i = 0; i < neq; i++) dst[i] += src[i];  // the reference ADDS into rhs (TPZFMatrix::AddFel)
+        }
     }
     c.assemble_ms = ms_since(t0);
 }
@@ -692,14 +991,15 @@ template <class TVar>
 void TPZStructMatrixB200<TVar>::SolveCG(const TPZFMatrix<TVar> &F, TPZFMatrix<TVar> &result, int64_t &numiterations, REAL &tol,
                                         bool jacobi, int fromcurrent) {
     TPZB200AssemblyCache &c = *fCache;
+    if (c.multi) Fatal("SolveCG: the device CG runs on one GPU (SetDevice); the row-sharded matrix of several GPUs is downloaded by Assemble");
     if (!c.ctx || !c.pattern_set) Fatal("SolveCG: Assemble(stiffness, rhs) must run first (the matrix lives on the device)");
     if constexpr (std::is_same<TVar, double>::value) {
         if (F.Rows() != c.nactive || F.Cols() != 1) Fatal("SolveCG: F has the wrong size");
         if (!fromcurrent || result.Rows() != c.nactive || result.Cols() != 1) result.Redim(c.nactive, 1);
         int64_t iters = 0;
         double resid = 0;
-        Check(c, b200asm_cg_solve(c.ctx, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid),
-              "b200asm_cg_solve");
+        if (b200asm_cg_solve(c.ctx, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid) < 0)
+            Fatal(std::string("b200asm_cg_solve failed: ") + b200asm_last_error(c.ctx));
         numiterations = iters;
         tol = resid;
     } else {
@@ -745,9 +1045,8 @@ void TPZStructMatrixB200<TVar>::CreatePatternOnDevice(bool symmetric, TPZStack<i
         Fatal("Create() on the device does not support an active equation filter: use TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>");
     TPZCompMesh *cmesh = strmat->Mesh();
     TPZB200AssemblyCache &c = *fCache;
-    if (!c.ctx) {
-        if (b200asm_create(&c.ctx, fDevice) != 0) Fatal(std::string("b200asm_create: ") + b200asm_last_error(nullptr));
-    }
+    EnsureEngine(c, WantedDevices(fDevice, fDevices, this->fNumThreads), fDropTiny);
+    b200asm_ctx *pctx = c.AnyContext();  // (several GPUs: the first one builds the pattern, Assemble() then shards it)
     auto t0 = clk::now();
     // block table: TPZBlock::Position / Size per sequence number of the independent connects
     // (External/TPZRenumbering.cpp:76-110 works on NIndependentConnects() blocks)
@@ -759,16 +1058,18 @@ void TPZStructMatrixB200<TVar>::CreatePatternOnDevice(bool symmetric, TPZStack<i
     }
     const int64_t nel = elgraphindex.size() - 1;
     int64_t neq = 0, nnz = 0;
-    Check(c, b200asm_build_pattern_device(c.ctx, symmetric ? 1 : 0, nel, &elgraphindex[0], nel && elgraph.size() ? &elgraph[0] : nullptr,
-                                          nblock, bpos.data(), bsize.data(), &neq, &nnz),
-          "b200asm_build_pattern_device");
+    if (b200asm_build_pattern_device(pctx, symmetric ? 1 : 0, nel, &elgraphindex[0], nel && elgraph.size() ? &elgraph[0] : nullptr,
+                                     nblock, bpos.data(), bsize.data(), &neq, &nnz) < 0)
+        Fatal(std::string("b200asm_build_pattern_device failed: ") + b200asm_last_error(pctx));
     if (neq != cmesh->NEquations()) Fatal("device pattern: unexpected number of equations");
     ia.resize(neq + 1);
     ja.resize(nnz);
-    Check(c, b200asm_get_pattern(c.ctx, &ia[0], nnz ? &ja[0] : nullptr), "b200asm_get_pattern");
-    c.pattern_set = true;  // the next Assemble() finds its pattern resident (same nnz / storage kind)
+    if (b200asm_get_pattern(pctx, &ia[0], nnz ? &ja[0] : nullptr) < 0) Fatal(std::string("b200asm_get_pattern failed: ") + b200asm_last_error(pctx));
+    // one GPU: the next Assemble() finds its pattern resident (same hash / nnz / storage kind) and only builds the scatter maps
+    c.pattern_set = c.multi == nullptr;
     c.symmetric = symmetric ? 1 : 0;
     c.nnz = nnz;
+    c.pattern_hash = PatternHash(neq, &ia[0], nnz ? &ja[0] : nullptr);
     c.pattern_ms = ms_since(t0);
 }
 

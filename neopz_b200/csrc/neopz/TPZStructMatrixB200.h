@@ -16,16 +16,39 @@
  * The CSR pattern is the one the struct matrix's own Create() produced; values are written in place
  * into TPZSYsmpMatrix::A() / TPZFYsmpMatrix storage and the rhs into the TPZFMatrix.
  *
- * Supported: H1 TPZCompElH1 elements of uniform order p in {1,2} on hexahedra / tetrahedra with
- * TPZMatPoisson<STATE> or TPZElasticity3D, boundary faces with TPZBndCondT<STATE> (types 0,1; 2 for
- * elasticity), no hanging nodes, inactive equation filter, one load case.  Anything else is reported on
- * PZError followed by DebugStop(), the reference's error convention (pzstrmatrixor.cpp:107-114).
- * There is no CPU fallback.
+ * Supported (everything else is reported on PZError followed by DebugStop(), the reference's error convention,
+ * pzstrmatrixor.cpp:107-114; there is no CPU fallback):
+ *  - H1 TPZCompElH1 elements on hexahedra, tetrahedra, prisms, pyramids (volume) and quadrilaterals, triangles, lines (boundary
+ *    faces, or the domain and boundary of a plane problem), any order up to 9 and sides of different order (p-refined meshes);
+ *    specialised kernels for uniform p <= 4 on hexahedra / tetrahedra and p <= 2 on prisms / pyramids, the generic runtime-size
+ *    kernel for the rest; (multi)linear geometric maps, no hanging nodes / condensed connects;
+ *  - TPZMatPoisson<STATE> (dim 2, 3), TPZElasticity3D, TPZElasticity2D (plane strain / stress, prestress), with constant data or
+ *    std::function forcing (tabulated by the host at every integration point, re-evaluated at every Assemble unless
+ *    SetForcingIsStatic(true));
+ *  - TPZBndCondT<STATE>: TPZMatPoisson types 0, 1, 2; TPZElasticity3D types 0-8; TPZElasticity2D types 0, 1, 3; constant data or
+ *    TPZBndCondT::SetForcingFunctionBC;
+ *  - several load cases of TPZMatPoisson (TPZMatLoadCases: the rhs has NumLoadCases() columns);
+ *  - symmetric (TPZSYsmpMatrix) and full (TPZFYsmpMatrix) storage, material-id subsets (SetMaterialIds), an active
+ *    TPZEquationFilter;
+ *  - one GPU (SetDevice) or several (SetNumThreads(n >= 2) = the first n CUDA devices, or SetDevices): elements partitioned by
+ *    their smallest destination equation, every GPU owns a row block of the CSR, interface rows travel over NVLink.
+ *
+ * Semantics that differ from TPZStructMatrixOR on purpose:
+ *  - Assemble(stiffness, rhs) OVERWRITES the value array of `stiffness` with the assembled matrix (the reference's AddKel
+ *    accumulates into whatever the matrix holds; TPZLinearAnalysis::Assemble zeroes it first, so the two agree there).  A
+ *    caller that assembles several passes into one matrix turns SetAccumulate(true) on: the previous values are then added
+ *    on the host after the download.  The rhs is always ADDED to, like TPZFMatrix::AddFel does.
+ *  - TPZSYsmpMatrix::AddKel drops element entries with |value| < 1e-12 (Matrix/pzsysmp.cpp:381, IsZero); the GPU adds
+ *    them unless SetDropTinyEntries(true) asks for the reference's behaviour.
+ *  - the flattened mesh is cached between calls and revalidated with a signature of the mesh (element list, connect
+ *    sequence numbers / orders / block positions, materials, material-id filter, equation filter) at every Assemble;
+ *    SetCheckMesh(false) skips that walk (then call Invalidate() after changing the mesh).
  */
 #ifndef TPZSTRUCTMATRIXB200_H
 #define TPZSTRUCTMATRIXB200_H
 
 #include <memory>
+#include <vector>
 
 #include "TPZMatrixSolver.h"
 #include "TPZStrMatParInterface.h"
@@ -59,9 +82,26 @@ public:
     void SolveCG(const TPZFMatrix<TVar> &F, TPZFMatrix<TVar> &result, int64_t &numiterations, REAL &tol, bool jacobi = true,
                  int fromcurrent = 0);
 
-    //! CUDA device used by this strategy (default 0).
-    void SetDevice(int device) { fDevice = device; }
+    //! CUDA device used by this strategy (default 0) when it runs on one GPU.
+    void SetDevice(int device) { fDevice = device; fDevices.clear(); }
     int Device() const { return fDevice; }
+    //! Several GPUs of this process share the assembly (b200asm_multi_*): the GPU counterpart of SetNumThreads
+    //! (StrMatrix/TPZStrMatParInterface.h:62-69).  Without an explicit list, SetNumThreads(n >= 2) selects the first
+    //! min(n, devices present) CUDA devices; n = 0 / 1 (the default) keeps the single device of SetDevice.
+    void SetDevices(const std::vector<int> &devices) { fDevices = devices; }
+    const std::vector<int> &Devices() const { return fDevices; }
+    //! GPUs the last Assemble() ran on.
+    int NumDevicesUsed() const;
+    //! Add the assembled matrix to the values `stiffness` already holds (TPZSYsmpMatrix::AddKel semantics) instead of overwriting.
+    void SetAccumulate(bool accumulate) { fAccumulate = accumulate; }
+    //! Drop element entries with |value| < 1e-12 like TPZSYsmpMatrix::AddKel does (Matrix/pzsysmp.cpp:381).  Symmetric storage only.
+    void SetDropTinyEntries(bool drop) { fDropTiny = drop; }
+    //! Forcing functions / boundary functions do not change between assemblies: tabulate them once per flatten only.
+    void SetForcingIsStatic(bool is_static) { fStaticForcing = is_static; }
+    //! Revalidate the cached flattened mesh at every Assemble (default true).
+    void SetCheckMesh(bool check) { fCheckMesh = check; }
+    //! Forget the cached flattened mesh (the next Assemble flattens again).
+    void Invalidate();
     //! Page-lock the value array of the matrix handed to Assemble() (cudaHostRegister, once per array): the download then
     //! runs at PCIe speed and overlaps the kernels.  Off by default because the array belongs to the caller's matrix:
     //! call UnpinHostMatrix() (or destroy / reassign this object) BEFORE that matrix is destroyed.
@@ -84,7 +124,12 @@ protected:
     template <class T>
     friend class TPZSpStructMatrixB200;
     int fDevice{0};
+    std::vector<int> fDevices;
     bool fPinHost{false};
+    bool fAccumulate{false};
+    bool fDropTiny{false};
+    bool fStaticForcing{false};
+    bool fCheckMesh{true};
     std::shared_ptr<TPZB200AssemblyCache> fCache;
 };
 

@@ -479,7 +479,14 @@ static int cmd_dump(const std::string &dir, const Case &c, int with_elmats) {
     return 0;
 }
 
-static int cmd_time(const Case &c, int nthreads, int reps) {
+// raw binary dump (bench.py's parity leg reads it with numpy.fromfile)
+template <class T>
+static void save_raw(const std::string &path, const T *data, size_t n) {
+    std::ofstream f(path, std::ios::binary);
+    f.write((const char *)data, sizeof(T) * n);
+}
+
+static int cmd_time(const Case &c, int nthreads, int reps, const std::string &dumpdir = "") {
     auto t0 = clk::now();
     TPZCompMesh *cmesh = build_mesh(c);
     auto t1 = clk::now();
@@ -511,8 +518,18 @@ static int cmd_time(const Case &c, int nthreads, int reps) {
         TPZCompEl *cel = cmesh->Element(iel);
         if (cel && cel->Reference() && cel->Reference()->Dimension() == c.dim) nvol++;
     }
+    long double rn2 = 0;
+    TPZFMatrix<STATE> &rhs = an.Rhs();
+    for (int64_t k = 0; k < rhs.Rows(); k++) rn2 += (long double)rhs(k, 0) * rhs(k, 0);
+    if (!dumpdir.empty()) {  // the assembled system of the timed mesh, for the parity check of the GPU arm on the SAME mesh
+        save_raw(dumpdir + "/ia.bin", &sp->IA()[0], (size_t)sp->IA().size());
+        save_raw(dumpdir + "/ja.bin", &sp->JA()[0], (size_t)sp->JA().size());
+        save_raw(dumpdir + "/a.bin", &sp->A()[0], (size_t)sp->A().size());
+        save_raw(dumpdir + "/rhs.bin", &rhs(0, 0), (size_t)rhs.Rows());
+    }
     std::cout.precision(17);
     std::cout << "{\"n\": " << c.n << ", \"p\": " << c.p << ", \"phys\": " << c.phys << ", \"tet\": " << c.tet
+              << ", \"perturb\": " << c.perturb << ", \"rhs2\": " << (double)rn2
               << ", \"threads\": " << nthreads << ", \"reps\": " << reps << ", \"vol_elements\": " << nvol
               << ", \"neq\": " << cmesh->NEquations() << ", \"nnz\": " << sp->JA().size()
               << ", \"mesh_s\": " << std::chrono::duration<double>(t1 - t0).count()
@@ -524,7 +541,7 @@ static int cmd_time(const Case &c, int nthreads, int reps) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        std::cerr << "usage: refdriver dump <dir> n p phys tet perturb bctype with_elmats | time n p phys tet threads reps\n";
+        std::cerr << "usage: refdriver dump <dir> n p phys tet perturb bctype with_elmats | time n p phys tet threads reps [perturb [dumpdir]]\n";
         return 1;
     }
     std::string cmd = argv[1];
@@ -540,7 +557,8 @@ int main(int argc, char **argv) {
     }
     if (cmd == "time" && argc >= 8) {
         c.n = atoi(argv[2]); c.p = atoi(argv[3]); c.phys = atoi(argv[4]); c.tet = atoi(argv[5]);
-        return cmd_time(c, atoi(argv[6]), atoi(argv[7]));
+        if (argc >= 9) c.perturb = atof(argv[8]);
+        return cmd_time(c, atoi(argv[6]), atoi(argv[7]), argc >= 10 ? argv[9] : "");
     }
     std::cerr << "bad arguments\n";
     return 1;

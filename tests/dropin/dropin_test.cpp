@@ -33,6 +33,17 @@
 using clk = std::chrono::steady_clock;
 static double secs(clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); }
 
+// environment knobs (kept out of the positional arguments the existing tests use)
+static int EnvInt(const char *name, int def) { const char *v = getenv(name); return v ? atoi(v) : def; }
+static double EnvDouble(const char *name, double def) { const char *v = getenv(name); return v ? atof(v) : def; }
+static int g_gpus = 0;        // B200_GPUS: TPZStructMatrixB200::SetNumThreads(n) = GPUs that share the assembly
+static int g_bctype = 1;      // B200_BCTYPE: type of the boundary condition on matid -2 (default 1, Neumann)
+static int g_loadcases = 1;   // B200_LOADCASES: TPZMatPoisson with several load cases (rhs columns)
+static int g_droptiny = 0;    // B200_DROPTINY: SetDropTinyEntries(true) (AddKel's IsZero drop, Matrix/pzsysmp.cpp:381)
+static double g_scale = 1.0;  // B200_SCALE: node coordinates multiplied by this (micro-scale geometry makes the drop visible)
+static int g_skip_serial = 0; // B200_SKIP_SERIAL: the threaded OR run is the reference (large meshes: timing runs)
+static int g_accumulate = 0;  // B200_ACCUMULATE: a second Assemble() straight into the non-zero matrix, both strategies
+
 // dirichlet: value imposed on matid -1.  The CG comparison uses 0: with a non-zero value the right-hand side norm
 // is ~1e16 (penalty), and a relative residual tolerance of 1e-15 no longer constrains the interior equations.
 // phys 2 / 3: TPZElasticity2D (plane strain / plane stress) on a plane mesh of quadrilaterals (tet = 0) or triangles
@@ -59,6 +70,12 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
                 nd.SetCoord(d, nd.Coord(d) + perturb * h * std::sin(2.0 * M_PI * (double)i / 97.0 + (double)d));
             }
     }
+    if (g_scale != 1.0)
+        for (int64_t i = 0; i < gmesh->NNodes(); i++)
+            for (int d = 0; d < dim; d++) {
+                TPZGeoNode &nd = gmesh->NodeVec()[i];
+                nd.SetCoord(d, nd.Coord(d) * g_scale);
+            }
     TPZCompMesh *cmesh = new TPZCompMesh(gmesh);
     cmesh->SetDimModel(dim);
     cmesh->SetDefaultOrder(p);
@@ -85,18 +102,30 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
         cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
     } else if (phys == 0) {
         auto *m = new TPZMatPoisson<STATE>(1, 3);
-        // x-dependent source: exercises the host-evaluated forcing table
-        m->SetForcingFunction([](const TPZVec<REAL> &x, TPZVec<STATE> &f) { f[0] = 1.0 + x[0] * x[1] - 0.5 * x[2]; }, 2);
+        const int nlc = g_loadcases;
+        m->SetNumLoadCases(nlc);  // (before CreateBC: the boundary conditions copy the count, TPZMatLoadCases.cpp:49-60)
+        // x-dependent source: exercises the host-evaluated forcing table; one value per load case (TPZMatPoisson.cpp:23-27)
+        m->SetForcingFunction([nlc](const TPZVec<REAL> &x, TPZVec<STATE> &f) {
+            for (int l = 0; l < nlc; l++) f[l] = (1.0 + x[0] * x[1] - 0.5 * x[2]) * (1.0 + 0.5 * l) + 0.25 * l * x[2];
+        }, 2);
         cmesh->InsertMaterialObject(m);
         TPZFNMatrix<1, STATE> v1(1, 1, 0.);
         TPZManVector<STATE, 1> v2(1, dirichlet), v2n(1, 0.75);
         auto *bcd = m->CreateBC(m, -1, 0, v1, v2);
         if (bcfunc)
-            bcd->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) {
-                u[0] = 0.3 + x[0] * x[1] - 0.5 * x[2] * x[2];
+            bcd->SetForcingFunctionBC([nlc](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) {
+                for (int l = 0; l < nlc; l++) u[l] = (0.3 + x[0] * x[1] - 0.5 * x[2] * x[2]) * (1.0 - 0.25 * l);
             });
         cmesh->InsertMaterialObject(bcd);
-        cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+        TPZFNMatrix<1, STATE> v1n(1, 1, 0.);
+        v1n(0, 0) = 2.5e-15;  // type 2 multiplies it by BigNumber (TPZMatPoisson.cpp:112)
+        auto *bcn = m->CreateBC(m, -2, g_bctype, v1n, v2n);
+        if (nlc > 1) {  // TPZMatLoadCasesBC::SetBCRhsValVec: one value per load case
+            TPZVec<TPZVec<STATE>> vals(nlc);
+            for (int l = 0; l < nlc; l++) vals[l] = TPZManVector<STATE, 1>(1, 0.75 - 0.5 * l);
+            dynamic_cast<TPZMatLoadCasesBC<STATE> *>(bcn)->SetBCRhsValVec(vals);
+        }
+        cmesh->InsertMaterialObject(bcn);
     } else {
         TPZManVector<STATE, 3> force(3, 0.);
         force[2] = -1.;
@@ -114,7 +143,15 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
                 u[2] = 0.005 + 0.01 * x[2];
             });
         cmesh->InsertMaterialObject(bcd);
-        cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+        if (g_bctype == 1) {
+            cmesh->InsertMaterialObject(m->CreateBC(m, -2, 1, v1, v2n));
+        } else {  // the other types of TPZElasticity3D::ContributeBC (:616-773); 4 = stress field times the face normal
+            TPZFNMatrix<9, STATE> v1m(3, 3, 0.);
+            v1m(0, 0) = 4.0; v1m(0, 1) = 0.5; v1m(0, 2) = -0.3; v1m(1, 0) = 0.5; v1m(1, 1) = 3.0; v1m(1, 2) = 0.25; v1m(2, 0) = -0.3; v1m(2, 1) = 0.25; v1m(2, 2) = 5.0;
+            TPZManVector<STATE, 3> v2m(3, 0.);
+            v2m[0] = 0.3; v2m[1] = -0.2; v2m[2] = 0.7;
+            cmesh->InsertMaterialObject(m->CreateBC(m, -2, g_bctype, v1m, v2m));
+        }
     }
     cmesh->SetAllCreateFunctionsContinuous();
     cmesh->AutoBuild();
@@ -137,6 +174,8 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
 struct Csr {
     std::vector<int64_t> ia, ja;
     std::vector<double> a, rhs, sol;
+    std::vector<double> a_twice;       // B200_ACCUMULATE: values after a second Assemble() into the NON-zeroed matrix
+    int devices = 1;
     std::vector<double> residual_rhs;  // TPZLinearAnalysis::AssembleResidual() -> Assemble(rhs)
     std::vector<double> sol_device;    // B200 only: CG on the device-resident matrix (TPZB200CGSolver through an.Solve())
     int64_t device_cg_iters = 0;
@@ -150,6 +189,10 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
     TPZLinearAnalysis an(cmesh, false);
     TStrMat strmat(cmesh);
     strmat.SetNumThreads(nthreads);
+    if (auto *b = dynamic_cast<TPZStructMatrixB200<STATE> *>(&strmat)) {
+        if (g_gpus) b->SetNumThreads(g_gpus);
+        if (g_droptiny) b->SetDropTinyEntries(true);
+    }
     if (g_filter) strmat.EquationFilter().SetMinMaxEq(cmesh->NEquations() / 4, cmesh->NEquations());
     if (g_pin)
         if (auto *b = dynamic_cast<TPZStructMatrixB200<STATE> *>(&strmat)) b->SetPinHostMatrix(true);
@@ -180,9 +223,23 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
         out.ja.assign(ja.begin(), ja.end());
         out.a.assign(a.begin(), a.end());
     }
-    out.rhs.resize(neq);
     TPZFMatrix<STATE> &rhsm = an.Rhs();
-    for (int64_t i = 0; i < neq; i++) out.rhs[i] = rhsm(i, 0);
+    const int ncols = (int)rhsm.Cols();  // one column per load case (Analysis/TPZLinearAnalysis.cpp:70-72)
+    out.rhs.resize(neq * ncols);
+    for (int l = 0; l < ncols; l++)
+        for (int64_t i = 0; i < neq; i++) out.rhs[l * neq + i] = rhsm(i, l);
+    auto *b200 = dynamic_cast<TPZStructMatrixB200<STATE> *>(an.StructMatrix().operator->());
+    if (b200) out.devices = b200->NumDevicesUsed();
+    if (g_accumulate && symmetric) {
+        // TPZStrMatParInterface::Assemble straight into the matrix that already holds one assembly: AddKel accumulates
+        if (b200) b200->SetAccumulate(true);
+        TPZFMatrix<STATE> rhs2(neq, ncols, 0.);
+        an.StructMatrix()->Assemble(*mtx.operator->(), rhs2, nullptr);
+        auto *sp = dynamic_cast<TPZSYsmpMatrix<STATE> *>(mtx.operator->());
+        out.a_twice.assign(sp->A().begin(), sp->A().end());
+        if (b200) b200->SetAccumulate(false);
+        an.Assemble();  // back to one assembly for the checks below
+    }
     if (solve) {
         // the reference's own CG (Solvers/LinearSolvers/cg.h:44-120 through TPZMatrix::SolveCG) with its Jacobi
         // preconditioner, on the assembled system
@@ -196,8 +253,7 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
         for (int64_t i = 0; i < neq; i++) out.sol[i] = sol(i, 0);
         // the same solve on the GPU, through the unmodified TPZLinearAnalysis::Solve(): the matrix the strategy left on
         // the device, the reference's CG algorithm with its Jacobi(1) preconditioner
-        auto *b200 = dynamic_cast<TPZStructMatrixB200<STATE> *>(an.StructMatrix().operator->());
-        if (b200) {
+        if (b200 && b200->NumDevicesUsed() == 1) {
             TPZB200CGSolver<STATE> dev(b200, 50000, 1.e-15, true, 0);
             dev.SetMatrix(mtx);
             an.SetSolver(dev);
@@ -211,10 +267,12 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
     }
     // right-hand side only: TPZLinearAnalysis::AssembleResidual() -> TPZStrMatParInterface::Assemble(rhs)
     an.AssembleResidual();
-    out.residual_rhs.resize(neq);
     {
         TPZFMatrix<STATE> &res = an.Rhs();
-        for (int64_t i = 0; i < neq; i++) out.residual_rhs[i] = res(i, 0);
+        const int rc = (int)res.Cols();
+        out.residual_rhs.resize(neq * rc);
+        for (int l = 0; l < rc; l++)
+            for (int64_t i = 0; i < neq; i++) out.residual_rhs[l * neq + i] = res(i, l);
     }
     // the value array belongs to the analysis' matrix: release the page lock before the analysis goes away
     if (auto *b = dynamic_cast<TPZStructMatrixB200<STATE> *>(an.StructMatrix().operator->())) b->UnpinHostMatrix();
@@ -243,10 +301,28 @@ int main(int argc, char **argv) {
     g_pin = argc > 10 ? atoi(argv[10]) : 0;
     const int prefine = argc > 11 ? atoi(argv[11]) : 0;
     const int bcfunc = argc > 12 ? atoi(argv[12]) : 0;
+    g_gpus = EnvInt("B200_GPUS", 0);
+    g_bctype = EnvInt("B200_BCTYPE", 1);
+    g_loadcases = EnvInt("B200_LOADCASES", 1);
+    g_droptiny = EnvInt("B200_DROPTINY", 0);
+    g_scale = EnvDouble("B200_SCALE", 1.0);
+    g_skip_serial = EnvInt("B200_SKIP_SERIAL", 0);
+    g_accumulate = EnvInt("B200_ACCUMULATE", 0);
     TPZCompMesh *cmesh = BuildMesh(n, p, phys, tet, 0.12, solve ? 0.0 : 0.3, prefine, bcfunc);
     Csr ref, refmt, gpu;
-    double t1, t2, tm1, tm2, g1, g2;
-    if (symmetric) {
+    double t1 = 0, t2 = 0, tm1, tm2, g1, g2;
+    if (g_skip_serial) {  // timing runs on large meshes: the threaded OR assembly (bit-identical to the serial one) is the reference
+        if (symmetric) {
+            Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, true, solve, ref, tm1, tm2);
+            if (device_create) Run<TPZSSpStructMatrixB200<STATE>>(cmesh, 0, true, solve, gpu, g1, g2);
+            else Run<TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, true, solve, gpu, g1, g2);
+        } else {
+            Run<TPZSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, false, false, ref, tm1, tm2);
+            if (device_create) Run<TPZSpStructMatrixB200<STATE>>(cmesh, 0, false, false, gpu, g1, g2);
+            else Run<TPZSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>>(cmesh, 0, false, false, gpu, g1, g2);
+        }
+        refmt.a = ref.a;
+    } else if (symmetric) {
         Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, 0, true, solve, ref, t1, t2);
         Run<TPZSSpStructMatrix<STATE, TPZStructMatrixOR<STATE>>>(cmesh, threads, true, false, refmt, tm1, tm2);
         if (device_create) Run<TPZSSpStructMatrixB200<STATE>>(cmesh, 0, true, solve, gpu, g1, g2);
@@ -284,16 +360,20 @@ int main(int argc, char **argv) {
     double errSol = 0;
     if (solve && symmetric) errSol = RelF(gpu.sol, ref.sol);
     double errSolDev = 0;
-    if (solve && symmetric) errSolDev = RelF(gpu.sol_device, ref.sol);
+    if (solve && symmetric && !gpu.sol_device.empty()) errSolDev = RelF(gpu.sol_device, ref.sol);
+    const double errTwice = (g_accumulate && symmetric) ? RelF(gpu.a_twice, ref.a_twice) : 0.0;
     const double errRes = RelF(gpu.residual_rhs, ref.residual_rhs), errResVsRhs = RelF(ref.residual_rhs, ref.rhs);
     int64_t nvol = 0;  // elements of the mesh dimension
     for (int64_t iel = 0; iel < cmesh->NElements(); iel++) {
         TPZCompEl *cel = cmesh->Element(iel);
         if (cel && cel->Reference() && cel->Reference()->Dimension() == cmesh->Dimension()) nvol++;
     }
-    const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12;
+    const bool ok = same_ia && same_ja && errA <= 1e-12 && errR <= 1e-12 && errInt <= 1e-12 && errSol <= 1e-10 && errSolDev <= 1e-10 && errRes <= 1e-12 && errTwice <= 1e-12 &&
+                    (g_gpus < 2 || gpu.devices >= 2);
     std::cout.precision(6);
-    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"prefine\": " << prefine << ", \"bcfunc\": " << bcfunc << ", \"cpu_first_assemble_s\": " << t1
+    std::cout << "{\"n\": " << n << ", \"p\": " << p << ", \"phys\": " << phys << ", \"tet\": " << tet << ", \"symmetric\": " << symmetric << ", \"device_create\": " << device_create << ", \"equation_filter\": " << g_filter << ", \"pin_host\": " << g_pin << ", \"prefine\": " << prefine << ", \"bcfunc\": " << bcfunc
+              << ", \"gpus\": " << gpu.devices << ", \"bctype\": " << g_bctype << ", \"loadcases\": " << g_loadcases << ", \"droptiny\": " << g_droptiny
+              << ", \"scale\": " << g_scale << ", \"relF_A_accumulated_twice\": " << errTwice << ", \"cpu_first_assemble_s\": " << t1
               << ", \"neq\": " << neq << ", \"nnz\": " << ref.ja.size() << ", \"vol_elements\": " << nvol
               << ", \"ia_identical\": " << same_ia << ", \"ja_identical\": " << same_ja << ", \"relF_A\": " << errA
               << ", \"relF_A_nonpenalty_rows\": " << errInt << ", \"max_entry_err_over_rowmax\": " << maxrel
