@@ -1435,6 +1435,9 @@ int choose_kernels(b200asm_ctx *ctx) {
 }
 
 int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
+    for (const Group &g : ctx->groups)
+        if (g.max_dest >= ctx->neq)
+            return fail(ctx, B200ASM_EINVAL, "a group's destination indices exceed the equations of the pattern (pattern and groups of different meshes?)");
     if (ctx->d_xyz) {  // the layout of a group's map follows the kernel that will run it
         const int rc = choose_kernels(ctx);
         if (rc) return rc;
@@ -1657,6 +1660,12 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
     if (!ctx || !gi) return B200ASM_EINVAL;
     CK(cudaSetDevice(ctx->device));
     Group g;
+    // every early return below releases what has been uploaded so far
+    struct Guard {
+        Group &g;
+        bool armed = true;
+        ~Guard() { if (armed) free_group(g); }
+    } guard{g};
     g.topology = gi->topology; g.porder = gi->porder; g.kind = gi->kind; g.ns = gi->nstate; g.nel = gi->nel;
     g.nn = ncorner_of(gi->topology);
     g.n = nshape_of(gi->topology, gi->porder);
@@ -1825,7 +1834,11 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
             dest32[(size_t)e * g.m + k] = (int32_t)d;
             g.max_dest = std::max(g.max_dest, d);
         }
-        for (int k = 0; k < g.nn; k++) elnodes[(size_t)e * g.nn + k] = gi->elnodes[src * g.nn + k];
+        for (int k = 0; k < g.nn; k++) {
+            const int32_t node = gi->elnodes[src * g.nn + k];
+            if (node < 0 || (ctx->nnodes > 0 && node >= ctx->nnodes)) return fail(ctx, B200ASM_EINVAL, "add_group: corner node index outside the node table");
+            elnodes[(size_t)e * g.nn + k] = node;
+        }
     }
     // smallest destination equation of every chunk (chunks are sets of elements: the order inside does not matter)
     g.chunk_min.assign(g.chunk.size() - 1, INT64_MAX);
@@ -1908,6 +1921,7 @@ extern "C" int b200asm_add_group(b200asm_ctx *ctx, const b200asm_group *gi) {
         g.stored_order = order;
     }
     CK(cudaStreamSynchronize(ctx->stream));  // dest32 / dng are stack-owned
+    guard.armed = false;
     ctx->groups.push_back(g);
     ctx->maps_valid = false;  // scatter maps are rebuilt (on the resident pattern) by the next assembly
     return (int)ctx->groups.size() - 1;
@@ -2205,6 +2219,8 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
 int begin_assembly(b200asm_ctx *ctx) {
     if (!ctx->have_pattern && !ctx->rhs_only) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_pattern after the last add_group");
     if (!ctx->d_xyz) return fail(ctx, B200ASM_ESTATE, "assemble: call b200asm_set_nodes first");
+    for (const Group &g : ctx->groups)
+        if (g.max_dest >= ctx->neq) return fail(ctx, B200ASM_EINVAL, "assemble: a group's destination indices exceed the equations of the system");
     CK(cudaSetDevice(ctx->device));
     {
         const int rc = choose_kernels(ctx);

@@ -119,6 +119,38 @@ class FlatMesh:
         return index, graph
 
 
+def face_outward(mesh, block):
+    """For every boundary face of `block`: centre of the face minus centre of the volume element it bounds - the vector
+    TPZInterpolationSpace::ComputeNormal (Mesh/pzinterpolationspace.cpp:338-381) turns data.normal towards.  The centres are
+    the images of the master-element centres (TPZGeoEl::CenterPoint + X), i.e. the corner averages of (multi)linear maps.
+    Only its direction relative to the face matters.  [nel][3]; zero where no volume element owns the face."""
+    fn = np.sort(np.asarray(block.elnodes, dtype=np.int64), axis=1)[:, :3]   # the three smallest nodes identify a face
+    nn = np.int64(len(mesh.nodes) + 1)
+    if float(nn) ** 3 >= 9.2e18:
+        raise ValueError("face_outward: too many nodes for the packed face key")
+    key = (fn[:, 0] * nn + fn[:, 1]) * nn + fn[:, 2]
+    out = np.zeros((len(fn), 3))
+    found = np.zeros(len(fn), dtype=bool)
+    fc = mesh.nodes[block.elnodes].mean(axis=1)
+    for vb in mesh.blocks:
+        if DIM[vb.topology] != 3:
+            continue
+        en = np.asarray(vb.elnodes, dtype=np.int64)
+        vc = mesh.nodes[vb.elnodes].mean(axis=1)
+        for loc in SIDES[vb.topology]:
+            if len(loc) not in (3, 4) or len(loc) == NCORNER[vb.topology]:
+                continue
+            sn = np.sort(en[:, loc], axis=1)[:, :3]
+            vkey = (sn[:, 0] * nn + sn[:, 1]) * nn + sn[:, 2]
+            order = np.argsort(vkey, kind="stable")
+            pos = np.searchsorted(vkey[order], key)
+            pos = np.minimum(pos, len(vkey) - 1)
+            hit = (vkey[order][pos] == key) & ~found
+            out[hit] = fc[hit] - vc[order[pos[hit]]]
+            found |= hit
+    return out
+
+
 def _first_touch_ids(keys):
     """Rank of first occurrence: keys[k] -> index in order of first appearance (greedy connect creation)."""
     uniq, first, inv = np.unique(keys, return_index=True, return_inverse=True)

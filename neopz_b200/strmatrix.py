@@ -12,6 +12,7 @@ import os
 import numpy as np
 
 from . import capi
+from .gridmesh import face_outward as gridmesh_face_outward
 from .gridmesh import DIM, FlatMesh
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
@@ -123,8 +124,10 @@ class TPZElasticity2D:
 
 
 class TPZBndCond:
-    """TPZBndCondT: type 0 Dirichlet (penalty), 1 Neumann; Elasticity3D also 2 mixed, 3 directional null Dirichlet,
-    5-8 directional Dirichlet (x, y, z, x and z)."""
+    """TPZBndCondT: type 0 Dirichlet (penalty), 1 Neumann; TPZMatPoisson also 2 (the Robin branch as the reference computes it:
+    penalty load vector + BigNumber * Val1(0,0) * dphix(0,i) dphix(0,j), TPZMatPoisson.cpp:104-118); Elasticity3D also 2 mixed,
+    3 directional null Dirichlet, 4 stress field times the face normal (TPZElasticity3D.cpp:724-737), 5-8 directional
+    Dirichlet (x, y, z, x and z)."""
     kind = capi.BC
 
     def __init__(self, material, matid, bctype, val1, val2):
@@ -158,6 +161,8 @@ class TPZBndCond:
                 return self.material.fBigNumber * v2
             if self.type == 1:
                 return v2 * self.material.fScale
+            if self.type == 2:
+                return self.material.fBigNumber * v2
         elif isinstance(self.material, TPZElasticity2D):
             if self.type == 0:
                 return self.material.fBigNumber * v2
@@ -201,6 +206,9 @@ class TPZBndCond:
                 v[0] = big * self.val2[0]
             elif self.type == 1:    # :93-100
                 v[0] = self.val2[0] * self.material.fScale
+            elif self.type == 2:    # :104-118: coef[12] = coefficient of dphix(0,i) dphix(0,j) w
+                v[0] = big * self.val2[0]
+                return M.reshape(-1).tolist() + v.tolist() + [big * self.val1[0, 0]]
             else:
                 raise ValueError("TPZMatPoisson: boundary condition type %d not supported" % self.type)
         else:
@@ -215,6 +223,8 @@ class TPZBndCond:
                 v[:ns] = self.val2[:ns]
             elif self.type == 3:    # :715-723 directional null Dirichlet: penalty scaled by val2 per direction
                 M[:ns, :ns] = np.diag(big * self.val2[:ns])
+            elif self.type == 4:    # :724-737: load vector only, -(val1 . normal) per integration point (table, see face_normals)
+                pass
             elif self.type in (5, 6, 7, 8):   # :739-772 directional Dirichlet on x / y / z / x and z
                 for k in {5: (0,), 6: (1,), 7: (2,), 8: (0, 2)}[self.type]:
                     M[k, k] = big
@@ -253,6 +263,20 @@ def points_x(topology, qpts, coords):
     for a in range(geo.shape[1]):
         x += geo[None, :, a, None] * coords[:, None, a, :]
     return x
+
+
+def face_normals(topology, qpts, coords, outward):
+    """data.normal of boundary faces at the integration points (TPZInterpolationSpace::ComputeNormal,
+    Mesh/pzinterpolationspace.cpp:300-383): the unit vector axes(0) x axes(1) of the Gram-Schmidt Jacobian, i.e. the
+    normalised dx/dxi x dx/deta, turned towards `outward` (gridmesh.face_outward).  coords [nel][ncorner][3] -> [nel][nq][3]."""
+    _, dgeo = capi.shape_tables(topology, 1, qpts)          # [nq][2][ncorner]
+    v1 = np.einsum("qa,eak->eqk", dgeo[:, 0, :], coords)
+    v2 = np.einsum("qa,eak->eqk", dgeo[:, 1, :], coords)
+    n = np.cross(v1, v2)
+    n /= np.linalg.norm(n, axis=2, keepdims=True)
+    flip = np.einsum("eqk,ek->eq", n, outward) < 0.0
+    n[flip] *= -1.0
+    return n
 
 
 # ---------------------------------------------------------------------------------------------
@@ -310,7 +334,12 @@ class TPZStructMatrixB200:
                 sel = slice(None) if mesh.porder < 3 else np.nonzero(keys == key)[0]
                 qpts, qw, phi, dphi = element_tables(b.topology, mesh.porder, key)
                 force = None
-                if mat.kind == capi.BC and mat.HasForcingFunctionBC():
+                if mat.kind == capi.BC and mat.type == 4 and isinstance(mat.material, TPZElasticity3D):
+                    # stress-field Neumann: ef += -(val1 . normal) phi w, the normal of every integration point tabulated here
+                    coords = mesh.nodes[b.elnodes[sel]]
+                    nrm = face_normals(b.topology, qpts, coords, gridmesh_face_outward(mesh, b)[sel])
+                    force = -np.einsum("ab,eqb->eqa", mat.val1, nrm)
+                elif mat.kind == capi.BC and mat.HasForcingFunctionBC():
                     force = mat.rhs_coefficient(mat.forcing(points_x(b.topology, qpts, mesh.nodes[b.elnodes[sel]]).reshape(-1, 3)))
                     force = force.reshape(len(b.elnodes[sel]), len(qw), mat.nstate)
                 elif mat.kind != capi.BC and getattr(mat, "forcing", None) is not None:

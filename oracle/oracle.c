@@ -985,6 +985,9 @@ typedef struct {
                              mat[10..12].  Domain kinds: the forcing function of the material - the source of TPZMatPoisson
                              (TPZMatPoisson.cpp:24-27, replaces mat[1]), the body force of TPZElasticity3D (:271-274, mat[3..5]) and of
                              TPZElasticity2D (:120-127, mat[3..4]).  NULL: the constants */
+    double outward[3];    /* boundary faces: centre of the face minus centre of the neighbouring volume element, the vector
+                             TPZInterpolationSpace::ComputeNormal orients data.normal with (Mesh/pzinterpolationspace.cpp:338-381);
+                             used by TPZElasticity3D boundary type 4 only */
 } orc_elem_t;
 
 static int topo_dim(int topo) {
@@ -1034,9 +1037,18 @@ static void contribute_elast(int n, const double *phi, const double *dphi, doubl
 #undef EK
 }
 
-/* Material/Poisson/TPZMatPoisson.cpp:45-121 (types 0,1) */
-static int contribute_poisson_bc(int n, const double *phi, double weight, int type, const double *mat, double *ek, double *ef) {
+/* Material/Poisson/TPZMatPoisson.cpp:45-121 (types 0, 1 and 2 as computed there: the Robin branch adds the penalty load vector
+ * and BigNumber * Val1(0,0) * dphix(0,in) * dphix(0,jn), then falls through to the "not implemented" message) */
+static int contribute_poisson_bc(int n, const double *phi, const double *dphix, double weight, int type, const double *mat, double *ek, double *ef) {
     const double big = mat[0], v2 = mat[10], fScale = mat[13];
+    if (type == 2) {
+        const double v1 = mat[1];
+        for (int in = 0; in < n; in++) {
+            ef[in] += big * v2 * phi[in] * weight;
+            for (int jn = 0; jn < n; jn++) ek[jn * n + in] += big * v1 * dphix[in] * dphix[jn] * weight;
+        }
+        return 0;
+    }
     if (type == 0) {
         for (int in = 0; in < n; in++) {
             ef[in] += big * v2 * phi[in] * weight;
@@ -1052,7 +1064,8 @@ static int contribute_poisson_bc(int n, const double *phi, double weight, int ty
 }
 
 /* Material/Elasticity/TPZElasticity3D.cpp:616-773 (types 0,1,2), BIGNUMBER=1e12 (:630) */
-static int contribute_elast_bc(int n, const double *phi, double weight, int type, const double *mat, double *ek, double *ef) {
+static int contribute_elast_bc(int n, const double *phi, double weight, int type, const double *mat, const double axes[3][3],
+                               const double *outward, double *ek, double *ef) {
     const double BIG = 1.e12;
     const double *val1 = mat + 1, *val2 = mat + 10;
     const int nd = 3 * n;
@@ -1083,6 +1096,26 @@ static int contribute_elast_bc(int n, const double *phi, double weight, int type
                 for (int jn = 0; jn < n; jn++)
                     for (int k = 0; k < 3; k++) EK(3 * in + k, 3 * jn + k) += BIG * phi[in] * phi[jn] * weight * val2[k];
             return 0;
+        case 4: { /* stress-field Neumann, :724-737, with data.normal of Mesh/pzinterpolationspace.cpp:300-383:
+                     VectorialProd(axes(0), axes(1), normal, unitary) turned towards `vec` */
+            double nrm[3];
+            nrm[0] = axes[0][1] * axes[1][2] - axes[0][2] * axes[1][1];
+            nrm[1] = -axes[0][0] * axes[1][2] + axes[0][2] * axes[1][0];
+            nrm[2] = axes[0][0] * axes[1][1] - axes[0][1] * axes[1][0];
+            double size = 0.;
+            for (int i = 0; i < 3; i++) size += nrm[i] * nrm[i];
+            size = sqrt(size);
+            for (int i = 0; i < 3; i++) nrm[i] /= size;
+            double dot = 0.;
+            for (int i = 0; i < 3; i++) dot += nrm[i] * outward[i];
+            if (dot < 0.)
+                for (int i = 0; i < 3; i++) nrm[i] *= -1.;
+            double v2l[3];
+            for (int i = 0; i < 3; i++) v2l[i] = -(val1[3 * i + 0] * nrm[0] + val1[3 * i + 1] * nrm[1] + val1[3 * i + 2] * nrm[2]);
+            for (int in = 0; in < n; in++)
+                for (int k = 0; k < 3; k++) ef[3 * in + k] += v2l[k] * phi[in] * weight;
+            return 0;
+        }
         case 5: case 6: case 7: case 8: { /* directional Dirichlet on x / y / z / x and z, :739-772 */
             const int on[3] = {type == 5 || type == 8, type == 6, type == 7 || type == 8};
             for (int in = 0; in < n; in++) {
@@ -1096,7 +1129,7 @@ static int contribute_elast_bc(int n, const double *phi, double weight, int type
         }
     }
 #undef EK
-    return -1; /* type 4 (stress field times the face normal) is not restated */
+    return -1;
 }
 
 /* Material/Elasticity/TPZElasticity2D.cpp:86-203.  mat[0]=E, mat[1]=nu, mat[2]=fPlaneStress, mat[3..4]=ff,
@@ -1231,8 +1264,8 @@ int orc_calcstiff(const orc_elem_t *e, double *ek, double *ef) {
             case ORC_ELAST2D: contribute_elast2d(n, phi, dphix, axes, weight, bm, ek, ef); break;
             case ORC_ELAST2D_BC: rc = contribute_elast2d_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
             case ORC_ELAST3D: contribute_elast(n, phi, dphix, weight, bm, ek, ef); break;
-            case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
-            case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, bm, ek, ef); break;
+            case ORC_POISSON_BC: rc = contribute_poisson_bc(n, phi, dphix, weight, e->bctype, bm, ek, ef); break;
+            case ORC_ELAST3D_BC: rc = contribute_elast_bc(n, phi, weight, e->bctype, bm, axes, e->outward, ek, ef); break;
             default: rc = -1;
         }
         if (rc) return -2;

@@ -33,7 +33,7 @@ class Elem(C.Structure):
                 ("nq", C.c_int32), ("pad", C.c_int32),
                 ("qpts", C.POINTER(C.c_double)), ("qw", C.POINTER(C.c_double)),
                 ("ids", C.c_int64 * 8),
-                ("bcval2", C.POINTER(C.c_double))]
+                ("bcval2", C.POINTER(C.c_double)), ("outward", C.c_double * 3)]
 
 
 _lib = None
@@ -113,7 +113,7 @@ def elast_constants(E, nu):
     return c
 
 
-def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None, bcval2=None):
+def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None, bcval2=None, outward=None):
     """coords: (nel, nnode, 3); ids: (nel, nnode) global corner-node indices (orientation, p >= 3); bcval2: (nel, nq, 3) val2 of
     a boundary condition with a forcing function at every integration point.  Returns (ctypes array of Elem, keepalive)."""
     nel = coords.shape[0]
@@ -129,6 +129,8 @@ def make_elems(topo, p, kind, bctype, coords, mat, qpts, qw, ids=None, bcval2=No
         el.topo, el.p, el.kind, el.bctype = topo, p, kind, bctype
         if bcval2 is not None:
             el.bcval2 = _dp(bcval2[e])
+        if outward is not None:  # (nel, 3): face centre minus centre of the neighbouring volume element (boundary type 4)
+            el.outward[:] = [float(v) for v in outward[e]]
         flat = np.zeros(24)
         flat[: nn * 3] = coords[e].reshape(-1)
         el.coords[:] = flat.tolist()

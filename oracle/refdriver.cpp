@@ -184,7 +184,10 @@ static TPZCompMesh *build_mesh(const Case &c) {
         cmesh->InsertMaterialObject(bcd);
         if (c.bctype >= 1) {
             TPZManVector<STATE, 1> v2n(1, 0.75);
-            auto *bcn = m->CreateBC(m, -2, 1, v1, v2n);
+            // type 2: the Robin branch of TPZMatPoisson::ContributeBC (penalty load vector + BigNumber * Val1(0,0) * dphix0 dphix0)
+            TPZFNMatrix<1, STATE> v1n(1, 1, 0.);
+            if (c.bctype == 2) v1n(0, 0) = 2.5e-15;
+            auto *bcn = m->CreateBC(m, -2, c.bctype == 2 ? 2 : 1, c.bctype == 2 ? v1n : v1, v2n);
             if (c.bcfunc)
                 bcn->SetForcingFunctionBC([](const TPZVec<REAL> &x, TPZVec<STATE> &u, TPZFMatrix<STATE> &du) { u[0] = 0.75 + 2.0 * x[0] - x[1] * x[1]; });
             cmesh->InsertMaterialObject(bcn);

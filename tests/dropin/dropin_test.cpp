@@ -40,7 +40,7 @@ static int g_gpus = 0;        // B200_GPUS: TPZStructMatrixB200::SetNumThreads(n
 static int g_bctype = 1;      // B200_BCTYPE: type of the boundary condition on matid -2 (default 1, Neumann)
 static int g_loadcases = 1;   // B200_LOADCASES: TPZMatPoisson with several load cases (rhs columns)
 static int g_droptiny = 0;    // B200_DROPTINY: SetDropTinyEntries(true) (AddKel's IsZero drop, Matrix/pzsysmp.cpp:381)
-static double g_scale = 1.0;  // B200_SCALE: node coordinates multiplied by this (micro-scale geometry makes the drop visible)
+static double g_scale = 1.0;  // B200_SCALE: TPZMatPoisson::SetScaleFactor (a tiny factor puts element entries below AddKel's 1e-12 drop)
 static int g_skip_serial = 0; // B200_SKIP_SERIAL: the threaded OR run is the reference (large meshes: timing runs)
 static int g_accumulate = 0;  // B200_ACCUMULATE: a second Assemble() straight into the non-zero matrix, both strategies
 
@@ -70,12 +70,6 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
                 nd.SetCoord(d, nd.Coord(d) + perturb * h * std::sin(2.0 * M_PI * (double)i / 97.0 + (double)d));
             }
     }
-    if (g_scale != 1.0)
-        for (int64_t i = 0; i < gmesh->NNodes(); i++)
-            for (int d = 0; d < dim; d++) {
-                TPZGeoNode &nd = gmesh->NodeVec()[i];
-                nd.SetCoord(d, nd.Coord(d) * g_scale);
-            }
     TPZCompMesh *cmesh = new TPZCompMesh(gmesh);
     cmesh->SetDimModel(dim);
     cmesh->SetDefaultOrder(p);
@@ -103,6 +97,7 @@ static TPZCompMesh *BuildMesh(int n, int p, int phys, int tet, double perturb, d
     } else if (phys == 0) {
         auto *m = new TPZMatPoisson<STATE>(1, 3);
         const int nlc = g_loadcases;
+        if (g_scale != 1.0) m->SetScaleFactor(g_scale);
         m->SetNumLoadCases(nlc);  // (before CreateBC: the boundary conditions copy the count, TPZMatLoadCases.cpp:49-60)
         // x-dependent source: exercises the host-evaluated forcing table; one value per load case (TPZMatPoisson.cpp:23-27)
         m->SetForcingFunction([nlc](const TPZVec<REAL> &x, TPZVec<STATE> &f) {

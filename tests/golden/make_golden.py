@@ -74,6 +74,13 @@ CASES = {
     "hex_p2_poisson_n2_bcfunc": (2, 2, 0, 0, 0.15, 1, 1, 0, 3, 1),
     "tet_p2_elast_n2_bcfunc": (2, 2, 1, 1, 0.15, 2, 1, 0, 3, 1),
     "prism_p2_poisson_n2_bcfunc": (2, 2, 0, 2, 0.15, 1, 1, 0, 3, 1),
+    # TPZMatPoisson::ContributeBC type 2 as the reference computes it (gradient penalty on the zmax face, TPZMatPoisson.cpp:104-118);
+    # TPZElasticity3D::ContributeBC type 4 (stress field times the face normal, TPZElasticity3D.cpp:724-737)
+    "hex_p2_poisson_n2_bc2": (2, 2, 0, 0, 0.15, 2, 1),
+    "tet_p2_poisson_n2_bc2": (2, 2, 0, 1, 0.15, 2, 1),
+    "hex_p2_elast_n2_bc4": (2, 2, 1, 0, 0.15, 4, 1),
+    "tet_p2_elast_n2_bc4": (2, 2, 1, 1, 0.15, 4, 1),
+    "hex_p3_poisson_n2_bc2_scr": (2, 3, 0, 0, 0.15, 2, 0, 7),
 }
 
 

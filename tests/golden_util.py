@@ -22,6 +22,7 @@ CORE_CASES = [c for c in ALL_CASES if c not in WEDGE_CASES and c not in SIMPLEX3
 E_MOD, NU = 1000.0, 0.3
 ELAST_FORCE = (0.0, 0.0, -1.0)
 NEUMANN_POISSON = 0.75
+POISSON_BC2_VAL1 = 2.5e-15   # Val1(0,0) of the type-2 condition of oracle/refdriver.cpp
 NEUMANN_ELAST = (0.25, -0.5, 2.0)
 BC_VAL1 = np.array([[4.0, 0.5, 0.0], [0.5, 3.0, 0.25], [0.0, 0.25, 5.0]])
 BC_VAL2 = (0.3, -0.2, 0.7)
@@ -71,8 +72,10 @@ def material_vector(g, topo, matid):
     mat[0] = big
     mat[13] = 1.0
     if phys == 0:
-        bctype = min(bctype, 1)
+        bctype = min(bctype, 2)
         mat[10] = 0.0 if bctype == 0 else NEUMANN_POISSON
+        if bctype == 2:
+            mat[1] = POISSON_BC2_VAL1
         return orc.POISSON_BC, bctype, mat
     if bctype == 1:
         mat[10:13] = NEUMANN_ELAST
@@ -120,6 +123,21 @@ def bc_point_values(g, topo, matid, bctype, coords, qpts):
     return out
 
 
+def fixture_outward(g, e):
+    """Centre of boundary face e minus centre of the volume element that owns it (the vector ComputeNormal orients with)."""
+    topo = int(g["el_type"][e])
+    fn = set(int(v) for v in g["el_nodes"][e, : orc.TOPO_NNODE[topo]])
+    fc = g["nodes"][sorted(fn)].mean(axis=0)
+    for v in range(len(g["el_type"])):
+        vt = int(g["el_type"][v])
+        if orc.TOPO_DIM[vt] != 3:
+            continue
+        vn = [int(x) for x in g["el_nodes"][v, : orc.TOPO_NNODE[vt]]]
+        if fn.issubset(vn):
+            return fc - g["nodes"][vn].mean(axis=0)
+    return np.zeros(3)
+
+
 def oracle_elements(g):
     """One ctypes Elem per computational element, in element order; returns (list_of_arrays, keepalive)."""
     p = g["meta"]["p"]
@@ -133,8 +151,9 @@ def oracle_elements(g):
         kind, bctype, mat = material_vector(g, topo, int(g["el_matid"][e]))
         tag = TAGS[topo]
         bcv = bc_point_values(g, topo, int(g["el_matid"][e]), bctype, coords[0], g[f"rule_{tag}_pts"])
+        outward = fixture_outward(g, e)[None, :] if (kind == orc.ELAST3D_BC and bctype == 4) else None
         arr, k = orc.make_elems(topo, p, kind, bctype, coords, mat, g[f"rule_{tag}_pts"], g[f"rule_{tag}_w"],
-                                ids=nodes[None, :], bcval2=bcv)
+                                ids=nodes[None, :], bcval2=bcv, outward=outward)
         arrays.append(arr)
         keep.append(k)
     return arrays, keep

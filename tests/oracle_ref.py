@@ -79,7 +79,12 @@ def oracle_assemble(mesh, materials, symmetric, ia, ja):
                 v2 = w
             bcval2 = np.zeros((len(coords), len(qw), 3))
             bcval2[..., : v2.shape[-1]] = v2
-        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw, ids=b.elnodes, bcval2=bcval2)
+        outward = None
+        if kind == orc.ELAST3D_BC and bctype == 4:  # the vector data.normal is oriented with (ComputeNormal)
+            from neopz_b200 import gridmesh
+            outward = gridmesh.face_outward(mesh, b)
+        arr, k = orc.make_elems(b.topology, mesh.porder, kind, bctype, coords, mvec, qpts, qw, ids=b.elnodes, bcval2=bcval2,
+                                outward=outward)
         elems.append(arr)
         keep.append(k)
         dest_parts.append(b.dest)

@@ -59,6 +59,8 @@ def fixture_setup(g):
         mesh = gridmesh.grid_mesh(m["n"], m["p"], 3 if m["phys"] == 1 else 1, tetrahedra=m["tet"] == 1, prisms=m["tet"] == 2,
                                   bc_matids=bc, perturb=m["perturb"], node_perm=g["node_perm"] if m.get("scramble") else None)
     mats = materials_for(m["phys"], neumann=bct >= 1)
+    if m["phys"] == 0 and bct == 2:  # TPZMatPoisson::ContributeBC type 2 with refdriver's Val1
+        mats[-2] = mats[1].CreateBC(-2, 2, [[gu.POISSON_BC2_VAL1]], [gu.NEUMANN_POISSON])
     if m["phys"] == 1 and bct >= 2:  # the other TPZElasticity3D::ContributeBC types on the zmax face
         mats[-2] = mats[1].CreateBC(-2, bct, gu.BC_VAL1, gu.BC_VAL2)
     if m.get("bcfunc"):  # boundary data from the functions of oracle/refdriver.cpp (vectorised over the points)
