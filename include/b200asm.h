@@ -235,6 +235,12 @@ int b200asm_multi_assemble_rhs(b200asm_multi *m, double *rhs_host);
 int b200asm_multi_assemble_async(b200asm_multi *m);
 int b200asm_multi_synchronize(b200asm_multi *m);
 int b200asm_multi_counters(const b200asm_multi *m, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* b200asm_cg_solve on the row-sharded matrix of the last b200asm_multi_assemble: every GPU multiplies its row block, the halos of
+ * the direction vector and of the product travel over NVLink (peer loads / reductions), the scalars of the iteration are summed
+ * on the host in GPU order.  f_host / x_host are GLOBAL vectors (f_host == NULL: the assembled load vector); x_host == NULL leaves
+ * the solution slices on the devices. */
+int b200asm_multi_cg_solve(b200asm_multi *m, int precond, int64_t max_iter, double tol, int from_current, const double *f_host,
+                           double *x_host, int64_t *iters_out, double *resid_out);
 /* duration (ms, CUDA events on the context stream) of the kernel launches of one group in the LAST assembly;
  * needs option "timing" = 1.  Waits for that group's launches to finish. */
 int b200asm_group_time_ms(b200asm_ctx *ctx, int group, double *ms);

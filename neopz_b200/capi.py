@@ -56,7 +56,7 @@ SYMBOLS = [
     "b200asm_multi_set_option", "b200asm_multi_set_nodes", "b200asm_multi_add_group", "b200asm_multi_set_group_coef",
     "b200asm_multi_set_group_force", "b200asm_multi_clear_groups", "b200asm_multi_set_pattern", "b200asm_multi_partition",
     "b200asm_multi_assemble", "b200asm_multi_assemble_rhs", "b200asm_multi_assemble_async", "b200asm_multi_synchronize",
-    "b200asm_multi_counters", "b200asm_device_count",
+    "b200asm_multi_counters", "b200asm_device_count", "b200asm_multi_cg_solve",
 ]
 
 
@@ -133,6 +133,7 @@ def lib():
     L.b200asm_multi_assemble_async.argtypes = [vp]
     L.b200asm_multi_synchronize.argtypes = [vp]
     L.b200asm_multi_counters.argtypes = [vp, ip64, ip64, ip64]
+    L.b200asm_multi_cg_solve.argtypes = [vp, C.c_int, C.c_int64, C.c_double, C.c_int, dp, dp, ip64, dp]
     _lib = L
     return L
 
@@ -511,3 +512,19 @@ class MultiContext:
         k, h, d = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(lib().b200asm_multi_counters(self._h, C.byref(k), C.byref(h), C.byref(d)))
         return k.value, h.value, d.value
+
+    def cg_solve(self, precond=1, max_iter=50000, tol=1e-15, x0=None, f=None, download=True):
+        """CG on the row-sharded device-resident matrix (b200asm_multi_cg_solve); global vectors in and out.
+        Returns (x or None, iterations, relative residual)."""
+        n = self.neq()
+        x = None
+        if x0 is not None:
+            x = np.ascontiguousarray(x0, dtype=np.float64).copy()
+        elif download:
+            x = np.zeros(n)
+        if f is not None:
+            f = np.ascontiguousarray(f, dtype=np.float64)
+        it, res = C.c_int64(), C.c_double()
+        self._check(lib().b200asm_multi_cg_solve(self._h, int(precond), int(max_iter), float(tol), int(x0 is not None), dptr(f), dptr(x),
+                                                 C.byref(it), C.byref(res)))
+        return x, it.value, res.value

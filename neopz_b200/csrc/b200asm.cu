@@ -2812,6 +2812,259 @@ extern "C" int b200asm_cg_solve(b200asm_ctx *ctx, int precond, int64_t max_iter,
     return 0;
 }
 
+// ---- row-sharded conjugate gradients (several GPUs of this process; driven by b200asm_multi_cg_solve in multi.cpp) ----------
+#include "cg_sharded.h"
+int b200asm_cg_sharded(int nshards, const b200asm_cg_shard *sh, int precond, int64_t max_iter, double tol, int from_current,
+                       const double *f_host, double *x_host, int64_t *iters_out, double *resid_out, std::string &err) {
+#define CKS(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                              \
+            return B200ASM_ECUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+    if (nshards < 1 || !sh || max_iter < 0 || (precond != 0 && precond != 1)) { err = "cg_sharded: bad arguments"; return B200ASM_EINVAL; }
+    struct Dev {
+        double *x, *r, *p, *z, *q, *diag, *f;
+        int32_t *h_local = nullptr, *h_owner = nullptr, *h_remote = nullptr;
+        double **peer_p = nullptr, **peer_q = nullptr;
+        int grid = 1, grid_rows = 1, grid_halo = 1;
+    };
+    std::vector<Dev> dv(nshards);
+    auto cleanup = [&]() {
+        for (int k = 0; k < nshards; k++) {
+            cudaSetDevice(sh[k].ctx->device);
+            cudaFree(dv[k].h_local); cudaFree(dv[k].h_owner); cudaFree(dv[k].h_remote); cudaFree(dv[k].peer_p); cudaFree(dv[k].peer_q);
+        }
+    };
+    // workspace per shard: 7 vectors of the LOCAL length (x, r, p, z, q, diag, f), the owned segment is authoritative
+    for (int k = 0; k < nshards; k++) {
+        b200asm_ctx *ctx = sh[k].ctx;
+        if (!ctx->have_pattern || !ctx->d_a || !ctx->d_ja) { err = "cg_sharded: assemble a matrix first"; return B200ASM_ESTATE; }
+        CKS(cudaSetDevice(ctx->device));
+        const int64_t n = ctx->neq;
+        if (ctx->cg_n != n || !ctx->d_cg) {
+            if (from_current && !x_host) { err = "cg_sharded: from_current needs an initial guess"; return B200ASM_EINVAL; }
+            cudaFree(ctx->d_cg); cudaFree(ctx->d_cg_part); cudaFree(ctx->d_cg_sc);
+            ctx->d_cg = ctx->d_cg_part = nullptr; ctx->d_cg_sc = nullptr; ctx->cg_n = 0;
+            CKS(cudaMalloc((void **)&ctx->d_cg, (size_t)std::max<int64_t>(n, 1) * 7 * sizeof(double)));
+            CKS(cudaMalloc((void **)&ctx->d_cg_part, (size_t)ctx->num_sms * 8 * sizeof(double)));
+            CKS(cudaMalloc((void **)&ctx->d_cg_sc, sizeof(cgdev::Scalars)));
+            CKS(cudaMemsetAsync(ctx->d_cg, 0, (size_t)std::max<int64_t>(n, 1) * 7 * sizeof(double), ctx->stream));
+            ctx->cg_n = n;
+        }
+        Dev &d = dv[k];
+        d.x = ctx->d_cg; d.r = d.x + n; d.p = d.r + n; d.z = d.p + n; d.q = d.z + n; d.diag = d.q + n; d.f = d.diag + n;
+        const int64_t no = std::max<int64_t>(sh[k].nown, 1);
+        d.grid = (int)std::max<int64_t>(1, std::min<int64_t>((no + cgdev::THREADS - 1) / cgdev::THREADS, (int64_t)ctx->num_sms * 8));
+        d.grid_rows = (int)std::max<int64_t>(1, std::min<int64_t>((no + 7) / 8, (int64_t)ctx->num_sms * 32));
+        d.grid_halo = (int)std::max<int64_t>(1, std::min<int64_t>((sh[k].nhalo + 255) / 256, (int64_t)ctx->num_sms * 8));
+    }
+    // halo maps and the peers' vector addresses; peer access in both directions of every halo relation
+    for (int k = 0; k < nshards; k++) {
+        b200asm_ctx *ctx = sh[k].ctx;
+        CKS(cudaSetDevice(ctx->device));
+        Dev &d = dv[k];
+        std::vector<double *> pp(nshards), pq(nshards);
+        for (int j = 0; j < nshards; j++) { pp[j] = dv[j].p; pq[j] = dv[j].q; }
+        CKS(cudaMalloc((void **)&d.peer_p, nshards * sizeof(double *)));
+        CKS(cudaMalloc((void **)&d.peer_q, nshards * sizeof(double *)));
+        CKS(cudaMemcpyAsync(d.peer_p, pp.data(), nshards * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+        CKS(cudaMemcpyAsync(d.peer_q, pq.data(), nshards * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+        if (sh[k].nhalo) {
+            const size_t b = (size_t)sh[k].nhalo * sizeof(int32_t);
+            CKS(cudaMalloc((void **)&d.h_local, b)); CKS(cudaMalloc((void **)&d.h_owner, b)); CKS(cudaMalloc((void **)&d.h_remote, b));
+            CKS(cudaMemcpyAsync(d.h_local, sh[k].halo_local, b, cudaMemcpyHostToDevice, ctx->stream));
+            CKS(cudaMemcpyAsync(d.h_owner, sh[k].halo_owner, b, cudaMemcpyHostToDevice, ctx->stream));
+            CKS(cudaMemcpyAsync(d.h_remote, sh[k].halo_remote, b, cudaMemcpyHostToDevice, ctx->stream));
+            std::vector<char> need(nshards, 0);
+            for (int64_t i = 0; i < sh[k].nhalo; i++) need[sh[k].halo_owner[i]] = 1;
+            for (int j = 0; j < nshards; j++) {
+                if (!need[j] || sh[j].ctx->device == ctx->device) continue;
+                int can = 0;
+                CKS(cudaDeviceCanAccessPeer(&can, ctx->device, sh[j].ctx->device));
+                if (!can) { err = "cg_sharded: no peer access between two devices"; cleanup(); return B200ASM_ECUDA; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(sh[j].ctx->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); cleanup(); return B200ASM_ECUDA; }
+                cudaGetLastError();
+            }
+        }
+        CKS(cudaStreamSynchronize(ctx->stream));
+    }
+    auto sync_all = [&]() -> cudaError_t {
+        for (int k = 0; k < nshards; k++) {
+            cudaError_t e = cudaSetDevice(sh[k].ctx->device);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(sh[k].ctx->stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    // sum over the shards (in shard order) of one device scalar each
+    std::vector<cgdev::Scalars> hs(nshards);
+    auto gather_scalars = [&]() -> cudaError_t {
+        for (int k = 0; k < nshards; k++) {
+            cudaError_t e = cudaSetDevice(sh[k].ctx->device);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&hs[k], sh[k].ctx->d_cg_sc, sizeof(cgdev::Scalars), cudaMemcpyDeviceToHost, sh[k].ctx->stream);
+            if (e != cudaSuccess) return e;
+        }
+        return sync_all();
+    };
+    // q = A p over all shards: halo of p in, product, halo of q out
+    auto product = [&](int which /*0: p -> q ; 1: x -> q (initial residual)*/) -> cudaError_t {
+        for (int k = 0; k < nshards; k++) {   // the owners' values must be complete before anybody pulls them
+            b200asm_ctx *ctx = sh[k].ctx;
+            cudaSetDevice(ctx->device);
+            cudaError_t e = cudaMemsetAsync(dv[k].q, 0, (size_t)std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream);
+            if (e != cudaSuccess) return e;
+            if (which == 1) {  // x rides in p's place for the halo pull
+                e = cudaMemcpyAsync(dv[k].p + sh[k].own_first, dv[k].x + sh[k].own_first, (size_t)sh[k].nown * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        cudaError_t e = sync_all();
+        if (e != cudaSuccess) return e;
+        for (int k = 0; k < nshards; k++) {
+            b200asm_ctx *ctx = sh[k].ctx;
+            cudaSetDevice(ctx->device);
+            if (sh[k].nhalo)
+                cgdev::halo_pull_kernel<<<dv[k].grid_halo, 256, 0, ctx->stream>>>(sh[k].nhalo, dv[k].h_local, dv[k].h_owner, dv[k].h_remote, dv[k].peer_p, dv[k].p);
+            if (sh[k].nown)
+                cgdev::spmv_rows_kernel<<<dv[k].grid_rows, cgdev::THREADS, 0, ctx->stream>>>(sh[k].own_first, sh[k].nown, ctx->d_ia, ctx->d_ja, ctx->d_a,
+                                                                                             ctx->symmetric, 1.0, dv[k].p, dv[k].q);
+            ctx->launches += 2;
+        }
+        e = sync_all();   // every local product is done: the halo contributions may travel
+        if (e != cudaSuccess) return e;
+        for (int k = 0; k < nshards; k++) {
+            b200asm_ctx *ctx = sh[k].ctx;
+            if (!ctx->symmetric || !sh[k].nhalo) continue;
+            cudaSetDevice(ctx->device);
+            cgdev::halo_push_kernel<<<dv[k].grid_halo, 256, 0, ctx->stream>>>(sh[k].nhalo, dv[k].h_local, dv[k].h_owner, dv[k].h_remote, dv[k].peer_q, dv[k].q);
+            ctx->launches++;
+        }
+        return sync_all();
+    };
+    // right-hand side, initial guess
+    for (int k = 0; k < nshards; k++) {
+        b200asm_ctx *ctx = sh[k].ctx;
+        CKS(cudaSetDevice(ctx->device));
+        Dev &d = dv[k];
+        const int64_t o = sh[k].own_first, no = sh[k].nown;
+        CKS(cudaMemsetAsync(ctx->d_cg_sc, 0, sizeof(cgdev::Scalars), ctx->stream));
+        if (f_host) {
+            CKS(cudaMemcpyAsync(d.f + o, f_host + sh[k].row0, (size_t)no * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d += no * (int64_t)sizeof(double);
+        } else {
+            CKS(cudaMemcpyAsync(d.f + o, ctx->d_rhs + o, (size_t)no * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        if (from_current && x_host) {
+            CKS(cudaMemcpyAsync(d.x + o, x_host + sh[k].row0, (size_t)no * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d += no * (int64_t)sizeof(double);
+        } else if (!from_current) {
+            CKS(cudaMemsetAsync(d.x, 0, (size_t)std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
+        }
+        CKS(cudaMemcpyAsync(d.r + o, d.f + o, (size_t)no * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        cgdev::dot_kernel<<<d.grid, cgdev::THREADS, 0, ctx->stream>>>(no, d.f + o, d.f + o, ctx->d_cg_part, ctx->d_cg_sc, 1);
+        if (precond == 1) cgdev::extract_diag_kernel<<<d.grid, cgdev::THREADS, 0, ctx->stream>>>(ctx->neq, ctx->d_ia, ctx->d_ja, ctx->d_a, ctx->symmetric, d.diag);
+        ctx->launches += 2;
+    }
+    CKS(gather_scalars());
+    double normb2 = 0.0;
+    for (int k = 0; k < nshards; k++) normb2 += hs[k].rr;
+    double normb = std::sqrt(normb2);
+    if (normb == 0.0) normb = 1.0;
+    if (from_current) {  // r = b - A x
+        CKS(product(1));
+        for (int k = 0; k < nshards; k++) {
+            b200asm_ctx *ctx = sh[k].ctx;
+            CKS(cudaSetDevice(ctx->device));
+            const int64_t o = sh[k].own_first, no = sh[k].nown;
+            // r -= q with the x/r update kernel: alpha = 1 on (p = 0-vector is not at hand): do it as r = r - 1 * q through z as scratch
+            cgdev::update_xr_val_kernel<<<dv[k].grid, cgdev::THREADS, 0, ctx->stream>>>(no, 1.0, dv[k].z + o, dv[k].q + o, dv[k].z + o, dv[k].r + o,
+                                                                                        ctx->d_cg_part, ctx->d_cg_sc);
+        }
+    } else {
+        for (int k = 0; k < nshards; k++) {
+            b200asm_ctx *ctx = sh[k].ctx;
+            CKS(cudaSetDevice(ctx->device));
+            const int64_t o = sh[k].own_first, no = sh[k].nown;
+            cgdev::dot_kernel<<<dv[k].grid, cgdev::THREADS, 0, ctx->stream>>>(no, dv[k].r + o, dv[k].r + o, ctx->d_cg_part, ctx->d_cg_sc, 1);
+        }
+    }
+    CKS(gather_scalars());
+    double rr = 0.0;
+    for (int k = 0; k < nshards; k++) rr += hs[k].rr;
+    double resid = std::sqrt(rr) / normb;
+    int64_t it = 0;
+    double rho = 0.0, rho_prev = 0.0;
+    if (resid > tol) {
+        for (it = 1; it <= max_iter; it++) {
+            for (int k = 0; k < nshards; k++) {   // z = M^-1 r, rho = r.z
+                b200asm_ctx *ctx = sh[k].ctx;
+                cudaSetDevice(ctx->device);
+                const int64_t o = sh[k].own_first;
+                cgdev::precond_dot_kernel<<<dv[k].grid, cgdev::THREADS, 0, ctx->stream>>>(sh[k].nown, dv[k].r + o, precond == 1 ? dv[k].diag + o : nullptr,
+                                                                                          dv[k].z + o, ctx->d_cg_part, ctx->d_cg_sc);
+                ctx->launches++;
+            }
+            CKS(gather_scalars());
+            rho_prev = rho;
+            rho = 0.0;
+            for (int k = 0; k < nshards; k++) rho += hs[k].rho;
+            const double beta = it == 1 ? 0.0 : rho / rho_prev;
+            for (int k = 0; k < nshards; k++) {
+                b200asm_ctx *ctx = sh[k].ctx;
+                cudaSetDevice(ctx->device);
+                const int64_t o = sh[k].own_first;
+                cgdev::update_p_val_kernel<<<dv[k].grid, cgdev::THREADS, 0, ctx->stream>>>(sh[k].nown, it == 1, beta, dv[k].z + o, dv[k].p + o);
+                ctx->launches++;
+            }
+            CKS(product(0));
+            for (int k = 0; k < nshards; k++) {
+                b200asm_ctx *ctx = sh[k].ctx;
+                cudaSetDevice(ctx->device);
+                const int64_t o = sh[k].own_first;
+                cgdev::dot_kernel<<<dv[k].grid, cgdev::THREADS, 0, ctx->stream>>>(sh[k].nown, dv[k].p + o, dv[k].q + o, ctx->d_cg_part, ctx->d_cg_sc, 0);
+                ctx->launches++;
+            }
+            CKS(gather_scalars());
+            double pq = 0.0;
+            for (int k = 0; k < nshards; k++) pq += hs[k].pq;
+            const double alpha = rho / pq;
+            for (int k = 0; k < nshards; k++) {
+                b200asm_ctx *ctx = sh[k].ctx;
+                cudaSetDevice(ctx->device);
+                const int64_t o = sh[k].own_first;
+                cgdev::update_xr_val_kernel<<<dv[k].grid, cgdev::THREADS, 0, ctx->stream>>>(sh[k].nown, alpha, dv[k].p + o, dv[k].q + o, dv[k].x + o, dv[k].r + o,
+                                                                                            ctx->d_cg_part, ctx->d_cg_sc);
+                ctx->launches++;
+            }
+            CKS(gather_scalars());
+            rr = 0.0;
+            for (int k = 0; k < nshards; k++) rr += hs[k].rr;
+            resid = std::sqrt(rr) / normb;
+            if (!(resid == resid)) { err = "cg_sharded: the iteration produced NaN (singular or indefinite system)"; cleanup(); return B200ASM_ECUDA; }
+            if (resid <= tol) break;
+        }
+        if (it > max_iter) it = max_iter;
+    }
+    if (x_host) {
+        for (int k = 0; k < nshards; k++) {
+            b200asm_ctx *ctx = sh[k].ctx;
+            CKS(cudaSetDevice(ctx->device));
+            CKS(cudaMemcpyAsync(x_host + sh[k].row0, dv[k].x + sh[k].own_first, (size_t)sh[k].nown * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h += sh[k].nown * (int64_t)sizeof(double);
+        }
+        CKS(sync_all());
+    }
+    cleanup();
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = resid;
+    return 0;
+#undef CKS
+}
+
 extern "C" int b200asm_cg_solution_device(b200asm_ctx *ctx, double **x_dev) {
     if (!ctx || !x_dev) return B200ASM_EINVAL;
     *x_dev = ctx->d_cg;

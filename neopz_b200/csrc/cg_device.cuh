@@ -153,3 +153,74 @@ __global__ void __launch_bounds__(THREADS) update_xr_kernel(int64_t n, const dou
 }
 
 }  // namespace cgdev
+
+// ---- row-sharded solve (several GPUs, b200asm_multi_cg_solve) -------------------------------------------------------------
+// Every GPU holds the rows it owns (local rows [row_base, row_base + nrows)) with their complete pattern in a LOCAL numbering
+// that also contains the equations other GPUs own but these rows couple to ("halo").  One iteration exchanges two halos over
+// peer memory (NVLink): the owners' values of p are pulled into the halo before the product, and (symmetric storage) the
+// transposed contributions that the product left in the halo of q are added into the owners' q.  Scalars are summed on the
+// host in GPU order, so the iteration is the reference's statement by statement (Solvers/LinearSolvers/cg.h:44-120).
+namespace cgdev {
+
+// y += alpha * A x restricted to the owned rows
+__global__ void __launch_bounds__(THREADS) spmv_rows_kernel(int64_t row_base, int64_t nrows, const int64_t *__restrict__ ia,
+                                                            const int32_t *__restrict__ ja, const double *__restrict__ a, int symmetric,
+                                                            double alpha, const double *__restrict__ x, double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (THREADS / 32);
+    for (int64_t k0 = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); k0 < nrows; k0 += nwarps) {
+        const int64_t row = row_base + k0;
+        const int64_t s = ia[row], e = ia[row + 1];
+        const double xr = alpha * x[row];
+        double sum = 0.0;
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const int32_t c = ja[k];
+            const double v = a[k];
+            sum += v * x[c];
+            if (symmetric && c != row) atomicAdd(y + c, v * xr);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+        if (lane == 0) atomicAdd(y + row, alpha * sum);
+    }
+}
+
+// halo of a vector: v[local[k]] = (vector of the owning GPU)[remote[k]]      (P2P loads)
+__global__ void halo_pull_kernel(int64_t n, const int32_t *__restrict__ local, const int32_t *__restrict__ owner,
+                                 const int32_t *__restrict__ remote, double *const *__restrict__ peer_vec, double *__restrict__ v) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        v[local[k]] = peer_vec[owner[k]][remote[k]];
+}
+
+// (vector of the owning GPU)[remote[k]] += v[local[k]]                          (P2P reductions)
+__global__ void halo_push_kernel(int64_t n, const int32_t *__restrict__ local, const int32_t *__restrict__ owner,
+                                 const int32_t *__restrict__ remote, double *const *__restrict__ peer_vec, const double *__restrict__ v) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[local[k]];
+        if (x != 0.0) atomicAdd_system(peer_vec[owner[k]] + remote[k], x);
+    }
+    __threadfence_system();
+}
+
+// p = z (first) or p = beta p + z, beta from the host
+__global__ void update_p_val_kernel(int64_t n, int first, double beta, const double *__restrict__ z, double *__restrict__ p) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = first ? z[i] : beta * p[i] + z[i];
+}
+
+// x += alpha p;  r -= alpha q;  rr (this GPU's part) = r.r
+__global__ void __launch_bounds__(THREADS) update_xr_val_kernel(int64_t n, double alpha, const double *__restrict__ p,
+                                                                const double *__restrict__ q, double *__restrict__ x,
+                                                                double *__restrict__ r, double *partials, Scalars *sc) {
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        acc += ri * ri;
+    }
+    double total;
+    if (reduce_and_finish(acc, partials, &sc->counter, total)) sc->rr = total;
+}
+
+}  // namespace cgdev

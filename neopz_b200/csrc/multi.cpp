@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/b200asm.h"
+#include "cg_sharded.h"
 
 namespace {
 
@@ -57,6 +58,8 @@ struct Part {
     std::vector<std::vector<int64_t>> elements;  // per global group: element indices assigned to this GPU
     std::vector<int> local_group;      // per global group: index of its sub-group in ctx (-1: none)
     int64_t nelements = 0;
+    // halo of the owned rows (sharded CG): local equations owned by other GPUs that appear as columns of the owned rows
+    std::vector<int32_t> halo_local, halo_owner, halo_remote;
 };
 
 }  // namespace
@@ -356,7 +359,10 @@ extern "C" int b200asm_multi_set_pattern(b200asm_multi *m, int64_t neq, const in
                 const int64_t r = p.eqs[l];
                 lia[l] = pos;
                 if (r >= p.row0 && r < p.row1) {
-                    for (int64_t q = ia[r]; q < ia[r + 1]; q++) lja[pos++] = g2l[ja[q]];
+                    for (int64_t q = ia[r]; q < ia[r + 1]; q++) {
+                        lja[pos++] = g2l[ja[q]];
+                        if (ja[q] < p.row0 || ja[q] >= p.row1) mark[ja[q]] = 2;  // a column another GPU owns: halo of the solver
+                    }
                 } else {
                     while (rk < rem.size() && rem[rk].row < r) rk++;
                     while (rk < rem.size() && rem[rk].row == r) lja[pos++] = g2l[rem[rk++].col];
@@ -364,6 +370,9 @@ extern "C" int b200asm_multi_set_pattern(b200asm_multi *m, int64_t neq, const in
             }
             lia[p.nlocal] = pos;
             if (pos != p.nnz_local) return mfail(m, B200ASM_EINVAL, "b200asm_multi_set_pattern: internal: local pattern size");
+            p.halo_local.clear();
+            for (int64_t l = 0; l < p.nlocal; l++)
+                if (mark[p.eqs[l]] == 2) p.halo_local.push_back((int32_t)l);
             // rows above the owned block that an element of this GPU touches (their load-vector entries travel too)
             std::vector<uint8_t> touched((size_t)neq, 0);
             for (size_t gi = 0; gi < ng; gi++) {
@@ -452,7 +461,37 @@ extern "C" int b200asm_multi_set_pattern(b200asm_multi *m, int64_t neq, const in
         }
         if (a0 != rem.size() || r0 != rrows.size()) return mfail(m, B200ASM_EINVAL, "b200asm_multi_set_pattern: internal: staged entries without an owner");
     }
+    // halo maps of the sharded solver: owner and position there of every halo equation (every own_first is known now)
+    for (int k = 0; k < ndev; k++) {
+        Part &p = m->parts[k];
+        p.halo_owner.resize(p.halo_local.size());
+        p.halo_remote.resize(p.halo_local.size());
+        for (size_t i = 0; i < p.halo_local.size(); i++) {
+            const int64_t eq = p.eqs[p.halo_local[i]];
+            const int o = owner_of(eq);
+            p.halo_owner[i] = o;
+            p.halo_remote[i] = (int32_t)(m->parts[o].own_first + (eq - m->parts[o].row0));
+        }
+    }
     m->have_pattern = true;
+    return 0;
+}
+
+// Conjugate gradients on the row-sharded matrix of the last b200asm_multi_assemble (csrc/cg_device.cuh): the reference's CG
+// (Solvers/LinearSolvers/cg.h:44-120), the product of TPZSYsmpMatrix::MultAdd (Matrix/pzsysmp.cpp:190-232) split by row blocks,
+// halos of p and q over NVLink.  Same arguments as b200asm_cg_solve; f_host / x_host are GLOBAL vectors.
+extern "C" int b200asm_multi_cg_solve(b200asm_multi *m, int precond, int64_t max_iter, double tol, int from_current, const double *f_host,
+                                      double *x_host, int64_t *iters_out, double *resid_out) {
+    if (!m) return B200ASM_EINVAL;
+    if (!m->have_pattern) return mfail(m, B200ASM_ESTATE, "b200asm_multi_cg_solve: assemble a matrix first");
+    std::vector<b200asm_cg_shard> sh(m->parts.size());
+    for (size_t k = 0; k < m->parts.size(); k++) {
+        Part &p = m->parts[k];
+        sh[k] = {p.ctx, p.own_first, p.row1 - p.row0, p.row0, (int64_t)p.halo_local.size(), p.halo_local.data(), p.halo_owner.data(), p.halo_remote.data()};
+    }
+    std::string err;
+    const int rc = b200asm_cg_sharded((int)sh.size(), sh.data(), precond, max_iter, tol, from_current, f_host, x_host, iters_out, resid_out, err);
+    if (rc < 0) return mfail(m, rc, err);
     return 0;
 }
 

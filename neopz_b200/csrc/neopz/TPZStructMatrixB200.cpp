@@ -991,15 +991,16 @@ template <class TVar>
 void TPZStructMatrixB200<TVar>::SolveCG(const TPZFMatrix<TVar> &F, TPZFMatrix<TVar> &result, int64_t &numiterations, REAL &tol,
                                         bool jacobi, int fromcurrent) {
     TPZB200AssemblyCache &c = *fCache;
-    if (c.multi) Fatal("SolveCG: the device CG runs on one GPU (SetDevice); the row-sharded matrix of several GPUs is downloaded by Assemble");
-    if (!c.ctx || !c.pattern_set) Fatal("SolveCG: Assemble(stiffness, rhs) must run first (the matrix lives on the device)");
+    if ((!c.ctx && !c.multi) || !c.pattern_set) Fatal("SolveCG: Assemble(stiffness, rhs) must run first (the matrix lives on the device)");
     if constexpr (std::is_same<TVar, double>::value) {
         if (F.Rows() != c.nactive || F.Cols() != 1) Fatal("SolveCG: F has the wrong size");
         if (!fromcurrent || result.Rows() != c.nactive || result.Cols() != 1) result.Redim(c.nactive, 1);
         int64_t iters = 0;
         double resid = 0;
-        if (b200asm_cg_solve(c.ctx, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid) < 0)
-            Fatal(std::string("b200asm_cg_solve failed: ") + b200asm_last_error(c.ctx));
+        // several GPUs: every GPU multiplies its row block, halos over NVLink (b200asm_multi_cg_solve)
+        const int rc = c.multi ? b200asm_multi_cg_solve(c.multi, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid)
+                               : b200asm_cg_solve(c.ctx, jacobi ? 1 : 0, numiterations, tol, fromcurrent, &F.g(0, 0), &result(0, 0), &iters, &resid);
+        if (rc < 0) Fatal(std::string("b200asm_cg_solve failed: ") + c.LastError());
         numiterations = iters;
         tol = resid;
     } else {

@@ -196,9 +196,25 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
     step.SetDirect(symmetric ? ELDLt : ELU);  // never decomposed: the CG below is run on the assembled matrix
     an.SetSolver(step);
     auto t0 = clk::now();
-    an.Assemble();
+    if (g_loadcases > 1) {
+        // TPZAnalysis::ComputeNumberofLoadCases (Analysis/TPZAnalysis.cpp:307-335) never finds more than one load case (its
+        // everyMatHasLoadCase flag starts false and is never set), so TPZLinearAnalysis::Assemble sizes fRhs with one column and
+        // the reference's own AddFel then aborts.  Several load cases are driven the way the struct matrix supports them: the
+        // caller sizes the rhs (StrMatrix/TPZStrMatParInterface.cpp:13-14 keeps its columns).
+        an.Rhs().Redim(cmesh->NEquations(), g_loadcases);
+        auto *mat = an.StructMatrix()->CreateAssemble(an.Rhs(), nullptr);
+        an.MatrixSolver<STATE>().SetMatrix(mat);
+    } else {
+        an.Assemble();
+    }
     auto t1 = clk::now();
-    an.Assemble();
+    if (g_loadcases > 1) {
+        an.MatrixSolver<STATE>().Matrix()->Zero();
+        an.Rhs().Zero();
+        an.StructMatrix()->Assemble(*an.MatrixSolver<STATE>().Matrix().operator->(), an.Rhs(), nullptr);
+    } else {
+        an.Assemble();
+    }
     auto t2 = clk::now();
     t_first = secs(t0, t1);
     t_second = secs(t1, t2);
@@ -248,7 +264,7 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
         for (int64_t i = 0; i < neq; i++) out.sol[i] = sol(i, 0);
         // the same solve on the GPU, through the unmodified TPZLinearAnalysis::Solve(): the matrix the strategy left on
         // the device, the reference's CG algorithm with its Jacobi(1) preconditioner
-        if (b200 && b200->NumDevicesUsed() == 1) {
+        if (b200) {  // (several GPUs: the row-sharded CG, halos over NVLink)
             TPZB200CGSolver<STATE> dev(b200, 50000, 1.e-15, true, 0);
             dev.SetMatrix(mtx);
             an.SetSolver(dev);
@@ -261,7 +277,12 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
         }
     }
     // right-hand side only: TPZLinearAnalysis::AssembleResidual() -> TPZStrMatParInterface::Assemble(rhs)
-    an.AssembleResidual();
+    if (g_loadcases > 1) {
+        an.Rhs().Redim(neq, g_loadcases);
+        an.StructMatrix()->Assemble(an.Rhs(), nullptr);
+    } else {
+        an.AssembleResidual();
+    }
     {
         TPZFMatrix<STATE> &res = an.Rhs();
         const int rc = (int)res.Cols();

@@ -87,6 +87,12 @@ int b200asm_assemble_async(b200asm_ctx *) { return B200ASM_ENODEVICE; }
 int b200asm_counters(const b200asm_ctx *, int64_t *a, int64_t *b, int64_t *c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return 0; }
 }
 
+#include "../../neopz_b200/csrc/cg_sharded.h"
+// the solver needs the device: the CPU harness only checks the partition / push maps / halo maps
+int b200asm_cg_sharded(int, const b200asm_cg_shard *, int, int64_t, double, int, const double *, double *, int64_t *, double *, std::string &err) {
+    err = "stub: no device";
+    return B200ASM_ENODEVICE;
+}
 #include "../../neopz_b200/csrc/multi.cpp"
 
 static double w_of(int64_t a, int64_t b) {  // symmetric, integer valued

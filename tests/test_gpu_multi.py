@@ -64,3 +64,41 @@ def test_multi_device_against_oracle(ndev, n, p, phys, tet, symmetric, shuffle):
     multi.Assemble(a_pin.numpy(), r_pin.numpy())
     assert relF(a_pin.numpy(), a_ref) <= TOL and relF(r_pin.numpy(), rhs_ref) <= TOL
     multi.ctx.close()
+
+
+@pytest.mark.parametrize("ndev", [2, 4])
+@pytest.mark.parametrize("n,p,phys,tet,symmetric,shuffle", [(6, 2, 0, False, True, 0), (4, 2, 1, False, True, 0), (5, 2, 0, True, True, 3),
+                                                            (6, 1, 0, False, False, 0), (5, 2, 0, False, False, 9)])
+def test_sharded_cg_against_one_gpu_and_scipy(ndev, n, p, phys, tet, symmetric, shuffle):
+    """N2 across GPUs (b200asm_multi_cg_solve): the reference's CG (Solvers/LinearSolvers/cg.h:44-120, Jacobi(1) preconditioner)
+    on the row-sharded resident matrix - row-block products, halos of p and q over NVLink - against the one-GPU device CG and a
+    direct solve of the assembled system (1e-10, the north star's bound for the CG solution)."""
+    if torch.cuda.device_count() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=tet, perturb=0.1)   # Dirichlet on all faces: definite
+    if shuffle:
+        mesh = renumbered(mesh, shuffle)
+    mats = materials_for(phys)
+    one = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+    ia, ja, a1, rhs1 = one.CreateAssemble()
+    x1, it1, res1 = one.SolveCG(max_iter=20000, tol=1e-14)
+    one.ctx.close()
+    multi = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric, devices=list(range(ndev)))
+    multi.Create()
+    a, rhs = multi.Assemble()
+    x, it, res = multi.SolveCG(max_iter=20000, tol=1e-14)
+    assert res <= 1e-14 and it > 0
+    U = sp.csr_matrix((a1, ja, ia), shape=(mesh.neq, mesh.neq))
+    A = (U + sp.triu(U, 1).T) if symmetric else U
+    xd = spla.spsolve(sp.csc_matrix(A), rhs1)
+    assert relF(x, xd) <= 1e-10 and relF(x1, xd) <= 1e-10
+    assert relF(x, x1) <= 1e-10
+    # warm start from the solution: nothing left to do; a second right-hand side through the same matrix
+    x2, it2, res2 = multi.SolveCG(max_iter=20000, tol=1e-12, x0=x)
+    assert it2 <= 2 and res2 <= 1e-12
+    f2 = np.linspace(0.5, 1.5, mesh.neq)
+    x3, _it3, _res3 = multi.SolveCG(max_iter=20000, tol=1e-14, f=f2)
+    assert relF(x3, spla.spsolve(sp.csc_matrix(A), f2)) <= 1e-10
+    multi.ctx.close()
