@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--extra", default="c5,c4,c3", help="other BASELINE.json configurations measured after the headline and reported under "
                     "\"configs\" (c3 tetrahedra p2 elasticity, c4 hexahedra p4 Poisson, c5 hexahedra p2 elasticity; per-GPU slabs, weak scaling)")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--gather", type=int, default=0, help="1: closed-form groups are assembled row by row in a fixed order (option gather of the C ABI; slower, deterministic)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -75,8 +76,12 @@ def parse():
 def kernel_name(a):
     if a.engine == 1:
         if a.topo == "tet" and a.variant == 0 and a.p <= 2:
+            if a.gpus == 1 and a.gather:
+                return "gat::gather_rows_kernel (closed-form element matrices of straight-sided tetrahedra, every CSR row written once by the warp that owns its node)"
             return "assemble_affine_simplex_kernel (closed-form element matrices of straight-sided tetrahedra, one warp per element)"
         if a.topo == "hex" and a.perturb == 0.0 and a.p <= 2:
+            if a.gpus == 1 and a.gather:
+                return "gat::gather_rows_kernel (closed-form element matrices of parallelepiped hexahedra, every CSR row written once by the warp that owns its node)"
             return "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)"
         if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and (a.variant == 0 or 8 <= a.variant <= 15):
             return "assemble_sumfact_hex_p2_poisson_kernel (sum factorisation with prefetch, one CTA of 64 threads per element)"
@@ -265,6 +270,8 @@ class Case:
             self.strmat.ctx.set_option("locality", 0)
         if a.debug:
             self.strmat.ctx.set_option("debug", a.debug)
+        if a.gather:
+            self.strmat.ctx.set_option("gather", 1)
         t0 = time.time()
         if self.sharded:
             ia, ja = self.sharded.Create()
@@ -335,7 +342,11 @@ class Case:
         ach_tf = flops / (self.kernel_ms * 1e-3) / 1e12
         ach_gb = byts / (self.kernel_ms * 1e-3) / 1e9
         t_fp, t_hbm = flops / (fp64_peak * 1e12), byts / (hbm_peak * 1e9)
-        if t_fp >= t_hbm:
+        kname = kernel_name(a)
+        closed_form = "closed-form" in kname
+        # closed-form kernels do not execute the reference's quadrature arithmetic (6-15x fewer flops): what bounds them is
+        # the memory system, so their fraction is quoted on the HBM roofline of the compulsory bytes
+        if t_fp >= t_hbm and not closed_form:
             r = {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 / DFMA; the larger measured peak)", "achieved": ach_tf,
                  "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                  "peak_source": "measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json): "
@@ -343,6 +354,8 @@ class Case:
         else:
             r = {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+            if closed_form:
+                r["note"] = "closed-form element matrices: the FP64 roofline of the reference's arithmetic (%.2f of it) does not bound this kernel" % (ach_tf / fp64_peak)
         traffic = None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{a.topo},{a.p},{a.phys},{a.n},{a.scatter}")
@@ -352,12 +365,12 @@ class Case:
             pass
         # executed arithmetic of the kernels (upper triangle of ek only, fused multiply-adds counted as 2): what the FP64
         # pipe actually does per element, next to the reference-arithmetic count `achieved` is quoted on
-        x_el = executed_flops(a.topo, a.p, a.phys, kernel_name(a))
+        x_el = executed_flops(a.topo, a.p, a.phys, kname)
         r.update({"traffic": traffic, "algorithmic_flops_per_element": f_el, "algorithmic_bytes_per_element": b_el,
                   "hbm_GBps_algorithmic": ach_gb, "hbm_frac_algorithmic": ach_gb / hbm_peak, "hbm_peak_GBps": hbm_peak,
                   "executed_flops_per_element": x_el,
                   "fp64_pipe_utilisation_executed": (x_el * self.nvol / (self.kernel_ms * 1e-3) / 1e12 / fp64_peak) if x_el else None,
-                  "kernel": kernel_name(a), "kernel_ms": self.kernel_ms, "kernel_share_of_step": self.kernel_ms / self.ms_per_step,
+                  "kernel": kname, "kernel_ms": self.kernel_ms, "kernel_share_of_step": self.kernel_ms / self.ms_per_step,
                   "peaks": {"fp64_tflops": fp64_peak, "hbm_gbs": hbm_peak}})
         return r
 
@@ -385,6 +398,9 @@ def executed_flops(topo, p, phys, kernel):
         return None
     pairs = n * (n + 1) // 2
     geom = q * (194 if topo == "hex" else 122) + q * 18 * n
+    if "gather" in kernel:      # both triangles of the node pairs (the owner of a row recomputes its part of every element)
+        n2 = n * n
+        return 2.0 * 6 * n2 if phys == "poisson" else 2.0 * 54 * n2 + 30 * n2
     if "affine" in kernel:      # 54 FMA per node pair (9 Jinv products x 6 table rows) + block combination
         return 2.0 * 54 * pairs + (9 * 3 * pairs if phys == "elasticity" else 0) + 200
     if "sumfact" in kernel:
@@ -573,7 +589,8 @@ def main():
         ums = u0.elapsed_time(u1) / a.steps
         f_el, b_el = algorithmic_work(a.topo, a.p, a.phys, nvol, neq, nnz)
         uniform = {"value": nvol / (ums * 1e-3), "unit": "elements/s", "ms_per_step": ums,
-                   "kernel": "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)",
+                   "kernel": ("gat::gather_rows_kernel (closed-form element matrices of parallelepiped hexahedra, every CSR row written once)" if a.gather else
+                              "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)"),
                    "hbm_GBps_algorithmic": b_el * nvol / (ums * 1e-3) / 1e9,
                    "hbm_frac_algorithmic": b_el * nvol / (ums * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
                    "note": "same pattern and materials, unperturbed grid nodes; device-resident like `value`"}

@@ -244,6 +244,10 @@ int b200asm_multi_cg_solve(b200asm_multi *m, int precond, int64_t max_iter, doub
 /* duration (ms, CUDA events on the context stream) of the kernel launches of one group in the LAST assembly;
  * needs option "timing" = 1.  Waits for that group's launches to finish. */
 int b200asm_group_time_ms(b200asm_ctx *ctx, int group, double *ms);
+/* kernel family that assembles the matrix part of a group (chosen when the scatter maps are built, i.e. valid after the first
+ * assembly): "sumfact", "dmma", "closed_form", "gather_rows", "register_tile", "generic", "plane", "boundary".  Diagnostic: the
+ * reference has no counterpart (its one code path is Mesh/pzinterpolationspace.cpp:404-473). */
+int b200asm_group_kernel(const b200asm_ctx *ctx, int group, char *name, int len);
 /* number of kernels launched by this context so far, and bytes moved H2D/D2H */
 int b200asm_counters(const b200asm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

@@ -56,7 +56,7 @@ SYMBOLS = [
     "b200asm_multi_set_option", "b200asm_multi_set_nodes", "b200asm_multi_add_group", "b200asm_multi_set_group_coef",
     "b200asm_multi_set_group_force", "b200asm_multi_clear_groups", "b200asm_multi_set_pattern", "b200asm_multi_partition",
     "b200asm_multi_assemble", "b200asm_multi_assemble_rhs", "b200asm_multi_assemble_async", "b200asm_multi_synchronize",
-    "b200asm_multi_counters", "b200asm_device_count", "b200asm_multi_cg_solve",
+    "b200asm_multi_counters", "b200asm_device_count", "b200asm_multi_cg_solve", "b200asm_group_kernel",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
     L.b200asm_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.b200asm_counters.argtypes = [vp, ip64, ip64, ip64]
     L.b200asm_group_time_ms.argtypes = [vp, C.c_int, dp]
+    L.b200asm_group_kernel.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     L.b200asm_scatter_add.argtypes = [vp, C.c_int, vp, vp, C.c_int64]
     L.b200asm_gauss_legendre.argtypes = [C.c_int, dp, dp]
     L.b200asm_tensor_rule.argtypes = [C.c_int, C.c_int, dp, dp]
@@ -409,6 +410,12 @@ class Context:
         k, h, d = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(lib().b200asm_counters(self._h, C.byref(k), C.byref(h), C.byref(d)))
         return k.value, h.value, d.value
+
+    def group_kernel(self, group):
+        """Kernel family of the matrix part of a group in the last assembly (b200asm_group_kernel)."""
+        buf = C.create_string_buffer(32)
+        self._check(lib().b200asm_group_kernel(self._h, int(group), buf, 32))
+        return buf.value.decode()
 
 
 class _Borrowed(Context):

@@ -120,6 +120,7 @@ __device__ __forceinline__ void scatter_many(double *a, const int32_t (&pos)[N],
 #include "gram_mma_team.cuh"
 #include "affine_simplex.cuh"
 #include "affine_hex.cuh"
+#include "gather_rows.cuh"
 #include "sumfact_hex.cuh"
 #include "pattern_device.cuh"
 #include "cg_device.cuh"
@@ -932,6 +933,18 @@ struct Group {
     double *d_qw = nullptr, *d_phi = nullptr, *d_dphi = nullptr, *d_dng = nullptr, *d_force = nullptr;
     double *d_dng_t = nullptr, *d_dphi_pad = nullptr, *d_phi_pad = nullptr, *d_aux = nullptr, *d_aux2 = nullptr;
     bool sumfact_ok = false;  // hexahedra p = 2, Poisson, the 27-point tensor rule: the sum-factorisation kernel applies
+    // owner-computes assembly of the closed-form groups (gather_rows.cuh)
+    bool use_gather = false;   // the group's matrix part runs gat::gather_rows_kernel (decided by choose_kernels)
+    bool gather_bad = false;   // the setup found a requirement violated (node blocks not consecutive, filtered equations, long rows)
+    int64_t ng = 0;            // node blocks of the group
+    int gather_rl = 0;         // doubles per row buffer
+    int32_t *d_grow = nullptr, *d_gptr = nullptr;
+    gat::NodeRec *d_grec = nullptr;
+    int gather_wpc = 8;        // warps per CTA of the gather kernel (as many as the row buffers leave room for)
+    uint32_t *d_glist = nullptr;
+    unsigned short *d_relpos = nullptr;
+    double *d_fac = nullptr;
+    std::vector<int64_t> gchunk, gchunk_min;  // node-block ranges launched apart (overlapped download) and their first rows
     size_t smap_len = 0;
     // element colouring (B200ASM_SCATTER_COLORED): elements are stored sorted by colour; seg = colour boundaries
     // ({0, nel} when not coloured); seg_smap = offset of every segment's scatter map (register-tile kernels)
@@ -977,6 +990,10 @@ struct b200asm_ctx {
     int scatter = B200ASM_SCATTER_ATOMIC;
     int engine = 1;  // 1: DMMA panel kernel where one exists, 0: register-tile DFMA kernels only
     int debug = 0;     // profiling aid, see VolParams::debug
+    int gather = 0;     // option "gather" (off by default: measured 2-3x slower than the scatter kernels, profiles/r02_gather_vs_scatter.md):
+                        // closed-form groups are assembled row by row in a fixed order (gather_rows.cuh) instead of scattered
+    unsigned char *d_rowflag = nullptr;  // [neq] see gather_rows.cuh (valid with the scatter maps, when any group gathers)
+    bool any_gather = false;
     int drop_tiny = 0;  // option "drop_tiny": the matrix scatter skips |value| < 1e-12 like the reference's AddKel (entry-major kernels only)
     int variant = 0;   // tuning alternative of the DMMA kernels (option "variant", before add_group)
     int rhs_only = 0;  // set while b200asm_assemble_rhs runs
@@ -1132,6 +1149,7 @@ struct MmaEntry {
                                int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t);
     cudaError_t (*prepare)(size_t smem, int *ctas_per_sm);
     bool sumfact = false;  // sum-factorisation kernel: needs Group::sumfact_ok (the 3 x 3 x 3 tensor rule in the reference's point order)
+    bool closed = false;   // closed-form kernel of affine elements (affine_simplex.cuh / affine_hex.cuh): the gather kernel can take over
 };
 template <class C>
 cudaError_t launch_mma(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
@@ -1209,7 +1227,9 @@ cudaError_t prepare_aff(size_t smem, int *ctas_per_sm) {
 }
 template <class C>
 MmaEntry make_aff_entry(int porder, int variant = 0) {
-    return MmaEntry{variant, B200ASM_TET, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_aff<C>, &launch_aff_smap<C>, &prepare_aff<C>};
+    MmaEntry e{variant, B200ASM_TET, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_aff<C>, &launch_aff_smap<C>, &prepare_aff<C>};
+    e.closed = true;
+    return e;
 }
 // Ghat[e][f](in,jn) = sum_q w dphi(e,in) dphi(f,jn), cphi[j] = sum_q w phi_j, cd[e][j] = sum_q w dphi(e,j): the aux table
 template <class C>
@@ -1302,7 +1322,9 @@ cudaError_t prepare_affhex(size_t smem, int *ctas_per_sm) {
 }
 template <class C>
 MmaEntry make_affhex_entry(int porder, int topology = B200ASM_HEX, int variant = 0) {
-    return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_affhex<C>, &launch_affhex_smap<C>, &prepare_affhex<C>};
+    MmaEntry e{variant, topology, porder, C::NS, C::SLOTS, C::WPC * 32, C::WPC, &C::smem_bytes, &launch_affhex<C>, &launch_affhex_smap<C>, &prepare_affhex<C>};
+    e.closed = true;
+    return e;
 }
 // the same closed-form kernel on straight-sided tetrahedra of order 3, 4 (table in shared memory): the default of these orders
 // since round 2 (profiles/r02_time_tet_closed_form.jsonl: p3 Poisson 489 M elements/s against 108 M of the register-tile
@@ -1401,6 +1423,7 @@ void free_group(Group &g) {
     cudaFree(g.d_elnodes); cudaFree(g.d_dest); cudaFree(g.d_smap); cudaFree(g.d_smapT);
     cudaFree(g.d_qw); cudaFree(g.d_phi); cudaFree(g.d_dphi); cudaFree(g.d_dng); cudaFree(g.d_force);
     cudaFree(g.d_dng_t); cudaFree(g.d_dphi_pad); cudaFree(g.d_phi_pad); cudaFree(g.d_aux); cudaFree(g.d_aux2);
+    cudaFree(g.d_grow); cudaFree(g.d_gptr); cudaFree(g.d_glist); cudaFree(g.d_relpos); cudaFree(g.d_fac); cudaFree(g.d_grec);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
     if (g.ev2) cudaEventDestroy(g.ev2);
@@ -1431,7 +1454,147 @@ int choose_kernels(b200asm_ctx *ctx) {
         }
         g.aff_checked = true;
     }
+    // closed-form groups of order <= 2 are assembled row by row (gather_rows.cuh) when nothing else writes into their rows
+    // concurrently: one GPU (no staging rows, no peers), atomic mode (the coloured mode keeps its own deterministic launches)
+    for (Group &g : ctx->groups) {
+        bool want = false;
+        if (ctx->gather && ctx->engine == 1 && !ctx->drop_tiny && ctx->scatter == B200ASM_SCATTER_ATOMIC && ctx->links.empty() &&
+            ctx->staging_lo == ctx->staging_hi && g.dim == 3 && !g.generic && g.uniform && g.porder <= 2 && g.nel > 0 &&
+            g.nel < (1 << 27) && g.d_aux && !g.gather_bad && (g.topology == B200ASM_HEX || g.topology == B200ASM_TET)) {
+            const MmaEntry *fe = fast_entry(ctx, g);
+            want = fe && fe->closed;
+        }
+        if (want != g.use_gather) {
+            g.use_gather = want;
+            ctx->maps_valid = false;
+        }
+    }
     return 0;
+}
+
+// warps of gat::gather_rows_kernel<n, ns> whose buffers fit the shared memory of an SM next to the table (0: no such kernel)
+template <int N, int NS>
+int gather_warps_fit(int rl) {
+    using C = gat::Cfg<N, NS>;
+    const size_t avail = 226 * 1024, table = sizeof(double) * C::GT_LEN, per_warp = sizeof(double) * C::warp_doubles(rl);
+    return table >= avail ? 0 : (int)((avail - table) / per_warp);
+}
+int gather_max_warps(int n, int ns, int rl) {
+    if (n == 4) return ns == 1 ? gather_warps_fit<4, 1>(rl) : gather_warps_fit<4, 3>(rl);
+    if (n == 8) return ns == 1 ? gather_warps_fit<8, 1>(rl) : gather_warps_fit<8, 3>(rl);
+    if (n == 10) return ns == 1 ? gather_warps_fit<10, 1>(rl) : gather_warps_fit<10, 3>(rl);
+    if (n == 27) return ns == 1 ? gather_warps_fit<27, 1>(rl) : gather_warps_fit<27, 3>(rl);
+    return 0;
+}
+
+// Gather structures of one closed-form group (gather_rows.cuh).  Returns 1 when a requirement is violated (the group then
+// keeps its scatter kernel), 0 when built, < 0 on errors.
+int build_gather(b200asm_ctx *ctx, Group &g, const int32_t *d_ja) {
+    auto drop = [&]() {
+        cudaFree(g.d_grow); cudaFree(g.d_gptr); cudaFree(g.d_glist); cudaFree(g.d_relpos); cudaFree(g.d_fac); cudaFree(g.d_grec);
+        g.d_grow = g.d_gptr = nullptr; g.d_glist = nullptr; g.d_relpos = nullptr; g.d_fac = nullptr; g.d_grec = nullptr;
+    };
+    drop();
+    const int64_t neq = ctx->neq;
+    const int64_t npairs = g.nel * g.n;
+    cudaStream_t st = ctx->stream;
+    int32_t *d_cnt = nullptr, *d_slot = nullptr, *d_flag = nullptr;
+    int *d_misc = nullptr;  // [0] bad, [1] missing, [2] max row length
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_cnt); cudaFree(d_slot); cudaFree(d_flag); cudaFree(d_misc); cudaFree(d_tmp); };
+#define CKG(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            cleanup();                                                                                   \
+            return fail(ctx, B200ASM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                                \
+    } while (0)
+    CKG(cudaMalloc((void **)&d_cnt, (size_t)(neq + 1) * sizeof(int32_t)));
+    CKG(cudaMalloc((void **)&d_slot, (size_t)(neq + 1) * sizeof(int32_t)));
+    CKG(cudaMalloc((void **)&d_flag, (size_t)(neq + 1) * sizeof(int32_t)));
+    CKG(cudaMalloc((void **)&d_misc, 3 * sizeof(int)));
+    CKG(cudaMalloc((void **)&g.d_gptr, (size_t)(neq + 1) * sizeof(int32_t)));
+    CKG(cudaMemsetAsync(d_cnt, 0, (size_t)(neq + 1) * sizeof(int32_t), st));
+    CKG(cudaMemsetAsync(d_flag, 0, (size_t)(neq + 1) * sizeof(int32_t), st));
+    CKG(cudaMemsetAsync(d_misc, 0, 3 * sizeof(int), st));
+    const int grid = (int)std::min<int64_t>((npairs + 255) / 256, (int64_t)ctx->num_sms * 32);
+    const int grid_eq = (int)std::max<int64_t>(1, std::min<int64_t>((neq + 255) / 256, (int64_t)ctx->num_sms * 32));
+    gat::count_kernel<<<grid, 256, 0, st>>>(g.nel, g.n, g.ns, g.d_dest, d_cnt, d_misc);
+    gat::flag_nonempty_kernel<<<grid_eq, 256, 0, st>>>(neq, d_cnt, d_flag);
+    size_t tmp_bytes = 0, tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, g.d_gptr, (int)(neq + 1), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_flag, d_slot, (int)(neq + 1), st);
+    tmp_bytes = std::max(tmp_bytes, tmp2);
+    CKG(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 1)));
+    CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, g.d_gptr, (int)(neq + 1), st));
+    CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flag, d_slot, (int)(neq + 1), st));
+    int misc[3] = {0, 0, 0};
+    int32_t ng32 = 0;
+    CKG(cudaMemcpyAsync(misc, d_misc, sizeof(misc), cudaMemcpyDeviceToHost, st));
+    CKG(cudaMemcpyAsync(&ng32, d_slot + neq, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+    ctx->launches += 4;
+    if (misc[0]) {  // node blocks not consecutive / filtered equations
+        cleanup();
+        drop();
+        return 1;
+    }
+    g.ng = ng32;
+    CKG(cudaMalloc((void **)&g.d_grow, std::max<size_t>((size_t)g.ng, 1) * sizeof(int32_t)));
+    CKG(cudaMalloc((void **)&g.d_grec, std::max<size_t>((size_t)g.ng, 1) * sizeof(gat::NodeRec)));
+    CKG(cudaMalloc((void **)&g.d_glist, std::max<size_t>((size_t)npairs, 1) * sizeof(uint32_t)));
+    CKG(cudaMalloc((void **)&g.d_relpos, std::max<size_t>((size_t)npairs * g.ns * g.n, 1) * sizeof(unsigned short)));
+    CKG(cudaMalloc((void **)&g.d_fac, std::max<size_t>((size_t)g.nel * (g.ns == 1 ? 6 : 10), 1) * sizeof(double)));
+    gat::compact_keys_kernel<<<grid_eq, 256, 0, st>>>(neq, d_cnt, d_slot, g.d_grow);
+    gat::node_records_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>((g.ng + 255) / 256, (int64_t)ctx->num_sms * 32)), 256, 0, st>>>(
+        g.ng, g.d_grow, g.d_gptr, g.d_grec, d_misc);
+    CKG(cudaMemsetAsync(d_flag, 0, (size_t)(neq + 1) * sizeof(int32_t), st));  // (reused as the fill cursor)
+    gat::fill_kernel<<<grid, 256, 0, st>>>(g.nel, g.n, g.ns, g.d_dest, g.d_gptr, d_flag, g.d_glist);
+    const int grid_g = (int)std::max<int64_t>(1, std::min<int64_t>((g.ng + 127) / 128, (int64_t)ctx->num_sms * 32));
+    gat::sort_groups_kernel<<<grid_g, 128, 0, st>>>(g.ng, g.d_grow, g.d_gptr, g.d_glist);
+    const int grid_w = (int)std::max<int64_t>(1, std::min<int64_t>((g.ng + gat::WPC - 1) / gat::WPC, (int64_t)ctx->num_sms * 16));
+    gat::relpos_kernel<<<grid_w, gat::WPC * 32, 0, st>>>(g.ng, g.n, g.ns, ctx->symmetric, g.d_grow, g.d_gptr, g.d_glist, g.d_dest, ctx->d_ia, d_ja,
+                                                          g.d_relpos, d_misc + 1, d_misc, d_misc + 2);
+    CKG(cudaGetLastError());
+    CKG(cudaMemcpyAsync(misc, d_misc, sizeof(misc), cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+    ctx->launches += 4;
+    if (misc[1]) {
+        cleanup();
+        return fail(ctx, B200ASM_EPATTERN, "gather map: " + std::to_string(misc[1]) + " element entries have no position in the CSR pattern");
+    }
+    // per-warp row buffers: ns rows of the longest row for every node block a warp handles side by side; the table and at
+    // least 4 warps must fit the shared memory of an SM (rows too long for that or for the 16-bit positions, nodes with more
+    // than gat::MAXDEG elements: the group keeps its scatter kernel)
+    g.gather_rl = ((misc[2] + 3) / 4) * 4 + 4;
+    const int wmax = gather_max_warps(g.n, g.ns, g.gather_rl);
+    if (misc[0] || wmax < 4) {
+        cleanup();
+        drop();
+        return 1;
+    }
+    g.gather_wpc = std::min(wmax, 24);
+    // node-block ranges for the overlapped download: the rows of a range are final when its launch has finished
+    g.gchunk.assign(1, 0);
+    if (g.nel >= 2 * ctx->overlap_min_elements) {
+        const int nchunk = (int)std::min<int64_t>(16, g.nel / ctx->overlap_min_elements);
+        for (int c = 1; c < nchunk; c++) {
+            const int64_t b = g.ng * c / nchunk;
+            if (b > g.gchunk.back() && b < g.ng) g.gchunk.push_back(b);
+        }
+    }
+    g.gchunk.push_back(g.ng);
+    g.gchunk_min.assign(g.gchunk.size() - 1, 0);
+    for (size_t c = 0; c + 1 < g.gchunk.size(); c++) {
+        int32_t key = 0;
+        if (g.gchunk[c] < g.ng) CKG(cudaMemcpyAsync(&key, g.d_grow + g.gchunk[c], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CKG(cudaStreamSynchronize(st));
+        g.gchunk_min[c] = key;
+    }
+    cleanup();
+    return 0;
+#undef CKG
 }
 
 int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
@@ -1442,10 +1605,52 @@ int build_smaps(b200asm_ctx *ctx, const int32_t *d_ja) {
         const int rc = choose_kernels(ctx);
         if (rc) return rc;
     }
+    // closed-form groups that gather: their row lists replace the scatter map; a group that does not qualify falls back
+    ctx->any_gather = false;
+    for (Group &g : ctx->groups) {
+        if (!g.use_gather) continue;
+        const int rc = build_gather(ctx, g, d_ja);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            g.gather_bad = true;
+            g.use_gather = false;
+        } else {
+            ctx->any_gather = true;
+        }
+    }
+    cudaFree(ctx->d_rowflag);
+    ctx->d_rowflag = nullptr;
+    if (ctx->any_gather) {
+        // rows another group contributes to are zeroed and added to; the rest of a gathering group's rows are stored once
+        unsigned char *d_touched = nullptr;
+        CK(cudaMalloc((void **)&ctx->d_rowflag, std::max<int64_t>(ctx->neq, 1)));
+        CK(cudaMalloc((void **)&d_touched, std::max<int64_t>(ctx->neq, 1)));
+        CK(cudaMemsetAsync(ctx->d_rowflag, 0, std::max<int64_t>(ctx->neq, 1), ctx->stream));
+        CK(cudaMemsetAsync(d_touched, 0, std::max<int64_t>(ctx->neq, 1), ctx->stream));
+        for (Group &g : ctx->groups) {
+            if (g.use_gather || g.nel == 0) continue;
+            const int64_t n = g.nel * g.m;
+            gat::mark_rows_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 32), 256, 0, ctx->stream>>>(n, g.d_dest, d_touched);
+            ctx->launches++;
+        }
+        for (Group &g : ctx->groups) {
+            if (!g.use_gather) continue;
+            const int grid_g = (int)std::max<int64_t>(1, std::min<int64_t>((g.ng + 127) / 128, (int64_t)ctx->num_sms * 32));
+            gat::flag_rows_kernel<<<grid_g, 128, 0, ctx->stream>>>(g.ng, g.ns, g.d_grow, d_touched, ctx->d_rowflag);
+            ctx->launches++;
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_touched);
+    }
     CK(cudaMemsetAsync(ctx->d_missing, 0, sizeof(int), ctx->stream));
     for (Group &g : ctx->groups) {
         cudaFree(g.d_smap); cudaFree(g.d_smapT);
         g.d_smap = g.d_smapT = nullptr;
+        if (g.use_gather) {
+            g.smap_len = 0;
+            continue;
+        }
         if (entry_major(ctx, g)) {
             g.smap_len = (size_t)g.n * g.n * g.ns * g.ns * g.nel;
         } else if (const MmaEntry *me = fast_entry(ctx, g)) {
@@ -1544,6 +1749,7 @@ extern "C" void b200asm_destroy(b200asm_ctx *ctx) {
     if (ctx->ev_if) cudaEventDestroy(ctx->ev_if);
     if (ctx->ev_push) cudaEventDestroy(ctx->ev_push);
     cudaFree(ctx->d_xyz); cudaFree(ctx->d_ia); cudaFree(ctx->d_ja); cudaFree(ctx->d_a); cudaFree(ctx->d_rhs); cudaFree(ctx->d_missing);
+    cudaFree(ctx->d_rowflag);
     cudaFree(ctx->d_cg); cudaFree(ctx->d_cg_part); cudaFree(ctx->d_cg_sc);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1579,6 +1785,12 @@ extern "C" int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t va
     }
     if (!strcmp(name, "debug")) {
         ctx->debug = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "gather")) {
+        ctx->gather = value ? 1 : 0;
+        ctx->maps_valid = false;
+        for (Group &g : ctx->groups) g.aff_checked = false;
         return 0;
     }
     if (!strcmp(name, "drop_tiny")) {
@@ -2173,6 +2385,70 @@ int enqueue_group(b200asm_ctx *ctx, Group &g, int64_t r0, int64_t r1) {
     const bool use_mma = fast != nullptr;
     size_t smem = 0;
     int per_sm = 1;
+    if (g.use_gather && fast) {
+        // load vector: the closed-form kernel in its load-vector-only mode (whole group, with the first node-block range);
+        // matrix: node blocks [r0, r1) gathered row by row (r0 < 0: all)
+        const int64_t b0 = r0 < 0 ? 0 : r0, b1 = r0 < 0 ? g.ng : r1;
+        if (b0 == 0) {  // (once per assembly: a load-vector-only pass must not repeat it for every node-block range)
+            smem = fast->smem(g.nq);
+            CK(fast->prepare(smem, &per_sm));
+            if (per_sm < 1) return fail(ctx, B200ASM_ECUDA, "assemble: kernel does not fit on an SM");
+            VolParams p;
+            p.nel = g.nel; p.nq = g.nq; p.kind = g.kind; p.atomic = 1; p.rhs_only = 1; p.debug = 0; p.nbatch = 0;
+            p.xyz = ctx->d_xyz; p.elnodes = g.d_elnodes; p.dest = g.d_dest;
+            p.qw = g.d_qw; p.phi = g.d_phi; p.dphi = g.d_dphi; p.dng = g.d_dng; p.force = g.d_force;
+            p.dng_t = g.d_dng_t; p.dphi_pad = g.d_dphi_pad; p.phi_pad = g.d_phi_pad; p.aux = g.d_aux; p.aux2 = g.d_aux2;
+            p.smap = nullptr; p.smapT = nullptr;
+            p.a = ctx->d_a; p.rhs = ctx->d_rhs;
+            memcpy(p.coef, g.coef, sizeof(p.coef));
+            const int64_t want = (g.nel + fast->wpc - 1) / fast->wpc;
+            CK(fast->launch(p, (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * per_sm), smem, ctx->stream));
+            ctx->launches++;
+        }
+        if (ctx->rhs_only || b1 <= b0) return 0;
+        if (b0 == 0) {  // Jacobian factors of every element of the group
+            const int gridf = (int)std::min<int64_t>((g.nel + 127) / 128, (int64_t)ctx->num_sms * 16);
+            const double scale = g.ns == 1 ? g.coef[0] : 1.0;
+            if (g.nn == 4 && g.ns == 1) gat::factors_kernel<4, 1><<<gridf, 128, 0, ctx->stream>>>(g.nel, g.d_elnodes, ctx->d_xyz, scale, g.d_fac);
+            else if (g.nn == 4) gat::factors_kernel<4, 3><<<gridf, 128, 0, ctx->stream>>>(g.nel, g.d_elnodes, ctx->d_xyz, scale, g.d_fac);
+            else if (g.ns == 1) gat::factors_kernel<8, 1><<<gridf, 128, 0, ctx->stream>>>(g.nel, g.d_elnodes, ctx->d_xyz, scale, g.d_fac);
+            else gat::factors_kernel<8, 3><<<gridf, 128, 0, ctx->stream>>>(g.nel, g.d_elnodes, ctx->d_xyz, scale, g.d_fac);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        gat::Params gp;
+        gp.g0 = b0; gp.g1 = b1; gp.symmetric = ctx->symmetric; gp.rl = g.gather_rl;
+        gp.rec = g.d_grec; gp.glist = g.d_glist; gp.relpos = g.d_relpos; gp.rowflag = ctx->d_rowflag;
+        gp.fac = g.d_fac; gp.aux = g.d_aux; gp.npp = ((g.n * (g.n + 1) / 2 + 31) / 32) * 32;
+        gp.ia = ctx->d_ia; gp.a = ctx->d_a;
+        gp.c1 = g.coef[0]; gp.c2 = g.coef[1]; gp.c3 = g.coef[2];
+        // persistent grid: as many CTAs per SM as fit, every warp walks its tasks (SUBS node blocks each) with a grid stride
+#define B200ASM_GATHER(N_, NS_)                                                                                                   \
+    do {                                                                                                                          \
+        using GC = gat::Cfg<N_, NS_>;                                                                                             \
+        const size_t gsmem = GC::smem_bytes(g.gather_rl, g.gather_wpc);                                                           \
+        int per = 0;                                                                                                              \
+        CK(cudaFuncSetAttribute(gat::gather_rows_kernel<N_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));       \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gat::gather_rows_kernel<N_, NS_>, g.gather_wpc * 32, gsmem));       \
+        if (per < 1) return fail(ctx, B200ASM_ECUDA, "assemble: the gather kernel does not fit on an SM");                        \
+        const int64_t tasks = (b1 - b0 + GC::SUBS - 1) / GC::SUBS;                                                                \
+        const int ggrid = (int)std::max<int64_t>(1, std::min<int64_t>((tasks + g.gather_wpc - 1) / g.gather_wpc, (int64_t)ctx->num_sms * per)); \
+        gat::gather_rows_kernel<N_, NS_><<<ggrid, g.gather_wpc * 32, gsmem, ctx->stream>>>(gp);                                    \
+    } while (0)
+        if (g.n == 4 && g.ns == 1) B200ASM_GATHER(4, 1);
+        else if (g.n == 4) B200ASM_GATHER(4, 3);
+        else if (g.n == 10 && g.ns == 1) B200ASM_GATHER(10, 1);
+        else if (g.n == 10) B200ASM_GATHER(10, 3);
+        else if (g.n == 8 && g.ns == 1) B200ASM_GATHER(8, 1);
+        else if (g.n == 8) B200ASM_GATHER(8, 3);
+        else if (g.n == 27 && g.ns == 1) B200ASM_GATHER(27, 1);
+        else if (g.n == 27) B200ASM_GATHER(27, 3);
+        else return fail(ctx, B200ASM_EINVAL, "assemble: no gather kernel for this group");
+#undef B200ASM_GATHER
+        CK(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
     if (use_mma) {
         smem = fast->smem(g.nq);
         if (smem > 227 * 1024) return fail(ctx, B200ASM_EINVAL, "assemble: integration rule too large for shared memory");
@@ -2230,8 +2506,17 @@ int begin_assembly(b200asm_ctx *ctx) {
         const int rc = build_smaps(ctx, ctx->d_ja);
         if (rc) return rc;
     }
-    // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75
-    if (!ctx->rhs_only) CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
+    // Matrix()->Zero() + rhs.Redim of Analysis/TPZLinearAnalysis.cpp:70-75.  With gathering groups only the rows that are not
+    // stored outright start from zero (gather_rows.cuh): the stored rows are never read
+    if (!ctx->rhs_only) {
+        if (ctx->any_gather && ctx->d_rowflag) {
+            gat::zero_rows_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->neq, ctx->d_ia, ctx->d_rowflag, ctx->d_a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        } else {
+            CK(cudaMemsetAsync(ctx->d_a, 0, std::max<int64_t>(ctx->nnz, 1) * sizeof(double), ctx->stream));
+        }
+    }
     CK(cudaMemsetAsync(ctx->d_rhs, 0, std::max<int64_t>(ctx->neq, 1) * sizeof(double), ctx->stream));
     return 0;
 }
@@ -2249,7 +2534,7 @@ void build_units(const b200asm_ctx *ctx, std::vector<Unit> &units, size_t &npref
     units.clear();
     for (size_t gi = 0; gi < ctx->groups.size(); gi++) {
         const Group &g = ctx->groups[gi];
-        if (g.nel == 0 || g.n_if == 0) continue;
+        if (g.nel == 0 || g.n_if == 0 || g.use_gather) continue;
         units.push_back({(int)gi, 0, g.chunk[1], g.chunk_min[0], true});
     }
     nprefix = units.size();
@@ -2257,6 +2542,11 @@ void build_units(const b200asm_ctx *ctx, std::vector<Unit> &units, size_t &npref
         for (size_t gi = 0; gi < ctx->groups.size(); gi++) {
             const Group &g = ctx->groups[gi];
             if (g.nel == 0) continue;
+            if (g.use_gather) {  // node-block ranges in row order (they run last: the other groups add into zeroed rows first)
+                if (pass == 1)
+                    for (size_t c = 0; c + 1 < g.gchunk.size(); c++) units.push_back({(int)gi, g.gchunk[c], g.gchunk[c + 1], g.gchunk_min[c], false});
+                continue;
+            }
             const bool chunked = g.chunk.size() > 2;
             if (chunked != (pass == 1)) continue;
             if (!chunked) {
@@ -2515,7 +2805,7 @@ extern "C" int b200asm_assemble(b200asm_ctx *ctx, double *a_host, double *rhs_ho
     if (!ctx) return B200ASM_EINVAL;
     if (a_host && ctx->overlap && ctx->scatter == B200ASM_SCATTER_ATOMIC && !ctx->rhs_only && ctx->have_pattern) {
         bool chunked = false;
-        for (const Group &g : ctx->groups) chunked = chunked || g.chunk.size() > 2;
+        for (const Group &g : ctx->groups) chunked = chunked || (g.use_gather ? g.gchunk.size() > 2 : g.chunk.size() > 2);
         // pageable destinations make cudaMemcpyAsync block the launching thread: overlap only into pinned / registered memory
         cudaPointerAttributes attr;
         const bool pinned = cudaPointerGetAttributes(&attr, a_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -2675,6 +2965,8 @@ extern "C" int b200asm_exchange_add_peer(b200asm_ctx *ctx, int push, int slot_th
     if (!l.push && incoming_min_row >= 0) ctx->incoming_min_row = std::min(ctx->incoming_min_row, incoming_min_row);
     ctx->links.push_back(l);
     ctx->ov_valid = false;
+    for (const Group &g : ctx->groups)
+        if (g.use_gather) ctx->maps_valid = false;  // another GPU adds into this context's rows: back to the scatter kernels
     return (int)ctx->links.size() - 1;
 }
 
@@ -3075,6 +3367,20 @@ extern "C" int b200asm_device_pointers(b200asm_ctx *ctx, double **a_dev, double 
     if (!ctx) return B200ASM_EINVAL;
     if (a_dev) *a_dev = ctx->d_a;
     if (rhs_dev) *rhs_dev = ctx->d_rhs;
+    return 0;
+}
+
+// kernel family of the matrix part of a group, as chosen for the LAST assembly / scatter-map build
+extern "C" int b200asm_group_kernel(const b200asm_ctx *ctx, int group, char *name, int len) {
+    if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !name || len < 1) return B200ASM_EINVAL;
+    const Group &g = ctx->groups[group];
+    const char *k = "register_tile";
+    if (g.kind == B200ASM_BC) k = "boundary";
+    else if (g.plane) k = "plane";
+    else if (runs_generic(ctx, g)) k = "generic";
+    else if (g.use_gather) k = "gather_rows";
+    else if (const MmaEntry *fe = fast_entry(ctx, g)) k = fe->closed ? "closed_form" : (fe->sumfact ? "sumfact" : "dmma");
+    snprintf(name, (size_t)len, "%s", k);
     return 0;
 }
 

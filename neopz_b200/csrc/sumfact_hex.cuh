@@ -79,13 +79,14 @@ inline void build_tables(const double x[3], double *aux, double *F3) {
 
 // ---- phases (thread index t) -------------------------------------------------------------------------------------------
 // geometry at point q = t < 27: Msm[6][27] = s w|detJ| jacinv jacinv^T (symmetric part), Wd[27] = w|detJ|
-// X: corner coordinates [8][3]; dng: gradients of the corner functions [27][3][8]; qw[27]
-SF_HD void geometry(int q, const double *X, const double *dng, const double *qw, double scale, double *Msm, double *Wd) {
-    const double *dn = dng + (size_t)q * 24;
+// X: corner coordinates [8][3]; gradients of the corner functions: dN_a/dxi_k at point q = dn[(k * 8 + a) * ds] (dn = dng + 24 q,
+// ds = 1 for the table [27][3][8]; dn = dng_t + q, ds = 27 for the transposed table [3][8][27], whose reads are contiguous over
+// the lanes q of a warp: 2 wavefronts per load instead of 27); qw[27]
+SF_HD void geometry(int q, const double *X, const double *dn, int ds, const double *qw, double scale, double *Msm, double *Wd) {
     double j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0, j20 = 0, j21 = 0, j22 = 0;
 #pragma unroll
     for (int a = 0; a < 8; a++) {  // gradx(j,k) += x_a[j] * dN_a/dxi_k   (Geom/TPZGeoCube.h:141-149)
-        const double d0 = dn[a], d1 = dn[8 + a], d2 = dn[16 + a];
+        const double d0 = dn[a * ds], d1 = dn[(8 + a) * ds], d2 = dn[(16 + a) * ds];
         const double x = X[a * 3], y = X[a * 3 + 1], z = X[a * 3 + 2];
         j00 += x * d0; j01 += x * d1; j02 += x * d2;
         j10 += y * d0; j11 += y * d1; j12 += y * d2;
@@ -194,7 +195,9 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
     __shared__ double Msm[6 * 27];
     __shared__ double Wd[27];
     __shared__ double S1[2][sf::NITEM + 2];
+    __shared__ double Dn[24 * 27];  // dng_t [3][8][27]: the geometry phase reads it with the point index on the lanes
     const int t = threadIdx.x;
+    for (int i = t; i < 24 * 27; i += sf::NTHREADS) Dn[i] = __ldg(p.dng_t + i);
     const bool active = t < sf::NITEM;
     const int p1 = active ? t / 9 : 0, p2 = active ? t % 9 : 0;
     double F1[4][3], F2[4][3];  // the thread's rows of the factor tables, all four variants
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
             }
         }
         __syncthreads();
-        if (t < 27) sf::geometry(t, Xs, p.dng, p.qw, p.coef[0], Msm, Wd);
+        if (t < 27) sf::geometry(t, Xs, Dn + t, 27, p.qw, p.coef[0], Msm, Wd);
         __syncthreads();
         // ---- load vector: ef(i) += weight*fScale*phi(i)*force (TPZMatPoisson.cpp:39-40), threads 32..58 (the second warp)
         if (t >= 32 && t < 32 + 27) {

@@ -178,3 +178,94 @@ def test_mesh_signature_catches_a_material_filter_change():
     assert np.abs(a).max() > 1e10 and np.abs(a2).max() < 1e10
     st.ctx.close()
     st2.ctx.close()
+
+
+# ---- owner-computes ("gather") assembly of the closed-form groups (csrc/gather_rows.cuh) ------------------------------------
+@pytest.mark.parametrize("tet,p,phys", [(True, 1, 0), (True, 2, 0), (True, 1, 1), (True, 2, 1), (False, 1, 0), (False, 2, 0), (False, 1, 1), (False, 2, 1)])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_gather_equals_scatter_and_oracle(tet, p, phys, symmetric):
+    """Straight-sided tetrahedra (perturbed nodes) and parallelepiped hexahedra (sheared lattice): every CSR row written once by
+    the warp that owns its node, against the scatter kernels (option gather = 0) and the oracle; two assemblies bit-identical."""
+    n = 5
+    mesh = gridmesh.grid_mesh(n, p, 3 if phys else 1, tetrahedra=tet, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.12 if tet else 0.0)
+    if not tet:  # affine image of the grid: still parallelepipeds, no axis-aligned symmetry left
+        shear = np.array([[1.0, 0.2, -0.1], [0.05, 0.9, 0.15], [0.1, -0.2, 1.1]])
+        mesh.nodes[:] = mesh.nodes @ shear.T
+    mats = materials_for(phys, neumann=True)
+    st = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+    st.ctx.set_option("gather", 1)
+    ia, ja, a, rhs = st.CreateAssemble()
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+    assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+    assert "gather_rows" in [st.ctx.group_kernel(g) for gids in st.groups_of_block for g in gids], "the gather kernel ran"
+    a2, rhs2 = st.Assemble()
+    # fixed summation order in the rows only the gather kernel writes; the rows of the boundary nodes also receive the
+    # (atomic) penalty terms of the boundary elements first, so those agree to rounding only
+    assert relF(a, a2) <= 1e-15
+    same = a == a2
+    assert same.mean() > 0.5
+    st.ctx.close()
+    sc = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+    sc.ctx.set_option("gather", 0)
+    sc.SetPattern(ia, ja)
+    a3, rhs3 = sc.Assemble()
+    assert relF(a, a3) <= 1e-14 and relF(rhs, rhs3) <= 1e-14
+    sc.ctx.close()
+
+
+def test_gather_rows_shared_with_other_groups():
+    """Hexahedra + pyramids on the unperturbed grid: the hexahedra are parallelepipeds and gather, the pyramids scatter into the
+    rows they share (zeroed first, added to); two materials on the same rows likewise."""
+    mesh = gridmesh.hexpyr_mesh(4, 2, 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.0)
+    mats = materials_for(0, neumann=True)
+    for symmetric in (True, False):
+        st = sm.TPZStructMatrixB200(mesh, mats, symmetric=symmetric)
+        st.ctx.set_option("gather", 1)
+        ia, ja, a, rhs = st.CreateAssemble()
+        a_ref, rhs_ref = oracle_assemble(mesh, mats, symmetric, ia, ja)
+        assert relF(a, a_ref) <= TOL and relF(rhs, rhs_ref) <= TOL
+        a2, _ = st.Assemble()
+        assert relF(a2, a_ref) <= TOL
+        st.ctx.close()
+
+
+def test_gather_follows_the_geometry():
+    """b200asm_set_nodes: parallelepipeds -> gather; perturbed -> quadrature kernels + scatter maps; back again."""
+    n, p = 6, 2
+    mesh = gridmesh.grid_mesh(n, p, 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.0)
+    mats = materials_for(0, neumann=True)
+    st = sm.TPZStructMatrixB200(mesh, mats, symmetric=True)
+    st.ctx.set_option("gather", 1)
+    ia, ja, a0, rhs0 = st.CreateAssemble()
+    ref0 = oracle_assemble(mesh, mats, True, ia, ja)
+    assert relF(a0, ref0[0]) <= TOL
+    moved = gridmesh.grid_mesh(n, p, 1, bc_matids=(-1, -1, -1, -1, -1, -2), perturb=0.1)
+    st.ctx.set_nodes(moved.nodes)
+    a1, rhs1 = st.Assemble()
+    ref1 = oracle_assemble(moved, mats, True, ia, ja)
+    assert relF(a1, ref1[0]) <= TOL and relF(rhs1, ref1[1]) <= TOL
+    st.ctx.set_nodes(mesh.nodes)
+    a2, rhs2 = st.Assemble()
+    assert relF(a2, a0) <= 1e-15 and relF(rhs2, rhs0) <= 1e-14
+    st.ctx.close()
+
+
+def test_gather_overlapped_download_in_chunks():
+    """Page-locked host matrix + small chunks: node-block ranges are downloaded while later ranges are assembled."""
+    import torch
+    mesh = gridmesh.grid_mesh(10, 2, 3, tetrahedra=True, perturb=0.1)
+    mats = materials_for(1)
+    st = sm.TPZStructMatrixB200(mesh, mats, symmetric=True)
+    st.ctx.set_option("gather", 1)
+    st.ctx.set_option("overlap_min_elements", 256)
+    st.ctx.set_option("overlap_min_bytes", 4096)
+    ia, ja = st.Create(on_device=True)
+    a_pin = torch.empty(len(ja), dtype=torch.float64).pin_memory()
+    r_pin = torch.empty(mesh.neq, dtype=torch.float64).pin_memory()
+    st.Assemble(a_pin.numpy(), r_pin.numpy())
+    a_ref, rhs_ref = oracle_assemble(mesh, mats, True, ia, ja)
+    assert relF(a_pin.numpy(), a_ref) <= TOL and relF(r_pin.numpy(), rhs_ref) <= TOL
+    st.ctx.set_option("overlap", 0)
+    a2, rhs2 = st.Assemble()
+    assert relF(a2, a_pin.numpy()) <= 1e-15
+    st.ctx.close()

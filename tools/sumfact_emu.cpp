@@ -21,7 +21,7 @@ extern "C" int sf_emulate_mode(const double *X, const double *dng, const double 
     double aux[sf::AUX_LEN];
     sf::build_tables(x1d, aux, h_sfF3);
     double Msm[6 * 27], S1[2][sf::NITEM + 2];
-    for (int t = 0; t < 27; t++) sf::geometry(t, X, dng, qw, scale, Msm, Wd);
+    for (int t = 0; t < 27; t++) sf::geometry(t, X, dng + (size_t)t * 24, 1, qw, scale, Msm, Wd);
     double acc[sf::NTHREADS][9];
     std::memset(acc, 0, sizeof(acc));
     for (int c = 0; c < 9; c++) {
