@@ -83,7 +83,9 @@ def kernel_name(a):
             if a.gpus == 1 and a.gather:
                 return "gat::gather_rows_kernel (closed-form element matrices of parallelepiped hexahedra, every CSR row written once by the warp that owns its node)"
             return "assemble_affine_hex_kernel (closed-form element matrices of parallelepiped hexahedra, one warp per element)"
-        if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and (a.variant == 0 or 8 <= a.variant <= 15):
+        if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and a.variant in (0, 20):
+            return "assemble_sumfact_hex_p2_poisson_warp_kernel (sum factorisation, one warp per element, no block-wide barrier)"
+        if a.topo == "hex" and a.phys == "poisson" and a.p == 2 and a.variant == 13:
             return "assemble_sumfact_hex_p2_poisson_kernel (sum factorisation with prefetch, one CTA of 64 threads per element)"
         if a.topo == "hex" and a.phys == "poisson" and a.p == 2:
             return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"

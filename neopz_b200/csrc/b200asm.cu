@@ -1255,45 +1255,63 @@ void aff_tables(int nq, const double *qw, const double *phi, const double *dphi,
     }
 }
 // sum-factorisation kernel for hexahedra p = 2, Poisson (sumfact_hex.cuh): one CTA of 64 threads per element
-constexpr int kSumfactVariant = 8;
-template <int MINB, int PRIVATE, int PREFETCH>
+template <int MINB, int PREFETCH>
 cudaError_t launch_sumfact(const VolParams &p, int grid, size_t, cudaStream_t s) {
-    assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE, PREFETCH><<<grid, sf::NTHREADS, 0, s>>>(p);
+    assemble_sumfact_hex_p2_poisson_kernel<MINB, PREFETCH><<<grid, sf::NTHREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 inline cudaError_t launch_sumfact_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
                                        int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
-    build_sumfact_smap_kernel<<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    build_sumfact_smap_kernel<0><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
     return cudaGetLastError();
 }
-template <int MINB, int PRIVATE, int PREFETCH>
+// the one-warp-per-element form (WPC warps = WPC elements per CTA)
+template <int WPC, int MINB>
+cudaError_t launch_sumfact_warp(const VolParams &p, int grid, size_t, cudaStream_t s) {
+    assemble_sumfact_hex_p2_poisson_warp_kernel<WPC, MINB><<<grid, WPC * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+inline cudaError_t launch_sumfact_warp_smap(int64_t nel, const int32_t *dest, const int64_t *ia, const int32_t *ja, int symmetric,
+                                            int32_t *smap, int32_t *smapT, int *missing, int grid, cudaStream_t s) {
+    build_sumfact_smap_kernel<1><<<grid, 256, 0, s>>>(nel, dest, ia, ja, symmetric, smap, smapT, missing);
+    return cudaGetLastError();
+}
+template <int WPC, int MINB>
+cudaError_t prepare_sumfact_warp(size_t, int *ctas_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_sumfact_hex_p2_poisson_warp_kernel<WPC, MINB>, WPC * 32, 0);
+}
+template <int MINB, int PREFETCH>
 cudaError_t prepare_sumfact(size_t, int *ctas_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_sumfact_hex_p2_poisson_kernel<MINB, PRIVATE, PREFETCH>,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_sumfact_hex_p2_poisson_kernel<MINB, PREFETCH>,
                                                          sf::NTHREADS, 0);
 }
 inline size_t sumfact_smem(int) { return 0; }
-template <int MINB, int PRIVATE = 0, int PREFETCH = 0>
+template <int MINB, int PREFETCH>
 MmaEntry make_sumfact_entry(int variant) {
-    return MmaEntry{variant, B200ASM_HEX, 2, 1, sf::SLOTS, sf::NTHREADS, 1, &sumfact_smem, &launch_sumfact<MINB, PRIVATE, PREFETCH>,
-                    &launch_sumfact_smap, &prepare_sumfact<MINB, PRIVATE, PREFETCH>, true};
+    return MmaEntry{variant, B200ASM_HEX, 2, 1, sf::SLOTS, sf::NTHREADS, 1, &sumfact_smem, &launch_sumfact<MINB, PREFETCH>,
+                    &launch_sumfact_smap, &prepare_sumfact<MINB, PREFETCH>, true};
+}
+template <int WPC, int MINB>
+MmaEntry make_sumfact_warp_entry(int variant) {
+    return MmaEntry{variant, B200ASM_HEX, 2, 1, sfw::SLOTS, WPC * 32, WPC, &sumfact_smem, &launch_sumfact_warp<WPC, MINB>,
+                    &launch_sumfact_warp_smap, &prepare_sumfact_warp<WPC, MINB>, true};
 }
 // wpc = elements processed concurrently by one CTA; variant 0 = default (the first match wins).  Alternatives kept because a
-// test or a profile refers to them: 7 = the DMMA Gram kernels for tetrahedra that the closed-form kernels replaced, 8 = sum
-// factorisation without the prefetch (12 CTAs/SM), 11 = its barrier-free form, 13 = the default again, 16 = the one-warp DMMA Gram
-// kernel that was the default of hexahedra p = 2 Poisson in round 1 (it still runs every such group whose rule is not the 3 x 3 x 3
-// tensor rule).  Measured on a 96^3 perturbed grid (profiles/r02_sumfact_variants.jsonl): 13: 193.9 M elements/s, 16: 169.1,
-// 8: 163.7, 11: 148.3; the other alternatives of round 1 (9, 10, 12, 14, 15 and the DMMA occupancy variants 1-6) lost and were removed.
+// test or a profile refers to them: 7 = the DMMA Gram kernels for tetrahedra that the closed-form kernels replaced; for hexahedra
+// p = 2 Poisson 20 = the default again (sum factorisation, one warp per element), 13 = sum factorisation with one CTA of 64
+// threads per element (the default of the first round-2 passes), 16 = the one-warp DMMA Gram kernel that was the default in round
+// 1 (it still runs every such group whose rule is not the 3 x 3 x 3 tensor rule).  Measured on a 96^3 perturbed grid
+// (profiles/r02_sumfact_warp_variants.jsonl): 20: 286 M elements/s, 13: 219, 16: 159; the other alternatives lost and were removed.
 const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP1ElastAff>(1),
                          make_aff_entry<TetP2PoissonAff>(2), make_aff_entry<TetP2ElastAff>(2),
-                         make_sumfact_entry<8, 0, 1>(0),
+                         make_sumfact_warp_entry<4, 6>(0),
                          make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2, 7),
                          make_team_entry<HexP2ElastTeamV3>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
                          make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
                          make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2, 16),
                          make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 7),
-                         make_sumfact_entry<12>(kSumfactVariant), make_sumfact_entry<8, 1>(kSumfactVariant + 3),
-                         make_sumfact_entry<8, 0, 1>(kSumfactVariant + 5)};
+                         make_sumfact_entry<8, 1>(13), make_sumfact_warp_entry<4, 6>(20)};
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);

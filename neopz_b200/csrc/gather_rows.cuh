@@ -402,67 +402,70 @@ __global__ void __launch_bounds__(768) gather_rows_kernel(const Params p) {
             __syncwarp();
 #pragma unroll 1
             for (int s = 0; s < PC; s++) {
-                if (c0 + s >= deg) break;
-                const int li = cc[c0 + s] & 31;
-                const int tix = li * N + jn;
-                const double2 *f2 = reinterpret_cast<const double2 *>(myfac + s * FS);
-                if (NS == 1) {
-                    const unsigned short r0 = myrel[s * N];
-                    if (r0 != NOPOS) {
-                        const double2 fa = f2[0], fb = f2[1], fc = f2[2];
-                        double v = fa.x * Gt[0 * NN2 + tix];
-                        v += fa.y * Gt[1 * NN2 + tix];
-                        v += fb.x * Gt[2 * NN2 + tix];
-                        v += fb.y * Gt[3 * NN2 + tix];
-                        v += fc.x * Gt[4 * NN2 + tix];
-                        v += fc.y * Gt[5 * NN2 + tix];
-                        mybuf[r0] += v;
-                    }
-                } else {
-                    unsigned short rel[NS];
-                    bool any = false;
-#pragma unroll
-                    for (int a = 0; a < NS; a++) {
-                        rel[a] = myrel[(s * NS + a) * N];
-                        any = any || rel[a] != NOPOS;
-                    }
-                    if (any) {
-                        double ji[3][3];
-                        const double2 f0 = f2[0], f1 = f2[1], f2_ = f2[2], f3 = f2[3], f4 = f2[4];
-                        ji[0][0] = f0.x; ji[0][1] = f0.y; ji[0][2] = f1.x; ji[1][0] = f1.y; ji[1][1] = f2_.x;
-                        ji[1][2] = f2_.y; ji[2][0] = f3.x; ji[2][1] = f3.y; ji[2][2] = f4.x;
-                        const double adet = f4.y;
-                        const double C1 = p.c1 * adet, C2 = p.c2 * adet, C3 = p.c3 * adet;
-                        // S[v][u] = sum_{e,f} jacinv(e,v) jacinv(f,u) Ghat[e][f](li,jn), one table row e at a time
-                        double S[3][3];
-#pragma unroll
-                        for (int e2 = 0; e2 < 3; e2++) {
-                            const double g0 = Gt[(e2 * 3 + 0) * NN2 + tix], g1 = Gt[(e2 * 3 + 1) * NN2 + tix], g2 = Gt[(e2 * 3 + 2) * NN2 + tix];
-                            double T[3];
-#pragma unroll
-                            for (int u = 0; u < 3; u++) T[u] = g0 * ji[0][u] + g1 * ji[1][u] + g2 * ji[2][u];
-#pragma unroll
-                            for (int v = 0; v < 3; v++)
-#pragma unroll
-                                for (int u = 0; u < 3; u++) S[v][u] = e2 == 0 ? ji[0][v] * T[u] : S[v][u] + ji[e2][v] * T[u];
+                // (a column block can be another local node of the next element: the additions of one element are complete - on
+                //  every lane, whichever branch it took - before the next element's begin: compute-sanitizer racecheck)
+                if (c0 + s < deg) {
+                    const int li = cc[c0 + s] & 31;
+                    const int tix = li * N + jn;
+                    const double2 *f2 = reinterpret_cast<const double2 *>(myfac + s * FS);
+                    if (NS == 1) {
+                        const unsigned short r0 = myrel[s * N];
+                        if (r0 != NOPOS) {
+                            const double2 fa = f2[0], fb = f2[1], fc = f2[2];
+                            double v = fa.x * Gt[0 * NN2 + tix];
+                            v += fa.y * Gt[1 * NN2 + tix];
+                            v += fb.x * Gt[2 * NN2 + tix];
+                            v += fb.y * Gt[3 * NN2 + tix];
+                            v += fc.x * Gt[4 * NN2 + tix];
+                            v += fc.y * Gt[5 * NN2 + tix];
+                            mybuf[r0] += v;
                         }
-                        // the nine formulas of Material/Elasticity/TPZElasticity3D.cpp:318-326 (row node li, column node jn)
+                    } else {
+                        unsigned short rel[NS];
+                        bool any = false;
 #pragma unroll
                         for (int a = 0; a < NS; a++) {
-                            if (rel[a] == NOPOS) continue;
-                            const int b0 = (p.symmetric && jn == li) ? a : 0;
-                            double *row = mybuf + a * p.rl + rel[a] - b0;
+                            rel[a] = myrel[(s * NS + a) * N];
+                            any = any || rel[a] != NOPOS;
+                        }
+                        if (any) {
+                            double ji[3][3];
+                            const double2 f0 = f2[0], f1 = f2[1], f2_ = f2[2], f3 = f2[3], f4 = f2[4];
+                            ji[0][0] = f0.x; ji[0][1] = f0.y; ji[0][2] = f1.x; ji[1][0] = f1.y; ji[1][1] = f2_.x;
+                            ji[1][2] = f2_.y; ji[2][0] = f3.x; ji[2][1] = f3.y; ji[2][2] = f4.x;
+                            const double adet = f4.y;
+                            const double C1 = p.c1 * adet, C2 = p.c2 * adet, C3 = p.c3 * adet;
+                            // S[v][u] = sum_{e,f} jacinv(e,v) jacinv(f,u) Ghat[e][f](li,jn), one table row e at a time
+                            double S[3][3];
 #pragma unroll
-                            for (int b = 0; b < NS; b++) {
-                                const double x = a == b ? (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3
-                                                        : S[b][a] * C1 - S[a][b] * C2;
-                                if (b >= b0) row[b] += x;
+                            for (int e2 = 0; e2 < 3; e2++) {
+                                const double g0 = Gt[(e2 * 3 + 0) * NN2 + tix], g1 = Gt[(e2 * 3 + 1) * NN2 + tix], g2 = Gt[(e2 * 3 + 2) * NN2 + tix];
+                                double T[3];
+#pragma unroll
+                                for (int u = 0; u < 3; u++) T[u] = g0 * ji[0][u] + g1 * ji[1][u] + g2 * ji[2][u];
+#pragma unroll
+                                for (int v = 0; v < 3; v++)
+#pragma unroll
+                                    for (int u = 0; u < 3; u++) S[v][u] = e2 == 0 ? ji[0][v] * T[u] : S[v][u] + ji[e2][v] * T[u];
+                            }
+                            // the nine formulas of Material/Elasticity/TPZElasticity3D.cpp:318-326 (row node li, column node jn)
+#pragma unroll
+                            for (int a = 0; a < NS; a++) {
+                                if (rel[a] == NOPOS) continue;
+                                const int b0 = (p.symmetric && jn == li) ? a : 0;
+                                double *row = mybuf + a * p.rl + rel[a] - b0;
+#pragma unroll
+                                for (int b = 0; b < NS; b++) {
+                                    const double x = a == b ? (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3
+                                                            : S[b][a] * C1 - S[a][b] * C2;
+                                    if (b >= b0) row[b] += x;
+                                }
                             }
                         }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
         // the rows of the node blocks leave once, coalesced (all lanes on every row); the buffers are zero again afterwards
 #pragma unroll 1

@@ -81,8 +81,13 @@ inline void build_tables(const double x[3], double *aux, double *F3) {
 // geometry at point q = t < 27: Msm[6][27] = s w|detJ| jacinv jacinv^T (symmetric part), Wd[27] = w|detJ|
 // X: corner coordinates [8][3]; gradients of the corner functions: dN_a/dxi_k at point q = dn[(k * 8 + a) * ds] (dn = dng + 24 q,
 // ds = 1 for the table [27][3][8]; dn = dng_t + q, ds = 27 for the transposed table [3][8][27], whose reads are contiguous over
-// the lanes q of a warp: 2 wavefronts per load instead of 27); qw[27]
-SF_HD void geometry(int q, const double *X, const double *dn, int ds, const double *qw, double scale, double *Msm, double *Wd) {
+// the lanes q of a warp: 2 wavefronts per load instead of 27); wq = weight of the point.
+// Layout of M: Msm[m * MS + MT * (q / 3) + q % 3] - (MS, MT) = (27, 3) dense; (36, 4) pads the q1-triples to 32 bytes so that
+// stage 1 can read a triple with one 16-byte + one 8-byte load: measured SLOWER (259 against 287 M elements/s,
+// profiles/r02_sumfact_warp_variants.jsonl: a 16-byte shared load of nine distinct addresses costs more wavefronts than two
+// 8-byte loads), so the kernels use the dense layout
+template <int MS = 27, int MT = 3>
+SF_HD void geometry(int q, const double *X, const double *dn, int ds, double wq, double scale, double *Msm, double *Wd) {
     double j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0, j20 = 0, j21 = 0, j22 = 0;
 #pragma unroll
     for (int a = 0; a < 8; a++) {  // gradx(j,k) += x_a[j] * dN_a/dxi_k   (Geom/TPZGeoCube.h:141-149)
@@ -111,7 +116,7 @@ SF_HD void geometry(int q, const double *X, const double *dn, int ds, const doub
     ji[6] = (-j11 * j20 + j10 * j21) * id;
     ji[7] = (j01 * j20 - j00 * j21) * id;
     ji[8] = (-j01 * j10 + j00 * j11) * id;
-    const double w = qw[q] * fabs(det);  // weight *= fabs(detjac)  (pzinterpolationspace.cpp:468)
+    const double w = wq * fabs(det);  // weight *= fabs(detjac)  (pzinterpolationspace.cpp:468)
     Wd[q] = w;
     const double sw = scale * w;
     int m = 0;
@@ -119,15 +124,25 @@ SF_HD void geometry(int q, const double *X, const double *dn, int ds, const doub
     for (int e = 0; e < 3; e++)
 #pragma unroll
         for (int f = e; f < 3; f++) {
-            Msm[m * 27 + q] = sw * (ji[3 * e] * ji[3 * f] + ji[3 * e + 1] * ji[3 * f + 1] + ji[3 * e + 2] * ji[3 * f + 2]);
+            Msm[m * MS + MT * (q / 3) + q % 3] = sw * (ji[3 * e] * ji[3 * f] + ji[3 * e + 1] * ji[3 * f + 1] + ji[3 * e + 2] * ji[3 * f + 2]);
             m++;
         }
 }
 
-// stage 1 of the pair (e,f): thread t = (p1, q2q3); F1v = the thread's F1[variant(0,e,f)][3]
+// stage 1 of the pair (e,f): thread t = (p1, q2q3); F1v = the thread's F1[variant(0,e,f)][3].  S1buf[GS * (t / 9) + t % 9]:
+// GS = 9 dense, GS = 10 the nine values of a p1 group start on a 16-byte boundary (stage 2 then reads them with 16-byte loads:
+// measured to cost 250 bytes of spills in the one-warp kernel - aligned register quads -, so GS = 9 is what the kernels use)
+template <int MS = 27, int MT = 3, int GS = 9>
 SF_HD void stage1(int t, int e, int f, const double *F1v, const double *Msm, double *S1buf) {
-    const double *Mq = Msm + msym(e, f) * 27 + 3 * (t % 9);
-    S1buf[t] = F1v[0] * Mq[0] + F1v[1] * Mq[1] + F1v[2] * Mq[2];
+    const double *Mq = Msm + msym(e, f) * MS + MT * (t % 9);
+    double m0, m1, m2;
+    if constexpr (MT == 4) {
+        const double2 m01 = *reinterpret_cast<const double2 *>(Mq);
+        m0 = m01.x; m1 = m01.y; m2 = Mq[2];
+    } else {
+        m0 = Mq[0]; m1 = Mq[1]; m2 = Mq[2];
+    }
+    S1buf[GS * (t / 9) + t % 9] = F1v[0] * m0 + F1v[1] * m1 + F1v[2] * m2;
 }
 
 }  // namespace sf
@@ -142,31 +157,28 @@ extern double h_sfF3[4 * 9 * 3];        // (CPU emulation, tools/sumfact_emu.cpp
 
 namespace sf {
 // stages 2 and 3 of the pair (e,f) for work item t = (p1, p2): F2v = the thread's F2[variant(1,e,f)][3]
+template <int GS = 9>
 SF_HD void stage23(int t, int e, int f, const double *F2v, const double *S1buf, double *acc) {
-    const double *s1 = S1buf + 9 * (t / 9);  // [q2 + 3 q3]
+    const double *s1 = S1buf + GS * (t / 9);  // [q2 + 3 q3]
     const int v3 = variant(2, e, f);
 #pragma unroll
     for (int q3 = 0; q3 < 3; q3++) {
-        const double s2 = F2v[0] * s1[3 * q3] + F2v[1] * s1[3 * q3 + 1] + F2v[2] * s1[3 * q3 + 2];
-#pragma unroll
-        for (int k = 0; k < 9; k++) acc[k] = fma(s2, SF_F3((v3 * 9 + k) * 3 + q3), acc[k]);
-    }
-}
-// barrier-free form of the three stages: the work item recomputes the nine S1[p1][q2q3] of its own p1 from M (27 broadcast
-// loads, 27 multiply-adds per (e,f) instead of 3) and needs no exchange with other threads: 63 DFMA per (e,f) instead of 39,
-// no shared S1 buffer, no __syncthreads inside the loop over (e,f)
-SF_HD void stages_private(int t, int e, int f, const double *F1v, const double *F2v, const double *Msm, double *acc) {
-    const double *M = Msm + msym(e, f) * 27;
-    const int v3 = variant(2, e, f);
-#pragma unroll
-    for (int q3 = 0; q3 < 3; q3++) {
-        double s2 = 0.0;
-#pragma unroll
-        for (int q2 = 0; q2 < 3; q2++) {
-            const double *Mq = M + 3 * (q2 + 3 * q3);
-            const double s1 = F1v[0] * Mq[0] + F1v[1] * Mq[1] + F1v[2] * Mq[2];
-            s2 = fma(F2v[q2], s1, s2);
+        double a, b, c;
+        if constexpr (GS == 10) {  // 16-byte loads where the alignment allows: (0,1) 2 | 3 (4,5) | (6,7) 8
+            if (q3 == 0) {
+                const double2 x = *reinterpret_cast<const double2 *>(s1);
+                a = x.x; b = x.y; c = s1[2];
+            } else if (q3 == 1) {
+                const double2 x = *reinterpret_cast<const double2 *>(s1 + 4);
+                a = s1[3]; b = x.x; c = x.y;
+            } else {
+                const double2 x = *reinterpret_cast<const double2 *>(s1 + 6);
+                a = x.x; b = x.y; c = s1[8];
+            }
+        } else {
+            a = s1[3 * q3]; b = s1[3 * q3 + 1]; c = s1[3 * q3 + 2];
         }
+        const double s2 = F2v[0] * a + F2v[1] * b + F2v[2] * c;
 #pragma unroll
         for (int k = 0; k < 9; k++) acc[k] = fma(s2, SF_F3((v3 * 9 + k) * 3 + q3), acc[k]);
     }
@@ -185,11 +197,11 @@ SF_HD bool entry_of(int t, int k, int &i, int &j) {
 
 #ifdef __CUDACC__
 
-// PRIVATE = 0: stage 1 shared through smem, one barrier per (e,f); PRIVATE = 1: barrier-free (stages_private)
+// The round-2 default until the one-warp-per-element kernel below replaced it (kept as variant 13: profiles refer to it).
 // PREFETCH = 1: the corner coordinates of the CTA's next element are loaded (and the node ids of the one after) while the current
 // element is computed, and the scatter positions are loaded before the factor stages instead of after them: the dependent global
 // loads (ids -> coordinates, ~2 DRAM latencies) and the position loads leave the critical path of every element
-template <int MINB, int PRIVATE = 0, int PREFETCH = 0>
+template <int MINB, int PREFETCH = 0>
 __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_poisson_kernel(const VolParams p) {
     __shared__ double Xs[24];
     __shared__ double Msm[6 * 27];
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
             }
         }
         __syncthreads();
-        if (t < 27) sf::geometry(t, Xs, Dn + t, 27, p.qw, p.coef[0], Msm, Wd);
+        if (t < 27) sf::geometry(t, Xs, Dn + t, 27, __ldg(p.qw + t), p.coef[0], Msm, Wd);
         __syncthreads();
         // ---- load vector: ef(i) += weight*fScale*phi(i)*force (TPZMatPoisson.cpp:39-40), threads 32..58 (the second warp)
         if (t >= 32 && t < 32 + 27) {
@@ -259,13 +271,9 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
 #pragma unroll
         for (int c = 0; c < 9; c++) {
             const int e = c / 3, f = c % 3;
-            if (PRIVATE) {
-                if (active) sf::stages_private(t, e, f, F1[sf::variant(0, e, f)], F2[sf::variant(1, e, f)], Msm, acc);
-            } else {
-                if (active) sf::stage1(t, e, f, F1[sf::variant(0, e, f)], Msm, S1[c & 1]);
-                __syncthreads();
-                if (active) sf::stage23(t, e, f, F2[sf::variant(1, e, f)], S1[c & 1], acc);
-            }
+            if (active) sf::stage1(t, e, f, F1[sf::variant(0, e, f)], Msm, S1[c & 1]);
+            __syncthreads();
+            if (active) sf::stage23(t, e, f, F2[sf::variant(1, e, f)], S1[c & 1], acc);
         }
         // ---- scatter-add: entry k = (i3, j3) of work item t
         if (!PREFETCH) {
@@ -282,16 +290,129 @@ __global__ void __launch_bounds__(sf::NTHREADS, MINB) assemble_sumfact_hex_p2_po
     }
 }
 
+// ---- one warp per element ---------------------------------------------------------------------------------------------
+// The same three stages with NO block-wide barrier: a warp owns an element and walks its 54 work items in two passes of 27
+// (pass ps: p1 = 3 ps + lane / 9, p2 = lane % 9, i.e. item 27 ps + lane; the nine S1 values an item needs are produced by
+// the nine lanes of its own p1 group, so __syncwarp orders stage 1 against stage 2).  Stage 1 runs for all nine (e,f) first
+// (S1[9][28] per warp), then stages 2 + 3: two __syncwarp per pass instead of nine __syncthreads per element, and the warps
+// of a CTA never wait for each other (the CTA only shares the read-only tables).  Scatter map: [el][ps][k][32 lanes].
+namespace sfw {
+constexpr int SLOTS = 2 * 9 * 32;
+}
+
+template <int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB) assemble_sumfact_hex_p2_poisson_warp_kernel(const VolParams p) {
+    __shared__ double Dn[24 * 27];       // dng_t [3][8][27]
+    __shared__ double Ft[sf::AUX_LEN];   // F1[4][6][3], F2[4][9][3]
+    __shared__ double Xs[WPC][24];
+    __shared__ double Msm[WPC][6 * 27];
+    __shared__ double Wd[WPC][28];
+    __shared__ double S1[WPC][9][28];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 24 * 27; i += WPC * 32) Dn[i] = __ldg(p.dng_t + i);
+    for (int i = threadIdx.x; i < sf::AUX_LEN; i += WPC * 32) Ft[i] = __ldg(p.aux2 + i);
+    __syncthreads();
+    const bool active = lane < 27;
+    const int l = active ? lane : 0;
+    const int g1 = l / 9, p2 = l % 9;
+    double F2[4][3];
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) F2[v][k] = Ft[sf::AUX_F2 + (v * 9 + p2) * 3 + k];
+    const double myqw = active ? __ldg(p.qw + l) : 0.0;
+    const int64_t nwarps = (int64_t)gridDim.x * WPC;
+    int64_t el = (int64_t)blockIdx.x * WPC + warp;
+    double cnext = 0.0;
+    int32_t node_next = 0;
+    if (lane < 24 && el < p.nel) {
+        cnext = p.xyz[(int64_t)p.elnodes[el * 8 + lane / 3] * 3 + lane % 3];
+        if (el + nwarps < p.nel) node_next = p.elnodes[(el + nwarps) * 8 + lane / 3];
+    }
+    for (; el < p.nel; el += nwarps) {
+        if (!p.rhs_only && lane < (sfw::SLOTS * 4 + 127) / 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(p.smap + (size_t)el * sfw::SLOTS) + lane * 128));
+        if (lane < 24) {
+            Xs[warp][lane] = cnext;
+            if (el + nwarps < p.nel) {
+                cnext = p.xyz[(int64_t)node_next * 3 + lane % 3];
+                if (el + 2 * nwarps < p.nel) node_next = p.elnodes[(el + 2 * nwarps) * 8 + lane / 3];
+            }
+        }
+        __syncwarp();
+        if (active) sf::geometry(lane, Xs[warp], Dn + lane, 27, myqw, p.coef[0], Msm[warp], Wd[warp]);
+        __syncwarp();
+        // ---- load vector: ef(i) += weight*fScale*phi(i)*force (TPZMatPoisson.cpp:39-40), lane <-> i
+        if (active) {
+            double f = 0.0;
+            for (int q = 0; q < 27; q++) {
+                const double a = Wd[warp][q] * __ldg(p.phi + (size_t)q * 27 + lane);
+                f += p.force ? a * p.force[el * 27 + q] : a;
+            }
+            f *= p.coef[0] * (p.force ? 1.0 : p.coef[1]);
+            scatter_rhs(p.rhs, p.dest[el * 27 + lane], f, p.atomic);
+        }
+        if (p.rhs_only) {
+            __syncwarp();
+            continue;
+        }
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++) {
+            const int32_t *sm = p.smap + (size_t)el * sfw::SLOTS + ps * 9 * 32 + lane;
+            int32_t pos[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) pos[k] = __ldcs(sm + k * 32);
+            {
+                double F1[4][3];
+                const int p1 = 3 * ps + g1;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) F1[v][k] = Ft[sf::AUX_F1 + (v * 6 + p1) * 3 + k];
+#pragma unroll
+                for (int c = 0; c < 9; c++)
+                    if (active) sf::stage1(l, c / 3, c % 3, F1[sf::variant(0, c / 3, c % 3)], Msm[warp], S1[warp][c]);
+            }
+            __syncwarp();
+            double acc[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) acc[k] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 9; c++)
+                if (active) sf::stage23<9>(l, c / 3, c % 3, F2[sf::variant(1, c / 3, c % 3)], S1[warp][c], acc);
+            scatter_many<9>(p.a, pos, acc, p.atomic);
+            if (p.smapT) {
+                const int32_t *smT = p.smapT + (size_t)el * sfw::SLOTS + ps * 9 * 32 + lane;
+#pragma unroll
+                for (int k = 0; k < 9; k++) pos[k] = __ldcs(smT + k * 32);
+                scatter_many<9>(p.a, pos, acc, p.atomic);
+            }
+            __syncwarp();  // S1 is rewritten by the next pass / Xs, Msm, Wd by the next element
+        }
+    }
+}
+
 // scatter map: entry (el, k = i3*3+j3, t = p1*9+p2) -> CSR position of ek(i, j), i = (i1,i2,i3), j = (j1,j2,j3), (i1,j1) the
 // unordered pair p1 (i1 <= j1), (i2,j2) = (p2/3, p2%3); -1 for idle threads and for the second copy of an entry (i1 == j1, i > j)
+// WARP = 1: the layout of the one-warp-per-element kernel, slot (ps * 9 + k) * 32 + lane <-> work item 27 ps + lane (lane < 27)
+template <int WARP>
 __global__ void build_sumfact_smap_kernel(int64_t nel, const int32_t *__restrict__ dest, const int64_t *__restrict__ ia,
                                           const int32_t *__restrict__ ja, int symmetric, int32_t *__restrict__ smap,
                                           int32_t *__restrict__ smapT, int *__restrict__ missing) {
+    static_assert(sf::SLOTS == sfw::SLOTS, "both layouts have 576 slots per element");
     const int64_t total = nel * sf::SLOTS;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t el = idx / sf::SLOTS;
         const int slot = (int)(idx - el * sf::SLOTS);
-        const int t = slot % sf::NTHREADS, k = slot / sf::NTHREADS;
+        int t, k;
+        if (WARP) {
+            const int lane = slot % 32, pk = slot / 32;
+            k = pk % 9;
+            t = lane < 27 ? 27 * (pk / 9) + lane : sf::NITEM;  // (NITEM: idle lane)
+        } else {
+            t = slot % sf::NTHREADS;
+            k = slot / sf::NTHREADS;
+        }
         int32_t pos = -1, posT = -1;
         int i, j;
         if (sf::entry_of(t, k, i, j)) {

@@ -41,6 +41,7 @@ def main():
     hex2 = gridmesh.grid_mesh(3, 2, 1, bc_matids=bc, perturb=0.1)
     run("sumfact hex p2 poisson, atomic", hex2, pois, cg=True)
     run("sumfact hex p2 poisson, coloured", hex2, pois, scatter="colored")
+    run("sumfact hex p2 poisson, one warp per element (variant 20), full storage", hex2, pois, symmetric=False, variant=20)
     run("one-warp DMMA hex p2 poisson (variant 16), full storage", hex2, pois, symmetric=False, variant=16)
     run("one-warp DMMA hex p1 poisson", gridmesh.grid_mesh(4, 1, 1, bc_matids=bc, perturb=0.1), pois)
     run("team DMMA hex p2 elasticity", gridmesh.grid_mesh(3, 2, 3, bc_matids=bc, perturb=0.1), elas)

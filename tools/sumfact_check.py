@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""One-shot check of the sum-factorisation kernel (option variant = 8 / 9, neopz_b200/csrc/sumfact_hex.cuh) on a GPU:
+"""One-shot check of the sum-factorisation kernels (option variant, neopz_b200/csrc/sumfact_hex.cuh) on a GPU
+(usage: sumfact_check.py [grid] [variant ...]):
 parity against the oracle on small perturbed meshes (both storages, coloured scatter, load vector only, forcing table),
 then the CUDA-event time of the volume group next to the default DMMA kernel.  JSON lines on stdout."""
 import json
@@ -26,7 +27,8 @@ def relF(x, ref):
 
 def main():
     n_time = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    for variant in (8, 9):
+    variants = [int(v) for v in sys.argv[2:]] or [8, 13]
+    for variant in variants:
         worst = 0.0
         for n, sym, scatter, forcing in ((5, True, "atomic", None), (4, False, "atomic", None), (5, True, "colored", None),
                                           (7, True, "atomic", lambda x: 1.0 + x[:, 0] * x[:, 1] - 0.5 * x[:, 2])):
@@ -42,7 +44,7 @@ def main():
         print(json.dumps({"variant": variant, "parity_worst_relF": worst, "ok": worst <= 1e-12}), flush=True)
     mesh = gridmesh.grid_mesh(n_time, 2, 1, perturb=0.1)
     nvol = len(mesh.blocks[0].elnodes)
-    for variant in (0, 8, 9):
+    for variant in [0, 16] + variants:
         mm = mats()
         s = sm.TPZStructMatrixB200(mesh, mm, symmetric=True, variant=variant)
         s.Create(on_device=True, download=False)

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #define SF_HD inline
+struct double2 { double x, y; };
 #include "../neopz_b200/csrc/sumfact_hex.cuh"
 
 double h_sfF3[4 * 9 * 3];
@@ -12,7 +13,7 @@ double h_sfF3[4 * 9 * 3];
 // X[8][3], dng[27][3][8], qw[27], x1d[3] (the line rule), scale = fScale.  K[27][27] (both triangles filled), ef_w[27] = w|detJ|.
 // Returns the number of distinct upper-triangle entries written (378 when the work-item map is complete and free of duplicates),
 // negative when an entry was written twice.
-// mode 0: stage 1 through the shared buffer (barriers = loop boundaries); mode 1: the barrier-free form (stages_private)
+// mode: unused (kept for the binding)
 extern "C" int sf_emulate_mode(const double *X, const double *dng, const double *qw, const double *x1d, double scale, double *K, double *Wd, int mode);
 extern "C" int sf_emulate(const double *X, const double *dng, const double *qw, const double *x1d, double scale, double *K, double *Wd) {
     return sf_emulate_mode(X, dng, qw, x1d, scale, K, Wd, 0);
@@ -21,17 +22,11 @@ extern "C" int sf_emulate_mode(const double *X, const double *dng, const double 
     double aux[sf::AUX_LEN];
     sf::build_tables(x1d, aux, h_sfF3);
     double Msm[6 * 27], S1[2][sf::NITEM + 2];
-    for (int t = 0; t < 27; t++) sf::geometry(t, X, dng + (size_t)t * 24, 1, qw, scale, Msm, Wd);
+    for (int t = 0; t < 27; t++) sf::geometry(t, X, dng + (size_t)t * 24, 1, qw[t], scale, Msm, Wd);
     double acc[sf::NTHREADS][9];
     std::memset(acc, 0, sizeof(acc));
     for (int c = 0; c < 9; c++) {
         const int e = c / 3, f = c % 3;
-        if (mode == 1) {
-            for (int t = 0; t < sf::NITEM; t++)
-                sf::stages_private(t, e, f, aux + sf::AUX_F1 + (sf::variant(0, e, f) * 6 + t / 9) * 3,
-                                   aux + sf::AUX_F2 + (sf::variant(1, e, f) * 9 + t % 9) * 3, Msm, acc[t]);
-            continue;
-        }
         for (int t = 0; t < sf::NITEM; t++) sf::stage1(t, e, f, aux + sf::AUX_F1 + (sf::variant(0, e, f) * 6 + t / 9) * 3, Msm, S1[c & 1]);
         for (int t = 0; t < sf::NITEM; t++) sf::stage23(t, e, f, aux + sf::AUX_F2 + (sf::variant(1, e, f) * 9 + t % 9) * 3, S1[c & 1], acc[t]);
     }
