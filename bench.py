@@ -91,6 +91,8 @@ def kernel_name(a):
             return "assemble_gram_mma_kernel (one warp per element, mma.sync.m8n8k4.f64)"
         if a.topo == "hex" and a.phys == "poisson" and a.p >= 3:
             return "assemble_gram_team_kernel (warp team per element, mma.sync.m8n8k4.f64)"
+        if a.phys == "elasticity" and a.topo == "hex" and a.p == 2 and a.variant in (0, 31):
+            return "assemble_gram_warp_elast_kernel (a pair of warps per element, whole panel in shared memory, mma.sync.m8n8k4.f64)"
         if a.phys == "elasticity" and a.topo == "hex":
             return "assemble_gram_team_kernel (warp team per element, mma.sync.m8n8k4.f64)"
     return "assemble_volume_kernel (register-tile DFMA)"

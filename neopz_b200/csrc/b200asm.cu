@@ -1202,6 +1202,26 @@ template <class C>
 MmaEntry make_team_entry(int topology, int porder, int variant = 0) {
     return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, C::NTHREADS, C::EPC, &C::smem_bytes, &launch_team<C>, &launch_team_smap<C>, &prepare_team<C>};
 }
+// one warp (or a pair of warps) per element on the team kernel's panel / tiles / scatter map (gram_mma_team.cuh,
+// assemble_gram_warp_elast_kernel): WPC warps per CTA, WPE warps per element, GI tile groups in flight per warp
+template <class C, int WPC, int WPE, int GI>
+size_t warp_elast_smem(int nq) { return WarpElastCfg<C>::smem_bytes(nq, WPC / WPE); }
+template <class C, int WPC, int WPE, int GI>
+cudaError_t launch_warp_elast(const VolParams &p, int grid, size_t smem, cudaStream_t s) {
+    assemble_gram_warp_elast_kernel<C, WPC, WPE, GI><<<grid, WPC * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class C, int WPC, int WPE, int GI>
+cudaError_t prepare_warp_elast(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_gram_warp_elast_kernel<C, WPC, WPE, GI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, assemble_gram_warp_elast_kernel<C, WPC, WPE, GI>, WPC * 32, smem);
+}
+template <class C, int WPC, int WPE, int GI>
+MmaEntry make_warp_elast_entry(int topology, int porder, int variant) {
+    return MmaEntry{variant, topology, porder, C::NS, C::SLOTS, WPC * 32, WPC / WPE, &warp_elast_smem<C, WPC, WPE, GI>, &launch_warp_elast<C, WPC, WPE, GI>,
+                    &launch_team_smap<C>, &prepare_warp_elast<C, WPC, WPE, GI>};
+}
 // closed-form kernels for straight-sided tetrahedra (affine_simplex.cuh):  N  NS  warps/CTA  min CTAs/SM
 using TetP1PoissonAff = AffCfg<4, 1, 8, 3>;
 using TetP1ElastAff = AffCfg<4, 3, 8, 3>;
@@ -1300,18 +1320,22 @@ MmaEntry make_sumfact_warp_entry(int variant) {
 // test or a profile refers to them: 7 = the DMMA Gram kernels for tetrahedra that the closed-form kernels replaced; for hexahedra
 // p = 2 Poisson 20 = the default again (sum factorisation, one warp per element), 13 = sum factorisation with one CTA of 64
 // threads per element (the default of the first round-2 passes), 16 = the one-warp DMMA Gram kernel that was the default in round
-// 1 (it still runs every such group whose rule is not the 3 x 3 x 3 tensor rule).  Measured on a 96^3 perturbed grid
+// 1 (it still runs every such group whose rule is not the 3 x 3 x 3 tensor rule); for hexahedra p = 2 elasticity 31 = the default
+// again (a pair of warps per element), 30 = one warp per element, 34 = the team of ten warps per element that was the default
+// before (64^3 perturbed grid, profiles/r02_elast_warp_variants.jsonl: 36.6 / 32.2 / 29.3 M elements/s).  Measured on a 96^3 perturbed grid
 // (profiles/r02_sumfact_warp_variants.jsonl): 20: 286 M elements/s, 13: 219, 16: 159; the other alternatives lost and were removed.
 const MmaEntry kMma[] = {make_aff_entry<TetP1PoissonAff>(1), make_aff_entry<TetP1ElastAff>(1),
                          make_aff_entry<TetP2PoissonAff>(2), make_aff_entry<TetP2ElastAff>(2),
                          make_sumfact_warp_entry<4, 6>(0),
                          make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2), make_mma_entry<TetP2PoissonMma>(B200ASM_TET, 2, 7),
-                         make_team_entry<HexP2ElastTeamV3>(B200ASM_HEX, 2), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
+                         make_warp_elast_entry<HexP2ElastTeamV3, 8, 2, 1>(B200ASM_HEX, 2, 0), make_team_entry<HexP1ElastTeam>(B200ASM_HEX, 1),
                          make_team_entry<HexP3PoissonTeam>(B200ASM_HEX, 3), make_team_entry<HexP4PoissonTeam>(B200ASM_HEX, 4),
                          make_mma_entry<HexP1PoissonMma>(B200ASM_HEX, 1, 0),
                          make_mma_entry<HexP2PoissonMma>(B200ASM_HEX, 2, 16),
                          make_team_entry<TetP2ElastTeamV2>(B200ASM_TET, 2, 7),
-                         make_sumfact_entry<8, 1>(13), make_sumfact_warp_entry<4, 6>(20)};
+                         make_sumfact_entry<8, 1>(13), make_sumfact_warp_entry<4, 6>(20),
+                         make_warp_elast_entry<HexP2ElastTeamV3, 4, 1, 2>(B200ASM_HEX, 2, 30), make_warp_elast_entry<HexP2ElastTeamV3, 8, 2, 1>(B200ASM_HEX, 2, 31),
+                         make_team_entry<HexP2ElastTeamV3>(B200ASM_HEX, 2, 34)};
 // (tetrahedra p=2 elasticity, DMMA team kernel: 4 teams of 3 warps per CTA, 24 warps/SM: 208 M el/s vs 135 M el/s for the
 //  register-tile kernel on a 64^3x5 mesh, although padding 10 shape functions to 16 wastes 60 % of every DMMA tile)
 constexpr int kNumMma = sizeof(kMma) / sizeof(kMma[0]);

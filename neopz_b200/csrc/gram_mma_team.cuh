@@ -436,6 +436,218 @@ __global__ void __launch_bounds__(C::NTHREADS, C::MINB) assemble_gram_team_kerne
     }
 }
 
+// ---- TPZElasticity3D with ONE WARP PER ELEMENT ------------------------------------------------------------------------
+// Same panel, tiles, epilogue and scatter map as the team kernel with GPW == 1 (C = its TeamCfg), but no warp waits for
+// another one: a warp computes the geometry of its element, builds the WHOLE panel (all nq rows, its own shared-memory
+// buffer) and then walks the NGROUPS tile groups one after the other - nine accumulator tiles, nq/4 DMMA steps, the nine
+// formulas, the reductions - so the only synchronisation is __syncwarp.  Why: the team kernel spends its time in the named
+// barriers that separate its phases (7.3 stall cycles per issued instruction, profiles/r01_ncu_full_final2_team_hexp2elast.csv)
+// while the scatter (3321 reductions per element, ~1.3 LSU cycles each) is what bounds the configuration; here the
+// reductions of one warp overlap the DMMAs of the others.  Shared memory per warp: 24 + 11 QS + KR LD doubles (25 KB for
+// nq = 27), i.e. 8 warps per SM.
+template <class C>
+struct WarpElastCfg {
+    __host__ __device__ static int krows(int nq) { return ((nq + 3) / 4) * 4; }
+    __host__ __device__ static int warp_doubles(int nq) { return 24 + 11 * C::qstride(nq) + krows(nq) * C::LD; }
+    static size_t smem_bytes(int nq, int teams) { return sizeof(double) * (size_t)teams * warp_doubles(nq); }
+};
+
+// WPE = 1: one warp per element, two tile groups at a time (GI = 2).  WPE = 2: a PAIR of warps shares the geometry and the
+// panel of an element (same shared memory per element, twice the warps per SM: 16) and splits the tile groups round-robin;
+// the pair meets at a 64-thread named barrier four times per element (coordinates, geometry, panel, end of the element).
+template <class C, int WPC, int WPE, int GI>
+__global__ void __launch_bounds__(WPC * 32, (8 * WPE / WPC > 0 ? 8 * WPE / WPC : 1)) assemble_gram_warp_elast_kernel(const VolParams p) {
+    static_assert(C::NS == 3 && C::SB == 0 && C::GPW == 1 && C::NN == 8, "hexahedra, elasticity, one tile group per team warp");
+    static_assert(WPC % WPE == 0 && C::NGROUPS % (WPE * GI) == 0, "whole teams per CTA, whole batches of groups per warp");
+    constexpr int N = C::N, LD = C::LD, NP = C::NP, NPAD = C::NPAD, M = C::M, JS = C::JS, TT = 32 * WPE, EPC = WPC / WPE;
+    extern __shared__ double smem[];
+    const int team = threadIdx.x / TT, tt = threadIdx.x - team * TT;
+    const int lane = tt & 31, w = tt >> 5;
+    const int nq = p.nq;
+    const int QS = C::qstride(nq), KR = WarpElastCfg<C>::krows(nq);
+    double *Xs = smem + (size_t)team * WarpElastCfg<C>::warp_doubles(nq);
+    double *JI = Xs + 24;
+    double *Pn = JI + JS * QS;
+    for (int i = tt; i < KR * LD; i += TT) Pn[i] = 0.0;  // padding columns and rows stay zero
+    team_sync<TT>(team);
+    const int g = lane >> 2, tg = lane & 3;
+    const bool pointwise = p.force != nullptr || p.coef[6] != 0.0 || p.coef[7] != 0.0 || p.coef[8] != 0.0;
+    const int64_t nteams = (int64_t)gridDim.x * EPC;
+    int64_t el = (int64_t)blockIdx.x * EPC + team;
+    // corner coordinates one element ahead, node ids two ahead (the dependent loads leave the critical path)
+    double cnext = 0.0;
+    int32_t node_next = 0;
+    if (tt < 24 && el < p.nel) {
+        cnext = p.xyz[(int64_t)p.elnodes[el * 8 + tt / 3] * 3 + tt % 3];
+        if (el + nteams < p.nel) node_next = p.elnodes[(el + nteams) * 8 + tt / 3];
+    }
+    for (; el < p.nel; el += nteams) {
+        if (!p.rhs_only) {
+            const char *base = (const char *)(p.smap + (size_t)el * C::SLOTS);
+            for (int off = tt * 128; off < C::SLOTS * 4; off += TT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+        if (tt < 24) {
+            Xs[tt] = cnext;
+            if (el + nteams < p.nel) {
+                cnext = p.xyz[(int64_t)node_next * 3 + tt % 3];
+                if (el + 2 * nteams < p.nel) node_next = p.elnodes[(el + 2 * nteams) * 8 + tt / 3];
+            }
+        }
+        team_sync<TT>(team);
+        // ---- geometry at the integration points (thread <-> point) ------------------------------------------------------
+        for (int q = tt; q < nq; q += TT) {
+            const double *dn = p.dng_t + q;
+            double j00 = 0, j01 = 0, j02 = 0, j10 = 0, j11 = 0, j12 = 0, j20 = 0, j21 = 0, j22 = 0;
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const double d0 = __ldg(dn + (size_t)a * nq), d1 = __ldg(dn + (size_t)(8 + a) * nq), d2 = __ldg(dn + (size_t)(16 + a) * nq);
+                const double x = Xs[a * 3], y = Xs[a * 3 + 1], z = Xs[a * 3 + 2];
+                j00 += x * d0; j01 += x * d1; j02 += x * d2;
+                j10 += y * d0; j11 += y * d1; j12 += y * d2;
+                j20 += z * d0; j21 += z * d1; j22 += z * d2;
+            }
+            double det = 0.0;
+            det -= j02 * j11 * j20;
+            det += j01 * j12 * j20;
+            det += j02 * j10 * j21;
+            det -= j00 * j12 * j21;
+            det -= j01 * j10 * j22;
+            det += j00 * j11 * j22;
+            if (fabs(det) < 1.e-12) det = 1.e-12;
+            const double id = 1.0 / det;
+            const double wq = __ldg(p.qw + q) * fabs(det);
+            const double sid = sqrt(wq) * id;
+            double *o = JI + q;
+            o[0 * QS] = (-j12 * j21 + j11 * j22) * sid;
+            o[1 * QS] = (j02 * j21 - j01 * j22) * sid;
+            o[2 * QS] = (-j02 * j11 + j01 * j12) * sid;
+            o[3 * QS] = (j12 * j20 - j10 * j22) * sid;
+            o[4 * QS] = (-j02 * j20 + j00 * j22) * sid;
+            o[5 * QS] = (j02 * j10 - j00 * j12) * sid;
+            o[6 * QS] = (-j11 * j20 + j10 * j21) * sid;
+            o[7 * QS] = (j01 * j20 - j00 * j21) * sid;
+            o[8 * QS] = (-j01 * j10 + j00 * j11) * sid;
+            o[9 * QS] = wq;
+            o[10 * QS] = sqrt(wq);
+        }
+        team_sync<TT>(team);
+        // ---- panel P[q][d * NPAD + i] = sqrt(w|detJ|) dphix(d, i) at point q, items (point, shape function) over the threads
+#pragma unroll 2
+        for (int it = tt; it < nq * N; it += TT) {
+            const int q = it / N, i = it - q * N;
+            const double *dp = p.dphi_pad + (size_t)q * 3 * NP + i;
+            const double d0 = __ldg(dp), d1 = __ldg(dp + NP), d2 = __ldg(dp + 2 * NP);
+            const double *ji = JI + q;
+            double *row = Pn + q * LD + i;
+            row[0] = ji[0 * QS] * d0 + ji[3 * QS] * d1 + ji[6 * QS] * d2;
+            row[NPAD] = ji[1 * QS] * d0 + ji[4 * QS] * d1 + ji[7 * QS] * d2;
+            row[2 * NPAD] = ji[2 * QS] * d0 + ji[5 * QS] * d1 + ji[8 * QS] * d2;
+        }
+        team_sync<TT>(team);
+        // ---- load vector: ef(3j+k) = sum_q w (f_k phi_j - sigma0_k dphix(k,j))   (TPZElasticity3D.cpp:278), the last warp
+        if (w == WPE - 1) {
+            if (!pointwise) {
+                // constant force: t_j = sum_q w phi_j(q) once per shape function (lane <-> j, three partial sums), then lane <-> dof
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+                if (lane < N) {
+                    int q = 0;
+                    for (; q + 2 < nq; q += 3) {
+                        t0 += JI[9 * QS + q] * __ldg(p.phi_pad + (size_t)q * NP + lane);
+                        t1 += JI[9 * QS + q + 1] * __ldg(p.phi_pad + (size_t)(q + 1) * NP + lane);
+                        t2 += JI[9 * QS + q + 2] * __ldg(p.phi_pad + (size_t)(q + 2) * NP + lane);
+                    }
+                    for (; q < nq; q++) t0 += JI[9 * QS + q] * __ldg(p.phi_pad + (size_t)q * NP + lane);
+                }
+                const double tj = (t0 + t1) + t2;
+                for (int m0 = 0; m0 < M; m0 += 32) {
+                    const int m = m0 + lane, j = m < M ? m / 3 : 0;
+                    const double t = __shfl_sync(0xffffffffu, tj, j);
+                    if (m < M) scatter_rhs(p.rhs, p.dest[el * M + m], p.coef[3 + (m - 3 * j)] * t, p.atomic);
+                }
+            } else {
+                for (int m = lane; m < M; m += 32) {
+                    const int j = m / 3, kd = m - 3 * j;
+                    double f = 0.0;
+                    for (int q = 0; q < nq; q++) {
+                        const double fq = p.force ? p.force[(el * nq + q) * 3 + kd] : p.coef[3 + kd];
+                        f += JI[9 * QS + q] * fq * __ldg(p.phi_pad + (size_t)q * NP + j);
+                        f -= p.coef[6 + kd] * JI[10 * QS + q] * Pn[q * LD + kd * NPAD + j];  // w dphix = sqrt(w) * panel entry
+                    }
+                    scatter_rhs(p.rhs, p.dest[el * M + m], f, p.atomic);
+                }
+            }
+        }
+        if (!p.rhs_only) {
+            // ---- the tile groups (node-block pairs ib <= jb) of this warp, GI at a time: 9 GI independent accumulator tiles
+            // keep the tensor pipe busy across the dependent k-steps, and the scatter positions are loaded before the DMMA
+            // loop, so their latency is hidden behind it
+            const double C1 = p.coef[0], C2 = p.coef[1], C3 = p.coef[2];
+#pragma unroll 1
+            for (int gidx = w * GI; gidx < C::NGROUPS; gidx += WPE * GI) {
+                int ib[GI], jb[GI];
+                int32_t pos[GI][18];
+#pragma unroll
+                for (int h = 0; h < GI; h++) {
+                    ib[h] = C::group_ib(gidx + h);
+                    jb[h] = C::group_jb(gidx + h);
+                    const int32_t *sm = p.smap + (size_t)el * C::SLOTS + (size_t)(gidx + h) * 9 * 64 + lane;
+#pragma unroll
+                    for (int k = 0; k < 18; k++) pos[h][k] = __ldcs(sm + k * 32);
+                }
+                double acc[GI][9][2];
+#pragma unroll
+                for (int h = 0; h < GI; h++)
+#pragma unroll
+                    for (int t = 0; t < 9; t++) acc[h][t][0] = acc[h][t][1] = 0.0;
+                const double *col = Pn + tg * LD + g;
+#pragma unroll 1
+                for (int s = 0; s < KR / 4; s++) {
+                    const double *r = col + 4 * s * LD;
+#pragma unroll
+                    for (int h = 0; h < GI; h++) {
+                        double fi[3], fj[3];
+#pragma unroll
+                        for (int v = 0; v < 3; v++) fi[v] = r[v * NPAD + 8 * ib[h]];
+#pragma unroll
+                        for (int u = 0; u < 3; u++) fj[u] = r[u * NPAD + 8 * jb[h]];
+#pragma unroll
+                        for (int v = 0; v < 3; v++)
+#pragma unroll
+                            for (int u = 0; u < 3; u++) dmma_m8n8k4(acc[h][v * 3 + u][0], acc[h][v * 3 + u][1], fi[v], fj[u]);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < GI; h++) {
+                    double val[18];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        double S[3][3];
+#pragma unroll
+                        for (int v = 0; v < 3; v++)
+#pragma unroll
+                            for (int u = 0; u < 3; u++) S[v][u] = acc[h][v * 3 + u][e];
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++)
+                                val[(a * 3 + b) * 2 + e] = a == b ? (S[(a + 1) % 3][(a + 1) % 3] + S[(a + 2) % 3][(a + 2) % 3]) * C1 + S[a][a] * C3
+                                                                  : S[b][a] * C1 - S[a][b] * C2;
+                    }
+                    scatter_many<18>(p.a, pos[h], val, p.atomic);
+                    if (p.smapT) {
+                        const int32_t *smT = p.smapT + (size_t)el * C::SLOTS + (size_t)(gidx + h) * 9 * 64 + lane;
+                        int32_t posT[18];
+#pragma unroll
+                        for (int k = 0; k < 18; k++) posT[k] = __ldcs(smT + k * 32);
+                        scatter_many<18>(p.a, posT, val, p.atomic);
+                    }
+                }
+            }
+        }
+        team_sync<TT>(team);  // Xs, JI and the panel are rewritten for the next element
+    }
+}
+
 // scatter map of the team kernel: slot ((((W*GPW+gl)*TPG + t)*2 + e)*32 + lane) of element el
 template <class C>
 __global__ void build_team_smap_kernel(int64_t nel, const int32_t *__restrict__ dest, const int64_t *__restrict__ ia,

@@ -44,8 +44,11 @@ def main():
     run("sumfact hex p2 poisson, one warp per element (variant 20), full storage", hex2, pois, symmetric=False, variant=20)
     run("one-warp DMMA hex p2 poisson (variant 16), full storage", hex2, pois, symmetric=False, variant=16)
     run("one-warp DMMA hex p1 poisson", gridmesh.grid_mesh(4, 1, 1, bc_matids=bc, perturb=0.1), pois)
-    run("team DMMA hex p2 elasticity", gridmesh.grid_mesh(3, 2, 3, bc_matids=bc, perturb=0.1), elas)
-    run("team DMMA hex p2 elasticity, coloured, full", gridmesh.grid_mesh(2, 2, 3, bc_matids=bc, perturb=0.1), elas, symmetric=False, scatter="colored")
+    run("warp-pair DMMA hex p2 elasticity", gridmesh.grid_mesh(3, 2, 3, bc_matids=bc, perturb=0.1), elas)
+    run("warp-pair DMMA hex p2 elasticity, coloured, full", gridmesh.grid_mesh(2, 2, 3, bc_matids=bc, perturb=0.1), elas, symmetric=False, scatter="colored")
+    run("one-warp DMMA hex p2 elasticity (variant 30)", gridmesh.grid_mesh(2, 2, 3, bc_matids=bc, perturb=0.1), elas, variant=30)
+    run("team DMMA hex p2 elasticity (variant 34)", gridmesh.grid_mesh(2, 2, 3, bc_matids=bc, perturb=0.1), elas, variant=34)
+    run("team DMMA hex p1 elasticity", gridmesh.grid_mesh(3, 1, 3, bc_matids=bc, perturb=0.1), elas)
     run("team DMMA hex p3 poisson", gridmesh.grid_mesh(2, 3, 1, bc_matids=bc, perturb=0.1), pois)
     run("team DMMA hex p4 poisson", gridmesh.grid_mesh(2, 4, 1, bc_matids=bc, perturb=0.1), pois)
     tet2 = gridmesh.grid_mesh(3, 2, 3, tetrahedra=True, bc_matids=bc, perturb=0.1)
