@@ -69,6 +69,8 @@ def parse():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--gather", type=int, default=0, help="1: closed-form groups are assembled row by row in a fixed order (option gather of the C ABI; slower, deterministic)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the timing of TPZLinearAnalysis::Assemble() inside the unmodified reference")
+    ap.add_argument("--dropin-n", type=int, default=48, help="grid of the drop-in timing mesh")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -374,6 +376,7 @@ class Case:
                   "hbm_GBps_algorithmic": ach_gb, "hbm_frac_algorithmic": ach_gb / hbm_peak, "hbm_peak_GBps": hbm_peak,
                   "executed_flops_per_element": x_el,
                   "fp64_pipe_utilisation_executed": (x_el * self.nvol / (self.kernel_ms * 1e-3) / 1e12 / fp64_peak) if x_el else None,
+                  "binding_resource": binding_resource(kname),
                   "kernel": kname, "kernel_ms": self.kernel_ms, "kernel_share_of_step": self.kernel_ms / self.ms_per_step,
                   "peaks": {"fp64_tflops": fp64_peak, "hbm_gbs": hbm_peak}})
         return r
@@ -387,6 +390,23 @@ class Case:
         import gc
         gc.collect()
         self.torch.cuda.empty_cache()
+
+
+def binding_resource(kernel):
+    """What the committed ncu captures show the kernel to be bound by (profiles/): none of the kernels is
+    limited by the FP64 pipe or by HBM bandwidth any more, so `frac` (quoted on the reference's arithmetic, as north_star asks)
+    can exceed 1 where the kernel executes fewer flops than the reference."""
+    if "sumfact" in kernel and "warp" in kernel:
+        return ("LSU wavefronts 81 % of peak (profiles/r02_ncu_sumfact_warp_raw.csv): shared-memory loads of the factor stages 54 %, "
+                "378 red.global.add.f64 lanes per element at ~1.3 LSU cycles each (488 of the ~1000 cycles per element and SM)")
+    if "warp_elast" in kernel:
+        return ("3321 red.global.add.f64 lanes per element at ~1.3 LSU cycles each = 4284 of 7940 cycles per element and SM; tensor pipe 29 % busy "
+                "(630 DMMA per element), 16 warps per SM (profiles/r02_ncu_elast_warp_raw.csv: the one-warp form)")
+    if "closed-form" in kernel:
+        return "red.global.add.f64 issue: ~1.3 LSU cycles per lane, 465 (tetrahedra p2 elasticity) / 378 / 3321 (hexahedra p2) lanes per element"
+    if "team" in kernel:
+        return "DMMA pipe (51 % in executed flops for p4) and the named barriers between the team's phases (profiles/r01_ncu_full_final_team_hexp4poisson.csv)"
+    return None
 
 
 def executed_flops(topo, p, phys, kernel):
@@ -412,6 +432,39 @@ def executed_flops(topo, p, phys, kernel):
     if phys == "poisson":
         return 2.0 * 3 * q * pairs + geom
     return 2.0 * 9 * q * pairs + 9 * 3 * pairs + geom
+
+
+def dropin_timing(a, local_rank):
+    """an.Assemble() of the UNMODIFIED reference (tests/_bin/dropin_test: TPZLinearAnalysis + TPZSSpStructMatrix) on one
+    TPZCompMesh, first with its TPZStructMatrixOR strategy on the host cores, then with TPZStructMatrixB200: the wall-clock
+    times a NeoPZ user sees (mesh flattening, uploads, kernels, download into the TPZSYsmpMatrix included), and the
+    comparison of the two results.  None when the binary was not built (needs /root/reference at build time)."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_bin", "dropin_test")
+    if not os.path.exists(exe) or a.topo == "prism":
+        return None
+    threads = min(16, os.cpu_count() or 1)
+    phys = 1 if a.phys == "elasticity" else 0
+    n = a.dropin_n if a.phys == "poisson" and a.p <= 2 else max(8, a.dropin_n // 3)
+    env = dict(os.environ, B200_SKIP_SERIAL="1", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+    # n p phys tet symmetric solve cpu_threads device_create equation_filter pin_host
+    out = subprocess.run([exe, str(n), str(a.p), str(phys), "1" if a.topo == "tet" else "0", "1", "0", str(threads), "1", "0", "1"],
+                         capture_output=True, text=True, timeout=900, env=env)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if not lines:
+        return {"error": (out.stdout[-300:] + out.stderr[-300:]).strip()}
+    r = json.loads(lines[-1])
+    nvol = r.get("vol_elements")
+    d = {"mesh": workload_name(a, n), "api": "TPZLinearAnalysis::Assemble() of the unmodified reference, strategy TPZStructMatrixOR against TPZStructMatrixB200 "
+         "(device-side Create(), page-locked TPZSYsmpMatrix values)", "cpu_threads": r.get("cpu_threads"),
+         "cpu_threaded_assemble_s": r.get("cpu_threaded_assemble_s"), "gpu_first_assemble_s": r.get("gpu_first_assemble_s"),
+         "gpu_second_assemble_s": r.get("gpu_second_assemble_s"), "ia_identical": r.get("ia_identical"), "ja_identical": r.get("ja_identical"),
+         "relF_A": r.get("relF_A"), "relF_rhs": r.get("relF_rhs"), "ok": r.get("ok")}
+    if nvol and r.get("gpu_second_assemble_s") and r.get("cpu_threaded_assemble_s"):
+        d["volume_elements"] = nvol
+        d["cpu_elements_per_s"] = nvol / r["cpu_threaded_assemble_s"]
+        d["gpu_elements_per_s_second_assemble"] = nvol / r["gpu_second_assemble_s"]
+    return d
 
 
 def parity_against_reference(a, dumpdir, n, local_rank):
@@ -572,6 +625,29 @@ def main():
             e2e["rank_cpu_affinity"] = f"{numa_cpus} CPUs closest to the GPU (NVML), pinned buffers first-touched there"
         if serial_s is not None:
             e2e["ms_per_step_without_overlap"] = serial_s * 1e3
+        # the same call with the matrix LEFT on the device (a_host = NULL: what TPZB200CGSolver / b200asm_cg_solve consume): the
+        # step then returns the load vector only, and the PCIe copy of the CSR values - the bound of `e2e` - disappears
+        try:
+            if not (sharded and a.exchange == "nccl"):
+                def resident_step():
+                    strmat.ctx.set_nodes(x_np)
+                    strmat.ctx.assemble(None, r_np)
+                resident_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(ksteps):
+                    resident_step()
+                barrier()
+                res_s = (time.perf_counter() - t0) / ksteps
+                if world > 1:
+                    t = torch.tensor([res_s], device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    res_s = float(t.item())
+                e2e["matrix_resident"] = {"value": nvol * world / res_s, "unit": "elements/s", "ms_per_step": res_s * 1e3,
+                                          "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": int(r_np.nbytes),
+                                          "note": "b200asm_set_nodes + b200asm_assemble(NULL, rhs_host): the CSR values stay on the device for the device CG"}
+        except Exception as ex:
+            e2e["matrix_resident"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
         del a_host, r_host, x_host, a_np, r_np
 
     # ---- the same mesh WITHOUT the node perturbation (the literal CreateGeoMeshOnGrid grid of BASELINE.json): every cell is
@@ -683,6 +759,13 @@ def main():
         finally:
             shutil.rmtree(dump, ignore_errors=True)
 
+    dropin = None
+    if world == 1 and not a.no_dropin and not a.no_cpu_baseline:
+        try:
+            dropin = dropin_timing(a, local_rank)
+        except Exception as ex:
+            dropin = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+
     line = {"metric": "assembled volume elements/s (Assemble on a created pattern)", "value": value, "unit": "elements/s",
             "dof_per_s": neq * world / (ms_per_step * 1e-3),
             "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_per_step,
@@ -699,6 +782,8 @@ def main():
         line["device_cg"] = cg
     if uniform:
         line["uniform_grid"] = uniform
+    if dropin:
+        line["dropin"] = dropin
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -108,8 +108,13 @@ int b200asm_set_stream(b200asm_ctx *ctx, void *cuda_stream);
  * are then revisited while they are still in L2),
  * "overlap" (default 1: b200asm_assemble with a host matrix copies the finished rows of A back while later element
  * chunks are still being assembled; "overlap_min_elements" (before add_group) and "overlap_min_bytes" tune the chunking),
- * "variant" (before add_group: 0 default kernels; 7 DMMA kernels on tetrahedra p <= 2, 8 / 11 / 13 sum-factorisation forms and
- * 16 the one-warp DMMA kernel on hexahedra p = 2 Poisson, 21 register-tile kernel on tetrahedra p = 3, 4),
+ * "variant" (before add_group: 0 default kernels; 7 DMMA kernels on tetrahedra p <= 2; hexahedra p = 2 Poisson: 20 sum factorisation
+ * with one warp per element (= the default), 13 with one CTA per element, 16 the one-warp DMMA kernel; hexahedra p = 2
+ * elasticity: 31 a pair of warps per element (= the default), 30 one warp, 34 the team of ten warps; 21 register-tile kernel on
+ * tetrahedra p = 3, 4),
+ * "gather" (default 0; 1: on one GPU in atomic mode the closed-form groups are assembled row by row by the warp that owns the
+ * node - every CSR row written once, fixed summation order, no atomics on those rows; slower than the scatter kernels),
+ * "drop_tiny" (default 0; 1: element entries below 1e-12 are skipped like TPZSYsmpMatrix::AddKel does, Matrix/pzsysmp.cpp:381),
  * "staging_lo" / "staging_hi" (before add_group, row-sharded assembly: see b200asm_exchange_*), "exchange_timeout_ms" */
 int b200asm_set_option(b200asm_ctx *ctx, const char *name, int64_t value);
 

@@ -1,27 +1,31 @@
 // gather_rows.cuh — owner-computes ("gather") assembly for the groups whose element matrices have a closed form
-// (straight-sided tetrahedra, parallelepiped hexahedra of order <= 2: affine_simplex.cuh / affine_hex.cuh).
+// (straight-sided tetrahedra, parallelepiped hexahedra of order <= 2: affine_simplex.cuh / affine_hex.cuh).  OPT-IN (option
+// "gather" = 1): the deterministic alternative to the scatter kernels, not the fast path.
 //
-// Why.  The scatter formulation of TPZSYsmpMatrix::AddKel (Matrix/pzsysmp.cpp:370-411) adds every element entry into the CSR
-// values with a reduction.  On the device that costs, per assembly, a memset of A, a read-modify-write of every line of A in
-// L2 (the line has to come from HBM before the first reduction lands) and one L2 reduction per element entry: 2-2.5x the
-// compulsory HBM bytes (profiles/traffic.json) and, for the closed-form kernels whose arithmetic is negligible, LSU / L2
-// reduction throughput as the bound (0.2-0.3 of the HBM roofline in round 1).  Here every CSR row is produced by exactly
-// one warp: the rows of a node (connect) are accumulated in shared memory from the elements that contain the node - each
-// contribution recomputed from the element's Jacobian factors in closed form - and written to A ONCE, coalesced, with plain
-// stores.  No memset, no atomics, no read of A; the summation order is fixed (elements in ascending order), so the result is
-// bit-reproducible like the reference's ordered assembly (StrMatrix/pzstrmatrixor.cpp:714-717).
+// Idea.  The scatter formulation of TPZSYsmpMatrix::AddKel (Matrix/pzsysmp.cpp:370-411) adds every element entry into the CSR
+// values with a reduction: a memset of A, a read-modify-write of every line of A in L2 and one L2 reduction per element entry
+// (~1.3 LSU cycles per lane: what bounds the closed-form kernels).  Here every CSR row is produced by
+// exactly one sub-warp: the rows of a node (connect) are accumulated in shared memory from the elements that contain the node -
+// each contribution recomputed from the element's Jacobian factors in closed form - and written to A ONCE, coalesced, with
+// plain stores.  No memset, no atomics, no read of A; the summation order is fixed (elements in ascending order), so the rows
+// that no other group adds to are bit-reproducible like the reference's ordered assembly (StrMatrix/pzstrmatrixor.cpp:714-717).
+//
+// Measured (one B200, profiles/r02_gather_vs_scatter.md): 2-3x SLOWER than the scatter kernels (hexahedra p2 Poisson 128^3 uniform:
+// 146 against 407 M elements/s; hexahedra p2 elasticity 81^3: 25.9 against 45.0; tetrahedra p2 elasticity 113^3: 126 against 513).
+// A (node, element) pair costs six / nine table loads, the staged factors and a shared-memory read-modify-write for at most N
+// useful lanes (half of them idle under symmetric storage), and the pairs of a node are a serial chain: the gather trades the
+// reductions for about as many shared-memory wavefronts and loses the parallelism of one warp per element.
 //
 // Data (built on the device when the scatter maps would be built):
-//   grow[ng]            first equation ("key") of every node block that has elements in the group, ascending
-//   gptr[neq + 1]       range of glist per key (empty for equations that do not start a node block)
-//   glist[nel * N]      (element << 5) | local node, the elements of a node in ascending order
+//   rec[ng]             NodeRec {first equation ("key"), first pair, number of elements} of every node block, ascending keys
+//   glist[nel * N]      (element << 5) | local node: the pairs of a node are consecutive, elements in ascending order
 //   relpos[pair][a][jn] uint16: position, within row key + a, of the first stored column of local node jn of that element
 //                       (0xFFFF: block not stored - symmetric storage keeps the columns >= row only)
 //   rowflag[neq]        0 row without a gather group (zeroed, other groups add), 1 exclusive (stored, never zeroed),
 //                       2 shared with another group (zeroed, the others add first, this kernel adds on top)
 //   fac[nel][FS]        per assembly: Poisson s|detJ| (Jinv Jinv^T) (6), Elasticity3D Jinv (9) and |detJ|
 // Requirements checked at setup (otherwise the group keeps its scatter kernel): the NS equations of a node are consecutive
-// and none is filtered; rows shorter than 65535 entries; at most 2^27 elements.
+// and none is filtered; rows shorter than 65535 entries; at most 2^27 elements and MAXDEG elements per node; one GPU, atomic mode.
 #pragma once
 #include <cstdint>
 

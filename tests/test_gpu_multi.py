@@ -95,9 +95,10 @@ def test_sharded_cg_against_one_gpu_and_scipy(ndev, n, p, phys, tet, symmetric, 
     xd = spla.spsolve(sp.csc_matrix(A), rhs1)
     assert relF(x, xd) <= 1e-10 and relF(x1, xd) <= 1e-10
     assert relF(x, x1) <= 1e-10
-    # warm start from the solution: nothing left to do; a second right-hand side through the same matrix
-    x2, it2, res2 = multi.SolveCG(max_iter=20000, tol=1e-12, x0=x)
-    assert it2 <= 2 and res2 <= 1e-12
+    # warm start from the solution: nothing left to do (the TRUE residual of a solution whose recurrence residual reached
+    # 1e-14 sits around cond(A) * eps, so the restart is asked for 1e-10); a second right-hand side through the same matrix
+    x2, it2, res2 = multi.SolveCG(max_iter=20000, tol=1e-10, x0=x)
+    assert it2 <= 2 and res2 <= 1e-10
     f2 = np.linspace(0.5, 1.5, mesh.neq)
     x3, _it3, _res3 = multi.SolveCG(max_iter=20000, tol=1e-14, f=f2)
     assert relF(x3, spla.spsolve(sp.csc_matrix(A), f2)) <= 1e-10

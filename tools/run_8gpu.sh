@@ -1,9 +1,9 @@
-run() { tag=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 "$@" > gpurun_out/r01_final3_n8_$tag.json 2> gpurun_out/r01_final3_n8_$tag.err; python -c "
-import json,sys
-try:
-    d=json.loads(open('gpurun_out/r01_final3_n8_$tag.json').read().strip().splitlines()[-1]); print('$tag', d['config']['workload'][:70], '| el/s %.4g dof/s %.4g ms %.3f frac %.3f'%(d['value'],d['dof_per_s'],d['ms_per_step'],d['roofline']['frac']), 'dof/gpu', d['config']['dof_per_gpu'])
-except Exception as e: print('$tag FAILED', e); print(open('gpurun_out/r01_final3_n8_$tag.err').read()[-800:])
-"; }
-run c5 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --phys elasticity --grid 81
-run c3 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --phys elasticity --topo tet --grid 80
-run c5uniform --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --phys elasticity --grid 81 --perturb 0
+#!/bin/bash
+# eight GPUs: the multi-GPU tests (2 and 4 devices behind the C ABI / the strategy, NCCL ranks), then the 8-rank bench (weak scaling, all configs)
+#   gpurun --gpus 8 --timeout 1500 -- 'bash tools/run_8gpu.sh'
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/r02_topo_8gpu.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_distributed.py tests/test_gpu_zzzzz_round2.py -q -p no:cacheprovider -k "sharded or several_gpus or multi" 2>&1 | tail -8 | tee gpurun_out/r02_tests_8gpu.log
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err
+tail -2 gpurun_out/r02_bench_8gpu.err | cut -c 1-300
+head -c 600 gpurun_out/r02_bench_8gpu.json
