@@ -363,7 +363,7 @@ class Case:
             if closed_form:
                 r["note"] = "closed-form element matrices: the FP64 roofline of the reference's arithmetic (%.2f of it) does not bound this kernel" % (ach_tf / fp64_peak)
         traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
+        try:  # DRAM bytes per assembly of the dominant kernel from the committed ncu launch list of this exact workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{a.topo},{a.p},{a.phys},{a.n},{a.scatter}")
             if tr and self.world == 1 and a.engine == 1:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]

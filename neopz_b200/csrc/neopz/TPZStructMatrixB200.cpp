@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -228,6 +229,22 @@ inline void HashWord(uint64_t &h, uint64_t v) {
     h = (h * 0x100000001B3ull) ^ (v ^ (v >> 31));
 }
 
+// host threads of the per-Assemble host work (TPZStructMatrixB200::SetHostThreads), set at the entry points of the strategy
+thread_local int t_host_threads = 1;
+
+// body(first, last) over contiguous ranges of [0, n), one range per host thread (small n: the calling thread alone)
+template <class F>
+void ParallelFor(int64_t n, int64_t grain, F body) {
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(t_host_threads, n / std::max<int64_t>(grain, 1)));
+    if (nthreads == 1) {
+        body((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back([=]() { body(n * t / nthreads, n * (t + 1) / nthreads); });
+    for (std::thread &th : pool) th.join();
+}
+
 // What the flattened arrays depend on besides node coordinates and material constants (those are refreshed at every
 // Assemble): the element list, the material object and id of every element, the ShouldCompute outcome, per connect its block
 // position, block size and order, the geometric corner nodes, and the equation filter.  Connect renumbering (Permute), p
@@ -240,27 +257,44 @@ uint64_t MeshSignature(TPZStructMatrix *strmat) {
     HashWord(h, (uint64_t)cmesh->NEquations());
     const TPZEquationFilter &filter = strmat->EquationFilter();
     HashWord(h, filter.IsActive() ? (uint64_t)filter.NActiveEquations() + 1 : 0);
-    for (int64_t iel = 0; iel < nel; iel++) {
-        TPZCompEl *cel = cmesh->Element(iel);
-        if (!cel) { HashWord(h, 1); continue; }
-        TPZMaterial *mat = cel->Material();
-        if (!mat) { HashWord(h, 2); continue; }
-        if (!strmat->ShouldCompute(mat->Id())) { HashWord(h, 3); continue; }
-        HashWord(h, (uint64_t)(uintptr_t)mat);
-        HashWord(h, (uint64_t)(int64_t)mat->Id());
-        const int ncon = cel->NConnects();
-        for (int i = 0; i < ncon; i++) {
-            TPZConnect &con = cel->Connect(i);
-            const int64_t seq = con.SequenceNumber();
-            HashWord(h, (uint64_t)cmesh->Block().Position(seq) * 64u + (uint64_t)con.Order());
-            HashWord(h, (uint64_t)cmesh->Block().Size(seq));
+    // read-only walk over the elements: contiguous element ranges are hashed by separate threads (the walk is the largest
+    // host cost of a repeated Assemble() on a cached mesh), the range hashes are folded in element order
+    auto range_hash = [&](int64_t e0, int64_t e1) {
+        uint64_t hr = 0x452821E638D01377ull;
+        for (int64_t iel = e0; iel < e1; iel++) {
+            TPZCompEl *cel = cmesh->Element(iel);
+            if (!cel) { HashWord(hr, 1); continue; }
+            TPZMaterial *mat = cel->Material();
+            if (!mat) { HashWord(hr, 2); continue; }
+            if (!strmat->ShouldCompute(mat->Id())) { HashWord(hr, 3); continue; }
+            HashWord(hr, (uint64_t)(uintptr_t)mat);
+            HashWord(hr, (uint64_t)(int64_t)mat->Id());
+            const int ncon = cel->NConnects();
+            for (int i = 0; i < ncon; i++) {
+                TPZConnect &con = cel->Connect(i);
+                const int64_t seq = con.SequenceNumber();
+                HashWord(hr, (uint64_t)cmesh->Block().Position(seq) * 64u + (uint64_t)con.Order());
+                HashWord(hr, (uint64_t)cmesh->Block().Size(seq));
+            }
+            TPZGeoEl *gel = cel->Reference();
+            if (gel) {
+                const int nc = gel->NCornerNodes();
+                for (int i = 0; i < nc; i++) HashWord(hr, (uint64_t)gel->NodeIndex(i));
+            }
         }
-        TPZGeoEl *gel = cel->Reference();
-        if (gel) {
-            const int nc = gel->NCornerNodes();
-            for (int i = 0; i < nc; i++) HashWord(h, (uint64_t)gel->NodeIndex(i));
-        }
+        return hr;
+    };
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(t_host_threads, nel / 4096));
+    std::vector<uint64_t> part(nthreads, 0);
+    if (nthreads == 1) {
+        part[0] = range_hash(0, nel);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++)
+            pool.emplace_back([&, t]() { part[t] = range_hash(nel * t / nthreads, nel * (t + 1) / nthreads); });
+        for (std::thread &th : pool) th.join();
     }
+    for (int t = 0; t < nthreads; t++) HashWord(h, part[t]);
     return h;
 }
 
@@ -269,7 +303,7 @@ uint64_t PatternHash(int64_t neq, const int64_t *ia, const int64_t *ja) {
     HashWord(h, (uint64_t)neq);
     for (int64_t i = 0; i <= neq; i++) HashWord(h, (uint64_t)ia[i]);
     const int64_t nnz = ia[neq];
-    const int64_t stride = std::max<int64_t>(1, nnz / (1 << 20));  // the row pointers pin the shape; the columns are sampled
+    const int64_t stride = std::max<int64_t>(1, nnz / (1 << 16));  // the row pointers pin the shape; the columns are sampled (65 k probes)
     for (int64_t k = 0; k < nnz; k += stride) HashWord(h, (uint64_t)ja[k]);
     return h;
 }
@@ -482,8 +516,9 @@ void FillForce(HostGroup &g, int lc = 0) {
         const int fdim = g.meta.topology == B200ASM_LINE ? 1 : 2;
         const int nq = g.meta.nqp;
         g.force.assign((size_t)g.meta.nel * nq * ns, 0.0);
+        ParallelFor(g.meta.nel, 512, [&, fdim, nq, ns, type, lc](int64_t e_first, int64_t e_last) {
         TPZManVector<REAL, 3> qsi(fdim), x(3);
-        for (int64_t e = 0; e < g.meta.nel; e++) {
+        for (int64_t e = e_first; e < e_last; e++) {
             TPZGeoEl *gel = g.elements[e]->Reference();
             for (int q = 0; q < nq; q++) {
                 for (int d = 0; d < fdim; d++) qsi[d] = g.qpts[(size_t)q * fdim + d];
@@ -514,6 +549,7 @@ void FillForce(HostGroup &g, int lc = 0) {
                 }
             }
         }
+        });
         g.has_forcing = true;
         g.meta.force = g.force.data();
         return;
@@ -527,8 +563,9 @@ void FillForce(HostGroup &g, int lc = 0) {
         if (!((p2 && p2->HasForcingFunction()) || (e2 && e2->HasForcingFunction()))) return;
         const int nq = g.meta.nqp;
         g.force.assign((size_t)g.meta.nel * nq * ns, 0.0);
+        ParallelFor(g.meta.nel, 512, [&, nq, ns, lc](int64_t e_first, int64_t e_last) {
         TPZManVector<REAL, 3> qsi(2), x(3);
-        for (int64_t e = 0; e < g.meta.nel; e++) {
+        for (int64_t e = e_first; e < e_last; e++) {
             TPZGeoEl *gel = g.elements[e]->Reference();
             for (int q = 0; q < nq; q++) {
                 for (int d = 0; d < 2; d++) qsi[d] = g.qpts[(size_t)q * 2 + d];
@@ -539,6 +576,7 @@ void FillForce(HostGroup &g, int lc = 0) {
                 else for (int k = 0; k < ns; k++) g.force[((size_t)e * nq + q) * ns + k] = f[k];
             }
         }
+        });
         g.has_forcing = true;
         g.meta.force = g.force.data();
         return;
@@ -549,8 +587,11 @@ void FillForce(HostGroup &g, int lc = 0) {
     if (!hasf) return;
     const int nq = g.meta.nqp;
     g.force.assign((size_t)g.meta.nel * nq * ns, 0.0);
+    // (the reference calls the function from every assembly thread at once, Material/Poisson/TPZMatPoisson.cpp:24-27 under
+    //  StrMatrix/pzstrmatrixor.cpp:476-513; so does this table, range by range)
+    ParallelFor(g.meta.nel, 256, [&, nq, ns, lc](int64_t e_first, int64_t e_last) {
     TPZManVector<REAL, 3> qsi(3), x(3);
-    for (int64_t e = 0; e < g.meta.nel; e++) {
+    for (int64_t e = e_first; e < e_last; e++) {
         TPZGeoEl *gel = g.elements[e]->Reference();
         for (int q = 0; q < nq; q++) {
             for (int d = 0; d < 3; d++) qsi[d] = g.qpts[(size_t)q * 3 + d];
@@ -567,6 +608,7 @@ void FillForce(HostGroup &g, int lc = 0) {
             for (int k = 0; k < ns; k++) g.force[((size_t)e * nq + q) * ns + k] = f[k];
         }
     }
+    });
     g.has_forcing = true;
     g.meta.force = g.force.data();
 }
@@ -776,6 +818,7 @@ void PrepareMesh(TPZB200AssemblyCache &c, TPZStructMatrix *strmat, bool check_me
         }
         gi++;
     }
+    c.flatten_ms = ms_since(t0);  // (cached mesh: signature walk + refresh of coordinates, constants and tables)
 }
 
 // load case lc >= 1: the groups whose data depend on the load case get the coefficients / tables of that case
@@ -800,7 +843,8 @@ TPZStructMatrixB200<TVar>::TPZStructMatrixB200() : fCache(std::make_shared<TPZB2
 template <class TVar>
 TPZStructMatrixB200<TVar>::TPZStructMatrixB200(const TPZStructMatrixB200 &copy)
     : TPZStrMatParInterface(copy), fDevice(copy.fDevice), fDevices(copy.fDevices), fPinHost(copy.fPinHost), fAccumulate(copy.fAccumulate),
-      fDropTiny(copy.fDropTiny), fStaticForcing(copy.fStaticForcing), fCheckMesh(copy.fCheckMesh), fCache(std::make_shared<TPZB200AssemblyCache>()) {}
+      fDropTiny(copy.fDropTiny), fStaticForcing(copy.fStaticForcing), fCheckMesh(copy.fCheckMesh), fHostThreads(copy.fHostThreads),
+      fCache(std::make_shared<TPZB200AssemblyCache>()) {}
 
 template <class TVar>
 TPZStructMatrixB200<TVar> &TPZStructMatrixB200<TVar>::operator=(const TPZStructMatrixB200 &copy) {
@@ -812,6 +856,7 @@ TPZStructMatrixB200<TVar> &TPZStructMatrixB200<TVar>::operator=(const TPZStructM
     fDropTiny = copy.fDropTiny;
     fStaticForcing = copy.fStaticForcing;
     fCheckMesh = copy.fCheckMesh;
+    fHostThreads = copy.fHostThreads;
     fCache = std::make_shared<TPZB200AssemblyCache>();
     return *this;
 }
@@ -854,6 +899,7 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
     if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
     if (!sym && !full) Fatal("the stiffness matrix must be TPZSYsmpMatrix<STATE> or TPZFYsmpMatrix<STATE>");
     TPZB200AssemblyCache &c = *fCache;
+    t_host_threads = fHostThreads > 0 ? fHostThreads : std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
     EnsureEngine(c, WantedDevices(fDevice, fDevices, this->fNumThreads), fDropTiny);
     PrepareMesh(c, strmat, fCheckMesh, fStaticForcing);
     if (guiInterface && guiInterface->AmIKilled()) return;
@@ -896,8 +942,8 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &stiffness, TPZBaseMatrix
         c.symmetric = symmetric;
         c.nnz = nnz;
         c.pattern_hash = phash;
-        c.pattern_ms = ms_since(t0);
     }
+    c.pattern_ms = ms_since(t0);  // (pattern hash; + upload when the pattern changed)
     if (guiInterface && guiInterface->AmIKilled()) return;
     // assemble; the reference ADDS into rhs (TPZFMatrix::AddFel), the matrix arrives zeroed
     t0 = clk::now();
@@ -959,6 +1005,7 @@ void TPZStructMatrixB200<TVar>::Assemble(TPZBaseMatrix &rhs, TPZAutoPointer<TPZG
     auto *rhsmat = dynamic_cast<TPZFMatrix<STATE> *>(&rhs);
     if (!rhsmat) Fatal("rhs is not a TPZFMatrix<STATE>");
     TPZB200AssemblyCache &c = *fCache;
+    t_host_threads = fHostThreads > 0 ? fHostThreads : std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
     EnsureEngine(c, WantedDevices(fDevice, fDevices, this->fNumThreads), fDropTiny);
     PrepareMesh(c, strmat, fCheckMesh, fStaticForcing);
     if (guiInterface && guiInterface->AmIKilled()) return;
@@ -1046,6 +1093,7 @@ void TPZStructMatrixB200<TVar>::CreatePatternOnDevice(bool symmetric, TPZStack<i
         Fatal("Create() on the device does not support an active equation filter: use TPZSSpStructMatrix<STATE, TPZStructMatrixB200<STATE>>");
     TPZCompMesh *cmesh = strmat->Mesh();
     TPZB200AssemblyCache &c = *fCache;
+    t_host_threads = fHostThreads > 0 ? fHostThreads : std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
     EnsureEngine(c, WantedDevices(fDevice, fDevices, this->fNumThreads), fDropTiny);
     b200asm_ctx *pctx = c.AnyContext();  // (several GPUs: the first one builds the pattern, Assemble() then shards it)
     auto t0 = clk::now();

@@ -98,6 +98,11 @@ public:
     void SetDropTinyEntries(bool drop) { fDropTiny = drop; }
     //! Forcing functions / boundary functions do not change between assemblies: tabulate them once per flatten only.
     void SetForcingIsStatic(bool is_static) { fStaticForcing = is_static; }
+    //! Host threads for the per-Assemble host work (tabulating forcing / boundary functions at the integration points, the mesh
+    //! signature walk).  Default 0 = min(16, hardware threads).  The callbacks are then called concurrently, exactly as
+    //! TPZStructMatrixOR does with SetNumThreads(n > 0) (StrMatrix/pzstrmatrixor.cpp:476-513); SetHostThreads(1) for callbacks
+    //! that are not thread-safe.
+    void SetHostThreads(int n) { fHostThreads = n; }
     //! Revalidate the cached flattened mesh at every Assemble (default true).
     void SetCheckMesh(bool check) { fCheckMesh = check; }
     //! Forget the cached flattened mesh (the next Assemble flattens again).
@@ -130,6 +135,7 @@ protected:
     bool fDropTiny{false};
     bool fStaticForcing{false};
     bool fCheckMesh{true};
+    int fHostThreads{0};
     std::shared_ptr<TPZB200AssemblyCache> fCache;
 };
 

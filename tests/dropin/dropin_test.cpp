@@ -174,6 +174,7 @@ struct Csr {
     std::vector<double> residual_rhs;  // TPZLinearAnalysis::AssembleResidual() -> Assemble(rhs)
     std::vector<double> sol_device;    // B200 only: CG on the device-resident matrix (TPZB200CGSolver through an.Solve())
     int64_t device_cg_iters = 0;
+    double prepare_ms = 0, pattern_ms = 0, device_ms = 0;  // B200 only: TPZStructMatrixB200::LastTimings of the second Assemble()
 };
 
 static int g_pin = 0;     // 1: TPZStructMatrixB200::SetPinHostMatrix(true) — the matrix values are page-locked for the download
@@ -218,6 +219,7 @@ static void Run(TPZCompMesh *cmesh, int nthreads, bool symmetric, bool solve, Cs
     auto t2 = clk::now();
     t_first = secs(t0, t1);
     t_second = secs(t1, t2);
+    if (auto *b = dynamic_cast<TPZStructMatrixB200<STATE> *>(an.StructMatrix().operator->())) b->LastTimings(out.prepare_ms, out.pattern_ms, out.device_ms);
     auto mtx = an.MatrixSolver<STATE>().Matrix();
     const int64_t neq = cmesh->NEquations();
     if (symmetric) {
@@ -397,6 +399,8 @@ int main(int argc, char **argv) {
               << ", \"device_cg_iterations\": " << gpu.device_cg_iters << ", \"relF_residual_rhs\": " << errRes
               << ", \"ref_residual_rhs_vs_rhs\": " << errResVsRhs << ", \"relF_A_ref_threads_vs_serial\": " << errMT
               << ", \"cpu_serial_assemble_s\": " << t2 << ", \"cpu_threads\": " << threads << ", \"cpu_threaded_assemble_s\": " << tm2
-              << ", \"gpu_first_assemble_s\": " << g1 << ", \"gpu_second_assemble_s\": " << g2 << ", \"ok\": " << ok << "}" << std::endl;
+              << ", \"gpu_first_assemble_s\": " << g1 << ", \"gpu_second_assemble_s\": " << g2
+              << ", \"gpu_second_prepare_ms\": " << gpu.prepare_ms << ", \"gpu_second_pattern_ms\": " << gpu.pattern_ms
+              << ", \"gpu_second_assemble_call_ms\": " << gpu.device_ms << ", \"ok\": " << ok << "}" << std::endl;
     return ok ? 0 : 1;
 }
