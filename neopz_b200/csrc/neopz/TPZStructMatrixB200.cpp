@@ -284,17 +284,14 @@ uint64_t MeshSignature(TPZStructMatrix *strmat) {
         }
         return hr;
     };
-    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(t_host_threads, nel / 4096));
-    std::vector<uint64_t> part(nthreads, 0);
-    if (nthreads == 1) {
-        part[0] = range_hash(0, nel);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthreads; t++)
-            pool.emplace_back([&, t]() { part[t] = range_hash(nel * t / nthreads, nel * (t + 1) / nthreads); });
-        for (std::thread &th : pool) th.join();
-    }
-    for (int t = 0; t < nthreads; t++) HashWord(h, part[t]);
+    // fixed blocks of 4096 elements, whatever the thread count: the signature does not depend on SetHostThreads
+    constexpr int64_t kBlock = 4096;
+    const int64_t nblocks = (nel + kBlock - 1) / kBlock;
+    std::vector<uint64_t> part((size_t)nblocks, 0);
+    ParallelFor(nblocks, 1, [&](int64_t b0, int64_t b1) {
+        for (int64_t b = b0; b < b1; b++) part[b] = range_hash(b * kBlock, std::min(nel, (b + 1) * kBlock));
+    });
+    for (int64_t b = 0; b < nblocks; b++) HashWord(h, part[b]);
     return h;
 }
 
